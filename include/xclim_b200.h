@@ -1,0 +1,229 @@
+/*
+ * xclim_b200 -- C ABI of the B200-native (sm_100a) per-grid-cell time-series kernels.
+ *
+ * This is the drop-in boundary for ONE hot path of Ouranosinc/xclim (reference @ a8cbec8c):
+ * the per-cell reductions behind `xclim.indices.run_length`, `xclim.indices.generic`,
+ * `xclim.core.calendar.percentile_doy` (+ bootstrap) and sdba empirical quantile mapping.
+ * The reference is pure Python (no FFI); a maintainer binds these symbols with `ctypes`
+ * (INTEGRATION.md shows the stub).  Each entry point cites the reference interface it
+ * replaces as `file:line` relative to /root/reference/src/xclim.
+ *
+ * Conventions
+ *   - All array arguments are DEVICE pointers unless the name ends in `_host`.
+ *   - Gridded inputs are `(time, cell)` row-major float32: element (t, c) at x[t*ldx + c],
+ *     where `cell` is the flattened `(lat, lon)` index (the reference's (time, lat, lon)
+ *     C-contiguous layout has ldx == C == lat*lon).
+ *   - `period_offsets` is an int32 device array of P+1 boundaries produced by
+ *     `resample(time=freq)`: period p covers time steps [off[p], off[p+1]).
+ *   - `doy_index` is an int16 device array of length T holding `time.dt.dayofyear` (1-based).
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream) on the CURRENT device; the library allocates nothing, keeps no global
+ *     mutable state and is re-entrant (one host thread or process per GPU).
+ *   - Return value: 0 on success, negative XC_ERR_* otherwise; `xc_last_error()` returns a
+ *     thread-local message.  Nothing throws across the boundary.
+ */
+#ifndef XCLIM_B200_H
+#define XCLIM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XC_VERSION 100
+
+/* status codes */
+#define XC_OK 0
+#define XC_ERR_INVALID (-1)  /* bad argument (ValueError in the reference) */
+#define XC_ERR_UNSUPPORTED (-2) /* NotImplementedError in the reference */
+#define XC_ERR_CUDA (-3)     /* CUDA runtime error, see xc_last_error() */
+
+/* comparison operators: indices/generic.py:255-326 (`binary_ops`, `get_op`, `compare`) */
+#define XC_OP_GT 0
+#define XC_OP_LT 1
+#define XC_OP_GE 2
+#define XC_OP_LE 3
+#define XC_OP_EQ 4
+#define XC_OP_NE 5
+
+/* run-length reducers over the run lengths >= window attributed to a period:
+ * indices/run_length.py:275-335 (`rle_statistics`, `get_rl_stat`), 381-488
+ * (`windowed_run_events` == COUNT, `windowed_run_count` == SUM). */
+#define XC_RL_MAX 0
+#define XC_RL_MIN 1
+#define XC_RL_SUM 2
+#define XC_RL_COUNT 3
+#define XC_RL_MEAN 4
+#define XC_RL_STD 5
+
+/* resample reductions: indices/generic.py:83-125 (`select_resample_op`) */
+#define XC_STAT_SUM 0
+#define XC_STAT_MEAN 1
+#define XC_STAT_MIN 2
+#define XC_STAT_MAX 3
+#define XC_STAT_STD 4
+#define XC_STAT_VAR 5
+#define XC_STAT_COUNT 6
+
+/* element transforms fused into xc_period_reduce_f32 */
+#define XC_TF_NONE 0
+#define XC_TF_EXCESS 1  /* (x - thr).clip(0) for >,>= ; (thr - x).clip(0) for <,<= : generic.py:1514-1552 */
+#define XC_TF_WHERE 2   /* x where (x op thr) else NaN: generic.py:1278-1320 (`thresholded_statistics`) */
+
+int32_t xc_version(void);
+const char* xc_last_error(void);
+
+/* Device properties the host side sizes its launches with (no reference counterpart). */
+int32_t xc_device_sm_count(int32_t* out_sm_count);
+
+/* ---------------------------------------------------------------------------------------------
+ * a1+a2  threshold_count  -- indices/generic.py:329-361 (+ domain_count 364-392 via two calls)
+ *   out[p, c] = #{ t in period p : x[t, c] op thr }   (NaN compares False)
+ *   thr is a double; cmp_f64 == 0 reproduces numpy>=2 `float32_array op python_float`
+ *   (comparison in float32 against float(thr)); cmp_f64 == 1 reproduces a float64 threshold.
+ *   valid_count (optional, may be NULL): number of non-NaN steps per period (the fused
+ *   MissingAny input, core/missing.py:296-298, 318-322).
+ * ------------------------------------------------------------------------------------------- */
+int32_t xc_period_count_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                            const int32_t* period_offsets, int32_t P,
+                            int32_t op, double thr, int32_t cmp_f64,
+                            int32_t* out_count, int32_t* valid_count, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a6-a11  run-length statistics of the condition (x op thr)
+ *   replaces  generic._spell_length_statistics (window==1)   indices/generic.py:543-585
+ *             run_length.resample_and_rl                      indices/run_length.py:87-132
+ *             run_length.rle / rle_statistics / longest_run   indices/run_length.py:223-378
+ *             run_length.windowed_run_count / _events         indices/run_length.py:381-488
+ *   resample_before_rl != 0: runs are cut at period edges (run_length.py:122-129);
+ *   resample_before_rl == 0: runs are found on the whole series and attributed, with their full
+ *   length, to the period holding their first element (run_length.py:318, 329-334).
+ *   out[p, c] (float32) = reducer over run lengths >= window, 0 when there is none.
+ * ------------------------------------------------------------------------------------------- */
+int32_t xc_period_runstat_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                              const int32_t* period_offsets, int32_t P,
+                              int32_t op, double thr, int32_t cmp_f64,
+                              int32_t reducer, int32_t window, int32_t resample_before_rl,
+                              float* out, int32_t* valid_count, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a3  per-period reductions -- indices/generic.py:83-125 (`select_resample_op`), 1255-1320
+ *   (`statistics`, `thresholded_statistics`), 1514-1552 (`cumulative_difference`); _simple.py:113
+ *   NaN steps are skipped (xarray skipna); an all-NaN period gives NaN (0 for SUM, COUNT).
+ *   Accumulation is in float64, results are rounded once to float32.
+ * ------------------------------------------------------------------------------------------- */
+int32_t xc_period_reduce_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                             const int32_t* period_offsets, int32_t P,
+                             int32_t stat, int32_t transform, int32_t op, double thr,
+                             float* out, int32_t* valid_count, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a4  rolling window then per-period reduction -- indices/generic.py:128-174
+ *   (`select_rolling_resample_op`), _simple.py:485-525 (`max_n_day_precipitation_amount`).
+ *   window_stat in {SUM, MEAN, MIN, MAX}; right-aligned (center == 0) or centred window,
+ *   min_periods == window (NaN for incomplete windows or windows holding a NaN); then `stat`.
+ * ------------------------------------------------------------------------------------------- */
+int32_t xc_rolling_period_reduce_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                     const int32_t* period_offsets, int32_t P,
+                                     int32_t window, int32_t window_stat, int32_t center,
+                                     int32_t stat, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a14+a15  percentile_doy -- core/calendar.py:395-494 with the quantile of
+ *   core/utils.py:279-557 (`calc_perc` -> `_nan_quantile`, Hyndman-Fan alpha/beta).
+ *   x: (T, C) float32 base-period series; doy_index/year_index: int16 (T) day-of-year (1-based)
+ *   and 0-based year ordinal of every step; n_doy = max day-of-year present; n_years = number of
+ *   distinct years.  out: (n_per, n_doy, C) float64.  The 366 -> 1..366 re-interpolation of
+ *   core/calendar.py:484-485 is xc_doy_interp_f64 (separate, tiny).
+ *   workspace: device scratch of xc_percentile_doy_workspace_bytes() bytes (may be 0 / NULL).
+ * ------------------------------------------------------------------------------------------- */
+int64_t xc_percentile_doy_workspace_bytes(int64_t T, int64_t C, int32_t n_doy, int32_t n_years,
+                                          int32_t window, int32_t n_per);
+int32_t xc_percentile_doy_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                              const int16_t* doy_index, const int16_t* year_index,
+                              int32_t n_doy, int32_t n_years, int32_t window,
+                              const double* percentiles_host, int32_t n_per,
+                              double alpha, double beta,
+                              double* out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* core/calendar.py:690-726 (`_interpolate_doy_calendar`): table (n_src, C) float64 on doys
+ * linspace(doy_min, doy_max, n_src) -> (doy_max - doy_min + 1, C) by linear interpolation
+ * (NaN entries along doy are first filled by linear interpolation of their neighbours). */
+int32_t xc_doy_interp_f64(const double* table, int32_t n_src, int64_t C,
+                          int32_t doy_min, int32_t doy_max, double* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a16+a2  percentile-threshold count -- indices/_multivariate.py:1583-1590 (`tx90p` & family),
+ *   core/calendar.py:763-790 (`resample_doy` as an index into the table instead of a
+ *   materialised (lat, lon, time) float64 array), generic.py:357-361.
+ *   out[p, c] = #{ t in p : (double)x[t, c] op table[doy_index[t]-1, c] }  (float64 compare)
+ * ------------------------------------------------------------------------------------------- */
+int32_t xc_doy_threshold_count_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                   const int32_t* period_offsets, int32_t P,
+                                   const int16_t* doy_index, const double* table, int32_t n_doy,
+                                   int32_t op, int32_t* out_count, int32_t* valid_count,
+                                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a17  percentile bootstrap (Zhang 2005) -- core/bootstrapping.py:81-211, 235-282
+ *   x: (T, C) full studied series; base = steps [base_start, base_start + n_base_years*year_len)
+ *   (equal-length year blocks: noleap / 360_day, core/bootstrapping.py:264-265).
+ *   For every period p nested in in-base year y:
+ *     out[p, c] = mean over base years s != y of #{ t in p : x[t] op P^(y<-s)[doy(t)] }
+ *   where P^(y<-s) = percentile_doy of the base series with block y replaced by block s.
+ *   Periods outside the base are NOT written (use xc_doy_threshold_count_f32).
+ *   period_year[p] (int32 host array): base-year ordinal of period p, or -1 when out of base.
+ * ------------------------------------------------------------------------------------------- */
+int32_t xc_bootstrap_doy_count_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                   int64_t base_start, int32_t n_base_years, int32_t year_len,
+                                   const int32_t* period_offsets, const int32_t* period_offsets_host,
+                                   const int32_t* period_year_host, int32_t P,
+                                   int32_t window, double percentile, double alpha, double beta,
+                                   int32_t op, double* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a20  empirical quantile mapping -- xsdba.EmpiricalQuantileMapping (third-party, re-exported
+ *   by sdba.py:11; call sites tests/test_xsdba.py:21-34, 143-150).  group="time".
+ *   train : af, hist_q (nq, C) float32 from ref, hist (T, C); kind 0 = "+", 1 = "*".
+ *   adjust: scen (T, C) from sim (T, C); interp 0 = nearest, 1 = linear; constant extrapolation.
+ * ------------------------------------------------------------------------------------------- */
+int64_t xc_eqm_train_workspace_bytes(int64_t T, int64_t C, int32_t nq);
+int32_t xc_eqm_train_f32(const float* ref, const float* hist, int64_t T, int64_t C, int64_t ldx,
+                         int32_t nq, int32_t kind, float* af, float* hist_q,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+int32_t xc_eqm_adjust_f32(const float* sim, int64_t T, int64_t C, int64_t ldx,
+                          const float* af, const float* hist_q, int32_t nq,
+                          int32_t kind, int32_t interp, float* scen, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Synthetic inputs (BASELINE.json configs).  Stateless counter-based
+ * generators: value(t, global_cell) depends only on (seed, t, global_cell), so a lat tile
+ * generated on any rank equals the same slab of the global grid.
+ *   kind 0: pr in mm/d (10-day wet/dry regimes, exponential amounts, rare NaN blocks)
+ *   kind 1: tasmax in K (latitudinal gradient, annual cycle, daily + weekly anomalies)
+ * ------------------------------------------------------------------------------------------- */
+int32_t xc_synth_f32(float* out, int64_t T, int64_t C, int64_t ldx, int64_t cell_offset,
+                     int64_t cells_per_lat, int64_t n_lat_global, int32_t year_len,
+                     int32_t kind, uint64_t seed, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-buffer entry points (the end-to-end path: host -> device copies inside the call).
+ *   x_host: (T, C) float32 in (pinned or pageable) host memory; the call streams year-sized
+ *   slabs through the caller's device workspace with double buffering, launches the same
+ *   kernels per slab and copies the small outputs back.  Synchronous: returns when out_host is
+ *   complete.  workspace_bytes >= xc_host_stream_workspace_bytes(...).
+ * ------------------------------------------------------------------------------------------- */
+int64_t xc_host_stream_workspace_bytes(int64_t T, int64_t C, const int32_t* period_offsets_host,
+                                       int32_t P);
+int32_t xc_period_runstat_f32_host(const float* x_host, int64_t T, int64_t C,
+                                   const int32_t* period_offsets_host, int32_t P,
+                                   int32_t op, double thr, int32_t cmp_f64,
+                                   int32_t reducer, int32_t window,
+                                   float* out_host, int32_t* valid_count_host,
+                                   void* workspace, int64_t workspace_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XCLIM_B200_H */

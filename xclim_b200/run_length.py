@@ -1,0 +1,91 @@
+"""B200 implementations behind the signatures of ``xclim.indices.run_length``.
+
+The reference functions take a boolean (or 0/1 float) mask ``da`` and a ``freq``; here the mask is
+streamed once through the fused run-length kernel with the condition ``da > 0`` (``rle`` treats
+every value > 0 as part of a run, indices/run_length.py:264-265).  For the fully fused
+data-vs-threshold path use :func:`xclim_b200.generic.spell_length_statistics` /
+:func:`xclim_b200.indices.maximum_consecutive_dry_days`, which never materialise the mask.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib, device
+from .field import attrs_of
+from .generic import _unwrap, _wrap_periods
+
+_GT = _lib.OPS[">"]
+
+
+def _check(freq, index, ufunc_1dim):
+    if ufunc_1dim is True and freq is not None:  # indices/run_length.py:67-68
+        raise ValueError("Resampling after run length operations is not implemented for 1d method")
+    if index != "first":
+        raise NotImplementedError("index='last' is not supported by the B200 hot path")
+    if freq is None:
+        raise NotImplementedError("freq=None (whole-series statistics) : pass a freq covering the series, e.g. via "
+                                  "resample_and_rl(..., freq=...)")
+
+
+def _mask_unwrap(da):
+    vals = da.values if not hasattr(da, "numpy") else da.values
+    if getattr(vals, "dtype", None) is not None and str(vals.dtype) in ("bool", "torch.bool"):
+        if hasattr(vals, "detach"):
+            import torch
+            da_vals = vals.to(torch.float32)
+        else:
+            da_vals = np.asarray(vals, dtype=np.float32)
+        from .field import Field, is_xarray
+        if is_xarray(da):
+            da = da.astype(np.float32)
+        else:
+            da = Field(da_vals, da.dims, da.time, dict(da.coords), dict(da.attrs), da.name)
+    return _unwrap(da)
+
+
+def rle_statistics(da, reducer, window, dim="time", freq=None, ufunc_1dim="from_context", index="first"):
+    """indices/run_length.py:275-335 with ``freq`` given (run-length THEN resample: each run is
+    attributed with its full length to the period of its first element)."""
+    if dim != "time":
+        raise NotImplementedError("only dim='time' is supported")
+    _check(freq, index, ufunc_1dim)
+    if reducer not in _lib.RL_REDUCERS:
+        raise NotImplementedError(f"reducer {reducer!r} is not supported by the B200 hot path")
+    x2d, cell_shape, other, ta = _mask_unwrap(da)
+    out, _ = device.period_runstat(x2d, ta.period_offsets(freq), _GT, 0.0, _lib.RL_REDUCERS[reducer], window,
+                                   resample_before_rl=False)
+    return _wrap_periods(da, out, cell_shape, other, ta, freq, attrs_of(da), dtype=np.float32)
+
+
+def longest_run(da, dim="time", freq=None, ufunc_1dim="from_context", index="first"):
+    """indices/run_length.py:338-378."""
+    return rle_statistics(da, "max", 1, dim=dim, freq=freq, ufunc_1dim=ufunc_1dim, index=index)
+
+
+def windowed_run_count(da, window, dim="time", freq=None, ufunc_1dim="from_context", index="first"):
+    """indices/run_length.py:437-488: total length of runs at least ``window`` long."""
+    return rle_statistics(da, "sum", window, dim=dim, freq=freq, ufunc_1dim=ufunc_1dim, index=index)
+
+
+def windowed_run_events(da, window, dim="time", freq=None, ufunc_1dim="from_context", index="first"):
+    """indices/run_length.py:381-434: number of runs at least ``window`` long."""
+    return rle_statistics(da, "count", window, dim=dim, freq=freq, ufunc_1dim=ufunc_1dim, index=index)
+
+
+def resample_and_rl(da, resample_before_rl, compute, *args, freq, dim="time", **kwargs):
+    """indices/run_length.py:87-132.  ``compute`` must be one of this module's run statistics."""
+    table = {rle_statistics: None, longest_run: ("max", 1), windowed_run_count: "sum", windowed_run_events: "count"}
+    if compute not in table:
+        raise NotImplementedError("resample_and_rl supports rle_statistics, longest_run, windowed_run_count/events")
+    if compute is rle_statistics:
+        reducer = kwargs.get("reducer", args[0] if args else None)
+        window = kwargs.get("window", args[1] if len(args) > 1 else None)
+    elif compute is longest_run:
+        reducer, window = "max", 1
+    else:
+        reducer = table[compute]
+        window = kwargs.get("window", args[0] if args else None)
+    x2d, cell_shape, other, ta = _mask_unwrap(da)
+    out, _ = device.period_runstat(x2d, ta.period_offsets(freq), _GT, 0.0, _lib.RL_REDUCERS[reducer], window,
+                                   resample_before_rl=bool(resample_before_rl))
+    return _wrap_periods(da, out, cell_shape, other, ta, freq, attrs_of(da), dtype=np.float32)

@@ -1,0 +1,237 @@
+"""Daily time axis, calendars and ``resample(time=freq)`` period boundaries (host logic).
+
+The reference delegates all of this to xarray/pandas/cftime (``da.resample(time=freq)``,
+``time.dt.dayofyear`` ...; e.g. indices/generic.py:114, core/calendar.py:450-457).  The kernels only
+need three small integer arrays per time axis -- period offsets, day-of-year index and a group
+(year) index -- so this module computes them directly for the CF calendars, without xarray.  When an
+``xarray.DataArray`` is passed in, :func:`TimeAxis.from_xarray` reads the same fields from
+``da.time.dt`` instead, so any calendar xarray supports works.
+"""
+from __future__ import annotations
+
+import re
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_MONTHS = ["JAN", "FEB", "MAR", "APR", "MAY", "JUN", "JUL", "AUG", "SEP", "OCT", "NOV", "DEC"]
+_DPM_NOLEAP = np.array([31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31])
+_DPM_LEAP = np.array([31, 29, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31])
+
+#: ``max_doy`` table of the reference (core/calendar.py:56-66).
+MAX_DOY = {"standard": 366, "gregorian": 366, "proleptic_gregorian": 366, "julian": 366,
+           "noleap": 365, "365_day": 365, "all_leap": 366, "366_day": 366, "360_day": 360}
+
+
+def _is_leap(year: np.ndarray, calendar: str) -> np.ndarray:
+    year = np.asarray(year)
+    if calendar in ("noleap", "365_day", "360_day"):
+        return np.zeros(year.shape, bool)
+    if calendar in ("all_leap", "366_day"):
+        return np.ones(year.shape, bool)
+    if calendar == "julian":
+        return year % 4 == 0
+    return (year % 4 == 0) & ((year % 100 != 0) | (year % 400 == 0))
+
+
+def _year_fields(year: int, calendar: str):
+    """(month, day, doy) arrays for every day of ``year``."""
+    if calendar == "360_day":
+        month = np.repeat(np.arange(1, 13), 30)
+        day = np.tile(np.arange(1, 31), 12)
+    else:
+        dpm = _DPM_LEAP if bool(_is_leap(np.array(year), calendar)) else _DPM_NOLEAP
+        month = np.repeat(np.arange(1, 13), dpm)
+        day = np.concatenate([np.arange(1, n + 1) for n in dpm])
+    return month, day, np.arange(1, month.size + 1)
+
+
+def parse_offset(freq: str):
+    """Mirror of ``xclim.core.calendar.parse_offset`` (core/calendar.py:558-606) for the frequencies
+    the hot path uses: returns ``(multiplier, base, is_start_anchored, anchor)``."""
+    m = re.fullmatch(r"(\d*)([A-Za-z]+?)(S|E)?(?:-([A-Za-z]{3}))?", freq)
+    if not m:
+        raise ValueError(f"Cannot parse frequency {freq!r}")
+    mult, base, se, anchor = m.groups()
+    mult = int(mult) if mult else 1
+    base = base.upper()
+    if base == "A":
+        base = "Y"
+    if base in ("Y", "Q", "M"):
+        start = se == "S"
+    else:
+        start = True
+    if anchor is not None:
+        anchor = anchor.upper()
+        if anchor not in _MONTHS:
+            raise ValueError(f"Unknown anchor {anchor!r} in {freq!r}")
+    elif base == "Y":
+        anchor = "JAN" if start else "DEC"
+    elif base == "Q":
+        anchor = "JAN" if start else "DEC"  # pandas: QS == QS-JAN, QE == QE-DEC
+    return mult, base, start, anchor
+
+
+@dataclass
+class TimeAxis:
+    """A sorted, gap-free *daily* time axis described by its integer date fields."""
+
+    year: np.ndarray
+    month: np.ndarray
+    day: np.ndarray
+    doy: np.ndarray
+    calendar: str = "standard"
+    coord: object = None          # the original xarray time coordinate, when there was one
+    _cache: dict = field(default_factory=dict, repr=False)
+
+    # ------------------------------------------------------------------ constructors
+    @classmethod
+    def daily(cls, start: str, periods: int, calendar: str = "standard") -> "TimeAxis":
+        """``periods`` consecutive days from ``start`` ("YYYY-MM-DD") in a CF ``calendar``."""
+        if calendar not in MAX_DOY:
+            raise ValueError(f"Unknown calendar {calendar!r}")
+        y0, m0, d0 = (int(v) for v in start.split("-"))
+        ys, ms, ds, js = [], [], [], []
+        y = y0
+        # offset of the start date inside its year
+        mm, dd, jj = _year_fields(y, calendar)
+        sel = np.nonzero((mm == m0) & (dd == d0))[0]
+        if sel.size == 0:
+            raise ValueError(f"{start} is not a valid date in calendar {calendar}")
+        off = int(sel[0])
+        need = periods
+        while need > 0:
+            mm, dd, jj = _year_fields(y, calendar)
+            take = slice(off, min(mm.size, off + need))
+            n = take.stop - take.start
+            ys.append(np.full(n, y))
+            ms.append(mm[take]); ds.append(dd[take]); js.append(jj[take])
+            need -= n
+            off = 0
+            y += 1
+        cat = lambda parts: np.concatenate(parts).astype(np.int32) if parts else np.zeros(0, np.int32)  # noqa: E731
+        return cls(cat(ys), cat(ms), cat(ds), cat(js), calendar)
+
+    @classmethod
+    def from_xarray(cls, time) -> "TimeAxis":
+        """From an xarray time coordinate (numpy datetime64 or cftime), via ``.dt``."""
+        dt = time.dt
+        cal = getattr(dt, "calendar", "standard")
+        return cls(np.asarray(dt.year.values, np.int32), np.asarray(dt.month.values, np.int32),
+                   np.asarray(dt.day.values, np.int32), np.asarray(dt.dayofyear.values, np.int32),
+                   str(cal), coord=time)
+
+    # ------------------------------------------------------------------ basic fields
+    def __len__(self) -> int:
+        return int(self.year.size)
+
+    @property
+    def max_doy(self) -> int:
+        return MAX_DOY.get(self.calendar, 366)
+
+    def isel(self, sl: slice) -> "TimeAxis":
+        c = self.coord[sl] if self.coord is not None else None
+        return TimeAxis(self.year[sl], self.month[sl], self.day[sl], self.doy[sl], self.calendar, coord=c)
+
+    def sel_years(self, first: int, last: int) -> slice:
+        """Index slice of the days whose calendar year is in ``[first, last]``
+        (``da.sel(time=slice("first", "last"))`` with year-resolution strings)."""
+        idx = np.nonzero((self.year >= first) & (self.year <= last))[0]
+        if idx.size == 0:
+            return slice(0, 0)
+        return slice(int(idx[0]), int(idx[-1]) + 1)
+
+    def date_strings(self, idx) -> list[str]:
+        idx = np.atleast_1d(idx)
+        return [f"{int(self.year[i]):04d}-{int(self.month[i]):02d}-{int(self.day[i]):02d}" for i in idx]
+
+    # ------------------------------------------------------------------ resampling
+    def group_ids(self, freq: str) -> np.ndarray:
+        """Monotonic integer id of the ``resample(time=freq)`` bin each day falls in."""
+        mult, base, start, anchor = parse_offset(freq)
+        y = self.year.astype(np.int64)
+        m0 = self.month.astype(np.int64) - 1
+        if base == "Y":
+            am = _MONTHS.index(anchor)
+            first_month = am if start else (am + 1) % 12
+            gid = np.where(m0 >= first_month, y, y - 1)
+        elif base == "Q":
+            am = _MONTHS.index(anchor)
+            first_month = (am if start else (am + 1)) % 3
+            mon = y * 12 + m0 - first_month
+            gid = np.floor_divide(mon, 3)
+        elif base == "M":
+            gid = y * 12 + m0
+        elif base == "D":
+            gid = np.arange(len(self), dtype=np.int64)
+        else:
+            raise NotImplementedError(f"frequency {freq!r} is not supported by the B200 hot path")
+        if mult != 1:
+            gid = np.floor_divide(gid - gid[0], mult) if gid.size else gid
+        return gid
+
+    def period_offsets(self, freq: str) -> np.ndarray:
+        """int32 array of P+1 boundaries: period p covers ``[off[p], off[p+1])``."""
+        key = ("poff", freq)
+        if key not in self._cache:
+            gid = self.group_ids(freq)
+            if gid.size == 0:
+                off = np.zeros(1, np.int32)
+            else:
+                cuts = np.nonzero(np.diff(gid) != 0)[0] + 1
+                off = np.concatenate([[0], cuts, [gid.size]]).astype(np.int32)
+            self._cache[key] = off
+        return self._cache[key]
+
+    def period_labels(self, freq: str) -> list[str]:
+        """Date label of every period as xarray would give it (period start for ``*S`` offsets,
+        period end for ``*E``), as ISO strings."""
+        mult, base, start, anchor = parse_offset(freq)
+        off = self.period_offsets(freq)
+        labels = []
+        for p in range(off.size - 1):
+            i = int(off[p])
+            y, m = int(self.year[i]), int(self.month[i])
+            if base == "D":
+                labels.append(self.date_strings(i)[0])
+                continue
+            if base == "M":
+                span = 1
+                ms = m
+                ys = y
+            elif base == "Q":
+                am = _MONTHS.index(anchor)
+                first_month = (am if start else (am + 1)) % 3
+                k = (y * 12 + m - 1 - first_month) // 3
+                tot = k * 3 + first_month
+                ys, ms = divmod(tot, 12)
+                ms += 1
+                span = 3
+            else:
+                am = _MONTHS.index(anchor)
+                first_month = am if start else (am + 1) % 12
+                ys = y if (m - 1) >= first_month else y - 1
+                ms = first_month + 1
+                span = 12
+            if start:
+                labels.append(f"{ys:04d}-{ms:02d}-01")
+            else:
+                tot = ys * 12 + ms - 1 + span * mult - 1
+                ye, me = divmod(tot, 12)
+                me += 1
+                if self.calendar == "360_day":
+                    dl = 30
+                else:
+                    dpm = _DPM_LEAP if bool(_is_leap(np.array(ye), self.calendar)) else _DPM_NOLEAP
+                    dl = int(dpm[me - 1])
+                labels.append(f"{ye:04d}-{me:02d}-{dl:02d}")
+        return labels
+
+    def bootstrap_group_ids(self, freq: str) -> np.ndarray:
+        """Year grouping used by the percentile bootstrap (core/bootstrapping.py:214-223):
+        ``Y`` + ``S``/``E`` + the anchor of ``freq`` when its base is yearly or quarterly."""
+        mult, base, start, anchor = parse_offset(freq)
+        bfreq = "YS" if start else "YE"
+        if base in ("Y", "Q") and anchor is not None:
+            bfreq = f"{bfreq}-{anchor}"
+        return self.group_ids(bfreq)
