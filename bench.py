@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the xclim_b200 hot path (contract: see DESIGN.md section 6).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA kernels)
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle port on host cores
+
+Workload (BASELINE.json configs[1]): ``maximum_consecutive_dry_days`` (+ fused MissingAny valid
+count) on synthetic daily float32 ``pr`` of shape (10950, 721, 1440) in mm/d, yearly periods.
+One step = one pass of the hot path over the whole grid.  ``value`` = grid-cells/s with the input
+resident in HBM; ``e2e`` = the same through the host-buffer C-ABI call (pinned host input, H2D and
+D2H inside the timed region).  At N > 1 every rank owns one (10950, 721, 1440) lat tile of an
+N x 721-row global grid (weak scaling, no collective on the data path).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+T_FULL, Y_FULL, X_FULL, YEAR = 10950, 721, 1440, 365
+METRIC = "grid_cells_per_s:maximum_consecutive_dry_days(10950x721x1440,f32)"
+UNIT = "grid-cells/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--lat", type=int, default=Y_FULL, help="lat rows per rank (default: full 721)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-tx90p", action="store_true")
+    ap.add_argument("--cpu-lat", type=int, default=16, help="lat rows of the bounded CPU sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons with NVML during the timed region."""
+
+    def __init__(self, index=0, period=0.1):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._th = None
+        self.index, self.period = index, period
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._th = threading.Thread(target=self._run, daemon=True)
+            self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._th:
+            self._th.join(timeout=2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def _cpu_cdd_band(args):
+    """One worker: `lat` rows of (10950, 1, 1440), processed row by row to bound memory."""
+    from oracle import xclim_oracle as O
+    seed, lat, X = args
+    rng = np.random.default_rng(seed)
+    poff = np.arange(T_FULL // YEAR + 1) * YEAR
+    busy = 0.0
+    acc = 0.0
+    for _ in range(lat):
+        x = rng.random((T_FULL, 1, X), dtype=np.float32) * 12.0
+        x[x < 6.0] = 0.0
+        t = time.perf_counter()
+        out = O.maximum_consecutive_dry_days(x, 1.0, poff)
+        miss = O.missing_any(x, poff)
+        out = np.where(miss, np.nan, out)
+        busy += time.perf_counter() - t
+        acc += float(np.nansum(out))
+    return busy, acc
+
+
+def _cpu_procs():
+    cores = os.cpu_count() or 1
+    use = max(1, min(cores, 64))
+    try:
+        import psutil
+        use = max(1, min(use, int(psutil.virtual_memory().available // (3 << 30))))
+    except Exception:
+        pass
+    return use
+
+
+def cpu_arm(lat_rows: int, cores: int, steps: int = 1, warmup: int = 0):
+    """Oracle port (numpy restatement of the reference's whole-array algorithm) on `cores`
+    processes, each working on its own lat band of `lat_rows` rows.  Returns cells/s computed from
+    the slowest worker's busy time (input generation excluded)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    jobs = [(1000 + i, lat_rows, X_FULL) for i in range(cores)]
+    times = []
+    with ctx.Pool(cores) as pool:
+        for it in range(warmup + steps):
+            res = pool.map(_cpu_cdd_band, jobs)
+            if it >= warmup:
+                times.append(max(r[0] for r in res))
+    cells = cores * lat_rows * X_FULL
+    dt = float(np.mean(times))
+    return cells / dt, dt, cells
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    use = _cpu_procs()
+    value, dt, cells = cpu_arm(args.cpu_lat, use, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "maximum_consecutive_dry_days (10950,721,1440) f32 pr mm/d, freq=YS, + MissingAny",
+                   "note": "reference package not importable offline (xarray/dask/pint absent): oracle port timed"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": use, "kind": "port",
+                         "sample": f"{use} lat bands of (10950,{args.cpu_lat},1440) per step, one process per core, {dt:.1f} s busy"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from xclim_b200 import _lib, device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    T, Y, X = T_FULL, args.lat, X_FULL
+    C = Y * X
+    P = T // YEAR
+    poff = np.arange(P + 1, dtype=np.int32) * YEAR
+    n_lat_global = Y * world
+    # ---- inputs generated in HBM (each rank: its lat tile of the global grid)
+    pr = device.synth(T, C, kind=0, seed=2, cell_offset=rank * C, cells_per_lat=X, n_lat_global=n_lat_global)
+    op, red = _lib.OPS["<"], _lib.RL_REDUCERS["max"]
+    launches = [0]
+
+    def step():
+        out, valid = device.period_runstat(pr, poff, op, 1.0, red, 1, resample_before_rl=True, want_valid=True)
+        launches[0] += 1
+        return out, valid
+
+    for _ in range(max(args.warmup, 3)):
+        out, valid = step()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    launches[0] = 0
+    with ClockSampler(local) as clk:
+        barrier()
+        ev[0].record()
+        for i in range(args.steps):
+            out, valid = step()
+            ev[i + 1].record()
+        barrier()
+    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[args.steps])
+    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms = float(tt.item())
+    ms_per_step = total_ms / args.steps
+    cells_total = C * world
+    value = cells_total / (ms_per_step * 1e-3)
+    # ---- roofline of the dominant kernel (period_runstat_kernel): algorithmic bytes / launch time
+    alg_bytes = T * C * 4 + P * C * 4 + P * C * 4  # read x once; write out f32 + valid i32
+    kern_ms = float(np.mean(per_step))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "period_runstat_kernel<LT,MAX,VEC4,VALID,FASTMAX>",
+                "algorithmic_bytes": alg_bytes,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"}
+
+    # ---- checksum of checksums (size-independent sanity: every output in [0, 365], NaN rows counted)
+    out_max = float(out.max().item())
+    n_missing = int((valid != YEAR).sum().item())
+    assert 0 <= out_max <= YEAR
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"maximum_consecutive_dry_days ({T},{Y},{X}) f32 pr mm/d per GPU, thresh 1 mm/day, "
+                               f"op <, freq=YS, fused MissingAny valid count",
+                   "global_grid": [T, n_lat_global, X], "partition": f"lat tiles x{world}, no collective",
+                   "l2_policy": "input 45.5 GB >> 126 MB L2, read once per step (no flush needed)"},
+        "roofline": roofline, "gpu_launches": launches[0], "clocks": clk.summary(),
+        "check": {"out_max_days": out_max, "periods_masked_missing": n_missing},
+    }
+
+    # ---- tx90p (second headline kernel) when available
+    if not args.no_tx90p:
+        try:
+            from bench_tx90p import tx90p_section  # optional module, added with the percentile kernels
+            line["tx90p"] = tx90p_section(args, dev, rank, world, peak, barrier)
+        except ImportError:
+            pass
+
+    # ---- end to end through the host-buffer C-ABI call
+    if not args.no_e2e:
+        try:
+            from bench_e2e import e2e_section
+            line["e2e"] = e2e_section(args, dev, rank, world, pr, poff, barrier)
+        except ImportError:
+            line["e2e"] = None
+
+    # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N == 1 only
+    if rank == 0 and world == 1 and not args.no_cpu:
+        use = _cpu_procs()
+        v, dt, cells = cpu_arm(args.cpu_lat, use)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": use, "kind": "port",
+                                "sample": f"{use} lat bands of (10950,{args.cpu_lat},1440), one process per core, "
+                                          f"{dt:.1f} s"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import xclim_oracle as O
-from tests.conftest import make_field
+from xb_helpers import make_field
 
 pytestmark = pytest.mark.gpu
 
