@@ -273,7 +273,7 @@ def run_ours(args):
     if not args.no_e2e:
         try:
             from bench_e2e import e2e_section
-            line["e2e"] = e2e_section(args, dev, rank, world, pr, poff, barrier)
+            line["e2e"] = e2e_section(args, dev, rank, world, pr, poff, barrier, out, valid)
         except ImportError:
             line["e2e"] = None
 

@@ -132,20 +132,33 @@ int32_t xc_rolling_period_reduce_f32(const float* x, int64_t T, int64_t C, int64
 /* ---------------------------------------------------------------------------------------------
  * a14+a15  percentile_doy -- core/calendar.py:395-494 with the quantile of
  *   core/utils.py:279-557 (`calc_perc` -> `_nan_quantile`, Hyndman-Fan alpha/beta).
- *   x: (T, C) float32 base-period series; doy_index/year_index: int16 (T) day-of-year (1-based)
- *   and 0-based year ordinal of every step; n_doy = max day-of-year present; n_years = number of
- *   distinct years.  out: (n_per, n_doy, C) float64.  The 366 -> 1..366 re-interpolation of
- *   core/calendar.py:484-485 is xc_doy_interp_f64 (separate, tiny).
- *   workspace: device scratch of xc_percentile_doy_workspace_bytes() bytes (may be 0 / NULL).
+ *   x: (T, C) float32 base-period series (device).  doy_index_host / year_index_host: HOST int16
+ *   arrays (T) with the 1-based day-of-year and the 0-based year ordinal of every step (tiny
+ *   calendar metadata, read synchronously during the call); n_doy = max day-of-year present;
+ *   n_years = number of distinct years; window must be odd.
+ *   out: (n_per, n_doy, C) float64 (device), i.e. the reference's (lat, lon, dayofyear,
+ *   percentiles) table stored doy-major so that it is coalesced along cells.  The 366 -> 1..366
+ *   re-interpolation of core/calendar.py:484-485 is xc_doy_interp_f64 (separate, tiny).
+ *   Percentiles whose order statistics lie more than 64 ranks from both ends of the sample are
+ *   rejected with XC_ERR_UNSUPPORTED.
+ *   workspace: device scratch of xc_percentile_doy_workspace_bytes() bytes.
  * ------------------------------------------------------------------------------------------- */
 int64_t xc_percentile_doy_workspace_bytes(int64_t T, int64_t C, int32_t n_doy, int32_t n_years,
                                           int32_t window, int32_t n_per);
 int32_t xc_percentile_doy_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
-                              const int16_t* doy_index, const int16_t* year_index,
+                              const int16_t* doy_index_host, const int16_t* year_index_host,
                               int32_t n_doy, int32_t n_years, int32_t window,
                               const double* percentiles_host, int32_t n_per,
                               double alpha, double beta,
                               double* out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Test hook: same contract as xc_percentile_doy_f32 for ONE percentile, but always through the
+ * generic (any-calendar) kernel, so the fast uniform-year kernel can be checked against it. */
+int32_t xc_percentile_doy_generic_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                      const int16_t* doy_index_host, const int16_t* year_index_host,
+                                      int32_t n_doy, int32_t n_years, int32_t window, double percentile,
+                                      double alpha, double beta, double* out, void* workspace,
+                                      int64_t workspace_bytes, void* stream);
 
 /* core/calendar.py:690-726 (`_interpolate_doy_calendar`): table (n_src, C) float64 on doys
  * linspace(doy_min, doy_max, n_src) -> (doy_max - doy_min + 1, C) by linear interpolation

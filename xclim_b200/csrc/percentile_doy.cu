@@ -1,0 +1,435 @@
+// percentile_doy: day-of-year rolling-window percentiles per grid cell.
+//
+// Replaces core/calendar.py:395-494 (`percentile_doy`: rolling(center).construct -> unstack by
+// (year, dayofyear) -> stack (year, window) -> calc_perc) and core/utils.py:279-557 (the NaN-aware
+// Hyndman-Fan quantile with its full sort, :538).
+//
+// Sample of day-of-year d (window w = 2h+1):  S(d) = { x[i+k] : doy(i) = d, |k| <= h, 0 <= i+k < T }.
+//
+// Design (B200).  The (time, lat, lon) buffer is coalesced along cells, so a LANE owns one cell
+// (a warp reads one 128-byte row segment per time step) and keeps the order statistics it needs in
+// REGISTERS: only the K extreme values of S(d) matter (K = 16 for the 90th percentile of 150
+// samples), never the full sort the reference does.
+//   * generic kernel (any calendar): a small (year, doy) -> row table drives direct insertion of
+//     every sample into a sorted K-register list (2K min/max per sample).
+//   * fast kernel (all years the same length, e.g. noleap / 360_day): S(d) is the union of the w
+//     per-day lists Y(e) = { x[y*L + e] : y }, e = d-h..d+h.  Each Y(e) is loaded once (N coalesced
+//     rows), sorted by a register sorting network and kept for the w consecutive days that use
+//     it; S(d)'s K extremes come from w-1 bitonic top-K merges.  Days are processed in order so
+//     every input row is read once per chunk (+2h halo days).
+// No shared memory, no tensor cores (there is no contraction); the kernel is bound by the
+// min/max (ALU) pipe, see DESIGN.md.
+#include <type_traits>
+#include <vector>
+
+#include "common.cuh"
+#include "quantile.cuh"
+#include "sortnet.cuh"
+
+namespace xc {
+namespace {
+
+constexpr int kThreads = 128;
+#define XC_NEG_INF (__int_as_float(0xff800000))
+
+// value as inserted in the lists: NaN -> -inf (never selected), bottom side -> negated
+__device__ __forceinline__ float prep(float v, bool top, int& n) {
+  const bool ok = (v == v);
+  n += ok ? 1 : 0;
+  v = top ? v : -v;
+  return ok ? v : XC_NEG_INF;
+}
+
+template <int K>
+__device__ __forceinline__ void insert_desc(float (&lst)[K], float v) {
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float hi = fmaxf(lst[k], v);
+    v = fminf(lst[k], v);
+    lst[k] = hi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic kernel: pos[y * n_doy + (d-1)] = row of (year y, doy d) or -1
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(kThreads)
+percentile_doy_generic_kernel(const float* __restrict__ x, int64_t T, int64_t C, int64_t ldx,
+                              const int32_t* __restrict__ pos, int32_t n_doy, int32_t n_years, int32_t h,
+                              QuantSpec spec, int32_t doys_per_chunk, double* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (c >= C) return;
+  const int d0 = blockIdx.y * doys_per_chunk;
+  const int d1 = min(n_doy, d0 + doys_per_chunk);
+  const float* col = x + c;
+  const bool top = spec.top != 0;
+  for (int d = d0; d < d1; ++d) {
+    float lst[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) lst[k] = XC_NEG_INF;
+    int n = 0;
+    for (int y = 0; y < n_years; ++y) {
+      const int i = pos[y * n_doy + d];
+      if (i < 0) continue;
+      const int j0 = max(0, i - h), j1 = min((int)T - 1, i + h);
+      for (int j = j0; j <= j1; ++j) {
+        const float v = prep(__ldg(col + (int64_t)j * ldx), top, n);
+        insert_desc<K>(lst, v);
+      }
+    }
+    out[(int64_t)d * C + c] = finalize_quantile<K>(lst, n, spec);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fast kernel: uniform year length L == n_doy, T == N*L, series starts on doy 1
+// ------------------------------------------------------------------------------------------------
+// Sorted (descending) K extremes of Y(e) = { x[y*L + e] : 0 <= y*L + e < T } ; e may lie in
+// [-h, L+h) (the window reaches into the neighbouring year, core/calendar.py:448 pads only at the
+// two ends of the SERIES).
+template <int K>
+__device__ __forceinline__ void load_day_list(const float* __restrict__ col, int64_t ldx, int T, int L, int N,
+                                              int e, bool top, float (&lst)[K], int& n) {
+  n = 0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) lst[k] = XC_NEG_INF;
+  bool first = true;
+  for (int y0 = 0; y0 < N; y0 += K) {
+    float v[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int y = y0 + k;
+      const int row = y * L + e;
+      const bool ok = (y < N) && (row >= 0) && (row < T);
+      float r = XC_NEG_INF;
+      if (ok) r = prep(ld_stream(col + (int64_t)row * ldx), top, n);
+      v[k] = r;
+    }
+    sort_desc<K>(v);
+    if (first) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) lst[k] = v[k];
+      first = false;
+    } else {
+      merge_top_desc<K>(lst, v);
+    }
+  }
+}
+
+template <int K, int W>
+__global__ void __launch_bounds__(kThreads)
+percentile_doy_uniform_kernel(const float* __restrict__ x, int32_t T, int64_t C, int64_t ldx, int32_t L,
+                              int32_t N, QuantSpec spec, int32_t doys_per_chunk, double* __restrict__ out) {
+  constexpr int H = W / 2;
+  const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (c >= C) return;
+  const int d0 = blockIdx.y * doys_per_chunk;
+  const int d1 = min(L, d0 + doys_per_chunk);
+  if (d0 >= d1) return;
+  const float* col = x + c;
+  const bool top = spec.top != 0;
+
+  // ring of W day lists; list of day e lives in slot (e - (d0 - H)) mod W
+  float ring[W][K];
+  int cnt[W];
+#pragma unroll
+  for (int s = 0; s < W - 1; ++s) load_day_list<K>(col, ldx, T, L, N, d0 - H + s, top, ring[s], cnt[s]);
+
+  for (int d = d0; d < d1; d += W) {
+#pragma unroll
+    for (int ph = 0; ph < W; ++ph) {
+      const int dd = d + ph;
+      if (dd < d1) {
+        constexpr int kDummy = 0;
+        (void)kDummy;
+        const int slot_new = (ph + W - 1) % W;  // compile-time after unrolling
+        load_day_list<K>(col, ldx, T, L, N, dd + H, top, ring[slot_new], cnt[slot_new]);
+        float acc[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k] = ring[0][k];
+        int n = cnt[0];
+#pragma unroll
+        for (int s = 1; s < W; ++s) {
+          merge_top_desc<K>(acc, ring[s]);
+          n += cnt[s];
+        }
+        out[(int64_t)dd * C + c] = finalize_quantile<K>(acc, n, spec);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// doy table interpolation (core/calendar.py:690-726)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+doy_interp_kernel(const double* __restrict__ tab, int32_t n_src, int64_t C, int32_t doy_min, int32_t doy_max,
+                  double* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int n_out = doy_max - doy_min + 1;
+  // source coordinates: linspace(doy_min, doy_max, n_src)
+  const double step = (n_src > 1) ? ((double)(doy_max - doy_min) / (double)(n_src - 1)) : 0.0;
+  for (int o = blockIdx.y; o < n_out; o += gridDim.y) {
+    const double t = (double)(doy_min + o);
+    // np.interp: find i with xs[i] <= t <= xs[i+1]
+    int i = (step > 0.0) ? (int)floor((t - doy_min) / step) : 0;
+    i = max(0, min(i, n_src - 2));
+    // guard against rounding of the division: enforce xs[i] <= t < xs[i+1]
+    while (i > 0 && (doy_min + i * step) > t) --i;
+    while (i < n_src - 2 && (doy_min + (i + 1) * step) <= t) ++i;
+    // linspace as numpy computes it: start + i*step (last point forced to stop)
+    const double x0 = (i == n_src - 1) ? (double)doy_max : __dadd_rn((double)doy_min, __dmul_rn((double)i, step));
+    const double x1 = (i + 1 == n_src - 1) ? (double)doy_max
+                                           : __dadd_rn((double)doy_min, __dmul_rn((double)(i + 1), step));
+    const double y0 = tab[(int64_t)i * C + c];
+    const double y1 = tab[(int64_t)(i + 1) * C + c];
+    double r;
+    if (t == x1) {
+      r = y1;
+    } else if (t == x0) {
+      r = y0;
+    } else {
+      // numpy's interp: slope = (y1-y0)/(x1-x0); r = slope*(t-x0) + y0
+      const double slope = __ddiv_rn(__dadd_rn(y1, -y0), __dadd_rn(x1, -x0));
+      r = __dadd_rn(__dmul_rn(slope, __dadd_rn(t, -x0)), y0);
+    }
+    out[(int64_t)o * C + c] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// percentile-threshold count
+// ------------------------------------------------------------------------------------------------
+template <int OP, bool VALID>
+__global__ void __launch_bounds__(kThreads)
+doy_count_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, const int32_t* __restrict__ poff,
+                 const int16_t* __restrict__ doy, const double* __restrict__ table,
+                 int32_t* __restrict__ out, int32_t* __restrict__ valid) {
+  // blockIdx.x = period (fastest): the blocks sharing a cell range run together and share the
+  // table rows through L2; blockIdx.y = cell block
+  const int p = blockIdx.x;
+  const int64_t c = ((int64_t)blockIdx.y * kThreads + threadIdx.x) * 2;
+  if (c >= C) return;
+  const bool two = (c + 1 < C);
+  const int t0 = poff[p], t1 = poff[p + 1];
+  int32_t n0 = 0, n1 = 0, v0 = 0, v1 = 0;
+  const float* col = x + c;
+  if (two && ((ldx & 1) == 0) && ((C & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 7u) == 0) &&
+      ((reinterpret_cast<uintptr_t>(table) & 15u) == 0)) {
+#pragma unroll 4
+    for (int t = t0; t < t1; ++t) {
+      const int d = doy[t] - 1;
+      const float2 xv = *reinterpret_cast<const float2*>(col + (int64_t)t * ldx);
+      const double2 th = *reinterpret_cast<const double2*>(table + (int64_t)d * C + c);
+      n0 += cmpd<OP>((double)xv.x, th.x) ? 1 : 0;
+      n1 += cmpd<OP>((double)xv.y, th.y) ? 1 : 0;
+      if constexpr (VALID) {
+        v0 += (xv.x == xv.x) ? 1 : 0;
+        v1 += (xv.y == xv.y) ? 1 : 0;
+      }
+    }
+  } else {
+    for (int t = t0; t < t1; ++t) {
+      const int d = doy[t] - 1;
+      const float a = col[(int64_t)t * ldx];
+      n0 += cmpd<OP>((double)a, table[(int64_t)d * C + c]) ? 1 : 0;
+      if constexpr (VALID) v0 += (a == a) ? 1 : 0;
+      if (two) {
+        const float b = col[(int64_t)t * ldx + 1];
+        n1 += cmpd<OP>((double)b, table[(int64_t)d * C + c + 1]) ? 1 : 0;
+        if constexpr (VALID) v1 += (b == b) ? 1 : 0;
+      }
+    }
+  }
+  out[(int64_t)p * C + c] = n0;
+  if (two) out[(int64_t)p * C + c + 1] = n1;
+  if constexpr (VALID) {
+    valid[(int64_t)p * C + c] = v0;
+    if (two) valid[(int64_t)p * C + c + 1] = v1;
+  }
+}
+
+template <int K>
+int32_t launch_generic(const float* x, int64_t T, int64_t C, int64_t ldx, const int32_t* pos, int32_t n_doy,
+                       int32_t n_years, int32_t h, const QuantSpec& spec, double* out, cudaStream_t st) {
+  const int64_t cblocks = (C + kThreads - 1) / kThreads;
+  // enough chunks to fill the machine when the grid is narrow
+  int chunks = (int)((148 * 8 + cblocks - 1) / cblocks);
+  chunks = chunks < 1 ? 1 : (chunks > n_doy ? n_doy : chunks);
+  const int per = (n_doy + chunks - 1) / chunks;
+  chunks = (n_doy + per - 1) / per;
+  dim3 grid((unsigned)cblocks, (unsigned)chunks, 1);
+  percentile_doy_generic_kernel<K><<<grid, kThreads, 0, st>>>(x, T, C, ldx, pos, n_doy, n_years, h, spec, per, out);
+  return launch_status("percentile_doy_generic_kernel");
+}
+
+template <int K, int W>
+int32_t launch_uniform(const float* x, int64_t T, int64_t C, int64_t ldx, int32_t L, int32_t N,
+                       const QuantSpec& spec, double* out, cudaStream_t st) {
+  const int64_t cblocks = (C + kThreads - 1) / kThreads;
+  int chunks = (int)((148 * 12 + cblocks - 1) / cblocks);
+  chunks = chunks < 1 ? 1 : chunks;
+  int per = (L + chunks - 1) / chunks;
+  if (per < 8 * W) per = 8 * W;  // keep the halo overhead (2h extra day lists per chunk) small
+  if (per > L) per = L;
+  per = ((per + W - 1) / W) * W;
+  chunks = (L + per - 1) / per;
+  dim3 grid((unsigned)cblocks, (unsigned)chunks, 1);
+  percentile_doy_uniform_kernel<K, W><<<grid, kThreads, 0, st>>>(x, (int32_t)T, C, ldx, L, N, spec, per, out);
+  return launch_status("percentile_doy_uniform_kernel");
+}
+
+}  // namespace
+}  // namespace xc
+
+using namespace xc;
+
+extern "C" int64_t xc_percentile_doy_workspace_bytes(int64_t T, int64_t C, int32_t n_doy, int32_t n_years,
+                                                     int32_t window, int32_t n_per) {
+  (void)T; (void)C; (void)window; (void)n_per;
+  return (int64_t)n_doy * (int64_t)n_years * 4 + 256;
+}
+
+extern "C" int32_t xc_percentile_doy_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                         const int16_t* doy_index_host, const int16_t* year_index_host,
+                                         int32_t n_doy, int32_t n_years, int32_t window,
+                                         const double* percentiles_host, int32_t n_per, double alpha, double beta,
+                                         double* out, void* workspace, int64_t workspace_bytes, void* stream) {
+  XC_REQUIRE(x && doy_index_host && year_index_host && percentiles_host && out, "null pointer argument");
+  XC_REQUIRE(T > 0 && C > 0 && ldx >= C && T < 2147483647LL, "bad shape");
+  XC_REQUIRE(n_doy > 0 && n_doy <= 366 && n_years > 0 && n_per > 0, "bad calendar description");
+  XC_REQUIRE(window >= 1, "window must be >= 1");
+  if (window % 2 == 0) {
+    set_error("even `window` (xarray's center=True convention for even windows) is not supported");
+    return XC_ERR_UNSUPPORTED;
+  }
+  const int h = window / 2;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  // (year, doy) -> row table, and detection of the uniform-year fast path
+  std::vector<int32_t> pos((size_t)n_doy * n_years, -1);
+  bool uniform = (T == (int64_t)n_doy * n_years);
+  for (int64_t t = 0; t < T; ++t) {
+    const int d = doy_index_host[t], y = year_index_host[t];
+    XC_REQUIRE(d >= 1 && d <= n_doy && y >= 0 && y < n_years, "doy/year index out of range at step %lld", (long long)t);
+    pos[(size_t)y * n_doy + (d - 1)] = (int32_t)t;
+    if (uniform && (d - 1 != (int)(t % n_doy) || y != (int)(t / n_doy))) uniform = false;
+  }
+  int32_t* pos_d = nullptr;
+  if (!uniform) {
+    const int64_t need = (int64_t)pos.size() * 4;
+    XC_REQUIRE(workspace != nullptr && workspace_bytes >= need, "workspace too small: need %lld bytes", (long long)need);
+    pos_d = (int32_t*)workspace;
+    XC_CHECK_CUDA(cudaMemcpyAsync(pos_d, pos.data(), (size_t)need, cudaMemcpyHostToDevice, st));
+    // pos lives on this stack frame: make sure the copy has been issued from pageable memory
+    XC_CHECK_CUDA(cudaStreamSynchronize(st));
+  }
+
+  for (int ip = 0; ip < n_per; ++ip) {
+    const double per = percentiles_host[ip];
+    XC_REQUIRE(per >= 0.0 && per <= 100.0, "percentiles must be in [0, 100], got %g", per);
+    QuantSpec spec;
+    const int need = plan_quantile(per, alpha, beta, n_years * window, &spec);
+    if (need < 0 || need > 64) {
+      set_error("percentile %g of up to %d samples needs %d order statistics per cell; at most 64 are kept in "
+                "registers", per, n_years * window, need);
+      return XC_ERR_UNSUPPORTED;
+    }
+    double* o = out + (int64_t)ip * n_doy * C;
+    int32_t e;
+    if (uniform && window == 5 && need <= 16) {
+      e = need <= 8 ? launch_uniform<8, 5>(x, T, C, ldx, n_doy, n_years, spec, o, st)
+                    : launch_uniform<16, 5>(x, T, C, ldx, n_doy, n_years, spec, o, st);
+    } else if (uniform && window == 3 && need <= 16) {
+      e = launch_uniform<16, 3>(x, T, C, ldx, n_doy, n_years, spec, o, st);
+    } else if (uniform && window == 7 && need <= 16) {
+      e = launch_uniform<16, 7>(x, T, C, ldx, n_doy, n_years, spec, o, st);
+    } else {
+      if (uniform && pos_d == nullptr) {  // uniform calendar but no fast instantiation: use the generic kernel
+        const int64_t nbytes = (int64_t)pos.size() * 4;
+        XC_REQUIRE(workspace != nullptr && workspace_bytes >= nbytes, "workspace too small: need %lld bytes",
+                   (long long)nbytes);
+        pos_d = (int32_t*)workspace;
+        XC_CHECK_CUDA(cudaMemcpyAsync(pos_d, pos.data(), (size_t)nbytes, cudaMemcpyHostToDevice, st));
+        XC_CHECK_CUDA(cudaStreamSynchronize(st));
+      }
+      if (need <= 4) e = launch_generic<4>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st);
+      else if (need <= 8) e = launch_generic<8>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st);
+      else if (need <= 16) e = launch_generic<16>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st);
+      else if (need <= 32) e = launch_generic<32>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st);
+      else e = launch_generic<64>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st);
+    }
+    if (e) return e;
+  }
+  return XC_OK;
+}
+
+// Forces the generic kernel (test hook: the two paths must agree bit for bit).
+extern "C" int32_t xc_percentile_doy_generic_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                                 const int16_t* doy_index_host, const int16_t* year_index_host,
+                                                 int32_t n_doy, int32_t n_years, int32_t window, double percentile,
+                                                 double alpha, double beta, double* out, void* workspace,
+                                                 int64_t workspace_bytes, void* stream) {
+  XC_REQUIRE(x && doy_index_host && year_index_host && out && workspace, "null pointer argument");
+  XC_REQUIRE(window >= 1 && window % 2 == 1, "window must be odd");
+  std::vector<int32_t> pos((size_t)n_doy * n_years, -1);
+  for (int64_t t = 0; t < T; ++t) {
+    const int d = doy_index_host[t], y = year_index_host[t];
+    XC_REQUIRE(d >= 1 && d <= n_doy && y >= 0 && y < n_years, "doy/year index out of range");
+    pos[(size_t)y * n_doy + (d - 1)] = (int32_t)t;
+  }
+  const int64_t need_b = (int64_t)pos.size() * 4;
+  XC_REQUIRE(workspace_bytes >= need_b, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  XC_CHECK_CUDA(cudaMemcpyAsync(workspace, pos.data(), (size_t)need_b, cudaMemcpyHostToDevice, st));
+  XC_CHECK_CUDA(cudaStreamSynchronize(st));
+  QuantSpec spec;
+  const int need = plan_quantile(percentile, alpha, beta, n_years * window, &spec);
+  if (need < 0 || need > 64) {
+    set_error("percentile needs %d order statistics; at most 64 are kept", need);
+    return XC_ERR_UNSUPPORTED;
+  }
+  const int32_t* pos_d = (const int32_t*)workspace;
+  const int h = window / 2;
+  if (need <= 4) return launch_generic<4>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, out, st);
+  if (need <= 8) return launch_generic<8>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, out, st);
+  if (need <= 16) return launch_generic<16>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, out, st);
+  if (need <= 32) return launch_generic<32>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, out, st);
+  return launch_generic<64>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, out, st);
+}
+
+extern "C" int32_t xc_doy_interp_f64(const double* table, int32_t n_src, int64_t C, int32_t doy_min,
+                                     int32_t doy_max, double* out, void* stream) {
+  XC_REQUIRE(table && out, "null pointer argument");
+  XC_REQUIRE(n_src >= 2 && C > 0 && doy_max > doy_min, "bad shape");
+  const int n_out = doy_max - doy_min + 1;
+  dim3 grid((unsigned)((C + 255) / 256), (unsigned)(n_out < 64 ? n_out : 64), 1);
+  doy_interp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table, n_src, C, doy_min, doy_max, out);
+  return launch_status("doy_interp_kernel");
+}
+
+extern "C" int32_t xc_doy_threshold_count_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                              const int32_t* period_offsets, int32_t P,
+                                              const int16_t* doy_index, const double* table, int32_t n_doy,
+                                              int32_t op, int32_t* out_count, int32_t* valid_count, void* stream) {
+  XC_REQUIRE(x && period_offsets && doy_index && table && out_count, "null pointer argument");
+  XC_REQUIRE(T > 0 && C > 0 && ldx >= C && P > 0 && n_doy > 0, "bad shape");
+  (void)n_doy;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t pairs = (C + 1) / 2;
+  const int64_t cblocks = (pairs + kThreads - 1) / kThreads;
+  XC_REQUIRE(cblocks <= 65535, "too many cells for one launch: tile the grid by latitude");
+  dim3 grid((unsigned)P, (unsigned)cblocks, 1);
+  return dispatch_op(op, [&](auto OPC) -> int32_t {
+    constexpr int OP = decltype(OPC)::value;
+    if (valid_count)
+      doy_count_kernel<OP, true><<<grid, kThreads, 0, st>>>(x, C, ldx, period_offsets, doy_index, table, out_count,
+                                                            valid_count);
+    else
+      doy_count_kernel<OP, false><<<grid, kThreads, 0, st>>>(x, C, ldx, period_offsets, doy_index, table, out_count,
+                                                             valid_count);
+    return launch_status("doy_count_kernel");
+  });
+}

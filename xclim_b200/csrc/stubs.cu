@@ -8,20 +8,6 @@ extern "C" int32_t xc_rolling_period_reduce_f32(const float*, int64_t, int64_t, 
                                                 int32_t, int32_t, int32_t, int32_t, float*, void*) {
   XC_STUB("xc_rolling_period_reduce_f32");
 }
-extern "C" int64_t xc_percentile_doy_workspace_bytes(int64_t, int64_t, int32_t, int32_t, int32_t, int32_t) { return 0; }
-extern "C" int32_t xc_percentile_doy_f32(const float*, int64_t, int64_t, int64_t, const int16_t*, const int16_t*,
-                                         int32_t, int32_t, int32_t, const double*, int32_t, double, double, double*,
-                                         void*, int64_t, void*) {
-  XC_STUB("xc_percentile_doy_f32");
-}
-extern "C" int32_t xc_doy_interp_f64(const double*, int32_t, int64_t, int32_t, int32_t, double*, void*) {
-  XC_STUB("xc_doy_interp_f64");
-}
-extern "C" int32_t xc_doy_threshold_count_f32(const float*, int64_t, int64_t, int64_t, const int32_t*, int32_t,
-                                              const int16_t*, const double*, int32_t, int32_t, int32_t*, int32_t*,
-                                              void*) {
-  XC_STUB("xc_doy_threshold_count_f32");
-}
 extern "C" int32_t xc_bootstrap_doy_count_f32(const float*, int64_t, int64_t, int64_t, int64_t, int32_t, int32_t,
                                               const int32_t*, const int32_t*, const int32_t*, int32_t, int32_t, double,
                                               double, double, int32_t, double*, void*) {
@@ -35,9 +21,4 @@ extern "C" int32_t xc_eqm_train_f32(const float*, const float*, int64_t, int64_t
 extern "C" int32_t xc_eqm_adjust_f32(const float*, int64_t, int64_t, int64_t, const float*, const float*, int32_t,
                                      int32_t, int32_t, float*, void*) {
   XC_STUB("xc_eqm_adjust_f32");
-}
-extern "C" int64_t xc_host_stream_workspace_bytes(int64_t, int64_t, const int32_t*, int32_t) { return 0; }
-extern "C" int32_t xc_period_runstat_f32_host(const float*, int64_t, int64_t, const int32_t*, int32_t, int32_t, double,
-                                              int32_t, int32_t, int32_t, float*, int32_t*, void*, int64_t) {
-  XC_STUB("xc_period_runstat_f32_host");
 }

@@ -126,3 +126,81 @@ def synth(T, C, kind, seed, cell_offset=0, cells_per_lat=1440, n_lat_global=721,
     check(load().xc_synth_f32(out.data_ptr(), T, C, C, cell_offset, cells_per_lat, n_lat_global, year_len,
                               kind, seed, current_stream_ptr()))
     return out
+
+
+# ------------------------------------------------------------------------------------ percentiles
+def percentile_doy(x2d, doy_index, year_index, n_doy, n_years, window, percentiles, alpha, beta,
+                   force_generic=False):
+    """(n_per, n_doy, C) float64 table of day-of-year percentiles (core/calendar.py:448-479)."""
+    T, C = x2d.shape
+    per = np.ascontiguousarray(np.atleast_1d(np.asarray(percentiles, dtype=np.float64)))
+    doy = np.ascontiguousarray(np.asarray(doy_index, dtype=np.int16))
+    yr = np.ascontiguousarray(np.asarray(year_index, dtype=np.int16))
+    assert doy.size == T and yr.size == T
+    lib = load()
+    ws_bytes = int(lib.xc_percentile_doy_workspace_bytes(T, C, n_doy, n_years, window, per.size))
+    ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=x2d.device)
+    out = torch.empty((per.size, n_doy, C), dtype=torch.float64, device=x2d.device)
+    if force_generic:
+        for i, p in enumerate(per):
+            check(lib.xc_percentile_doy_generic_f32(x2d.data_ptr(), T, C, x2d.stride(0), doy.ctypes.data,
+                                                    yr.ctypes.data, n_doy, n_years, int(window), float(p),
+                                                    float(alpha), float(beta), out[i].data_ptr(), ws.data_ptr(),
+                                                    ws.numel(), current_stream_ptr()))
+    else:
+        check(lib.xc_percentile_doy_f32(x2d.data_ptr(), T, C, x2d.stride(0), doy.ctypes.data, yr.ctypes.data,
+                                        n_doy, n_years, int(window), per.ctypes.data, per.size, float(alpha),
+                                        float(beta), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                        current_stream_ptr()))
+    return out
+
+
+def doy_interp(table2d, doy_min, doy_max):
+    """core/calendar.py:690-726 on a (n_src, C) float64 device table."""
+    n_src, C = table2d.shape
+    out = torch.empty((doy_max - doy_min + 1, C), dtype=torch.float64, device=table2d.device)
+    check(load().xc_doy_interp_f64(table2d.data_ptr(), n_src, C, doy_min, doy_max, out.data_ptr(),
+                                   current_stream_ptr()))
+    return out
+
+
+def doy_threshold_count(x2d, poff, doy_index, table2d, op_code, want_valid=False):
+    """#{t in period : float64(x[t]) op table[doy[t]-1]} (indices/_multivariate.py:1583-1590)."""
+    T, C = x2d.shape
+    P = len(poff) - 1
+    poff_d = dev_ints(poff, np.int32, x2d.device)
+    doy_d = dev_ints(doy_index, np.int16, x2d.device)
+    assert table2d.dtype == torch.float64 and table2d.is_contiguous() and table2d.shape[1] == C
+    assert int(np.max(doy_index)) <= table2d.shape[0] and int(np.min(doy_index)) >= 1
+    out = torch.empty((P, C), dtype=torch.int32, device=x2d.device)
+    valid = torch.empty((P, C), dtype=torch.int32, device=x2d.device) if want_valid else None
+    check(load().xc_doy_threshold_count_f32(x2d.data_ptr(), T, C, x2d.stride(0), poff_d.data_ptr(), P,
+                                            doy_d.data_ptr(), table2d.data_ptr(), table2d.shape[0], op_code,
+                                            out.data_ptr(), _ptr(valid), current_stream_ptr()))
+    return out, valid
+
+
+# ------------------------------------------------------------------------------------ host-buffer path
+def period_runstat_host(x_host, poff, op_code, thr, reducer_code, window, cmp_f64=False, want_valid=True,
+                        workspace=None, out_host=None, valid_host=None):
+    """End-to-end call with HOST buffers (the `_host` C-ABI entry point): ``x_host`` is a (T, C)
+    float32 CPU tensor (ideally pinned); slabs are streamed H2D inside the call, results land in
+    host memory.  Returns ``(out_host, valid_host, workspace)`` so that buffers can be reused."""
+    _require_cuda()
+    assert x_host.dtype == torch.float32 and x_host.is_contiguous() and not x_host.is_cuda
+    T, C = x_host.shape
+    P = len(poff) - 1
+    poff_h = np.ascontiguousarray(np.asarray(poff, dtype=np.int32))
+    lib = load()
+    need = int(lib.xc_host_stream_workspace_bytes(T, C, poff_h.ctypes.data, P))
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device="cuda")
+    if out_host is None:
+        out_host = torch.empty((P, C), dtype=torch.float32).pin_memory()
+    if want_valid and valid_host is None:
+        valid_host = torch.empty((P, C), dtype=torch.int32).pin_memory()
+    check(lib.xc_period_runstat_f32_host(x_host.data_ptr(), T, C, poff_h.ctypes.data, P, op_code, float(thr),
+                                         int(bool(cmp_f64)), reducer_code, int(window), out_host.data_ptr(),
+                                         valid_host.data_ptr() if want_valid else None, workspace.data_ptr(),
+                                         workspace.numel()))
+    return out_host, (valid_host if want_valid else None), workspace

@@ -38,3 +38,58 @@ def dry_days(pr, thresh="0.2 mm/d", freq="YS", op="<"):
     thr = threshold_in_units_of(thresh, pr)
     out = generic.threshold_count(pr, op, thr, freq, constrain=("<", "<="))
     return out.assign_attrs(units="d")
+
+
+# ------------------------------------------------------------------ percentile-threshold day counts
+def _percentile_day_count(da, per, freq, bootstrap, op, constrain):
+    """Shared body of tx90p & family -- indices/_multivariate.py:1583-1590:
+    ``thresh = resample_doy(per, da); threshold_count(da, op, thresh, freq)``; the (lat, lon, time)
+    float64 threshold array of the reference is never built: the kernel indexes the per-doy table."""
+    import numpy as np
+
+    from . import _lib, device
+    from .calendar import adjust_table, table_on_device
+    from .generic import _unwrap, _wrap_periods
+    from .field import attrs_of
+
+    code = _lib.op_code(op, constrain)
+    if bootstrap:
+        from .bootstrapping import bootstrap_doy_count
+        return bootstrap_doy_count(da, per, freq, op, constrain)
+    x2d, cell_shape, other, ta = _unwrap(da)
+    table = table_on_device(per, cell_shape, other, x2d.device)
+    table, doy_idx = adjust_table(table, ta)
+    out, _ = device.doy_threshold_count(x2d, ta.period_offsets(freq), doy_idx, table, code)
+    attrs = attrs_of(da)
+    attrs["units"] = "d"
+    return _wrap_periods(da, out, cell_shape, other, ta, freq, attrs, dtype=np.int64)
+
+
+def tx90p(tasmax, tasmax_per, freq="YS", bootstrap=False, op=">"):
+    """Days with daily maximum temperature over the 90th percentile -- indices/_multivariate.py:1534-1590."""
+    return _percentile_day_count(tasmax, tasmax_per, freq, bootstrap, op, (">", ">="))
+
+
+def tx10p(tasmax, tasmax_per, freq="YS", bootstrap=False, op="<"):
+    """indices/_multivariate.py:1593-1650."""
+    return _percentile_day_count(tasmax, tasmax_per, freq, bootstrap, op, ("<", "<="))
+
+
+def tn90p(tasmin, tasmin_per, freq="YS", bootstrap=False, op=">"):
+    """indices/_multivariate.py:1417-1473."""
+    return _percentile_day_count(tasmin, tasmin_per, freq, bootstrap, op, (">", ">="))
+
+
+def tn10p(tasmin, tasmin_per, freq="YS", bootstrap=False, op="<"):
+    """indices/_multivariate.py:1476-1531."""
+    return _percentile_day_count(tasmin, tasmin_per, freq, bootstrap, op, ("<", "<="))
+
+
+def tg90p(tas, tas_per, freq="YS", bootstrap=False, op=">"):
+    """indices/_multivariate.py:1300-1356."""
+    return _percentile_day_count(tas, tas_per, freq, bootstrap, op, (">", ">="))
+
+
+def tg10p(tas, tas_per, freq="YS", bootstrap=False, op="<"):
+    """indices/_multivariate.py:1359-1414."""
+    return _percentile_day_count(tas, tas_per, freq, bootstrap, op, ("<", "<="))
