@@ -180,20 +180,23 @@ int32_t xc_doy_threshold_count_f32(const float* x, int64_t T, int64_t C, int64_t
 
 /* ---------------------------------------------------------------------------------------------
  * a17  percentile bootstrap (Zhang 2005) -- core/bootstrapping.py:81-211, 235-282
- *   x: (T, C) full studied series; base = steps [base_start, base_start + n_base_years*year_len)
- *   (equal-length year blocks: noleap / 360_day, core/bootstrapping.py:264-265).
- *   For every period p nested in in-base year y:
- *     out[p, c] = mean over base years s != y of #{ t in p : x[t] op P^(y<-s)[doy(t)] }
- *   where P^(y<-s) = percentile_doy of the base series with block y replaced by block s.
- *   Periods outside the base are NOT written (use xc_doy_threshold_count_f32).
- *   period_year[p] (int32 host array): base-year ordinal of period p, or -1 when out of base.
+ *   x: (T, C) studied series; the base (climatology) period is the n_base_years equal-length
+ *   year blocks of year_len steps starting at row base_start (noleap / 360_day calendars,
+ *   core/bootstrapping.py:264-265; 365<->366 block conversion is not supported).
+ *   step_period: device int32[n_base_years*year_len], output period index of every base step
+ *   (periods nest in years: freq YS/QS/MS...).  For every period p holding steps of in-base
+ *   year y:
+ *     out[p, c] = mean over base years s != y of #{ t in p : (double)x[t] op P^(y<-s)[doy(t)] }
+ *   where P^(y<-s) = percentile_doy(window, percentile, alpha, beta) of the base series with
+ *   block y replaced by block s.  out is (P, C) float64 and is written for ALL p (periods without
+ *   base steps get 0: the caller fills them with xc_doy_threshold_count_f32, bootstrapping.py:205-207).
+ *   count_scratch: device int32 (P, C).
  * ------------------------------------------------------------------------------------------- */
 int32_t xc_bootstrap_doy_count_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
                                    int64_t base_start, int32_t n_base_years, int32_t year_len,
-                                   const int32_t* period_offsets, const int32_t* period_offsets_host,
-                                   const int32_t* period_year_host, int32_t P,
+                                   const int32_t* step_period, int32_t P,
                                    int32_t window, double percentile, double alpha, double beta,
-                                   int32_t op, double* out, void* stream);
+                                   int32_t op, int32_t* count_scratch, double* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a20  empirical quantile mapping -- xsdba.EmpiricalQuantileMapping (third-party, re-exported

@@ -1,0 +1,269 @@
+// Percentile bootstrap (Zhang et al. 2005) of a day-of-year percentile exceedance count.
+//
+// Replaces core/bootstrapping.py:81-211 (`bootstrap_func`) + 235-282 (`build_bootstrap_year_da`):
+// for every in-base year y and every other base year s the reference rebuilds the base series with
+// block y overwritten by block s, recomputes percentile_doy on it (N*(N-1) full evaluations, each a
+// rolling-construct + sort of the whole base period) and counts year y's exceedances against it.
+//
+// Here (uniform year length L, base = N blocks of L steps):
+//   S(d)      = base sample of day d (W*N values, as in percentile_doy)
+//   R_y(d)    = the <= W values of S(d) that sit in block y   (circular days d-h..d+h of year y)
+//   I_s(d)    = the values of block s at the same positions
+//   M(y,s,d)  = S(d) - R_y(d) + I_s(d)      -- the sample of day d in the altered series
+// so P^(y<-s)(d) is a quantile of "the sorted top list of S(d), minus <= W values, plus <= W values":
+// per (cell, day) the sorted extremes of S(d) are built ONCE (same register/shared-memory machinery
+// as percentile_doy), per year the <= W removals are applied once, and per (y, s) pair only W
+// insertions into a short list and one lerp remain.  Counts are accumulated per output period with
+// integer atomics and divided by N-1 at the end (mean over the N-1 altered series,
+// core/bootstrapping.py:203; numpy's int64 mean is exactly sum/(N-1) in float64).
+#include <type_traits>
+#include <vector>
+
+#include "common.cuh"
+#include "quantile.cuh"
+#include "sortnet.cuh"
+
+namespace xc {
+namespace {
+
+constexpr int kThreads = 128;
+#define XC_NEG_INF (__int_as_float(0xff800000))
+
+template <int K>
+__device__ __forceinline__ void insert_desc(float (&lst)[K], float v) {
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const float hi = fmaxf(lst[k], v);
+    v = fminf(lst[k], v);
+    lst[k] = hi;
+  }
+}
+
+// remove ONE instance of value r from the sorted list (no-op when absent; NaN never matches)
+template <int K>
+__device__ __forceinline__ void remove_one(float (&a)[K], float r) {
+  bool found = false;
+#pragma unroll
+  for (int i = 0; i < K - 1; ++i) {
+    found = found || (a[i] == r);
+    a[i] = found ? a[i + 1] : a[i];
+  }
+  found = found || (a[K - 1] == r);
+  a[K - 1] = found ? XC_NEG_INF : a[K - 1];
+}
+
+// Shared-memory layout per lane (column `lane` of every row):
+//   sring [W-1][KA]  sorted (selection-side, masked) extremes of the W-1 previous day lists
+//   scnt  [W-1]      their valid counts
+//   raw   [W][N]     raw block values x[base + b*L + dd] of the W days of the current window
+template <int KA, int KB, int OP>
+__global__ void __launch_bounds__(kThreads)
+bootstrap_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int64_t base_start, int32_t N, int32_t L,
+                 int32_t W, QuantSpec spec, const int32_t* __restrict__ step_period, int32_t doys_per_chunk,
+                 int32_t* __restrict__ counts) {
+  extern __shared__ float smem[];
+  const int H = W / 2, R = W - 1;
+  const int lane = threadIdx.x;
+  float* sring = smem;
+  int* scnt = reinterpret_cast<int*>(smem + (size_t)R * KA * kThreads);
+  float* raw = smem + (size_t)R * (KA + 1) * kThreads;
+  const int64_t c = (int64_t)blockIdx.x * kThreads + lane;
+  if (c >= C) return;
+  const int d0 = blockIdx.y * doys_per_chunk;
+  const int d1 = min(L, d0 + doys_per_chunk);
+  if (d0 >= d1) return;
+  const bool top = spec.top != 0;
+  const float sgn = top ? 1.f : -1.f;
+  const float* xb = x + base_start * ldx + c;
+
+  // Loads day e (may be < 0 or >= L: the window wraps into the neighbouring year), stores the raw
+  // block values into raw slot `rs`, returns the sorted masked top-KA list + valid count.
+  auto load_day = [&](int e, int rs, float (&lst)[KA], int& n) {
+    const int dd = e < 0 ? e + L : (e >= L ? e - L : e);
+    // block b contributes to S(.) through a step i of year b+1 (e < 0) / b-1 (e >= L) / b
+    const int blo = (e >= L) ? 1 : 0;
+    const int bhi = (e < 0) ? N - 1 : N;
+    n = 0;
+    bool first = true;
+    for (int b0 = 0; b0 < N; b0 += KA) {
+      float v[KA];
+#pragma unroll
+      for (int k = 0; k < KA; ++k) {
+        const int b = b0 + k;
+        float r = XC_NEG_INF;
+        if (b < N) {
+          const float xv = ld_stream(xb + ((int64_t)b * L + dd) * ldx);
+          raw[((size_t)rs * N + b) * kThreads + lane] = xv;
+          const bool ok = (b >= blo) && (b < bhi) && (xv == xv);
+          n += ok ? 1 : 0;
+          r = ok ? sgn * xv : XC_NEG_INF;
+        }
+        v[k] = r;
+      }
+      sort_desc<KA>(v);
+      if (first) {
+#pragma unroll
+        for (int k = 0; k < KA; ++k) lst[k] = v[k];
+        first = false;
+      } else {
+        merge_top_desc<KA>(lst, v);
+      }
+    }
+  };
+
+  float ynew[KA];
+  int nnew;
+  // prologue: days e = d0-H .. d0+H-1 ; sorted slot = (e - (d0-H)) mod R, raw slot = (e - (d0-H)) mod W
+  for (int s = 0; s < R; ++s) {
+    load_day(d0 - H + s, s % W, ynew, nnew);
+#pragma unroll
+    for (int k = 0; k < KA; ++k) sring[((size_t)s * KA + k) * kThreads + lane] = ynew[k];
+    scnt[s * kThreads + lane] = nnew;
+  }
+  int oldest = 0;     // sorted-ring slot of day d-H
+  int raw_first = 0;  // raw-ring slot of day d-H
+  for (int d = d0; d < d1; ++d) {
+    const int raw_new = (raw_first + W - 1) % W;
+    load_day(d + H, raw_new, ynew, nnew);
+    float tl[KA];
+#pragma unroll
+    for (int k = 0; k < KA; ++k) tl[k] = ynew[k];
+    int nbase = nnew;
+#pragma unroll 1
+    for (int s = 0; s < R; ++s) {
+      const float* slot = sring + (size_t)s * KA * kThreads + lane;
+#pragma unroll
+      for (int k = 0; k < KA; ++k) tl[k] = fmaxf(tl[k], slot[(size_t)(KA - 1 - k) * kThreads]);
+      bitonic_finish_desc<KA>(tl);
+      nbase += scnt[s * kThreads + lane];
+    }
+    // ---- every in-base year y: remove its window values, then try every other year s
+    const int raw_mid = (raw_first + H) % W;
+#pragma unroll 1
+    for (int y = 0; y < N; ++y) {
+      float a[KA];
+#pragma unroll
+      for (int k = 0; k < KA; ++k) a[k] = tl[k];
+      int na = nbase;
+      unsigned vmask = 0;  // window offsets whose position in block y belongs to S(d)
+#pragma unroll 1
+      for (int k = 0; k < W; ++k) {
+        const int e = d - H + k;
+        const bool valid = (e < 0) ? (y + 1 < N) : ((e >= L) ? (y >= 1) : true);
+        if (!valid) continue;
+        vmask |= 1u << k;
+        const float r = raw[((size_t)((raw_first + k) % W) * N + y) * kThreads + lane];
+        if (r == r) {
+          remove_one<KA>(a, sgn * r);
+          na -= 1;
+        }
+      }
+      const float xq = raw[((size_t)raw_mid * N + y) * kThreads + lane];
+      int cnt = 0;
+#pragma unroll 1
+      for (int s = 0; s < N; ++s) {
+        if (s == y) continue;
+        float bl[KB];
+#pragma unroll
+        for (int k = 0; k < KB; ++k) bl[k] = a[k];
+        int nm = na;
+#pragma unroll 1
+        for (int k = 0; k < W; ++k) {
+          if (!((vmask >> k) & 1u)) continue;
+          const float v = raw[((size_t)((raw_first + k) % W) * N + s) * kThreads + lane];
+          const bool ok = (v == v);
+          nm += ok ? 1 : 0;
+          insert_desc<KB>(bl, ok ? sgn * v : XC_NEG_INF);
+        }
+        const double p = finalize_quantile<KB>(bl, nm, spec);
+        cnt += cmpd<OP>((double)xq, p) ? 1 : 0;
+      }
+      if (cnt) atomicAdd(counts + (int64_t)step_period[y * L + d] * C + c, cnt);
+    }
+    // rotate the rings
+#pragma unroll
+    for (int k = 0; k < KA; ++k) sring[((size_t)oldest * KA + k) * kThreads + lane] = ynew[k];
+    scnt[oldest * kThreads + lane] = nnew;
+    oldest = (oldest + 1 == R) ? 0 : oldest + 1;
+    raw_first = (raw_first + 1 == W) ? 0 : raw_first + 1;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bootstrap_finish_kernel(const int32_t* __restrict__ counts, int64_t n, double denom, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (double)counts[i] / denom;
+}
+
+template <int KA, int KB>
+int32_t launch_bootstrap(int32_t op, const float* x, int64_t C, int64_t ldx, int64_t base_start, int32_t N,
+                         int32_t L, int32_t W, const QuantSpec& spec, const int32_t* step_period, int32_t* counts,
+                         cudaStream_t st) {
+  const int64_t cblocks = (C + kThreads - 1) / kThreads;
+  int chunks = (int)((148 * 6 + cblocks - 1) / cblocks);
+  chunks = chunks < 1 ? 1 : chunks;
+  int per = (L + chunks - 1) / chunks;
+  if (per < 4 * W) per = 4 * W;
+  if (per > L) per = L;
+  chunks = (L + per - 1) / per;
+  const size_t smem = ((size_t)(W - 1) * (KA + 1) + (size_t)W * N) * kThreads * 4;
+  if (smem > 227 * 1024) {
+    set_error("bootstrap: %d base years x window %d need %zu bytes of shared memory per block", N, W, smem);
+    return XC_ERR_UNSUPPORTED;
+  }
+  dim3 grid((unsigned)cblocks, (unsigned)chunks, 1);
+  return dispatch_op(op, [&](auto OPC) -> int32_t {
+    constexpr int OP = decltype(OPC)::value;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(bootstrap_kernel<KA, KB, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(bootstrap_kernel)");
+    }
+    bootstrap_kernel<KA, KB, OP><<<grid, kThreads, smem, st>>>(x, C, ldx, base_start, N, L, W, spec, step_period, per,
+                                                               counts);
+    return launch_status("bootstrap_kernel");
+  });
+}
+
+}  // namespace
+}  // namespace xc
+
+using namespace xc;
+
+extern "C" int32_t xc_bootstrap_doy_count_f32(const float* x, int64_t T, int64_t C, int64_t ldx, int64_t base_start,
+                                              int32_t n_base_years, int32_t year_len, const int32_t* step_period,
+                                              int32_t P, int32_t window, double percentile, double alpha,
+                                              double beta, int32_t op, int32_t* count_scratch, double* out,
+                                              void* stream) {
+  XC_REQUIRE(x && step_period && count_scratch && out, "null pointer argument");
+  XC_REQUIRE(T > 0 && C > 0 && ldx >= C && P > 0, "bad shape");
+  XC_REQUIRE(n_base_years >= 2 && year_len >= 1, "bootstrap needs at least two base years");
+  XC_REQUIRE(base_start >= 0 && base_start + (int64_t)n_base_years * year_len <= T, "base period outside the series");
+  XC_REQUIRE(window >= 1 && window % 2 == 1 && window <= 31 && window <= year_len, "window must be odd and <= 31");
+  XC_REQUIRE(op == XC_OP_GT || op == XC_OP_GE || op == XC_OP_LT || op == XC_OP_LE,
+             "Operation `%d` not permitted for indice.", op);
+  cudaStream_t st = (cudaStream_t)stream;
+  QuantSpec spec;
+  const int need = plan_quantile(percentile, alpha, beta, n_base_years * window, &spec);
+  XC_CHECK_CUDA(cudaMemsetAsync(count_scratch, 0, (size_t)P * C * 4, st));
+  int32_t e;
+  if (need > 0 && need <= 8 && need + window <= 16)
+    e = launch_bootstrap<16, 8>(op, x, C, ldx, base_start, n_base_years, year_len, window, spec, step_period,
+                                count_scratch, st);
+  else if (need > 0 && need <= 16 && need + window <= 32)
+    e = launch_bootstrap<32, 16>(op, x, C, ldx, base_start, n_base_years, year_len, window, spec, step_period,
+                                 count_scratch, st);
+  else if (need > 0 && need + window <= 32)
+    e = launch_bootstrap<32, 32>(op, x, C, ldx, base_start, n_base_years, year_len, window, spec, step_period,
+                                 count_scratch, st);
+  else {
+    set_error("bootstrap: percentile %g of %d samples needs %d order statistics (+%d removals); at most 32 are kept",
+              percentile, n_base_years * window, need, window);
+    return XC_ERR_UNSUPPORTED;
+  }
+  if (e) return e;
+  const int64_t n = (int64_t)P * C;
+  bootstrap_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(count_scratch, n, (double)(n_base_years - 1),
+                                                                      out);
+  return launch_status("bootstrap_finish_kernel");
+}

@@ -89,23 +89,55 @@ percentile_doy_generic_kernel(const float* __restrict__ x, int64_t T, int64_t C,
 // [-h, L+h) (the window reaches into the neighbouring year, core/calendar.py:448 pads only at the
 // two ends of the SERIES).
 template <int K>
-__device__ __forceinline__ void load_day_list(const float* __restrict__ col, int64_t ldx, int T, int L, int N,
-                                              int e, bool top, float (&lst)[K], int& n) {
+__device__ __forceinline__ void load_day_list(const float* __restrict__ x, int64_t c, int64_t ldx, int T, int L,
+                                              int N, int e, bool top, float (&lst)[K], int& n) {
   n = 0;
-#pragma unroll
-  for (int k = 0; k < K; ++k) lst[k] = XC_NEG_INF;
+  // rows y*L + e that exist: e < 0 reaches into the previous year (no year -1), e >= L into the next
+  const int ylo = (e < 0) ? 1 : 0;
+  const int yhi = (e >= L) ? N - 1 : N;
   bool first = true;
   for (int y0 = 0; y0 < N; y0 += K) {
     float v[K];
+    // byte pointer of (row y0*L + e, cell c), advanced by one year per load: one 64-bit add each
+    const char* p = reinterpret_cast<const char*>(x + ((int64_t)y0 * L + e) * ldx + c);
+    const int64_t ystride = (int64_t)L * ldx * 4;
+    int nv;
+    if (y0 >= ylo && y0 + K <= yhi) {  // whole chunk in range (the common case): unpredicated loads
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      const int y = y0 + k;
-      const int row = y * L + e;
-      const bool ok = (y < N) && (row >= 0) && (row < T);
-      float r = XC_NEG_INF;
-      if (ok) r = prep(ld_stream(col + (int64_t)row * ldx), top, n);
-      v[k] = r;
+      for (int k = 0; k < K; ++k) {
+        v[k] = ld_stream(reinterpret_cast<const float*>(p));
+        p += ystride;
+      }
+      nv = K;
+    } else {
+      nv = 0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int y = y0 + k;
+        const bool ok = (y >= ylo) && (y < yhi);
+        v[k] = ok ? ld_stream(reinterpret_cast<const float*>(p)) : XC_NEG_INF;
+        nv += ok ? 1 : 0;
+        p += ystride;
+      }
     }
+    if (!top) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) v[k] = -v[k];
+    }
+    // NaN handling off the fast path: one predicate-accumulating compare per value, and only a
+    // lane that actually saw a NaN pays for counting / replacing them (NaN -> -inf, never selected)
+    bool any_nan = false;
+#pragma unroll
+    for (int k = 0; k < K; ++k) any_nan = any_nan || (v[k] != v[k]);
+    if (any_nan) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const bool bad = (v[k] != v[k]);
+        nv -= bad ? 1 : 0;
+        v[k] = bad ? XC_NEG_INF : v[k];
+      }
+    }
+    n += nv;
     sort_desc<K>(v);
     if (first) {
 #pragma unroll
@@ -117,46 +149,60 @@ __device__ __forceinline__ void load_day_list(const float* __restrict__ col, int
   }
 }
 
-template <int K, int W>
+// Per-lane ring of the W-1 most recent day lists in SHARED memory, laid out [slot][k][lane] so that
+// a warp's access to element k of a slot is one conflict-free 128-byte wavefront (each lane only
+// ever touches its own column).  Keeping the ring out of the register file lets ~24 warps per SM
+// stay resident (the kernel is latency-bound otherwise) and keeps the code small enough for the
+// instruction cache (one copy of the sorting network and of the merge, no unrolling over W).
+template <int K>
 __global__ void __launch_bounds__(kThreads)
 percentile_doy_uniform_kernel(const float* __restrict__ x, int32_t T, int64_t C, int64_t ldx, int32_t L,
-                              int32_t N, QuantSpec spec, int32_t doys_per_chunk, double* __restrict__ out) {
-  constexpr int H = W / 2;
-  const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (c >= C) return;
+                              int32_t N, int32_t W, QuantSpec spec, int32_t doys_per_chunk,
+                              double* __restrict__ out) {
+  extern __shared__ float smem[];
+  const int H = W / 2;
+  const int R = W - 1;  // ring slots
+  float* ring = smem;                                        // [R][K][kThreads]
+  int* rcnt = reinterpret_cast<int*>(smem + (size_t)R * K * kThreads);  // [R][kThreads]
+  const int lane = threadIdx.x;
+  const int64_t c = (int64_t)blockIdx.x * kThreads + lane;
+  if (c >= C) return;  // no block-level synchronisation below: every lane owns its smem column
   const int d0 = blockIdx.y * doys_per_chunk;
   const int d1 = min(L, d0 + doys_per_chunk);
   if (d0 >= d1) return;
-  const float* col = x + c;
   const bool top = spec.top != 0;
 
-  // ring of W day lists; list of day e lives in slot (e - (d0 - H)) mod W
-  float ring[W][K];
-  int cnt[W];
+  float ynew[K];
+  int nnew;
+  // prologue: day lists e = d0-H .. d0+H-1 -> ring slots 0..R-1 (slot = (e - (d0-H)) mod R)
+  for (int s = 0; s < R; ++s) {
+    load_day_list<K>(x, c, ldx, T, L, N, d0 - H + s, top, ynew, nnew);
 #pragma unroll
-  for (int s = 0; s < W - 1; ++s) load_day_list<K>(col, ldx, T, L, N, d0 - H + s, top, ring[s], cnt[s]);
-
-  for (int d = d0; d < d1; d += W) {
+    for (int k = 0; k < K; ++k) ring[((size_t)s * K + k) * kThreads + lane] = ynew[k];
+    rcnt[s * kThreads + lane] = nnew;
+  }
+  int oldest = 0;  // slot holding day list e = d-H
+  for (int d = d0; d < d1; ++d) {
+    load_day_list<K>(x, c, ldx, T, L, N, d + H, top, ynew, nnew);
+    float acc[K];
 #pragma unroll
-    for (int ph = 0; ph < W; ++ph) {
-      const int dd = d + ph;
-      if (dd < d1) {
-        constexpr int kDummy = 0;
-        (void)kDummy;
-        const int slot_new = (ph + W - 1) % W;  // compile-time after unrolling
-        load_day_list<K>(col, ldx, T, L, N, dd + H, top, ring[slot_new], cnt[slot_new]);
-        float acc[K];
+    for (int k = 0; k < K; ++k) acc[k] = ynew[k];
+    int n = nnew;
+#pragma unroll 1
+    for (int s = 0; s < R; ++s) {
+      const float* slot = ring + (size_t)s * K * kThreads + lane;
+      // acc <- top-K of (acc U slot): max against the reversed list, then bitonic clean-up
 #pragma unroll
-        for (int k = 0; k < K; ++k) acc[k] = ring[0][k];
-        int n = cnt[0];
-#pragma unroll
-        for (int s = 1; s < W; ++s) {
-          merge_top_desc<K>(acc, ring[s]);
-          n += cnt[s];
-        }
-        out[(int64_t)dd * C + c] = finalize_quantile<K>(acc, n, spec);
-      }
+      for (int k = 0; k < K; ++k) acc[k] = fmaxf(acc[k], slot[(size_t)(K - 1 - k) * kThreads]);
+      bitonic_finish_desc<K>(acc);
+      n += rcnt[s * kThreads + lane];
     }
+    out[(int64_t)d * C + c] = finalize_quantile<K>(acc, n, spec);
+    // the new list replaces the oldest one
+#pragma unroll
+    for (int k = 0; k < K; ++k) ring[((size_t)oldest * K + k) * kThreads + lane] = ynew[k];
+    rcnt[oldest * kThreads + lane] = nnew;
+    oldest = (oldest + 1 == R) ? 0 : oldest + 1;
   }
 }
 
@@ -265,19 +311,24 @@ int32_t launch_generic(const float* x, int64_t T, int64_t C, int64_t ldx, const 
   return launch_status("percentile_doy_generic_kernel");
 }
 
-template <int K, int W>
-int32_t launch_uniform(const float* x, int64_t T, int64_t C, int64_t ldx, int32_t L, int32_t N,
+template <int K>
+int32_t launch_uniform(const float* x, int64_t T, int64_t C, int64_t ldx, int32_t L, int32_t N, int32_t W,
                        const QuantSpec& spec, double* out, cudaStream_t st) {
   const int64_t cblocks = (C + kThreads - 1) / kThreads;
   int chunks = (int)((148 * 12 + cblocks - 1) / cblocks);
   chunks = chunks < 1 ? 1 : chunks;
   int per = (L + chunks - 1) / chunks;
-  if (per < 8 * W) per = 8 * W;  // keep the halo overhead (2h extra day lists per chunk) small
+  if (per < 8 * W) per = 8 * W;  // keep the halo overhead (W-1 extra day lists per chunk) small
   if (per > L) per = L;
-  per = ((per + W - 1) / W) * W;
   chunks = (L + per - 1) / per;
+  const size_t smem = (size_t)(W - 1) * (K + 1) * kThreads * 4;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(percentile_doy_uniform_kernel<K>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(percentile_doy_uniform_kernel)");
+  }
   dim3 grid((unsigned)cblocks, (unsigned)chunks, 1);
-  percentile_doy_uniform_kernel<K, W><<<grid, kThreads, 0, st>>>(x, (int32_t)T, C, ldx, L, N, spec, per, out);
+  percentile_doy_uniform_kernel<K><<<grid, kThreads, smem, st>>>(x, (int32_t)T, C, ldx, L, N, W, spec, per, out);
   return launch_status("percentile_doy_uniform_kernel");
 }
 
@@ -339,13 +390,11 @@ extern "C" int32_t xc_percentile_doy_f32(const float* x, int64_t T, int64_t C, i
     }
     double* o = out + (int64_t)ip * n_doy * C;
     int32_t e;
-    if (uniform && window == 5 && need <= 16) {
-      e = need <= 8 ? launch_uniform<8, 5>(x, T, C, ldx, n_doy, n_years, spec, o, st)
-                    : launch_uniform<16, 5>(x, T, C, ldx, n_doy, n_years, spec, o, st);
-    } else if (uniform && window == 3 && need <= 16) {
-      e = launch_uniform<16, 3>(x, T, C, ldx, n_doy, n_years, spec, o, st);
-    } else if (uniform && window == 7 && need <= 16) {
-      e = launch_uniform<16, 7>(x, T, C, ldx, n_doy, n_years, spec, o, st);
+    const size_t smem_need = (size_t)(window - 1) * ((need <= 8 ? 8 : need <= 16 ? 16 : 32) + 1) * kThreads * 4;
+    if (uniform && window >= 3 && need <= 32 && smem_need <= 200 * 1024) {
+      e = need <= 8    ? launch_uniform<8>(x, T, C, ldx, n_doy, n_years, window, spec, o, st)
+          : need <= 16 ? launch_uniform<16>(x, T, C, ldx, n_doy, n_years, window, spec, o, st)
+                       : launch_uniform<32>(x, T, C, ldx, n_doy, n_years, window, spec, o, st);
     } else {
       if (uniform && pos_d == nullptr) {  // uniform calendar but no fast instantiation: use the generic kernel
         const int64_t nbytes = (int64_t)pos.size() * 4;

@@ -8,11 +8,6 @@ extern "C" int32_t xc_rolling_period_reduce_f32(const float*, int64_t, int64_t, 
                                                 int32_t, int32_t, int32_t, int32_t, float*, void*) {
   XC_STUB("xc_rolling_period_reduce_f32");
 }
-extern "C" int32_t xc_bootstrap_doy_count_f32(const float*, int64_t, int64_t, int64_t, int64_t, int32_t, int32_t,
-                                              const int32_t*, const int32_t*, const int32_t*, int32_t, int32_t, double,
-                                              double, double, int32_t, double*, void*) {
-  XC_STUB("xc_bootstrap_doy_count_f32");
-}
 extern "C" int64_t xc_eqm_train_workspace_bytes(int64_t, int64_t, int32_t) { return 0; }
 extern "C" int32_t xc_eqm_train_f32(const float*, const float*, int64_t, int64_t, int64_t, int32_t, int32_t, float*,
                                     float*, void*, int64_t, void*) {

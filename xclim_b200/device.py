@@ -204,3 +204,18 @@ def period_runstat_host(x_host, poff, op_code, thr, reducer_code, window, cmp_f6
                                          valid_host.data_ptr() if want_valid else None, workspace.data_ptr(),
                                          workspace.numel()))
     return out_host, (valid_host if want_valid else None), workspace
+
+
+def bootstrap_doy_count(x2d, base_start, n_base_years, year_len, step_period, P, window, percentile, alpha, beta,
+                        op_code):
+    """(P, C) float64 bootstrapped exceedance counts for the in-base periods (0 elsewhere)."""
+    T, C = x2d.shape
+    sp = dev_ints(step_period, np.int32, x2d.device)
+    assert sp.numel() == n_base_years * year_len
+    scratch = torch.empty((P, C), dtype=torch.int32, device=x2d.device)
+    out = torch.empty((P, C), dtype=torch.float64, device=x2d.device)
+    check(load().xc_bootstrap_doy_count_f32(x2d.data_ptr(), T, C, x2d.stride(0), int(base_start), int(n_base_years),
+                                            int(year_len), sp.data_ptr(), P, int(window), float(percentile),
+                                            float(alpha), float(beta), op_code, scratch.data_ptr(), out.data_ptr(),
+                                            current_stream_ptr()))
+    return out
