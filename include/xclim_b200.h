@@ -130,6 +130,19 @@ int32_t xc_rolling_period_reduce_f32(const float* x, int64_t T, int64_t C, int64
                                      int32_t stat, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * a5+a6  spell statistics for spells defined by a rolling window (window > 1)
+ *   replaces generic.spell_mask (indices/generic.py:434-540: a step is in a spell iff it belongs
+ *   to at least one block of `window` consecutive steps, fully inside the series, whose
+ *   window_stat (sum/mean/min/max, NaN if the block holds a NaN) satisfies `op thr`) followed by
+ *   generic._spell_length_statistics (:543-585: run statistics of that mask per period with
+ *   window 1).  thr is compared in float32 (Python-float threshold).  out (P, C) float32.
+ * ------------------------------------------------------------------------------------------- */
+int32_t xc_spell_runstat_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                             const int32_t* period_offsets, int32_t P,
+                             int32_t window, int32_t window_stat, int32_t op, double thr,
+                             int32_t reducer, int32_t resample_before_rl, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * a14+a15  percentile_doy -- core/calendar.py:395-494 with the quantile of
  *   core/utils.py:279-557 (`calc_perc` -> `_nan_quantile`, Hyndman-Fan alpha/beta).
  *   x: (T, C) float32 base-period series (device).  doy_index_host / year_index_host: HOST int16

@@ -1,0 +1,125 @@
+"""GPU parity: rolling+resample, rolling-window spells, empirical quantile mapping."""
+import numpy as np
+import pytest
+
+from oracle import xclim_oracle as O
+from xb_helpers import make_field
+
+pytestmark = pytest.mark.gpu
+
+
+def _pr(rng, T, shape, nan_frac=0.01):
+    x = rng.gamma(0.4, 6.0, size=(T,) + shape).astype(np.float32)
+    x[rng.random(x.shape) < 0.45] = 0.0
+    x = (np.round(x * 4) / 4).astype(np.float32)
+    x[rng.random(x.shape) < nan_frac] = np.nan
+    return x
+
+
+@pytest.mark.parametrize("window,center,wop,op", [(3, False, "sum", "max"), (5, True, "mean", "max"),
+                                                  (14, False, "mean", "min"), (7, True, "max", "mean"),
+                                                  (2, False, "min", "sum")])
+def test_rolling_resample(cuda, window, center, wop, op):
+    from xclim_b200 import generic
+    rng = np.random.default_rng(41)
+    x = _pr(rng, 800, (5, 6))
+    da = make_field(x, "2000-01-01", units="mm/d")
+    for freq in ("YS", "MS"):
+        got = generic.select_rolling_resample_op(da, op, window, window_center=center, window_op=wop, freq=freq)
+        exp = O.select_rolling_resample_op(x.astype(np.float64), op, window, da.time.period_offsets(freq),
+                                           window_center=center, window_op=wop)
+        np.testing.assert_allclose(got.values, exp, rtol=1e-5, equal_nan=True)  # float reductions: 1e-5
+
+
+def test_rolling_reference_known_answers(cuda):
+    """tests/test_generic.py:35-67 (values) and max_n_day_precipitation_amount."""
+    from xclim_b200 import generic, indices
+    q = make_field(np.arange(1, 366 + 365 + 365 + 1, dtype=np.float32), "2000-01-01", units="m3 s-1")
+    o = generic.select_rolling_resample_op(q, "max", window=14, window_center=False, window_op="mean")
+    np.testing.assert_array_equal(o.values, [np.mean(np.arange(353, 367)), np.mean(np.arange(353 + 365, 367 + 365)),
+                                             np.mean(np.arange(353 + 730, 367 + 730))])
+    assert o.attrs["units"] == "m3 s-1"
+    o = generic.select_rolling_resample_op(q, "max", window=3, window_center=True, window_op="sum", freq="MS")
+    np.testing.assert_array_equal(o.values[:2], [30 + 31 + 32, 59 + 60 + 61])
+    pr = np.zeros(365, np.float32); pr[10:13] = [5, 7, 2]
+    out = indices.max_n_day_precipitation_amount(make_field(pr, "2001-01-01", units="mm/d"), window=2)
+    assert out.values[0] == 12 and out.attrs["units"] == "mm"
+
+
+@pytest.mark.parametrize("window,winred,op,thr", [(3, "min", ">=", 1.0), (3, "max", "<", 1.0), (5, "sum", "<", 3.0),
+                                                  (2, "mean", ">=", 2.0), (7, "sum", ">=", 20.0)])
+@pytest.mark.parametrize("before", [True, False])
+def test_spell_length_statistics_windows(cuda, window, winred, op, thr, before):
+    from xclim_b200 import generic
+    rng = np.random.default_rng(42)
+    x = _pr(rng, 365 * 2 + 60, (4, 5))
+    da = make_field(x, "2001-01-01", units="mm/d")
+    for freq in ("YS", "MS"):
+        poff = da.time.period_offsets(freq)
+        for red in ("max", "sum", "count"):
+            got = generic.spell_length_statistics(da, thr, window, winred, op, red, freq, resample_before_rl=before)
+            exp = O.spell_length_statistics(x, thr, window, winred, op, red, poff, resample_before_rl=before)
+            np.testing.assert_array_equal(got.values, exp, err_msg=f"{window} {winred} {op} {red} {freq} {before}")
+
+
+def test_spell_mask_reference_truth_tables(cuda):
+    """tests/test_generic.py:702-713 through the statistics (total spell length == number of True)."""
+    from xclim_b200 import generic
+    data = make_field(np.array([0, 1, 2, 3, 2, 1, 0, 0], np.float32), "2001-01-01", units="")
+    for window, red, op, thr, mask in [(3, "min", ">=", 2, [0, 0, 1, 1, 1, 0, 0, 0]),
+                                       (3, "max", ">=", 2, [1, 1, 1, 1, 1, 1, 1, 0]),
+                                       (2, "mean", ">=", 2, [0, 0, 1, 1, 1, 0, 0, 0])]:
+        out = generic.spell_length_statistics(data, thr, window, red, op, "sum", "YS")
+        assert out.values[0] == sum(mask)
+        np.testing.assert_array_equal(O.spell_mask(data.values, window, red, op, thr), np.array(mask, bool))
+
+
+@pytest.mark.parametrize("pr,thresh1,thresh2,window,outs", [
+    ([1.01] * 6 + [0.01] * 3 + [0.51] * 2 + [0.75] * 2 + [0.51] + [0.01] * 3 + [1.01] * 3, 3, 3, 7, (1, 12, 20, 12, 20)),
+    ([0.01] * 6 + [1.01] * 3 + [0.51] * 2 + [0.75] * 2 + [0.51] + [0.01] * 3 + [0.01] * 3, 3, 3, 7, (2, 18, 20, 10, 20)),
+    ([3.01] * 358 + [0.99] * 14 + [3.01] * 358, 1, 14, 14, (0, 7, 7, 7, 7)),
+])
+def test_dry_spell_reference_known_answers(cuda, pr, thresh1, thresh2, window, outs):
+    """tests/test_indices.py:4069-4112 (rtol=1e-1 as in the reference)."""
+    from xclim_b200 import indices
+    da = make_field(np.array(pr, np.float32), "1981-01-01", units="mm/day")
+    ev, tds, tdm, mds, mdm = outs
+    np.testing.assert_allclose(indices.dry_spell_frequency(da, thresh=f"{thresh1} mm", window=window).values[0], ev,
+                               rtol=1e-1)
+    np.testing.assert_allclose(indices.dry_spell_total_length(da, thresh=f"{thresh2} mm", window=window,
+                                                              op="sum").values[0], tds, rtol=1e-1)
+    np.testing.assert_allclose(indices.dry_spell_total_length(da, thresh=f"{thresh1} mm", window=window,
+                                                              op="max").values[0], tdm, rtol=1e-1)
+    np.testing.assert_allclose(indices.dry_spell_max_length(da, thresh=f"{thresh2} mm", window=window,
+                                                            op="sum").values[0], mds, rtol=1e-1)
+    np.testing.assert_allclose(indices.dry_spell_max_length(da, thresh=f"{thresh1} mm", window=window,
+                                                            op="max").values[0], mdm, rtol=1e-1)
+
+
+@pytest.mark.parametrize("kind,interp", [("+", "linear"), ("+", "nearest"), ("*", "linear")])
+def test_eqm_train_adjust(cuda, kind, interp):
+    """EQM vs the numpy restatement (PARITY UNPINNED against xsdba itself): 1e-5 relative."""
+    from xclim_b200 import sdba
+    rng = np.random.default_rng(43)
+    T, shape = 2000, (3, 4)
+    ref = (285 + 6 * rng.standard_normal((T,) + shape)).astype(np.float32)
+    hist = (286.5 + 7 * rng.standard_normal((T,) + shape)).astype(np.float32)
+    sim = (288.5 + 7 * rng.standard_normal((T,) + shape)).astype(np.float32)
+    hist[rng.random(hist.shape) < 0.01] = np.nan
+    sim[rng.random(sim.shape) < 0.01] = np.nan
+    ref[:, 0, 0] = np.nan   # untrainable cell -> NaN output
+    f = lambda a: make_field(a, "1981-01-01", calendar="noleap", units="K")
+    eqm = sdba.EmpiricalQuantileMapping.train(f(ref), f(hist), nquantiles=20, kind=kind, group="time")
+    af_o, hq_o = O.eqm_train(ref, hist, 20, kind)
+    ds = eqm.ds
+    np.testing.assert_allclose(ds["hist_q"].values, hq_o, rtol=1e-5, equal_nan=True)
+    np.testing.assert_allclose(ds["af"].values, af_o, rtol=1e-4, atol=1e-5, equal_nan=True)
+    scen = eqm.adjust(f(sim), interp=interp, extrapolation="constant")
+    exp = O.eqm_adjust(sim, ds["af"].values, ds["hist_q"].values, kind, interp)
+    assert scen.values.dtype == np.float32 and scen.values.shape == sim.shape
+    np.testing.assert_allclose(scen.values, exp, rtol=1e-5, equal_nan=True)
+    # property (tests/test_xsdba.py:112-155 spirit): adjusting hist itself maps its quantiles onto ref's
+    if kind == "+" and interp == "linear":
+        back = eqm.adjust(f(hist), interp="linear").values[:, 1, 1]
+        q = np.nanquantile(back, [0.25, 0.5, 0.75])
+        np.testing.assert_allclose(q, np.nanquantile(ref[:, 1, 1], [0.25, 0.5, 0.75]), atol=0.15)

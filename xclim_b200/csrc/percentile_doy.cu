@@ -115,7 +115,8 @@ __device__ __forceinline__ void load_day_list(const float* __restrict__ x, int64
       for (int k = 0; k < K; ++k) {
         const int y = y0 + k;
         const bool ok = (y >= ylo) && (y < yhi);
-        v[k] = ok ? ld_stream(reinterpret_cast<const float*>(p)) : XC_NEG_INF;
+        // rows that do not exist are +/-inf BEFORE the bottom-side negation below turns them into -inf
+        v[k] = ok ? ld_stream(reinterpret_cast<const float*>(p)) : (top ? XC_NEG_INF : -XC_NEG_INF);
         nv += ok ? 1 : 0;
         p += ystride;
       }

@@ -219,3 +219,45 @@ def bootstrap_doy_count(x2d, base_start, n_base_years, year_len, step_period, P,
                                             float(alpha), float(beta), op_code, scratch.data_ptr(), out.data_ptr(),
                                             current_stream_ptr()))
     return out
+
+
+# ------------------------------------------------------------------------------------ rolling / spells
+def rolling_period_reduce(x2d, poff, window, window_stat_code, center, stat_code):
+    T, C = x2d.shape
+    P = len(poff) - 1
+    poff_d = dev_ints(poff, np.int32, x2d.device)
+    out = torch.empty((P, C), dtype=torch.float32, device=x2d.device)
+    check(load().xc_rolling_period_reduce_f32(x2d.data_ptr(), T, C, x2d.stride(0), poff_d.data_ptr(), P, int(window),
+                                              window_stat_code, int(bool(center)), stat_code, out.data_ptr(),
+                                              current_stream_ptr()))
+    return out
+
+
+def spell_runstat(x2d, poff, window, window_stat_code, op_code, thr, reducer_code, resample_before_rl=True):
+    T, C = x2d.shape
+    P = len(poff) - 1
+    poff_d = dev_ints(poff, np.int32, x2d.device)
+    out = torch.empty((P, C), dtype=torch.float32, device=x2d.device)
+    check(load().xc_spell_runstat_f32(x2d.data_ptr(), T, C, x2d.stride(0), poff_d.data_ptr(), P, int(window),
+                                      window_stat_code, op_code, float(thr), reducer_code,
+                                      int(bool(resample_before_rl)), out.data_ptr(), current_stream_ptr()))
+    return out
+
+
+# ------------------------------------------------------------------------------------ quantile mapping
+def eqm_train(ref2d, hist2d, nq, kind_code):
+    T, C = ref2d.shape
+    assert hist2d.shape == ref2d.shape and ref2d.stride(0) == hist2d.stride(0)
+    af = torch.empty((nq, C), dtype=torch.float32, device=ref2d.device)
+    hq = torch.empty((nq, C), dtype=torch.float32, device=ref2d.device)
+    check(load().xc_eqm_train_f32(ref2d.data_ptr(), hist2d.data_ptr(), T, C, ref2d.stride(0), int(nq), kind_code,
+                                  af.data_ptr(), hq.data_ptr(), None, 0, current_stream_ptr()))
+    return af, hq
+
+
+def eqm_adjust(sim2d, af, hq, kind_code, interp_code):
+    T, C = sim2d.shape
+    scen = torch.empty((T, C), dtype=torch.float32, device=sim2d.device)
+    check(load().xc_eqm_adjust_f32(sim2d.data_ptr(), T, C, sim2d.stride(0), af.data_ptr(), hq.data_ptr(),
+                                   af.shape[0], kind_code, interp_code, scen.data_ptr(), current_stream_ptr()))
+    return scen

@@ -150,3 +150,23 @@ def spell_length_statistics(data, threshold, window, win_reducer, op, spell_redu
         attrs["units"] = "" if sr == "count" else "d"
         outs.append(_wrap_periods(data, out, cell_shape, other, ta, freq, attrs, dtype=np.float32))
     return outs[0] if len(outs) == 1 else tuple(outs)
+
+
+# --------------------------------------------------------------------------------- a4 rolling + resample
+def select_rolling_resample_op(da, op, window, window_center=True, window_op="mean", freq="YS", out_units=None,
+                               **indexer):
+    """Rolling window statistic, then per-period reduction -- indices/generic.py:128-174."""
+    if indexer:
+        raise NotImplementedError("select_time indexers are outside the B200 hot path (SURVEY.md section 8f)")
+    wop = window_op.replace("integral", "sum")
+    if wop not in ("sum", "mean", "min", "max"):
+        raise NotImplementedError(f"rolling window_op {window_op!r} is not supported by the B200 hot path")
+    if not isinstance(op, str) or op not in _lib.STATS:
+        raise NotImplementedError(f"resample op {op!r} is not supported by the B200 hot path")
+    x2d, cell_shape, other, ta = _unwrap(da)
+    out = device.rolling_period_reduce(x2d, ta.period_offsets(freq), window, _lib.STATS[wop], window_center,
+                                       _lib.STATS[op])
+    attrs = attrs_of(da)
+    if out_units is not None:
+        attrs["units"] = out_units
+    return _wrap_periods(da, out, cell_shape, other, ta, freq, attrs)

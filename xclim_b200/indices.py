@@ -93,3 +93,49 @@ def tg90p(tas, tas_per, freq="YS", bootstrap=False, op=">"):
 def tg10p(tas, tas_per, freq="YS", bootstrap=False, op="<"):
     """indices/_multivariate.py:1359-1414."""
     return _percentile_day_count(tas, tas_per, freq, bootstrap, op, ("<", "<="))
+
+
+# ------------------------------------------------------------------ rolling / spell families
+def max_n_day_precipitation_amount(pr, window=1, freq="YS"):
+    """Highest precipitation amount cumulated over an n-day moving window -- indices/_simple.py:485-525:
+    ``rate2amount(pr).rolling(time=window).sum(skipna=False).resample(time=freq).max()``.  The input
+    is expected in mm/d (rate2amount is then the identity factor 1 d, core/units.py:853-937)."""
+    from . import _lib, device
+    from .field import attrs_of
+    from .generic import _unwrap, _wrap_periods
+    x2d, cell_shape, other, ta = _unwrap(pr)
+    out = device.rolling_period_reduce(x2d, ta.period_offsets(freq), window, _lib.STATS["sum"], False,
+                                       _lib.STATS["max"])
+    attrs = attrs_of(pr)
+    attrs["units"] = "mm"
+    return _wrap_periods(pr, out, cell_shape, other, ta, freq, attrs)
+
+
+def _dry_wet_spell(pr, thresh, window, op, win_reducer, spell_reducer, freq, resample_before_rl):
+    thr = threshold_in_units_of(thresh, pr)
+    return generic.spell_length_statistics(pr, thr, window, win_reducer, op, spell_reducer, freq,
+                                           resample_before_rl=resample_before_rl)
+
+
+def dry_spell_frequency(pr, thresh="1.0 mm", window=3, freq="YS", resample_before_rl=True, op="sum"):
+    """indices/_threshold.py:3314-3382 (input in mm/d so that the daily amount equals the rate)."""
+    return _dry_wet_spell(pr, thresh.replace(" mm", " mm/d") if isinstance(thresh, str) else thresh, window, "<", op,
+                          "count", freq, resample_before_rl)
+
+
+def dry_spell_total_length(pr, thresh="1.0 mm", window=3, op="sum", freq="YS", resample_before_rl=True):
+    """indices/_threshold.py:3385-3454."""
+    return _dry_wet_spell(pr, thresh.replace(" mm", " mm/d") if isinstance(thresh, str) else thresh, window, "<", op,
+                          "sum", freq, resample_before_rl)
+
+
+def dry_spell_max_length(pr, thresh="1.0 mm", window=1, op="sum", freq="YS", resample_before_rl=True):
+    """indices/_threshold.py:3457-3522."""
+    return _dry_wet_spell(pr, thresh.replace(" mm", " mm/d") if isinstance(thresh, str) else thresh, window, "<", op,
+                          "max", freq, resample_before_rl)
+
+
+def wet_spell_frequency(pr, thresh="1.0 mm", window=3, freq="YS", resample_before_rl=True, op="sum"):
+    """indices/_threshold.py:3525-3592."""
+    return _dry_wet_spell(pr, thresh.replace(" mm", " mm/d") if isinstance(thresh, str) else thresh, window, ">=", op,
+                          "count", freq, resample_before_rl)
