@@ -108,6 +108,19 @@ int32_t xc_period_runstat_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
                               float* out, int32_t* valid_count, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * a12  first / last run of at least `window` steps of the condition (x op thr), per period
+ *   replaces run_length._boundary_run / first_run / last_run (indices/run_length.py:543-740,
+ *   general branches with `freq`).  out[p, c] (float32) = index, relative to the period start, of
+ *   the first element of the first run (position_last == 0) or of the last element of the last
+ *   run (position_last != 0); NaN when there is none.  window == 1 keeps the reference's
+ *   argmax == argmin rule (:603-605): an all-True period also gives NaN.
+ * ------------------------------------------------------------------------------------------- */
+int32_t xc_period_boundary_run_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                   const int32_t* period_offsets, int32_t P,
+                                   int32_t op, double thr, int32_t cmp_f64,
+                                   int32_t window, int32_t position_last, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * a3  per-period reductions -- indices/generic.py:83-125 (`select_resample_op`), 1255-1320
  *   (`statistics`, `thresholded_statistics`), 1514-1552 (`cumulative_difference`); _simple.py:113
  *   NaN steps are skipped (xarray skipna); an all-NaN period gives NaN (0 for SUM, COUNT).

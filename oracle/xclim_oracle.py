@@ -676,8 +676,11 @@ def eqm_adjust(sim, af, hist_q, kind="+", interp="linear"):
         if interp == "linear":
             f = np.interp(sv[m], xq, yq)
         else:
-            bds = (xq[1:] + xq[:-1]) / 2.0
-            f = yq[np.searchsorted(bds, sv[m], side="left")]
+            # scipy.interpolate.interp1d(kind="nearest"): x_bds = x/2; x_bds[1:] + x_bds[:-1] evaluated in
+            # the dtype of hist_q (float32), searchsorted(side="left") -> ties go to the lower node
+            h32 = hq2[:, c][ok] / np.float32(2.0)
+            bds = h32[1:] + h32[:-1]
+            f = yq[np.searchsorted(bds, s2[:, c][m], side="left")]
         res = sv[m] + f if kind == "+" else sv[m] * f
         col = np.full(T, np.nan)
         col[m] = res

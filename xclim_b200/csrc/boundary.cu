@@ -1,0 +1,99 @@
+// First / last run of at least `window` steps per period.
+//
+// Replaces indices/run_length.py:543-740 (`_boundary_run`, `first_run`, `last_run`), general
+// (non-ufunc) branches with `freq` given:
+//   window == 1 : per period, index of the first (last) True; NaN when argmax == argmin, i.e. when
+//                 the period is all False -- or all True (:603-605, reproduced on purpose).
+//   window  > 1 : d = (_cumsum_reset(da, index=position) >= window) on the WHOLE series (:632-633),
+//                 then per period the first (last) position where d is set: "first" = first t of the
+//                 period with da true on t..t+window-1 (the run may extend past the period end),
+//                 "last" = last t of the period with da true on t-window+1..t.
+// Output: float32 index relative to the period start, NaN when there is none.
+#include "common.cuh"
+
+namespace xc {
+namespace {
+
+constexpr int kThreads = 128;
+
+template <int OP>
+__global__ void __launch_bounds__(kThreads)
+boundary_run_kernel(const float* __restrict__ x, int64_t T, int64_t C, int64_t ldx,
+                    const int32_t* __restrict__ poff, float thr, int32_t window, int32_t last,
+                    float* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (c >= C) return;
+  const int p = blockIdx.y;
+  const int t0 = poff[p], t1 = poff[p + 1];
+  const float* col = x + c;
+  float res = NAN;
+  if (window == 1) {
+    int first = -1, lastt = -1, ntrue = 0;
+    for (int t = t0; t < t1; ++t) {
+      const bool m = cmp<OP>(ld_stream(col + (int64_t)t * ldx), thr);
+      if (m) {
+        if (first < 0) first = t;
+        lastt = t;
+        ++ntrue;
+      }
+    }
+    if (ntrue > 0 && ntrue < t1 - t0) res = (float)((last ? lastt : first) - t0);
+  } else if (!last) {
+    int cur = 0, first = -1;
+    bool any_false = false;
+    const int end = min((int)T, t1 + window - 1);
+    for (int s = t0; s < end; ++s) {
+      const bool m = cmp<OP>(ld_stream(col + (int64_t)s * ldx), thr);
+      cur = m ? cur + 1 : 0;
+      any_false = any_false || !m;
+      if (first < 0 && cur >= window) {
+        first = s - window + 1;  // < t1 because s < t1 + window - 1
+        if (first > t0) break;   // d[t0] == 0: the argmax == argmin rule cannot apply
+      }
+      if (first >= 0 && any_false) break;
+    }
+    // every position of the period qualifies (d all ones) -> argmax == argmin == 0 -> NaN (:603-605)
+    const bool all_set = (first == t0) && !any_false && (end == t1 + window - 1);
+    if (first >= 0 && !all_set) res = (float)(first - t0);
+  } else {
+    int cur = 0, lastt = -1;
+    bool any_false = false;
+    const int begin = max(0, t0 - window + 1);
+    for (int s = t1 - 1; s >= begin; --s) {
+      const bool m = cmp<OP>(ld_stream(col + (int64_t)s * ldx), thr);
+      cur = m ? cur + 1 : 0;
+      any_false = any_false || !m;
+      if (lastt < 0 && cur >= window) {
+        lastt = s + window - 1;
+        if (lastt < t1 - 1) break;
+      }
+      if (lastt >= 0 && any_false) break;
+    }
+    const bool all_set = (lastt == t1 - 1) && !any_false && (begin == t0 - window + 1);
+    if (lastt >= 0 && !all_set) res = (float)(lastt - t0);
+  }
+  out[(int64_t)p * C + c] = res;
+}
+
+}  // namespace
+}  // namespace xc
+
+using namespace xc;
+
+extern "C" int32_t xc_period_boundary_run_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                              const int32_t* period_offsets, int32_t P, int32_t op, double thr,
+                                              int32_t cmp_f64, int32_t window, int32_t position_last, float* out,
+                                              void* stream) {
+  XC_REQUIRE(x && period_offsets && out, "null pointer argument");
+  XC_REQUIRE(T > 0 && C > 0 && ldx >= C && P > 0 && P <= 65535 && T < 2147483647LL, "bad shape");
+  XC_REQUIRE(window >= 1, "window must be >= 1");
+  const float t32 = fold_threshold(op, thr, cmp_f64);
+  dim3 grid((unsigned)((C + kThreads - 1) / kThreads), (unsigned)P, 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  return dispatch_op(op, [&](auto OPC) -> int32_t {
+    constexpr int OP = decltype(OPC)::value;
+    boundary_run_kernel<OP><<<grid, kThreads, 0, st>>>(x, T, C, ldx, period_offsets, t32, window,
+                                                       position_last ? 1 : 0, out);
+    return launch_status("boundary_run_kernel");
+  });
+}

@@ -261,3 +261,15 @@ def eqm_adjust(sim2d, af, hq, kind_code, interp_code):
     check(load().xc_eqm_adjust_f32(sim2d.data_ptr(), T, C, sim2d.stride(0), af.data_ptr(), hq.data_ptr(),
                                    af.shape[0], kind_code, interp_code, scen.data_ptr(), current_stream_ptr()))
     return scen
+
+
+def period_boundary_run(x2d, poff, op_code, thr, window, last=False, cmp_f64=False):
+    """Index of the first (last) run of >= window steps per period, NaN if none (run_length.py:543-740)."""
+    T, C = x2d.shape
+    P = len(poff) - 1
+    poff_d = dev_ints(poff, np.int32, x2d.device)
+    out = torch.empty((P, C), dtype=torch.float32, device=x2d.device)
+    check(load().xc_period_boundary_run_f32(x2d.data_ptr(), T, C, x2d.stride(0), poff_d.data_ptr(), P, op_code,
+                                            float(thr), int(bool(cmp_f64)), int(window), int(bool(last)),
+                                            out.data_ptr(), current_stream_ptr()))
+    return out

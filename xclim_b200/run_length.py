@@ -89,3 +89,31 @@ def resample_and_rl(da, resample_before_rl, compute, *args, freq, dim="time", **
     out, _ = device.period_runstat(x2d, ta.period_offsets(freq), _GT, 0.0, _lib.RL_REDUCERS[reducer], window,
                                    resample_before_rl=bool(resample_before_rl))
     return _wrap_periods(da, out, cell_shape, other, ta, freq, attrs_of(da), dtype=np.float32)
+
+
+def _boundary(da, window, dim, freq, coord, position):
+    if dim != "time":
+        raise NotImplementedError("only dim='time' is supported")
+    if freq is None:
+        raise NotImplementedError("freq=None: pass a freq covering the series")
+    if coord not in (False, None, "dayofyear"):
+        raise NotImplementedError("coord must be False or 'dayofyear'")
+    x2d, cell_shape, other, ta = _mask_unwrap(da)
+    poff = ta.period_offsets(freq)
+    out = device.period_boundary_run(x2d, poff, _GT, 0.0, window, last=(position == "last"))
+    vals = out.cpu().numpy().astype(np.float64)
+    if coord == "dayofyear":  # lazy_indexing(time.dt.dayofyear, index), core/utils.py:202-276
+        idx = np.where(np.isnan(vals), 0, vals).astype(np.int64) + poff[:-1].reshape((-1,) + (1,) * (vals.ndim - 1))
+        vals = np.where(np.isnan(vals), np.nan, ta.doy[np.clip(idx, 0, len(ta) - 1)].astype(np.float64))
+    import torch
+    return _wrap_periods(da, torch.from_numpy(vals), cell_shape, other, ta, freq, attrs_of(da), dtype=np.float64)
+
+
+def first_run(da, window, dim="time", freq=None, coord=False, ufunc_1dim="from_context"):
+    """indices/run_length.py:643-690: index of the first item of the first run of at least ``window``."""
+    return _boundary(da, window, dim, freq, coord, "first")
+
+
+def last_run(da, window, dim="time", freq=None, coord=False, ufunc_1dim="from_context"):
+    """indices/run_length.py:693-740: index of the last item of the last run of at least ``window``."""
+    return _boundary(da, window, dim, freq, coord, "last")
