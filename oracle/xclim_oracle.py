@@ -535,10 +535,10 @@ def resample_doy(table, target_doy, cal_max_doy=None):
     return adoy[np.asarray(target_doy) - first]
 
 
-def doy_threshold_count(x, table, doy, poff, op=">"):
+def doy_threshold_count(x, table, doy, poff, op=">", cal_max_doy=None):
     """indices/_multivariate.py:1583-1590 + generic.py:357-361: float64 compare against the
     per-doy table (``table`` is (n_doy, ...))."""
-    thresh = resample_doy(table, doy)
+    thresh = resample_doy(table, doy, cal_max_doy)
     return threshold_count(x, op, thresh, poff, constrain=(">", ">=") if op in (">", ">=") else ("<", "<="))
 
 
@@ -546,7 +546,7 @@ def doy_threshold_count(x, table, doy, poff, op=">"):
 # a17 percentile bootstrap (core/bootstrapping.py:128-211, 235-282)
 # --------------------------------------------------------------------------------------------------
 def bootstrap_doy_count(x, year, doy, poff, base_years, window=5, per=90.0, alpha=1 / 3., beta=1 / 3.,
-                        op=">", table=None):
+                        op=">", table=None, cal_max_doy=None):
     """Zhang-2005 bootstrap of a doy-percentile exceedance count.
 
     ``poff`` groups must nest inside calendar years (freq YS/MS/QS...).  ``base_years`` =
@@ -560,6 +560,8 @@ def bootstrap_doy_count(x, year, doy, poff, base_years, window=5, per=90.0, alph
     x = np.asarray(x)
     year = np.asarray(year)
     doy = np.asarray(doy)
+    if cal_max_doy is None:   # max_doy[get_calendar(target)] (core/calendar.py:748-750): a property of
+        cal_max_doy = int(doy.max())  # the calendar, not of the sub-period being indexed
     y0, y1 = base_years
     in_base = (year >= y0) & (year <= y1)
     xb, yb, db = x[in_base], year[in_base], doy[in_base]
@@ -587,10 +589,10 @@ def bootstrap_doy_count(x, year, doy, poff, base_years, window=5, per=90.0, alph
                 z = xb.copy()
                 z[pos_y] = xb[pos_s]
                 tab = percentile_doy(z, yb, db, window, per, alpha, beta)[:, 0]
-                acc.append(threshold_count(blk, op, resample_doy(tab, dblk), [0, e_ - s_])[0])
+                acc.append(threshold_count(blk, op, resample_doy(tab, dblk, cal_max_doy), [0, e_ - s_])[0])
             out.append(np.mean(np.stack(acc, axis=0), axis=0))
         else:
-            out.append(threshold_count(blk, op, resample_doy(table, dblk), [0, e_ - s_])[0].astype(np.float64))
+            out.append(threshold_count(blk, op, resample_doy(table, dblk, cal_max_doy), [0, e_ - s_])[0].astype(np.float64))
     return np.stack(out, axis=0)
 
 

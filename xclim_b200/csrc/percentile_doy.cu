@@ -207,6 +207,94 @@ percentile_doy_uniform_kernel(const float* __restrict__ x, int32_t T, int64_t C,
   }
 }
 
+// Window 5 specialisation: adjacent day lists are merged in PAIRS, A(e) = Y(e-1) U Y(e), which are
+// reused by two different days:  S(d) = A(d-1) U A(d+1) U Y(d+2).  Per day: one pair merge, one
+// merge of two stored pairs and one final merge -- and when no NaN is present in the lane's sample
+// (warp-uniform test) the final merge only extracts the two order statistics the quantile needs
+// (the two smallest of the top-K) instead of sorting: 16 min/max instead of 80 + two select chains.
+// Ring in shared memory: 3 pair lists per lane, [slot][k][lane].
+template <int K>
+__global__ void __launch_bounds__(kThreads)
+percentile_doy_w5_kernel(const float* __restrict__ x, int32_t T, int64_t C, int64_t ldx, int32_t L, int32_t N,
+                         QuantSpec spec, int32_t doys_per_chunk, double* __restrict__ out) {
+  extern __shared__ float smem[];
+  float* ring = smem;                                                   // [3][K][kThreads]
+  int* rcnt = reinterpret_cast<int*>(smem + (size_t)3 * K * kThreads);  // [3][kThreads]
+  const int lane = threadIdx.x;
+  const int64_t c = (int64_t)blockIdx.x * kThreads + lane;
+  if (c >= C) return;
+  const int d0 = blockIdx.y * doys_per_chunk;
+  const int d1 = min(L, d0 + doys_per_chunk);
+  if (d0 >= d1) return;
+  const bool top = spec.top != 0;
+  const int n_full = 5 * N;
+
+  auto store_pair = [&](int slot, const float (&a)[K], int n) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) ring[((size_t)slot * K + k) * kThreads + lane] = a[k];
+    rcnt[slot * kThreads + lane] = n;
+  };
+
+  float yprev[K], ynew[K];
+  int nprev, nnew;
+  // prologue: A(d0-1) -> slot 0, A(d0) -> slot 1, A(d0+1) -> slot 2 ; yprev = Y(d0+1)
+  load_day_list<K>(x, c, ldx, T, L, N, d0 - 2, top, yprev, nprev);
+  for (int j = 0; j < 3; ++j) {
+    load_day_list<K>(x, c, ldx, T, L, N, d0 - 1 + j, top, ynew, nnew);
+    merge_top_desc<K>(yprev, ynew);  // yprev <- A(d0-1+j)
+    store_pair(j, yprev, nprev + nnew);
+#pragma unroll
+    for (int k = 0; k < K; ++k) yprev[k] = ynew[k];
+    nprev = nnew;
+  }
+  int s_lo = 0;  // slot of A(d-1); A(d+1) lives in slot (s_lo + 2) % 3
+  for (int d = d0; d < d1; ++d) {
+    load_day_list<K>(x, c, ldx, T, L, N, d + 2, top, ynew, nnew);
+    const int s_hi = (s_lo + 2 >= 3) ? s_lo - 1 : s_lo + 2;
+    float t[K];
+    {
+      const float* a = ring + (size_t)s_lo * K * kThreads + lane;
+      const float* b = ring + (size_t)s_hi * K * kThreads + lane;
+#pragma unroll
+      for (int k = 0; k < K; ++k) t[k] = fmaxf(a[(size_t)k * kThreads], b[(size_t)(K - 1 - k) * kThreads]);
+      bitonic_finish_desc<K>(t);
+    }
+    const int n = rcnt[s_lo * kThreads + lane] + rcnt[s_hi * kThreads + lane] + nnew;
+    // final merge with Y(d+2): the K largest of the union as a bitonic sequence
+#pragma unroll
+    for (int k = 0; k < K; ++k) t[k] = fmaxf(t[k], ynew[K - 1 - k]);
+    const QuantIdx qi = quant_index(n, spec);
+    const bool in_range = (n >= 2) && (qi.vi < (double)n - 1.0) && (qi.vi >= 0.0);
+    const bool fast = in_range && (top ? (n - 1 - qi.ilo == K - 1) : (qi.ilo + 1 == K - 1));
+    double res;
+    if (__all_sync(__activemask(), fast)) {
+      // the two smallest of t: halve the bitonic sequence keeping the minima
+      float m[K / 2];
+#pragma unroll
+      for (int i = 0; i < K / 2; ++i) m[i] = fminf(t[i], t[i + K / 2]);
+#pragma unroll
+      for (int h = K / 4; h >= 2; h >>= 1) {
+#pragma unroll
+        for (int i = 0; i < h; ++i) m[i] = fminf(m[i], m[i + h]);
+      }
+      const float smallest = fminf(m[0], m[1]), second = fmaxf(m[0], m[1]);
+      res = top ? quant_lerp(smallest, second, qi) : quant_lerp(-second, -smallest, qi);
+    } else {
+      bitonic_finish_desc<K>(t);
+      res = finalize_quantile<K>(t, n, spec);
+    }
+    out[(int64_t)d * C + c] = res;
+    // A(d+2) = Y(d+1) U Y(d+2) replaces A(d-1)
+    merge_top_desc<K>(yprev, ynew);
+    store_pair(s_lo, yprev, nprev + nnew);
+#pragma unroll
+    for (int k = 0; k < K; ++k) yprev[k] = ynew[k];
+    nprev = nnew;
+    s_lo = (s_lo + 1 == 3) ? 0 : s_lo + 1;
+  }
+  (void)n_full;
+}
+
 // ------------------------------------------------------------------------------------------------
 // doy table interpolation (core/calendar.py:690-726)
 // ------------------------------------------------------------------------------------------------
@@ -333,6 +421,22 @@ int32_t launch_uniform(const float* x, int64_t T, int64_t C, int64_t ldx, int32_
   return launch_status("percentile_doy_uniform_kernel");
 }
 
+template <int K>
+int32_t launch_w5(const float* x, int64_t T, int64_t C, int64_t ldx, int32_t L, int32_t N, const QuantSpec& spec,
+                  double* out, cudaStream_t st) {
+  const int64_t cblocks = (C + kThreads - 1) / kThreads;
+  int chunks = (int)((148 * 16 + cblocks - 1) / cblocks);
+  chunks = chunks < 1 ? 1 : chunks;
+  int per = (L + chunks - 1) / chunks;
+  if (per < 40) per = 40;  // 4 extra day lists per chunk
+  if (per > L) per = L;
+  chunks = (L + per - 1) / per;
+  const size_t smem = (size_t)3 * (K + 1) * kThreads * 4;
+  dim3 grid((unsigned)cblocks, (unsigned)chunks, 1);
+  percentile_doy_w5_kernel<K><<<grid, kThreads, smem, st>>>(x, (int32_t)T, C, ldx, L, N, spec, per, out);
+  return launch_status("percentile_doy_w5_kernel");
+}
+
 }  // namespace
 }  // namespace xc
 
@@ -392,7 +496,10 @@ extern "C" int32_t xc_percentile_doy_f32(const float* x, int64_t T, int64_t C, i
     double* o = out + (int64_t)ip * n_doy * C;
     int32_t e;
     const size_t smem_need = (size_t)(window - 1) * ((need <= 8 ? 8 : need <= 16 ? 16 : 32) + 1) * kThreads * 4;
-    if (uniform && window >= 3 && need <= 32 && smem_need <= 200 * 1024) {
+    if (uniform && window == 5 && need <= 16 && n_doy >= 5) {
+      e = need <= 8 ? launch_w5<8>(x, T, C, ldx, n_doy, n_years, spec, o, st)
+                    : launch_w5<16>(x, T, C, ldx, n_doy, n_years, spec, o, st);
+    } else if (uniform && window >= 3 && need <= 32 && smem_need <= 200 * 1024) {
       e = need <= 8    ? launch_uniform<8>(x, T, C, ldx, n_doy, n_years, window, spec, o, st)
           : need <= 16 ? launch_uniform<16>(x, T, C, ldx, n_doy, n_years, window, spec, o, st)
                        : launch_uniform<32>(x, T, C, ldx, n_doy, n_years, window, spec, o, st);

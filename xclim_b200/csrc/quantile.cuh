@@ -88,4 +88,25 @@ __device__ __forceinline__ double finalize_quantile(const float (&lst)[K], int n
   return r;
 }
 
+
+// Per-lane virtual index pieces, shared by the full and the rank-only finalisation.
+struct QuantIdx {
+  double vi, lo;
+  int ilo;
+};
+__device__ __forceinline__ QuantIdx quant_index(int n, const QuantSpec& s) {
+  QuantIdx r;
+  r.vi = __dadd_rn(__dadd_rn(__dmul_rn((double)n, s.q), s.c), -1.0);
+  r.lo = floor(r.vi);
+  r.ilo = (int)r.lo;
+  return r;
+}
+// lerp of core/utils.py:464-491 given the two neighbours (already de-negated)
+__device__ __forceinline__ double quant_lerp(float left, float right, const QuantIdx& qi) {
+  const double g = __dadd_rn(qi.vi, -qi.lo);
+  const float diff = __fsub_rn(right, left);
+  if (g >= 0.5) return __dadd_rn((double)right, -__dmul_rn((double)diff, __dadd_rn(1.0, -g)));
+  return __dadd_rn((double)left, __dmul_rn((double)diff, g));
+}
+
 }  // namespace xc
