@@ -1,0 +1,104 @@
+#!/usr/bin/env python
+"""Secondary measurements (not the driver's contract): BASELINE.json configs 3b (bootstrap) and 4 (EQM)
+plus the other streaming kernels, on a lat band of the headline grid.  One JSON line per kernel.
+
+    python bench_extra.py --lat 180 --steps 3
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+T, X, YEAR = 10950, 1440, 365
+
+
+def timeit(fn, steps, warmup=2):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for i in range(steps):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    return float(np.mean([ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--lat", type=int, default=180)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    import torch
+    from xclim_b200 import _lib, device
+    C = a.lat * X
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0) \
+        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    poff = np.arange(T // YEAR + 1, dtype=np.int32) * YEAR
+    poff_m = None
+    doy = (np.arange(T) % YEAR + 1).astype(np.int16)
+    yidx = (np.arange(T) // YEAR).astype(np.int16)
+    tas = device.synth(T, C, kind=1, seed=3, cells_per_lat=X, n_lat_global=a.lat)
+    pr = device.synth(T, C, kind=0, seed=2, cells_per_lat=X, n_lat_global=a.lat)
+
+    def report(name, ms, alg_bytes, extra=None):
+        gbs = alg_bytes / (ms * 1e-3) / 1e9
+        line = {"kernel": name, "grid": [T, a.lat, X], "ms": ms, "cells_per_s": C / (ms * 1e-3),
+                "algorithmic_bytes": alg_bytes, "achieved_gbs": gbs, "frac_of_measured_hbm_peak": gbs / peak}
+        if extra:
+            line.update(extra)
+        print(json.dumps(line), flush=True)
+
+    want = lambda k: (not a.only) or (k in a.only.split(","))
+    P = T // YEAR
+    if want("count"):
+        ms = timeit(lambda: device.period_count(pr, poff, _lib.OPS[">="], 1.0, want_valid=True), a.steps)
+        report("period_count (wetdays, fused valid)", ms, T * C * 4 + 2 * P * C * 4)
+    if want("reduce"):
+        ms = timeit(lambda: device.period_reduce(tas, poff, _lib.STATS["mean"], want_valid=True), a.steps)
+        report("period_reduce mean (tg_mean, fused valid)", ms, T * C * 4 + 2 * P * C * 4)
+    if want("runsum"):
+        ms = timeit(lambda: device.period_runstat(pr, poff, _lib.OPS["<"], 1.0, _lib.RL_REDUCERS["sum"], 3), a.steps)
+        report("period_runstat sum window=3 (windowed_run_count)", ms, T * C * 4 + P * C * 4)
+    if want("after"):
+        ms = timeit(lambda: device.period_runstat(pr, poff, _lib.OPS["<"], 1.0, _lib.RL_REDUCERS["max"], 1, False),
+                    a.steps)
+        report("period_runstat max, resample_before_rl=False", ms, T * C * 4 + P * C * 4)
+    if want("rolling"):
+        ms = timeit(lambda: device.rolling_period_reduce(pr, poff, 5, _lib.STATS["sum"], False, _lib.STATS["max"]),
+                    a.steps)
+        report("rolling(5).sum -> max (max_n_day_precipitation_amount)", ms, T * C * 4 + P * C * 4)
+    if want("spell"):
+        ms = timeit(lambda: device.spell_runstat(pr, poff, 3, _lib.STATS["sum"], _lib.OPS["<"], 1.0,
+                                                 _lib.RL_REDUCERS["count"]), a.steps)
+        report("spell_runstat window=3 sum<1 count (dry_spell_frequency)", ms, T * C * 4 + P * C * 4)
+    if want("first"):
+        ms = timeit(lambda: device.period_boundary_run(tas, poff, _lib.OPS[">"], 283.15, 5), a.steps)
+        report("period_boundary_run first, window=5", ms, T * C * 4 + P * C * 4)
+    if want("bootstrap"):
+        nb = 15
+        step_period = np.repeat(np.arange(nb), YEAR).astype(np.int32)
+        fn = lambda: device.bootstrap_doy_count(tas, 0, nb, YEAR, step_period, P, 5, 90.0, 1 / 3, 1 / 3, _lib.OPS[">"])
+        ms = timeit(fn, max(1, a.steps // 2), warmup=1)
+        report("bootstrap_doy_count (tx90p 3b: 15-year base, 14 resamples per year)", ms, T * C * 4 + P * C * 8,
+               {"quantile_evaluations_per_cell": nb * (nb - 1) * YEAR})
+    if want("eqm"):
+        hist = device.synth(T, C, kind=1, seed=5, cells_per_lat=X, n_lat_global=a.lat)
+        ms = timeit(lambda: device.eqm_train(tas, hist, 20, 0), max(1, a.steps // 2), warmup=1)
+        report("eqm_train nq=20 (ref, hist)", ms, 2 * T * C * 4 + 2 * 20 * C * 4)
+        af, hq = device.eqm_train(tas, hist, 20, 0)
+        ms = timeit(lambda: device.eqm_adjust(hist, af, hq, 0, 1), a.steps)
+        report("eqm_adjust linear (sim -> scen)", ms, 2 * T * C * 4 + 2 * 20 * C * 4)
+
+
+if __name__ == "__main__":
+    main()
