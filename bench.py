@@ -49,7 +49,7 @@ def parse_args():
 class ClockSampler:
     """Samples SM clock / throttle reasons with NVML during the timed region."""
 
-    def __init__(self, index=0, period=0.1):
+    def __init__(self, index=0, period=0.005):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._th = None

@@ -204,6 +204,15 @@ int32_t xc_doy_threshold_count_f32(const float* x, int64_t T, int64_t C, int64_t
                                    int32_t op, int32_t* out_count, int32_t* valid_count,
                                    void* stream);
 
+/* Same count for the common layout "n_years whole years of year_len steps starting at first_row,
+ * day-of-year == position in the year" (noleap / 360_day with freq YS): out[y, c] for y < n_years.
+ * Year-blocked so that each table row is read once per 6 years; needs C, ldx % 4 == 0 and 16-byte
+ * aligned buffers (use xc_doy_threshold_count_f32 otherwise). */
+int32_t xc_doy_threshold_count_years_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                         int64_t first_row, int32_t n_years, int32_t year_len,
+                                         const double* table, int32_t op,
+                                         int32_t* out_count, int32_t* valid_count, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a17  percentile bootstrap (Zhang 2005) -- core/bootstrapping.py:81-211, 235-282
  *   x: (T, C) studied series; the base (climatology) period is the n_base_years equal-length

@@ -132,3 +132,30 @@ def test_tx90p_reference_known_answer_leap_year(cuda):
     tas2 = tas.copy(); tas2[175:180] = 1
     out = indices.tx90p(make_field(tas2, "2000-01-01", units="K"), t90, freq="MS")
     assert out.values[0] == 30 and out.values[1] == 29 and out.values[5] == 25
+
+
+@pytest.mark.parametrize("op", [">", ">=", "<", "<="])
+def test_doy_count_year_blocked_kernel_exact_ties(cuda, op):
+    """The year-blocked kernel folds float64 thresholds to float32 by directed rounding: it must agree
+    with the float64 compare for thresholds equal to data values, one double-ulp off, +-0, inf, NaN."""
+    import torch
+    from xclim_b200 import device, _lib
+    rng = np.random.default_rng(15)
+    L, N, C = 365, 7, 64
+    x = (np.round(rng.standard_normal((L * N, C)) * 4) / 4).astype(np.float32)
+    x[rng.random(x.shape) < 0.01] = np.nan
+    tab = x[:L].astype(np.float64).copy()                       # exact ties with year 0
+    tab[1::3] = np.nextafter(tab[1::3], np.inf)                 # just above a representable value
+    tab[2::3] = np.nextafter(tab[2::3], -np.inf)                # just below
+    tab[5, :8] = [0.0, -0.0, np.inf, -np.inf, np.nan, 1e-300, -1e-300, 1e300]
+    x[5, :8] = [0.0, -0.0, 1.0, -1.0, 0.0, 0.0, -0.0, 3e38]
+    poff = np.arange(N + 1, dtype=np.int32) * L
+    doy = np.tile(np.arange(1, L + 1), N).astype(np.int16)
+    xd, td = torch.from_numpy(x).cuda(), torch.from_numpy(tab).cuda()
+    got, valid = device.doy_threshold_count(xd, poff, doy, td, _lib.OPS[op], want_valid=True)   # year-blocked
+    exp = O.threshold_count(x, op, tab[doy - 1], poff)
+    np.testing.assert_array_equal(got.cpu().numpy(), exp)
+    np.testing.assert_array_equal(valid.cpu().numpy(), np.stack([(~np.isnan(x[s:e])).sum(0) for s, e in zip(poff[:-1], poff[1:])]))
+    # generic kernel on the same data (odd number of cells forces it)
+    got2, _ = device.doy_threshold_count(xd[:, :63].contiguous(), poff, doy, td[:, :63].contiguous(), _lib.OPS[op])
+    np.testing.assert_array_equal(got2.cpu().numpy(), exp[:, :63])

@@ -32,6 +32,10 @@ namespace {
 constexpr int kThreads = 128;
 #define XC_NEG_INF (__int_as_float(0xff800000))
 
+__device__ __forceinline__ void store_vec4(int32_t* dst, const int32_t (&v)[4]) {
+  *reinterpret_cast<int4*>(dst) = make_int4(v[0], v[1], v[2], v[3]);
+}
+
 // value as inserted in the lists: NaN -> -inf (never selected), bottom side -> negated
 __device__ __forceinline__ float prep(float v, bool top, int& n) {
   const bool ok = (v == v);
@@ -386,6 +390,72 @@ doy_count_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, const int3
   }
 }
 
+// Year-blocked count for the common case "periods are whole years of equal length and the doy of a
+// step is its position in the year" (noleap / 360_day, freq YS): a thread owns 4 adjacent cells and
+// YB consecutive years, so every table row is fetched once per YB years instead of once per year
+// (the table is 365*C*8 B = 3 GB at full size, far beyond L2), and it is folded once per row into a
+// float32 threshold by directed rounding (x op t64  <=>  x op' t32 for every float32 x), which turns
+// the per-element float64 compare + conversion into one float32 compare.
+template <int OP>
+__device__ __forceinline__ float fold_thr(double t) {
+  float f = __double2float_rn(t);
+  if (t != t) return f;  // NaN threshold: every compare is False
+  if constexpr (OP == XC_OP_GT || OP == XC_OP_LE) {  // largest float32 <= t
+    if ((double)f > t) f = __int_as_float(__float_as_int(f) + ((f > 0.f) ? -1 : 1));
+    if (f == 0.f && t < 0.0) f = -1.401298464e-45f;
+  } else {                                           // smallest float32 >= t
+    if ((double)f < t) f = __int_as_float(__float_as_int(f) + ((f >= 0.f) ? 1 : -1));
+    if (f == 0.f && t > 0.0) f = 1.401298464e-45f;
+  }
+  return f;
+}
+
+template <int OP, int YB, bool VALID>
+__global__ void __launch_bounds__(kThreads)
+doy_count_years_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int64_t first_row, int32_t n_years,
+                       int32_t L, const double* __restrict__ table, int32_t* __restrict__ out,
+                       int32_t* __restrict__ valid) {
+  // blockIdx.x = year group (fastest: groups of one cell range run together and share table rows in L2)
+  const int y0 = blockIdx.x * YB;
+  const int64_t c = ((int64_t)blockIdx.y * kThreads + threadIdx.x) * 4;
+  if (c >= C) return;
+  int32_t cnt[YB][4], nv[YB][4];
+#pragma unroll
+  for (int j = 0; j < YB; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { cnt[j][i] = 0; nv[j][i] = 0; }
+  const int ny = min(YB, n_years - y0);
+  const float* base = x + (first_row + (int64_t)y0 * L) * ldx + c;
+  const int64_t ystride = (int64_t)L * ldx;
+  for (int d = 0; d < L; ++d) {
+    const double2 ta = *reinterpret_cast<const double2*>(table + (int64_t)d * C + c);
+    const double2 tb = *reinterpret_cast<const double2*>(table + (int64_t)d * C + c + 2);
+    float thr[4] = {fold_thr<OP>(ta.x), fold_thr<OP>(ta.y), fold_thr<OP>(tb.x), fold_thr<OP>(tb.y)};
+    float4 v[YB];
+#pragma unroll
+    for (int j = 0; j < YB; ++j)
+      if (j < ny) v[j] = ld_stream4(base + (int64_t)j * ystride + (int64_t)d * ldx);
+#pragma unroll
+    for (int j = 0; j < YB; ++j) {
+      if (j < ny) {
+        const float xv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          cnt[j][i] += cmp<OP>(xv[i], thr[i]) ? 1 : 0;
+          if constexpr (VALID) nv[j][i] += (xv[i] == xv[i]) ? 1 : 0;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < YB; ++j) {
+    if (j < ny) {
+      store_vec4(out + (int64_t)(y0 + j) * C + c, cnt[j]);
+      if constexpr (VALID) store_vec4(valid + (int64_t)(y0 + j) * C + c, nv[j]);
+    }
+  }
+}
+
 template <int K>
 int32_t launch_generic(const float* x, int64_t T, int64_t C, int64_t ldx, const int32_t* pos, int32_t n_doy,
                        int32_t n_years, int32_t h, const QuantSpec& spec, double* out, cudaStream_t st) {
@@ -588,5 +658,35 @@ extern "C" int32_t xc_doy_threshold_count_f32(const float* x, int64_t T, int64_t
       doy_count_kernel<OP, false><<<grid, kThreads, 0, st>>>(x, C, ldx, period_offsets, doy_index, table, out_count,
                                                              valid_count);
     return launch_status("doy_count_kernel");
+  });
+}
+
+extern "C" int32_t xc_doy_threshold_count_years_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                                    int64_t first_row, int32_t n_years, int32_t year_len,
+                                                    const double* table, int32_t op, int32_t* out_count,
+                                                    int32_t* valid_count, void* stream) {
+  XC_REQUIRE(x && table && out_count, "null pointer argument");
+  XC_REQUIRE(T > 0 && C > 0 && ldx >= C && n_years > 0 && year_len > 0, "bad shape");
+  XC_REQUIRE(first_row >= 0 && first_row + (int64_t)n_years * year_len <= T, "years outside the series");
+  XC_REQUIRE(op >= XC_OP_GT && op <= XC_OP_LE, "Operation `%d` not permitted for indice.", op);
+  XC_REQUIRE((C % 4 == 0) && (ldx % 4 == 0) && aligned16(x) && aligned16(table) && aligned16(out_count) &&
+                 (valid_count == nullptr || aligned16(valid_count)),
+             "xc_doy_threshold_count_years_f32 needs C, ldx multiples of 4 and 16-byte aligned buffers");
+  constexpr int YB = 6;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t cblocks = (C / 4 + kThreads - 1) / kThreads;
+  XC_REQUIRE(cblocks <= 65535, "too many cells for one launch: tile the grid by latitude");
+  dim3 grid((unsigned)((n_years + YB - 1) / YB), (unsigned)cblocks, 1);
+  return dispatch_op(op, [&](auto OPC) -> int32_t {
+    constexpr int OP = decltype(OPC)::value;
+    if constexpr (OP <= XC_OP_LE) {
+      if (valid_count)
+        doy_count_years_kernel<OP, YB, true><<<grid, kThreads, 0, st>>>(x, C, ldx, first_row, n_years, year_len, table,
+                                                                        out_count, valid_count);
+      else
+        doy_count_years_kernel<OP, YB, false><<<grid, kThreads, 0, st>>>(x, C, ldx, first_row, n_years, year_len,
+                                                                         table, out_count, valid_count);
+    }
+    return launch_status("doy_count_years_kernel");
   });
 }

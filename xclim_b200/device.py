@@ -168,12 +168,23 @@ def doy_threshold_count(x2d, poff, doy_index, table2d, op_code, want_valid=False
     """#{t in period : float64(x[t]) op table[doy[t]-1]} (indices/_multivariate.py:1583-1590)."""
     T, C = x2d.shape
     P = len(poff) - 1
-    poff_d = dev_ints(poff, np.int32, x2d.device)
-    doy_d = dev_ints(doy_index, np.int16, x2d.device)
     assert table2d.dtype == torch.float64 and table2d.is_contiguous() and table2d.shape[1] == C
-    assert int(np.max(doy_index)) <= table2d.shape[0] and int(np.min(doy_index)) >= 1
+    doy_index = np.asarray(doy_index)
+    assert int(doy_index.max()) <= table2d.shape[0] and int(doy_index.min()) >= 1
     out = torch.empty((P, C), dtype=torch.int32, device=x2d.device)
     valid = torch.empty((P, C), dtype=torch.int32, device=x2d.device) if want_valid else None
+    # whole years of equal length with doy == position in the year: the year-blocked kernel
+    poff = np.asarray(poff)
+    L = int(poff[1] - poff[0])
+    if (op_code <= 3 and C % 4 == 0 and x2d.stride(0) % 4 == 0 and x2d.data_ptr() % 16 == 0
+            and np.all(np.diff(poff) == L) and L == table2d.shape[0]
+            and np.array_equal(doy_index[poff[0]:poff[-1]], np.tile(np.arange(1, L + 1), P))):
+        check(load().xc_doy_threshold_count_years_f32(x2d.data_ptr(), T, C, x2d.stride(0), int(poff[0]), P, L,
+                                                       table2d.data_ptr(), op_code, out.data_ptr(), _ptr(valid),
+                                                       current_stream_ptr()))
+        return out, valid
+    poff_d = dev_ints(poff, np.int32, x2d.device)
+    doy_d = dev_ints(doy_index, np.int16, x2d.device)
     check(load().xc_doy_threshold_count_f32(x2d.data_ptr(), T, C, x2d.stride(0), poff_d.data_ptr(), P,
                                             doy_d.data_ptr(), table2d.data_ptr(), table2d.shape[0], op_code,
                                             out.data_ptr(), _ptr(valid), current_stream_ptr()))
