@@ -292,6 +292,12 @@ def run_ours(args):
 
 if __name__ == "__main__":
     a = parse_args()
+    # the contract is ONE JSON line on stdout: libraries that print to fd 1 (e.g. "NCCL version ...")
+    # are sent to stderr, and only the final line goes to the real stdout
+    sys.stdout.flush()
+    _real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = _real_stdout
     if a.impl == "reference":
         run_reference(a)
     else:

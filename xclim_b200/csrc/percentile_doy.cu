@@ -419,39 +419,63 @@ doy_count_years_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int6
   const int y0 = blockIdx.x * YB;
   const int64_t c = ((int64_t)blockIdx.y * kThreads + threadIdx.x) * 4;
   if (c >= C) return;
-  int32_t cnt[YB][4], nv[YB][4];
+  // packed counters: low 16 bits = exceedance count, high 16 bits = valid count (both <= 366)
+  uint32_t acc[YB][4];
 #pragma unroll
   for (int j = 0; j < YB; ++j)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { cnt[j][i] = 0; nv[j][i] = 0; }
+    for (int i = 0; i < 4; ++i) acc[j][i] = 0u;
   const int ny = min(YB, n_years - y0);
   const float* base = x + (first_row + (int64_t)y0 * L) * ldx + c;
   const int64_t ystride = (int64_t)L * ldx;
-  for (int d = 0; d < L; ++d) {
-    const double2 ta = *reinterpret_cast<const double2*>(table + (int64_t)d * C + c);
-    const double2 tb = *reinterpret_cast<const double2*>(table + (int64_t)d * C + c + 2);
-    float thr[4] = {fold_thr<OP>(ta.x), fold_thr<OP>(ta.y), fold_thr<OP>(tb.x), fold_thr<OP>(tb.y)};
-    float4 v[YB];
+  const double* trow = table + c;
+  auto row = [&](int d, double2& ta, double2& tb, float4 (&v)[YB]) {
+    ta = *reinterpret_cast<const double2*>(trow + (int64_t)d * C);
+    tb = *reinterpret_cast<const double2*>(trow + (int64_t)d * C + 2);
 #pragma unroll
     for (int j = 0; j < YB; ++j)
       if (j < ny) v[j] = ld_stream4(base + (int64_t)j * ystride + (int64_t)d * ldx);
+  };
+  auto tally = [&](const double2& ta, const double2& tb, const float4 (&v)[YB]) {
+    const float thr[4] = {fold_thr<OP>(ta.x), fold_thr<OP>(ta.y), fold_thr<OP>(tb.x), fold_thr<OP>(tb.y)};
 #pragma unroll
     for (int j = 0; j < YB; ++j) {
       if (j < ny) {
         const float xv[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          cnt[j][i] += cmp<OP>(xv[i], thr[i]) ? 1 : 0;
-          if constexpr (VALID) nv[j][i] += (xv[i] == xv[i]) ? 1 : 0;
+          acc[j][i] += cmp<OP>(xv[i], thr[i]) ? 1u : 0u;
+          if constexpr (VALID) acc[j][i] += (xv[i] == xv[i]) ? 65536u : 0u;
         }
       }
     }
+  };
+  int d = 0;
+  for (; d + 2 <= L; d += 2) {  // two table rows and 2*YB data rows in flight before any use
+    double2 ta0, tb0, ta1, tb1;
+    float4 v0[YB], v1[YB];
+    row(d, ta0, tb0, v0);
+    row(d + 1, ta1, tb1, v1);
+    tally(ta0, tb0, v0);
+    tally(ta1, tb1, v1);
+  }
+  for (; d < L; ++d) {
+    double2 ta, tb;
+    float4 v[YB];
+    row(d, ta, tb, v);
+    tally(ta, tb, v);
   }
 #pragma unroll
   for (int j = 0; j < YB; ++j) {
     if (j < ny) {
-      store_vec4(out + (int64_t)(y0 + j) * C + c, cnt[j]);
-      if constexpr (VALID) store_vec4(valid + (int64_t)(y0 + j) * C + c, nv[j]);
+      const int32_t cn[4] = {(int32_t)(acc[j][0] & 0xffffu), (int32_t)(acc[j][1] & 0xffffu),
+                             (int32_t)(acc[j][2] & 0xffffu), (int32_t)(acc[j][3] & 0xffffu)};
+      store_vec4(out + (int64_t)(y0 + j) * C + c, cn);
+      if constexpr (VALID) {
+        const int32_t vn[4] = {(int32_t)(acc[j][0] >> 16), (int32_t)(acc[j][1] >> 16), (int32_t)(acc[j][2] >> 16),
+                               (int32_t)(acc[j][3] >> 16)};
+        store_vec4(valid + (int64_t)(y0 + j) * C + c, vn);
+      }
     }
   }
 }
@@ -672,7 +696,8 @@ extern "C" int32_t xc_doy_threshold_count_years_f32(const float* x, int64_t T, i
   XC_REQUIRE((C % 4 == 0) && (ldx % 4 == 0) && aligned16(x) && aligned16(table) && aligned16(out_count) &&
                  (valid_count == nullptr || aligned16(valid_count)),
              "xc_doy_threshold_count_years_f32 needs C, ldx multiples of 4 and 16-byte aligned buffers");
-  constexpr int YB = 6;
+  constexpr int YB = 3;
+  XC_REQUIRE(year_len <= 65535, "year length too large for the packed counters");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t cblocks = (C / 4 + kThreads - 1) / kThreads;
   XC_REQUIRE(cblocks <= 65535, "too many cells for one launch: tile the grid by latitude");

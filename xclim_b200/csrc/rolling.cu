@@ -50,6 +50,26 @@ __device__ __forceinline__ float window_stat(const float* __restrict__ col, int6
   }
 }
 
+// Sliding window state for sum / mean windows: running float64 sum of the non-NaN values plus the
+// number of NaNs in the window.  Sums of float32 values whose exponents lie within a few decades of
+// each other are exact in float64, so the running sum equals the direct sum of the w values.
+struct SlideSum {
+  double s;
+  int nan;
+  __device__ __forceinline__ void add(float v) {
+    const bool bad = (v != v);
+    nan += bad ? 1 : 0;
+    s += bad ? 0.0 : (double)v;
+  }
+  __device__ __forceinline__ void drop(float v) {
+    const bool bad = (v != v);
+    nan -= bad ? 1 : 0;
+    s -= bad ? 0.0 : (double)v;
+  }
+};
+
+constexpr int kChunk = 8;
+
 __global__ void __launch_bounds__(kThreads)
 rolling_period_reduce_kernel(const float* __restrict__ x, int64_t T, int64_t C, int64_t ldx,
                              const int32_t* __restrict__ poff, int32_t w, int32_t wstat, int32_t shift,
@@ -62,16 +82,55 @@ rolling_period_reduce_kernel(const float* __restrict__ x, int64_t T, int64_t C, 
   double s = 0.0, q = 0.0;
   float m = (stat == XC_STAT_MIN) ? INFINITY : -INFINITY;
   int n = 0;
-  for (int t = t0; t < t1; ++t) {
-    // value labelled t covers x[t+shift-w+1 .. t+shift] (shift = 0 right-aligned, w/2 centred)
-    const int i = t + shift - w + 1;
-    float r = NAN;
-    if (i >= 0 && i + w <= (int)T) r = window_stat(col, ldx, i, w, wstat);
+  auto take = [&](float r) {
     if (r == r) {
       ++n;
       s += (double)r;
       q += (double)r * (double)r;
       m = (stat == XC_STAT_MIN) ? fminf(m, r) : fmaxf(m, r);
+    }
+  };
+  // the value labelled t covers x[i .. i+w-1], i = t + shift - w + 1 (shift 0: right-aligned, w/2: centred)
+  if (wstat == XC_STAT_SUM || wstat == XC_STAT_MEAN) {
+    const double inv = (wstat == XC_STAT_MEAN) ? 1.0 / (double)w : 1.0;
+    int t = t0;
+    // labels whose window is incomplete at the series start give NaN
+    while (t < t1 && t + shift - w + 1 < 0) ++t;
+    SlideSum win{0.0, 0};
+    int i = t + shift - w + 1;          // first complete window of this period
+    if (t < t1 && i + w <= (int)T)
+      for (int k = 0; k < w; ++k) win.add(__ldg(col + (int64_t)(i + k) * ldx));
+    while (t < t1 && i + w <= (int)T) {
+      take(win.nan ? NAN : (float)(wstat == XC_STAT_MEAN ? win.s / (double)w : win.s));
+      // slide by up to kChunk steps with all loads issued first
+      const int steps = min(kChunk, min(t1 - 1 - t, (int)T - (i + w)));
+      if (steps <= 0) break;
+      float vin[kChunk], vout[kChunk];
+#pragma unroll
+      for (int k = 0; k < kChunk; ++k) {
+        if (k < steps) {
+          vin[k] = ld_stream(col + (int64_t)(i + w + k) * ldx);
+          vout[k] = __ldg(col + (int64_t)(i + k) * ldx);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kChunk; ++k) {
+        if (k < steps) {
+          win.add(vin[k]);
+          win.drop(vout[k]);
+          if (k + 1 < steps) take(win.nan ? NAN : (float)(wstat == XC_STAT_MEAN ? win.s / (double)w : win.s));
+        }
+      }
+      t += steps;
+      i += steps;
+    }
+    (void)inv;
+  } else {
+    for (int t = t0; t < t1; ++t) {
+      const int i = t + shift - w + 1;
+      float r = NAN;
+      if (i >= 0 && i + w <= (int)T) r = window_stat(col, ldx, i, w, wstat);
+      take(r);
     }
   }
   float res;
