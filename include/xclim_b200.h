@@ -108,6 +108,16 @@ int32_t xc_period_runstat_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
                               float* out, int32_t* valid_count, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * a11  windowed_max_run_sum of the excess over a threshold -- indices/run_length.py:491-540 on
+ *   `(x - thr).clip(0)` (indices/_threshold.py:2064-2073, `hot_spell_max_magnitude`): per period the
+ *   largest sum of (x - thr) (op >, >=; thr - x for <, <=) over a run at least `window` long.
+ * ------------------------------------------------------------------------------------------- */
+int32_t xc_period_run_maxsum_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                 const int32_t* period_offsets, int32_t P,
+                                 int32_t op, double thr, int32_t window, int32_t resample_before_rl,
+                                 float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * a12  first / last run of at least `window` steps of the condition (x op thr), per period
  *   replaces run_length._boundary_run / first_run / last_run (indices/run_length.py:543-740,
  *   general branches with `freq`).  out[p, c] (float32) = index, relative to the period start, of

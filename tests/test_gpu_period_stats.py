@@ -184,3 +184,28 @@ def test_strided_rows_and_large_cells(cuda):
     np.testing.assert_array_equal(got.cpu().numpy(),
                                   O.resample_and_rl((x[:, 1000:2200] < 1.0), True, O.rle_statistics, poff=poff,
                                                     reducer="sum", window=2))
+
+
+@pytest.mark.parametrize("window", [1, 3])
+@pytest.mark.parametrize("before", [True, False])
+def test_hot_spell_max_magnitude(cuda, window, before):
+    """windowed_max_run_sum of (tasmax - thresh).clip(0): 1e-5 relative (float64 run sums here, float32
+    cumulative sums in the reference)."""
+    from xclim_b200 import indices, generic
+    rng = np.random.default_rng(6)
+    x = (295 + 6 * rng.standard_normal((365 * 2 + 30, 6, 8))).astype(np.float32)
+    x[rng.random(x.shape) < 0.01] = np.nan
+    da = make_field(x, "2001-01-01", units="K")
+    for freq in ("YS", "MS"):
+        poff = da.time.period_offsets(freq)
+        got = indices.hot_spell_max_magnitude(da, "25 degC", window=window, freq=freq, resample_before_rl=before)
+        over = np.clip(x - np.float32(298.15), 0, None)
+        over = np.where(np.isnan(over), 0, over).astype(np.float64)
+        exp = O.resample_and_rl(over, before, O.windowed_max_run_sum, window, poff=poff)
+        np.testing.assert_allclose(got.values, exp, rtol=1e-5, atol=1e-6)
+    # thresholded statistics / count_occurrences wrappers
+    got = generic.thresholded_statistics(da, ">", 298.15, "mean", "YS").values
+    exp = O.resample_reduce(np.where(x > np.float32(298.15), x, np.nan).astype(np.float64), da.time.period_offsets("YS"), "mean")
+    np.testing.assert_allclose(got, exp, rtol=1e-5)
+    np.testing.assert_array_equal(generic.count_occurrences(da, 298.15, "YS", ">").values,
+                                  O.threshold_count(x, ">", 298.15, da.time.period_offsets("YS")))

@@ -102,16 +102,18 @@ __device__ __forceinline__ void load_day_list(const float* __restrict__ x, int64
   bool first = true;
   for (int y0 = 0; y0 < N; y0 += K) {
     float v[K];
-    // byte pointer of (row y0*L + e, cell c), advanced by one year per load: one 64-bit add each
-    const char* p = reinterpret_cast<const char*>(x + ((int64_t)y0 * L + e) * ldx + c);
-    const int64_t ystride = (int64_t)L * ldx * 4;
+    // byte address of (row (y0+k)*L + e, cell c) = p0 + k * ystride: when the year stride fits 32 bits
+    // (it does for any grid below 4 GiB per year) this is ONE 32x32+64 multiply-add per load on the
+    // FMA pipe, leaving the ALU pipe to the min/max network
+    const char* p0 = reinterpret_cast<const char*>(x + ((int64_t)y0 * L + e) * ldx + c);
+    const uint64_t ystride = (uint64_t)L * (uint64_t)ldx * 4ull;
+    const uint32_t ys32 = (uint32_t)ystride;
+    const bool narrow = (ystride >> 32) == 0;
     int nv;
-    if (y0 >= ylo && y0 + K <= yhi) {  // whole chunk in range (the common case): unpredicated loads
+    if (y0 >= ylo && y0 + K <= yhi && narrow) {  // whole chunk in range (the common case)
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        v[k] = ld_stream(reinterpret_cast<const float*>(p));
-        p += ystride;
-      }
+      for (int k = 0; k < K; ++k)
+        v[k] = ld_stream(reinterpret_cast<const float*>(p0 + (uint64_t)((uint32_t)k) * (uint64_t)ys32));
       nv = K;
     } else {
       nv = 0;
@@ -120,21 +122,21 @@ __device__ __forceinline__ void load_day_list(const float* __restrict__ x, int64
         const int y = y0 + k;
         const bool ok = (y >= ylo) && (y < yhi);
         // rows that do not exist are +/-inf BEFORE the bottom-side negation below turns them into -inf
-        v[k] = ok ? ld_stream(reinterpret_cast<const float*>(p)) : (top ? XC_NEG_INF : -XC_NEG_INF);
+        v[k] = ok ? ld_stream(reinterpret_cast<const float*>(p0 + (uint64_t)k * ystride))
+                  : (top ? XC_NEG_INF : -XC_NEG_INF);
         nv += ok ? 1 : 0;
-        p += ystride;
       }
     }
     if (!top) {
 #pragma unroll
       for (int k = 0; k < K; ++k) v[k] = -v[k];
     }
-    // NaN handling off the fast path: one predicate-accumulating compare per value, and only a
-    // lane that actually saw a NaN pays for counting / replacing them (NaN -> -inf, never selected)
-    bool any_nan = false;
+    // NaN handling off the fast path: a chain of FMAs (FMA pipe) makes `probe` NaN iff some value is
+    // NaN or infinite; only then does the lane look at each value (NaN -> -inf, never selected)
+    float probe = 0.f;
 #pragma unroll
-    for (int k = 0; k < K; ++k) any_nan = any_nan || (v[k] != v[k]);
-    if (any_nan) {
+    for (int k = 0; k < K; ++k) probe = __fmaf_rn(v[k], 0.f, probe);
+    if (probe != probe) {
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const bool bad = (v[k] != v[k]);

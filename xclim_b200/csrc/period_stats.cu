@@ -238,6 +238,86 @@ period_runstat_kernel(const float* __restrict__ x, int64_t T, int64_t C, int64_t
 }
 
 // ------------------------------------------------------------------------------------------------
+// windowed_max_run_sum of the excess over a threshold (indices/run_length.py:491-540 applied to
+// `(x - thr).clip(0)`, indices/_threshold.py:2064-2073 `hot_spell_max_magnitude`): per period the
+// largest sum of (x - thr) over a run of x > thr (x < thr: thr - x) at least `window` long, 0 if none.
+// The excess is formed in float32 like the reference's `tasmax - thresh`; run sums are float64.
+// ------------------------------------------------------------------------------------------------
+template <int OP, int VEC, bool AFTER>
+__global__ void __launch_bounds__(kThreads)
+period_run_maxsum_kernel(const float* __restrict__ x, int64_t T, int64_t C, int64_t ldx,
+                         const int32_t* __restrict__ poff, float thr, int32_t window, float* __restrict__ out) {
+  const int64_t c0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * VEC;
+  if (c0 >= C) return;
+  const int p = blockIdx.y;
+  const int t0 = poff[p], t1 = poff[p + 1];
+  const float* col = x + c0;
+  int32_t cur[VEC];
+  double rs[VEC], best[VEC];
+  bool skip[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) { cur[i] = 0; rs[i] = 0.0; best[i] = 0.0; skip[i] = false; }
+  auto excess = [&](float v) -> float {
+    const float d = (OP == XC_OP_GT || OP == XC_OP_GE) ? (v - thr) : (thr - v);
+    return (d > 0.f) ? d : 0.f;  // NaN -> 0: not part of a run (rle: da > 0)
+  };
+  if constexpr (AFTER) {
+    if (t0 > 0) {
+      Vec<VEC> r;
+      r.load(col + (int64_t)(t0 - 1) * ldx);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) skip[i] = excess(r.v[i]) > 0.f;
+    }
+  }
+  auto step = [&](const Vec<VEC>& r, bool only_open) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float e = excess(r.v[i]);
+      bool in = e > 0.f;
+      if constexpr (AFTER) {
+        if (!only_open) {
+          skip[i] = skip[i] && in;
+          in = in && !skip[i];
+        } else {
+          in = in && (cur[i] > 0);
+        }
+      }
+      if (in) {
+        cur[i] += 1;
+        rs[i] += (double)e;
+      } else {
+        if (cur[i] >= window) best[i] = fmax(best[i], rs[i]);
+        cur[i] = 0;
+        rs[i] = 0.0;
+      }
+    }
+  };
+  stream_rows<VEC>(col, ldx, t0, t1, [&](const Vec<VEC>& r) { step(r, false); });
+  if constexpr (AFTER) {
+    int t = t1;
+    bool open = false;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) open = open || (cur[i] > 0);
+    while (open && t < (int)T) {
+      Vec<VEC> r;
+      r.load(col + (int64_t)t * ldx);
+      step(r, true);
+      open = false;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) open = open || (cur[i] > 0);
+      ++t;
+    }
+  }
+  float res[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    if (cur[i] >= window) best[i] = fmax(best[i], rs[i]);
+    res[i] = (float)best[i];
+  }
+  store_vec<VEC>(out + (int64_t)p * C + c0, res);
+}
+
+// ------------------------------------------------------------------------------------------------
 // per-period reductions with optional fused transform
 // ------------------------------------------------------------------------------------------------
 template <int STAT, int TF, int OP, int VEC, bool VALID>
@@ -458,4 +538,32 @@ extern "C" int32_t xc_period_reduce_f32(const float* x, int64_t T, int64_t C, in
   }
   set_error("unknown transform %d", transform);
   return XC_ERR_INVALID;
+}
+
+extern "C" int32_t xc_period_run_maxsum_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                            const int32_t* period_offsets, int32_t P, int32_t op, double thr,
+                                            int32_t window, int32_t resample_before_rl, float* out, void* stream) {
+  if (int32_t e = check_common(x, T, C, ldx, period_offsets, P, out)) return e;
+  XC_REQUIRE(window >= 1, "window must be >= 1, got %d", window);
+  XC_REQUIRE(op >= XC_OP_GT && op <= XC_OP_LE, "Operation `%d` not permitted for indice.", op);
+  const float t32 = (float)thr;
+  const bool after = resample_before_rl == 0;
+  const bool v4 = can_vec4(x, C, ldx, out, nullptr);
+  cudaStream_t st = (cudaStream_t)stream;
+  auto go = [&](auto OPC, auto VECC, auto AFTC) -> int32_t {
+    constexpr int OP = decltype(OPC)::value;
+    constexpr int VEC = decltype(VECC)::value;
+    constexpr bool AFT = decltype(AFTC)::value;
+    period_run_maxsum_kernel<OP, VEC, AFT><<<grid_for(C, VEC, P), kThreads, 0, st>>>(x, T, C, ldx, period_offsets,
+                                                                                   t32, window, out);
+    return launch_status("period_run_maxsum_kernel");
+  };
+  auto go2 = [&](auto OPC) -> int32_t {
+    if (v4) return after ? go(OPC, std::integral_constant<int, 4>{}, std::true_type{})
+                         : go(OPC, std::integral_constant<int, 4>{}, std::false_type{});
+    return after ? go(OPC, std::integral_constant<int, 1>{}, std::true_type{})
+                 : go(OPC, std::integral_constant<int, 1>{}, std::false_type{});
+  };
+  return (op == XC_OP_GT || op == XC_OP_GE) ? go2(std::integral_constant<int, XC_OP_GT>{})
+                                            : go2(std::integral_constant<int, XC_OP_LT>{});
 }

@@ -284,3 +284,15 @@ def period_boundary_run(x2d, poff, op_code, thr, window, last=False, cmp_f64=Fal
                                             float(thr), int(bool(cmp_f64)), int(window), int(bool(last)),
                                             out.data_ptr(), current_stream_ptr()))
     return out
+
+
+def period_run_maxsum(x2d, poff, op_code, thr, window, resample_before_rl=True):
+    """windowed_max_run_sum of the excess over ``thr`` per period (run_length.py:491-540)."""
+    T, C = x2d.shape
+    P = len(poff) - 1
+    poff_d = dev_ints(poff, np.int32, x2d.device)
+    out = torch.empty((P, C), dtype=torch.float32, device=x2d.device)
+    check(load().xc_period_run_maxsum_f32(x2d.data_ptr(), T, C, x2d.stride(0), poff_d.data_ptr(), P, op_code,
+                                          float(thr), int(window), int(bool(resample_before_rl)), out.data_ptr(),
+                                          current_stream_ptr()))
+    return out

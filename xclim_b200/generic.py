@@ -170,3 +170,33 @@ def select_rolling_resample_op(da, op, window, window_center=True, window_op="me
     if out_units is not None:
         attrs["units"] = out_units
     return _wrap_periods(da, out, cell_shape, other, ta, freq, attrs)
+
+
+def statistics(data, reducer, freq):
+    """indices/generic.py:1255-1275."""
+    out = select_resample_op(data, reducer, freq)
+    return out.assign_attrs(units=attrs_of(data).get("units", ""))
+
+
+def thresholded_statistics(data, op, threshold, reducer, freq, constrain=None):
+    """Statistic of the values fulfilling ``data op threshold`` -- indices/generic.py:1278-1320."""
+    code = get_op(op, constrain)
+    thr = threshold_in_units_of(threshold, data) if isinstance(threshold, str) else float(threshold)
+    if reducer not in ("max", "min", "mean", "sum"):
+        raise NotImplementedError(f"reducer {reducer!r} is not supported")
+    x2d, cell_shape, other, ta = _unwrap(data)
+    out, _ = device.period_reduce(x2d, ta.period_offsets(freq), _lib.STATS[reducer], _lib.TF_WHERE, code, thr)
+    return _wrap_periods(data, out, cell_shape, other, ta, freq, attrs_of(data))
+
+
+def temperature_sum(data, op, threshold, freq):
+    """indices/generic.py:1323-1357: sum of (data - threshold) where the condition holds, sign-flipped
+    for < / <= -- numerically the clipped difference of :func:`cumulative_difference`."""
+    return cumulative_difference(data, threshold, op, freq)
+
+
+def count_occurrences(data, threshold, freq, op, constrain=None):
+    """indices/generic.py:960-999."""
+    thr = threshold_in_units_of(threshold, data) if isinstance(threshold, str) else threshold
+    out = threshold_count(data, op, thr, freq, constrain)
+    return out.assign_attrs(units="d")

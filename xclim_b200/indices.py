@@ -139,3 +139,17 @@ def wet_spell_frequency(pr, thresh="1.0 mm", window=3, freq="YS", resample_befor
     """indices/_threshold.py:3525-3592."""
     return _dry_wet_spell(pr, thresh.replace(" mm", " mm/d") if isinstance(thresh, str) else thresh, window, ">=", op,
                           "count", freq, resample_before_rl)
+
+
+def hot_spell_max_magnitude(tasmax, thresh="25.0 degC", window=3, freq="YS", resample_before_rl=True):
+    """Largest cumulated exceedance of a hot spell -- indices/_threshold.py:2019-2073; the
+    ``(tasmax - thresh).clip(0)`` array of the reference is never built."""
+    from . import _lib, device
+    from .field import attrs_of
+    from .generic import _unwrap, _wrap_periods
+    thr = threshold_in_units_of(thresh, tasmax)
+    x2d, cell_shape, other, ta = _unwrap(tasmax)
+    out = device.period_run_maxsum(x2d, ta.period_offsets(freq), _lib.OPS[">"], thr, window, resample_before_rl)
+    attrs = attrs_of(tasmax)
+    attrs["units"] = "K d"
+    return _wrap_periods(tasmax, out, cell_shape, other, ta, freq, attrs)

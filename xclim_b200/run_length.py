@@ -117,3 +117,15 @@ def first_run(da, window, dim="time", freq=None, coord=False, ufunc_1dim="from_c
 def last_run(da, window, dim="time", freq=None, coord=False, ufunc_1dim="from_context"):
     """indices/run_length.py:693-740: index of the last item of the last run of at least ``window``."""
     return _boundary(da, window, dim, freq, coord, "last")
+
+
+def windowed_max_run_sum(da, window, dim="time", freq=None, index="first"):
+    """indices/run_length.py:491-540 for a non-negative float input (e.g. an excess over a threshold):
+    largest run sum of the positive values over runs at least ``window`` long."""
+    if dim != "time" or index != "first":
+        raise NotImplementedError("only dim='time', index='first' are supported")
+    if freq is None:
+        raise NotImplementedError("freq=None: pass a freq covering the series")
+    x2d, cell_shape, other, ta = _mask_unwrap(da)
+    out = device.period_run_maxsum(x2d, ta.period_offsets(freq), _GT, 0.0, window, resample_before_rl=False)
+    return _wrap_periods(da, out, cell_shape, other, ta, freq, attrs_of(da), dtype=np.float32)
