@@ -153,3 +153,250 @@ def hot_spell_max_magnitude(tasmax, thresh="25.0 degC", window=3, freq="YS", res
     attrs = attrs_of(tasmax)
     attrs["units"] = "K d"
     return _wrap_periods(tasmax, out, cell_shape, other, ta, freq, attrs)
+
+
+# =====================================================================================================
+# The index families of SURVEY.md section 2.2 (the "batch of 50 atmos indicators" configuration): thin
+# entry points over the same few kernels.  Signatures/defaults follow xclim.indices; thresholds are
+# converted on the host (a Python float reaches the kernel, compared in float32 like numpy >= 2).
+# =====================================================================================================
+def _resample(da, op, freq):
+    return generic.select_resample_op(da, op=op, freq=freq)
+
+
+def _count(da, thresh, op, freq, constrain):
+    thr = threshold_in_units_of(thresh, da) if isinstance(thresh, str) else float(thresh)
+    return generic.threshold_count(da, op, thr, freq, constrain=constrain).assign_attrs(units="d")
+
+
+def _spell(da, thresh, op, constrain, reducer, window, freq, resample_before_rl, units="d", clip_below=None):
+    """compare -> rl.resample_and_rl(<run statistic>, window) (e.g. indices/_threshold.py:204-214)."""
+    import numpy as np
+
+    from . import _lib, device
+    from .field import attrs_of
+    from .generic import _unwrap, _wrap_periods
+    code = _lib.op_code(op, constrain)
+    thr = threshold_in_units_of(thresh, da) if isinstance(thresh, str) else float(thresh)
+    x2d, cell_shape, other, ta = _unwrap(da)
+    out, _ = device.period_runstat(x2d, ta.period_offsets(freq), code, thr, _lib.RL_REDUCERS[reducer], window,
+                                   resample_before_rl)
+    if clip_below is not None:      # `max_l.where(max_l >= window, 0)` (indices/_threshold.py:311)
+        out = out * (out >= clip_below)
+    attrs = attrs_of(da)
+    attrs["units"] = units
+    return _wrap_periods(da, out, cell_shape, other, ta, freq, attrs, dtype=np.float32)
+
+
+# ---- resample reductions (indices/_simple.py:46-303, 447-482; _multivariate.py:930-1056)
+def tg_max(tas, freq="YS"):
+    return _resample(tas, "max", freq)
+
+
+def tg_min(tas, freq="YS"):
+    return _resample(tas, "min", freq)
+
+
+def tn_max(tasmin, freq="YS"):
+    return _resample(tasmin, "max", freq)
+
+
+def tn_mean(tasmin, freq="YS"):
+    return _resample(tasmin, "mean", freq)
+
+
+def tn_min(tasmin, freq="YS"):
+    return _resample(tasmin, "min", freq)
+
+
+def tx_max(tasmax, freq="YS"):
+    return _resample(tasmax, "max", freq)
+
+
+def tx_mean(tasmax, freq="YS"):
+    return _resample(tasmax, "mean", freq)
+
+
+def tx_min(tasmax, freq="YS"):
+    return _resample(tasmax, "min", freq)
+
+
+def max_1day_precipitation_amount(pr, freq="YS"):
+    """indices/_simple.py:447-482 (input in mm/d: the daily amount in mm equals the rate)."""
+    return _resample(pr, "max", freq).assign_attrs(units="mm")
+
+
+def precip_accumulation(pr, freq="YS"):
+    """indices/_multivariate.py:930-991 without phase separation (input in mm/d -> mm)."""
+    return _resample(pr, "sum", freq).assign_attrs(units="mm")
+
+
+def sfcWind_max(sfcWind, freq="YS"):
+    return _resample(sfcWind, "max", freq)
+
+
+def sfcWind_mean(sfcWind, freq="YS"):
+    return _resample(sfcWind, "mean", freq)
+
+
+def sfcWind_min(sfcWind, freq="YS"):
+    return _resample(sfcWind, "min", freq)
+
+
+# ---- threshold counts (indices/_simple.py:334-444, _threshold.py:122-155, 2422-2632, 3135-3167)
+def frost_days(tasmin, thresh="0 degC", freq="YS"):
+    return _count(tasmin, thresh, "<", freq, ("<", "<="))
+
+
+def ice_days(tasmax, thresh="0 degC", freq="YS"):
+    return _count(tasmax, thresh, "<", freq, ("<", "<="))
+
+
+def hot_days(tasmax, thresh="25 degC", freq="YS"):
+    return _count(tasmax, thresh, ">", freq, (">", ">="))
+
+
+def tx_days_above(tasmax, thresh="25.0 degC", freq="YS", op=">"):
+    return _count(tasmax, thresh, op, freq, (">", ">="))
+
+
+def tx_days_below(tasmax, thresh="25.0 degC", freq="YS", op="<"):
+    return _count(tasmax, thresh, op, freq, ("<", "<="))
+
+
+def tn_days_above(tasmin, thresh="20.0 degC", freq="YS", op=">"):
+    return _count(tasmin, thresh, op, freq, (">", ">="))
+
+
+def tn_days_below(tasmin, thresh="-10.0 degC", freq="YS", op="<"):
+    return _count(tasmin, thresh, op, freq, ("<", "<="))
+
+
+def tg_days_above(tas, thresh="10.0 degC", freq="YS", op=">"):
+    return _count(tas, thresh, op, freq, (">", ">="))
+
+
+def tg_days_below(tas, thresh="10.0 degC", freq="YS", op="<"):
+    return _count(tas, thresh, op, freq, ("<", "<="))
+
+
+def calm_days(sfcWind, thresh="2 m s-1", freq="MS"):
+    return _count(sfcWind, thresh, "<", freq, ("<", "<="))
+
+
+def windy_days(sfcWind, thresh="10.8 m s-1", freq="MS"):
+    return _count(sfcWind, thresh, ">=", freq, (">", ">="))
+
+
+def wetdays_prop(pr, thresh="1.0 mm/day", freq="YS", op=">="):
+    """indices/_threshold.py:2792-2834: mean of the boolean wet-day mask per period."""
+    import numpy as np
+    from .field import time_axis_of as _ta
+    cnt = _count(pr, thresh, op, freq, (">", ">="))
+    n = np.diff(_ta(pr).period_offsets(freq)).reshape((-1,) + (1,) * (cnt.values.ndim - 1))
+    out = cnt.values / n
+    from .field import Field, is_xarray
+    if is_xarray(cnt):
+        return cnt.copy(data=out).assign_attrs(units="1")
+    return Field(out, cnt.dims, cnt.time, dict(cnt.coords), {**cnt.attrs, "units": "1"}, cnt.name)
+
+
+# ---- thresholded sums (indices/_threshold.py:680-753, 905-972, 2127-2166)
+def growing_degree_days(tas, thresh="4.0 degC", freq="YS"):
+    return generic.cumulative_difference(tas, threshold=thresh, op=">", freq=freq)
+
+
+def cooling_degree_days(tas, thresh="18 degC", freq="YS"):
+    return generic.cumulative_difference(tas, threshold=thresh, op=">", freq=freq)
+
+
+def heating_degree_days(tas, thresh="17.0 degC", freq="YS"):
+    return generic.cumulative_difference(tas, threshold=thresh, op="<", freq=freq)
+
+
+def daily_pr_intensity(pr, thresh="1 mm/day", freq="YS", op=">="):
+    """indices/_threshold.py:680-753: precipitation of wet days divided by the number of wet days."""
+    import numpy as np
+    thr = threshold_in_units_of(thresh, pr)
+    s = generic.thresholded_statistics(pr, op, thr, "sum", freq, constrain=(">", ">="))
+    wd = _count(pr, thr, op, freq, (">", ">="))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out = s.values.astype(np.float64) / wd.values
+    from .field import Field, is_xarray
+    if is_xarray(s):
+        return s.copy(data=out).assign_attrs(units="mm d-1")
+    return Field(out, s.dims, s.time, dict(s.coords), {**s.attrs, "units": "mm d-1"}, s.name)
+
+
+# ---- spells on runs (indices/_threshold.py:158-313, 1476-1523, 1972-2016, 2169-2345, 2837-3000)
+def cold_spell_days(tas, thresh="-10 degC", window=5, freq="YS-JUL", op="<", resample_before_rl=True):
+    return _spell(tas, thresh, op, ("<", "<="), "sum", window, freq, resample_before_rl)
+
+
+def cold_spell_frequency(tas, thresh="-10 degC", window=5, freq="YS-JUL", op="<", resample_before_rl=True):
+    return _spell(tas, thresh, op, ("<", "<="), "count", window, freq, resample_before_rl, units="")
+
+
+def cold_spell_max_length(tas, thresh="-10 degC", window=1, freq="YS-JUL", op="<", resample_before_rl=True):
+    return _spell(tas, thresh, op, ("<", "<="), "max", 1, freq, resample_before_rl, clip_below=window)
+
+
+def cold_spell_total_length(tas, thresh="-10 degC", window=3, freq="YS-JUL", op="<", resample_before_rl=True):
+    return _spell(tas, thresh, op, ("<", "<="), "sum", window, freq, resample_before_rl)
+
+
+def hot_spell_frequency(tasmax, thresh="30 degC", window=3, freq="YS", op=">", resample_before_rl=True):
+    return _spell(tasmax, thresh, op, (">", ">="), "count", window, freq, resample_before_rl, units="")
+
+
+def hot_spell_max_length(tasmax, thresh="30 degC", window=1, freq="YS", op=">", resample_before_rl=True):
+    return _spell(tasmax, thresh, op, (">", ">="), "max", 1, freq, resample_before_rl, clip_below=window)
+
+
+def hot_spell_total_length(tasmax, thresh="30 degC", window=3, freq="YS", op=">", resample_before_rl=True):
+    return _spell(tasmax, thresh, op, (">", ">="), "sum", window, freq, resample_before_rl)
+
+
+def heat_wave_index(tasmax, thresh="25.0 degC", window=5, freq="YS", op=">", resample_before_rl=True):
+    return _spell(tasmax, thresh, op, (">", ">="), "sum", window, freq, resample_before_rl)
+
+
+def frost_free_spell_max_length(tasmin, thresh="0.0 degC", window=1, freq="YS-JUL", op=">=", resample_before_rl=True):
+    return _spell(tasmin, thresh, op, (">", ">="), "max", 1, freq, resample_before_rl, clip_below=window)
+
+
+def maximum_consecutive_frost_days(tasmin, thresh="0.0 degC", freq="YS-JUL", resample_before_rl=True):
+    return cold_spell_max_length(tasmin, thresh=thresh, window=1, freq=freq, op="<",
+                                 resample_before_rl=resample_before_rl)
+
+
+def maximum_consecutive_frost_free_days(tasmin, thresh="0 degC", freq="YS", resample_before_rl=True):
+    return frost_free_spell_max_length(tasmin, thresh=thresh, window=1, freq=freq, op=">=",
+                                       resample_before_rl=resample_before_rl)
+
+
+def maximum_consecutive_tx_days(tasmax, thresh="25 degC", freq="YS", resample_before_rl=True):
+    return hot_spell_max_length(tasmax, thresh=thresh, window=1, freq=freq, op=">",
+                                resample_before_rl=resample_before_rl)
+
+
+#: the (name, variable) list of the "batch of 50" configuration (BASELINE.json configs[4]); every entry is
+#: parity-tested against the oracle in tests/test_gpu_batch.py
+BATCH_INDICATORS = [
+    ("tg_mean", "tas"), ("tg_max", "tas"), ("tg_min", "tas"), ("tn_mean", "tasmin"), ("tn_max", "tasmin"),
+    ("tn_min", "tasmin"), ("tx_mean", "tasmax"), ("tx_max", "tasmax"), ("tx_min", "tasmax"),
+    ("max_1day_precipitation_amount", "pr"), ("precip_accumulation", "pr"), ("max_n_day_precipitation_amount", "pr"),
+    ("frost_days", "tasmin"), ("ice_days", "tasmax"), ("hot_days", "tasmax"), ("tx_days_above", "tasmax"),
+    ("tx_days_below", "tasmax"), ("tn_days_above", "tasmin"), ("tn_days_below", "tasmin"), ("tg_days_above", "tas"),
+    ("tg_days_below", "tas"), ("wetdays", "pr"), ("dry_days", "pr"), ("wetdays_prop", "pr"),
+    ("growing_degree_days", "tas"), ("cooling_degree_days", "tas"), ("heating_degree_days", "tas"),
+    ("daily_pr_intensity", "pr"),
+    ("cold_spell_days", "tas"), ("cold_spell_frequency", "tas"), ("cold_spell_max_length", "tas"),
+    ("cold_spell_total_length", "tas"), ("hot_spell_frequency", "tasmax"), ("hot_spell_max_length", "tasmax"),
+    ("hot_spell_total_length", "tasmax"), ("hot_spell_max_magnitude", "tasmax"), ("heat_wave_index", "tasmax"),
+    ("frost_free_spell_max_length", "tasmin"), ("maximum_consecutive_frost_days", "tasmin"),
+    ("maximum_consecutive_frost_free_days", "tasmin"), ("maximum_consecutive_tx_days", "tasmax"),
+    ("maximum_consecutive_dry_days", "pr"), ("maximum_consecutive_wet_days", "pr"),
+    ("dry_spell_frequency", "pr"), ("dry_spell_total_length", "pr"), ("dry_spell_max_length", "pr"),
+    ("wet_spell_frequency", "pr"), ("tx90p", "tasmax"), ("tx10p", "tasmax"), ("tn90p", "tasmin"),
+]
