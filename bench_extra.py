@@ -91,6 +91,32 @@ def main():
         ms = timeit(fn, max(1, a.steps // 2), warmup=1)
         report("bootstrap_doy_count (tx90p 3b: 15-year base, 14 resamples per year)", ms, T * C * 4 + P * C * 8,
                {"quantile_evaluations_per_cell": nb * (nb - 1) * YEAR})
+    if want("batch50"):
+        from xclim_b200 import Field, TimeAxis, indices, calendar as xcal
+        ta = TimeAxis.daily("1981-01-01", T, "noleap")
+        tasmin = tas - 8.0
+        mk = lambda t, u: Field(t.reshape(T, a.lat, X), ("time", "lat", "lon"), ta, {}, {"units": u})  # noqa: E731
+        fields = {"tas": mk(tas, "K"), "tasmax": mk(tas, "K"), "tasmin": mk(tasmin, "K"), "pr": mk(pr, "mm/d")}
+        pers = {p_: xcal.select_percentile(xcal.percentile_doy(fields["tasmax"], window=5, per=p_), p_) for p_ in (10.0, 90.0)}
+
+        def run_batch():
+            for name, var in indices.BATCH_INDICATORS:
+                fn = getattr(indices, name)
+                if name in ("tx90p", "tn90p"):
+                    fn(fields[var], pers[90.0])
+                elif name == "tx10p":
+                    fn(fields[var], pers[10.0])
+                else:
+                    fn(fields[var])
+        import time
+        run_batch()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run_batch()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        report("batch of 50 atmos indicators (sequential calls, outputs copied to host)", ms, 50 * T * C * 4,
+               {"unique_input_bytes": 4 * T * C * 4, "note": "effective GB/s = sum of per-indicator input bytes / time"})
     if want("eqm"):
         hist = device.synth(T, C, kind=1, seed=5, cells_per_lat=X, n_lat_global=a.lat)
         ms = timeit(lambda: device.eqm_train(tas, hist, 20, 0), max(1, a.steps // 2), warmup=1)
