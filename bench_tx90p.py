@@ -63,6 +63,20 @@ def tx90p_section(args, dev, rank, world, peak, barrier):
     assert 0.07 < frac < 0.13, frac
     assert table_equal and counts_equal, (table_equal, counts_equal)
 
+    # ---- CPU side of the same path: the oracle port (rolling construct + unstack + sort-based quantile +
+    # reindex-by-doy count, like the reference) on a bounded sample, one process
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import time
+        ncell = 4096
+        xs_cpu = tasmax[:, :ncell].cpu().numpy()
+        t0 = time.perf_counter()
+        tab_c = O.percentile_doy(xs_cpu, yidx.astype(np.int64), doy.astype(np.int64), 5, 90.0)[:, 0]
+        O.doy_threshold_count(xs_cpu, tab_c, doy.astype(np.int64), poff, ">")
+        dt = time.perf_counter() - t0
+        cpu = {"value": ncell / dt, "unit": "grid-cells/s", "cores": 1, "kind": "port",
+               "sample": f"(10950, {ncell}) cells, percentile_doy + count, {dt:.1f} s"}
+
     alg_per = T * C * 4 + YEAR * C * 8
     alg_cnt = T * C * 4 + YEAR * C * 8 + N * C * 4 * 2
     ach_per = alg_per / (t_per * 1e-3) / 1e9
@@ -76,7 +90,7 @@ def tx90p_section(args, dev, rank, world, peak, barrier):
                                     "kernel": "percentile_doy_uniform_kernel<16,5>"},
         "roofline_count": {"bound": "hbm", "achieved": ach_cnt, "peak": peak, "unit": "GB/s",
                            "frac": ach_cnt / peak, "algorithmic_bytes": alg_cnt, "kernel": "doy_count_kernel<GT>"},
-        "gpu_launches_per_step": 2,
+        "gpu_launches_per_step": 2, "cpu_baseline": cpu,
         "check": {"oracle_cells": int(sel.numel()), "table_bit_exact": table_equal, "counts_exact": counts_equal,
                   "mean_exceedance_fraction": frac},
     }

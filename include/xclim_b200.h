@@ -130,6 +130,20 @@ int32_t xc_period_boundary_run_f32(const float* x, int64_t T, int64_t C, int64_t
                                    int32_t op, double thr, int32_t cmp_f64,
                                    int32_t window, int32_t position_last, float* out, void* stream);
 
+/* a12 (cont.)  runs confined to a per-period sub-range: the per-group calls of
+ *   run_length.first_run_after_date / last_run_before_date / first_run_before_date /
+ *   run_end_after_date (indices/run_length.py:1148-1331) and the two steps of run_length.season
+ *   (:998-1110).  Period p is searched on [range_lo[p], range_hi[p]) (absolute steps; range_lo < 0:
+ *   the date is not in the group -> NaN); negate != 0 runs on NOT(x op thr) (season end, `~da`);
+ *   cell_lo (optional (P, C) float32, relative to the period start, NaN -> 0) raises the lower
+ *   bound per cell (`index >= beg.fillna(0)`, :977).  out as xc_period_boundary_run_f32. */
+int32_t xc_period_boundary_run_range_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                         const int32_t* period_offsets, const int32_t* range_lo,
+                                         const int32_t* range_hi, int32_t P,
+                                         int32_t op, double thr, int32_t cmp_f64, int32_t negate,
+                                         int32_t window, int32_t position_last,
+                                         const float* cell_lo, float* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a3  per-period reductions -- indices/generic.py:83-125 (`select_resample_op`), 1255-1320
  *   (`statistics`, `thresholded_statistics`), 1514-1552 (`cumulative_difference`); _simple.py:113

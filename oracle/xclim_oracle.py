@@ -688,3 +688,87 @@ def eqm_adjust(sim, af, hist_q, kind="+", interp="linear"):
         col[m] = res
         out[:, c] = col.astype(sim.dtype)
     return out.reshape(sim.shape)
+
+
+# --------------------------------------------------------------------------------------------------
+# a12 (cont.) date-bounded runs and seasons, per GROUP (indices/run_length.py:891-1331).  ``da`` is a
+# boolean group (n, ...); ``mid`` is the index of the MM-DD date inside the group (``index_of_date``,
+# :1621-1665) or None when the date is absent / not requested.
+# --------------------------------------------------------------------------------------------------
+def _masked(da, keep):
+    """``da.where(keep)``: NaN outside (later ``fillna(0)`` -> False, run_length.py:612)."""
+    daf = np.asarray(da, dtype=np.float64)
+    k = keep.reshape((-1,) + (1,) * (daf.ndim - 1))
+    return np.where(k, daf, np.nan)
+
+
+def first_run_after_date(da, window, mid):
+    """indices/run_length.py:1204-1244."""
+    da = np.asarray(da)
+    if mid is None:
+        return np.full(da.shape[1:], np.nan)
+    idx = np.arange(da.shape[0])
+    return boundary_run(_masked(da, idx >= mid), window, "first")
+
+
+def last_run_before_date(da, window, mid):
+    """indices/run_length.py:1247-1284."""
+    da = np.asarray(da)
+    if mid is None:
+        return np.full(da.shape[1:], np.nan)
+    idx = np.arange(da.shape[0])
+    return boundary_run(_masked(da, idx <= mid), window, "last")
+
+
+def first_run_before_date(da, window, mid, has_date=True):
+    """indices/run_length.py:1287-1331 (``has_date=False``: ``date=None`` -> plain first_run)."""
+    da = np.asarray(da)
+    if has_date:
+        if mid is None:
+            return np.full(da.shape[1:], np.nan)
+        idx = np.arange(da.shape[0])
+        da = _masked(da, idx < mid + window - 1)
+    return boundary_run(da, window, "first")
+
+
+def run_end_after_date(da, window, mid):
+    """indices/run_length.py:1148-1201 (index outputs)."""
+    da = np.asarray(da).astype(bool)
+    if mid is None:
+        return np.full(da.shape[1:], np.nan)
+    idx = np.arange(da.shape[0])
+    end = boundary_run(_masked(~da, idx >= mid), window, "first")
+    beg = boundary_run(_masked(da, idx < mid), window, "first")
+    end = np.where(np.isnan(end) & ~np.isnan(beg), da.shape[0] - 1, end)
+    return np.where(np.isnan(beg), np.nan, end)
+
+
+def season_group(da, window, mid, has_date=True):
+    """indices/run_length.py:998-1110 with ``coord=False``: (start, end, length) of one group."""
+    da = np.asarray(da).astype(bool)
+    n = da.shape[0]
+    beg = first_run_before_date(da, window, mid, has_date)                       # season_start (:929)
+    idx = np.arange(n).reshape((-1,) + (1,) * (da.ndim - 1))
+    not_da = np.where(idx >= np.where(np.isnan(beg), 0, beg), (~da).astype(np.float64), np.nan)   # :977
+    if has_date:
+        end = first_run_after_date(not_da, window, mid)                          # :978
+    else:
+        end = boundary_run(not_da, window, "first")                              # date=None -> index 0
+    length = np.where(np.isnan(beg), 0, np.where(np.isnan(end), n - beg, end - beg))   # :1072-1077
+    end = np.where(np.isnan(end) & ~np.isnan(beg), n - 1, end)                   # :1081-1082
+    end = np.where(np.isnan(beg), np.nan, end)
+    return beg, end, length
+
+
+def season(cond, window, mids, poff, stat, doy=None, has_date=True):
+    """indices/generic.py:769-853 after the compare: per period ``season_*`` (start/end as dayofyear)."""
+    outs = []
+    for p, (s, e) in enumerate(_groups(poff)):
+        beg, end, length = season_group(cond[s:e], window, mids[p] if has_date else None, has_date)
+        if stat == "length":
+            outs.append(length)
+        else:
+            v = beg if stat == "start" else end
+            t = np.where(np.isnan(v), 0, v).astype(int) + s
+            outs.append(np.where(np.isnan(v), np.nan, np.asarray(doy)[t]))
+    return np.stack(outs, axis=0)

@@ -190,3 +190,59 @@ def test_live_against_reference_sources():
         warnings.simplefilter("ignore")
         exp = ut["calc_perc"](x.copy(), [10.0, 90.0], 1 / 3, 1 / 3)
     np.testing.assert_array_equal(O.calc_perc(x, [10.0, 90.0], 1 / 3, 1 / 3), exp)
+
+
+def _warm(d1, d2, n=365, start="2000-01-01"):
+    """tas = 0 K except 280 K between the two dates (tests/test_indices.py:1668-1672)."""
+    import pandas as pd
+    from xclim_b200 import TimeAxis
+    idx = pd.date_range(start, periods=n, freq="D")
+    tas = np.zeros(n, np.float32)
+    tas[(idx >= d1) & (idx <= d2)] = 280
+    return tas, TimeAxis.daily(start, n)
+
+
+@pytest.mark.parametrize("d1,d2,mid_date,expected", [
+    ("1950-01-01", "1951-01-01", "07-01", np.nan), ("2000-01-01", "2000-12-31", "07-01", 365),
+    ("2000-07-10", "2001-01-01", "07-01", np.nan), ("2000-06-15", "2000-07-15", "07-01", 198),
+    ("2000-06-15", "2000-07-25", "07-15", 208), ("2000-06-15", "2000-07-15", "10-01", 275),
+    ("2000-06-15", "2000-07-15", "01-10", np.nan), ("2000-06-15", "2000-07-15", "06-15", np.nan)])
+def test_known_answers_growing_season_end(d1, d2, mid_date, expected):
+    # tests/test_indices.py:1654-1678
+    tas, ta = _warm(d1, d2)
+    mids = ta.date_index_in_periods("YS", mid_date)
+    out = O.season(tas > np.float32(278.15), 5, [int(m) if m >= 0 else None for m in mids], ta.period_offsets("YS"), "end", ta.doy)
+    np.testing.assert_array_equal(out[0], expected)
+
+
+@pytest.mark.parametrize("d1,d2,expected", [("1950-01-01", "1951-01-01", 0), ("2000-01-01", "2000-12-31", 365),
+                                            ("2000-07-10", "2001-01-01", 0), ("2000-06-15", "2001-01-01", 199),
+                                            ("2000-06-15", "2000-07-15", 31)])
+def test_known_answers_growing_season_length(d1, d2, expected):
+    # tests/test_indices.py:1681-1700
+    tas, ta = _warm(d1, d2)
+    mids = ta.date_index_in_periods("YS", "07-01")
+    out = O.season(tas >= np.float32(278.15), 6, [int(m) for m in mids], ta.period_offsets("YS"), "length", ta.doy)
+    assert out[0] == expected
+
+
+def test_known_answers_season_and_start():
+    # tests/test_run_length.py:674-690 ; tests/test_indices.py:1625-1645
+    t = np.zeros(360); t[140:150] = 1
+    beg, end, length = O.season_group(t >= 1, 2, None, has_date=False)
+    assert (beg, end, length) == (140, 150, 10)
+    tg = np.zeros(365) - 1
+    tg[10:14] += 6; tg[20:25] += 6; tg[30:36] += 6
+    beg, _, _ = O.season_group(tg + 273.15 >= 278.15, 5, 182)
+    assert beg == 20
+    # south hemisphere (tests/test_indices.py:1702-1707): YS-JUL groups, mid_date 01-01
+    from xclim_b200 import TimeAxis
+    import pandas as pd
+    idx = pd.date_range("2000-01-01", periods=730, freq="D")
+    tas = np.zeros(730, np.float32); tas[(idx >= "2000-11-01") & (idx <= "2001-03-01")] = 280
+    ta = TimeAxis.daily("2000-01-01", 730)
+    mids = ta.date_index_in_periods("YS-JUL", "01-01")
+    poff = ta.period_offsets("YS-JUL")
+    rel = [int(m) - int(s) if m >= 0 else None for m, s in zip(mids, poff[:-1])]   # index inside each group
+    out = O.season(tas >= np.float32(278.15), 6, rel, poff, "length", ta.doy)
+    assert out[ta.period_labels("YS-JUL").index("2000-07-01")] == 121

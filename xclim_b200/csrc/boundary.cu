@@ -97,3 +97,101 @@ extern "C" int32_t xc_period_boundary_run_f32(const float* x, int64_t T, int64_t
     return launch_status("boundary_run_kernel");
   });
 }
+
+// ------------------------------------------------------------------------------------------------
+// Runs confined to a per-period sub-range (date-bounded runs and seasons)
+// ------------------------------------------------------------------------------------------------
+// Replaces the per-group calls of indices/run_length.py:1148-1331 (`run_end_after_date`,
+// `first_run_after_date`, `last_run_before_date`, `first_run_before_date`) and the two steps of
+// `season` (:998-1110): the reference masks the group outside a date range (`da.where(time >= date)`,
+// NaN -> False) and calls first_run / last_run on the group, so runs are confined to the range and to
+// the group.  Here the range of period p is [range_lo[p], range_hi[p]) (absolute steps, inside the
+// period; range_lo[p] < 0 = "the date is not in this group" -> NaN), `negate` evaluates the run on
+// NOT(condition) (season end: `~da`, NaN data count as condition broken) and `cell_lo` (optional,
+// (P, C) float32, relative to the period start, NaN -> 0) raises the lower bound per cell
+// (`index >= beg.fillna(0)`, :977).
+namespace xc {
+namespace {
+
+template <int OP>
+__global__ void __launch_bounds__(kThreads)
+boundary_run_range_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, const int32_t* __restrict__ poff,
+                          const int32_t* __restrict__ rlo, const int32_t* __restrict__ rhi, float thr,
+                          int32_t negate, int32_t window, int32_t last, const float* __restrict__ cell_lo,
+                          float* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (c >= C) return;
+  const int p = blockIdx.y;
+  const int t0 = poff[p], t1 = poff[p + 1];
+  int lo = rlo[p], hi = min(rhi[p], t1);
+  float res = NAN;
+  if (lo >= 0) {
+    lo = max(lo, t0);
+    bool full = (lo == t0) && (hi == t1);
+    if (cell_lo != nullptr) {
+      const float b = cell_lo[(int64_t)p * C + c];
+      const int bl = (b == b) ? (int)b : 0;
+      if (t0 + bl > lo) { lo = t0 + bl; full = false; }
+    }
+    const float* col = x + c;
+    auto cond = [&](int s) -> bool {
+      const bool m = cmp<OP>(ld_stream(col + (int64_t)s * ldx), thr);
+      return negate ? !m : m;
+    };
+    if (window == 1 && full) {
+      // argmax == argmin rule on the whole group (indices/run_length.py:603-605): all-True -> NaN
+      int first = -1, lastt = -1, ntrue = 0;
+      for (int s = lo; s < hi; ++s) {
+        if (cond(s)) {
+          if (first < 0) first = s;
+          lastt = s;
+          ++ntrue;
+        }
+      }
+      if (ntrue > 0 && ntrue < hi - lo) res = (float)((last ? lastt : first) - t0);
+    } else if (!last) {
+      int cur = 0;
+      for (int s = lo; s < hi; ++s) {
+        cur = cond(s) ? cur + 1 : 0;
+        if (cur >= window) {
+          res = (float)(s - window + 1 - t0);
+          break;
+        }
+      }
+    } else {
+      int cur = 0;
+      for (int s = hi - 1; s >= lo; --s) {
+        cur = cond(s) ? cur + 1 : 0;
+        if (cur >= window) {
+          res = (float)(s + window - 1 - t0);
+          break;
+        }
+      }
+    }
+  }
+  out[(int64_t)p * C + c] = res;
+}
+
+}  // namespace
+}  // namespace xc
+
+extern "C" int32_t xc_period_boundary_run_range_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                                    const int32_t* period_offsets, const int32_t* range_lo,
+                                                    const int32_t* range_hi, int32_t P, int32_t op, double thr,
+                                                    int32_t cmp_f64, int32_t negate, int32_t window,
+                                                    int32_t position_last, const float* cell_lo, float* out,
+                                                    void* stream) {
+  XC_REQUIRE(x && period_offsets && range_lo && range_hi && out, "null pointer argument");
+  XC_REQUIRE(T > 0 && C > 0 && ldx >= C && P > 0 && P <= 65535 && T < 2147483647LL, "bad shape");
+  XC_REQUIRE(window >= 1, "window must be >= 1");
+  const float t32 = fold_threshold(op, thr, cmp_f64);
+  dim3 grid((unsigned)((C + kThreads - 1) / kThreads), (unsigned)P, 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  return dispatch_op(op, [&](auto OPC) -> int32_t {
+    constexpr int OP = decltype(OPC)::value;
+    boundary_run_range_kernel<OP><<<grid, kThreads, 0, st>>>(x, C, ldx, period_offsets, range_lo, range_hi, t32,
+                                                             negate ? 1 : 0, window, position_last ? 1 : 0, cell_lo,
+                                                             out);
+    return launch_status("boundary_run_range_kernel");
+  });
+}

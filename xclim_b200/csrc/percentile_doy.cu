@@ -61,11 +61,12 @@ template <int K>
 __global__ void __launch_bounds__(kThreads)
 percentile_doy_generic_kernel(const float* __restrict__ x, int64_t T, int64_t C, int64_t ldx,
                               const int32_t* __restrict__ pos, int32_t n_doy, int32_t n_years, int32_t h,
-                              QuantSpec spec, int32_t doys_per_chunk, double* __restrict__ out) {
+                              QuantSpec spec, int32_t doys_per_chunk, double* __restrict__ out,
+                              int32_t d_begin, int32_t d_end) {
   const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (c >= C) return;
-  const int d0 = blockIdx.y * doys_per_chunk;
-  const int d1 = min(n_doy, d0 + doys_per_chunk);
+  const int d0 = d_begin + blockIdx.y * doys_per_chunk;
+  const int d1 = min(d_end, d0 + doys_per_chunk);
   const float* col = x + c;
   const bool top = spec.top != 0;
   for (int d = d0; d < d1; ++d) {
@@ -92,10 +93,43 @@ percentile_doy_generic_kernel(const float* __restrict__ x, int64_t T, int64_t C,
 // Sorted (descending) K extremes of Y(e) = { x[y*L + e] : 0 <= y*L + e < T } ; e may lie in
 // [-h, L+h) (the window reaches into the neighbouring year, core/calendar.py:448 pads only at the
 // two ends of the SERIES).
+// Table mode (pos != nullptr; calendars whose years differ in length): the row of (year y, day e) is
+// pos[y * n_doy + e] (-1 when that day does not exist); only days e in [0, n_doy) are requested.
 template <int K>
 __device__ __forceinline__ void load_day_list(const float* __restrict__ x, int64_t c, int64_t ldx, int T, int L,
-                                              int N, int e, bool top, float (&lst)[K], int& n) {
+                                              int N, int e, bool top, float (&lst)[K], int& n,
+                                              const int32_t* __restrict__ pos = nullptr, int n_doy = 0) {
   n = 0;
+  if (pos != nullptr) {
+    bool first_t = true;
+    for (int y0 = 0; y0 < N; y0 += K) {
+      float v[K];
+      int nv = 0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int y = y0 + k;
+        const int row = (y < N) ? pos[y * n_doy + e] : -1;
+        float r = XC_NEG_INF;
+        if (row >= 0) {
+          r = ld_stream(x + (int64_t)row * ldx + c);
+          const bool ok = (r == r);
+          nv += ok ? 1 : 0;
+          r = ok ? (top ? r : -r) : XC_NEG_INF;
+        }
+        v[k] = r;
+      }
+      n += nv;
+      sort_desc<K>(v);
+      if (first_t) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) lst[k] = v[k];
+        first_t = false;
+      } else {
+        merge_top_desc<K>(lst, v);
+      }
+    }
+    return;
+  }
   // rows y*L + e that exist: e < 0 reaches into the previous year (no year -1), e >= L into the next
   const int ylo = (e < 0) ? 1 : 0;
   const int yhi = (e >= L) ? N - 1 : N;
@@ -165,7 +199,8 @@ template <int K>
 __global__ void __launch_bounds__(kThreads)
 percentile_doy_uniform_kernel(const float* __restrict__ x, int32_t T, int64_t C, int64_t ldx, int32_t L,
                               int32_t N, int32_t W, QuantSpec spec, int32_t doys_per_chunk,
-                              double* __restrict__ out) {
+                              double* __restrict__ out, const int32_t* __restrict__ pos, int32_t n_doy,
+                              int32_t d_begin, int32_t d_end) {
   extern __shared__ float smem[];
   const int H = W / 2;
   const int R = W - 1;  // ring slots
@@ -174,8 +209,8 @@ percentile_doy_uniform_kernel(const float* __restrict__ x, int32_t T, int64_t C,
   const int lane = threadIdx.x;
   const int64_t c = (int64_t)blockIdx.x * kThreads + lane;
   if (c >= C) return;  // no block-level synchronisation below: every lane owns its smem column
-  const int d0 = blockIdx.y * doys_per_chunk;
-  const int d1 = min(L, d0 + doys_per_chunk);
+  const int d0 = d_begin + blockIdx.y * doys_per_chunk;
+  const int d1 = min(d_end, d0 + doys_per_chunk);
   if (d0 >= d1) return;
   const bool top = spec.top != 0;
 
@@ -183,14 +218,14 @@ percentile_doy_uniform_kernel(const float* __restrict__ x, int32_t T, int64_t C,
   int nnew;
   // prologue: day lists e = d0-H .. d0+H-1 -> ring slots 0..R-1 (slot = (e - (d0-H)) mod R)
   for (int s = 0; s < R; ++s) {
-    load_day_list<K>(x, c, ldx, T, L, N, d0 - H + s, top, ynew, nnew);
+    load_day_list<K>(x, c, ldx, T, L, N, d0 - H + s, top, ynew, nnew, pos, n_doy);
 #pragma unroll
     for (int k = 0; k < K; ++k) ring[((size_t)s * K + k) * kThreads + lane] = ynew[k];
     rcnt[s * kThreads + lane] = nnew;
   }
   int oldest = 0;  // slot holding day list e = d-H
   for (int d = d0; d < d1; ++d) {
-    load_day_list<K>(x, c, ldx, T, L, N, d + H, top, ynew, nnew);
+    load_day_list<K>(x, c, ldx, T, L, N, d + H, top, ynew, nnew, pos, n_doy);
     float acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = ynew[k];
@@ -222,15 +257,16 @@ percentile_doy_uniform_kernel(const float* __restrict__ x, int32_t T, int64_t C,
 template <int K>
 __global__ void __launch_bounds__(kThreads)
 percentile_doy_w5_kernel(const float* __restrict__ x, int32_t T, int64_t C, int64_t ldx, int32_t L, int32_t N,
-                         QuantSpec spec, int32_t doys_per_chunk, double* __restrict__ out) {
+                         QuantSpec spec, int32_t doys_per_chunk, double* __restrict__ out,
+                         const int32_t* __restrict__ pos, int32_t n_doy, int32_t d_begin, int32_t d_end) {
   extern __shared__ float smem[];
   float* ring = smem;                                                   // [3][K][kThreads]
   int* rcnt = reinterpret_cast<int*>(smem + (size_t)3 * K * kThreads);  // [3][kThreads]
   const int lane = threadIdx.x;
   const int64_t c = (int64_t)blockIdx.x * kThreads + lane;
   if (c >= C) return;
-  const int d0 = blockIdx.y * doys_per_chunk;
-  const int d1 = min(L, d0 + doys_per_chunk);
+  const int d0 = d_begin + blockIdx.y * doys_per_chunk;
+  const int d1 = min(d_end, d0 + doys_per_chunk);
   if (d0 >= d1) return;
   const bool top = spec.top != 0;
   const int n_full = 5 * N;
@@ -244,9 +280,9 @@ percentile_doy_w5_kernel(const float* __restrict__ x, int32_t T, int64_t C, int6
   float yprev[K], ynew[K];
   int nprev, nnew;
   // prologue: A(d0-1) -> slot 0, A(d0) -> slot 1, A(d0+1) -> slot 2 ; yprev = Y(d0+1)
-  load_day_list<K>(x, c, ldx, T, L, N, d0 - 2, top, yprev, nprev);
+  load_day_list<K>(x, c, ldx, T, L, N, d0 - 2, top, yprev, nprev, pos, n_doy);
   for (int j = 0; j < 3; ++j) {
-    load_day_list<K>(x, c, ldx, T, L, N, d0 - 1 + j, top, ynew, nnew);
+    load_day_list<K>(x, c, ldx, T, L, N, d0 - 1 + j, top, ynew, nnew, pos, n_doy);
     merge_top_desc<K>(yprev, ynew);  // yprev <- A(d0-1+j)
     store_pair(j, yprev, nprev + nnew);
 #pragma unroll
@@ -255,7 +291,7 @@ percentile_doy_w5_kernel(const float* __restrict__ x, int32_t T, int64_t C, int6
   }
   int s_lo = 0;  // slot of A(d-1); A(d+1) lives in slot (s_lo + 2) % 3
   for (int d = d0; d < d1; ++d) {
-    load_day_list<K>(x, c, ldx, T, L, N, d + 2, top, ynew, nnew);
+    load_day_list<K>(x, c, ldx, T, L, N, d + 2, top, ynew, nnew, pos, n_doy);
     const int s_hi = (s_lo + 2 >= 3) ? s_lo - 1 : s_lo + 2;
     float t[K];
     {
@@ -484,28 +520,38 @@ doy_count_years_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int6
 
 template <int K>
 int32_t launch_generic(const float* x, int64_t T, int64_t C, int64_t ldx, const int32_t* pos, int32_t n_doy,
-                       int32_t n_years, int32_t h, const QuantSpec& spec, double* out, cudaStream_t st) {
+                       int32_t n_years, int32_t h, const QuantSpec& spec, double* out, cudaStream_t st,
+                       int d_begin = 0, int d_end = -1) {
+  if (d_end < 0) d_end = n_doy;
+  const int nd = d_end - d_begin;
+  if (nd <= 0) return XC_OK;
   const int64_t cblocks = (C + kThreads - 1) / kThreads;
   // enough chunks to fill the machine when the grid is narrow
   int chunks = (int)((148 * 8 + cblocks - 1) / cblocks);
-  chunks = chunks < 1 ? 1 : (chunks > n_doy ? n_doy : chunks);
-  const int per = (n_doy + chunks - 1) / chunks;
-  chunks = (n_doy + per - 1) / per;
+  chunks = chunks < 1 ? 1 : (chunks > nd ? nd : chunks);
+  const int per = (nd + chunks - 1) / chunks;
+  chunks = (nd + per - 1) / per;
   dim3 grid((unsigned)cblocks, (unsigned)chunks, 1);
-  percentile_doy_generic_kernel<K><<<grid, kThreads, 0, st>>>(x, T, C, ldx, pos, n_doy, n_years, h, spec, per, out);
+  percentile_doy_generic_kernel<K><<<grid, kThreads, 0, st>>>(x, T, C, ldx, pos, n_doy, n_years, h, spec, per, out,
+                                                              d_begin, d_end);
   return launch_status("percentile_doy_generic_kernel");
 }
 
+// pos == nullptr: uniform years (days [0, L)); else table mode on the interior days [d_begin, d_end)
 template <int K>
 int32_t launch_uniform(const float* x, int64_t T, int64_t C, int64_t ldx, int32_t L, int32_t N, int32_t W,
-                       const QuantSpec& spec, double* out, cudaStream_t st) {
+                       const QuantSpec& spec, double* out, cudaStream_t st, const int32_t* pos = nullptr,
+                       int n_doy = 0, int d_begin = 0, int d_end = -1) {
+  if (d_end < 0) d_end = L;
+  const int nd = d_end - d_begin;
+  if (nd <= 0) return XC_OK;
   const int64_t cblocks = (C + kThreads - 1) / kThreads;
   int chunks = (int)((148 * 12 + cblocks - 1) / cblocks);
   chunks = chunks < 1 ? 1 : chunks;
-  int per = (L + chunks - 1) / chunks;
+  int per = (nd + chunks - 1) / chunks;
   if (per < 8 * W) per = 8 * W;  // keep the halo overhead (W-1 extra day lists per chunk) small
-  if (per > L) per = L;
-  chunks = (L + per - 1) / per;
+  if (per > nd) per = nd;
+  chunks = (nd + per - 1) / per;
   const size_t smem = (size_t)(W - 1) * (K + 1) * kThreads * 4;
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(percentile_doy_uniform_kernel<K>,
@@ -513,23 +559,29 @@ int32_t launch_uniform(const float* x, int64_t T, int64_t C, int64_t ldx, int32_
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(percentile_doy_uniform_kernel)");
   }
   dim3 grid((unsigned)cblocks, (unsigned)chunks, 1);
-  percentile_doy_uniform_kernel<K><<<grid, kThreads, smem, st>>>(x, (int32_t)T, C, ldx, L, N, W, spec, per, out);
+  percentile_doy_uniform_kernel<K><<<grid, kThreads, smem, st>>>(x, (int32_t)T, C, ldx, L, N, W, spec, per, out, pos,
+                                                                 n_doy, d_begin, d_end);
   return launch_status("percentile_doy_uniform_kernel");
 }
 
 template <int K>
 int32_t launch_w5(const float* x, int64_t T, int64_t C, int64_t ldx, int32_t L, int32_t N, const QuantSpec& spec,
-                  double* out, cudaStream_t st) {
+                  double* out, cudaStream_t st, const int32_t* pos = nullptr, int n_doy = 0, int d_begin = 0,
+                  int d_end = -1) {
+  if (d_end < 0) d_end = L;
+  const int nd = d_end - d_begin;
+  if (nd <= 0) return XC_OK;
   const int64_t cblocks = (C + kThreads - 1) / kThreads;
   int chunks = (int)((148 * 16 + cblocks - 1) / cblocks);
   chunks = chunks < 1 ? 1 : chunks;
-  int per = (L + chunks - 1) / chunks;
+  int per = (nd + chunks - 1) / chunks;
   if (per < 40) per = 40;  // 4 extra day lists per chunk
-  if (per > L) per = L;
-  chunks = (L + per - 1) / per;
+  if (per > nd) per = nd;
+  chunks = (nd + per - 1) / per;
   const size_t smem = (size_t)3 * (K + 1) * kThreads * 4;
   dim3 grid((unsigned)cblocks, (unsigned)chunks, 1);
-  percentile_doy_w5_kernel<K><<<grid, kThreads, smem, st>>>(x, (int32_t)T, C, ldx, L, N, spec, per, out);
+  percentile_doy_w5_kernel<K><<<grid, kThreads, smem, st>>>(x, (int32_t)T, C, ldx, L, N, spec, per, out, pos, n_doy,
+                                                            d_begin, d_end);
   return launch_status("percentile_doy_w5_kernel");
 }
 
@@ -579,6 +631,8 @@ extern "C" int32_t xc_percentile_doy_f32(const float* x, int64_t T, int64_t C, i
     XC_CHECK_CUDA(cudaStreamSynchronize(st));
   }
 
+  // interior days whose windows never leave the year: [h, L_int - h) with L_int the shortest full year
+  const int L_int = (n_doy == 366) ? 365 : n_doy;
   for (int ip = 0; ip < n_per; ++ip) {
     const double per = percentiles_host[ip];
     XC_REQUIRE(per >= 0.0 && per <= 100.0, "percentiles must be in [0, 100], got %g", per);
@@ -590,17 +644,20 @@ extern "C" int32_t xc_percentile_doy_f32(const float* x, int64_t T, int64_t C, i
       return XC_ERR_UNSUPPORTED;
     }
     double* o = out + (int64_t)ip * n_doy * C;
-    int32_t e;
-    const size_t smem_need = (size_t)(window - 1) * ((need <= 8 ? 8 : need <= 16 ? 16 : 32) + 1) * kThreads * 4;
-    if (uniform && window == 5 && need <= 16 && n_doy >= 5) {
-      e = need <= 8 ? launch_w5<8>(x, T, C, ldx, n_doy, n_years, spec, o, st)
-                    : launch_w5<16>(x, T, C, ldx, n_doy, n_years, spec, o, st);
-    } else if (uniform && window >= 3 && need <= 32 && smem_need <= 200 * 1024) {
-      e = need <= 8    ? launch_uniform<8>(x, T, C, ldx, n_doy, n_years, window, spec, o, st)
-          : need <= 16 ? launch_uniform<16>(x, T, C, ldx, n_doy, n_years, window, spec, o, st)
-                       : launch_uniform<32>(x, T, C, ldx, n_doy, n_years, window, spec, o, st);
+    const int kk = need <= 8 ? 8 : need <= 16 ? 16 : 32;
+    const size_t smem_need = (size_t)(window - 1) * (kk + 1) * kThreads * 4;
+    const bool fast_ok = window >= 3 && need <= 32 && smem_need <= 200 * 1024 && (L_int - 2 * h) >= 8;
+    int32_t e = XC_OK;
+    if (uniform && fast_ok) {
+      if (window == 5 && need <= 16)
+        e = need <= 8 ? launch_w5<8>(x, T, C, ldx, n_doy, n_years, spec, o, st)
+                      : launch_w5<16>(x, T, C, ldx, n_doy, n_years, spec, o, st);
+      else
+        e = need <= 8    ? launch_uniform<8>(x, T, C, ldx, n_doy, n_years, window, spec, o, st)
+            : need <= 16 ? launch_uniform<16>(x, T, C, ldx, n_doy, n_years, window, spec, o, st)
+                         : launch_uniform<32>(x, T, C, ldx, n_doy, n_years, window, spec, o, st);
     } else {
-      if (uniform && pos_d == nullptr) {  // uniform calendar but no fast instantiation: use the generic kernel
+      if (pos_d == nullptr) {  // uniform calendar without a fast instantiation: the table is still needed
         const int64_t nbytes = (int64_t)pos.size() * 4;
         XC_REQUIRE(workspace != nullptr && workspace_bytes >= nbytes, "workspace too small: need %lld bytes",
                    (long long)nbytes);
@@ -608,11 +665,34 @@ extern "C" int32_t xc_percentile_doy_f32(const float* x, int64_t T, int64_t C, i
         XC_CHECK_CUDA(cudaMemcpyAsync(pos_d, pos.data(), (size_t)nbytes, cudaMemcpyHostToDevice, st));
         XC_CHECK_CUDA(cudaStreamSynchronize(st));
       }
-      if (need <= 4) e = launch_generic<4>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st);
-      else if (need <= 8) e = launch_generic<8>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st);
-      else if (need <= 16) e = launch_generic<16>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st);
-      else if (need <= 32) e = launch_generic<32>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st);
-      else e = launch_generic<64>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st);
+      int g0 = 0, g1 = n_doy;  // days left to the generic kernel: [0, g0) and [g1, n_doy)
+      if (fast_ok) {
+        // interior days through the day-list kernels (table mode), edge days through the generic kernel
+        g0 = h;
+        g1 = L_int - h;
+        if (window == 5 && need <= 16)
+          e = need <= 8 ? launch_w5<8>(x, T, C, ldx, n_doy, n_years, spec, o, st, pos_d, n_doy, g0, g1)
+                        : launch_w5<16>(x, T, C, ldx, n_doy, n_years, spec, o, st, pos_d, n_doy, g0, g1);
+        else
+          e = need <= 8    ? launch_uniform<8>(x, T, C, ldx, n_doy, n_years, window, spec, o, st, pos_d, n_doy, g0, g1)
+              : need <= 16 ? launch_uniform<16>(x, T, C, ldx, n_doy, n_years, window, spec, o, st, pos_d, n_doy, g0, g1)
+                           : launch_uniform<32>(x, T, C, ldx, n_doy, n_years, window, spec, o, st, pos_d, n_doy, g0,
+                                                g1);
+        if (e) return e;
+      } else {
+        g0 = n_doy;  // everything generic: one range [0, n_doy)
+        g1 = n_doy;
+      }
+      for (int part = 0; part < 2; ++part) {
+        const int a = part == 0 ? 0 : g1, b = part == 0 ? g0 : n_doy;
+        if (a >= b) continue;
+        if (need <= 4) e = launch_generic<4>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b);
+        else if (need <= 8) e = launch_generic<8>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b);
+        else if (need <= 16) e = launch_generic<16>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b);
+        else if (need <= 32) e = launch_generic<32>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b);
+        else e = launch_generic<64>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b);
+        if (e) return e;
+      }
     }
     if (e) return e;
   }

@@ -296,3 +296,19 @@ def period_run_maxsum(x2d, poff, op_code, thr, window, resample_before_rl=True):
                                           float(thr), int(window), int(bool(resample_before_rl)), out.data_ptr(),
                                           current_stream_ptr()))
     return out
+
+
+def period_boundary_run_range(x2d, poff, range_lo, range_hi, op_code, thr, window, last=False, negate=False,
+                              cell_lo=None, cmp_f64=False):
+    """First/last run confined to [range_lo[p], range_hi[p]) of every period (run_length.py:1148-1331)."""
+    T, C = x2d.shape
+    P = len(poff) - 1
+    poff_d = dev_ints(poff, np.int32, x2d.device)
+    lo_d = dev_ints(range_lo, np.int32, x2d.device)
+    hi_d = dev_ints(range_hi, np.int32, x2d.device)
+    out = torch.empty((P, C), dtype=torch.float32, device=x2d.device)
+    check(load().xc_period_boundary_run_range_f32(x2d.data_ptr(), T, C, x2d.stride(0), poff_d.data_ptr(),
+                                                  lo_d.data_ptr(), hi_d.data_ptr(), P, op_code, float(thr),
+                                                  int(bool(cmp_f64)), int(bool(negate)), int(window), int(bool(last)),
+                                                  _ptr(cell_lo), out.data_ptr(), current_stream_ptr()))
+    return out

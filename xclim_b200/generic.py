@@ -200,3 +200,33 @@ def count_occurrences(data, threshold, freq, op, constrain=None):
     thr = threshold_in_units_of(threshold, data) if isinstance(threshold, str) else threshold
     out = threshold_count(data, op, thr, freq, constrain)
     return out.assign_attrs(units="d")
+
+
+# --------------------------------------------------------------------------------- a12 seasons / dates
+def season(data, thresh, window, op, stat, freq, mid_date=None, constrain=None):
+    """Season start / end (day of year) or length -- indices/generic.py:769-853 (+ run_length.py:891-1145)."""
+    from . import seasons
+    code = get_op(op, constrain)
+    if stat not in ("start", "end", "length"):
+        raise ValueError(f"stat must be 'start', 'end' or 'length', got {stat!r}")
+    thr = threshold_in_units_of(thresh, data) if isinstance(thresh, str) else float(thresh)
+    x2d, cell_shape, other, ta = _unwrap(data)
+    out = seasons.season(x2d, ta, freq, code, thr, window, mid_date, stat)
+    attrs = attrs_of(data)
+    if stat == "length":
+        attrs["units"] = "d"
+    else:
+        attrs.update(units="", is_dayofyear=np.int32(1), calendar=ta.calendar)
+    return _wrap_periods(data, out, cell_shape, other, ta, freq, attrs, dtype=np.float64)
+
+
+def first_day_threshold_reached(data, *, threshold, op, after_date, window=1, freq="YS", constrain=None):
+    """indices/generic.py:1555-1608: day of year of the first run of `window` steps after a date."""
+    from . import seasons
+    code = get_op(op, constrain)
+    thr = threshold_in_units_of(threshold, data) if isinstance(threshold, str) else float(threshold)
+    x2d, cell_shape, other, ta = _unwrap(data)
+    out = seasons.first_run_after_date(x2d, ta, freq, code, thr, window, after_date)
+    attrs = attrs_of(data)
+    attrs.update(units="", is_dayofyear=np.int32(1), calendar=ta.calendar)
+    return _wrap_periods(data, out, cell_shape, other, ta, freq, attrs, dtype=np.float64)

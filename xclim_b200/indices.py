@@ -400,3 +400,58 @@ BATCH_INDICATORS = [
     ("dry_spell_frequency", "pr"), ("dry_spell_total_length", "pr"), ("dry_spell_max_length", "pr"),
     ("wet_spell_frequency", "pr"), ("tx90p", "tasmax"), ("tx10p", "tasmax"), ("tn90p", "tasmin"),
 ]
+
+
+# ---- seasons and dates (indices/_threshold.py:975-1395, 1526-1700)
+def growing_season_start(tas, thresh="5.0 degC", mid_date="07-01", window=5, freq="YS", op=">="):
+    return generic.season(tas, thresh, window, op, "start", freq, mid_date=mid_date, constrain=(">", ">="))
+
+
+def growing_season_end(tas, thresh="5.0 degC", mid_date="07-01", window=5, freq="YS", op=">"):
+    return generic.season(tas, thresh, window, op, "end", freq, mid_date=mid_date, constrain=(">", ">="))
+
+
+def growing_season_length(tas, thresh="5.0 degC", window=6, mid_date="07-01", freq="YS", op=">="):
+    return generic.season(tas, thresh, window, op, "length", freq, mid_date=mid_date, constrain=(">", ">="))
+
+
+def frost_season_length(tasmin, window=5, mid_date="01-01", thresh="0.0 degC", freq="YS-JUL", op="<"):
+    return generic.season(tasmin, thresh, window, op, "length", freq, mid_date=mid_date, constrain=("<", "<="))
+
+
+def frost_free_season_start(tasmin, thresh="0.0 degC", window=5, mid_date="07-01", op=">=", freq="YS"):
+    return generic.season(tasmin, thresh, window, op, "start", freq, mid_date=mid_date, constrain=(">", ">="))
+
+
+def frost_free_season_end(tasmin, thresh="0.0 degC", window=5, mid_date="07-01", op=">=", freq="YS"):
+    return generic.season(tasmin, thresh, window, op, "end", freq, mid_date=mid_date, constrain=(">", ">="))
+
+
+def frost_free_season_length(tasmin, thresh="0.0 degC", window=5, mid_date="07-01", op=">=", freq="YS"):
+    return generic.season(tasmin, thresh, window, op, "length", freq, mid_date=mid_date, constrain=(">", ">="))
+
+
+def first_day_temperature_below(tas, thresh="0 degC", op="<", after_date="07-01", window=1, freq="YS"):
+    return generic.first_day_threshold_reached(tas, threshold=thresh, op=op, after_date=after_date, window=window,
+                                               freq=freq, constrain=("<", "<="))
+
+
+def first_day_temperature_above(tas, thresh="0 degC", op=">", after_date="01-01", window=1, freq="YS"):
+    return generic.first_day_threshold_reached(tas, threshold=thresh, op=op, after_date=after_date, window=window,
+                                               freq=freq, constrain=(">", ">="))
+
+
+def last_spring_frost(tasmin, thresh="0 degC", op="<", before_date="07-01", window=1, freq="YS"):
+    """indices/_threshold.py:1526-1582: day of year of the last frost run before a date."""
+    import numpy as np
+
+    from . import _lib, seasons
+    from .field import attrs_of
+    from .generic import _unwrap, _wrap_periods
+    code = _lib.op_code(op, ("<", "<="))
+    thr = threshold_in_units_of(thresh, tasmin)
+    x2d, cell_shape, other, ta = _unwrap(tasmin)
+    out = seasons.last_run_before_date(x2d, ta, freq, code, thr, window, before_date)
+    attrs = attrs_of(tasmin)
+    attrs.update(units="", is_dayofyear=np.int32(1), calendar=ta.calendar)
+    return _wrap_periods(tasmin, out, cell_shape, other, ta, freq, attrs, dtype=np.float64)

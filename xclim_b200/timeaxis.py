@@ -235,3 +235,18 @@ class TimeAxis:
         if base in ("Y", "Q") and anchor is not None:
             bfreq = f"{bfreq}-{anchor}"
         return self.group_ids(bfreq)
+
+    def date_index_in_periods(self, freq: str, date: str) -> np.ndarray:
+        """Absolute index of the ``MM-DD`` date inside every ``resample(time=freq)`` group, -1 where the
+        date is absent (``run_length.index_of_date`` per group, indices/run_length.py:1621-1665;
+        more than one match in a group raises like the reference, :1663-1664)."""
+        mm, dd = (int(v) for v in date.split("-"))
+        off = self.period_offsets(freq)
+        hit = np.nonzero((self.month == mm) & (self.day == dd))[0]
+        out = np.full(off.size - 1, -1, np.int32)
+        which = np.searchsorted(off, hit, side="right") - 1
+        for p, t in zip(which, hit):
+            if out[p] >= 0:
+                raise ValueError(f"More than 1 instance of date {date} found in the coordinate array.")
+            out[p] = t
+        return out
