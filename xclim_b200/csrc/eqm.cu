@@ -65,7 +65,8 @@ eqm_train_kernel(const float* __restrict__ ref, const float* __restrict__ hist, 
     for (int j = tid; j < nq; j += kSortThreads) {
       float qv = NAN;
       if (n > 0) {
-        const double q = ((double)j + 0.5) / (double)nq;
+        // nodes are cast to the data dtype before use (xsdba: equally_spaced_nodes(n).astype(ref.dtype))
+        const double q = (double)(float)(((double)j + 0.5) / (double)nq);
         const double pos = q * (double)(n - 1);
         const double lo = floor(pos);
         const int ilo = (int)lo;
@@ -109,34 +110,44 @@ eqm_adjust_kernel(const float* __restrict__ sim, int64_t T, int64_t C, int64_t l
   const int64_t t1 = min(T, t0 + rows_per_block);
   const float h_first = hq[lane], h_last = hq[(nq - 1) * kAdjThreads + lane];
   const float a_first = fa[lane], a_last = fa[(nq - 1) * kAdjThreads + lane];
-  for (int64_t t = t0; t < t1; ++t) {
-    const float x = ld_stream(sim + t * ldx + c);
-    float f;
-    if (bad || x != x) {
-      f = NAN;
-    } else if (x <= h_first) {
-      f = a_first;
-    } else if (x >= h_last) {
-      f = a_last;
-    } else {
-      // idx = #{hq < x} (searchsorted side="left"), clipped to [1, nq-1]
-      int lo = 0, hi = nq;  // invariant: hq[lo-1] < x <= hq[hi]
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (hq[mid * kAdjThreads + lane] < x) lo = mid + 1; else hi = mid;
-      }
-      int idx = max(1, min(lo, nq - 1));
-      const float x0 = hq[(idx - 1) * kAdjThreads + lane], x1 = hq[idx * kAdjThreads + lane];
-      const float y0 = fa[(idx - 1) * kAdjThreads + lane], y1 = fa[idx * kAdjThreads + lane];
-      if (INTERP == 1) {
-        const float slope = __fdiv_rn(__fsub_rn(y1, y0), __fsub_rn(x1, x0));
-        f = __fadd_rn(__fmul_rn(slope, __fsub_rn(x, x0)), y0);
-      } else {
-        // nearest: boundaries at the mid-points, ties go to the lower node
-        const float mid = __fmul_rn(__fadd_rn(x0, x1), 0.5f);
-        f = (x <= mid) ? y0 : y1;
-      }
+  int top_step = 1;  // largest power of two < nq
+  while (top_step * 2 < nq) top_step *= 2;
+  auto factor = [&](float x) -> float {
+    if (bad || x != x) return NAN;
+    if (x <= h_first) return a_first;
+    if (x >= h_last) return a_last;
+    // idx = #{hq < x} (searchsorted side="left") by a fixed-depth, branch-free bisection
+    int idx = 0;
+    for (int step = top_step; step >= 1; step >>= 1) {
+      const int probe = idx + step;
+      const float hv = hq[min(probe, nq) * kAdjThreads - kAdjThreads + lane];  // hq[probe - 1]
+      idx = (probe <= nq && hv < x) ? probe : idx;
     }
+    idx = max(1, min(idx, nq - 1));
+    const float x0 = hq[(idx - 1) * kAdjThreads + lane], x1 = hq[idx * kAdjThreads + lane];
+    const float y0 = fa[(idx - 1) * kAdjThreads + lane], y1 = fa[idx * kAdjThreads + lane];
+    if (INTERP == 1) {
+      const float slope = __fdiv_rn(__fsub_rn(y1, y0), __fsub_rn(x1, x0));
+      return __fadd_rn(__fmul_rn(slope, __fsub_rn(x, x0)), y0);
+    }
+    // nearest: boundaries at the mid-points, ties go to the lower node
+    const float mid = __fmul_rn(__fadd_rn(x0, x1), 0.5f);
+    return (x <= mid) ? y0 : y1;
+  };
+  constexpr int U = 4;  // rows in flight per lane
+  int64_t t = t0;
+  for (; t + U <= t1; t += U) {
+    float xv[U], fv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) xv[u] = ld_stream(sim + (t + u) * ldx + c);
+#pragma unroll
+    for (int u = 0; u < U; ++u) fv[u] = factor(xv[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) scen[(t + u) * C + c] = (KIND == 0) ? __fadd_rn(xv[u], fv[u]) : __fmul_rn(xv[u], fv[u]);
+  }
+  for (; t < t1; ++t) {
+    const float x = ld_stream(sim + t * ldx + c);
+    const float f = factor(x);
     scen[t * C + c] = (KIND == 0) ? __fadd_rn(x, f) : __fmul_rn(x, f);
   }
 }

@@ -665,33 +665,40 @@ extern "C" int32_t xc_percentile_doy_f32(const float* x, int64_t T, int64_t C, i
         XC_CHECK_CUDA(cudaMemcpyAsync(pos_d, pos.data(), (size_t)nbytes, cudaMemcpyHostToDevice, st));
         XC_CHECK_CUDA(cudaStreamSynchronize(st));
       }
-      int g0 = 0, g1 = n_doy;  // days left to the generic kernel: [0, g0) and [g1, n_doy)
+      // Days whose samples decompose into per-day lists: the window must stay inside the year
+      // ([h, L_int - h)) and no window centre may fall outside the series (the h days before the first
+      // step's day-of-year and after the last step's: their neighbours exist but their centres do not).
+      std::vector<char> fast_day((size_t)n_doy, 0);
       if (fast_ok) {
-        // interior days through the day-list kernels (table mode), edge days through the generic kernel
-        g0 = h;
-        g1 = L_int - h;
-        if (window == 5 && need <= 16)
-          e = need <= 8 ? launch_w5<8>(x, T, C, ldx, n_doy, n_years, spec, o, st, pos_d, n_doy, g0, g1)
-                        : launch_w5<16>(x, T, C, ldx, n_doy, n_years, spec, o, st, pos_d, n_doy, g0, g1);
-        else
-          e = need <= 8    ? launch_uniform<8>(x, T, C, ldx, n_doy, n_years, window, spec, o, st, pos_d, n_doy, g0, g1)
-              : need <= 16 ? launch_uniform<16>(x, T, C, ldx, n_doy, n_years, window, spec, o, st, pos_d, n_doy, g0, g1)
-                           : launch_uniform<32>(x, T, C, ldx, n_doy, n_years, window, spec, o, st, pos_d, n_doy, g0,
-                                                g1);
-        if (e) return e;
-      } else {
-        g0 = n_doy;  // everything generic: one range [0, n_doy)
-        g1 = n_doy;
+        for (int d = h; d < L_int - h; ++d) fast_day[d] = 1;
+        const int s0 = doy_index_host[0] - 1, e1 = doy_index_host[T - 1] - 1;
+        for (int d = s0 - h; d < s0; ++d)
+          if (d >= 0) fast_day[d] = 0;
+        for (int d = e1 + 1; d <= e1 + h; ++d)
+          if (d < n_doy) fast_day[d] = 0;
       }
-      for (int part = 0; part < 2; ++part) {
-        const int a = part == 0 ? 0 : g1, b = part == 0 ? g0 : n_doy;
-        if (a >= b) continue;
-        if (need <= 4) e = launch_generic<4>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b);
-        else if (need <= 8) e = launch_generic<8>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b);
-        else if (need <= 16) e = launch_generic<16>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b);
-        else if (need <= 32) e = launch_generic<32>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b);
-        else e = launch_generic<64>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b);
+      for (int a = 0; a < n_doy;) {
+        int b = a;
+        const bool fast = fast_day[a] != 0;
+        while (b < n_doy && (fast_day[b] != 0) == fast) ++b;
+        if (fast && (b - a) >= 8) {
+          if (window == 5 && need <= 16)
+            e = need <= 8 ? launch_w5<8>(x, T, C, ldx, n_doy, n_years, spec, o, st, pos_d, n_doy, a, b)
+                          : launch_w5<16>(x, T, C, ldx, n_doy, n_years, spec, o, st, pos_d, n_doy, a, b);
+          else
+            e = need <= 8    ? launch_uniform<8>(x, T, C, ldx, n_doy, n_years, window, spec, o, st, pos_d, n_doy, a, b)
+                : need <= 16 ? launch_uniform<16>(x, T, C, ldx, n_doy, n_years, window, spec, o, st, pos_d, n_doy, a, b)
+                             : launch_uniform<32>(x, T, C, ldx, n_doy, n_years, window, spec, o, st, pos_d, n_doy, a,
+                                                  b);
+        } else {
+          if (need <= 4) e = launch_generic<4>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b);
+          else if (need <= 8) e = launch_generic<8>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b);
+          else if (need <= 16) e = launch_generic<16>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b);
+          else if (need <= 32) e = launch_generic<32>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b);
+          else e = launch_generic<64>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b);
+        }
         if (e) return e;
+        a = b;
       }
     }
     if (e) return e;

@@ -155,22 +155,67 @@ rolling_period_reduce_kernel(const float* __restrict__ x, int64_t T, int64_t C, 
 // mask[t] = any length-w block [i, i+w-1] containing t, fully inside the series, whose window
 // statistic satisfies (stat op thr)   (indices/generic.py:519-535); then run-length statistics of
 // the mask per period (window == 1 on the mask, generic.py:562-570).
-struct SpellState {
+//
+// The block statistics are produced in time order by BlockStream: for sum / mean windows a sliding
+// float64 sum (+ NaN counter) advanced with kChunk (incoming, outgoing) loads issued together; for
+// min / max windows the w values are re-read (L1 hits).
+struct BlockStream {
   const float* col;
   int64_t ldx;
   int T, w, wstat, op;
   float thr;
-  int last_true;  // most recent block start i whose block qualifies
-  int next_i;     // next block start to evaluate
-  __device__ __forceinline__ bool mask_at(int t) {
-    // evaluate blocks up to start index t (blocks starting after t cannot contain t)
-    const int imax = min(t, T - w);
-    while (next_i <= imax) {
-      const float r = window_stat(col, ldx, next_i, w, wstat);
-      if (cmp_rt(op, r, thr)) last_true = next_i;
-      ++next_i;
+  int i;          // start of the next block to evaluate
+  SlideSum win;   // window [i, i+w-1] when sliding
+  bool primed;
+  // prefetched (incoming, outgoing) values for the next slides
+  float vin[kChunk], vout[kChunk];
+  int have, used;
+
+  __device__ __forceinline__ void init(int start) {
+    i = start;
+    primed = false;
+    have = used = 0;
+    win.s = 0.0;
+    win.nan = 0;
+  }
+  __device__ __forceinline__ bool sliding() const { return wstat == XC_STAT_SUM || wstat == XC_STAT_MEAN; }
+  // qualifies(block starting at i) ; advances to i + 1.  Caller guarantees i + w <= T.
+  __device__ __forceinline__ bool next() {
+    float r;
+    if (sliding()) {
+      if (!primed) {
+        for (int k = 0; k < w; ++k) win.add(__ldg(col + (int64_t)(i + k) * ldx));
+        primed = true;
+      }
+      r = win.nan ? NAN : (float)(wstat == XC_STAT_MEAN ? win.s / (double)w : win.s);
+      // slide to i + 1 (if that block exists)
+      if (i + 1 + w <= T) {
+        if (used == have) {
+          have = min(kChunk, T - (i + w));
+          used = 0;
+#pragma unroll
+          for (int k = 0; k < kChunk; ++k) {
+            if (k < have) {
+              vin[k] = ld_stream(col + (int64_t)(i + w + k) * ldx);
+              vout[k] = __ldg(col + (int64_t)(i + k) * ldx);
+            }
+          }
+        }
+        float a = vin[0], b = vout[0];
+#pragma unroll
+        for (int k = 1; k < kChunk; ++k) {
+          a = (used == k) ? vin[k] : a;
+          b = (used == k) ? vout[k] : b;
+        }
+        win.add(a);
+        win.drop(b);
+        ++used;
+      }
+    } else {
+      r = window_stat(col, ldx, i, w, wstat);
     }
-    return last_true >= t - w + 1 && last_true <= t && last_true >= 0;
+    ++i;
+    return cmp_rt(op, r, thr);
   }
 };
 
@@ -182,9 +227,22 @@ spell_runstat_kernel(const float* __restrict__ x, int64_t T, int64_t C, int64_t 
   if (c >= C) return;
   const int p = blockIdx.y;
   const int t0 = poff[p], t1 = poff[p + 1];
-  SpellState st{x + c, ldx, (int)T, w, wstat, op, thr, -1, max(0, t0 - 2 * w)};
+  BlockStream bs;
+  bs.col = x + c; bs.ldx = ldx; bs.T = (int)T; bs.w = w; bs.wstat = wstat; bs.op = op; bs.thr = thr;
+  // the mask at t needs the blocks starting in [t - w + 1, t]; with `after` the mask at t0 - 1 too
+  const int first_t = after ? max(0, t0 - 1) : t0;
+  bs.init(max(0, first_t - w + 1));
+  int last_true = -1;
+  auto mask_at = [&](int t) -> bool {
+    const int imax = min(t, (int)T - w);
+    while (bs.i <= imax) {
+      const int ii = bs.i;
+      if (bs.next()) last_true = ii;
+    }
+    return last_true >= 0 && last_true >= t - w + 1;
+  };
   bool skip = false;
-  if (after && t0 > 0) skip = st.mask_at(t0 - 1);  // a run already open belongs to an earlier period
+  if (after && t0 > 0) skip = mask_at(t0 - 1);  // a run already open belongs to an earlier period
   int cur = 0, mx = 0, mn = 0x7fffffff, sum = 0, cnt = 0;
   unsigned long long sq = 0ull;
   auto close_run = [&](int L) {
@@ -197,7 +255,7 @@ spell_runstat_kernel(const float* __restrict__ x, int64_t T, int64_t C, int64_t 
     }
   };
   for (int t = t0; t < t1; ++t) {
-    bool m = st.mask_at(t);
+    bool m = mask_at(t);
     if (after) {
       skip = skip && m;
       m = m && !skip;
@@ -212,7 +270,7 @@ spell_runstat_kernel(const float* __restrict__ x, int64_t T, int64_t C, int64_t 
   if (after) {
     int t = t1;
     while (cur > 0 && t < (int)T) {
-      if (st.mask_at(t)) {
+      if (mask_at(t)) {
         ++cur;
       } else {
         close_run(cur);
