@@ -72,6 +72,7 @@ bootstrap_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int64_t ba
   const int d0 = blockIdx.y * doys_per_chunk;
   const int d1 = min(L, d0 + doys_per_chunk);
   if (d0 >= d1) return;
+  const unsigned wmask = __activemask();  // lanes of this warp that own a cell
   const bool top = spec.top != 0;
   const float sgn = top ? 1.f : -1.f;
   const float* xb = x + base_start * ldx + c;
@@ -137,10 +138,71 @@ bootstrap_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int64_t ba
       bitonic_finish_desc<KA>(tl);
       nbase += scnt[s * kThreads + lane];
     }
-    // ---- every in-base year y: remove its window values, then try every other year s
+    // ---- every in-base year y: first a cheap, conservative test on ranks.  With M = S - R_y + I_s,
+    // ge(M) = #{m >= x} lies in [geA, geA + W] (geA from S - R_y alone) and the two order statistics the
+    // quantile interpolates sit at list indexes k1 and k1 + 1:  ge(M) <= k1 for every s  =>  x beats the
+    // threshold for every s (count N-1);  gt(M) >= k1 + 2 for every s  =>  never.  Only the years whose
+    // value lies within ~W ranks of the threshold ("in band", ~10 %) go through the exact per-(y, s)
+    // evaluation, and each lane walks ITS OWN list of such years, so a warp iterates max-over-lanes
+    // list length (~5) instead of N times.
     const int raw_mid = (raw_first + H) % W;
+    unsigned band = 0u;
 #pragma unroll 1
     for (int y = 0; y < N; ++y) {
+      const float xq = raw[((size_t)raw_mid * N + y) * kThreads + lane];
+      if (!(xq == xq)) continue;  // NaN never satisfies the comparison
+      const float xs = sgn * xq;
+      int geT = 0, gtT = 0;
+#pragma unroll
+      for (int k = 0; k < KA; ++k) {
+        geT += (tl[k] >= xs) ? 1 : 0;
+        gtT += (tl[k] > xs) ? 1 : 0;
+      }
+      int geR = 0, gtR = 0, nr = 0;
+#pragma unroll 1
+      for (int k = 0; k < W; ++k) {
+        const int e = d - H + k;
+        const bool valid = (e < 0) ? (y + 1 < N) : ((e >= L) ? (y >= 1) : true);
+        if (!valid) continue;
+        const float r = raw[((size_t)((raw_first + k) % W) * N + y) * kThreads + lane];
+        if (r == r) {
+          ++nr;
+          geR += (sgn * r >= xs) ? 1 : 0;
+          gtR += (sgn * r > xs) ? 1 : 0;
+        }
+      }
+      // values below the kept list: geT saturates at KA, which is far beyond any k1 + 2 (KA >= KB + W)
+      const int geA = geT - geR, gtA = (gtT == KA) ? KA : gtT - gtR;
+      const int na = nbase - nr;
+      const QuantIdx q0 = quant_index(na, spec), q1 = quant_index(na + W, spec);
+      const bool ok0 = (na >= 2) && (q0.vi < (double)na - 1.0) && (q0.vi >= 0.0);
+      const bool ok1 = (q1.vi < (double)(na + W) - 1.0) && (q1.vi >= 0.0);
+      const int k1min = top ? (na - 2 - q0.ilo) : q0.ilo;
+      const int k1max = top ? (na + W - 2 - q1.ilo) : q1.ilo;
+      bool decided = false;
+      if (ok0 && ok1 && N <= 32) {
+        if (gtA >= k1max + 2) {
+          decided = true;                       // never beats the threshold
+        } else if (geT < KA && geA + W <= k1min) {
+          decided = true;                       // beats it for every other year s
+          atomicAdd(counts + (int64_t)step_period[y * L + d] * C + c, N - 1);
+        }
+      }
+      if (!decided) band |= (N <= 32) ? (1u << y) : 0u;
+    }
+    // exact evaluation of the in-band years (all years when N > 32)
+    int y_all = 0;
+    while (true) {
+      int y = -1;
+      if (N <= 32) {
+        if (band) { y = __ffs(band) - 1; band &= band - 1u; }
+      } else if (y_all < N) {
+        y = y_all++;
+        const float xq0 = raw[((size_t)raw_mid * N + y) * kThreads + lane];
+        if (!(xq0 == xq0)) y = -2;  // skip, but keep looping
+      }
+      if (!__any_sync(wmask, y != -1)) break;
+      if (y < 0) continue;
       float a[KA];
 #pragma unroll
       for (int k = 0; k < KA; ++k) a[k] = tl[k];

@@ -157,8 +157,8 @@ rolling_period_reduce_kernel(const float* __restrict__ x, int64_t T, int64_t C, 
 // the mask per period (window == 1 on the mask, generic.py:562-570).
 //
 // The block statistics are produced in time order by BlockStream: for sum / mean windows a sliding
-// float64 sum (+ NaN counter) advanced with kChunk (incoming, outgoing) loads issued together; for
-// min / max windows the w values are re-read (L1 hits).
+// float64 sum (+ NaN counter), two loads per step; for min / max windows the w values are re-read
+// (L1 hits).
 struct BlockStream {
   const float* col;
   int64_t ldx;
@@ -167,14 +167,10 @@ struct BlockStream {
   int i;          // start of the next block to evaluate
   SlideSum win;   // window [i, i+w-1] when sliding
   bool primed;
-  // prefetched (incoming, outgoing) values for the next slides
-  float vin[kChunk], vout[kChunk];
-  int have, used;
 
   __device__ __forceinline__ void init(int start) {
     i = start;
     primed = false;
-    have = used = 0;
     win.s = 0.0;
     win.nan = 0;
   }
@@ -188,28 +184,9 @@ struct BlockStream {
         primed = true;
       }
       r = win.nan ? NAN : (float)(wstat == XC_STAT_MEAN ? win.s / (double)w : win.s);
-      // slide to i + 1 (if that block exists)
-      if (i + 1 + w <= T) {
-        if (used == have) {
-          have = min(kChunk, T - (i + w));
-          used = 0;
-#pragma unroll
-          for (int k = 0; k < kChunk; ++k) {
-            if (k < have) {
-              vin[k] = ld_stream(col + (int64_t)(i + w + k) * ldx);
-              vout[k] = __ldg(col + (int64_t)(i + k) * ldx);
-            }
-          }
-        }
-        float a = vin[0], b = vout[0];
-#pragma unroll
-        for (int k = 1; k < kChunk; ++k) {
-          a = (used == k) ? vin[k] : a;
-          b = (used == k) ? vout[k] : b;
-        }
-        win.add(a);
-        win.drop(b);
-        ++used;
+      if (i + 1 + w <= T) {  // slide to i + 1: one new row, one row re-read from L1/L2
+        win.add(__ldg(col + (int64_t)(i + w) * ldx));
+        win.drop(__ldg(col + (int64_t)i * ldx));
       }
     } else {
       r = window_stat(col, ldx, i, w, wstat);
