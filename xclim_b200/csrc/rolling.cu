@@ -174,7 +174,8 @@ struct BlockStream {
     win.s = 0.0;
     win.nan = 0;
   }
-  __device__ __forceinline__ bool sliding() const { return wstat == XC_STAT_SUM || wstat == XC_STAT_MEAN; }
+  // short windows are cheaper to re-read (L1 hits) than to slide with float64 adds
+  __device__ __forceinline__ bool sliding() const { return (wstat == XC_STAT_SUM || wstat == XC_STAT_MEAN) && w > 6; }
   // qualifies(block starting at i) ; advances to i + 1.  Caller guarantees i + w <= T.
   __device__ __forceinline__ bool next() {
     float r;
