@@ -65,11 +65,12 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("XCLIM_B200_LIB") or LIB_PATH   # XCLIM_B200_LIB: experiment builds only
+    if not os.path.exists(path):
         raise XclimB200Error(
-            f"{LIB_PATH} is missing: build it with `python -m xclim_b200._build` "
+            f"{path} is missing: build it with `python -m xclim_b200._build` "
             "(the xclim_b200 hot path has no CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res

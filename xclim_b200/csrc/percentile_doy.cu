@@ -95,12 +95,12 @@ percentile_doy_generic_kernel(const float* __restrict__ x, int64_t T, int64_t C,
 // two ends of the SERIES).
 // Table mode (pos != nullptr; calendars whose years differ in length): the row of (year y, day e) is
 // pos[y * n_doy + e] (-1 when that day does not exist); only days e in [0, n_doy) are requested.
-template <int K>
+template <int K, bool TABLE = false>
 __device__ __forceinline__ void load_day_list(const float* __restrict__ x, int64_t c, int64_t ldx, int T, int L,
                                               int N, int e, bool top, float (&lst)[K], int& n,
                                               const int32_t* __restrict__ pos = nullptr, int n_doy = 0) {
   n = 0;
-  if (pos != nullptr) {
+  if constexpr (TABLE) {
     bool first_t = true;
     for (int y0 = 0; y0 < N; y0 += K) {
       float v[K];
@@ -144,10 +144,22 @@ __device__ __forceinline__ void load_day_list(const float* __restrict__ x, int64
     const uint32_t ys32 = (uint32_t)ystride;
     const bool narrow = (ystride >> 32) == 0;
     int nv;
+#ifndef XC_PCTL_VARIANT
+#define XC_PCTL_VARIANT 0
+#endif
     if (y0 >= ylo && y0 + K <= yhi && narrow) {  // whole chunk in range (the common case)
+#if XC_PCTL_VARIANT == 1
 #pragma unroll
       for (int k = 0; k < K; ++k)
         v[k] = ld_stream(reinterpret_cast<const float*>(p0 + (uint64_t)((uint32_t)k) * (uint64_t)ys32));
+#else
+      const char* pp = p0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        v[k] = ld_stream(reinterpret_cast<const float*>(pp));
+        pp += ystride;
+      }
+#endif
       nv = K;
     } else {
       nv = 0;
@@ -167,10 +179,17 @@ __device__ __forceinline__ void load_day_list(const float* __restrict__ x, int64
     }
     // NaN handling off the fast path: a chain of FMAs (FMA pipe) makes `probe` NaN iff some value is
     // NaN or infinite; only then does the lane look at each value (NaN -> -inf, never selected)
+#if XC_PCTL_VARIANT == 1
     float probe = 0.f;
 #pragma unroll
     for (int k = 0; k < K; ++k) probe = __fmaf_rn(v[k], 0.f, probe);
-    if (probe != probe) {
+    const bool suspicious = (probe != probe);
+#else
+    bool suspicious = false;
+#pragma unroll
+    for (int k = 0; k < K; ++k) suspicious = suspicious || (v[k] != v[k]);
+#endif
+    if (suspicious) {
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const bool bad = (v[k] != v[k]);
@@ -195,7 +214,7 @@ __device__ __forceinline__ void load_day_list(const float* __restrict__ x, int64
 // ever touches its own column).  Keeping the ring out of the register file lets ~24 warps per SM
 // stay resident (the kernel is latency-bound otherwise) and keeps the code small enough for the
 // instruction cache (one copy of the sorting network and of the merge, no unrolling over W).
-template <int K>
+template <int K, bool TABLE>
 __global__ void __launch_bounds__(kThreads)
 percentile_doy_uniform_kernel(const float* __restrict__ x, int32_t T, int64_t C, int64_t ldx, int32_t L,
                               int32_t N, int32_t W, QuantSpec spec, int32_t doys_per_chunk,
@@ -218,14 +237,14 @@ percentile_doy_uniform_kernel(const float* __restrict__ x, int32_t T, int64_t C,
   int nnew;
   // prologue: day lists e = d0-H .. d0+H-1 -> ring slots 0..R-1 (slot = (e - (d0-H)) mod R)
   for (int s = 0; s < R; ++s) {
-    load_day_list<K>(x, c, ldx, T, L, N, d0 - H + s, top, ynew, nnew, pos, n_doy);
+    load_day_list<K, TABLE>(x, c, ldx, T, L, N, d0 - H + s, top, ynew, nnew, pos, n_doy);
 #pragma unroll
     for (int k = 0; k < K; ++k) ring[((size_t)s * K + k) * kThreads + lane] = ynew[k];
     rcnt[s * kThreads + lane] = nnew;
   }
   int oldest = 0;  // slot holding day list e = d-H
   for (int d = d0; d < d1; ++d) {
-    load_day_list<K>(x, c, ldx, T, L, N, d + H, top, ynew, nnew, pos, n_doy);
+    load_day_list<K, TABLE>(x, c, ldx, T, L, N, d + H, top, ynew, nnew, pos, n_doy);
     float acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = ynew[k];
@@ -254,8 +273,11 @@ percentile_doy_uniform_kernel(const float* __restrict__ x, int32_t T, int64_t C,
 // (warp-uniform test) the final merge only extracts the two order statistics the quantile needs
 // (the two smallest of the top-K) instead of sorting: 16 min/max instead of 80 + two select chains.
 // Ring in shared memory: 3 pair lists per lane, [slot][k][lane].
-template <int K>
-__global__ void __launch_bounds__(kThreads)
+#ifndef XC_PCTL_MINBLOCKS
+#define XC_PCTL_MINBLOCKS 8
+#endif
+template <int K, bool TABLE>
+__global__ void __launch_bounds__(kThreads, XC_PCTL_MINBLOCKS)
 percentile_doy_w5_kernel(const float* __restrict__ x, int32_t T, int64_t C, int64_t ldx, int32_t L, int32_t N,
                          QuantSpec spec, int32_t doys_per_chunk, double* __restrict__ out,
                          const int32_t* __restrict__ pos, int32_t n_doy, int32_t d_begin, int32_t d_end) {
@@ -280,9 +302,9 @@ percentile_doy_w5_kernel(const float* __restrict__ x, int32_t T, int64_t C, int6
   float yprev[K], ynew[K];
   int nprev, nnew;
   // prologue: A(d0-1) -> slot 0, A(d0) -> slot 1, A(d0+1) -> slot 2 ; yprev = Y(d0+1)
-  load_day_list<K>(x, c, ldx, T, L, N, d0 - 2, top, yprev, nprev, pos, n_doy);
+  load_day_list<K, TABLE>(x, c, ldx, T, L, N, d0 - 2, top, yprev, nprev, pos, n_doy);
   for (int j = 0; j < 3; ++j) {
-    load_day_list<K>(x, c, ldx, T, L, N, d0 - 1 + j, top, ynew, nnew, pos, n_doy);
+    load_day_list<K, TABLE>(x, c, ldx, T, L, N, d0 - 1 + j, top, ynew, nnew, pos, n_doy);
     merge_top_desc<K>(yprev, ynew);  // yprev <- A(d0-1+j)
     store_pair(j, yprev, nprev + nnew);
 #pragma unroll
@@ -291,7 +313,7 @@ percentile_doy_w5_kernel(const float* __restrict__ x, int32_t T, int64_t C, int6
   }
   int s_lo = 0;  // slot of A(d-1); A(d+1) lives in slot (s_lo + 2) % 3
   for (int d = d0; d < d1; ++d) {
-    load_day_list<K>(x, c, ldx, T, L, N, d + 2, top, ynew, nnew, pos, n_doy);
+    load_day_list<K, TABLE>(x, c, ldx, T, L, N, d + 2, top, ynew, nnew, pos, n_doy);
     const int s_hi = (s_lo + 2 >= 3) ? s_lo - 1 : s_lo + 2;
     float t[K];
     {
@@ -554,13 +576,19 @@ int32_t launch_uniform(const float* x, int64_t T, int64_t C, int64_t ldx, int32_
   chunks = (nd + per - 1) / per;
   const size_t smem = (size_t)(W - 1) * (K + 1) * kThreads * 4;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(percentile_doy_uniform_kernel<K>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = pos ? cudaFuncSetAttribute(percentile_doy_uniform_kernel<K, true>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : cudaFuncSetAttribute(percentile_doy_uniform_kernel<K, false>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(percentile_doy_uniform_kernel)");
   }
   dim3 grid((unsigned)cblocks, (unsigned)chunks, 1);
-  percentile_doy_uniform_kernel<K><<<grid, kThreads, smem, st>>>(x, (int32_t)T, C, ldx, L, N, W, spec, per, out, pos,
-                                                                 n_doy, d_begin, d_end);
+  if (pos)
+    percentile_doy_uniform_kernel<K, true><<<grid, kThreads, smem, st>>>(x, (int32_t)T, C, ldx, L, N, W, spec, per,
+                                                                         out, pos, n_doy, d_begin, d_end);
+  else
+    percentile_doy_uniform_kernel<K, false><<<grid, kThreads, smem, st>>>(x, (int32_t)T, C, ldx, L, N, W, spec, per,
+                                                                          out, pos, n_doy, d_begin, d_end);
   return launch_status("percentile_doy_uniform_kernel");
 }
 
@@ -580,8 +608,12 @@ int32_t launch_w5(const float* x, int64_t T, int64_t C, int64_t ldx, int32_t L, 
   chunks = (nd + per - 1) / per;
   const size_t smem = (size_t)3 * (K + 1) * kThreads * 4;
   dim3 grid((unsigned)cblocks, (unsigned)chunks, 1);
-  percentile_doy_w5_kernel<K><<<grid, kThreads, smem, st>>>(x, (int32_t)T, C, ldx, L, N, spec, per, out, pos, n_doy,
-                                                            d_begin, d_end);
+  if (pos)
+    percentile_doy_w5_kernel<K, true><<<grid, kThreads, smem, st>>>(x, (int32_t)T, C, ldx, L, N, spec, per, out, pos,
+                                                                    n_doy, d_begin, d_end);
+  else
+    percentile_doy_w5_kernel<K, false><<<grid, kThreads, smem, st>>>(x, (int32_t)T, C, ldx, L, N, spec, per, out, pos,
+                                                                     n_doy, d_begin, d_end);
   return launch_status("percentile_doy_w5_kernel");
 }
 
