@@ -123,3 +123,25 @@ def test_eqm_train_adjust(cuda, kind, interp):
         back = eqm.adjust(f(hist), interp="linear").values[:, 1, 1]
         q = np.nanquantile(back, [0.25, 0.5, 0.75])
         np.testing.assert_allclose(q, np.nanquantile(ref[:, 1, 1], [0.25, 0.5, 0.75]), atol=0.15)
+
+
+def test_eqm_train_heavy_ties_and_degenerate(cuda):
+    """Multi-select edge cases: a heavy bin of exact ties (dry days), heavy bins that are NOT constant
+    (forces the sort fallback), constant series, tiny series, all-NaN."""
+    import torch
+    from xclim_b200 import device
+    rng = np.random.default_rng(44)
+    T, C = 3000, 8
+    ref = rng.gamma(0.5, 5.0, size=(T, C)).astype(np.float32)
+    hist = rng.gamma(0.6, 4.0, size=(T, C)).astype(np.float32)
+    ref[rng.random(ref.shape) < 0.5] = 0.0          # half the days are exactly 0
+    hist[rng.random(hist.shape) < 0.6] = 0.0
+    ref[:, 1] = 3.25                                # constant series
+    hist[:, 2] = np.where(rng.random(T) < 0.5, 1.0, 1.0 + 1e-6).astype(np.float32)   # two values in one bin
+    hist[:2, 2] = [0.0, 1000.0]                     # ... inside a wide range -> heavy, non-constant bin
+    ref[:, 3] = np.nan                              # all NaN
+    hist[5:, 4] = np.nan                            # only five valid values
+    af, hq = device.eqm_train(torch.from_numpy(ref).cuda(), torch.from_numpy(hist).cuda(), 20, 0)
+    af_o, hq_o = O.eqm_train(ref, hist, 20, "+")
+    np.testing.assert_allclose(hq.cpu().numpy(), hq_o, rtol=1e-5, atol=1e-7, equal_nan=True)
+    np.testing.assert_allclose(af.cpu().numpy(), af_o, rtol=1e-4, atol=1e-6, equal_nan=True)

@@ -274,7 +274,7 @@ percentile_doy_uniform_kernel(const float* __restrict__ x, int32_t T, int64_t C,
 // (the two smallest of the top-K) instead of sorting: 16 min/max instead of 80 + two select chains.
 // Ring in shared memory: 3 pair lists per lane, [slot][k][lane].
 #ifndef XC_PCTL_MINBLOCKS
-#define XC_PCTL_MINBLOCKS 8
+#define XC_PCTL_MINBLOCKS 7
 #endif
 template <int K, bool TABLE>
 __global__ void __launch_bounds__(kThreads, XC_PCTL_MINBLOCKS)
