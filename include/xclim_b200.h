@@ -46,6 +46,10 @@ extern "C" {
 #define XC_OP_LE 3
 #define XC_OP_EQ 4
 #define XC_OP_NE 5
+/* NaN tests (threshold ignored), accepted by xc_period_count_f32 / xc_period_runstat_f32 only:
+ * the `~valid` / `valid` masks of core/missing.py:253-298, 434-450 (MissingWMO's longest NaN run) */
+#define XC_OP_ISNAN 6
+#define XC_OP_NOTNAN 7
 
 /* run-length reducers over the run lengths >= window attributed to a period:
  * indices/run_length.py:275-335 (`rle_statistics`, `get_rl_stat`), 381-488
@@ -106,6 +110,19 @@ int32_t xc_period_runstat_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
                               int32_t op, double thr, int32_t cmp_f64,
                               int32_t reducer, int32_t window, int32_t resample_before_rl,
                               float* out, int32_t* valid_count, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a6 (bivariate)  run statistics / counts of a condition on two variables:
+ *   cond = (x1 op1 thr1) AND|OR (x2 op2 thr2)  -> reducer over run lengths >= window per period.
+ *   replaces heat_wave_frequency / _max_length / _total_length (indices/_multivariate.py:646-880),
+ *   tx_tn_days_above (:1653-1716; reducer SUM, window 1 == count) and
+ *   generic.bivariate_count_occurrences (indices/generic.py:1002-1073; var_any != 0 for "any").
+ * ------------------------------------------------------------------------------------------- */
+int32_t xc_period_runstat2_f32(const float* x1, const float* x2, int64_t T, int64_t C, int64_t ldx,
+                               const int32_t* period_offsets, int32_t P,
+                               int32_t op1, double thr1, int32_t op2, double thr2, int32_t var_any,
+                               int32_t reducer, int32_t window, int32_t resample_before_rl,
+                               float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a11  windowed_max_run_sum of the excess over a threshold -- indices/run_length.py:491-540 on

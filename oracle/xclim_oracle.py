@@ -772,3 +772,37 @@ def season(cond, window, mids, poff, stat, doy=None, has_date=True):
             t = np.where(np.isnan(v), 0, v).astype(int) + s
             outs.append(np.where(np.isnan(v), np.nan, np.asarray(doy)[t]))
     return np.stack(outs, axis=0)
+
+
+# --------------------------------------------------------------------------------------------------
+# missing-value masks beyond "any" (core/missing.py:338-522)
+# --------------------------------------------------------------------------------------------------
+def missing_pct(x, poff, tolerance):
+    """core/missing.py:476-482."""
+    valid = ~np.isnan(x)
+    out = []
+    for s, e in _groups(poff):
+        out.append(((e - s) - valid[s:e].sum(axis=0)) / (e - s) >= tolerance)
+    return np.stack(out)
+
+
+def at_least_n_valid(x, poff, n):
+    """core/missing.py:517-522."""
+    valid = ~np.isnan(x)
+    return np.stack([valid[s:e].sum(axis=0) < n for s, e in _groups(poff)])
+
+
+def missing_wmo(x, poff_month, parent, n_parent, nm=11, nc=5):
+    """core/missing.py:434-450 at the monthly step, then MissingAny over the months of every coarser
+    period (:384-391).  ``parent[m]`` = index of the coarser period holding month m."""
+    valid = ~np.isnan(x)
+    miss_m = []
+    for s, e in _groups(poff_month):
+        missing_days = (e - s) - valid[s:e].sum(axis=0)
+        longest = rle_statistics(~valid[s:e], "max", 1)
+        miss_m.append((missing_days >= nm) | (longest >= nc))
+    miss_m = np.stack(miss_m)
+    out = np.zeros((n_parent,) + x.shape[1:], bool)
+    for m, p in enumerate(parent):
+        out[p] |= miss_m[m]
+    return out

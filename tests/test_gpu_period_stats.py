@@ -209,3 +209,33 @@ def test_hot_spell_max_magnitude(cuda, window, before):
     np.testing.assert_allclose(got, exp, rtol=1e-5)
     np.testing.assert_array_equal(generic.count_occurrences(da, 298.15, "YS", ">").values,
                                   O.threshold_count(x, ">", 298.15, da.time.period_offsets("YS")))
+
+
+@pytest.mark.parametrize("before", [True, False])
+def test_bivariate_heat_waves(cuda, before):
+    from xclim_b200 import indices, generic
+    rng = np.random.default_rng(7)
+    T, shape = 365 * 2 + 20, (5, 8)
+    season = 10 * np.sin(2 * np.pi * (np.arange(T) - 100) / 365)[:, None, None]
+    tn = (291 + season + 3 * rng.standard_normal((T,) + shape)).astype(np.float32)
+    tx = (tn + 8 + 2 * rng.standard_normal((T,) + shape)).astype(np.float32)
+    tn[rng.random(tn.shape) < 0.01] = np.nan
+    tx[rng.random(tx.shape) < 0.01] = np.nan
+    dtn, dtx = make_field(tn, "2001-01-01", units="K"), make_field(tx, "2001-01-01", units="K")
+    poff = dtn.time.period_offsets("YS")
+    cond = O.compare(tn, ">", 22 + 273.15) & O.compare(tx, ">", 30 + 273.15)
+    for fn, red in ((indices.heat_wave_frequency, "count"), (indices.heat_wave_max_length, "max"),
+                    (indices.heat_wave_total_length, "sum")):
+        got = fn(dtn, dtx, window=3, resample_before_rl=before).values
+        exp = O.resample_and_rl(cond, before, O.rle_statistics, poff=poff, reducer=red, window=3)
+        np.testing.assert_array_equal(got, exp.astype(np.float32), err_msg=fn.__name__)
+    np.testing.assert_array_equal(indices.tx_tn_days_above(dtn, dtx).values,
+                                  np.stack([cond[s:e].sum(0) for s, e in zip(poff[:-1], poff[1:])]))
+    got = generic.bivariate_count_occurrences(data_var1=dtn, data_var2=dtx, threshold_var1=295.15, threshold_var2=303.15,
+                                              freq="MS", op_var1=">", op_var2="<", var_reducer="any").values
+    cond2 = O.compare(tn, ">", 295.15) | O.compare(tx, "<", 303.15)
+    pm = dtn.time.period_offsets("MS")
+    np.testing.assert_array_equal(got, np.stack([cond2[s:e].sum(0) for s, e in zip(pm[:-1], pm[1:])]))
+    with pytest.raises(ValueError, match="Unsupported value"):
+        generic.bivariate_count_occurrences(data_var1=dtn, data_var2=dtx, threshold_var1=1, threshold_var2=1, freq="YS",
+                                            op_var1=">", op_var2=">", var_reducer="most")

@@ -13,6 +13,7 @@ from ._build import LIB_PATH
 XC_OK, XC_ERR_INVALID, XC_ERR_UNSUPPORTED, XC_ERR_CUDA = 0, -1, -2, -3
 
 OPS = {">": 0, "gt": 0, "<": 1, "lt": 1, ">=": 2, "ge": 2, "<=": 3, "le": 3, "==": 4, "eq": 4, "!=": 5, "ne": 5}
+OP_ISNAN, OP_NOTNAN = 6, 7
 RL_REDUCERS = {"max": 0, "min": 1, "sum": 2, "count": 3, "mean": 4, "std": 5}
 STATS = {"sum": 0, "integral": 0, "mean": 1, "min": 2, "max": 3, "std": 4, "var": 5, "count": 6}
 TF_NONE, TF_EXCESS, TF_WHERE = 0, 1, 2
@@ -27,6 +28,8 @@ SIGNATURES = {
     "xc_period_count_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _i32, _f64, _i32, _vp, _vp, _vp]),
     "xc_period_runstat_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _i32, _f64, _i32, _i32, _i32, _i32,
                                      _vp, _vp, _vp]),
+    "xc_period_runstat2_f32": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _i32, _f64, _i32, _f64, _i32, _i32, _i32,
+                                      _i32, _vp, _vp]),
     "xc_period_run_maxsum_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _i32, _f64, _i32, _i32, _vp, _vp]),
     "xc_period_boundary_run_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _i32, _f64, _i32, _i32, _i32, _vp, _vp]),
     "xc_period_boundary_run_range_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _f64, _i32, _i32,

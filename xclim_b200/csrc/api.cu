@@ -23,7 +23,7 @@ int32_t cuda_fail(cudaError_t e, const char* what) {
 
 float fold_threshold(int32_t op, double thr, int32_t cmp_f64) {
   float f = (float)thr;  // round to nearest even, as numpy does for a weak Python scalar
-  if (!cmp_f64 || thr != thr) return f;
+  if (!cmp_f64 || thr != thr || op > XC_OP_NE) return f;
   const double fd = (double)f;
   switch (op) {
     case XC_OP_GT:  // x > thr  <=>  x > rd(thr)   (largest float32 <= thr)

@@ -57,6 +57,8 @@ __device__ __forceinline__ bool cmp(float x, float t) {
   if constexpr (OP == XC_OP_GE) return x >= t;
   if constexpr (OP == XC_OP_LE) return x <= t;
   if constexpr (OP == XC_OP_EQ) return x == t;
+  if constexpr (OP == XC_OP_ISNAN) return x != x;
+  if constexpr (OP == XC_OP_NOTNAN) return x == x;
   return x != t;  // NaN != t is True, as in numpy
 }
 template <int OP>
@@ -86,6 +88,14 @@ inline int32_t dispatch_op(int32_t op, F&& f) {
   }
   set_error("Operation `%d` not recognized.", op);
   return XC_ERR_INVALID;
+}
+
+// the six comparison operators plus the two NaN tests (count / run-length entry points only)
+template <typename F>
+inline int32_t dispatch_op_nan(int32_t op, F&& f) {
+  if (op == XC_OP_ISNAN) return f(std::integral_constant<int, XC_OP_ISNAN>{});
+  if (op == XC_OP_NOTNAN) return f(std::integral_constant<int, XC_OP_NOTNAN>{});
+  return dispatch_op(op, f);
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -413,7 +413,7 @@ extern "C" int32_t xc_period_count_f32(const float* x, int64_t T, int64_t C, int
   const float t32 = fold_threshold(op, thr, cmp_f64);
   const bool v4 = can_vec4(x, C, ldx, out_count, valid_count);
   cudaStream_t st = (cudaStream_t)stream;
-  return dispatch_op(op, [&](auto OPC) -> int32_t {
+  return dispatch_op_nan(op, [&](auto OPC) -> int32_t {
     constexpr int OP = decltype(OPC)::value;
     auto go = [&](auto VECC, auto VALC) -> int32_t {
       constexpr int VEC = decltype(VECC)::value;
@@ -461,7 +461,7 @@ extern "C" int32_t xc_period_runstat_f32(const float* x, int64_t T, int64_t C, i
   const float t32 = fold_threshold(op, thr, cmp_f64);
   const bool after = resample_before_rl == 0;
   cudaStream_t st = (cudaStream_t)stream;
-  return dispatch_op(op, [&](auto OPC) -> int32_t {
+  return dispatch_op_nan(op, [&](auto OPC) -> int32_t {
     constexpr int OP = decltype(OPC)::value;
 #define XC_RS(RED, FAST) \
   return launch_runstat<OP, RED, FAST>(x, T, C, ldx, period_offsets, P, t32, window, after, out, valid_count, st)

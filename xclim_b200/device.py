@@ -312,3 +312,16 @@ def period_boundary_run_range(x2d, poff, range_lo, range_hi, op_code, thr, windo
                                                   int(bool(cmp_f64)), int(bool(negate)), int(window), int(bool(last)),
                                                   _ptr(cell_lo), out.data_ptr(), current_stream_ptr()))
     return out
+
+
+def period_runstat2(x1, x2, poff, op1, thr1, op2, thr2, reducer_code, window, resample_before_rl=True, var_any=False):
+    """Run statistics of (x1 op1 thr1) AND|OR (x2 op2 thr2) per period (heat_wave_* family)."""
+    T, C = x1.shape
+    assert x2.shape == x1.shape and x1.stride(0) == x2.stride(0)
+    P = len(poff) - 1
+    poff_d = dev_ints(poff, np.int32, x1.device)
+    out = torch.empty((P, C), dtype=torch.float32, device=x1.device)
+    check(load().xc_period_runstat2_f32(x1.data_ptr(), x2.data_ptr(), T, C, x1.stride(0), poff_d.data_ptr(), P, op1,
+                                        float(thr1), op2, float(thr2), int(bool(var_any)), reducer_code, int(window),
+                                        int(bool(resample_before_rl)), out.data_ptr(), current_stream_ptr()))
+    return out

@@ -230,3 +230,22 @@ def first_day_threshold_reached(data, *, threshold, op, after_date, window=1, fr
     attrs = attrs_of(data)
     attrs.update(units="", is_dayofyear=np.int32(1), calendar=ta.calendar)
     return _wrap_periods(data, out, cell_shape, other, ta, freq, attrs, dtype=np.float64)
+
+
+def bivariate_count_occurrences(*, data_var1, data_var2, threshold_var1, threshold_var2, freq, op_var1, op_var2,
+                                var_reducer, constrain_var1=None, constrain_var2=None):
+    """indices/generic.py:1002-1073: count of steps where both ("all") or either ("any") condition holds."""
+    if var_reducer not in ("all", "any"):
+        raise ValueError(f"Unsupported value for var_reducer: {var_reducer}")
+    c1, c2 = get_op(op_var1, constrain_var1), get_op(op_var2, constrain_var2)
+    t1 = threshold_in_units_of(threshold_var1, data_var1) if isinstance(threshold_var1, str) else float(threshold_var1)
+    t2 = threshold_in_units_of(threshold_var2, data_var2) if isinstance(threshold_var2, str) else float(threshold_var2)
+    x1, cell_shape, other, ta = _unwrap(data_var1)
+    x2, cs2, _, _ = _unwrap(data_var2)
+    if cs2 != cell_shape:
+        raise ValueError("the two variables must share the same grid")
+    out = device.period_runstat2(x1, x2, ta.period_offsets(freq), c1, t1, c2, t2, _lib.RL_REDUCERS["sum"], 1, True,
+                                 var_any=(var_reducer == "any"))
+    attrs = attrs_of(data_var1)
+    attrs["units"] = "d"
+    return _wrap_periods(data_var1, out, cell_shape, other, ta, freq, attrs, dtype=np.int64)

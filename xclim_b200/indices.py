@@ -455,3 +455,49 @@ def last_spring_frost(tasmin, thresh="0 degC", op="<", before_date="07-01", wind
     attrs = attrs_of(tasmin)
     attrs.update(units="", is_dayofyear=np.int32(1), calendar=ta.calendar)
     return _wrap_periods(tasmin, out, cell_shape, other, ta, freq, attrs, dtype=np.float64)
+
+
+# ---- bivariate conditions (indices/_multivariate.py:646-880, 1653-1716; generic.py:1002-1073)
+def _bivariate(v1, v2, th1, th2, op1, op2, reducer, window, freq, resample_before_rl, units, var_any=False,
+               constrain=None, dtype=None):
+    import numpy as np
+
+    from . import _lib, device
+    from .field import attrs_of
+    from .generic import _unwrap, _wrap_periods
+    c1, c2 = _lib.op_code(op1, constrain), _lib.op_code(op2, constrain)
+    t1 = threshold_in_units_of(th1, v1) if isinstance(th1, str) else float(th1)
+    t2 = threshold_in_units_of(th2, v2) if isinstance(th2, str) else float(th2)
+    x1, cell_shape, other, ta = _unwrap(v1)
+    x2, cs2, _, ta2 = _unwrap(v2)
+    if cs2 != cell_shape or len(ta2) != len(ta):
+        raise ValueError("the two variables must share the same grid and time axis")
+    out = device.period_runstat2(x1, x2, ta.period_offsets(freq), c1, t1, c2, t2, _lib.RL_REDUCERS[reducer], window,
+                                 resample_before_rl, var_any)
+    attrs = attrs_of(v1)
+    attrs["units"] = units
+    return _wrap_periods(v1, out, cell_shape, other, ta, freq, attrs, dtype=dtype or np.float32)
+
+
+def heat_wave_frequency(tasmin, tasmax, thresh_tasmin="22.0 degC", thresh_tasmax="30 degC", window=3, freq="YS", op=">",
+                        resample_before_rl=True):
+    return _bivariate(tasmin, tasmax, thresh_tasmin, thresh_tasmax, op, op, "count", window, freq, resample_before_rl,
+                      "", constrain=(">", ">="))
+
+
+def heat_wave_max_length(tasmin, tasmax, thresh_tasmin="22.0 degC", thresh_tasmax="30 degC", window=3, freq="YS", op=">",
+                         resample_before_rl=True):
+    return _bivariate(tasmin, tasmax, thresh_tasmin, thresh_tasmax, op, op, "max", window, freq, resample_before_rl,
+                      "d", constrain=(">", ">="))
+
+
+def heat_wave_total_length(tasmin, tasmax, thresh_tasmin="22.0 degC", thresh_tasmax="30 degC", window=3, freq="YS",
+                           op=">", resample_before_rl=True):
+    return _bivariate(tasmin, tasmax, thresh_tasmin, thresh_tasmax, op, op, "sum", window, freq, resample_before_rl,
+                      "d", constrain=(">", ">="))
+
+
+def tx_tn_days_above(tasmin, tasmax, thresh_tasmin="22 degC", thresh_tasmax="30 degC", freq="YS", op=">"):
+    import numpy as np
+    return _bivariate(tasmin, tasmax, thresh_tasmin, thresh_tasmax, op, op, "sum", 1, freq, True, "d",
+                      constrain=(">", ">="), dtype=np.int64)
