@@ -240,7 +240,10 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "period_runstat_kernel<LT,MAX,VEC4,VALID,FASTMAX>",
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, from the ncu
+                # --set full capture summarised in profiles/ncu_full_r1.md (45.475 GB + 0.216 GB per launch)
+                "traffic": 45.691e9 if (Y == Y_FULL) else None,
+                "kernel": "period_runstat_kernel<LT,MAX,VEC4,VALID,FASTMAX>",
                 "algorithmic_bytes": alg_bytes,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"}
 

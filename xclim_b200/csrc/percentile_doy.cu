@@ -276,14 +276,20 @@ percentile_doy_uniform_kernel(const float* __restrict__ x, int32_t T, int64_t C,
 #ifndef XC_PCTL_MINBLOCKS
 #define XC_PCTL_MINBLOCKS 7
 #endif
-template <int K, bool TABLE>
+// COUNT_OP >= 0 fuses the percentile-threshold day count of the SAME series (tx90p with the base period
+// equal to the studied period, sub-case 3a of SURVEY.md section 8d): once P(d) is known the N values
+// of day d (read two iterations earlier, so they come from L2) are compared with it and tallied per
+// year in shared memory; the input is read from HBM once for both results.
+template <int K, bool TABLE, int COUNT_OP = -1>
 __global__ void __launch_bounds__(kThreads, XC_PCTL_MINBLOCKS)
 percentile_doy_w5_kernel(const float* __restrict__ x, int32_t T, int64_t C, int64_t ldx, int32_t L, int32_t N,
                          QuantSpec spec, int32_t doys_per_chunk, double* __restrict__ out,
-                         const int32_t* __restrict__ pos, int32_t n_doy, int32_t d_begin, int32_t d_end) {
+                         const int32_t* __restrict__ pos, int32_t n_doy, int32_t d_begin, int32_t d_end,
+                         int32_t* __restrict__ year_counts = nullptr, int32_t* __restrict__ year_valid = nullptr) {
   extern __shared__ float smem[];
   float* ring = smem;                                                   // [3][K][kThreads]
   int* rcnt = reinterpret_cast<int*>(smem + (size_t)3 * K * kThreads);  // [3][kThreads]
+  unsigned* ycnt = reinterpret_cast<unsigned*>(rcnt + 3 * kThreads);    // [N][kThreads], COUNT_OP >= 0 only
   const int lane = threadIdx.x;
   const int64_t c = (int64_t)blockIdx.x * kThreads + lane;
   if (c >= C) return;
@@ -292,6 +298,9 @@ percentile_doy_w5_kernel(const float* __restrict__ x, int32_t T, int64_t C, int6
   if (d0 >= d1) return;
   const bool top = spec.top != 0;
   const int n_full = 5 * N;
+  if constexpr (COUNT_OP >= 0) {
+    for (int y = 0; y < N; ++y) ycnt[y * kThreads + lane] = 0u;
+  }
 
   auto store_pair = [&](int slot, const float (&a)[K], int n) {
 #pragma unroll
@@ -348,6 +357,18 @@ percentile_doy_w5_kernel(const float* __restrict__ x, int32_t T, int64_t C, int6
       res = finalize_quantile<K>(t, n, spec);
     }
     out[(int64_t)d * C + c] = res;
+    if constexpr (COUNT_OP >= 0) {
+      // low 16 bits: exceedances of year y, high 16 bits: valid days of year y
+      const float* p = x + (int64_t)d * ldx + c;
+      const int64_t ystride = (int64_t)L * ldx;
+#pragma unroll 4
+      for (int y = 0; y < N; ++y) {
+        const float v = __ldg(p + (int64_t)y * ystride);
+        unsigned add = cmpd<COUNT_OP>((double)v, res) ? 1u : 0u;
+        add += (v == v) ? 65536u : 0u;
+        ycnt[y * kThreads + lane] += add;
+      }
+    }
     // A(d+2) = Y(d+1) U Y(d+2) replaces A(d-1)
     merge_top_desc<K>(yprev, ynew);
     store_pair(s_lo, yprev, nprev + nnew);
@@ -357,6 +378,13 @@ percentile_doy_w5_kernel(const float* __restrict__ x, int32_t T, int64_t C, int6
     s_lo = (s_lo + 1 == 3) ? 0 : s_lo + 1;
   }
   (void)n_full;
+  if constexpr (COUNT_OP >= 0) {
+    for (int y = 0; y < N; ++y) {
+      const unsigned v = ycnt[y * kThreads + lane];
+      atomicAdd(year_counts + (int64_t)y * C + c, (int)(v & 0xffffu));
+      if (year_valid) atomicAdd(year_valid + (int64_t)y * C + c, (int)(v >> 16));
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -834,5 +862,55 @@ extern "C" int32_t xc_doy_threshold_count_years_f32(const float* x, int64_t T, i
                                                                          table, out_count, valid_count);
     }
     return launch_status("doy_count_years_kernel");
+  });
+}
+
+// Fused tx90p for the case "the percentile base IS the studied series" (uniform calendar, freq YS):
+// one pass produces the (n_doy, C) float64 table and the (n_years, C) int32 day counts.
+extern "C" int32_t xc_percentile_doy_count_f32(const float* x, int64_t T, int64_t C, int64_t ldx, int32_t year_len,
+                                               int32_t n_years, int32_t window, double percentile, double alpha,
+                                               double beta, int32_t op, double* table, int32_t* out_count,
+                                               int32_t* valid_count, void* stream) {
+  XC_REQUIRE(x && table && out_count, "null pointer argument");
+  XC_REQUIRE(T > 0 && C > 0 && ldx >= C && T == (int64_t)year_len * n_years, "series must be n_years whole years");
+  XC_REQUIRE(op >= XC_OP_GT && op <= XC_OP_LE, "Operation `%d` not permitted for indice.", op);
+  if (window != 5) {
+    set_error("the fused percentile + count kernel exists for window == 5 only");
+    return XC_ERR_UNSUPPORTED;
+  }
+  QuantSpec spec;
+  const int need = plan_quantile(percentile, alpha, beta, n_years * window, &spec);
+  if (need < 0 || need > 16 || year_len < 8) {
+    set_error("the fused percentile + count kernel keeps at most 16 order statistics (needs %d)", need);
+    return XC_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  XC_CHECK_CUDA(cudaMemsetAsync(out_count, 0, (size_t)n_years * C * 4, st));
+  if (valid_count) XC_CHECK_CUDA(cudaMemsetAsync(valid_count, 0, (size_t)n_years * C * 4, st));
+  const int64_t cblocks = (C + kThreads - 1) / kThreads;
+  int chunks = (int)((148 * 16 + cblocks - 1) / cblocks);
+  chunks = chunks < 1 ? 1 : chunks;
+  int per = (year_len + chunks - 1) / chunks;
+  if (per < 40) per = 40;
+  if (per > year_len) per = year_len;
+  chunks = (year_len + per - 1) / per;
+  const size_t smem = ((size_t)3 * (16 + 1) + (size_t)n_years) * kThreads * 4;
+  if (smem > 200 * 1024) {
+    set_error("too many years (%d) for the fused kernel", n_years);
+    return XC_ERR_UNSUPPORTED;
+  }
+  dim3 grid((unsigned)cblocks, (unsigned)chunks, 1);
+  return dispatch_op(op, [&](auto OPC) -> int32_t {
+    constexpr int OP = decltype(OPC)::value;
+    if constexpr (OP <= XC_OP_LE) {
+      if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(percentile_doy_w5_kernel<16, false, OP>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(percentile_doy_w5_kernel)");
+      }
+      percentile_doy_w5_kernel<16, false, OP><<<grid, kThreads, smem, st>>>(
+          x, (int32_t)T, C, ldx, year_len, n_years, spec, per, table, nullptr, 0, 0, year_len, out_count, valid_count);
+    }
+    return launch_status("percentile_doy_w5_kernel<count>");
   });
 }
