@@ -309,6 +309,11 @@ int32_t xc_synth_f32(float* out, int64_t T, int64_t C, int64_t ldx, int64_t cell
                      int64_t cells_per_lat, int64_t n_lat_global, int32_t year_len,
                      int32_t kind, uint64_t seed, void* stream);
 
+/* select_time(da, **indexer) with drop=False -- core/calendar.py:1259-1376: out[t, c] = keep[t] ? x[t, c] : NaN
+ * (keep: device uint8[T] built on the host from season / month / doy_bounds / date_bounds). */
+int32_t xc_mask_steps_f32(const float* x, int64_t T, int64_t C, int64_t ldx, const uint8_t* keep,
+                          float* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer entry points (the end-to-end path: host -> device copies inside the call).
  *   x_host: (T, C) float32 in (pinned or pageable) host memory; the call streams year-sized

@@ -806,3 +806,30 @@ def missing_wmo(x, poff_month, parent, n_parent, nm=11, nc=5):
     for m, p in enumerate(parent):
         out[p] |= miss_m[m]
     return out
+
+
+def select_time_mask(month, day, doy, calendar, season=None, months=None, doy_bounds=None, date_bounds=None):
+    """core/calendar.py:1259-1376 as a boolean step mask (inclusive bounds)."""
+    month, day, doy = np.asarray(month), np.asarray(day), np.asarray(doy)
+    if season is not None:
+        names = {12: "DJF", 1: "DJF", 2: "DJF", 3: "MAM", 4: "MAM", 5: "MAM", 6: "JJA", 7: "JJA", 8: "JJA",
+                 9: "SON", 10: "SON", 11: "SON"}
+        want = [season] if isinstance(season, str) else season
+        return np.array([names[int(m)] in want for m in month])
+    if months is not None:
+        return np.isin(month, months)
+    if doy_bounds is not None:
+        a, b = doy_bounds
+        doys = np.arange(a, b + 1) if a <= b else np.concatenate((np.arange(a, 367), np.arange(0, b + 1)))
+        return np.isin(doy, doys)
+    # date bounds: day numbers in the (uniform) calendar, or all_leap numbering for standard calendars
+    leap = calendar not in ("noleap", "365_day", "360_day")
+    def num(m, d):
+        if calendar == "360_day":
+            return (m - 1) * 30 + d
+        dpm = [31, 29 if leap else 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31]
+        return sum(dpm[: m - 1]) + d
+    cur = np.array([num(int(m), int(d)) for m, d in zip(month, day)])
+    a, b = (num(*(int(v) for v in s.split("-"))) for s in date_bounds)
+    doys = np.arange(a, b + 1) if a <= b else np.concatenate((np.arange(a, 367), np.arange(0, b + 1)))
+    return np.isin(cur, doys)

@@ -239,3 +239,28 @@ def test_bivariate_heat_waves(cuda, before):
     with pytest.raises(ValueError, match="Unsupported value"):
         generic.bivariate_count_occurrences(data_var1=dtn, data_var2=dtx, threshold_var1=1, threshold_var2=1, freq="YS",
                                             op_var1=">", op_var2=">", var_reducer="most")
+
+
+@pytest.mark.parametrize("indexer", [{"season": "JJA"}, {"month": [1, 12]}, {"doy_bounds": (300, 40)},
+                                     {"date_bounds": ("02-25", "03-05")}, {"season": ["DJF", "MAM"]}])
+@pytest.mark.parametrize("calendar", ["standard", "noleap"])
+def test_select_time_indexers_on_resample_ops(cuda, indexer, calendar):
+    """select_resample_op(da, op, freq, **indexer): select_time then reduce (indices/generic.py:110-114)."""
+    from xclim_b200 import generic
+    rng = np.random.default_rng(8)
+    x = (280 + 5 * rng.standard_normal((365 * 3 + 1, 4, 6))).astype(np.float32)
+    x[rng.random(x.shape) < 0.01] = np.nan
+    da = make_field(x, "2003-01-01", calendar=calendar, units="K")
+    ta = da.time
+    kw = dict(indexer)
+    if "month" in kw:
+        kw = {"months": kw["month"]}
+    keep = O.select_time_mask(ta.month, ta.day, ta.doy, ta.calendar, **kw)
+    np.testing.assert_array_equal(ta.select_mask(**indexer), keep)
+    xm = np.where(keep[:, None, None], x, np.nan)
+    for op in ("mean", "max", "count", "sum"):
+        got = generic.select_resample_op(da, op, "YS", **indexer).values
+        exp = O.select_resample_op(xm.astype(np.float64), op, ta.period_offsets("YS"))
+        np.testing.assert_allclose(got, exp.astype(got.dtype) if op == "count" else exp, rtol=1e-5, equal_nan=True)
+    with pytest.raises(ValueError, match="Only one method"):
+        generic.select_resample_op(da, "mean", "YS", season="JJA", month=[1])

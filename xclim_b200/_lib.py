@@ -53,6 +53,7 @@ SIGNATURES = {
     "xc_eqm_train_f32": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
     "xc_eqm_adjust_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "xc_synth_f32": (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _u64, _vp]),
+    "xc_mask_steps_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "xc_host_stream_workspace_bytes": (_i64, [_i64, _i64, _vp, _i32]),
     "xc_period_runstat_f32_host": (_i32, [_vp, _i64, _i64, _vp, _i32, _i32, _f64, _i32, _i32, _i32, _vp, _vp,
                                           _vp, _i64]),

@@ -85,3 +85,42 @@ extern "C" int32_t xc_synth_f32(float* out, int64_t T, int64_t C, int64_t ldx, i
     synth_kernel<1><<<grid, 256, 0, st>>>(out, T, C, ldx, cell_offset, cells_per_lat, n_lat_global, year_len, seed);
   return launch_status("synth_kernel");
 }
+
+// ---------------------------------------------------------------------------------------------
+// select_time as a step mask (core/calendar.py:1259-1376 with drop=False: `da.where(mask)`):
+// out[t, c] = keep[t] ? x[t, c] : NaN.  One streaming pass; the kernels downstream already treat NaN
+// as "not selected" (NaN compares False, reductions skip NaN).
+// ---------------------------------------------------------------------------------------------
+namespace xc {
+namespace {
+__global__ void __launch_bounds__(256)
+mask_steps_kernel(const float* __restrict__ x, int64_t T, int64_t C, int64_t ldx, const uint8_t* __restrict__ keep,
+                  float* __restrict__ out) {
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= C) return;
+  const int rows = (int)((T + gridDim.y - 1) / gridDim.y);
+  const int64_t t0 = (int64_t)blockIdx.y * rows, t1 = min(T, t0 + rows);
+  const bool v4 = (c + 3 < C) && ((ldx & 3) == 0) && ((C & 3) == 0) &&
+                  ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+  for (int64_t t = t0; t < t1; ++t) {
+    const bool k = keep[t] != 0;
+    if (v4) {
+      float4 v = make_float4(NAN, NAN, NAN, NAN);
+      if (k) v = ld_stream4(x + t * ldx + c);
+      *reinterpret_cast<float4*>(out + t * C + c) = v;
+    } else {
+      for (int i = 0; i < 4 && c + i < C; ++i) out[t * C + c + i] = k ? x[t * ldx + c + i] : NAN;
+    }
+  }
+}
+}  // namespace
+}  // namespace xc
+
+extern "C" int32_t xc_mask_steps_f32(const float* x, int64_t T, int64_t C, int64_t ldx, const uint8_t* keep,
+                                     float* out, void* stream) {
+  XC_REQUIRE(x && keep && out, "null pointer argument");
+  XC_REQUIRE(T > 0 && C > 0 && ldx >= C, "bad shape");
+  dim3 grid((unsigned)(((C + 3) / 4 + 255) / 256), (unsigned)(T < 128 ? T : 128), 1);
+  mask_steps_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, T, C, ldx, keep, out);
+  return launch_status("mask_steps_kernel");
+}

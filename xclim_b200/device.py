@@ -337,3 +337,13 @@ def percentile_doy_count(x2d, year_len, n_years, window, percentile, alpha, beta
                                              int(window), float(percentile), float(alpha), float(beta), op_code,
                                              table.data_ptr(), cnt.data_ptr(), _ptr(valid), current_stream_ptr()))
     return table, cnt, valid
+
+
+def mask_steps(x2d, keep):
+    """``select_time`` with drop=False: NaN on the steps where ``keep`` is False (a new buffer)."""
+    T, C = x2d.shape
+    k = dev_ints(np.asarray(keep, dtype=np.uint8), np.uint8, x2d.device)
+    out = torch.empty((T, C), dtype=torch.float32, device=x2d.device)
+    check(load().xc_mask_steps_f32(x2d.data_ptr(), T, C, x2d.stride(0), k.data_ptr(), out.data_ptr(),
+                                   current_stream_ptr()))
+    return out

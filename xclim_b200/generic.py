@@ -13,14 +13,19 @@ from .units import threshold_in_units_of, to_agg_units_attrs
 
 
 # --------------------------------------------------------------------------------------- plumbing
-def _unwrap(da):
+def _unwrap(da, indexer=None):
     dims = dims_of(da)
     if "time" not in dims:
         raise ValueError("input must have a `time` dimension")
     tpos = dims.index("time")
     x2d, cell_shape = device.to_time_cell(raw_values(da), tpos)
     other = tuple(d for d in dims if d != "time")
-    return x2d, cell_shape, other, time_axis_of(da)
+    ta = time_axis_of(da)
+    if indexer:  # select_time(da, **indexer), drop=False (core/calendar.py:1259-1376)
+        keep = ta.select_mask(**indexer)
+        if not keep.all():
+            x2d = device.mask_steps(x2d, keep)
+    return x2d, cell_shape, other, ta
 
 
 def _period_time(da, ta, freq):
@@ -94,11 +99,9 @@ def domain_count(da, low, high, freq):
 # --------------------------------------------------------------------------------- a3 resample ops
 def select_resample_op(da, op, freq="YS", out_units=None, **indexer):
     """Per-period reduction -- indices/generic.py:83-125 (string ops only)."""
-    if indexer:
-        raise NotImplementedError("select_time indexers are outside the B200 hot path (SURVEY.md section 8f)")
     if not isinstance(op, str) or op not in _lib.STATS:
         raise NotImplementedError(f"resample op {op!r} is not supported by the B200 hot path")
-    x2d, cell_shape, other, ta = _unwrap(da)
+    x2d, cell_shape, other, ta = _unwrap(da, indexer)
     out, _ = device.period_reduce(x2d, ta.period_offsets(freq), _lib.STATS[op])
     attrs = attrs_of(da)
     attrs.update({"units": out_units} if out_units is not None else to_agg_units_attrs(da, op.replace("integral", "sum")))
@@ -156,9 +159,11 @@ def spell_length_statistics(data, threshold, window, win_reducer, op, spell_redu
 def select_rolling_resample_op(da, op, window, window_center=True, window_op="mean", freq="YS", out_units=None,
                                **indexer):
     """Rolling window statistic, then per-period reduction -- indices/generic.py:128-174."""
-    if indexer:
-        raise NotImplementedError("select_time indexers are outside the B200 hot path (SURVEY.md section 8f)")
     wop = window_op.replace("integral", "sum")
+    if indexer:
+        # the reference selects AFTER rolling (indices/generic.py:169-174): rolling on the full series, then
+        # select_time on the rolled values -- not expressible as a mask on the input
+        raise NotImplementedError("select_time indexers on rolling ops are not supported by the B200 hot path")
     if wop not in ("sum", "mean", "min", "max"):
         raise NotImplementedError(f"rolling window_op {window_op!r} is not supported by the B200 hot path")
     if not isinstance(op, str) or op not in _lib.STATS:

@@ -250,3 +250,48 @@ class TimeAxis:
                 raise ValueError(f"More than 1 instance of date {date} found in the coordinate array.")
             out[p] = t
         return out
+
+    # ------------------------------------------------------------------ select_time
+    def select_mask(self, season=None, month=None, doy_bounds=None, date_bounds=None, include_bounds=True):
+        """Boolean step mask of ``select_time`` (core/calendar.py:1259-1376): exactly one of
+        ``season`` ("DJF", ...), ``month``, ``doy_bounds`` (ints) or ``date_bounds`` ("MM-DD", "MM-DD")."""
+        given = sum(a is not None for a in (season, month, doy_bounds, date_bounds))
+        if given > 1:
+            raise ValueError(f"Only one method of indexing may be given, got {given}.")
+        if given == 0:
+            return np.ones(len(self), bool)
+        if isinstance(include_bounds, bool):
+            include_bounds = (include_bounds, include_bounds)
+        if season is not None:
+            seasons = [season] if isinstance(season, str) else list(season)
+            names = np.array(["DJF", "DJF", "MAM", "MAM", "MAM", "JJA", "JJA", "JJA", "SON", "SON", "SON", "DJF"])
+            return np.isin(names[self.month - 1], seasons)
+        if month is not None:
+            months = [month] if isinstance(month, int) else list(month)
+            return np.isin(self.month, months)
+        if doy_bounds is not None:
+            lo, hi = (int(v) for v in doy_bounds)
+            return _between_doys(self.doy, lo, hi, include_bounds)
+        start, end = date_bounds
+        if self.calendar in ("noleap", "365_day", "360_day", "all_leap", "366_day"):
+            cal, doy = self.calendar, self.doy
+        else:  # non-uniform calendars are compared on the all_leap day numbers (:1343-1349)
+            cal = "all_leap"
+            doy = np.concatenate([[0], np.cumsum(_DPM_LEAP)])[self.month - 1] + self.day
+        def dnum(md):
+            mm, dd = (int(v) for v in md.split("-"))
+            if cal == "360_day":
+                return (mm - 1) * 30 + dd
+            dpm = _DPM_LEAP if cal in ("all_leap", "366_day") else _DPM_NOLEAP
+            return int(np.concatenate([[0], np.cumsum(dpm)])[mm - 1] + dd)
+        return _between_doys(doy, dnum(start), dnum(end), include_bounds)
+
+
+def _between_doys(doy, start, end, inclusive):
+    """Steps whose day number lies between ``start`` and ``end`` (the interval wraps the year end when
+    end < start); a bound flagged non-inclusive is excluded.  Same set as ``isin(_get_doys(...))`` of
+    the reference (core/calendar.py:1137-1163)."""
+    doy = np.asarray(doy)
+    lo_ok = (doy >= start) if inclusive[0] else (doy > start)
+    hi_ok = (doy <= end) if inclusive[1] else (doy < end)
+    return (lo_ok & hi_ok) if start <= end else (lo_ok | hi_ok)
