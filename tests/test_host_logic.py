@@ -1,0 +1,69 @@
+"""CPU tests of the host layer that need no GPU: units, containers, period bookkeeping, error behaviour."""
+import numpy as np
+import pytest
+
+from xclim_b200 import Field, TimeAxis
+from xclim_b200 import units as U
+
+
+def test_unit_conversions():
+    # thresholds reach the kernels as Python floats (core/units.py:398-403)
+    assert U.convert_units_to("1 mm/day", "mm/d") == 1.0
+    assert U.convert_units_to("1 mm/day", "kg m-2 s-1") == pytest.approx(1 / 86400)
+    assert U.convert_units_to("25 degC", "K") == pytest.approx(298.15)
+    assert U.convert_units_to("0 °C", "K") == pytest.approx(273.15)
+    assert U.convert_units_to("300 K", "degC") == pytest.approx(26.85)
+    assert U.convert_units_to(3.5, "K") == 3.5
+    assert isinstance(U.convert_units_to("25 degC", "K"), float)
+    with pytest.raises(ValueError):
+        U.convert_units_to("1 mm/day", "K")
+    assert U.parse_quantity("10.8 m s-1") == (10.8, "m s-1")
+    da = Field(np.zeros((3, 2), np.float32), ("time", "x"), TimeAxis.daily("2000-01-01", 3), attrs={"units": "K"})
+    assert U.threshold_in_units_of("0 degC", da) == pytest.approx(273.15)
+    assert U.to_agg_units_attrs(da, "count") == {"units": "d"} and U.to_agg_units_attrs(da, "mean") == {"units": "K"}
+
+
+def test_field_container_and_wrapping():
+    from xclim_b200.field import wrap_like, time_axis_of, dims_of
+    ta = TimeAxis.daily("2001-01-01", 10, "noleap")
+    f = Field(np.arange(40, dtype=np.float32).reshape(10, 2, 2), ("time", "lat", "lon"), ta,
+              {"lat": np.array([0., 1.]), "lon": np.array([5., 6.])}, {"units": "K"})
+    assert f.shape == (10, 2, 2) and dims_of(f) == ("time", "lat", "lon") and time_axis_of(f) is ta
+    sub = f.isel_time(slice(2, 5))
+    assert sub.shape == (3, 2, 2) and len(sub.time) == 3 and sub.time.doy[0] == 3
+    out = wrap_like(f, np.zeros((1, 2, 2)), ("time", "lat", "lon"), time=np.array(["2001-01-01"]), attrs={"units": "d"})
+    assert out.attrs["units"] == "d" and (out.coords["lat"] == f.coords["lat"]).all() and "time" in out.coords
+    with pytest.raises(TypeError):
+        time_axis_of(np.zeros(3))
+
+
+def test_date_index_and_bootstrap_groups():
+    ta = TimeAxis.daily("2000-01-01", 730)
+    mids = ta.date_index_in_periods("YS", "07-01")
+    assert ta.date_strings(mids) == ["2000-07-01", "2001-07-01"]
+    assert (ta.date_index_in_periods("YS-JUL", "01-01") >= 0).tolist() == [True, True, False]
+    with pytest.raises(ValueError, match="More than 1 instance"):
+        TimeAxis.daily("2000-01-01", 800).date_index_in_periods("2YS", "07-01")
+    assert ta.sel_years(2001, 2001) == slice(366, 730)
+
+
+def test_lat_tiles_cover_grid():
+    from xclim_b200.multigpu import lat_tiles, shard_lat
+    x = np.arange(721 * 3).reshape(1, 721, 3)
+    parts = [shard_lat(x, 1, r, 8) for r in range(8)]
+    assert sum(p.shape[1] for p in parts) == 721
+    np.testing.assert_array_equal(np.concatenate(parts, axis=1), x)
+
+
+def test_no_cuda_means_loud_failure():
+    """No CPU fallback: without a CUDA device the device layer raises (never silently computes)."""
+    import torch
+    from xclim_b200 import device, _lib
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_lib.XclimB200Error, match="no CPU fallback"):
+        device.to_time_cell(np.zeros((4, 2), np.float32), 0)
+    from xclim_b200 import indices
+    f = Field(np.zeros((365, 2), np.float32), ("time", "x"), TimeAxis.daily("2001-01-01", 365), attrs={"units": "mm/d"})
+    with pytest.raises(_lib.XclimB200Error):
+        indices.maximum_consecutive_dry_days(f)

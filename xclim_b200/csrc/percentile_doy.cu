@@ -267,6 +267,22 @@ percentile_doy_uniform_kernel(const float* __restrict__ x, int32_t T, int64_t C,
   }
 }
 
+// float32 threshold t32 with (x op t32) == ((double)x op t) for every float32 x (directed rounding)
+template <int OP>
+__device__ __forceinline__ float fold_thr(double t) {
+  float f = __double2float_rn(t);
+  if (t != t) return f;  // NaN threshold: every compare is False
+  if constexpr (OP == XC_OP_GT || OP == XC_OP_LE) {  // largest float32 <= t
+    if ((double)f > t) f = __int_as_float(__float_as_int(f) + ((f > 0.f) ? -1 : 1));
+    if (f == 0.f && t < 0.0) f = -1.401298464e-45f;
+  } else {                                           // smallest float32 >= t
+    if ((double)f < t) f = __int_as_float(__float_as_int(f) + ((f >= 0.f) ? 1 : -1));
+    if (f == 0.f && t > 0.0) f = 1.401298464e-45f;
+  }
+  return f;
+}
+
+
 // Window 5 specialisation: adjacent day lists are merged in PAIRS, A(e) = Y(e-1) U Y(e), which are
 // reused by two different days:  S(d) = A(d-1) U A(d+1) U Y(d+2).  Per day: one pair merge, one
 // merge of two stored pairs and one final merge -- and when no NaN is present in the lane's sample
@@ -358,15 +374,23 @@ percentile_doy_w5_kernel(const float* __restrict__ x, int32_t T, int64_t C, int6
     }
     out[(int64_t)d * C + c] = res;
     if constexpr (COUNT_OP >= 0) {
-      // low 16 bits: exceedances of year y, high 16 bits: valid days of year y
+      // low 16 bits: exceedances of year y, high 16 bits: valid days of year y.  P(d) is folded once to
+      // the float32 threshold with the same truth table (directed rounding); 16 rows in flight.
+      const float thr = fold_thr<COUNT_OP>(res);
       const float* p = x + (int64_t)d * ldx + c;
       const int64_t ystride = (int64_t)L * ldx;
-#pragma unroll 4
-      for (int y = 0; y < N; ++y) {
-        const float v = __ldg(p + (int64_t)y * ystride);
-        unsigned add = cmpd<COUNT_OP>((double)v, res) ? 1u : 0u;
-        add += (v == v) ? 65536u : 0u;
-        ycnt[y * kThreads + lane] += add;
+      for (int y0 = 0; y0 < N; y0 += 16) {
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = (y0 + k < N) ? __ldg(p + (int64_t)(y0 + k) * ystride) : NAN;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          if (y0 + k < N) {
+            unsigned add = cmp<COUNT_OP>(v[k], thr) ? 1u : 0u;
+            add += (v[k] == v[k]) ? 65536u : 0u;
+            ycnt[(y0 + k) * kThreads + lane] += add;
+          }
+        }
       }
     }
     // A(d+2) = Y(d+1) U Y(d+2) replaces A(d-1)
@@ -484,20 +508,6 @@ doy_count_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, const int3
 // (the table is 365*C*8 B = 3 GB at full size, far beyond L2), and it is folded once per row into a
 // float32 threshold by directed rounding (x op t64  <=>  x op' t32 for every float32 x), which turns
 // the per-element float64 compare + conversion into one float32 compare.
-template <int OP>
-__device__ __forceinline__ float fold_thr(double t) {
-  float f = __double2float_rn(t);
-  if (t != t) return f;  // NaN threshold: every compare is False
-  if constexpr (OP == XC_OP_GT || OP == XC_OP_LE) {  // largest float32 <= t
-    if ((double)f > t) f = __int_as_float(__float_as_int(f) + ((f > 0.f) ? -1 : 1));
-    if (f == 0.f && t < 0.0) f = -1.401298464e-45f;
-  } else {                                           // smallest float32 >= t
-    if ((double)f < t) f = __int_as_float(__float_as_int(f) + ((f >= 0.f) ? 1 : -1));
-    if (f == 0.f && t > 0.0) f = 1.401298464e-45f;
-  }
-  return f;
-}
-
 template <int OP, int YB, bool VALID>
 __global__ void __launch_bounds__(kThreads)
 doy_count_years_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int64_t first_row, int32_t n_years,
