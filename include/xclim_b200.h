@@ -124,6 +124,14 @@ int32_t xc_period_runstat2_f32(const float* x1, const float* x2, int64_t T, int6
                                int32_t reducer, int32_t window, int32_t resample_before_rl,
                                float* out, void* stream);
 
+/* a10 (cont.)  quantile reducers ("q90", "q10", ...) of rle_statistics -- indices/run_length.py:320-327
+ *   with reducer "quantile": numpy's linear quantile q of the run lengths >= window attributed to the
+ *   period, 0 when there is none.  period_offsets_host mirrors period_offsets (run-list sizing). */
+int32_t xc_period_run_quantile_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                   const int32_t* period_offsets, const int32_t* period_offsets_host, int32_t P,
+                                   int32_t op, double thr, int32_t cmp_f64, double q,
+                                   int32_t window, int32_t resample_before_rl, float* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a11  windowed_max_run_sum of the excess over a threshold -- indices/run_length.py:491-540 on
  *   `(x - thr).clip(0)` (indices/_threshold.py:2064-2073, `hot_spell_max_magnitude`): per period the

@@ -264,3 +264,26 @@ def test_select_time_indexers_on_resample_ops(cuda, indexer, calendar):
         np.testing.assert_allclose(got, exp.astype(got.dtype) if op == "count" else exp, rtol=1e-5, equal_nan=True)
     with pytest.raises(ValueError, match="Only one method"):
         generic.select_resample_op(da, "mean", "YS", season="JJA", month=[1])
+
+
+def test_run_length_quantile_reducers(cuda):
+    """rle_statistics(reducer="q90"/"q10") -- reference known answers 299.6 and 64.4
+    (tests/test_run_length.py:264-278) and parity on random masks."""
+    from xclim_b200 import run_length as rl
+    v = np.ones(365); v[35] = 0
+    da = make_field(v != 0, "2000-01-01", units="")
+    assert rl.rle_statistics(da, "q90", 1, freq="YS").values[0] == pytest.approx(299.6, rel=1e-6)
+    assert rl.rle_statistics(da, "q10", 1, freq="YS").values[0] == pytest.approx(64.4, rel=1e-6)
+    rng = np.random.default_rng(9)
+    m = rng.random((730, 5, 6)) < 0.6
+    da = make_field(m, "2001-01-01", units="")
+    for freq in ("YS", "MS"):
+        poff = da.time.period_offsets(freq)
+        for red in ("q50", "q90", "q25"):
+            for w in (1, 2):
+                got = rl.rle_statistics(da, red, w, freq=freq).values
+                exp = O.rle_statistics(m, red, w, poff=poff)
+                np.testing.assert_allclose(got, exp, rtol=1e-6, err_msg=f"{red} w={w} {freq}")
+                got = rl.resample_and_rl(da, True, rl.rle_statistics, reducer=red, window=w, freq=freq).values
+                exp = O.resample_and_rl(m, True, O.rle_statistics, poff=poff, reducer=red, window=w)
+                np.testing.assert_allclose(got, exp, rtol=1e-6)

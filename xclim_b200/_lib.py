@@ -30,6 +30,8 @@ SIGNATURES = {
                                      _vp, _vp, _vp]),
     "xc_period_runstat2_f32": (_i32, [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _i32, _f64, _i32, _f64, _i32, _i32, _i32,
                                       _i32, _vp, _vp]),
+    "xc_period_run_quantile_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _f64, _i32, _f64, _i32, _i32,
+                                          _vp, _vp]),
     "xc_period_run_maxsum_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _i32, _f64, _i32, _i32, _vp, _vp]),
     "xc_period_boundary_run_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _i32, _f64, _i32, _i32, _i32, _vp, _vp]),
     "xc_period_boundary_run_range_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _f64, _i32, _i32,

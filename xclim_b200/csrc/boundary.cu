@@ -195,3 +195,108 @@ extern "C" int32_t xc_period_boundary_run_range_f32(const float* x, int64_t T, i
     return launch_status("boundary_run_range_kernel");
   });
 }
+
+// ------------------------------------------------------------------------------------------------
+// Quantile of the run lengths of a period (rle_statistics reducer "qNN")
+// ------------------------------------------------------------------------------------------------
+// Replaces indices/run_length.py:320-327 with reducer = "quantile": `d.where(d >= window).quantile(q)`
+// (numpy's linear / type-7 quantile over the run lengths >= window attributed to the period; 0 when
+// there is none).  A lane owns one (period, cell): run lengths go to its shared-memory column
+// (uint16, at most ceil(len/2) runs), the two neighbouring order statistics are found by counting.
+namespace xc {
+namespace {
+
+template <int OP>
+__global__ void __launch_bounds__(kThreads)
+run_quantile_kernel(const float* __restrict__ x, int64_t T, int64_t C, int64_t ldx, const int32_t* __restrict__ poff,
+                    float thr, int32_t window, int32_t after, double q, int32_t cap, float* __restrict__ out) {
+  extern __shared__ unsigned short runs[];  // [cap][kThreads]
+  const int lane = threadIdx.x;
+  const int64_t c = (int64_t)blockIdx.x * kThreads + lane;
+  if (c >= C) return;
+  const int p = blockIdx.y;
+  const int t0 = poff[p], t1 = poff[p + 1];
+  const float* col = x + c;
+  int m = 0, cur = 0;
+  bool skip = false;
+  if (after && t0 > 0) skip = cmp<OP>(ld_stream(col + (int64_t)(t0 - 1) * ldx), thr);
+  auto close_run = [&]() {
+    if (cur >= window && m < cap) runs[(size_t)m++ * kThreads + lane] = (unsigned short)min(cur, 65535);
+    cur = 0;
+  };
+  for (int t = t0; t < t1; ++t) {
+    bool in = cmp<OP>(ld_stream(col + (int64_t)t * ldx), thr);
+    if (after) {
+      skip = skip && in;
+      in = in && !skip;
+    }
+    if (in) ++cur; else close_run();
+  }
+  if (after) {
+    int t = t1;
+    while (cur > 0 && t < (int)T) {
+      if (cmp<OP>(ld_stream(col + (int64_t)t * ldx), thr)) ++cur; else close_run();
+      ++t;
+    }
+  }
+  close_run();
+  float res = 0.f;
+  if (m > 0) {
+    // numpy linear quantile: pos = q (m - 1); lerp of the two neighbouring order statistics
+    const double pos = q * (double)(m - 1);
+    const int ilo = (int)floor(pos);
+    const int ihi = min(ilo + 1, m - 1);
+    const double g = pos - (double)ilo;
+    float vlo = 0.f, vhi = 0.f;
+    for (int i = 0; i < m; ++i) {
+      const unsigned short vi = runs[(size_t)i * kThreads + lane];
+      int less = 0;
+      for (int k = 0; k < m; ++k) {
+        const unsigned short vk = runs[(size_t)k * kThreads + lane];
+        less += (vk < vi || (vk == vi && k < i)) ? 1 : 0;
+      }
+      if (less == ilo) vlo = (float)vi;
+      if (less == ihi) vhi = (float)vi;
+    }
+    const double d = (double)vhi - (double)vlo;
+    res = (float)((g >= 0.5) ? ((double)vhi - d * (1.0 - g)) : ((double)vlo + d * g));
+  }
+  out[(int64_t)p * C + c] = res;
+}
+
+}  // namespace
+}  // namespace xc
+
+extern "C" int32_t xc_period_run_quantile_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                              const int32_t* period_offsets, const int32_t* period_offsets_host,
+                                              int32_t P, int32_t op, double thr, int32_t cmp_f64, double q,
+                                              int32_t window, int32_t resample_before_rl, float* out, void* stream) {
+  XC_REQUIRE(x && period_offsets && period_offsets_host && out, "null pointer argument");
+  XC_REQUIRE(T > 0 && C > 0 && ldx >= C && P > 0 && P <= 65535 && T < 2147483647LL, "bad shape");
+  XC_REQUIRE(window >= 1 && q >= 0.0 && q <= 1.0, "window must be >= 1 and q in [0, 1]");
+  int maxlen = 0;
+  for (int p = 0; p < P; ++p) {
+    const int len = period_offsets_host[p + 1] - period_offsets_host[p];
+    if (len > maxlen) maxlen = len;
+  }
+  const int cap = maxlen / 2 + 2;
+  const size_t smem = (size_t)cap * kThreads * sizeof(unsigned short);
+  if (smem > 200 * 1024) {
+    set_error("periods of %d steps hold too many runs for the shared-memory run list", maxlen);
+    return XC_ERR_UNSUPPORTED;
+  }
+  const float t32 = fold_threshold(op, thr, cmp_f64);
+  dim3 grid((unsigned)((C + kThreads - 1) / kThreads), (unsigned)P, 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  return dispatch_op(op, [&](auto OPC) -> int32_t {
+    constexpr int OP = decltype(OPC)::value;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(run_quantile_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(run_quantile_kernel)");
+    }
+    run_quantile_kernel<OP><<<grid, kThreads, smem, st>>>(x, T, C, ldx, period_offsets, t32, window,
+                                                          resample_before_rl ? 0 : 1, q, cap, out);
+    return launch_status("run_quantile_kernel");
+  });
+}

@@ -347,3 +347,17 @@ def mask_steps(x2d, keep):
     check(load().xc_mask_steps_f32(x2d.data_ptr(), T, C, x2d.stride(0), k.data_ptr(), out.data_ptr(),
                                    current_stream_ptr()))
     return out
+
+
+def period_run_quantile(x2d, poff, op_code, thr, q, window, resample_before_rl=True, cmp_f64=False):
+    """Linear quantile ``q`` of the run lengths >= window per period (rle_statistics reducer "qNN")."""
+    T, C = x2d.shape
+    P = len(poff) - 1
+    poff_h = np.ascontiguousarray(np.asarray(poff, dtype=np.int32))
+    poff_d = dev_ints(poff_h, np.int32, x2d.device)
+    out = torch.empty((P, C), dtype=torch.float32, device=x2d.device)
+    check(load().xc_period_run_quantile_f32(x2d.data_ptr(), T, C, x2d.stride(0), poff_d.data_ptr(),
+                                            poff_h.ctypes.data, P, op_code, float(thr), int(bool(cmp_f64)), float(q),
+                                            int(window), int(bool(resample_before_rl)), out.data_ptr(),
+                                            current_stream_ptr()))
+    return out

@@ -27,6 +27,17 @@ def _check(freq, index, ufunc_1dim):
                                   "resample_and_rl(..., freq=...)")
 
 
+def _run_reduce(x2d, poff, reducer, window, resample_before_rl):
+    """Run statistic of the mask ``x2d > 0``: named reducers, or "qNN" = quantile 0.NN of the run lengths
+    (indices/run_length.py:320-327)."""
+    if isinstance(reducer, str) and reducer.startswith("q") and reducer[1:].isdigit():
+        return device.period_run_quantile(x2d, poff, _GT, 0.0, float(f"0.{reducer[1:]}"), window, resample_before_rl)
+    if reducer not in _lib.RL_REDUCERS:
+        raise NotImplementedError(f"reducer {reducer!r} is not supported by the B200 hot path")
+    out, _ = device.period_runstat(x2d, poff, _GT, 0.0, _lib.RL_REDUCERS[reducer], window, resample_before_rl)
+    return out
+
+
 def _mask_unwrap(da):
     vals = da.values if not hasattr(da, "numpy") else da.values
     if getattr(vals, "dtype", None) is not None and str(vals.dtype) in ("bool", "torch.bool"):
@@ -49,11 +60,8 @@ def rle_statistics(da, reducer, window, dim="time", freq=None, ufunc_1dim="from_
     if dim != "time":
         raise NotImplementedError("only dim='time' is supported")
     _check(freq, index, ufunc_1dim)
-    if reducer not in _lib.RL_REDUCERS:
-        raise NotImplementedError(f"reducer {reducer!r} is not supported by the B200 hot path")
     x2d, cell_shape, other, ta = _mask_unwrap(da)
-    out, _ = device.period_runstat(x2d, ta.period_offsets(freq), _GT, 0.0, _lib.RL_REDUCERS[reducer], window,
-                                   resample_before_rl=False)
+    out = _run_reduce(x2d, ta.period_offsets(freq), reducer, window, False)
     return _wrap_periods(da, out, cell_shape, other, ta, freq, attrs_of(da), dtype=np.float32)
 
 
@@ -86,8 +94,7 @@ def resample_and_rl(da, resample_before_rl, compute, *args, freq, dim="time", **
         reducer = table[compute]
         window = kwargs.get("window", args[0] if args else None)
     x2d, cell_shape, other, ta = _mask_unwrap(da)
-    out, _ = device.period_runstat(x2d, ta.period_offsets(freq), _GT, 0.0, _lib.RL_REDUCERS[reducer], window,
-                                   resample_before_rl=bool(resample_before_rl))
+    out = _run_reduce(x2d, ta.period_offsets(freq), reducer, window, bool(resample_before_rl))
     return _wrap_periods(da, out, cell_shape, other, ta, freq, attrs_of(da), dtype=np.float32)
 
 
