@@ -50,25 +50,6 @@ def tx90p_section(args, dev, rank, world, peak, barrier):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_per, t_cnt = (float(v) for v in tt.tolist())
 
-    # ---- fused variant (one pass: table + counts), same result
-    for _ in range(2):
-        ft, fc, fv = device.percentile_doy_count(tasmax, YEAR, N, 5, 90.0, 1 / 3, 1 / 3, _lib.OPS[">"], want_valid=True)
-    barrier()
-    ef = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-    ef[0].record()
-    for i in range(steps):
-        ft, fc, fv = device.percentile_doy_count(tasmax, YEAR, N, 5, 90.0, 1 / 3, 1 / 3, _lib.OPS[">"], want_valid=True)
-        ef[i + 1].record()
-    barrier()
-    t_fused = float(np.mean([ef[i].elapsed_time(ef[i + 1]) for i in range(steps)]))
-    tf = torch.tensor([t_fused], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
-    t_fused = float(tf.item())
-    fused_equal = bool(torch.equal(fc, cnt) and torch.equal(fv, valid)
-                       and torch.equal(torch.nan_to_num(ft, nan=-1.0), torch.nan_to_num(table[0], nan=-1.0)))
-    assert fused_equal
-
     # ---- checks: (1) a sample of cells against the CPU oracle (bit-exact table, exact counts)
     sel = torch.tensor([0, 1, C // 3, C // 2 + 7, C - 1], device=dev)
     xs = tasmax[:, sel].cpu().numpy()
@@ -110,12 +91,6 @@ def tx90p_section(args, dev, rank, world, peak, barrier):
         "roofline_count": {"bound": "hbm", "achieved": ach_cnt, "peak": peak, "unit": "GB/s",
                            "frac": ach_cnt / peak, "algorithmic_bytes": alg_cnt, "kernel": "doy_count_kernel<GT>"},
         "gpu_launches_per_step": 2, "cpu_baseline": cpu,
-        "fused": {"ms": t_fused, "value": C * world / (t_fused * 1e-3), "unit": "grid-cells/s",
-                  "algorithmic_bytes": T * C * 4 + YEAR * C * 8 + 2 * N * C * 4,
-                  "achieved_gbs": (T * C * 4 + YEAR * C * 8 + 2 * N * C * 4) / (t_fused * 1e-3) / 1e9,
-                  "frac": (T * C * 4 + YEAR * C * 8 + 2 * N * C * 4) / (t_fused * 1e-3) / 1e9 / peak,
-                  "kernel": "percentile_doy_w5_kernel<16,uniform,count> (xc_percentile_doy_count_f32)",
-                  "identical_to_two_kernel_path": fused_equal},
         "check": {"oracle_cells": int(sel.numel()), "table_bit_exact": table_equal, "counts_exact": counts_equal,
                   "mean_exceedance_fraction": frac},
     }
