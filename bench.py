@@ -127,7 +127,7 @@ def _cpu_cdd_band(args):
 
 def _cpu_procs():
     cores = os.cpu_count() or 1
-    use = max(1, min(cores, 64))
+    use = max(1, cores)          # every host core (bounded below by the memory check: ~3 GB per worker)
     try:
         import psutil
         use = max(1, min(use, int(psutil.virtual_memory().available // (3 << 30))))
