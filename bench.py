@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-tx90p", action="store_true")
-    ap.add_argument("--cpu-lat", type=int, default=16, help="lat rows of the bounded CPU sample")
+    ap.add_argument("--cpu-lat", type=int, default=6, help="lat rows of the bounded CPU sample")
     return ap.parse_args()
 
 
