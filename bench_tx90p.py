@@ -50,42 +50,6 @@ def tx90p_section(args, dev, rank, world, peak, barrier):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_per, t_cnt = (float(v) for v in tt.tolist())
 
-    # ---- pipelined over lat tiles on two streams: the count of tile i (HBM-bound) overlaps the percentile
-    # kernel of tile i+1 (ALU-bound); same kernels, same results
-    n_tiles = 4
-    edges = [(C // n_tiles // 4 * 4) * i for i in range(n_tiles)] + [C]
-    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
-
-    def run_pipelined():
-        outs = []
-        torch.cuda.current_stream().synchronize()
-        for i in range(n_tiles):
-            c0, c1 = edges[i], edges[i + 1]
-            with torch.cuda.stream(streams[i % 2]):
-                tab = device.percentile_doy(tasmax[:, c0:c1], doy, yidx, YEAR, N, 5, [90.0], 1 / 3, 1 / 3)
-                cn, vl = device.doy_threshold_count(tasmax[:, c0:c1], poff, doy, tab[0], _lib.OPS[">"], want_valid=True)
-                outs.append((cn, vl))
-        for st in streams:
-            torch.cuda.current_stream().wait_stream(st)
-        return outs
-
-    run_pipelined()
-    barrier()
-    ep = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-    ep[0].record()
-    for i in range(steps):
-        pouts = run_pipelined()
-        ep[i + 1].record()
-    barrier()
-    t_pipe = float(np.mean([ep[i].elapsed_time(ep[i + 1]) for i in range(steps)]))
-    tp = torch.tensor([t_pipe], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
-    t_pipe = float(tp.item())
-    pipe_equal = bool(torch.equal(torch.cat([o[0] for o in pouts], dim=1), cnt)
-                      and torch.equal(torch.cat([o[1] for o in pouts], dim=1), valid))
-    assert pipe_equal
-
     # ---- checks: (1) a sample of cells against the CPU oracle (bit-exact table, exact counts)
     sel = torch.tensor([0, 1, C // 3, C // 2 + 7, C - 1], device=dev)
     xs = tasmax[:, sel].cpu().numpy()
@@ -127,9 +91,6 @@ def tx90p_section(args, dev, rank, world, peak, barrier):
         "roofline_count": {"bound": "hbm", "achieved": ach_cnt, "peak": peak, "unit": "GB/s",
                            "frac": ach_cnt / peak, "algorithmic_bytes": alg_cnt, "kernel": "doy_count_kernel<GT>"},
         "gpu_launches_per_step": 2, "cpu_baseline": cpu,
-        "pipelined": {"ms": t_pipe, "value": C * world / (t_pipe * 1e-3), "unit": "grid-cells/s", "lat_tiles": n_tiles,
-                      "streams": 2, "identical_counts": pipe_equal,
-                      "note": "count of tile i overlaps percentile_doy of tile i+1 (same kernels, ldx-strided tiles)"},
         "check": {"oracle_cells": int(sel.numel()), "table_bit_exact": table_equal, "counts_exact": counts_equal,
                   "mean_exceedance_fraction": frac},
     }
