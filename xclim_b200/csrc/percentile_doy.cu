@@ -198,7 +198,16 @@ __device__ __forceinline__ void load_day_list(const float* __restrict__ x, int64
       }
     }
     n += nv;
-    sort_desc<K>(v);
+    // the last chunk of e.g. a 30-year base holds 14 values + 2 pads (-inf, already at the bottom):
+    // comparators touching the padded wires are no-ops and are left out (53 instead of 63 for 14 of 16)
+    const int tail = N - y0;  // warp-uniform
+    if constexpr (K == 16) {
+      if (tail == 14) sort_desc_first<16, 14>(v);
+      else if (tail == 15) sort_desc_first<16, 15>(v);
+      else sort_desc<K>(v);
+    } else {
+      sort_desc<K>(v);
+    }
     if (first) {
 #pragma unroll
       for (int k = 0; k < K; ++k) lst[k] = v[k];
