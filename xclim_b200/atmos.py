@@ -1,0 +1,78 @@
+"""Indicator-level entry points for the headline configurations: index + fused missing-value mask.
+
+The reference's ``Indicator.__call__`` (core/indicator.py:865-944) runs ``compute`` and then, in
+``CheckMissingIndicator._postprocess`` (:1522-1549), a SECOND full read of every input to build the
+``MissingAny`` mask (core/missing.py:296-322).  Here the non-NaN step count per period comes out of the
+same streaming kernel as the index (the ``valid_count`` output of the C ABI), so the mask costs no
+extra pass.  Only the numeric part of the Indicator is mirrored: period values are NaN where a period
+has a missing step, ``units`` follow the stock indicators (``days`` / input units); CF attribute
+templating, cfchecks and translations stay with the real xclim.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib, device
+from .calendar import adjust_table, table_on_device
+from .field import attrs_of
+from .generic import _unwrap, _wrap_periods
+from .units import threshold_in_units_of
+
+
+def _mask_missing(out, valid, poff):
+    n = torch.from_numpy(np.diff(poff).astype(np.int32)).to(out.device)[:, None]
+    res = out.to(torch.float64) if out.dtype in (torch.int32, torch.int64) else out.clone()
+    res[valid != n] = float("nan")
+    return res
+
+
+def maximum_consecutive_dry_days(pr, thresh="1 mm/day", freq="YS", resample_before_rl=True):
+    """``xclim.atmos.maximum_consecutive_dry_days`` (identifier ``cdd``, indicators/atmos/_precip.py:237-247):
+    the index of indices/_threshold.py:2895-2937 with periods holding a missing day set to NaN."""
+    thr = threshold_in_units_of(thresh, pr)
+    x2d, cell_shape, other, ta = _unwrap(pr)
+    poff = ta.period_offsets(freq)
+    out, valid = device.period_runstat(x2d, poff, _lib.OPS["<"], thr, _lib.RL_REDUCERS["max"], 1, resample_before_rl,
+                                       want_valid=True)
+    attrs = attrs_of(pr)
+    attrs.update(units="days", standard_name="number_of_days_with_lwe_thickness_of_precipitation_amount_below_threshold",
+                 cell_methods="time: maximum over days")
+    return _wrap_periods(pr, _mask_missing(out, valid, poff), cell_shape, other, ta, freq, attrs, dtype=np.float32,
+                         name="cdd")
+
+
+def tg_mean(tas, freq="YS"):
+    """``xclim.atmos.tg_mean`` (indicators/atmos/_temperature.py:475-485)."""
+    x2d, cell_shape, other, ta = _unwrap(tas)
+    poff = ta.period_offsets(freq)
+    out, valid = device.period_reduce(x2d, poff, _lib.STATS["mean"], want_valid=True)
+    attrs = attrs_of(tas)
+    attrs.update(cell_methods="time: mean over days")
+    return _wrap_periods(tas, _mask_missing(out, valid, poff), cell_shape, other, ta, freq, attrs, name="tg_mean")
+
+
+def tx90p(tasmax, tasmax_per, freq="YS", bootstrap=False, op=">"):
+    """``xclim.atmos.tx90p`` (indicators/atmos/_temperature.py:1269-1281): counts become float with NaN
+    where the period has a missing day."""
+    from .indices import tx90p as index_tx90p
+    if bootstrap:
+        out = index_tx90p(tasmax, tasmax_per, freq=freq, bootstrap=True, op=op)
+        x2d, cell_shape, other, ta = _unwrap(tasmax)
+        poff = ta.period_offsets(freq)
+        _, valid = device.period_count(x2d, poff, _lib.OP_NOTNAN, 0.0, want_valid=True)
+        vals = torch.from_numpy(np.asarray(out.values, dtype=np.float64)).reshape(len(poff) - 1, -1).to(x2d.device)
+        masked = _mask_missing(vals, valid, poff)
+        attrs = attrs_of(out)
+        attrs["units"] = "days"
+        return _wrap_periods(tasmax, masked, cell_shape, other, ta, freq, attrs, dtype=np.float64, name="tx90p")
+    code = _lib.op_code(op, (">", ">="))
+    x2d, cell_shape, other, ta = _unwrap(tasmax)
+    poff = ta.period_offsets(freq)
+    table = table_on_device(tasmax_per, cell_shape, other, x2d.device)
+    table, doy_idx = adjust_table(table, ta)
+    cnt, valid = device.doy_threshold_count(x2d, poff, doy_idx, table, code, want_valid=True)
+    attrs = attrs_of(tasmax)
+    attrs.update(units="days", cell_methods="time: sum over days")
+    return _wrap_periods(tasmax, _mask_missing(cnt, valid, poff), cell_shape, other, ta, freq, attrs, dtype=np.float64,
+                         name="tx90p")
