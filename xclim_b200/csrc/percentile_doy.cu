@@ -87,6 +87,76 @@ percentile_doy_generic_kernel(const float* __restrict__ x, int64_t T, int64_t C,
   }
 }
 
+#ifndef XC_PCTL_VARIANT
+#define XC_PCTL_VARIANT 0
+#endif
+#ifndef XC_PCTL_ADDR      // 0: running 64-bit pointer (2 ALU-pipe adds per load); 1: one IMAD.WIDE (FMA pipe)
+#define XC_PCTL_ADDR (XC_PCTL_VARIANT == 1 ? 1 : 0)
+#endif
+#ifndef XC_PCTL_PROBE     // NaN probe: 0 = compare chain (ALU pipe); 1 = FMA chain; 2 = FADD tree + 1 compare per 4
+#define XC_PCTL_PROBE (XC_PCTL_VARIANT == 1 ? 1 : 0)
+#endif
+
+// NV rows p0 + k*ystride -> v[0..NV) (negated for a bottom-side quantile), pads -inf, NaN -> -inf
+// (never selected; nv counts the valid ones), then sorted descending.
+template <int K, int NV>
+__device__ __forceinline__ void load_sort_chunk(const char* p0, uint64_t ystride, bool top, float (&v)[K],
+                                                int& nv) {
+#if XC_PCTL_ADDR == 1
+  const uint32_t ys32 = (uint32_t)ystride;
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+    v[k] = ld_stream(reinterpret_cast<const float*>(p0 + (uint64_t)((uint32_t)k) * (uint64_t)ys32));
+#else
+  const char* pp = p0;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    v[k] = ld_stream(reinterpret_cast<const float*>(pp));
+    pp += ystride;
+  }
+#endif
+#pragma unroll
+  for (int k = NV; k < K; ++k) v[k] = XC_NEG_INF;
+  if (!top) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = -v[k];
+  }
+  // NaN handling off the fast path: only a lane that may hold a NaN looks at each value
+#if XC_PCTL_PROBE == 1
+  float probe = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) probe = __fmaf_rn(v[k], 0.f, probe);
+  const bool suspicious = (probe != probe);
+#elif XC_PCTL_PROBE == 2
+  // sums of four on the FMA pipe: NaN iff a NaN (or +inf and -inf) is among them
+  bool suspicious = false;
+#pragma unroll
+  for (int k = 0; k < NV; k += 4) {
+    float a = v[k];
+    if (k + 1 < NV) a = __fadd_rn(a, v[k + 1]);
+    float b = (k + 2 < NV) ? v[k + 2] : 0.f;
+    if (k + 3 < NV) b = __fadd_rn(b, v[k + 3]);
+    const float q = __fadd_rn(a, b);
+    suspicious = suspicious || (q != q);
+  }
+#else
+  bool suspicious = false;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) suspicious = suspicious || (v[k] != v[k]);
+#endif
+  nv = NV;
+  if (suspicious) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const bool bad = (v[k] != v[k]);
+      nv -= bad ? 1 : 0;
+      v[k] = bad ? XC_NEG_INF : v[k];
+    }
+  }
+  if constexpr (NV == K) sort_desc<K>(v);
+  else sort_desc_first<K, NV>(v);
+}
+
 // ------------------------------------------------------------------------------------------------
 // fast kernel: uniform year length L == n_doy, T == N*L, series starts on doy 1
 // ------------------------------------------------------------------------------------------------
@@ -133,81 +203,38 @@ __device__ __forceinline__ void load_day_list(const float* __restrict__ x, int64
   // rows y*L + e that exist: e < 0 reaches into the previous year (no year -1), e >= L into the next
   const int ylo = (e < 0) ? 1 : 0;
   const int yhi = (e >= L) ? N - 1 : N;
+  const uint64_t ystride = (uint64_t)L * (uint64_t)ldx * 4ull;
+  const bool narrow = (ystride >> 32) == 0;
   bool first = true;
   for (int y0 = 0; y0 < N; y0 += K) {
     float v[K];
-    // byte address of (row (y0+k)*L + e, cell c) = p0 + k * ystride: when the year stride fits 32 bits
-    // (it does for any grid below 4 GiB per year) this is ONE 32x32+64 multiply-add per load on the
-    // FMA pipe, leaving the ALU pipe to the min/max network
-    const char* p0 = reinterpret_cast<const char*>(x + ((int64_t)y0 * L + e) * ldx + c);
-    const uint64_t ystride = (uint64_t)L * (uint64_t)ldx * 4ull;
-    const uint32_t ys32 = (uint32_t)ystride;
-    const bool narrow = (ystride >> 32) == 0;
     int nv;
-#ifndef XC_PCTL_VARIANT
-#define XC_PCTL_VARIANT 0
-#endif
-    if (y0 >= ylo && y0 + K <= yhi && narrow) {  // whole chunk in range (the common case)
-#if XC_PCTL_VARIANT == 1
-#pragma unroll
-      for (int k = 0; k < K; ++k)
-        v[k] = ld_stream(reinterpret_cast<const float*>(p0 + (uint64_t)((uint32_t)k) * (uint64_t)ys32));
-#else
-      const char* pp = p0;
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        v[k] = ld_stream(reinterpret_cast<const float*>(pp));
-        pp += ystride;
-      }
-#endif
-      nv = K;
+    // byte address of (row (y0+k)*L + e, cell c) = p0 + k * ystride
+    const char* p0 = reinterpret_cast<const char*>(x + ((int64_t)y0 * L + e) * ldx + c);
+    const int tail = N - y0;  // warp-uniform
+    const bool inside = narrow && (y0 >= ylo) && ((tail >= K ? y0 + K : N) <= yhi);
+    // The last chunk of e.g. a 30-year base holds 14 values + 2 pads (-inf, already at the bottom):
+    // its loads are unconditional and comparators touching the padded wires are left out.
+    if (inside && tail >= K) {
+      load_sort_chunk<K, K>(p0, ystride, top, v, nv);
+    } else if (K == 16 && inside && tail == 14) {
+      load_sort_chunk<K, (K == 16 ? 14 : K)>(p0, ystride, top, v, nv);
+    } else if (K == 16 && inside && tail == 15) {
+      load_sort_chunk<K, (K == 16 ? 15 : K)>(p0, ystride, top, v, nv);
     } else {
       nv = 0;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const int y = y0 + k;
         const bool ok = (y >= ylo) && (y < yhi);
-        // rows that do not exist are +/-inf BEFORE the bottom-side negation below turns them into -inf
-        v[k] = ok ? ld_stream(reinterpret_cast<const float*>(p0 + (uint64_t)k * ystride))
-                  : (top ? XC_NEG_INF : -XC_NEG_INF);
-        nv += ok ? 1 : 0;
+        float r = ok ? ld_stream(reinterpret_cast<const float*>(p0 + (uint64_t)k * ystride)) : XC_NEG_INF;
+        const bool good = ok && (r == r);
+        nv += good ? 1 : 0;
+        v[k] = good ? (top ? r : -r) : XC_NEG_INF;
       }
-    }
-    if (!top) {
-#pragma unroll
-      for (int k = 0; k < K; ++k) v[k] = -v[k];
-    }
-    // NaN handling off the fast path: a chain of FMAs (FMA pipe) makes `probe` NaN iff some value is
-    // NaN or infinite; only then does the lane look at each value (NaN -> -inf, never selected)
-#if XC_PCTL_VARIANT == 1
-    float probe = 0.f;
-#pragma unroll
-    for (int k = 0; k < K; ++k) probe = __fmaf_rn(v[k], 0.f, probe);
-    const bool suspicious = (probe != probe);
-#else
-    bool suspicious = false;
-#pragma unroll
-    for (int k = 0; k < K; ++k) suspicious = suspicious || (v[k] != v[k]);
-#endif
-    if (suspicious) {
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const bool bad = (v[k] != v[k]);
-        nv -= bad ? 1 : 0;
-        v[k] = bad ? XC_NEG_INF : v[k];
-      }
-    }
-    n += nv;
-    // the last chunk of e.g. a 30-year base holds 14 values + 2 pads (-inf, already at the bottom):
-    // comparators touching the padded wires are no-ops and are left out (53 instead of 63 for 14 of 16)
-    const int tail = N - y0;  // warp-uniform
-    if constexpr (K == 16) {
-      if (tail == 14) sort_desc_first<16, 14>(v);
-      else if (tail == 15) sort_desc_first<16, 15>(v);
-      else sort_desc<K>(v);
-    } else {
       sort_desc<K>(v);
     }
+    n += nv;
     if (first) {
 #pragma unroll
       for (int k = 0; k < K; ++k) lst[k] = v[k];
@@ -300,6 +327,9 @@ __device__ __forceinline__ float fold_thr(double t) {
 // Ring in shared memory: 3 pair lists per lane, [slot][k][lane].
 #ifndef XC_PCTL_MINBLOCKS
 #define XC_PCTL_MINBLOCKS 7
+#endif
+#ifndef XC_PCTL_PAIR_MINBLOCKS
+#define XC_PCTL_PAIR_MINBLOCKS 6
 #endif
 // COUNT_OP >= 0 fuses the percentile-threshold day count of the SAME series (tx90p with the base period
 // equal to the studied period, sub-case 3a of SURVEY.md section 8d): once P(d) is known the N values
@@ -417,6 +447,108 @@ percentile_doy_w5_kernel(const float* __restrict__ x, int32_t T, int64_t C, int6
       atomicAdd(year_counts + (int64_t)y * C + c, (int)(v & 0xffffu));
       if (year_valid) atomicAdd(year_valid + (int64_t)y * C + c, (int)(v >> 16));
     }
+  }
+}
+
+// Window 5, days handled in PAIRS.  With B(d) = Y(d-2..d+1) = A(d-1) U A(d+1) the windows of two
+// neighbouring days are one rank-only merge away:  S(d-1) = Y(d-3) U B(d)  and  S(d) = B(d) U Y(d+2).
+// Per pair of days: one pair merge A(d+1), one merge B(d), two rank-only finals (2*80 + 2*32
+// min/max) instead of 2*(80 + 80 + 32) for the day-by-day kernel above; the per-day sort of the N
+// values of a day (the larger part of the work) is unchanged.
+// The loop still advances ONE day per iteration (even/odd branch) so that the body holds a single
+// copy of the day-list sort and of the final merge: two inlined copies overflow the 32 KB
+// instruction cache and cost more than the saved merges (measured: 17.1 ms vs 15.5 ms).
+// Shared memory per lane: A(d-1), the two most recent odd-position day lists Y(d-3), Y(d-1), and
+// the even-position list Y(d) waiting for its partner.
+template <int K, bool TABLE>
+__global__ void __launch_bounds__(kThreads, XC_PCTL_PAIR_MINBLOCKS)
+percentile_doy_w5p_kernel(const float* __restrict__ x, int32_t T, int64_t C, int64_t ldx, int32_t L, int32_t N,
+                          QuantSpec spec, int32_t doys_per_chunk, double* __restrict__ out,
+                          const int32_t* __restrict__ pos, int32_t n_doy, int32_t d_begin, int32_t d_end) {
+  extern __shared__ float smem[];
+  float* sA = smem;                                                    // [K][kThreads]
+  float* sY = smem + (size_t)K * kThreads;                             // [2][K][kThreads]
+  float* sE = smem + (size_t)3 * K * kThreads;                         // [K][kThreads]
+  int* sn = reinterpret_cast<int*>(smem + (size_t)4 * K * kThreads);   // [4][kThreads]: n(A), n(Y0), n(Y1), n(E)
+  const int lane = threadIdx.x;
+  const int64_t c = (int64_t)blockIdx.x * kThreads + lane;
+  if (c >= C) return;
+  const int p0 = d_begin + blockIdx.y * doys_per_chunk;
+  const int p1 = min(d_end, p0 + doys_per_chunk);
+  if (p0 >= p1) return;
+  const bool top = spec.top != 0;
+
+  auto store_list = [&](float* dst, const float (&a)[K]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) dst[(size_t)k * kThreads + lane] = a[k];
+  };
+
+  float t[K], ynew[K], o[K];
+  int nnew, nB = 0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) t[k] = 0.f;
+  // The four warm-up iterations day = p0-4 .. p0-1 run the steady-state code without emitting:
+  // they leave Y(p0-2), Y(p0) in the two odd slots, A(p0) = Y(p0-1) U Y(p0) in sA and Y(p0+1) in sE
+  // (what they compute from the not-yet-written lists is overwritten before it is used).  No
+  // separate prologue means one copy of the day-list sort in the whole kernel.
+  int s = 0;  // slot of Y(d-3)
+#pragma unroll 1
+  for (int day = p0 - 4; day < p1; ++day) {
+    load_day_list<K, TABLE>(x, c, ldx, T, L, N, day + 2, top, ynew, nnew, pos, n_doy);
+    int n;
+    if (((day - p0) & 1) == 0) {
+      // first day of the pair (day = d-1): ynew = Y(d+1)
+#pragma unroll
+      for (int k = 0; k < K; ++k) o[k] = fmaxf(sE[(size_t)k * kThreads + lane], ynew[K - 1 - k]);
+      bitonic_finish_desc<K>(o);       // o <- A(d+1)
+      const int nA1 = sn[3 * kThreads + lane] + nnew;
+#pragma unroll
+      for (int k = 0; k < K; ++k) t[k] = fmaxf(sA[(size_t)k * kThreads + lane], o[K - 1 - k]);
+      bitonic_finish_desc<K>(t);       // t <- B(d)
+      nB = sn[lane] + nA1;
+      store_list(sA, o);
+      sn[lane] = nA1;
+      float* slot = sY + (size_t)s * K * kThreads;
+#pragma unroll
+      for (int k = 0; k < K; ++k) o[k] = slot[(size_t)k * kThreads + lane];   // Y(d-3)
+      n = nB + sn[(1 + s) * kThreads + lane];
+      store_list(slot, ynew);          // Y(d+1) replaces Y(d-3)
+      sn[(1 + s) * kThreads + lane] = nnew;
+      s ^= 1;
+    } else {
+      // second day of the pair (day = d): ynew = Y(d+2), the even-position list of the next pair
+      store_list(sE, ynew);
+      sn[3 * kThreads + lane] = nnew;
+#pragma unroll
+      for (int k = 0; k < K; ++k) o[k] = ynew[k];
+      n = nB + nnew;
+    }
+    if (day < p0) continue;
+    // quantile of (t U o), both sorted descending, n valid values in the window
+    float u[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) u[k] = fmaxf(t[k], o[K - 1 - k]);
+    const QuantIdx qi = quant_index(n, spec);
+    const bool in_range = (n >= 2) && (qi.vi < (double)n - 1.0) && (qi.vi >= 0.0);
+    const bool fast = in_range && (top ? (n - 1 - qi.ilo == K - 1) : (qi.ilo + 1 == K - 1));
+    double res;
+    if (__all_sync(__activemask(), fast)) {
+      // only the two smallest of the bitonic top-K are needed
+      float m[K / 2];
+#pragma unroll
+      for (int i = 0; i < K / 2; ++i) m[i] = fminf(u[i], u[i + K / 2]);
+#pragma unroll
+      for (int h = K / 4; h >= 2; h >>= 1) {
+#pragma unroll
+        for (int i = 0; i < h; ++i) m[i] = fminf(m[i], m[i + h]);
+      }
+      const float smallest = fminf(m[0], m[1]), second = fmaxf(m[0], m[1]);
+      res = top ? quant_lerp(smallest, second, qi) : quant_lerp(-second, -smallest, qi);
+    } else {
+      bitonic_finish_desc<K>(u);
+      res = finalize_quantile<K>(u, n, spec);
+    }
+    out[(int64_t)day * C + c] = res;
   }
 }
 
@@ -651,17 +783,18 @@ int32_t launch_w5(const float* x, int64_t T, int64_t C, int64_t ldx, int32_t L, 
   chunks = chunks < 1 ? 1 : chunks;
   int per = (nd + chunks - 1) / chunks;
   if (per < 40) per = 40;  // 4 extra day lists per chunk
+  per = (per + 1) & ~1;    // whole pairs of days
   if (per > nd) per = nd;
   chunks = (nd + per - 1) / per;
-  const size_t smem = (size_t)3 * (K + 1) * kThreads * 4;
+  const size_t smem = (size_t)4 * (K + 1) * kThreads * 4;
   dim3 grid((unsigned)cblocks, (unsigned)chunks, 1);
   if (pos)
-    percentile_doy_w5_kernel<K, true><<<grid, kThreads, smem, st>>>(x, (int32_t)T, C, ldx, L, N, spec, per, out, pos,
-                                                                    n_doy, d_begin, d_end);
-  else
-    percentile_doy_w5_kernel<K, false><<<grid, kThreads, smem, st>>>(x, (int32_t)T, C, ldx, L, N, spec, per, out, pos,
+    percentile_doy_w5p_kernel<K, true><<<grid, kThreads, smem, st>>>(x, (int32_t)T, C, ldx, L, N, spec, per, out, pos,
                                                                      n_doy, d_begin, d_end);
-  return launch_status("percentile_doy_w5_kernel");
+  else
+    percentile_doy_w5p_kernel<K, false><<<grid, kThreads, smem, st>>>(x, (int32_t)T, C, ldx, L, N, spec, per, out,
+                                                                      pos, n_doy, d_begin, d_end);
+  return launch_status("percentile_doy_w5p_kernel");
 }
 
 }  // namespace
