@@ -204,6 +204,15 @@ int32_t xc_spell_runstat_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
                              int32_t window, int32_t window_stat, int32_t op, double thr,
                              int32_t reducer, int32_t resample_before_rl, float* out, void* stream);
 
+/* Host-side helper of the entry point above (no device work; exported so that it can be tested
+ * without a GPU): for sum / mean windows the kernels compare the float64 window SUM s instead of
+ * the float32 statistic r(s) = (float)(s) or (float)(s / window).  r is monotone in s, hence
+ *   r(s) op (float)thr   <=>   ((s >= lo) && (hi_unbounded || s < hi)) != negate
+ * for the interval this function finds by bisection over the ordered doubles (window_stat is
+ * XC_STAT_SUM or XC_STAT_MEAN).  out4 = {hi_unbounded, negate, value of (NaN op thr), 0}. */
+int32_t xc_spell_sum_interval(int32_t op, double thr, int32_t window, int32_t window_stat,
+                              double* lo, double* hi, int32_t* out4);
+
 /* ---------------------------------------------------------------------------------------------
  * a14+a15  percentile_doy -- core/calendar.py:395-494 with the quantile of
  *   core/utils.py:279-557 (`calc_perc` -> `_nan_quantile`, Hyndman-Fan alpha/beta).

@@ -18,11 +18,13 @@ def _pr(rng, T, shape, nan_frac=0.01):
 
 @pytest.mark.parametrize("window,center,wop,op", [(3, False, "sum", "max"), (5, True, "mean", "max"),
                                                   (14, False, "mean", "min"), (7, True, "max", "mean"),
-                                                  (2, False, "min", "sum")])
-def test_rolling_resample(cuda, window, center, wop, op):
+                                                  (2, False, "min", "sum"), (31, True, "sum", "std"),
+                                                  (1, False, "sum", "max")])
+@pytest.mark.parametrize("shape", [(5, 6), (4, 6)])   # 30 cells: lane-per-cell kernel; 24: streaming 4-cell kernel
+def test_rolling_resample(cuda, window, center, wop, op, shape):
     from xclim_b200 import generic
     rng = np.random.default_rng(41)
-    x = _pr(rng, 800, (5, 6))
+    x = _pr(rng, 800, shape)
     da = make_field(x, "2000-01-01", units="mm/d")
     for freq in ("YS", "MS"):
         got = generic.select_rolling_resample_op(da, op, window, window_center=center, window_op=wop, freq=freq)
@@ -47,12 +49,14 @@ def test_rolling_reference_known_answers(cuda):
 
 
 @pytest.mark.parametrize("window,winred,op,thr", [(3, "min", ">=", 1.0), (3, "max", "<", 1.0), (5, "sum", "<", 3.0),
-                                                  (2, "mean", ">=", 2.0), (7, "sum", ">=", 20.0)])
+                                                  (2, "mean", ">=", 2.0), (7, "sum", ">=", 20.0),
+                                                  (30, "sum", "<", 40.0), (4, "max", ">", 6.0)])
 @pytest.mark.parametrize("before", [True, False])
-def test_spell_length_statistics_windows(cuda, window, winred, op, thr, before):
+@pytest.mark.parametrize("shape", [(4, 5), (3, 5)])   # 20 cells: streaming 4-cell kernel; 15: lane-per-cell
+def test_spell_length_statistics_windows(cuda, window, winred, op, thr, before, shape):
     from xclim_b200 import generic
     rng = np.random.default_rng(42)
-    x = _pr(rng, 365 * 2 + 60, (4, 5))
+    x = _pr(rng, 365 * 2 + 60, shape)
     da = make_field(x, "2001-01-01", units="mm/d")
     for freq in ("YS", "MS"):
         poff = da.time.period_offsets(freq)

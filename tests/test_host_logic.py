@@ -67,3 +67,47 @@ def test_no_cuda_means_loud_failure():
     f = Field(np.zeros((365, 2), np.float32), ("time", "x"), TimeAxis.daily("2001-01-01", 365), attrs={"units": "mm/d"})
     with pytest.raises(_lib.XclimB200Error):
         indices.maximum_consecutive_dry_days(f)
+
+
+def test_spell_sum_interval_matches_float32_compare():
+    """xc_spell_sum_interval (host helper of xc_spell_runstat_f32): the float64-sum interval must
+    reproduce `np.float32(s [/ w]) op np.float32(thr)` for every double s, including the doubles
+    right next to the rounding boundaries."""
+    import ctypes as C
+    from xclim_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    ops = {">": np.greater, "<": np.less, ">=": np.greater_equal, "<=": np.less_equal, "==": np.equal,
+           "!=": np.not_equal}
+    for thr in (1.0, 0.0, 3.3, -5.5, 1e-30, float("inf"), 16777216.0):
+        for w in (2, 3, 7):
+            for stat in ("sum", "mean"):
+                t32 = np.float32(thr)
+                centre = float(t32) * (w if stat == "mean" else 1)
+                near = np.nextafter(centre, np.inf) if np.isfinite(centre) else centre
+                s = [centre, near]
+                x = centre
+                for _ in range(40):                      # 40 doubles either side of the centre
+                    x = np.nextafter(x, -np.inf)
+                    s.append(x)
+                x = centre
+                for _ in range(40):
+                    x = np.nextafter(x, np.inf)
+                    s.append(x)
+                if np.isfinite(centre):                  # the float32 neighbours' midpoints
+                    for nb in (np.nextafter(t32, np.float32(-np.inf)), np.nextafter(t32, np.float32(np.inf))):
+                        mid = (float(nb) + float(t32)) / 2 * (w if stat == "mean" else 1)
+                        s += [mid, np.nextafter(mid, np.inf), np.nextafter(mid, -np.inf)]
+                s += list(rng.standard_normal(200) * 10.0) + [np.inf, -np.inf, 0.0, -0.0]
+                s = np.asarray(s, dtype=np.float64)
+                with np.errstate(all="ignore"):
+                    r = (s / w if stat == "mean" else s).astype(np.float32)
+                for name, fn in ops.items():
+                    lo, hi = C.c_double(), C.c_double()
+                    flags = (C.c_int32 * 4)()
+                    _lib.check(lib.xc_spell_sum_interval(_lib.op_code(name), float(thr), w, _lib.STATS[stat],
+                                                         C.byref(lo), C.byref(hi), flags))
+                    with np.errstate(invalid="ignore"):
+                        got = ((s >= lo.value) & (bool(flags[0]) | (s < hi.value))) != bool(flags[1])
+                    np.testing.assert_array_equal(got, fn(r, t32), err_msg=f"{thr} {w} {stat} {name}")
+                    assert bool(flags[2]) == (name == "!=")

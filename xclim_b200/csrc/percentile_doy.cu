@@ -93,6 +93,9 @@ percentile_doy_generic_kernel(const float* __restrict__ x, int64_t T, int64_t C,
 #ifndef XC_PCTL_ADDR      // 0: running 64-bit pointer (2 ALU-pipe adds per load); 1: one IMAD.WIDE (FMA pipe)
 #define XC_PCTL_ADDR (XC_PCTL_VARIANT == 1 ? 1 : 0)
 #endif
+#ifndef XC_PCTL_PREFETCH  // 1: L2 prefetch of the next day's rows (measured SLOWER: 16.1 vs 13.7 ms; off)
+#define XC_PCTL_PREFETCH 0
+#endif
 #ifndef XC_PCTL_PROBE     // NaN probe: 0 = compare chain (ALU pipe); 1 = FMA chain; 2 = FADD tree + 1 compare per 4
 #define XC_PCTL_PROBE (XC_PCTL_VARIANT == 1 ? 1 : 0)
 #endif
@@ -101,7 +104,7 @@ percentile_doy_generic_kernel(const float* __restrict__ x, int64_t T, int64_t C,
 // (never selected; nv counts the valid ones), then sorted descending.
 template <int K, int NV>
 __device__ __forceinline__ void load_sort_chunk(const char* p0, uint64_t ystride, bool top, float (&v)[K],
-                                                int& nv) {
+                                                int& nv, int64_t next_day_bytes) {
 #if XC_PCTL_ADDR == 1
   const uint32_t ys32 = (uint32_t)ystride;
 #pragma unroll
@@ -113,6 +116,17 @@ __device__ __forceinline__ void load_sort_chunk(const char* p0, uint64_t ystride
   for (int k = 0; k < NV; ++k) {
     v[k] = ld_stream(reinterpret_cast<const float*>(pp));
     pp += ystride;
+  }
+#endif
+#if XC_PCTL_PREFETCH
+  // the same rows of the NEXT day go to L2 now, so that the next iteration's loads see L2 latency
+  if (next_day_bytes != 0) {
+    const char* pf = p0 + next_day_bytes;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+      pf += ystride;
+    }
   }
 #endif
 #pragma unroll
@@ -215,12 +229,14 @@ __device__ __forceinline__ void load_day_list(const float* __restrict__ x, int64
     const bool inside = narrow && (y0 >= ylo) && ((tail >= K ? y0 + K : N) <= yhi);
     // The last chunk of e.g. a 30-year base holds 14 values + 2 pads (-inf, already at the bottom):
     // its loads are unconditional and comparators touching the padded wires are left out.
+    // next day's rows exist for the same years when e+1 is still inside the year
+    const int64_t nd = (e >= 0 && e + 1 < L) ? ldx * 4 : 0;
     if (inside && tail >= K) {
-      load_sort_chunk<K, K>(p0, ystride, top, v, nv);
+      load_sort_chunk<K, K>(p0, ystride, top, v, nv, nd);
     } else if (K == 16 && inside && tail == 14) {
-      load_sort_chunk<K, (K == 16 ? 14 : K)>(p0, ystride, top, v, nv);
+      load_sort_chunk<K, (K == 16 ? 14 : K)>(p0, ystride, top, v, nv, nd);
     } else if (K == 16 && inside && tail == 15) {
-      load_sort_chunk<K, (K == 16 ? 15 : K)>(p0, ystride, top, v, nv);
+      load_sort_chunk<K, (K == 16 ? 15 : K)>(p0, ystride, top, v, nv, nd);
     } else {
       nv = 0;
 #pragma unroll
