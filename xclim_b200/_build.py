@@ -68,8 +68,12 @@ def build_variant(tag: str, defines: list[str]) -> str:
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
     os.makedirs(LIB_DIR, exist_ok=True)
-    nvcc = _nvcc()
     hdr_m = _deps_mtime()
+    # a library newer than every source and header is current even when the objects did not travel
+    if not force and os.path.exists(LIB_PATH) and \
+            os.path.getmtime(LIB_PATH) >= max([hdr_m] + [os.path.getmtime(s) for s in sources()]):
+        return LIB_PATH
+    nvcc = _nvcc()
     jobs = []
     objs = []
     for src in sources():
