@@ -236,6 +236,18 @@ int32_t xc_percentile_doy_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
                               double alpha, double beta,
                               double* out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The same with a virtual-row map (bootstrap on calendars with leap years, core/bootstrapping.py:
+ * 235-282): the series keeps its time axis (doy / year labels) but the VALUE of step t is read
+ * from row vrow_host[t] (HOST int32[T]; -1 = missing, i.e. NaN).  Replacing the block of one year
+ * by the (calendar-converted) block of another year is such a map, so no copy of the input is
+ * made.  Workspace: xc_percentile_doy_workspace_bytes. */
+int32_t xc_percentile_doy_vrow_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                   const int16_t* doy_index_host, const int16_t* year_index_host,
+                                   const int32_t* vrow_host, int32_t n_doy, int32_t n_years,
+                                   int32_t window, const double* percentiles_host, int32_t n_per,
+                                   double alpha, double beta, double* out, void* workspace,
+                                   int64_t workspace_bytes, void* stream);
+
 /* Test hook: same contract as xc_percentile_doy_f32 for ONE percentile, but always through the
  * generic (any-calendar) kernel, so the fast uniform-year kernel can be checked against it. */
 int32_t xc_percentile_doy_generic_f32(const float* x, int64_t T, int64_t C, int64_t ldx,

@@ -546,15 +546,16 @@ def doy_threshold_count(x, table, doy, poff, op=">", cal_max_doy=None):
 # a17 percentile bootstrap (core/bootstrapping.py:128-211, 235-282)
 # --------------------------------------------------------------------------------------------------
 def bootstrap_doy_count(x, year, doy, poff, base_years, window=5, per=90.0, alpha=1 / 3., beta=1 / 3.,
-                        op=">", table=None, cal_max_doy=None):
+                        op=">", table=None, cal_max_doy=None, feb29_index=59):
     """Zhang-2005 bootstrap of a doy-percentile exceedance count.
 
     ``poff`` groups must nest inside calendar years (freq YS/MS/QS...).  ``base_years`` =
     (first, last) year of the climatology.  For periods of in-base year y the result is the mean
     over the other base years s of the count obtained with thresholds computed on the base series
     in which block y is replaced by block s (core/bootstrapping.py:182-203); other periods use the
-    plain table (:205-207).  Equal-length year blocks only (:264-265) -- i.e. noleap/360_day, or
-    standard-calendar cases where lengths agree; 365<->366 conversion (:266-269) is not restated.
+    plain table (:205-207).  Blocks of unequal length follow :255-279 (365 <-> 366 through
+    ``convert_calendar``: Feb 29, at ``feb29_index`` of a year starting on 1 January, is dropped or
+    filled with NaN).
     Returns float64 ``(P, ...)``.
     """
     x = np.asarray(x)
@@ -584,10 +585,20 @@ def bootstrap_doy_count(x, year, doy, poff, base_years, window=5, per=90.0, alph
                 if s == y:
                     continue
                 pos_s = np.nonzero(yb == s)[0]
-                if len(pos_s) != len(pos_y):
-                    raise NotImplementedError("unequal year blocks")
                 z = xb.copy()
-                z[pos_y] = xb[pos_s]
+                ly, ls = len(pos_y), len(pos_s)
+                if ls < 360 and ls < ly:                                 # :257-260 block left untouched
+                    pass
+                elif ls == ly:                                           # :264-265
+                    z[pos_y] = xb[pos_s]
+                elif ly == 365 and ls == 366:                            # :266-267 convert_calendar("noleap")
+                    z[pos_y] = np.delete(xb[pos_s], feb29_index, axis=0)  # drops Feb 29
+                elif ly == 366 and ls == 365:                            # :268-269 convert_calendar("366_day",
+                    z[pos_y] = np.insert(xb[pos_s], feb29_index, np.nan, axis=0)  # missing=NaN): NaN on Feb 29
+                elif ly < 365 and ls >= ly:                              # :270-273
+                    z[pos_y] = xb[pos_s][:ly]
+                else:
+                    raise NotImplementedError("unequal year blocks")
                 tab = percentile_doy(z, yb, db, window, per, alpha, beta)[:, 0]
                 acc.append(threshold_count(blk, op, resample_doy(tab, dblk, cal_max_doy), [0, e_ - s_])[0])
             out.append(np.mean(np.stack(acc, axis=0), axis=0))

@@ -111,3 +111,23 @@ def test_spell_sum_interval_matches_float32_compare():
                         got = ((s >= lo.value) & (bool(flags[0]) | (s < hi.value))) != bool(flags[1])
                     np.testing.assert_array_equal(got, fn(r, t32), err_msg=f"{thr} {w} {stat} {name}")
                     assert bool(flags[2]) == (name == "!=")
+
+
+def test_bootstrap_replacement_rows_calendar_conversion():
+    """core/bootstrapping.py:255-279 as a row map: equal blocks copy, 365 <- 366 drops the source's
+    Feb 29, 366 <- 365 leaves a hole (-1 = NaN) on the target's Feb 29."""
+    from xb_helpers import make_field
+    from xclim_b200.bootstrapping import replacement_rows
+    T = 366 + 365 * 3 + 366
+    da = make_field(np.zeros((T, 1), np.float32), "2000-01-01", calendar="standard", units="K")
+    ta = da.time
+    gid = ta.bootstrap_group_ids("YS")
+    _, starts, lens = np.unique(gid, return_index=True, return_counts=True)
+    assert lens.tolist() == [366, 365, 365, 365, 366]
+    r = replacement_rows(ta, starts, lens, 1, 2)
+    np.testing.assert_array_equal(r, starts[2] + np.arange(365))
+    r = replacement_rows(ta, starts, lens, 1, 4)               # common year <- leap year
+    assert len(r) == 365 and (starts[4] + 59) not in r and r[58] == starts[4] + 58 and r[59] == starts[4] + 60
+    r = replacement_rows(ta, starts, lens, 0, 2)               # leap year <- common year
+    assert len(r) == 366 and r[59] == -1 and r[58] == starts[2] + 58 and r[60] == starts[2] + 59
+    assert ta.month[starts[0] + 59] == 2 and ta.day[starts[0] + 59] == 29

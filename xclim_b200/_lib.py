@@ -43,6 +43,8 @@ SIGNATURES = {
     "xc_percentile_doy_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32, _i32, _i32]),
     "xc_percentile_doy_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _f64, _f64,
                                      _vp, _vp, _i64, _vp]),
+    "xc_percentile_doy_vrow_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _f64,
+                                          _f64, _vp, _vp, _i64, _vp]),
     "xc_percentile_doy_generic_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _f64, _f64, _f64,
                                              _vp, _vp, _i64, _vp]),
     "xc_doy_interp_f64": (_i32, [_vp, _i32, _i64, _i32, _i32, _vp, _vp]),

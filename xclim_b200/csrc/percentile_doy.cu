@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kThreads)
 percentile_doy_generic_kernel(const float* __restrict__ x, int64_t T, int64_t C, int64_t ldx,
                               const int32_t* __restrict__ pos, int32_t n_doy, int32_t n_years, int32_t h,
                               QuantSpec spec, int32_t doys_per_chunk, double* __restrict__ out,
-                              int32_t d_begin, int32_t d_end) {
+                              int32_t d_begin, int32_t d_end, const int32_t* __restrict__ vrow) {
   const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (c >= C) return;
   const int d0 = d_begin + blockIdx.y * doys_per_chunk;
@@ -79,7 +79,10 @@ percentile_doy_generic_kernel(const float* __restrict__ x, int64_t T, int64_t C,
       if (i < 0) continue;
       const int j0 = max(0, i - h), j1 = min((int)T - 1, i + h);
       for (int j = j0; j <= j1; ++j) {
-        const float v = prep(__ldg(col + (int64_t)j * ldx), top, n);
+        // vrow: the row holding the value of (virtual) step j, -1 = missing (bootstrap replacements)
+        const int row = vrow ? vrow[j] : j;
+        if (row < 0) continue;
+        const float v = prep(__ldg(col + (int64_t)row * ldx), top, n);
         insert_desc<K>(lst, v);
       }
     }
@@ -738,7 +741,7 @@ doy_count_years_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int6
 template <int K>
 int32_t launch_generic(const float* x, int64_t T, int64_t C, int64_t ldx, const int32_t* pos, int32_t n_doy,
                        int32_t n_years, int32_t h, const QuantSpec& spec, double* out, cudaStream_t st,
-                       int d_begin = 0, int d_end = -1) {
+                       int d_begin = 0, int d_end = -1, const int32_t* vrow = nullptr) {
   if (d_end < 0) d_end = n_doy;
   const int nd = d_end - d_begin;
   if (nd <= 0) return XC_OK;
@@ -750,7 +753,7 @@ int32_t launch_generic(const float* x, int64_t T, int64_t C, int64_t ldx, const 
   chunks = (nd + per - 1) / per;
   dim3 grid((unsigned)cblocks, (unsigned)chunks, 1);
   percentile_doy_generic_kernel<K><<<grid, kThreads, 0, st>>>(x, T, C, ldx, pos, n_doy, n_years, h, spec, per, out,
-                                                              d_begin, d_end);
+                                                              d_begin, d_end, vrow);
   return launch_status("percentile_doy_generic_kernel");
 }
 
@@ -820,15 +823,17 @@ using namespace xc;
 
 extern "C" int64_t xc_percentile_doy_workspace_bytes(int64_t T, int64_t C, int32_t n_doy, int32_t n_years,
                                                      int32_t window, int32_t n_per) {
-  (void)T; (void)C; (void)window; (void)n_per;
-  return (int64_t)n_doy * (int64_t)n_years * 4 + 256;
+  (void)C; (void)window; (void)n_per;
+  // (year, doy) -> step table, the same table through the virtual-row map, and the map itself
+  return 2 * (int64_t)n_doy * (int64_t)n_years * 4 + T * 4 + 256;
 }
 
-extern "C" int32_t xc_percentile_doy_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
-                                         const int16_t* doy_index_host, const int16_t* year_index_host,
-                                         int32_t n_doy, int32_t n_years, int32_t window,
-                                         const double* percentiles_host, int32_t n_per, double alpha, double beta,
-                                         double* out, void* workspace, int64_t workspace_bytes, void* stream) {
+static int32_t percentile_doy_impl(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                   const int16_t* doy_index_host, const int16_t* year_index_host,
+                                   int32_t n_doy, int32_t n_years, int32_t window,
+                                   const double* percentiles_host, int32_t n_per, double alpha, double beta,
+                                   double* out, void* workspace, int64_t workspace_bytes, void* stream,
+                                   const int32_t* vrow_host) {
   XC_REQUIRE(x && doy_index_host && year_index_host && percentiles_host && out, "null pointer argument");
   XC_REQUIRE(T > 0 && C > 0 && ldx >= C && T < 2147483647LL, "bad shape");
   XC_REQUIRE(n_doy > 0 && n_doy <= 366 && n_years > 0 && n_per > 0, "bad calendar description");
@@ -849,13 +854,29 @@ extern "C" int32_t xc_percentile_doy_f32(const float* x, int64_t T, int64_t C, i
     pos[(size_t)y * n_doy + (d - 1)] = (int32_t)t;
     if (uniform && (d - 1 != (int)(t % n_doy) || y != (int)(t / n_doy))) uniform = false;
   }
-  int32_t* pos_d = nullptr;
+  int32_t* pos_d = nullptr;      // (year, doy) -> step
+  int32_t* posrow_d = nullptr;   // (year, doy) -> row holding that step's value (== pos_d without vrow)
+  int32_t* vrow_d = nullptr;     // step -> row
+  if (vrow_host) uniform = false;
   if (!uniform) {
-    const int64_t need = (int64_t)pos.size() * 4;
+    const int64_t nb = (int64_t)pos.size() * 4;
+    const int64_t need = vrow_host ? 2 * nb + T * 4 : nb;
     XC_REQUIRE(workspace != nullptr && workspace_bytes >= need, "workspace too small: need %lld bytes", (long long)need);
     pos_d = (int32_t*)workspace;
-    XC_CHECK_CUDA(cudaMemcpyAsync(pos_d, pos.data(), (size_t)need, cudaMemcpyHostToDevice, st));
-    // pos lives on this stack frame: make sure the copy has been issued from pageable memory
+    posrow_d = pos_d;
+    XC_CHECK_CUDA(cudaMemcpyAsync(pos_d, pos.data(), (size_t)nb, cudaMemcpyHostToDevice, st));
+    std::vector<int32_t> posrow;
+    if (vrow_host) {
+      for (int64_t t = 0; t < T; ++t)
+        XC_REQUIRE(vrow_host[t] >= -1 && vrow_host[t] < T, "virtual row out of range at step %lld", (long long)t);
+      posrow.resize(pos.size());
+      for (size_t k = 0; k < pos.size(); ++k) posrow[k] = pos[k] < 0 ? -1 : vrow_host[pos[k]];
+      posrow_d = pos_d + pos.size();
+      vrow_d = posrow_d + pos.size();
+      XC_CHECK_CUDA(cudaMemcpyAsync(posrow_d, posrow.data(), (size_t)nb, cudaMemcpyHostToDevice, st));
+      XC_CHECK_CUDA(cudaMemcpyAsync(vrow_d, vrow_host, (size_t)T * 4, cudaMemcpyHostToDevice, st));
+    }
+    // the tables live on this stack frame: make sure the copies have been issued from pageable memory
     XC_CHECK_CUDA(cudaStreamSynchronize(st));
   }
 
@@ -890,6 +911,7 @@ extern "C" int32_t xc_percentile_doy_f32(const float* x, int64_t T, int64_t C, i
         XC_REQUIRE(workspace != nullptr && workspace_bytes >= nbytes, "workspace too small: need %lld bytes",
                    (long long)nbytes);
         pos_d = (int32_t*)workspace;
+        posrow_d = pos_d;
         XC_CHECK_CUDA(cudaMemcpyAsync(pos_d, pos.data(), (size_t)nbytes, cudaMemcpyHostToDevice, st));
         XC_CHECK_CUDA(cudaStreamSynchronize(st));
       }
@@ -911,19 +933,19 @@ extern "C" int32_t xc_percentile_doy_f32(const float* x, int64_t T, int64_t C, i
         while (b < n_doy && (fast_day[b] != 0) == fast) ++b;
         if (fast && (b - a) >= 8) {
           if (window == 5 && need <= 16)
-            e = need <= 8 ? launch_w5<8>(x, T, C, ldx, n_doy, n_years, spec, o, st, pos_d, n_doy, a, b)
-                          : launch_w5<16>(x, T, C, ldx, n_doy, n_years, spec, o, st, pos_d, n_doy, a, b);
+            e = need <= 8 ? launch_w5<8>(x, T, C, ldx, n_doy, n_years, spec, o, st, posrow_d, n_doy, a, b)
+                          : launch_w5<16>(x, T, C, ldx, n_doy, n_years, spec, o, st, posrow_d, n_doy, a, b);
           else
-            e = need <= 8    ? launch_uniform<8>(x, T, C, ldx, n_doy, n_years, window, spec, o, st, pos_d, n_doy, a, b)
-                : need <= 16 ? launch_uniform<16>(x, T, C, ldx, n_doy, n_years, window, spec, o, st, pos_d, n_doy, a, b)
-                             : launch_uniform<32>(x, T, C, ldx, n_doy, n_years, window, spec, o, st, pos_d, n_doy, a,
-                                                  b);
+            e = need <= 8    ? launch_uniform<8>(x, T, C, ldx, n_doy, n_years, window, spec, o, st, posrow_d, n_doy, a, b)
+                : need <= 16 ? launch_uniform<16>(x, T, C, ldx, n_doy, n_years, window, spec, o, st, posrow_d, n_doy, a, b)
+                             : launch_uniform<32>(x, T, C, ldx, n_doy, n_years, window, spec, o, st, posrow_d, n_doy,
+                                                  a, b);
         } else {
-          if (need <= 4) e = launch_generic<4>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b);
-          else if (need <= 8) e = launch_generic<8>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b);
-          else if (need <= 16) e = launch_generic<16>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b);
-          else if (need <= 32) e = launch_generic<32>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b);
-          else e = launch_generic<64>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b);
+          if (need <= 4) e = launch_generic<4>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b, vrow_d);
+          else if (need <= 8) e = launch_generic<8>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b, vrow_d);
+          else if (need <= 16) e = launch_generic<16>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b, vrow_d);
+          else if (need <= 32) e = launch_generic<32>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b, vrow_d);
+          else e = launch_generic<64>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec, o, st, a, b, vrow_d);
         }
         if (e) return e;
         a = b;
@@ -932,6 +954,26 @@ extern "C" int32_t xc_percentile_doy_f32(const float* x, int64_t T, int64_t C, i
     if (e) return e;
   }
   return XC_OK;
+}
+
+extern "C" int32_t xc_percentile_doy_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                         const int16_t* doy_index_host, const int16_t* year_index_host,
+                                         int32_t n_doy, int32_t n_years, int32_t window,
+                                         const double* percentiles_host, int32_t n_per, double alpha, double beta,
+                                         double* out, void* workspace, int64_t workspace_bytes, void* stream) {
+  return percentile_doy_impl(x, T, C, ldx, doy_index_host, year_index_host, n_doy, n_years, window,
+                             percentiles_host, n_per, alpha, beta, out, workspace, workspace_bytes, stream, nullptr);
+}
+
+extern "C" int32_t xc_percentile_doy_vrow_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                              const int16_t* doy_index_host, const int16_t* year_index_host,
+                                              const int32_t* vrow_host, int32_t n_doy, int32_t n_years,
+                                              int32_t window, const double* percentiles_host, int32_t n_per,
+                                              double alpha, double beta, double* out, void* workspace,
+                                              int64_t workspace_bytes, void* stream) {
+  XC_REQUIRE(vrow_host != nullptr, "null pointer argument");
+  return percentile_doy_impl(x, T, C, ldx, doy_index_host, year_index_host, n_doy, n_years, window,
+                             percentiles_host, n_per, alpha, beta, out, workspace, workspace_bytes, stream, vrow_host);
 }
 
 // Forces the generic kernel (test hook: the two paths must agree bit for bit).

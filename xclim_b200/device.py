@@ -130,8 +130,10 @@ def synth(T, C, kind, seed, cell_offset=0, cells_per_lat=1440, n_lat_global=721,
 
 # ------------------------------------------------------------------------------------ percentiles
 def percentile_doy(x2d, doy_index, year_index, n_doy, n_years, window, percentiles, alpha, beta,
-                   force_generic=False):
-    """(n_per, n_doy, C) float64 table of day-of-year percentiles (core/calendar.py:448-479)."""
+                   force_generic=False, vrow=None):
+    """(n_per, n_doy, C) float64 table of day-of-year percentiles (core/calendar.py:448-479).
+    ``vrow`` (int32[T], -1 = missing): read the value of step t from row vrow[t] (bootstrap
+    replacements on calendars with leap years)."""
     T, C = x2d.shape
     per = np.ascontiguousarray(np.atleast_1d(np.asarray(percentiles, dtype=np.float64)))
     doy = np.ascontiguousarray(np.asarray(doy_index, dtype=np.int16))
@@ -147,6 +149,13 @@ def percentile_doy(x2d, doy_index, year_index, n_doy, n_years, window, percentil
                                                     yr.ctypes.data, n_doy, n_years, int(window), float(p),
                                                     float(alpha), float(beta), out[i].data_ptr(), ws.data_ptr(),
                                                     ws.numel(), current_stream_ptr()))
+    elif vrow is not None:
+        vr = np.ascontiguousarray(np.asarray(vrow, dtype=np.int32))
+        assert vr.size == T
+        check(lib.xc_percentile_doy_vrow_f32(x2d.data_ptr(), T, C, x2d.stride(0), doy.ctypes.data, yr.ctypes.data,
+                                             vr.ctypes.data, n_doy, n_years, int(window), per.ctypes.data, per.size,
+                                             float(alpha), float(beta), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                             current_stream_ptr()))
     else:
         check(lib.xc_percentile_doy_f32(x2d.data_ptr(), T, C, x2d.stride(0), doy.ctypes.data, yr.ctypes.data,
                                         n_doy, n_years, int(window), per.ctypes.data, per.size, float(alpha),
