@@ -84,6 +84,25 @@ def main():
     if want("first"):
         ms = timeit(lambda: device.period_boundary_run(tas, poff, _lib.OPS[">"], 283.15, 5), a.steps)
         report("period_boundary_run first, window=5", ms, T * C * 4 + P * C * 4)
+    if want("heatwave"):
+        tmin = tas - 8.0
+        ms = timeit(lambda: device.period_runstat2(tmin, tas, poff, _lib.OPS[">"], 283.15, _lib.OPS[">"], 291.15,
+                                                   _lib.RL_REDUCERS["count"], 3), a.steps)
+        report("period_runstat2 (heat_wave_frequency: tasmin & tasmax, window 3)", ms, 2 * T * C * 4 + P * C * 4)
+        del tmin
+    if want("maxsum"):
+        ms = timeit(lambda: device.period_run_maxsum(tas, poff, _lib.OPS[">"], 291.15, 3), a.steps)
+        report("period_run_maxsum (hot_spell_max_magnitude, window 3)", ms, T * C * 4 + P * C * 4)
+    if want("runq"):
+        ms = timeit(lambda: device.period_run_quantile(pr, poff, _lib.OPS["<"], 1.0, 0.9, 1), a.steps)
+        report("period_run_quantile q90 of dry-run lengths (rle_statistics reducer='q90')", ms, T * C * 4 + P * C * 4)
+    if want("doycount"):
+        tab = device.percentile_doy(tas, doy, yidx, YEAR, P, 5, [90.0], 1 / 3, 1 / 3)[0]
+        poff_ms = np.concatenate([[0], np.cumsum(np.tile([31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31], P))]).astype(np.int32)
+        ms = timeit(lambda: device.doy_threshold_count(tas, poff_ms, doy, tab, _lib.OPS[">"]), a.steps)
+        report("doy_count_kernel (tx90p count, freq=MS: generic periods)", ms,
+               T * C * 4 + YEAR * C * 8 + (len(poff_ms) - 1) * C * 4)
+        del tab
     if want("bootstrap"):
         nb = 15
         step_period = np.repeat(np.arange(nb), YEAR).astype(np.int32)
@@ -109,14 +128,20 @@ def main():
                 else:
                     fn(fields[var])
         import time
-        run_batch()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        run_batch()
-        torch.cuda.synchronize()
-        ms = (time.perf_counter() - t0) * 1e3
-        report("batch of 50 atmos indicators (sequential calls, outputs copied to host)", ms, 50 * T * C * 4,
-               {"unique_input_bytes": 4 * T * C * 4, "note": "effective GB/s = sum of per-indicator input bytes / time"})
+        import xclim_b200
+        for dev_out in (False, True):
+            with xclim_b200.set_options(device_outputs=dev_out):
+                run_batch()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                run_batch()
+                torch.cuda.synchronize()
+                ms = (time.perf_counter() - t0) * 1e3
+            report("batch of 50 atmos indicators (sequential calls, outputs "
+                   + ("left in HBM: set_options(device_outputs=True))" if dev_out else "copied to host)"), ms,
+                   50 * T * C * 4,
+                   {"unique_input_bytes": 4 * T * C * 4,
+                    "note": "effective GB/s = sum of per-indicator input bytes / time"})
     if want("eqm"):
         hist = device.synth(T, C, kind=1, seed=5, cells_per_lat=X, n_lat_global=a.lat)
         ms = timeit(lambda: device.eqm_train(tas, hist, 20, 0), max(1, a.steps // 2), warmup=1)

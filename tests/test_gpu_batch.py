@@ -119,3 +119,37 @@ def test_batch_of_50_indicators(cuda):
             np.testing.assert_allclose(got, exp, rtol=1e-5, atol=1e-6, equal_nan=True, err_msg=name)  # float: 1e-5
         checked += 1
     assert checked == 50
+
+
+def test_device_outputs_option_matches_host_outputs(cuda):
+    """set_options(device_outputs=True): device-resident Fields in, device-resident Fields out, the
+    same values and dtypes as the host-materialised results."""
+    import torch
+    import xclim_b200
+    from xclim_b200 import Field, indices, run_length
+    data = _inputs()
+    units = {"tas": "K", "tasmax": "K", "tasmin": "K", "pr": "mm/d"}
+    host = {k: make_field(v, "1981-01-01", calendar="noleap", units=units[k]) for k, v in data.items()}
+    dev = {k: Field(torch.from_numpy(v).cuda(), f.dims, f.time, dict(f.coords), dict(f.attrs)) for (k, v), f in
+           zip(data.items(), host.values())}
+    names = ["tg_mean", "wetdays", "maximum_consecutive_dry_days", "dry_spell_frequency", "growing_degree_days",
+             "max_n_day_precipitation_amount", "hot_spell_max_magnitude", "cold_spell_days"]
+    var_of = dict(indices.BATCH_INDICATORS)
+    for name in names:
+        fn = getattr(indices, name)
+        ref = fn(host[var_of[name]])
+        with xclim_b200.set_options(device_outputs=True):
+            got = fn(dev[var_of[name]])
+        assert isinstance(got, Field) and got.values.is_cuda, name
+        assert got.numpy().dtype == ref.values.dtype, name
+        np.testing.assert_array_equal(got.numpy(), ref.values, err_msg=name)
+        assert got.attrs == ref.attrs
+    # first_run with coord="dayofyear" does its index -> doy lookup on the device
+    mask = host["pr"].assign_attrs()
+    ref = run_length.first_run(Field((data["pr"] > 5).astype(np.float32), mask.dims, mask.time), 2, freq="YS",
+                               coord="dayofyear")
+    with xclim_b200.set_options(device_outputs=True):
+        got = run_length.first_run(Field(torch.from_numpy((data["pr"] > 5).astype(np.float32)).cuda(), mask.dims,
+                                         mask.time), 2, freq="YS", coord="dayofyear")
+    np.testing.assert_array_equal(got.numpy(), ref.values)
+    assert not xclim_b200.options.OPTIONS["device_outputs"]

@@ -62,7 +62,7 @@ def test_date_bounded_runs_parity(cuda):
         np.testing.assert_array_equal(got, per_group(O.first_run_after_date, cond_lt, w))
         got = indices.last_spring_frost(da, window=w).values
         np.testing.assert_array_equal(got, per_group(O.last_run_before_date, cond_lt, w))
-        got = seasons.run_end_after_date(x2d, ta, "YS", _lib.OPS["<"], 273.15, w, "07-01").numpy().reshape((3, 4, 6))
+        got = seasons.run_end_after_date(x2d, ta, "YS", _lib.OPS["<"], 273.15, w, "07-01").cpu().numpy().reshape((3, 4, 6))
         np.testing.assert_array_equal(got, per_group(O.run_end_after_date, cond_lt, w))
 
 

@@ -6,5 +6,6 @@ CUDA; the shared library is loaded on first use and there is NO CPU fallback.
 """
 from .field import Field  # noqa: F401
 from .timeaxis import TimeAxis  # noqa: F401
+from .options import set_options  # noqa: F401
 
 __version__ = "0.1.0"

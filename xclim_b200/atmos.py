@@ -61,7 +61,8 @@ def tx90p(tasmax, tasmax_per, freq="YS", bootstrap=False, op=">"):
         x2d, cell_shape, other, ta = _unwrap(tasmax)
         poff = ta.period_offsets(freq)
         _, valid = device.period_count(x2d, poff, _lib.OP_NOTNAN, 0.0, want_valid=True)
-        vals = torch.from_numpy(np.asarray(out.values, dtype=np.float64)).reshape(len(poff) - 1, -1).to(x2d.device)
+        vals = out.values if hasattr(out.values, "is_cuda") else torch.from_numpy(np.asarray(out.values, np.float64))
+        vals = vals.reshape(len(poff) - 1, -1).to(x2d.device)
         masked = _mask_missing(vals, valid, poff)
         attrs = attrs_of(out)
         attrs["units"] = "days"

@@ -13,15 +13,24 @@ namespace {
 constexpr int kThreads = 128;
 constexpr int kUnroll = 4;
 
-__device__ __forceinline__ bool cmp_rt(int op, float x, float t) {
+// Runtime operator without a branch: (x op t) == (((x<t)&L) | ((x==t)&E) | ((x>t)&G)) != N with the
+// masks below (NaN makes the three tests false, so only != is true on NaN, as in numpy).
+struct OpMask {
+  bool L, E, G, N;
+};
+inline OpMask op_mask(int op) {
   switch (op) {
-    case XC_OP_GT: return x > t;
-    case XC_OP_LT: return x < t;
-    case XC_OP_GE: return x >= t;
-    case XC_OP_LE: return x <= t;
-    case XC_OP_EQ: return x == t;
-    default: return x != t;
+    case XC_OP_GT: return {false, false, true, false};
+    case XC_OP_LT: return {true, false, false, false};
+    case XC_OP_GE: return {false, true, true, false};
+    case XC_OP_LE: return {true, true, false, false};
+    case XC_OP_EQ: return {false, true, false, false};
+    default: return {false, true, false, true};
   }
+}
+__device__ __forceinline__ bool cmp_rt(const OpMask& m, float x, float t) {
+  const bool r = ((x < t) & m.L) | ((x == t) & m.E) | ((x > t) & m.G);
+  return r != m.N;
 }
 
 struct Acc {
@@ -30,10 +39,12 @@ struct Acc {
   bool skip;
 };
 
-template <int VEC>
+// RED: XC_RL_MAX / SUM / COUNT get branch-free single-accumulator updates (the heat-wave indices);
+// any other value keeps every accumulator and switches on `reducer` at the end.
+template <int VEC, int RED>
 __global__ void __launch_bounds__(kThreads)
 period_runstat2_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int64_t T, int64_t C, int64_t ldx,
-                       const int32_t* __restrict__ poff, int op1, float t1, int op2, float t2, int any,
+                       const int32_t* __restrict__ poff, OpMask op1, float t1, OpMask op2, float t2, int any,
                        int reducer, int window, int after, float* __restrict__ out) {
   const int64_t c0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * VEC;
   if (c0 >= C) return;
@@ -44,16 +55,25 @@ period_runstat2_kernel(const float* __restrict__ x1, const float* __restrict__ x
   for (int i = 0; i < VEC; ++i) a[i] = Acc{0, 0, 0x7fffffff, 0, 0, 0ull, false};
   auto cond = [&](float u, float v) -> bool {
     const bool c1 = cmp_rt(op1, u, t1), c2 = cmp_rt(op2, v, t2);
-    return any ? (c1 || c2) : (c1 && c2);
+    return any ? (c1 | c2) : (c1 & c2);
   };
   auto close_run = [&](Acc& s) {
     const int L = s.cur;
-    if (L >= window) {
-      s.mx = max(s.mx, L);
-      s.mn = min(s.mn, L);
-      s.sum += L;
-      s.cnt += 1;
-      s.sq += (unsigned long long)L * (unsigned long long)L;
+    const bool take = L >= window;
+    if constexpr (RED == XC_RL_MAX) {
+      s.mx = take ? max(s.mx, L) : s.mx;
+    } else if constexpr (RED == XC_RL_SUM) {
+      s.sum += take ? L : 0;
+    } else if constexpr (RED == XC_RL_COUNT) {
+      s.cnt += take ? 1 : 0;
+    } else {
+      if (take) {
+        s.mx = max(s.mx, L);
+        s.mn = min(s.mn, L);
+        s.sum += L;
+        s.cnt += 1;
+        s.sq += (unsigned long long)L * (unsigned long long)L;
+      }
     }
     s.cur = 0;
   };
@@ -84,7 +104,18 @@ period_runstat2_kernel(const float* __restrict__ x1, const float* __restrict__ x
           m = m && !a[i].skip;
         }
       }
-      if (m) a[i].cur += 1; else close_run(a[i]);
+      if constexpr (RED == XC_RL_MAX || RED == XC_RL_SUM || RED == XC_RL_COUNT) {
+        // branch-free: closing an empty run (cur == 0 < window) is a no-op
+        Acc closing = a[i];
+        close_run(closing);
+        const int next = a[i].cur + 1;
+        a[i].mx = m ? a[i].mx : closing.mx;
+        a[i].sum = m ? a[i].sum : closing.sum;
+        a[i].cnt = m ? a[i].cnt : closing.cnt;
+        a[i].cur = m ? next : 0;
+      } else {
+        if (m) a[i].cur += 1; else close_run(a[i]);
+      }
     }
   };
   int t = t0;
@@ -161,13 +192,21 @@ extern "C" int32_t xc_period_runstat2_f32(const float* x1, const float* x2, int6
   dim3 grid((unsigned)(((C + vec - 1) / vec + kThreads - 1) / kThreads), (unsigned)P, 1);
   cudaStream_t st = (cudaStream_t)stream;
   // thresholds are Python floats in the reference: compared in float32
-  if (v4)
-    period_runstat2_kernel<4><<<grid, kThreads, 0, st>>>(x1, x2, T, C, ldx, period_offsets, op1, (float)thr1, op2,
-                                                         (float)thr2, var_any ? 1 : 0, reducer, window,
-                                                         resample_before_rl ? 0 : 1, out);
-  else
-    period_runstat2_kernel<1><<<grid, kThreads, 0, st>>>(x1, x2, T, C, ldx, period_offsets, op1, (float)thr1, op2,
-                                                         (float)thr2, var_any ? 1 : 0, reducer, window,
-                                                         resample_before_rl ? 0 : 1, out);
+  const OpMask m1 = op_mask(op1), m2 = op_mask(op2);
+  const int anyf = var_any ? 1 : 0, afterf = resample_before_rl ? 0 : 1;
+#define XC_LAUNCH2(VEC, RED)                                                                                        \
+  period_runstat2_kernel<VEC, RED><<<grid, kThreads, 0, st>>>(x1, x2, T, C, ldx, period_offsets, m1, (float)thr1, m2, \
+                                                              (float)thr2, anyf, reducer, window, afterf, out)
+  if (v4) {
+    switch (reducer) {
+      case XC_RL_MAX: XC_LAUNCH2(4, XC_RL_MAX); break;
+      case XC_RL_SUM: XC_LAUNCH2(4, XC_RL_SUM); break;
+      case XC_RL_COUNT: XC_LAUNCH2(4, XC_RL_COUNT); break;
+      default: XC_LAUNCH2(4, XC_RL_STD);
+    }
+  } else {
+    XC_LAUNCH2(1, XC_RL_STD);
+  }
+#undef XC_LAUNCH2
   return launch_status("period_runstat2_kernel");
 }

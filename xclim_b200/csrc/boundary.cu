@@ -15,6 +15,39 @@ namespace xc {
 namespace {
 
 constexpr int kThreads = 128;
+constexpr int kChunk = 8;
+
+// Rows [lo, hi) of one cell in time order (or reversed), kChunk independent loads in flight before
+// the serial state machine consumes them; body(step, value) returns true to stop (early exit at
+// chunk granularity: at most kChunk - 1 rows are fetched for nothing).
+template <typename F>
+__device__ __forceinline__ void scan_forward(const float* __restrict__ col, int64_t ldx, int lo, int hi, F&& body) {
+  for (int s0 = lo; s0 < hi; s0 += kChunk) {
+    float v[kChunk];
+#pragma unroll
+    for (int k = 0; k < kChunk; ++k)
+      if (s0 + k < hi) v[k] = ld_stream(col + (int64_t)(s0 + k) * ldx);
+#pragma unroll
+    for (int k = 0; k < kChunk; ++k)
+      if (s0 + k < hi) {
+        if (body(s0 + k, v[k])) return;
+      }
+  }
+}
+template <typename F>
+__device__ __forceinline__ void scan_backward(const float* __restrict__ col, int64_t ldx, int lo, int hi, F&& body) {
+  for (int s0 = hi - 1; s0 >= lo; s0 -= kChunk) {
+    float v[kChunk];
+#pragma unroll
+    for (int k = 0; k < kChunk; ++k)
+      if (s0 - k >= lo) v[k] = ld_stream(col + (int64_t)(s0 - k) * ldx);
+#pragma unroll
+    for (int k = 0; k < kChunk; ++k)
+      if (s0 - k >= lo) {
+        if (body(s0 - k, v[k])) return;
+      }
+  }
+}
 
 template <int OP>
 __global__ void __launch_bounds__(kThreads)
@@ -29,29 +62,29 @@ boundary_run_kernel(const float* __restrict__ x, int64_t T, int64_t C, int64_t l
   float res = NAN;
   if (window == 1) {
     int first = -1, lastt = -1, ntrue = 0;
-    for (int t = t0; t < t1; ++t) {
-      const bool m = cmp<OP>(ld_stream(col + (int64_t)t * ldx), thr);
-      if (m) {
+    scan_forward(col, ldx, t0, t1, [&](int t, float v) {
+      if (cmp<OP>(v, thr)) {
         if (first < 0) first = t;
         lastt = t;
         ++ntrue;
       }
-    }
+      return false;
+    });
     if (ntrue > 0 && ntrue < t1 - t0) res = (float)((last ? lastt : first) - t0);
   } else if (!last) {
     int cur = 0, first = -1;
     bool any_false = false;
     const int end = min((int)T, t1 + window - 1);
-    for (int s = t0; s < end; ++s) {
-      const bool m = cmp<OP>(ld_stream(col + (int64_t)s * ldx), thr);
+    scan_forward(col, ldx, t0, end, [&](int s, float v) {
+      const bool m = cmp<OP>(v, thr);
       cur = m ? cur + 1 : 0;
       any_false = any_false || !m;
       if (first < 0 && cur >= window) {
-        first = s - window + 1;  // < t1 because s < t1 + window - 1
-        if (first > t0) break;   // d[t0] == 0: the argmax == argmin rule cannot apply
+        first = s - window + 1;        // < t1 because s < t1 + window - 1
+        if (first > t0) return true;   // d[t0] == 0: the argmax == argmin rule cannot apply
       }
-      if (first >= 0 && any_false) break;
-    }
+      return first >= 0 && any_false;
+    });
     // every position of the period qualifies (d all ones) -> argmax == argmin == 0 -> NaN (:603-605)
     const bool all_set = (first == t0) && !any_false && (end == t1 + window - 1);
     if (first >= 0 && !all_set) res = (float)(first - t0);
@@ -59,16 +92,16 @@ boundary_run_kernel(const float* __restrict__ x, int64_t T, int64_t C, int64_t l
     int cur = 0, lastt = -1;
     bool any_false = false;
     const int begin = max(0, t0 - window + 1);
-    for (int s = t1 - 1; s >= begin; --s) {
-      const bool m = cmp<OP>(ld_stream(col + (int64_t)s * ldx), thr);
+    scan_backward(col, ldx, begin, t1, [&](int s, float v) {
+      const bool m = cmp<OP>(v, thr);
       cur = m ? cur + 1 : 0;
       any_false = any_false || !m;
       if (lastt < 0 && cur >= window) {
         lastt = s + window - 1;
-        if (lastt < t1 - 1) break;
+        if (lastt < t1 - 1) return true;
       }
-      if (lastt >= 0 && any_false) break;
-    }
+      return lastt >= 0 && any_false;
+    });
     const bool all_set = (lastt == t1 - 1) && !any_false && (begin == t0 - window + 1);
     if (lastt >= 0 && !all_set) res = (float)(lastt - t0);
   }
@@ -134,39 +167,36 @@ boundary_run_range_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, c
       if (t0 + bl > lo) { lo = t0 + bl; full = false; }
     }
     const float* col = x + c;
-    auto cond = [&](int s) -> bool {
-      const bool m = cmp<OP>(ld_stream(col + (int64_t)s * ldx), thr);
+    auto cond = [&](float v) -> bool {
+      const bool m = cmp<OP>(v, thr);
       return negate ? !m : m;
     };
     if (window == 1 && full) {
       // argmax == argmin rule on the whole group (indices/run_length.py:603-605): all-True -> NaN
       int first = -1, lastt = -1, ntrue = 0;
-      for (int s = lo; s < hi; ++s) {
-        if (cond(s)) {
+      scan_forward(col, ldx, lo, hi, [&](int s, float v) {
+        if (cond(v)) {
           if (first < 0) first = s;
           lastt = s;
           ++ntrue;
         }
-      }
+        return false;
+      });
       if (ntrue > 0 && ntrue < hi - lo) res = (float)((last ? lastt : first) - t0);
     } else if (!last) {
       int cur = 0;
-      for (int s = lo; s < hi; ++s) {
-        cur = cond(s) ? cur + 1 : 0;
-        if (cur >= window) {
-          res = (float)(s - window + 1 - t0);
-          break;
-        }
-      }
+      scan_forward(col, ldx, lo, hi, [&](int s, float v) {
+        cur = cond(v) ? cur + 1 : 0;
+        if (cur >= window) res = (float)(s - window + 1 - t0);
+        return cur >= window;
+      });
     } else {
       int cur = 0;
-      for (int s = hi - 1; s >= lo; --s) {
-        cur = cond(s) ? cur + 1 : 0;
-        if (cur >= window) {
-          res = (float)(s + window - 1 - t0);
-          break;
-        }
-      }
+      scan_backward(col, ldx, lo, hi, [&](int s, float v) {
+        cur = cond(v) ? cur + 1 : 0;
+        if (cur >= window) res = (float)(s + window - 1 - t0);
+        return cur >= window;
+      });
     }
   }
   out[(int64_t)p * C + c] = res;

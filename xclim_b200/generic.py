@@ -8,7 +8,8 @@ from __future__ import annotations
 import numpy as np
 
 from . import _lib, device
-from .field import attrs_of, dims_of, raw_values, time_axis_of, wrap_like
+from .field import attrs_of, dims_of, is_xarray, raw_values, time_axis_of, wrap_like
+from .options import OPTIONS
 from .units import threshold_in_units_of, to_agg_units_attrs
 
 
@@ -41,9 +42,14 @@ def _period_time(da, ta, freq):
 
 def _wrap_periods(da, out2d, cell_shape, other_dims, ta, freq, attrs, dtype=None, name=None):
     vals = out2d.reshape((out2d.shape[0],) + cell_shape)
-    vals = vals.cpu().numpy()
-    if dtype is not None:
-        vals = vals.astype(dtype, copy=False)
+    if OPTIONS["device_outputs"] and not is_xarray(da) and getattr(vals, "is_cuda", False):
+        if dtype is not None:      # same dtype as the host path, converted where the data are
+            import torch
+            vals = vals.to(getattr(torch, np.dtype(dtype).name))
+    else:
+        vals = vals.cpu().numpy()
+        if dtype is not None:
+            vals = vals.astype(dtype, copy=False)
     return wrap_like(da, vals, ("time",) + other_dims, time=_period_time(da, ta, freq), attrs=attrs, name=name)
 
 

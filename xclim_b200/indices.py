@@ -288,13 +288,25 @@ def windy_days(sfcWind, thresh="10.8 m s-1", freq="MS"):
     return _count(sfcWind, thresh, ">=", freq, (">", ">="))
 
 
+def _ratio(num, den):
+    """``num / den`` in float64 for numpy arrays or CUDA tensors (set_options(device_outputs=True))."""
+    import numpy as np
+    if hasattr(num, "is_cuda"):
+        import torch
+        if not hasattr(den, "is_cuda"):
+            den = torch.from_numpy(np.ascontiguousarray(den)).to(num.device)
+        return num.to(torch.float64) / den.to(torch.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.asarray(num, dtype=np.float64) / den
+
+
 def wetdays_prop(pr, thresh="1.0 mm/day", freq="YS", op=">="):
     """indices/_threshold.py:2792-2834: mean of the boolean wet-day mask per period."""
     import numpy as np
     from .field import time_axis_of as _ta
     cnt = _count(pr, thresh, op, freq, (">", ">="))
     n = np.diff(_ta(pr).period_offsets(freq)).reshape((-1,) + (1,) * (cnt.values.ndim - 1))
-    out = cnt.values / n
+    out = _ratio(cnt.values, n)
     from .field import Field, is_xarray
     if is_xarray(cnt):
         return cnt.copy(data=out).assign_attrs(units="1")
@@ -320,8 +332,7 @@ def daily_pr_intensity(pr, thresh="1 mm/day", freq="YS", op=">="):
     thr = threshold_in_units_of(thresh, pr)
     s = generic.thresholded_statistics(pr, op, thr, "sum", freq, constrain=(">", ">="))
     wd = _count(pr, thr, op, freq, (">", ">="))
-    with np.errstate(divide="ignore", invalid="ignore"):
-        out = s.values.astype(np.float64) / wd.values
+    out = _ratio(s.values, wd.values)
     from .field import Field, is_xarray
     if is_xarray(s):
         return s.copy(data=out).assign_attrs(units="mm d-1")

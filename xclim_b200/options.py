@@ -1,0 +1,28 @@
+"""Package options, in the style of ``xclim.set_options`` (core/options.py).
+
+``device_outputs`` (default False): functions called with a :class:`xclim_b200.Field` return their
+result as a Field whose ``values`` is a CUDA tensor instead of copying it to the host, so that
+a batch of indices over device-resident inputs runs without a device->host round trip per call
+(``Field.numpy()`` materialises it).  xarray inputs always get numpy-backed DataArrays back.
+"""
+from __future__ import annotations
+
+OPTIONS = {"device_outputs": False}
+
+
+class set_options:
+    """``with set_options(device_outputs=True): ...`` or a plain call for a global change."""
+
+    def __init__(self, **kwargs):
+        self._old = {}
+        for k, v in kwargs.items():
+            if k not in OPTIONS:
+                raise ValueError(f"argument name {k!r} is not in the set of valid options {set(OPTIONS)!r}")
+            self._old[k] = OPTIONS[k]
+            OPTIONS[k] = v
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        OPTIONS.update(self._old)

@@ -108,12 +108,24 @@ def _boundary(da, window, dim, freq, coord, position):
     x2d, cell_shape, other, ta = _mask_unwrap(da)
     poff = ta.period_offsets(freq)
     out = device.period_boundary_run(x2d, poff, _GT, 0.0, window, last=(position == "last"))
-    vals = out.cpu().numpy().astype(np.float64)
-    if coord == "dayofyear":  # lazy_indexing(time.dt.dayofyear, index), core/utils.py:202-276
-        idx = np.where(np.isnan(vals), 0, vals).astype(np.int64) + poff[:-1].reshape((-1,) + (1,) * (vals.ndim - 1))
-        vals = np.where(np.isnan(vals), np.nan, ta.doy[np.clip(idx, 0, len(ta) - 1)].astype(np.float64))
     import torch
-    return _wrap_periods(da, torch.from_numpy(vals), cell_shape, other, ta, freq, attrs_of(da), dtype=np.float64)
+    vals = out.to(torch.float64)
+    if coord == "dayofyear":  # lazy_indexing(time.dt.dayofyear, index), core/utils.py:202-276
+        vals = index_to_doy(vals, poff, ta)
+    return _wrap_periods(da, vals, cell_shape, other, ta, freq, attrs_of(da), dtype=np.float64)
+
+
+def index_to_doy(vals, poff, ta):
+    """(P, C) float64 device tensor of step indices relative to the period start (NaN = none) -> the
+    day of year of that step, on the device (core/utils.py:202-276 ``lazy_indexing``)."""
+    import torch
+    dev = vals.device
+    nan = torch.isnan(vals)
+    start = torch.from_numpy(np.asarray(poff[:-1], dtype=np.int64)).to(dev)[:, None]
+    idx = torch.where(nan, torch.zeros_like(vals), vals).to(torch.int64) + start
+    doy = torch.from_numpy(np.asarray(ta.doy, dtype=np.float64)).to(dev)
+    out = doy[idx.clamp_(0, len(ta) - 1)]
+    return torch.where(nan, torch.full_like(out, float("nan")), out)
 
 
 def first_run(da, window, dim="time", freq=None, coord=False, ufunc_1dim="from_context"):

@@ -34,10 +34,8 @@ def _to_coord(vals, poff, ta, coord):
         return vals
     if coord != "dayofyear":
         raise NotImplementedError("coord must be False or 'dayofyear'")
-    v = vals.cpu().numpy().astype(np.float64)
-    idx = np.where(np.isnan(v), 0, v).astype(np.int64) + np.asarray(poff[:-1])[:, None]
-    out = np.where(np.isnan(v), np.nan, ta.doy[np.clip(idx, 0, len(ta) - 1)].astype(np.float64))
-    return torch.from_numpy(out)
+    from .run_length import index_to_doy
+    return index_to_doy(vals.to(torch.float64), poff, ta)
 
 
 def first_run_after_date(x2d, ta, freq, op_code, thr, window, date, coord="dayofyear"):
