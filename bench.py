@@ -49,7 +49,7 @@ def parse_args():
 class ClockSampler:
     """Samples SM clock / throttle reasons with NVML during the timed region."""
 
-    def __init__(self, index=0, period=0.005):
+    def __init__(self, index=0, period=0.002):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._th = None
@@ -88,6 +88,11 @@ class ClockSampler:
 
     def __enter__(self):
         if self.nv is not None:
+            try:   # the first NVML queries of a process take tens of ms: prime them outside the timed region
+                self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                pass
             self._th = threading.Thread(target=self._run, daemon=True)
             self._th.start()
         return self

@@ -18,8 +18,12 @@ sys.path.insert(0, ROOT)
 T, X, YEAR = 10950, 1440, 365
 
 
-def timeit(fn, steps, warmup=2):
+WARMUP = 2
+
+
+def timeit(fn, steps, warmup=None):
     import torch
+    warmup = WARMUP if warmup is None else min(warmup, WARMUP)
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
@@ -37,7 +41,10 @@ def main():
     ap.add_argument("--lat", type=int, default=180)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--only", default="")
+    ap.add_argument("--warmup", type=int, default=2, help="untimed launches per kernel (0 for ncu captures)")
     a = ap.parse_args()
+    global WARMUP
+    WARMUP = a.warmup
     import torch
     from xclim_b200 import _lib, device
     C = a.lat * X

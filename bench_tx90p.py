@@ -87,9 +87,9 @@ def tx90p_section(args, dev, rank, world, peak, barrier):
         "ms_percentile_doy": t_per, "ms_count": t_cnt, "steps": steps,
         "roofline_percentile_doy": {"bound": "hbm", "achieved": ach_per, "peak": peak, "unit": "GB/s",
                                     "frac": ach_per / peak, "algorithmic_bytes": alg_per,
-                                    "kernel": "percentile_doy_uniform_kernel<16,5>"},
+                                    "kernel": "percentile_doy_w5p_kernel<16>"},
         "roofline_count": {"bound": "hbm", "achieved": ach_cnt, "peak": peak, "unit": "GB/s",
-                           "frac": ach_cnt / peak, "algorithmic_bytes": alg_cnt, "kernel": "doy_count_kernel<GT>"},
+                           "frac": ach_cnt / peak, "algorithmic_bytes": alg_cnt, "kernel": "doy_count_years_kernel<GT,3,VALID>"},
         "gpu_launches_per_step": 2, "cpu_baseline": cpu,
         "check": {"oracle_cells": int(sel.numel()), "table_bit_exact": table_equal, "counts_exact": counts_equal,
                   "mean_exceedance_fraction": frac},

@@ -41,7 +41,9 @@ struct Acc {
 
 // RED: XC_RL_MAX / SUM / COUNT get branch-free single-accumulator updates (the heat-wave indices);
 // any other value keeps every accumulator and switches on `reducer` at the end.
-template <int VEC, int RED>
+// GTGT: both operators are ">" (the heat-wave indices and tx_tn_days_above): two compares and one
+// predicate op per element pair instead of the six + six of the operator masks.
+template <int VEC, int RED, bool GTGT>
 __global__ void __launch_bounds__(kThreads)
 period_runstat2_kernel(const float* __restrict__ x1, const float* __restrict__ x2, int64_t T, int64_t C, int64_t ldx,
                        const int32_t* __restrict__ poff, OpMask op1, float t1, OpMask op2, float t2, int any,
@@ -54,7 +56,14 @@ period_runstat2_kernel(const float* __restrict__ x1, const float* __restrict__ x
 #pragma unroll
   for (int i = 0; i < VEC; ++i) a[i] = Acc{0, 0, 0x7fffffff, 0, 0, 0ull, false};
   auto cond = [&](float u, float v) -> bool {
-    const bool c1 = cmp_rt(op1, u, t1), c2 = cmp_rt(op2, v, t2);
+    bool c1, c2;
+    if constexpr (GTGT) {
+      c1 = u > t1;
+      c2 = v > t2;
+    } else {
+      c1 = cmp_rt(op1, u, t1);
+      c2 = cmp_rt(op2, v, t2);
+    }
     return any ? (c1 | c2) : (c1 & c2);
   };
   auto close_run = [&](Acc& s) {
@@ -194,9 +203,16 @@ extern "C" int32_t xc_period_runstat2_f32(const float* x1, const float* x2, int6
   // thresholds are Python floats in the reference: compared in float32
   const OpMask m1 = op_mask(op1), m2 = op_mask(op2);
   const int anyf = var_any ? 1 : 0, afterf = resample_before_rl ? 0 : 1;
-#define XC_LAUNCH2(VEC, RED)                                                                                        \
-  period_runstat2_kernel<VEC, RED><<<grid, kThreads, 0, st>>>(x1, x2, T, C, ldx, period_offsets, m1, (float)thr1, m2, \
-                                                              (float)thr2, anyf, reducer, window, afterf, out)
+  const bool gtgt = (op1 == XC_OP_GT) && (op2 == XC_OP_GT);
+#define XC_LAUNCH2(VEC, RED)                                                                                       \
+  do {                                                                                                             \
+    if (gtgt)                                                                                                      \
+      period_runstat2_kernel<VEC, RED, true><<<grid, kThreads, 0, st>>>(                                           \
+          x1, x2, T, C, ldx, period_offsets, m1, (float)thr1, m2, (float)thr2, anyf, reducer, window, afterf, out); \
+    else                                                                                                           \
+      period_runstat2_kernel<VEC, RED, false><<<grid, kThreads, 0, st>>>(                                          \
+          x1, x2, T, C, ldx, period_offsets, m1, (float)thr1, m2, (float)thr2, anyf, reducer, window, afterf, out); \
+  } while (0)
   if (v4) {
     switch (reducer) {
       case XC_RL_MAX: XC_LAUNCH2(4, XC_RL_MAX); break;
