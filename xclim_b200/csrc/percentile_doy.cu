@@ -96,18 +96,16 @@ percentile_doy_generic_kernel(const float* __restrict__ x, int64_t T, int64_t C,
 #ifndef XC_PCTL_ADDR      // 0: running 64-bit pointer (2 ALU-pipe adds per load); 1: one IMAD.WIDE (FMA pipe)
 #define XC_PCTL_ADDR (XC_PCTL_VARIANT == 1 ? 1 : 0)
 #endif
-#ifndef XC_PCTL_PREFETCH  // 1: L2 prefetch of the next day's rows (measured SLOWER: 16.1 vs 13.7 ms; off)
-#define XC_PCTL_PREFETCH 0
+#ifndef XC_PCTL_STAGE     // 1: cp.async staging of the next day's rows in the window-5 paired kernel
+#define XC_PCTL_STAGE 1      // (an L2 prefetch of those rows was measured SLOWER: 16.1 vs 13.7 ms)
 #endif
 #ifndef XC_PCTL_PROBE     // NaN probe: 0 = compare chain (ALU pipe); 1 = FMA chain; 2 = FADD tree + 1 compare per 4
 #define XC_PCTL_PROBE (XC_PCTL_VARIANT == 1 ? 1 : 0)
 #endif
 
-// NV rows p0 + k*ystride -> v[0..NV) (negated for a bottom-side quantile), pads -inf, NaN -> -inf
-// (never selected; nv counts the valid ones), then sorted descending.
+// NV rows p0 + k*ystride -> v[0..NV)
 template <int K, int NV>
-__device__ __forceinline__ void load_sort_chunk(const char* p0, uint64_t ystride, bool top, float (&v)[K],
-                                                int& nv, int64_t next_day_bytes) {
+__device__ __forceinline__ void fetch_rows(const char* p0, uint64_t ystride, float (&v)[K]) {
 #if XC_PCTL_ADDR == 1
   const uint32_t ys32 = (uint32_t)ystride;
 #pragma unroll
@@ -121,17 +119,12 @@ __device__ __forceinline__ void load_sort_chunk(const char* p0, uint64_t ystride
     pp += ystride;
   }
 #endif
-#if XC_PCTL_PREFETCH
-  // the same rows of the NEXT day go to L2 now, so that the next iteration's loads see L2 latency
-  if (next_day_bytes != 0) {
-    const char* pf = p0 + next_day_bytes;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
-      pf += ystride;
-    }
-  }
-#endif
+}
+
+// v[0..NV) raw values -> negated for a bottom-side quantile, pads -inf, NaN -> -inf (never selected;
+// nv counts the valid ones), sorted descending.
+template <int K, int NV>
+__device__ __forceinline__ void finish_chunk(bool top, float (&v)[K], int& nv) {
 #pragma unroll
   for (int k = NV; k < K; ++k) v[k] = XC_NEG_INF;
   if (!top) {
@@ -174,6 +167,60 @@ __device__ __forceinline__ void load_sort_chunk(const char* p0, uint64_t ystride
   else sort_desc_first<K, NV>(v);
 }
 
+template <int K, int NV>
+__device__ __forceinline__ void load_sort_chunk(const char* p0, uint64_t ystride, bool top, float (&v)[K],
+                                                int& nv) {
+  fetch_rows<K, NV>(p0, ystride, v);
+  finish_chunk<K, NV>(top, v, nv);
+}
+
+// ---- asynchronous staging of the NEXT day's rows (cp.async, global -> shared) --------------------
+// The day-list kernels are bound by the min/max pipe but lose a third of their issue slots waiting
+// for the 30 row loads of a day (ncu: long_scoreboard 35 %).  With a Stager the rows of day e+1 are
+// copied to a per-lane shared-memory column while day e is sorted and merged; a lane reads back only
+// what it copied itself, so cp.async.wait_group is the only synchronisation.  The buffer is reused
+// chunk by chunk: as soon as the 16 (14) values of a chunk are in registers, the copy of the same
+// chunk of the next day is issued, so that exactly two groups are pending at the start of a day.
+// Used when a day has two chunks with every year present (K == 16, 30..32 years, 0 <= e < L).
+struct Stager {
+  float* col;      // this lane's column of the [32][kThreads] staging buffer
+  int staged_e;    // day in flight / in the buffer, or kNoDay
+  bool want_next;  // the caller asks for day e + 1 next
+};
+constexpr int kNoDay = -1000000;
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// chunk of NV years starting at year y0 of day e: from the staging buffer (have) or from global;
+// then (issue) start the copy of the same chunk of day e + 1
+template <int K, int NV>
+__device__ __forceinline__ void staged_chunk(Stager& sg, const char* pcur, uint64_t ystride, int64_t day_bytes,
+                                             int y0, bool have, bool issue, bool top, float (&v)[K], int& nv) {
+  if (have) {
+    if (issue) cp_async_wait<1>(); else cp_async_wait<0>();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = sg.col[(y0 + k) * kThreads];
+  } else {
+    fetch_rows<K, NV>(pcur + (uint64_t)y0 * ystride, ystride, v);
+  }
+  if (issue) {
+    const char* pn = pcur + day_bytes + (uint64_t)y0 * ystride;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      cp_async4(sg.col + (y0 + k) * kThreads, pn);
+      pn += ystride;
+    }
+    cp_async_commit();
+  }
+  finish_chunk<K, NV>(top, v, nv);
+}
+
 // ------------------------------------------------------------------------------------------------
 // fast kernel: uniform year length L == n_doy, T == N*L, series starts on doy 1
 // ------------------------------------------------------------------------------------------------
@@ -185,7 +232,8 @@ __device__ __forceinline__ void load_sort_chunk(const char* p0, uint64_t ystride
 template <int K, bool TABLE = false>
 __device__ __forceinline__ void load_day_list(const float* __restrict__ x, int64_t c, int64_t ldx, int T, int L,
                                               int N, int e, bool top, float (&lst)[K], int& n,
-                                              const int32_t* __restrict__ pos = nullptr, int n_doy = 0) {
+                                              const int32_t* __restrict__ pos = nullptr, int n_doy = 0,
+                                              Stager* sg = nullptr) {
   n = 0;
   if constexpr (TABLE) {
     bool first_t = true;
@@ -222,6 +270,33 @@ __device__ __forceinline__ void load_day_list(const float* __restrict__ x, int64
   const int yhi = (e >= L) ? N - 1 : N;
   const uint64_t ystride = (uint64_t)L * (uint64_t)ldx * 4ull;
   const bool narrow = (ystride >> 32) == 0;
+  if constexpr (K == 16) {
+    if (sg != nullptr) {
+      const int tail2 = N - K;                                   // years in the second chunk
+      const bool two_chunks = narrow && tail2 >= 14 && tail2 <= 16;
+      const bool now_ok = two_chunks && e >= 0 && e < L;         // every year has day e
+      if (now_ok) {
+        const bool have = (sg->staged_e == e);
+        const bool issue = sg->want_next && (e + 1 < L);
+        const char* pcur = reinterpret_cast<const char*>(x + (int64_t)e * ldx + c);
+        const int64_t day_bytes = ldx * 4;
+        float v[K];
+        int nv;
+        staged_chunk<K, K>(*sg, pcur, ystride, day_bytes, 0, have, issue, top, lst, nv);
+        n = nv;
+        if (tail2 == 14) staged_chunk<K, 14>(*sg, pcur, ystride, day_bytes, K, have, issue, top, v, nv);
+        else if (tail2 == 15) staged_chunk<K, 15>(*sg, pcur, ystride, day_bytes, K, have, issue, top, v, nv);
+        else staged_chunk<K, 16>(*sg, pcur, ystride, day_bytes, K, have, issue, top, v, nv);
+        n += nv;
+        merge_top_desc<K>(lst, v);
+        sg->staged_e = issue ? e + 1 : kNoDay;
+        return;
+      }
+      // a day that cannot be staged is never announced by the previous one (same predicate), so
+      // nothing is in flight here
+      sg->staged_e = kNoDay;
+    }
+  }
   bool first = true;
   for (int y0 = 0; y0 < N; y0 += K) {
     float v[K];
@@ -232,14 +307,12 @@ __device__ __forceinline__ void load_day_list(const float* __restrict__ x, int64
     const bool inside = narrow && (y0 >= ylo) && ((tail >= K ? y0 + K : N) <= yhi);
     // The last chunk of e.g. a 30-year base holds 14 values + 2 pads (-inf, already at the bottom):
     // its loads are unconditional and comparators touching the padded wires are left out.
-    // next day's rows exist for the same years when e+1 is still inside the year
-    const int64_t nd = (e >= 0 && e + 1 < L) ? ldx * 4 : 0;
     if (inside && tail >= K) {
-      load_sort_chunk<K, K>(p0, ystride, top, v, nv, nd);
+      load_sort_chunk<K, K>(p0, ystride, top, v, nv);
     } else if (K == 16 && inside && tail == 14) {
-      load_sort_chunk<K, (K == 16 ? 14 : K)>(p0, ystride, top, v, nv, nd);
+      load_sort_chunk<K, (K == 16 ? 14 : K)>(p0, ystride, top, v, nv);
     } else if (K == 16 && inside && tail == 15) {
-      load_sort_chunk<K, (K == 16 ? 15 : K)>(p0, ystride, top, v, nv, nd);
+      load_sort_chunk<K, (K == 16 ? 15 : K)>(p0, ystride, top, v, nv);
     } else {
       nv = 0;
 #pragma unroll
@@ -347,8 +420,8 @@ __device__ __forceinline__ float fold_thr(double t) {
 #ifndef XC_PCTL_MINBLOCKS
 #define XC_PCTL_MINBLOCKS 7
 #endif
-#ifndef XC_PCTL_PAIR_MINBLOCKS
-#define XC_PCTL_PAIR_MINBLOCKS 6
+#ifndef XC_PCTL_PAIR_MINBLOCKS   // with the staging buffer 4 CTAs fit an SM (51 KB each): 13.33 ms;
+#define XC_PCTL_PAIR_MINBLOCKS 4  // 6 (80 registers) gives 13.59 ms, no staging 13.65 ms
 #endif
 // COUNT_OP >= 0 fuses the percentile-threshold day count of the SAME series (tx90p with the base period
 // equal to the studied period, sub-case 3a of SURVEY.md section 8d): once P(d) is known the N values
@@ -506,6 +579,12 @@ percentile_doy_w5p_kernel(const float* __restrict__ x, int32_t T, int64_t C, int
   int nnew, nB = 0;
 #pragma unroll
   for (int k = 0; k < K; ++k) t[k] = 0.f;
+#if XC_PCTL_STAGE
+  Stager stager{reinterpret_cast<float*>(sn + 4 * kThreads) + lane, kNoDay, false};
+  Stager* sg = (K == 16 && !TABLE) ? &stager : nullptr;
+#else
+  Stager* sg = nullptr;
+#endif
   // The four warm-up iterations day = p0-4 .. p0-1 run the steady-state code without emitting:
   // they leave Y(p0-2), Y(p0) in the two odd slots, A(p0) = Y(p0-1) U Y(p0) in sA and Y(p0+1) in sE
   // (what they compute from the not-yet-written lists is overwritten before it is used).  No
@@ -513,7 +592,8 @@ percentile_doy_w5p_kernel(const float* __restrict__ x, int32_t T, int64_t C, int
   int s = 0;  // slot of Y(d-3)
 #pragma unroll 1
   for (int day = p0 - 4; day < p1; ++day) {
-    load_day_list<K, TABLE>(x, c, ldx, T, L, N, day + 2, top, ynew, nnew, pos, n_doy);
+    if (sg) sg->want_next = (day + 1 < p1);
+    load_day_list<K, TABLE>(x, c, ldx, T, L, N, day + 2, top, ynew, nnew, pos, n_doy, sg);
     int n;
     if (((day - p0) & 1) == 0) {
       // first day of the pair (day = d-1): ynew = Y(d+1)
@@ -805,8 +885,16 @@ int32_t launch_w5(const float* x, int64_t T, int64_t C, int64_t ldx, int32_t L, 
   per = (per + 1) & ~1;    // whole pairs of days
   if (per > nd) per = nd;
   chunks = (nd + per - 1) / per;
-  const size_t smem = (size_t)4 * (K + 1) * kThreads * 4;
+  // 4 lists + 4 counts per lane, plus the 32-row staging column of the cp.async prefetch
+  const size_t smem = (size_t)4 * (K + 1) * kThreads * 4 + (XC_PCTL_STAGE && K == 16 && !pos ? (size_t)32 * kThreads * 4 : 0);
   dim3 grid((unsigned)cblocks, (unsigned)chunks, 1);
+  if (smem > 48 * 1024) {
+    cudaError_t e = pos ? cudaFuncSetAttribute(percentile_doy_w5p_kernel<K, true>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : cudaFuncSetAttribute(percentile_doy_w5p_kernel<K, false>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(percentile_doy_w5p_kernel)");
+  }
   if (pos)
     percentile_doy_w5p_kernel<K, true><<<grid, kThreads, smem, st>>>(x, (int32_t)T, C, ldx, L, N, spec, per, out, pos,
                                                                      n_doy, d_begin, d_end);
