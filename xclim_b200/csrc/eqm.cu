@@ -248,17 +248,24 @@ template <int INTERP, int KIND>
 __global__ void __launch_bounds__(kAdjThreads)
 eqm_adjust_kernel(const float* __restrict__ sim, int64_t T, int64_t C, int64_t ldx, const float* __restrict__ af,
                   const float* __restrict__ hist_q, int32_t nq, int32_t rows_per_block, float* __restrict__ scen) {
-  extern __shared__ float tab[];  // [2][nq][kAdjThreads]: hist_q then af, column = lane
+  extern __shared__ float tab[];  // [3][nq][kAdjThreads]: hist_q, af, slope of the segment ending at j; column = lane
   float* hq = tab;
   float* fa = tab + (size_t)nq * kAdjThreads;
+  float* sl = fa + (size_t)nq * kAdjThreads;
   const int lane = threadIdx.x;
   const int64_t c = (int64_t)blockIdx.x * kAdjThreads + lane;
   if (c >= C) return;
   bool bad = false;
+  float hp = 0.f, ap = 0.f;
   for (int j = 0; j < nq; ++j) {
     const float h = hist_q[(int64_t)j * C + c], a = af[(int64_t)j * C + c];
     hq[j * kAdjThreads + lane] = h;
     fa[j * kAdjThreads + lane] = a;
+    // the division of the linear interpolation is done once per segment instead of once per element
+    // (same operands, same rounding: the results are bit-identical)
+    sl[j * kAdjThreads + lane] = (j > 0) ? __fdiv_rn(__fsub_rn(a, ap), __fsub_rn(h, hp)) : 0.f;
+    hp = h;
+    ap = a;
     bad = bad || (h != h) || (a != a);
   }
   const int64_t t0 = (int64_t)blockIdx.y * rows_per_block;
@@ -279,17 +286,18 @@ eqm_adjust_kernel(const float* __restrict__ sim, int64_t T, int64_t C, int64_t l
       idx = (probe <= nq && hv < x) ? probe : idx;
     }
     idx = max(1, min(idx, nq - 1));
-    const float x0 = hq[(idx - 1) * kAdjThreads + lane], x1 = hq[idx * kAdjThreads + lane];
-    const float y0 = fa[(idx - 1) * kAdjThreads + lane], y1 = fa[idx * kAdjThreads + lane];
+    const float x0 = hq[(idx - 1) * kAdjThreads + lane];
+    const float y0 = fa[(idx - 1) * kAdjThreads + lane];
     if (INTERP == 1) {
-      const float slope = __fdiv_rn(__fsub_rn(y1, y0), __fsub_rn(x1, x0));
+      const float slope = sl[idx * kAdjThreads + lane];
       return __fadd_rn(__fmul_rn(slope, __fsub_rn(x, x0)), y0);
     }
     // nearest: boundaries at the mid-points, ties go to the lower node
+    const float x1 = hq[idx * kAdjThreads + lane], y1 = fa[idx * kAdjThreads + lane];
     const float mid = __fmul_rn(__fadd_rn(x0, x1), 0.5f);
     return (x <= mid) ? y0 : y1;
   };
-  constexpr int U = 4;  // rows in flight per lane
+  constexpr int U = 8;  // rows in flight per lane
   int64_t t = t0;
   for (; t + U <= t1; t += U) {
     float xv[U], fv[U];
@@ -371,7 +379,7 @@ extern "C" int32_t xc_eqm_adjust_f32(const float* sim, int64_t T, int64_t C, int
   int rows = (int)((T + tchunks - 1) / tchunks);
   if (rows < 64) rows = 64;
   tchunks = (int)((T + rows - 1) / rows);
-  const size_t smem = (size_t)2 * nq * kAdjThreads * 4;
+  const size_t smem = (size_t)3 * nq * kAdjThreads * 4;
   dim3 grid((unsigned)cblocks, (unsigned)tchunks, 1);
 #define XC_ADJ(I, K)                                                                                               \
   do {                                                                                                             \
