@@ -223,8 +223,9 @@ int32_t xc_spell_sum_interval(int32_t op, double thr, int32_t window, int32_t wi
  *   out: (n_per, n_doy, C) float64 (device), i.e. the reference's (lat, lon, dayofyear,
  *   percentiles) table stored doy-major so that it is coalesced along cells.  The 366 -> 1..366
  *   re-interpolation of core/calendar.py:484-485 is xc_doy_interp_f64 (separate, tiny).
- *   Percentiles whose order statistics lie more than 64 ranks from both ends of the sample are
- *   rejected with XC_ERR_UNSUPPORTED.
+ *   Percentiles whose order statistics lie more than 64 ranks from both ends of the sample (the
+ *   median of 30 x 5 values ...) run through a slower exact selection kernel (samples of up to
+ *   768 values per day; larger ones are rejected with XC_ERR_UNSUPPORTED).
  *   workspace: device scratch of xc_percentile_doy_workspace_bytes() bytes.
  * ------------------------------------------------------------------------------------------- */
 int64_t xc_percentile_doy_workspace_bytes(int64_t T, int64_t C, int32_t n_doy, int32_t n_years,

@@ -179,3 +179,28 @@ def test_fused_percentile_and_count(cuda, per, op):
     np.testing.assert_array_equal(table.cpu().numpy(), tab_o)
     np.testing.assert_array_equal(cnt.cpu().numpy(), O.doy_threshold_count(x, tab_o, doy.astype(int), poff, op))
     np.testing.assert_array_equal(valid.cpu().numpy(), np.stack([(~np.isnan(x[s:e])).sum(0) for s, e in zip(poff[:-1], poff[1:])]))
+
+
+@pytest.mark.parametrize("calendar,years,window", [("noleap", 30, 5), ("standard", 20, 9), ("360_day", 40, 5)])
+def test_percentile_doy_mid_percentiles_selection_kernel(cuda, calendar, years, window):
+    """Percentiles whose order statistics are more than 64 ranks from both ends of the sample (the
+    median of 150 values ...) go through the selection kernel; a list of percentiles mixes it with the
+    network kernels.  Heavy ties, NaNs, an all-NaN cell and a single-value cell included."""
+    from xclim_b200 import calendar as xcal
+    rng = np.random.default_rng(13)
+    L = {"noleap": 365, "standard": 365.25, "360_day": 360}[calendar]
+    T = int(years * L)
+    x = _tas(rng, T, (3, 5), nan_frac=0.02)
+    x[:, 0, 0] = np.nan
+    x[:, 0, 1] = np.round(x[:, 0, 1])            # ties
+    x[:, 0, 2] = np.where(rng.random(T) < 0.5, 0.0, -0.0).astype(np.float32)  # signed zeros only
+    x[:, 1, 0] = np.nan
+    x[100, 1, 0] = 7.0                            # one valid value in the whole series
+    da = make_field(x, "1981-01-01", calendar=calendar, units="K")
+    pers = [50.0, 10.0, 42.0, 90.0, 58.5]
+    got = xcal.percentile_doy(da, window=window, per=pers)
+    exp = O.percentile_doy(x, da.time.year, da.time.doy, window, pers)       # (n_doy, n_per, *space)
+    g = np.moveaxis(got.values, (-2, -1), (0, 1))
+    assert g.shape == exp.shape
+    np.testing.assert_allclose(g, exp, rtol=RTOL, equal_nan=True)
+    np.testing.assert_array_equal(g, exp)

@@ -90,6 +90,87 @@ percentile_doy_generic_kernel(const float* __restrict__ x, int64_t T, int64_t C,
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// selection kernel: percentiles whose order statistics lie more than 64 ranks from both ends of the
+// sample (e.g. the median of 30 x 5 values).  A lane owns one cell: the non-NaN values of the day's
+// sample go to the lane's shared-memory column as order-preserving integer keys, the k-th smallest
+// is built bit by bit (v = max{t : #{key < t} <= k}, 32 counting passes), its successor is the
+// smallest key above it unless ties already cover rank k+1.  Exact for any sample that fits shared
+// memory (n_years * window <= 768); ~30x the cost of the network kernels, used only when needed.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSelThreads = 64;
+
+__device__ __forceinline__ uint32_t order_key(float v) {
+  const uint32_t b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_value(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+percentile_doy_select_kernel(const float* __restrict__ x, int64_t T, int64_t C, int64_t ldx,
+                             const int32_t* __restrict__ pos, int32_t n_doy, int32_t n_years, int32_t h,
+                             QuantSpec spec, int32_t doys_per_chunk, double* __restrict__ out,
+                             const int32_t* __restrict__ vrow) {
+  extern __shared__ uint32_t keys[];  // [n_years * (2h+1)][kSelThreads]
+  const int lane = threadIdx.x;
+  const int64_t c = (int64_t)blockIdx.x * kSelThreads + lane;
+  if (c >= C) return;
+  const int d0 = blockIdx.y * doys_per_chunk;
+  const int d1 = min(n_doy, d0 + doys_per_chunk);
+  const float* col = x + c;
+  uint32_t* mine = keys + lane;
+  for (int d = d0; d < d1; ++d) {
+    int n = 0;
+    for (int y = 0; y < n_years; ++y) {
+      const int i = pos[y * n_doy + d];
+      if (i < 0) continue;
+      const int j0 = max(0, i - h), j1 = min((int)T - 1, i + h);
+      for (int j = j0; j <= j1; ++j) {
+        const int row = vrow ? vrow[j] : j;
+        if (row < 0) continue;
+        const float v = __ldg(col + (int64_t)row * ldx);
+        if (v == v) mine[(n++) * kSelThreads] = order_key(v);
+      }
+    }
+    double res;
+    if (n == 0) {
+      res = __longlong_as_double(0x7ff8000000000000LL);
+    } else {
+      const QuantIdx qi = quant_index(n, spec);
+      // rank of the left neighbour: clamps of core/utils.py:417-461 (vi >= n-1 -> max, vi < 0 -> min)
+      int k = qi.ilo;
+      bool single = (n == 1);
+      if (n > 1 && qi.vi >= (double)n - 1.0) { k = n - 1; single = true; }
+      if (n > 1 && qi.vi < 0.0) { k = 0; single = true; }
+      if (n == 1) k = 0;
+      uint32_t v = 0u;
+      for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t t = v | (1u << bit);
+        int cnt = 0;
+        for (int i = 0; i < n; ++i) cnt += (mine[i * kSelThreads] < t) ? 1 : 0;
+        v = (cnt <= k) ? t : v;
+      }
+      const float left = key_value(v);
+      if (single) {
+        res = (double)left;
+      } else {
+        int le = 0;
+        uint32_t nxt = 0xffffffffu;
+        for (int i = 0; i < n; ++i) {
+          const uint32_t q = mine[i * kSelThreads];
+          le += (q <= v) ? 1 : 0;
+          nxt = (q > v && q < nxt) ? q : nxt;
+        }
+        const float right = (le >= k + 2) ? left : key_value(nxt);
+        res = quant_lerp(left, right, qi);
+      }
+    }
+    out[(int64_t)d * C + c] = res;
+  }
+}
+
 #ifndef XC_PCTL_VARIANT
 #define XC_PCTL_VARIANT 0
 #endif
@@ -975,12 +1056,45 @@ static int32_t percentile_doy_impl(const float* x, int64_t T, int64_t C, int64_t
     XC_REQUIRE(per >= 0.0 && per <= 100.0, "percentiles must be in [0, 100], got %g", per);
     QuantSpec spec;
     const int need = plan_quantile(per, alpha, beta, n_years * window, &spec);
-    if (need < 0 || need > 64) {
-      set_error("percentile %g of up to %d samples needs %d order statistics per cell; at most 64 are kept in "
-                "registers", per, n_years * window, need);
+    if (need < 0) {
+      set_error("percentile %g with alpha=%g beta=%g: plotting positions outside [0, 1] are not supported", per,
+                alpha, beta);
       return XC_ERR_UNSUPPORTED;
     }
     double* o = out + (int64_t)ip * n_doy * C;
+    if (need > 64) {
+      // order statistics far from both ends of the sample (e.g. the median): selection kernel
+      const int nmax = n_years * window;
+      if (nmax > 768) {
+        set_error("percentile %g of up to %d samples: the selection kernel holds at most 768 samples per cell", per,
+                  nmax);
+        return XC_ERR_UNSUPPORTED;
+      }
+      if (pos_d == nullptr) {
+        const int64_t nbytes = (int64_t)pos.size() * 4;
+        XC_REQUIRE(workspace != nullptr && workspace_bytes >= nbytes, "workspace too small: need %lld bytes",
+                   (long long)nbytes);
+        pos_d = (int32_t*)workspace;
+        posrow_d = pos_d;
+        XC_CHECK_CUDA(cudaMemcpyAsync(pos_d, pos.data(), (size_t)nbytes, cudaMemcpyHostToDevice, st));
+        XC_CHECK_CUDA(cudaStreamSynchronize(st));
+      }
+      const size_t smem = (size_t)nmax * kSelThreads * 4;
+      if (smem > 48 * 1024)
+        XC_CHECK_CUDA(cudaFuncSetAttribute(percentile_doy_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+      const int64_t cblocks = (C + kSelThreads - 1) / kSelThreads;
+      int chunks = (int)((148 * 8 + cblocks - 1) / cblocks);
+      chunks = chunks < 1 ? 1 : (chunks > n_doy ? n_doy : chunks);
+      const int per_chunk = (n_doy + chunks - 1) / chunks;
+      chunks = (n_doy + per_chunk - 1) / per_chunk;
+      dim3 grid((unsigned)cblocks, (unsigned)chunks, 1);
+      percentile_doy_select_kernel<<<grid, kSelThreads, smem, st>>>(x, T, C, ldx, pos_d, n_doy, n_years, h, spec,
+                                                                    per_chunk, o, vrow_d);
+      const int32_t es = launch_status("percentile_doy_select_kernel");
+      if (es) return es;
+      continue;
+    }
     const int kk = need <= 8 ? 8 : need <= 16 ? 16 : 32;
     const size_t smem_need = (size_t)(window - 1) * (kk + 1) * kThreads * 4;
     const bool fast_ok = window >= 3 && need <= 32 && smem_need <= 200 * 1024 && (L_int - 2 * h) >= 8;
