@@ -46,7 +46,7 @@ def main():
     ap.add_argument("--only", default="")
     ap.add_argument("--warmup", type=int, default=2, help="untimed launches per kernel (0 for ncu captures)")
     ap.add_argument("--cpu", action="store_true", help="time the oracle port of every index on a cell sample")
-    ap.add_argument("--cpu-cells", type=int, default=256)
+    ap.add_argument("--cpu-cells", type=int, default=1024)
     a = ap.parse_args()
     global WARMUP
     WARMUP = a.warmup

@@ -156,9 +156,15 @@ def test_doy_count_year_blocked_kernel_exact_ties(cuda, op):
     exp = O.threshold_count(x, op, tab[doy - 1], poff)
     np.testing.assert_array_equal(got.cpu().numpy(), exp)
     np.testing.assert_array_equal(valid.cpu().numpy(), np.stack([(~np.isnan(x[s:e])).sum(0) for s, e in zip(poff[:-1], poff[1:])]))
-    # generic kernel on the same data (odd number of cells forces it)
+    # generic kernel on the same data (odd number of cells forces the 2-cell float64-compare kernel)
     got2, _ = device.doy_threshold_count(xd[:, :63].contiguous(), poff, doy, td[:, :63].contiguous(), _lib.OPS[op])
     np.testing.assert_array_equal(got2.cpu().numpy(), exp[:, :63])
+    # monthly periods on 64 cells: the 4-cell generic kernel with folded thresholds
+    month = np.concatenate([[0], np.cumsum(np.tile([31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31], N))]).astype(np.int32)
+    got3, valid3 = device.doy_threshold_count(xd, month, doy, td, _lib.OPS[op], want_valid=True)
+    np.testing.assert_array_equal(got3.cpu().numpy(), O.threshold_count(x, op, tab[doy - 1], month))
+    np.testing.assert_array_equal(valid3.cpu().numpy(),
+                                  np.stack([(~np.isnan(x[s:e])).sum(0) for s, e in zip(month[:-1], month[1:])]))
 
 
 @pytest.mark.parametrize("per,op", [(90.0, ">"), (90.0, ">="), (10.0, "<")])

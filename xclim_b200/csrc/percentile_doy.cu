@@ -823,6 +823,58 @@ doy_count_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, const int3
   }
 }
 
+// Generic periods / calendars, 4 cells per thread: the float64 table entry of (doy[t], cell) is
+// folded to the float32 threshold with the same truth table (directed rounding, fold_thr) so that
+// the element test is one float32 compare; 4 steps (16 B of data + 32 B of table per thread each)
+// are in flight before any use.  The table rows are shared through L2 by the blocks of the same
+// cell range (blockIdx.x = period is the fastest index).  Operators >, <, >=, <= only.
+template <int OP, bool VALID>
+__global__ void __launch_bounds__(kThreads)
+doy_count4_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, const int32_t* __restrict__ poff,
+                  const int16_t* __restrict__ doy, const double* __restrict__ table,
+                  int32_t* __restrict__ out, int32_t* __restrict__ valid) {
+  const int p = blockIdx.x;
+  const int64_t c = ((int64_t)blockIdx.y * kThreads + threadIdx.x) * 4;
+  if (c >= C) return;
+  const int t0 = poff[p], t1 = poff[p + 1];
+  int32_t cn[4] = {0, 0, 0, 0}, vn[4] = {0, 0, 0, 0};
+  const float* col = x + c;
+  const double* trow = table + c;
+  constexpr int U = 4;
+  auto tally = [&](const float4& v, const double2& ta, const double2& tb) {
+    const float thr[4] = {fold_thr<OP>(ta.x), fold_thr<OP>(ta.y), fold_thr<OP>(tb.x), fold_thr<OP>(tb.y)};
+    const float xv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      cn[i] += cmp<OP>(xv[i], thr[i]) ? 1 : 0;
+      if constexpr (VALID) vn[i] += (xv[i] == xv[i]) ? 1 : 0;
+    }
+  };
+  int t = t0;
+  for (; t + U <= t1; t += U) {
+    float4 v[U];
+    double2 ta[U], tb[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int d = doy[t + u] - 1;
+      v[u] = ld_stream4(col + (int64_t)(t + u) * ldx);
+      ta[u] = *reinterpret_cast<const double2*>(trow + (int64_t)d * C);
+      tb[u] = *reinterpret_cast<const double2*>(trow + (int64_t)d * C + 2);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) tally(v[u], ta[u], tb[u]);
+  }
+  for (; t < t1; ++t) {
+    const int d = doy[t] - 1;
+    const float4 v = ld_stream4(col + (int64_t)t * ldx);
+    const double2 ta = *reinterpret_cast<const double2*>(trow + (int64_t)d * C);
+    const double2 tb = *reinterpret_cast<const double2*>(trow + (int64_t)d * C + 2);
+    tally(v, ta, tb);
+  }
+  store_vec4(out + (int64_t)p * C + c, cn);
+  if constexpr (VALID) store_vec4(valid + (int64_t)p * C + c, vn);
+}
+
 // Year-blocked count for the common case "periods are whole years of equal length and the doy of a
 // step is its position in the year" (noleap / 360_day, freq YS): a thread owns 4 adjacent cells and
 // YB consecutive years, so every table row is fetched once per YB years instead of once per year
@@ -1230,6 +1282,29 @@ extern "C" int32_t xc_doy_threshold_count_f32(const float* x, int64_t T, int64_t
   XC_REQUIRE(T > 0 && C > 0 && ldx >= C && P > 0 && n_doy > 0, "bad shape");
   (void)n_doy;
   cudaStream_t st = (cudaStream_t)stream;
+  // 4 cells per thread with float32-folded thresholds when the layout allows 128-bit accesses and the
+  // operator is an inequality
+  const bool vec4 = (C % 4 == 0) && (ldx % 4 == 0) && aligned16(x) && aligned16(table) && aligned16(out_count) &&
+                    (valid_count == nullptr || aligned16(valid_count)) && op >= XC_OP_GT && op <= XC_OP_LE;
+  if (vec4) {
+    const int64_t cb4 = (C / 4 + kThreads - 1) / kThreads;
+    XC_REQUIRE(cb4 <= 65535, "too many cells for one launch: tile the grid by latitude");
+    dim3 grid4((unsigned)P, (unsigned)cb4, 1);
+    return dispatch_op(op, [&](auto OPC) -> int32_t {
+      constexpr int OP = decltype(OPC)::value;
+      if constexpr (OP == XC_OP_EQ || OP == XC_OP_NE) {
+        return XC_ERR_INVALID;  // unreachable: vec4 requires an inequality
+      } else {
+        if (valid_count)
+          doy_count4_kernel<OP, true><<<grid4, kThreads, 0, st>>>(x, C, ldx, period_offsets, doy_index, table,
+                                                                  out_count, valid_count);
+        else
+          doy_count4_kernel<OP, false><<<grid4, kThreads, 0, st>>>(x, C, ldx, period_offsets, doy_index, table,
+                                                                   out_count, valid_count);
+        return launch_status("doy_count4_kernel");
+      }
+    });
+  }
   const int64_t pairs = (C + 1) / 2;
   const int64_t cblocks = (pairs + kThreads - 1) / kThreads;
   XC_REQUIRE(cblocks <= 65535, "too many cells for one launch: tile the grid by latitude");
