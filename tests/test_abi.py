@@ -52,3 +52,47 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.XclimB200Error, match="no CPU fallback"):
         _lib.load()
+
+
+def test_argument_validation_happens_before_any_device_work(lib):
+    """Every entry point validates pointers / shapes / enums on the host and reports through the status
+    code + xc_last_error() (thread-local) without touching the GPU: checkable on a CPU-only box."""
+    import ctypes as C
+    from xclim_b200 import _lib
+    INVALID, UNSUPPORTED = -1, -2
+    buf = (C.c_float * 16)()
+    ibuf = (C.c_int32 * 16)()
+    p, ip = C.cast(buf, C.c_void_p), C.cast(ibuf, C.c_void_p)
+    # null pointers
+    assert lib.xc_period_count_f32(None, 4, 4, 4, ip, 1, 0, 0.0, 0, ip, None, None) == INVALID
+    assert b"null pointer" in lib.xc_last_error()
+    # ldx < C
+    assert lib.xc_period_count_f32(p, 4, 4, 2, ip, 1, 0, 0.0, 0, ip, None, None) == INVALID
+    assert b"shape" in lib.xc_last_error()
+    # unknown operator: the reference's message (indices/generic.py:285)
+    assert lib.xc_period_runstat_f32(p, 4, 4, 4, ip, 1, 17, 0.0, 0, 0, 1, 1, p, None, None) == INVALID
+    assert b"not recognized" in lib.xc_last_error()
+    # window < 1
+    assert lib.xc_period_runstat_f32(p, 4, 4, 4, ip, 1, 0, 0.0, 0, 0, 0, 1, p, None, None) == INVALID
+    # rolling: unknown window statistic, even centred window
+    assert lib.xc_rolling_period_reduce_f32(p, 4, 4, 4, ip, 1, 3, 99, 0, 0, p, None) == INVALID
+    assert lib.xc_rolling_period_reduce_f32(p, 8, 4, 4, ip, 1, 4, _lib.STATS["sum"], 1, 0, p, None) == UNSUPPORTED
+    assert b"even" in lib.xc_last_error()
+    # percentile_doy: even window is unsupported, percentile outside [0, 100] invalid
+    doy = (C.c_int16 * 4)(1, 2, 3, 4)
+    yr = (C.c_int16 * 4)(0, 0, 0, 0)
+    per = (C.c_double * 1)(90.0)
+    args = [p, 4, 4, 4, C.cast(doy, C.c_void_p), C.cast(yr, C.c_void_p), 4, 1]
+    assert lib.xc_percentile_doy_f32(*args, 4, C.cast(per, C.c_void_p), 1, 1 / 3, 1 / 3, p, p, 64, None) == UNSUPPORTED
+    bad = (C.c_double * 1)(101.0)
+    assert lib.xc_percentile_doy_f32(*args, 1, C.cast(bad, C.c_void_p), 1, 1 / 3, 1 / 3, p, p, 1024, None) == INVALID
+    assert b"[0, 100]" in lib.xc_last_error()
+    # eqm: too many quantiles / bad kind
+    assert lib.xc_eqm_train_f32(p, p, 4, 4, 4, 65, 0, p, p, None, 0, None) == INVALID
+    assert lib.xc_eqm_train_f32(p, p, 4, 4, 4, 20, 7, p, p, None, 0, None) == INVALID
+    # the error text is per thread: another thread sees its own (empty) message
+    import threading
+    seen = []
+    th = threading.Thread(target=lambda: seen.append(lib.xc_last_error()))
+    th.start(); th.join()
+    assert seen == [b""]
