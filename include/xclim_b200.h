@@ -111,6 +111,17 @@ int32_t xc_period_runstat_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
                               int32_t reducer, int32_t window, int32_t resample_before_rl,
                               float* out, int32_t* valid_count, void* stream);
 
+/* The same statistics (runs cut at period edges) on the mask with holes filled: spells separated
+ * by fewer than min_gap non-spell steps are merged -- generic.spell_mask(min_gap > 1)
+ * (indices/generic.py:537-538) = run_length.runs_with_holes(m, 1, ~m, min_gap)
+ * (indices/run_length.py:844-888), including its rule that a short gap running into the end of
+ * the series is bridged while a gap that starts the series is not.  window == 1 masks only. */
+int32_t xc_period_runstat_gap_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                  const int32_t* period_offsets, int32_t P,
+                                  int32_t op, double thr, int32_t cmp_f64,
+                                  int32_t reducer, int32_t window, int32_t min_gap,
+                                  float* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * a6 (bivariate)  run statistics / counts of a condition on two variables:
  *   cond = (x1 op1 thr1) AND|OR (x2 op2 thr2)  -> reducer over run lengths >= window per period.

@@ -377,9 +377,24 @@ def spell_mask(data, window, win_reducer, op, thresh, min_gap=1):
             iis = rs >= 1                                                        # :533
         iis = _shift(iis, -(window - 1), False)
         is_in_spell = iis[:T]                                                    # :535
-    if min_gap > 1:
-        raise NotImplementedError("min_gap > 1 (runs_with_holes) is outside the oracle's scope")
+    if min_gap > 1:                                                              # :537-538
+        is_in_spell = runs_with_holes(is_in_spell, 1, ~is_in_spell, min_gap).astype(bool)
     return is_in_spell
+
+
+def runs_with_holes(da_start, window_start, da_stop, window_stop):
+    """indices/run_length.py:844-888: 1 from the first step of a run of >= window_start True in
+    ``da_start`` until the first step of a run of >= window_stop True in ``da_stop``."""
+    a = np.asarray(da_start).astype(bool)
+    b = np.asarray(da_stop).astype(bool)
+    start_runs = cumsum_reset(a, index="first")                                   # :881
+    stop_runs = cumsum_reset(b, index="first")                                    # :882
+    start_positions = np.where(start_runs >= window_start, 1.0, np.nan)           # :883
+    stop_positions = np.where(stop_runs >= window_stop, 0.0, np.nan)              # :884
+    runs = np.where(np.isnan(stop_positions), start_positions, stop_positions)    # combine_first (:887)
+    for t in range(1, runs.shape[0]):                                             # ffill
+        runs[t] = np.where(np.isnan(runs[t]), runs[t - 1], runs[t])
+    return np.where(np.isnan(runs), 0.0, runs)                                    # fillna(0)
 
 
 def spell_length_statistics(data, threshold, window, win_reducer, op, spell_reducer, poff,

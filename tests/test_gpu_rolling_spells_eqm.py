@@ -149,3 +149,24 @@ def test_eqm_train_heavy_ties_and_degenerate(cuda):
     af_o, hq_o = O.eqm_train(ref, hist, 20, "+")
     np.testing.assert_allclose(hq.cpu().numpy(), hq_o, rtol=1e-5, atol=1e-7, equal_nan=True)
     np.testing.assert_allclose(af.cpu().numpy(), af_o, rtol=1e-4, atol=1e-6, equal_nan=True)
+
+
+@pytest.mark.parametrize("min_gap", [2, 3, 5])
+@pytest.mark.parametrize("op,thr", [("<", 1.0), (">=", 4.0)])
+def test_spell_length_statistics_min_gap(cuda, min_gap, op, thr):
+    """generic.spell_mask(min_gap > 1) = runs_with_holes (indices/run_length.py:844-888): short gaps are
+    bridged, a short gap running into the end of the series too, a gap that starts the series is not."""
+    from xclim_b200 import generic
+    rng = np.random.default_rng(44)
+    x = _pr(rng, 365 * 2 + 40, (3, 7))
+    x[:3, 0, 0] = 0.0; x[3, 0, 0] = 9.0           # series starts inside a short gap
+    x[-2:, 0, 1] = 0.0; x[-3, 0, 1] = 9.0          # series ends inside a short gap
+    da = make_field(x, "2001-01-01", units="mm/d")
+    for freq in ("YS", "MS"):
+        poff = da.time.period_offsets(freq)
+        for red in ("max", "sum", "count", "mean"):
+            got = generic.spell_length_statistics(da, thr, 1, None, op, red, freq, min_gap=min_gap)
+            exp = O.spell_length_statistics(x, thr, 1, None, op, red, poff, min_gap=min_gap)
+            np.testing.assert_array_equal(got.values, exp, err_msg=f"{min_gap} {op} {red} {freq}")
+    with pytest.raises(NotImplementedError):
+        generic.spell_length_statistics(da, thr, 3, "sum", op, "max", "YS", min_gap=2)

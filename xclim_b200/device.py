@@ -358,6 +358,18 @@ def mask_steps(x2d, keep):
     return out
 
 
+def period_runstat_gap(x2d, poff, op_code, thr, reducer_code, min_gap, window=1, cmp_f64=False):
+    """Run statistics per period of the mask with holes < min_gap filled (generic.spell_mask(min_gap))."""
+    T, C = x2d.shape
+    P = len(poff) - 1
+    poff_d = dev_ints(poff, np.int32, x2d.device)
+    out = torch.empty((P, C), dtype=torch.float32, device=x2d.device)
+    check(load().xc_period_runstat_gap_f32(x2d.data_ptr(), T, C, x2d.stride(0), poff_d.data_ptr(), P, op_code,
+                                           float(thr), int(bool(cmp_f64)), reducer_code, int(window), int(min_gap),
+                                           out.data_ptr(), current_stream_ptr()))
+    return out
+
+
 def period_run_quantile(x2d, poff, op_code, thr, q, window, resample_before_rl=True, cmp_f64=False):
     """Linear quantile ``q`` of the run lengths >= window per period (rle_statistics reducer "qNN")."""
     T, C = x2d.shape

@@ -139,8 +139,10 @@ def spell_length_statistics(data, threshold, window, win_reducer, op, spell_redu
     """
     if indexer:
         raise NotImplementedError("select_time indexers are outside the B200 hot path (SURVEY.md section 8f)")
-    if min_gap != 1:
-        raise NotImplementedError("min_gap > 1 is not supported by the B200 hot path yet")
+    if min_gap < 1:
+        raise ValueError("min_gap must be >= 1")
+    if min_gap > 1 and (window != 1 or not resample_before_rl):
+        raise NotImplementedError("min_gap > 1 is supported for window == 1 spells with resample_before_rl=True")
     code = get_op(op)
     thr = threshold_in_units_of(threshold, data) if isinstance(threshold, str) else _scalar_threshold(threshold)[0]
     reducers = [spell_reducer] if isinstance(spell_reducer, str) else list(spell_reducer)
@@ -150,7 +152,9 @@ def spell_length_statistics(data, threshold, window, win_reducer, op, spell_redu
     for sr in reducers:
         if sr not in _lib.RL_REDUCERS:
             raise NotImplementedError(f"spell reducer {sr!r} is not supported by the B200 hot path")
-        if window == 1:
+        if window == 1 and min_gap > 1:     # runs_with_holes (indices/generic.py:537-538)
+            out = device.period_runstat_gap(x2d, poff, code, thr, _lib.RL_REDUCERS[sr], min_gap)
+        elif window == 1:
             out, _ = device.period_runstat(x2d, poff, code, thr, _lib.RL_REDUCERS[sr], 1, resample_before_rl)
         else:
             from .spells import spell_runstat  # rolling-window spell masks
