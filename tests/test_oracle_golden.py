@@ -246,3 +246,25 @@ def test_known_answers_season_and_start():
     rel = [int(m) - int(s) if m >= 0 else None for m, s in zip(mids, poff[:-1])]   # index inside each group
     out = O.season(tas >= np.float32(278.15), 6, rel, poff, "length", ta.doy)
     assert out[ta.period_labels("YS-JUL").index("2000-07-01")] == 121
+
+
+def test_runs_with_holes_reference_known_answers():
+    """tests/test_run_length.py:135-162 (values only): window_stop == 1 reproduces the input runs;
+    stop runs of 3 bridge the one- and two-step gaps and keep the four-step gap."""
+    from oracle import xclim_oracle as O
+    values = np.zeros((365, 3))
+    values[1:11] = 1
+    np.testing.assert_array_equal(O.runs_with_holes(values != 0, 1, values == 0, 1), values)
+    v = np.zeros(365)
+    a = [0, 1, 0, 1, 1, 0, 0, 1, 1, 1, 1, 0, 0, 0, 0, 1, 1, 1, 1, 1, 0, 0, 0, 0]
+    v[:len(a)] = a
+    expected = v * 0
+    expected[1:11] = 1
+    expected[15:20] = 1
+    np.testing.assert_array_equal(O.runs_with_holes(v == 1, 1, v == 0, 3), expected)
+    # the same through spell_mask(min_gap=3) and the spell statistics (one period): runs of 10 and 5
+    x = np.where(v == 1, 0.0, 5.0).astype(np.float32)[:, None]
+    np.testing.assert_array_equal(O.spell_mask(x, 1, None, "<", 1.0, min_gap=3)[:, 0], expected.astype(bool))
+    poff = np.array([0, 365], dtype=np.int32)
+    assert O.spell_length_statistics(x, 1.0, 1, None, "<", "max", poff, min_gap=3)[0, 0] == 10
+    assert O.spell_length_statistics(x, 1.0, 1, None, "<", "count", poff, min_gap=3)[0, 0] == 2
