@@ -1,0 +1,151 @@
+"""TEST INFRASTRUCTURE: a CPU stand-in for ``xclim_b200.device`` built on the oracle.
+
+``install(monkeypatch)`` replaces the device-layer functions by numpy/oracle equivalents working
+on CPU torch tensors, so that the HOST layer (units, thresholds, operators, period offsets,
+wrapping, attrs, dtypes, option handling) can be exercised by the ``-m "not gpu"`` suite.  It proves
+nothing about the kernels -- those are checked by the ``-m gpu`` tests through the C ABI -- and
+nothing outside ``tests/`` may import it.
+"""
+import numpy as np
+import torch
+
+from oracle import xclim_oracle as O
+from xclim_b200 import _lib
+
+OP_NAME = {0: ">", 1: "<", 2: ">=", 3: "<=", 4: "==", 5: "!="}
+RED_NAME = {v: k for k, v in _lib.RL_REDUCERS.items()}
+STAT_NAME = {0: "sum", 1: "mean", 2: "min", 3: "max", 4: "std", 5: "var", 6: "count"}
+
+
+def _np(t):
+    return t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+
+def _cond(x, op_code, thr, cmp_f64=False):
+    if op_code == _lib.OP_ISNAN:
+        return np.isnan(x)
+    if op_code == _lib.OP_NOTNAN:
+        return ~np.isnan(x)
+    return O.compare(x, OP_NAME[op_code], np.float64(thr) if cmp_f64 else float(thr))
+
+
+def _valid(x, poff):
+    return torch.from_numpy(np.stack([(~np.isnan(x[s:e])).sum(0) for s, e in O._groups(poff)]).astype(np.int32))
+
+
+def to_time_cell(values, time_axis, device=None):
+    a = _np(values)
+    if time_axis != 0:
+        a = np.moveaxis(a, time_axis, 0)
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return torch.from_numpy(a.reshape(a.shape[0], -1)), tuple(a.shape[1:])
+
+
+def period_count(x2d, poff, op_code, thr, cmp_f64=False, want_valid=False):
+    x = _np(x2d)
+    out = np.stack([_cond(x[s:e], op_code, thr, cmp_f64).sum(0) for s, e in O._groups(poff)]).astype(np.int32)
+    return torch.from_numpy(out), (_valid(x, poff) if want_valid else None)
+
+
+def period_runstat(x2d, poff, op_code, thr, reducer_code, window, resample_before_rl=True, cmp_f64=False,
+                   want_valid=False):
+    x = _np(x2d)
+    out = O.resample_and_rl(_cond(x, op_code, thr, cmp_f64), bool(resample_before_rl), O.rle_statistics, poff=poff,
+                            reducer=RED_NAME[reducer_code], window=int(window))
+    return torch.from_numpy(np.asarray(out, dtype=np.float32)), (_valid(x, poff) if want_valid else None)
+
+
+def period_runstat_gap(x2d, poff, op_code, thr, reducer_code, min_gap, window=1, cmp_f64=False):
+    x = _np(x2d)
+    m = _cond(x, op_code, thr, cmp_f64)
+    filled = O.runs_with_holes(m, 1, ~m, int(min_gap)).astype(np.float32)
+    out = O.resample_and_rl(filled, True, O.rle_statistics, poff=poff, reducer=RED_NAME[reducer_code], window=window)
+    return torch.from_numpy(np.asarray(out, dtype=np.float32))
+
+
+def period_reduce(x2d, poff, stat_code, transform=0, op_code=0, thr=0.0, want_valid=False):
+    x = _np(x2d)
+    if transform == _lib.TF_EXCESS:
+        out = O.cumulative_difference(x, float(thr), OP_NAME[op_code], poff)
+    else:
+        y = x.astype(np.float64)
+        if transform == _lib.TF_WHERE:
+            y = np.where(_cond(x, op_code, thr), y, np.nan)
+        out = O.resample_reduce(y, poff, STAT_NAME[stat_code])
+    return torch.from_numpy(np.asarray(out, dtype=np.float32)), (_valid(x, poff) if want_valid else None)
+
+
+def rolling_period_reduce(x2d, poff, window, window_stat_code, center, stat_code):
+    out = O.select_rolling_resample_op(_np(x2d).astype(np.float64), STAT_NAME[stat_code], int(window), poff,
+                                       window_center=bool(center), window_op=STAT_NAME[window_stat_code])
+    return torch.from_numpy(np.asarray(out, dtype=np.float32))
+
+
+def spell_runstat(x2d, poff, window, window_stat_code, op_code, thr, reducer_code, resample_before_rl=True):
+    out = O.spell_length_statistics(_np(x2d), float(thr), int(window), STAT_NAME[window_stat_code], OP_NAME[op_code],
+                                    RED_NAME[reducer_code], poff, resample_before_rl=bool(resample_before_rl))
+    return torch.from_numpy(np.asarray(out, dtype=np.float32))
+
+
+def period_run_maxsum(x2d, poff, op_code, thr, window, resample_before_rl=True):
+    x = _np(x2d)
+    t32 = np.float32(thr)
+    excess = np.where(np.isnan(x), 0, np.clip((x - t32) if op_code in (0, 2) else (t32 - x), 0, None)).astype(np.float64)
+    out = O.resample_and_rl(excess, bool(resample_before_rl), O.windowed_max_run_sum, int(window), poff=poff)
+    return torch.from_numpy(np.asarray(out, dtype=np.float32))
+
+
+def period_runstat2(x1, x2, poff, op1, thr1, op2, thr2, reducer_code, window, resample_before_rl=True, var_any=False):
+    c1, c2 = _cond(_np(x1), op1, thr1), _cond(_np(x2), op2, thr2)
+    m = (c1 | c2) if var_any else (c1 & c2)
+    out = O.resample_and_rl(m, bool(resample_before_rl), O.rle_statistics, poff=poff, reducer=RED_NAME[reducer_code],
+                            window=int(window))
+    return torch.from_numpy(np.asarray(out, dtype=np.float32))
+
+
+def percentile_doy(x2d, doy_index, year_index, n_doy, n_years, window, percentiles, alpha, beta, force_generic=False,
+                   vrow=None):
+    x = _np(x2d)
+    if vrow is not None:
+        vr = np.asarray(vrow)
+        x = np.where((vr >= 0)[:, None], x[np.maximum(vr, 0)], np.nan).astype(np.float32)
+    T, C = x.shape
+    year, doy = np.asarray(year_index), np.asarray(doy_index)
+    rr = O.rolling_construct_center(x, int(window))
+    rrr = np.full((n_doy, n_years * window, C), np.nan, dtype=rr.dtype)
+    for t in range(T):
+        rrr[doy[t] - 1, year[t] * window:(year[t] + 1) * window] = rr[t]
+    per = np.atleast_1d(np.asarray(percentiles, dtype=np.float64))
+    out = np.stack([O.nan_quantile(rrr[d], per / 100.0, alpha, beta) for d in range(n_doy)])  # (n_doy, n_per, C)
+    return torch.from_numpy(np.ascontiguousarray(np.moveaxis(out, 1, 0)))
+
+
+def doy_interp(table2d, doy_min, doy_max):
+    return torch.from_numpy(np.ascontiguousarray(O.interpolate_doy_calendar(_np(table2d), int(doy_max), int(doy_min))))
+
+
+def doy_threshold_count(x2d, poff, doy_index, table2d, op_code, want_valid=False):
+    x = _np(x2d)
+    out = O.threshold_count(x, OP_NAME[op_code], _np(table2d)[np.asarray(doy_index) - 1], poff)
+    return torch.from_numpy(np.asarray(out, dtype=np.int32)), (_valid(x, poff) if want_valid else None)
+
+
+def mask_steps(x2d, keep):
+    x = _np(x2d).copy()
+    x[~np.asarray(keep, dtype=bool)] = np.nan
+    return torch.from_numpy(x)
+
+
+def dev_ints(arr, dtype, device):
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(arr, dtype=dtype)))
+
+
+FUNCTIONS = [to_time_cell, period_count, period_runstat, period_runstat_gap, period_reduce, rolling_period_reduce,
+             spell_runstat, period_run_maxsum, period_runstat2, percentile_doy, doy_interp, doy_threshold_count,
+             mask_steps, dev_ints]
+
+
+def install(monkeypatch):
+    from xclim_b200 import device
+    for fn in FUNCTIONS:
+        monkeypatch.setattr(device, fn.__name__, fn)
