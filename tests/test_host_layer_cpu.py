@@ -81,3 +81,41 @@ def test_bootstrap_unequal_blocks_host_loop(host):
                                 per=90.0, op=">", cal_max_doy=366)
     np.testing.assert_array_equal(got.values, exp)
     assert got.values.dtype == np.float64 and got.attrs["units"] == "d"
+
+
+def test_more_index_entry_points(host):
+    """Thin entry points added over the existing kernels: oracle compositions of the reference bodies."""
+    from xclim_b200 import indices
+    data = batch._inputs()
+    K0 = 273.15
+    mk = lambda k, u: make_field(data[k], "1981-01-01", calendar="noleap", units=u)  # noqa: E731
+    pr, tx, tn = mk("pr", "mm/d"), mk("tasmax", "K"), mk("tasmin", "K")
+    poff = pr.time.period_offsets("YS")
+    # wet spells (indices/_threshold.py:3596-3733)
+    np.testing.assert_array_equal(indices.wet_spell_total_length(pr).values,
+                                  O.spell_length_statistics(data["pr"], 1.0, 3, "sum", ">=", "sum", poff))
+    np.testing.assert_array_equal(indices.wet_spell_max_length(pr).values,
+                                  O.spell_length_statistics(data["pr"], 1.0, 1, "sum", ">=", "max", poff))
+    # warm days / nights (:2674-2745): thresholds in degC against data in K
+    np.testing.assert_array_equal(indices.warm_day_frequency(tx).values,
+                                  O.threshold_count(data["tasmax"], ">", 30 + K0, poff))
+    np.testing.assert_array_equal(indices.warm_night_frequency(tn, thresh="5 degC").values,
+                                  O.threshold_count(data["tasmin"], ">", 5 + K0, poff))
+    # extreme temperature range (_multivariate.py:601-637)
+    etr = indices.extreme_temperature_range(tn, tx, freq="MS")
+    pm = pr.time.period_offsets("MS")
+    exp = O.select_resample_op(data["tasmax"].astype(np.float64), "max", pm) - \
+        O.select_resample_op(data["tasmin"].astype(np.float64), "min", pm)
+    np.testing.assert_allclose(etr.values, exp, rtol=1e-6, equal_nan=True)
+    assert etr.attrs["units"] == "K" and etr.attrs["units_metadata"] == "temperature: difference"
+    # days with snow (_threshold.py:1817-1860): low < prsn <= high
+    prsn = make_field((data["pr"] / 86400.0).astype(np.float32), "1981-01-01", calendar="noleap", units="kg m-2 s-1")
+    got = indices.days_with_snow(prsn, low="1e-5 kg m-2 s-1", high="1e-4 kg m-2 s-1")
+    x = prsn.values
+    pj = prsn.time.period_offsets("YS-JUL")
+    exp = np.stack([((x[s:e] > np.float32(1e-5)) & (x[s:e] <= np.float32(1e-4))).sum(0) for s, e in zip(pj[:-1], pj[1:])])
+    np.testing.assert_array_equal(got.values, exp)
+    assert got.attrs["units"] == "d"
+    # wind maxima
+    w = make_field(np.abs(data["tas"] - 270).astype(np.float32), "1981-01-01", calendar="noleap", units="m s-1")
+    np.testing.assert_allclose(indices.sfcWindmax_max(w).values, O.select_resample_op(w.values.astype(np.float64), "max", poff))

@@ -141,6 +141,18 @@ def wet_spell_frequency(pr, thresh="1.0 mm", window=3, freq="YS", resample_befor
                           "count", freq, resample_before_rl)
 
 
+def wet_spell_total_length(pr, thresh="1.0 mm", window=3, op="sum", freq="YS", resample_before_rl=True):
+    """indices/_threshold.py:3596-3663."""
+    return _dry_wet_spell(pr, thresh.replace(" mm", " mm/d") if isinstance(thresh, str) else thresh, window, ">=", op,
+                          "sum", freq, resample_before_rl)
+
+
+def wet_spell_max_length(pr, thresh="1.0 mm", window=1, op="sum", freq="YS", resample_before_rl=True):
+    """indices/_threshold.py:3667-3733."""
+    return _dry_wet_spell(pr, thresh.replace(" mm", " mm/d") if isinstance(thresh, str) else thresh, window, ">=", op,
+                          "max", freq, resample_before_rl)
+
+
 def hot_spell_max_magnitude(tasmax, thresh="25.0 degC", window=3, freq="YS", resample_before_rl=True):
     """Largest cumulated exceedance of a hot spell -- indices/_threshold.py:2019-2073; the
     ``(tasmax - thresh).clip(0)`` array of the reference is never built."""
@@ -243,7 +255,55 @@ def sfcWind_min(sfcWind, freq="YS"):
     return _resample(sfcWind, "min", freq)
 
 
+def sfcWindmax_max(sfcWindmax, freq="YS"):  # noqa: N802
+    """indices/_simple.py:720-753."""
+    return _resample(sfcWindmax, "max", freq)
+
+
+def sfcWindmax_mean(sfcWindmax, freq="YS"):  # noqa: N802
+    """indices/_simple.py:757-790."""
+    return _resample(sfcWindmax, "mean", freq)
+
+
+def sfcWindmax_min(sfcWindmax, freq="YS"):  # noqa: N802
+    """indices/_simple.py:794-826."""
+    return _resample(sfcWindmax, "min", freq)
+
+
+def extreme_temperature_range(tasmin, tasmax, freq="YS"):
+    """max(tasmax) - min(tasmin) per period -- indices/_multivariate.py:601-637 (both inputs in the same
+    units; the result is a temperature difference)."""
+    from .field import Field, attrs_of, is_xarray
+    from .units import units_of
+    if units_of(tasmax) != units_of(tasmin):
+        raise NotImplementedError("extreme_temperature_range: give tasmax and tasmin in the same units")
+    hi, lo = _resample(tasmax, "max", freq), _resample(tasmin, "min", freq)
+    out = hi.values - lo.values            # numpy arrays or CUDA tensors
+    u = attrs_of(tasmax).get("units", "")
+    attrs = {**attrs_of(hi), "units": {"degC": "K", "°C": "K", "C": "K"}.get(u, u), "units_metadata": "temperature: difference"}
+    if is_xarray(hi):
+        return hi.copy(data=out).assign_attrs(**attrs)
+    return Field(out, hi.dims, hi.time, dict(hi.coords), attrs, hi.name)
+
+
 # ---- threshold counts (indices/_simple.py:334-444, _threshold.py:122-155, 2422-2632, 3135-3167)
+def warm_day_frequency(tasmax, thresh="30 degC", freq="YS", op=">"):
+    """indices/_threshold.py:2674-2712."""
+    return _count(tasmax, thresh, op, freq, (">", ">="))
+
+
+def warm_night_frequency(tasmin, thresh="22 degC", freq="YS", op=">"):
+    """indices/_threshold.py:2716-2745."""
+    return _count(tasmin, thresh, op, freq, (">", ">="))
+
+
+def days_with_snow(prsn, low="0 kg m-2 s-1", high="1E6 kg m-2 s-1", freq="YS-JUL"):
+    """Days with ``low < prsn <= high`` -- indices/_threshold.py:1817-1860 (``domain_count``)."""
+    lo = threshold_in_units_of(low, prsn) if isinstance(low, str) else float(low)
+    hi = threshold_in_units_of(high, prsn) if isinstance(high, str) else float(high)
+    return generic.domain_count(prsn, lo, hi, freq).assign_attrs(units="d")
+
+
 def frost_days(tasmin, thresh="0 degC", freq="YS"):
     return _count(tasmin, thresh, "<", freq, ("<", "<="))
 
