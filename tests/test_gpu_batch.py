@@ -160,3 +160,4 @@ def test_more_index_entry_points_on_device(cuda):
     real kernels instead of the oracle stand-ins."""
     import test_host_layer_cpu as cpu_side
     cpu_side.test_more_index_entry_points(None)
+    cpu_side.test_days_over_precip_thresh(None)

@@ -119,3 +119,25 @@ def test_more_index_entry_points(host):
     # wind maxima
     w = make_field(np.abs(data["tas"] - 270).astype(np.float32), "1981-01-01", calendar="noleap", units="m s-1")
     np.testing.assert_allclose(indices.sfcWindmax_max(w).values, O.select_resample_op(w.values.astype(np.float64), "max", poff))
+
+
+def test_days_over_precip_thresh(host):
+    """indices/_multivariate.py:1223-1233: the per-doy percentile clamped from below by the wet-day
+    threshold, then the doy-threshold count."""
+    from xclim_b200 import calendar as xcal, indices
+    rng = np.random.default_rng(7)
+    pr = rng.gamma(0.4, 6.0, size=(365 * 4, 2, 3)).astype(np.float32)
+    pr[rng.random(pr.shape) < 0.5] = 0
+    pr[rng.random(pr.shape) < 0.01] = np.nan
+    da = make_field(pr, "1981-01-01", calendar="noleap", units="mm/d")
+    per = xcal.select_percentile(xcal.percentile_doy(da, window=5, per=75.0), 75.0)
+    tab = O.percentile_doy(pr, da.time.year, da.time.doy, 5, 75.0)[:, 0]
+    for freq in ("YS", "MS"):
+        poff = da.time.period_offsets(freq)
+        got = indices.days_over_precip_thresh(da, per, thresh="1 mm/day", freq=freq)
+        tp = np.where(tab > 1.0, tab, 1.0)
+        exp = O.doy_threshold_count(pr, tp, da.time.doy, poff, ">")
+        np.testing.assert_array_equal(got.values, exp)
+        assert got.values.dtype == np.int64 and got.attrs["units"] == "d"
+    # the clamp matters: many doy percentiles of this dry series are below 1 mm/d
+    assert (tab < 1.0).any() and (tab > 1.0).any()

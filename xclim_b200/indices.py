@@ -65,6 +65,32 @@ def _percentile_day_count(da, per, freq, bootstrap, op, constrain):
     return _wrap_periods(da, out, cell_shape, other, ta, freq, attrs, dtype=np.int64)
 
 
+def days_over_precip_thresh(pr, pr_per, thresh="1 mm/day", freq="YS", bootstrap=False, op=">"):
+    """Days with precipitation over both a doy percentile and a wet-day threshold (ETCCDI R95p-days) --
+    indices/_multivariate.py:1176-1233: ``tp = pr_per.where(pr_per > thresh, thresh)`` then the tx90p
+    count; the clamp is applied to the per-doy table on the device."""
+    import numpy as np
+    import torch
+
+    from . import _lib, device
+    from .calendar import adjust_table, table_on_device
+    from .field import attrs_of
+    from .generic import _unwrap, _wrap_periods
+
+    if bootstrap:
+        raise NotImplementedError("days_over_precip_thresh(bootstrap=True) is not supported by the B200 hot path")
+    code = _lib.op_code(op, (">", ">="))
+    thr = threshold_in_units_of(thresh, pr) if isinstance(thresh, str) else float(thresh)
+    x2d, cell_shape, other, ta = _unwrap(pr)
+    table = table_on_device(pr_per, cell_shape, other, x2d.device)
+    table = torch.where(table > thr, table, torch.full_like(table, thr))     # NaN percentiles -> thresh
+    table, doy_idx = adjust_table(table, ta)
+    out, _ = device.doy_threshold_count(x2d, ta.period_offsets(freq), doy_idx, table, code)
+    attrs = attrs_of(pr)
+    attrs["units"] = "d"
+    return _wrap_periods(pr, out, cell_shape, other, ta, freq, attrs, dtype=np.int64)
+
+
 def tx90p(tasmax, tasmax_per, freq="YS", bootstrap=False, op=">"):
     """Days with daily maximum temperature over the 90th percentile -- indices/_multivariate.py:1534-1590."""
     return _percentile_day_count(tasmax, tasmax_per, freq, bootstrap, op, (">", ">="))
