@@ -281,7 +281,11 @@ def run_ours(args):
     if not args.no_e2e:
         try:
             from bench_e2e import e2e_section
-            line["e2e"] = e2e_section(args, dev, rank, world, pr, poff, barrier, out, valid)
+            affinity = os.sched_getaffinity(0)   # the e2e leg pins this process to the GPU's NUMA node
+            try:
+                line["e2e"] = e2e_section(args, dev, rank, world, pr, poff, barrier, out, valid)
+            finally:
+                os.sched_setaffinity(0, affinity)  # ... the CPU arm below must see every core again
         except ImportError:
             line["e2e"] = None
 
