@@ -136,13 +136,19 @@ def mask_steps(x2d, keep):
     return torch.from_numpy(x)
 
 
+def period_boundary_run(x2d, poff, op_code, thr, window, last=False, cmp_f64=False):
+    fn = O.last_run if last else O.first_run
+    out = fn(_cond(_np(x2d), op_code, thr, cmp_f64), int(window), poff=poff)
+    return torch.from_numpy(np.asarray(out, dtype=np.float32))
+
+
 def dev_ints(arr, dtype, device):
     return torch.from_numpy(np.ascontiguousarray(np.asarray(arr, dtype=dtype)))
 
 
 FUNCTIONS = [to_time_cell, period_count, period_runstat, period_runstat_gap, period_reduce, rolling_period_reduce,
              spell_runstat, period_run_maxsum, period_runstat2, percentile_doy, doy_interp, doy_threshold_count,
-             mask_steps, dev_ints]
+             mask_steps, dev_ints, period_boundary_run]
 
 
 def install(monkeypatch):

@@ -1,0 +1,75 @@
+"""Known answers of the reference's own test-suite (VALUES only, re-expressed on the Field container),
+asserted through the host layer twice: on the CPU with the oracle stand-ins of tests/fake_device.py, and
+on the GPU through the real kernels (-m gpu)."""
+import numpy as np
+import pytest
+
+import fake_device
+from xb_helpers import make_field
+
+K2C = 273.15
+
+
+@pytest.fixture(params=["oracle-on-cpu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def backend(request, monkeypatch):
+    if request.param == "cuda":
+        import torch
+        if not torch.cuda.is_available():
+            pytest.skip("no CUDA device")
+    else:
+        fake_device.install(monkeypatch)
+    return request.param
+
+
+def test_first_and_last_run(backend):
+    """tests/test_run_length.py:313-331, 384-433: run at steps 30..39."""
+    from xclim_b200 import run_length as rl
+    t = np.zeros((60, 2), np.float32)
+    t[30:40] = 2
+    da = make_field(t, "2000-01-01", units="K")
+    assert (rl.first_run(da, 1, freq="YS").values == 30).all()
+    assert (rl.first_run(da, 1, freq="YS", coord="dayofyear").values == 31).all()
+    assert (rl.last_run(da, 1, freq="YS").values == 39).all()
+    assert (rl.last_run(da, 1, freq="YS", coord="dayofyear").values == 40).all()
+    t[0] = 2                                   # :411-425 resample after: [30, 8] / doy [31, 40]
+    da = make_field(t, "2000-01-01", units="K")
+    np.testing.assert_array_equal(rl.last_run(da, 1, freq="MS").values[:, 0], [30, 8])
+    np.testing.assert_array_equal(rl.last_run(da, 1, freq="MS", coord="dayofyear").values[:, 0], [31, 40])
+    a = np.zeros((100, 1), np.float32)         # :302-306
+    a[10:20] = 1
+    assert rl.first_run(make_field(a, "2000-01-01", units=""), 5, freq="YS").values[0, 0] == 10
+
+
+def test_windowed_max_run_sum(backend):
+    """tests/test_run_length.py:374-381: 2 steps too short, 5 steps, 10 steps of 5 -> 50."""
+    from xclim_b200 import run_length as rl
+    a = np.zeros((50, 1), np.float32)
+    a[4:6] = 5
+    a[25:30] = 5
+    a[35:45] = 5
+    out = rl.windowed_max_run_sum(make_field(a, "2001-01-01", calendar="noleap", units=""), 3, freq="YS")
+    assert out.values[0, 0] == 50
+
+
+@pytest.mark.parametrize("op,expected", [("gt", [0, 5, 10, 0, 0]), (">=", [0, 5, 10, 0, 0]), ("<", [20, 0, 0, 7, 0])])
+def test_cumulative_difference(backend, op, expected):
+    """tests/test_generic.py:316-334 (per-step values: one period per step here, freq="D")."""
+    from xclim_b200 import generic
+    tas = make_field((np.array([-10, 15, 20, 3, 10]) + K2C).astype(np.float32), "2000-01-01", units="K")
+    out = generic.cumulative_difference(tas, threshold="10 degC", op=op, freq="D")
+    np.testing.assert_allclose(out.values, expected, rtol=1e-5, atol=1e-4)
+    out_k = generic.cumulative_difference(tas, threshold="283.15 K", op=op, freq="D")
+    np.testing.assert_allclose(out.values, out_k.values)
+    with pytest.raises((NotImplementedError, ValueError)):
+        generic.cumulative_difference(tas, threshold="10 degC", op="!=", freq="D")
+
+
+def test_spell_length_with_holes(backend):
+    """tests/test_run_length.py:150-162 through spell_length_statistics(min_gap=3)."""
+    from xclim_b200 import generic
+    v = np.zeros(365, np.float32)
+    a = [0, 1, 0, 1, 1, 0, 0, 1, 1, 1, 1, 0, 0, 0, 0, 1, 1, 1, 1, 1, 0, 0, 0, 0]
+    v[:len(a)] = a
+    da = make_field(v, "2000-01-01", calendar="noleap", units="")
+    mx, total, n = generic.spell_length_statistics(da, 0.5, 1, None, ">", ["max", "sum", "count"], "YS", min_gap=3)
+    assert mx.values[0] == 10 and total.values[0] == 15 and n.values[0] == 2
