@@ -268,3 +268,17 @@ def test_runs_with_holes_reference_known_answers():
     poff = np.array([0, 365], dtype=np.int32)
     assert O.spell_length_statistics(x, 1.0, 1, None, "<", "max", poff, min_gap=3)[0, 0] == 10
     assert O.spell_length_statistics(x, 1.0, 1, None, "<", "count", poff, min_gap=3)[0, 0] == 2
+
+
+@pytest.mark.parametrize("op,expected", [(">", 6), (">=", 5), ("==", 5), ("!=", 1), ("lt", None), ("le", None)])
+def test_known_answers_first_day_threshold_reached(op, expected):
+    """tests/test_generic.py:343-383 (values): pr = 0, .001, ..., .007 then zeros; first day (doy) on
+    which `pr op 0.004` holds after 01-01, window 1.  The '<' family uses the flipped vector (:361-383)."""
+    a = np.zeros(365)
+    a[:8] = np.arange(8) / 1000
+    if expected is None:
+        a[:8] = a[:8][::-1].copy()
+        expected = {"lt": 5, "le": 4}[op]
+    cond = O.compare(a[:, None], op, 0.004)
+    idx = O.first_run_after_date(cond, 1, 0)[0]          # mid = index of 01-01 in the (single) group
+    assert idx + 1 == expected                             # dayofyear of a series starting on 1 January
