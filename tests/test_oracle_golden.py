@@ -282,3 +282,23 @@ def test_known_answers_first_day_threshold_reached(op, expected):
     cond = O.compare(a[:, None], op, 0.004)
     idx = O.first_run_after_date(cond, 1, 0)[0]          # mid = index of 01-01 in the (single) group
     assert idx + 1 == expected                             # dayofyear of a series starting on 1 January
+
+
+def test_known_answers_adjust_doy_calendar():
+    """tests/test_calendar.py:142-200 (values): 360 -> 366, 366 -> 360, a 92-day window onto 93 days
+    (all_leap JJA), and a leap DJF table onto a noleap axis keep their end points."""
+    src = np.arange(360, dtype=np.float64)
+    doy = np.concatenate([np.arange(1, 367), np.arange(1, 366)])          # 2000-01-01 .. 2001-12-31
+    out = O.adjust_doy_calendar(src, doy, cal_max_doy=366)
+    assert out.shape[0] == 366 and out[0] == src[0] and out[365] == src[359]
+    src = np.arange(366, dtype=np.float64)
+    out = O.adjust_doy_calendar(src, np.arange(1, 361), cal_max_doy=360)
+    assert out.shape[0] == 360 and out[0] == src[0] and out[359] == src[365]
+    src = np.arange(92, dtype=np.float64)                                  # doys 152..243 -> 153..244
+    out = O.adjust_doy_calendar(src, np.arange(153, 245), cal_max_doy=366)
+    assert out.shape[0] == 92 and out[0] == src[0] and out[-1] == src[-1]
+    # the same table size as the calendar: returned untouched (:748-750)
+    tab = np.arange(365, dtype=np.float64)
+    assert O.adjust_doy_calendar(tab, np.arange(1, 366), cal_max_doy=365) is tab
+    # resample_doy gathers by day of year
+    np.testing.assert_array_equal(O.resample_doy(tab, np.array([1, 365, 2]), cal_max_doy=365), [0, 364, 1])
