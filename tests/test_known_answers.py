@@ -73,3 +73,31 @@ def test_spell_length_with_holes(backend):
     da = make_field(v, "2000-01-01", calendar="noleap", units="")
     mx, total, n = generic.spell_length_statistics(da, 0.5, 1, None, ">", ["max", "sum", "count"], "YS", min_gap=3)
     assert mx.values[0] == 10 and total.values[0] == 15 and n.values[0] == 2
+
+
+def test_atmos_tx90p_simple_and_nan_treatment(backend):
+    """tests/test_temperature.py:1153-1181: leap year 0..365, window-1 percentiles (the table is the series
+    itself re-mapped onto 366 days), cold spell in June; a NaN day turns its month into NaN (MissingAny)."""
+    from xclim_b200 import atmos, calendar as xcal
+    arr = np.arange(366, dtype=np.float32)
+    tas = make_field(arr.copy(), "2000-01-01", units="K")
+    t90 = xcal.select_percentile(xcal.percentile_doy(tas, window=1, per=90), 90.0)
+    x = arr.copy()
+    x[175:180] = 1
+    out = atmos.tx90p(make_field(x, "2000-01-01", units="K"), t90, freq="MS").values
+    assert out[0] == 30 and out[1] == 29 and out[5] == 25
+    x[33] = np.nan
+    out = atmos.tx90p(make_field(x, "2000-01-01", units="K"), t90, freq="MS").values
+    assert out[0] == 30 and np.isnan(out[1]) and out[5] == 25
+
+
+def test_atmos_cdd_vector(backend):
+    """tests/test_precip.py:470-477: 31 wet days of 50 mm/day with five dry days -> 5."""
+    from xclim_b200 import atmos
+    x1 = np.full(31, 50.0, np.float32)
+    x1[5:10] = 0
+    out = atmos.maximum_consecutive_dry_days(make_field(x1, "2000-01-01", units="mm/day"), freq="MS")
+    assert out.values[0] == 5
+    x1[20] = np.nan
+    out = atmos.maximum_consecutive_dry_days(make_field(x1, "2000-01-01", units="mm/day"), freq="MS")
+    assert np.isnan(out.values[0])
