@@ -302,3 +302,66 @@ def test_known_answers_adjust_doy_calendar():
     assert O.adjust_doy_calendar(tab, np.arange(1, 366), cal_max_doy=365) is tab
     # resample_doy gathers by day of year
     np.testing.assert_array_equal(O.resample_doy(tab, np.array([1, 365, 2]), cal_max_doy=365), [0, 364, 1])
+
+
+def _date_index(start, n, date):
+    """Index of MM-DD in a standard-calendar daily series of n steps starting at `start` (None if absent)."""
+    from xclim_b200 import TimeAxis
+    ta = TimeAxis.daily(start, n)
+    mm, dd = (int(v) for v in date.split("-"))
+    hit = np.nonzero((ta.month == mm) & (ta.day == dd))[0]
+    return (int(hit[0]) if hit.size else None), ta
+
+
+@pytest.mark.parametrize("date,end,expected", [("07-01", 210, 70), ("07-01", 190, 50), ("04-01", 150, 0),
+                                               ("11-01", 150, 165), (None, 150, 10)])
+def test_known_answers_season_length_with_dates(date, end, expected):
+    """tests/test_run_length.py:473-503."""
+    t = np.zeros(360)
+    t[140:end] = 1
+    mid, _ = _date_index("2000-01-01", 360, date) if date else (None, None)
+    _, _, length = O.season_group(t == 1, 1, mid, has_date=date is not None)
+    assert length == expected
+
+
+@pytest.mark.parametrize("coord,date,end,expected", [("dayofyear", "07-01", 210, 211), (False, "07-01", 190, 190),
+                                                     ("dayofyear", "04-01", 150, np.nan),
+                                                     ("dayofyear", "11-01", 150, 306)])
+def test_known_answers_run_end_after_date(coord, date, end, expected):
+    """tests/test_run_length.py:505-529."""
+    t = np.zeros(360)
+    t[140:end] = 1
+    mid, ta = _date_index("2000-01-01", 360, date)
+    v = O.run_end_after_date(t == 1, 1, mid)
+    if coord and not np.isnan(v):
+        v = ta.doy[int(v)]
+    np.testing.assert_array_equal(v, expected)
+
+
+@pytest.mark.parametrize("coord,date,beg,expected", [("dayofyear", "07-01", 210, 211), (False, "07-01", 190, 190),
+                                                     ("dayofyear", "04-01", False, np.nan),
+                                                     ("dayofyear", "11-01", 150, 306)])
+def test_known_answers_first_run_after_date(coord, date, beg, expected):
+    """tests/test_run_length.py:531-554."""
+    t = np.zeros(365)
+    if beg:
+        t[beg:] = 1
+    mid, ta = _date_index("2000-01-01", 365, date)
+    v = O.first_run_after_date(t == 1, 1, mid)
+    if coord and not np.isnan(v):
+        v = ta.doy[int(v)]
+    np.testing.assert_array_equal(v, expected)
+
+
+@pytest.mark.parametrize("coord,date,end,expected", [("dayofyear", "07-01", 210, 183), (False, "07-01", 190, 182),
+                                                     ("dayofyear", "04-01", 150, np.nan),
+                                                     ("dayofyear", "11-01", 150, 150)])
+def test_known_answers_last_run_before_date(coord, date, end, expected):
+    """tests/test_run_length.py:556-579."""
+    t = np.zeros(360)
+    t[140:end] = 1
+    mid, ta = _date_index("2000-01-01", 360, date)
+    v = O.last_run_before_date(t == 1, 1, mid)
+    if coord and not np.isnan(v):
+        v = ta.doy[int(v)]
+    np.testing.assert_array_equal(v, expected)
