@@ -101,3 +101,39 @@ def test_atmos_cdd_vector(backend):
     x1[20] = np.nan
     out = atmos.maximum_consecutive_dry_days(make_field(x1, "2000-01-01", units="mm/day"), freq="MS")
     assert np.isnan(out.values[0])
+
+
+@pytest.mark.parametrize("op_high,op_low,expected", [(">", "<", 1), (">", "<=", 2), (">=", "<", 3), (">=", "<=", 4)])
+def test_count_level_crossings(backend, op_high, op_low, expected):
+    """tests/test_generic.py:412-431."""
+    from xclim_b200 import generic
+    tasmin = make_field((np.array([-1, -3, 0, 5, 9, 1, 3]) + K2C).astype(np.float32), "2000-01-01", units="K")
+    tasmax = make_field((np.array([5, 7, 3, 6, 13, 5, 4]) + K2C).astype(np.float32), "2000-01-01", units="K")
+    out = generic.count_level_crossings(tasmin, tasmax, threshold="5 degC", freq="YS", op_high=op_high, op_low=op_low)
+    np.testing.assert_array_equal(out.values, [expected])
+
+
+@pytest.mark.parametrize("op_high,op_low", [("<=", "<="), (">=", ">="), ("<", ">"), ("==", "!=")])
+def test_count_level_crossings_forbidden_ops(backend, op_high, op_low):
+    """tests/test_generic.py:433-446."""
+    from xclim_b200 import generic
+    tasmin = make_field((np.zeros(7) + K2C).astype(np.float32), "2000-01-01", units="K")
+    tasmax = make_field((np.ones(7) + K2C).astype(np.float32), "2000-01-01", units="K")
+    with pytest.raises(ValueError):
+        generic.count_level_crossings(tasmin, tasmax, threshold="0.5 degC", freq="YS", op_high=op_high, op_low=op_low)
+
+
+@pytest.mark.parametrize("op,constrain,expected,should_fail", [
+    ("<", ("!=", "<"), 4, False), (">", (">", "<="), 5, False), (">=", (">=", "=="), 6, False),
+    ("==", ("==", "!="), 1, False), ("==", (">", ">="), 1, True), ("!=", ("!=", ">"), 9, False),
+    ("!=", (">", "=="), 9, True), ("%", ("%", "$", "@"), 5.29e-11, True)])
+def test_count_occurrences(backend, op, constrain, expected, should_fail):
+    """tests/test_generic.py:448-469."""
+    from xclim_b200 import generic
+    tas = make_field((np.arange(10) + K2C).astype(np.float32), "2000-01-01", units="K")
+    if should_fail:
+        with pytest.raises(ValueError):
+            generic.count_occurrences(tas, "4 degC", freq="YS", op=op, constrain=constrain)
+    else:
+        out = generic.count_occurrences(tas, "4 degC", freq="YS", op=op, constrain=constrain)
+        np.testing.assert_array_equal(out.values, [expected])

@@ -217,6 +217,17 @@ def count_occurrences(data, threshold, freq, op, constrain=None):
     return out.assign_attrs(units="d")
 
 
+def count_level_crossings(low_data, high_data, threshold, freq, *, op_low="<", op_high=">="):
+    """Days on which ``low_data`` is under and ``high_data`` over the same threshold --
+    indices/generic.py:917-957 (both variables in the same units)."""
+    from .units import units_of
+    if units_of(high_data) != units_of(low_data):
+        raise NotImplementedError("count_level_crossings: give both variables in the same units")
+    return bivariate_count_occurrences(data_var1=low_data, data_var2=high_data, threshold_var1=threshold,
+                                       threshold_var2=threshold, freq=freq, op_var1=op_low, op_var2=op_high,
+                                       var_reducer="all", constrain_var1=("<", "<="), constrain_var2=(">", ">="))
+
+
 # --------------------------------------------------------------------------------- a12 seasons / dates
 def season(data, thresh, window, op, stat, freq, mid_date=None, constrain=None):
     """Season start / end (day of year) or length -- indices/generic.py:769-853 (+ run_length.py:891-1145)."""
