@@ -137,3 +137,33 @@ def test_count_occurrences(backend, op, constrain, expected, should_fail):
     else:
         out = generic.count_occurrences(tas, "4 degC", freq="YS", op=op, constrain=constrain)
         np.testing.assert_array_equal(out.values, [expected])
+
+
+@pytest.mark.parametrize("op,constrain,expected,should_fail", [
+    ("<", None, np.nan, False), ("<=", None, 3, False), ("!=", ("!=",), 1, False), ("==", ("==", "!="), 3, False),
+    ("==", (">=", ">", "<"), 3, True)])
+def test_first_occurrence(backend, op, constrain, expected, should_fail):
+    """tests/test_generic.py:469-487."""
+    from xclim_b200 import generic
+    tas = make_field((np.array([15, 12, 11, 12, 14, 13, 18, 11, 13]) + K2C).astype(np.float32), "2000-01-01", units="K")
+    if should_fail:
+        with pytest.raises(ValueError):
+            generic.first_occurrence(tas, threshold="11 degC", freq="YS", op=op, constrain=constrain)
+    else:
+        out = generic.first_occurrence(tas, threshold="11 degC", freq="YS", op=op, constrain=constrain)
+        np.testing.assert_array_equal(out.values, [expected])
+
+
+@pytest.mark.parametrize("op,constrain,expected,should_fail", [
+    ("<", None, np.nan, False), ("<=", None, 8, False), ("!=", ("!=",), 9, False), ("==", ("==", "!="), 8, False),
+    ("==", (">=", ">", "<"), 5, True)])
+def test_last_occurrence(backend, op, constrain, expected, should_fail):
+    """tests/test_generic.py:489-507."""
+    from xclim_b200 import generic
+    tas = make_field((np.array([15, 12, 11, 12, 14, 13, 18, 11, 13]) + K2C).astype(np.float32), "2000-01-01", units="K")
+    if should_fail:
+        with pytest.raises(ValueError):
+            generic.last_occurrence(tas, threshold="11 degC", freq="YS", op=op, constrain=constrain)
+    else:
+        out = generic.last_occurrence(tas, threshold="11 degC", freq="YS", op=op, constrain=constrain)
+        np.testing.assert_array_equal(out.values, [expected])

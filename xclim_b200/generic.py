@@ -217,6 +217,33 @@ def count_occurrences(data, threshold, freq, op, constrain=None):
     return out.assign_attrs(units="d")
 
 
+def _occurrence(data, threshold, freq, op, constrain, last):
+    from .run_length import index_to_doy
+    import torch
+    code = get_op(op, constrain)
+    thr, f64 = (threshold_in_units_of(threshold, data), False) if isinstance(threshold, str) else \
+        _scalar_threshold(threshold)
+    x2d, cell_shape, other, ta = _unwrap(data)
+    poff = ta.period_offsets(freq)
+    idx = device.period_boundary_run(x2d, poff, code, thr, 1, last=last, cmp_f64=f64)
+    out = index_to_doy(idx.to(torch.float64), poff, ta)      # coord="dayofyear" (core/utils.py:202-276)
+    attrs = attrs_of(data)
+    attrs.update(units="", is_dayofyear=np.int32(1), calendar=ta.calendar)
+    return _wrap_periods(data, out, cell_shape, other, ta, freq, attrs, dtype=np.float64)
+
+
+def first_occurrence(data, threshold, freq, op, constrain=None):
+    """Day of year of the first step of each period where ``data op threshold`` -- indices/generic.py:
+    1107-1156 (``rl.first_run(cond, window=1, coord="dayofyear")`` per group; NaN when there is none --
+    or, by the argmax == argmin rule of the reference, when every step qualifies)."""
+    return _occurrence(data, threshold, freq, op, constrain, last=False)
+
+
+def last_occurrence(data, threshold, freq, op, constrain=None):
+    """indices/generic.py:1159-1206."""
+    return _occurrence(data, threshold, freq, op, constrain, last=True)
+
+
 def count_level_crossings(low_data, high_data, threshold, freq, *, op_low="<", op_high=">="):
     """Days on which ``low_data`` is under and ``high_data`` over the same threshold --
     indices/generic.py:917-957 (both variables in the same units)."""
