@@ -167,3 +167,51 @@ def test_last_occurrence(backend, op, constrain, expected, should_fail):
     else:
         out = generic.last_occurrence(tas, threshold="11 degC", freq="YS", op=op, constrain=constrain)
         np.testing.assert_array_equal(out.values, [expected])
+
+
+@pytest.mark.parametrize("thresholds", [{}, {"thresh_tasmax": "0 degC", "thresh_tasmin": "0 degC"}])
+def test_freezethaw_cycles(backend, thresholds):
+    """tests/test_indices.py:1415-1439: five freeze-thaw days in January, one in February."""
+    from xclim_b200 import indices
+    mn = np.zeros(365, np.float32)
+    mx = np.zeros(365, np.float32)
+    mn[10:20] -= 1
+    mx[10:15] += 1
+    mn[40:44] += [1, 1, -1, -1]
+    mx[40:44] += [1, -1, 1, -1]
+    tn = make_field((mn + K2C).astype(np.float32), "2001-01-01", calendar="noleap", units="K")
+    tx = make_field((mx + K2C).astype(np.float32), "2001-01-01", calendar="noleap", units="K")
+    out = indices.multiday_temperature_swing(tn, tx, **thresholds, op="sum", window=1, freq="MS")
+    np.testing.assert_array_equal(out.values[:2], [5, 1])
+    np.testing.assert_array_equal(out.values[2:], 0)
+    np.testing.assert_array_equal(indices.daily_freezethaw_cycles(tn, tx, freq="MS").values, out.values)
+    # one event of five days and one of one day; the longest lasts five days
+    assert indices.multiday_temperature_swing(tn, tx, op="count", freq="YS").values[0] == 2
+    assert indices.multiday_temperature_swing(tn, tx, op="max", freq="YS").values[0] == 5
+    assert indices.multiday_temperature_swing(tn, tx, op="count", window=2, freq="YS").values[0] == 1
+
+
+def test_high_precip_low_temp(backend):
+    """tests/test_indices.py:3727-3732."""
+    from xclim_b200 import indices
+    pr = make_field(np.array([0, 1, 2, 0], np.float32), "2000-01-01", units="kg m-2 s-1")
+    tas = make_field((np.array([0, 0, 1, 1]) + K2C).astype(np.float32), "2000-01-01", units="K")
+    out = indices.high_precip_low_temp(pr, tas, pr_thresh="1 kg m-2 s-1", tas_thresh="1 degC")
+    np.testing.assert_array_equal(out.values, [1])
+
+
+def test_snowfall_frequency_intensity_and_dates(backend):
+    """tests/test_indices.py:4485-4521: [0, 2, .3, .2, 4] mm/day -> 40 % of the days, mean 3 mm/day."""
+    from xclim_b200 import indices
+    v = np.array([0, 2, 0.3, 0.2, 4], np.float32)
+    prsnd = make_field(v, "2000-07-01", units="mm/day")
+    np.testing.assert_allclose(indices.snowfall_frequency(prsnd).values, [40])
+    np.testing.assert_allclose(indices.snowfall_intensity(prsnd).values, [3])
+    prsn = make_field((v / 86400.0).astype(np.float32), "2000-07-01", units="kg m-2 s-1")
+    np.testing.assert_allclose(indices.snowfall_frequency(prsn).values, [40])
+    np.testing.assert_allclose(indices.snowfall_intensity(prsn).values, [3], rtol=1e-5)
+    # first / last day with snowfall >= 1 mm/day: 2 July (doy 184 in a leap year) and 5 July
+    assert indices.first_snowfall(prsnd).values[0] == 184
+    assert indices.last_snowfall(prsnd).values[0] == 187
+    none = make_field(np.zeros(5, np.float32), "2000-07-01", units="mm/day")
+    assert indices.snowfall_intensity(none).values[0] == 0 and np.isnan(indices.first_snowfall(none).values[0])

@@ -598,3 +598,98 @@ def tx_tn_days_above(tasmin, tasmax, thresh_tasmin="22 degC", thresh_tasmax="30 
     import numpy as np
     return _bivariate(tasmin, tasmax, thresh_tasmin, thresh_tasmax, op, op, "sum", 1, freq, True, "d",
                       constrain=(">", ">="), dtype=np.int64)
+
+
+# ---- more thin entry points over the same kernels -----------------------------------------------------
+def multiday_temperature_swing(tasmin, tasmax, thresh_tasmin="0 degC", thresh_tasmax="0 degC", window=1, op="mean",
+                               op_tasmin="<=", op_tasmax=">", freq="YS", resample_before_rl=True):
+    """Statistics of freeze-thaw spells (tasmin op_tasmin thresh AND tasmax op_tasmax thresh) --
+    indices/_multivariate.py:426-510: ``op="count"`` is ``windowed_run_events``, the others
+    ``rle_statistics(reducer=op)``, both through ``resample_and_rl``."""
+    import numpy as np
+
+    from . import _lib, device
+    from .field import attrs_of
+    from .generic import _unwrap, _wrap_periods
+    if op not in _lib.RL_REDUCERS:
+        raise NotImplementedError(f"op {op!r} is not supported by the B200 hot path")
+    c1 = _lib.op_code(op_tasmin, ("<", "<="))
+    c2 = _lib.op_code(op_tasmax, (">", ">="))
+    t1 = threshold_in_units_of(thresh_tasmin, tasmin) if isinstance(thresh_tasmin, str) else float(thresh_tasmin)
+    t2 = threshold_in_units_of(thresh_tasmax, tasmax) if isinstance(thresh_tasmax, str) else float(thresh_tasmax)
+    x1, cell_shape, other, ta = _unwrap(tasmin)
+    x2, cs2, _, ta2 = _unwrap(tasmax)
+    if cs2 != cell_shape or len(ta2) != len(ta):
+        raise ValueError("the two variables must share the same grid and time axis")
+    out = device.period_runstat2(x1, x2, ta.period_offsets(freq), c1, t1, c2, t2, _lib.RL_REDUCERS[op], int(window),
+                                 resample_before_rl, False)
+    attrs = attrs_of(tasmin)
+    attrs["units"] = "d"
+    return _wrap_periods(tasmin, out, cell_shape, other, ta, freq, attrs, dtype=np.float32)
+
+
+def daily_freezethaw_cycles(tasmin, tasmax, thresh_tasmin="0 degC", thresh_tasmax="0 degC", op_tasmin="<=",
+                            op_tasmax=">", freq="YS"):
+    """Days with tasmin <= 0 degC and tasmax > 0 degC -- indices/_multivariate.py:344-423
+    (``multiday_temperature_swing(window=1, op="sum")``)."""
+    return multiday_temperature_swing(tasmin, tasmax, thresh_tasmin, thresh_tasmax, 1, "sum", op_tasmin, op_tasmax,
+                                      freq, True)
+
+
+def high_precip_low_temp(pr, tas, pr_thresh="0.4 mm/d", tas_thresh="-0.2 degC", freq="YS"):
+    """Days with precipitation at or above and temperature under a threshold --
+    indices/_multivariate.py:1117-1171."""
+    return generic.bivariate_count_occurrences(data_var1=pr, data_var2=tas, threshold_var1=pr_thresh,
+                                               threshold_var2=tas_thresh, freq=freq, op_var1=">=", op_var2="<",
+                                               var_reducer="all")
+
+
+def first_snowfall(prsn, thresh="1 mm/day", freq="YS-JUL"):
+    """Day of year of the first day with snowfall at or above a threshold -- indices/_threshold.py:1701-1753."""
+    return generic.first_occurrence(prsn, thresh, freq, ">=")
+
+
+def last_snowfall(prsn, thresh="1 mm/day", freq="YS-JUL"):
+    """indices/_threshold.py:1757-1809."""
+    return generic.last_occurrence(prsn, thresh, freq, ">=")
+
+
+def snowfall_frequency(prsn, thresh="1 mm/day", freq="YS-JUL"):
+    """Percentage of the (non-missing) days of each period with snowfall over a threshold --
+    indices/_threshold.py:1863-1916: ``days_with_snow(low=thresh) / count * 100``."""
+    import numpy as np
+
+    from . import _lib, device
+    from .field import attrs_of
+    from .generic import _unwrap, _wrap_periods
+    thr = threshold_in_units_of(thresh, prsn) if isinstance(thresh, str) else float(thresh)
+    hi = threshold_in_units_of("1E6 kg m-2 s-1", prsn)
+    x2d, cell_shape, other, ta = _unwrap(prsn)
+    poff = ta.period_offsets(freq)
+    above, valid = device.period_count(x2d, poff, _lib.OPS[">"], thr, want_valid=True)
+    over, _ = device.period_count(x2d, poff, _lib.OPS[">"], hi)
+    out = _ratio(above - over, valid) * 100.0
+    attrs = attrs_of(prsn)
+    attrs["units"] = "%"
+    return _wrap_periods(prsn, out, cell_shape, other, ta, freq, attrs, dtype=np.float64)
+
+
+def snowfall_intensity(prsn, thresh="1 mm/day", freq="YS-JUL"):
+    """Mean snowfall rate (mm/day of liquid water) of the days at or above a threshold, 0 when there is
+    none -- indices/_threshold.py:1919-1967.  The mean is taken in the data's units and scaled once."""
+    import numpy as np
+
+    from . import _lib, device
+    from .field import attrs_of
+    from .generic import _unwrap, _wrap_periods
+    from .units import convert_units_to, units_of
+    thr = threshold_in_units_of(thresh, prsn) if isinstance(thresh, str) else float(thresh)
+    scale = convert_units_to(f"1 {units_of(prsn)}", "mm/d")      # data units -> mm/day
+    x2d, cell_shape, other, ta = _unwrap(prsn)
+    out, _ = device.period_reduce(x2d, ta.period_offsets(freq), _lib.STATS["mean"], _lib.TF_WHERE, _lib.OPS[">="], thr)
+    out = out * float(scale)
+    out = out.nan_to_num(nan=0.0) if hasattr(out, "nan_to_num") else np.nan_to_num(out, nan=0.0)
+    attrs = attrs_of(prsn)
+    attrs["units"] = "mm/day"
+    return _wrap_periods(prsn, out, cell_shape, other, ta, freq, attrs)
+
