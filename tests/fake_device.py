@@ -142,13 +142,55 @@ def period_boundary_run(x2d, poff, op_code, thr, window, last=False, cmp_f64=Fal
     return torch.from_numpy(np.asarray(out, dtype=np.float32))
 
 
+def period_boundary_run_range(x2d, poff, range_lo, range_hi, op_code, thr, window, last=False, negate=False,
+                              cell_lo=None, cmp_f64=False):
+    """Literal restatement of the C-ABI contract (include/xclim_b200.h, xc_period_boundary_run_range_f32):
+    first / last run of >= window steps of the (optionally negated) condition inside
+    [range_lo[p], range_hi[p]) of each period; window == 1 on the untouched whole period keeps the
+    argmax == argmin rule."""
+    x = _np(x2d)
+    cond = _cond(x, op_code, thr, cmp_f64)
+    if negate:
+        cond = ~cond
+    P, C = len(poff) - 1, x.shape[1]
+    out = np.full((P, C), np.nan, dtype=np.float32)
+    clo = None if cell_lo is None else _np(cell_lo)
+    for p in range(P):
+        t0, t1 = int(poff[p]), int(poff[p + 1])
+        if int(range_lo[p]) < 0:
+            continue
+        for c in range(C):
+            lo, hi = max(int(range_lo[p]), t0), min(int(range_hi[p]), t1)
+            full = (lo == t0) and (hi == t1)
+            if clo is not None:
+                b = clo[p, c]
+                bl = int(b) if b == b else 0
+                if t0 + bl > lo:
+                    lo, full = t0 + bl, False
+            m = cond[lo:hi, c]
+            if window == 1 and full:
+                n = int(m.sum())
+                if 0 < n < hi - lo:
+                    idx = np.nonzero(m)[0]
+                    out[p, c] = (idx[-1] if last else idx[0]) + lo - t0
+                continue
+            run = 0
+            steps = range(hi - 1, lo - 1, -1) if last else range(lo, hi)
+            for s in steps:
+                run = run + 1 if cond[s, c] else 0
+                if run >= window:
+                    out[p, c] = (s + window - 1 - t0) if last else (s - window + 1 - t0)
+                    break
+    return torch.from_numpy(out)
+
+
 def dev_ints(arr, dtype, device):
     return torch.from_numpy(np.ascontiguousarray(np.asarray(arr, dtype=dtype)))
 
 
 FUNCTIONS = [to_time_cell, period_count, period_runstat, period_runstat_gap, period_reduce, rolling_period_reduce,
              spell_runstat, period_run_maxsum, period_runstat2, percentile_doy, doy_interp, doy_threshold_count,
-             mask_steps, dev_ints, period_boundary_run]
+             mask_steps, dev_ints, period_boundary_run, period_boundary_run_range]
 
 
 def install(monkeypatch):

@@ -1,0 +1,142 @@
+"""Known answers of the reference's tests/test_indices.py (VALUES only; `*_series` fixtures become Fields
+starting 2000-07-01 like xclim.testing.helpers.test_timeseries), asserted through the index entry points
+on both backends: oracle stand-ins on the CPU (tests/fake_device.py), real kernels under -m gpu.
+Precipitation inputs are given in mm/d (the reference converts kg m-2 s-1 rates to daily amounts)."""
+import numpy as np
+import pytest
+
+import fake_device
+from xb_helpers import make_field
+
+K2C = 273.15
+
+
+@pytest.fixture(params=["oracle-on-cpu", pytest.param("cuda", marks=pytest.mark.gpu)])
+def backend(request, monkeypatch):
+    if request.param == "cuda":
+        import torch
+        if not torch.cuda.is_available():
+            pytest.skip("no CUDA device")
+    else:
+        fake_device.install(monkeypatch)
+    return request.param
+
+
+def series(values, units="K", start="2000-07-01", calendar="standard"):
+    return make_field(np.asarray(values, dtype=np.float32), start, calendar=calendar, units=units)
+
+
+def test_max_n_day_precipitation_amount(backend):          # :42-64
+    from xclim_b200 import indices
+    a = series([3, 4, 20, 20, 0, 6, 9, 25, 0, 0], "mm/d")
+    assert indices.max_n_day_precipitation_amount(a, 2).values[0] == 40
+    assert indices.max_n_day_precipitation_amount(a, 10).values[0] == 87
+    b = series([3, 4, 20, 20, 0, 6, 15, 25, 0, 0], "mm/d")
+    out = indices.max_n_day_precipitation_amount(b, 2)
+    assert out.values[0] == 40 and len(out.values) == 1
+
+
+def test_max_1day_precipitation_amount(backend):           # :66-103
+    from xclim_b200 import indices
+    for v in ([3, 4, 20, 0, 0], [20, 4, 20, 20, 0], [20, 20, 20, 20, 20]):
+        out = indices.max_1day_precipitation_amount(series(v, "mm/day"))
+        assert out.values[0] == 20 and len(out.values) == 1
+
+
+def _cold(start="2000-07-01", second=True):
+    a = np.zeros(365)
+    a[10:20] -= 15
+    a[40:43] -= 50
+    if second:
+        a[80:86] -= 30
+        a[95:101] -= 30
+    else:
+        a[80:100] -= 30
+    return series(a + K2C, "K", start)
+
+
+def test_cold_spell_days(backend):                          # :119-129
+    from xclim_b200 import indices
+    out = indices.cold_spell_days(_cold(second=False), thresh="-10. degC", freq="MS")
+    np.testing.assert_array_equal(out.values, [10, 0, 12, 8, 0, 0, 0, 0, 0, 0, 0, 0])
+    assert out.attrs["units"] == "d"
+
+
+def test_cold_spell_frequency_max_total(backend):           # :132-183
+    from xclim_b200 import indices
+    da = _cold("1971-01-01")
+    np.testing.assert_array_equal(indices.cold_spell_frequency(da, thresh="-10. degC", freq="MS").values,
+                                  [1, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0])
+    np.testing.assert_array_equal(indices.cold_spell_frequency(da, thresh="-10. degC", freq="YS").values, [3])
+    np.testing.assert_array_equal(indices.cold_spell_max_length(da, thresh="-10. degC", freq="MS").values,
+                                  [10, 3, 6, 6, 0, 0, 0, 0, 0, 0, 0, 0])
+    np.testing.assert_array_equal(indices.cold_spell_max_length(da, thresh="-10. degC", freq="YS").values, [10])
+    np.testing.assert_array_equal(indices.cold_spell_total_length(da, thresh="-10. degC", freq="MS").values,
+                                  [10, 3, 6, 6, 0, 0, 0, 0, 0, 0, 0, 0])
+    np.testing.assert_array_equal(indices.cold_spell_total_length(da, thresh="-10. degC", freq="YS").values, [25])
+
+
+def test_maximum_consecutive_frost_days(backend):           # :186-201
+    from xclim_b200 import indices
+    f = indices.maximum_consecutive_frost_days
+    assert f(series(np.array([3, 4, 5, -1, 3]) + K2C)).values[0] == 1
+    assert f(series(np.array([3, 4, 5, 1, 3]) + K2C)).values[0] == 0
+    assert f(series(np.zeros(365) - 10 + K2C)).values[0] == 365        # default freq YS-JUL: one period
+
+
+def test_maximum_consecutive_frost_free_days(backend):      # :204-229
+    from xclim_b200 import indices
+    f = indices.maximum_consecutive_frost_free_days
+    assert f(series(np.array([3, 4, 5, -1, 3]) + K2C)).values[0] == 3
+    assert f(series(np.array([3, 4, 5, -0.8, -2, 3]) + K2C), thresh="-1 degC").values[0] == 4
+    assert f(series(np.array([3, 4, 5, 1, 3]) + K2C)).values[0] == 5
+    assert (f(series(np.zeros(365) - 10 + K2C)).values == 0).all()
+    assert f(series(np.array([-1, -1, 1, 1, 0, 2, -1]) + K2C)).values[0] == 4
+
+
+def test_degree_days(backend):                              # :232-246, 1617-1622
+    from xclim_b200 import indices
+    assert indices.cooling_degree_days(series(np.array([10, 15, -5, 18]) + K2C)).values[0] == 0
+    np.testing.assert_allclose(indices.cooling_degree_days(series(np.array([20, 25, -15, 19]) + K2C)).values[0], 10,
+                               rtol=1e-5)
+    a = np.zeros(365)
+    a[0] = 5
+    np.testing.assert_allclose(indices.growing_degree_days(series(a + K2C)).values[0], 1, rtol=1e-4)
+
+
+def test_daily_pr_intensity(backend):                       # :1442-1454
+    from xclim_b200 import indices
+    pr = np.zeros(365)
+    pr[3:8] += [0.5, 1, 2, 3, 4]
+    np.testing.assert_allclose(indices.daily_pr_intensity(series(pr, "mm/d"), thresh="1 mm/day").values[0], 2.5)
+
+
+def test_frost_dates(backend):                              # :1474-1572
+    from xclim_b200 import indices
+    a = np.zeros(365)
+    a[180:270] = 303.15
+    tas = series(a, start="2000-01-01")
+    lsf = indices.last_spring_frost(tas)
+    assert lsf.values[0] == 180 and lsf.attrs["is_dayofyear"] == 1 and lsf.attrs["is_dayofyear"].dtype == np.int32
+    assert indices.first_day_temperature_below(tas).values[0] == 271
+    assert np.isnan(indices.first_day_temperature_below(series(np.zeros(365) + 303.15, start="2000-01-01")).values[0])
+    with pytest.raises(ValueError):
+        indices.first_day_temperature_below(tas, op=">=")
+    b = np.zeros(365) + 307
+    b[180:270] = 270
+    tas = series(b, start="2000-01-01")
+    assert indices.first_day_temperature_above(tas).values[0] == 1
+    assert indices.first_day_temperature_above(tas, after_date="07-01").values[0] == 271
+    assert np.isnan(indices.first_day_temperature_above(series(np.zeros(365) + 270, start="2000-01-01")).values[0])
+    with pytest.raises(ValueError):
+        indices.first_day_temperature_above(tas, op="<")
+    tg = np.zeros(365) - 1
+    w = 5
+    tg[10:10 + w - 1] += 6      # too short
+    tg[20:20 + w] += 1          # does not cross the threshold
+    tg[30:30 + w] += 6          # ok
+    tg[40:40 + w + 1] += 6      # second valid run, ignored
+    out = indices.first_day_temperature_above(series(tg + K2C, start="2000-01-01"), thresh="0 degC", window=w)
+    assert out.values[0] == 31
+    out = indices.first_day_temperature_above(series(np.zeros(365) - 1 + K2C, start="2000-01-01"), thresh="0 degC", window=5)
+    assert np.isnan(out.values[0])

@@ -32,7 +32,8 @@ def parse_quantity(q):
     """"1 mm/day" -> (1.0, "mm/day"); numbers pass through with units None."""
     if isinstance(q, (int, float)):
         return float(q), None
-    m = re.fullmatch(r"\s*([-+]?[0-9]*\.?[0-9]+(?:[eE][-+]?[0-9]+)?)\s*(.*)", str(q))
+    # 1, 1.5, .5, 10., 1e-5, 1E6 (what Python's float() accepts, without inf / nan)
+    m = re.fullmatch(r"\s*([-+]?(?:[0-9]+\.?[0-9]*|\.[0-9]+)(?:[eE][-+]?[0-9]+)?)\s*(.*)", str(q))
     if not m:
         raise ValueError(f"Cannot parse quantity {q!r}")
     return float(m.group(1)), m.group(2).strip()
