@@ -140,3 +140,82 @@ def test_frost_dates(backend):                              # :1474-1572
     assert out.values[0] == 31
     out = indices.first_day_temperature_above(series(np.zeros(365) - 1 + K2C, start="2000-01-01"), thresh="0 degC", window=5)
     assert np.isnan(out.values[0])
+
+
+def _dated(base, inside, d1, d2, n=365, start="2000-01-01"):
+    """`base` everywhere except `inside` between the two dates (inclusive), like tas.where(~isin(slice(d1, d2)))."""
+    import pandas as pd
+    idx = pd.date_range(start, periods=n, freq="D")
+    v = np.full(n, base, np.float32)
+    v[(idx >= d1) & (idx <= d2)] = inside
+    return series(v, start=start)
+
+
+@pytest.mark.parametrize("d1,d2,expected", [("1950-01-01", "1951-01-01", 0), ("2000-01-01", "2000-12-31", 365),
+                                            ("2000-06-15", "2001-01-01", 199), ("2000-06-15", "2000-07-15", 31)])
+def test_frost_season_length(backend, d1, d2, expected):    # :1710-1727
+    from xclim_b200 import indices
+    out = indices.frost_season_length(_dated(300, 270, d1, d2), freq="YS", mid_date="07-01")
+    np.testing.assert_array_equal(out.values, [expected])
+
+
+def test_frost_season_length_north_hemisphere(backend):     # :1729-1734
+    from xclim_b200 import indices
+    tas = _dated(300, 270, "2000-11-01", "2001-03-01", n=730)
+    out = indices.frost_season_length(tas)
+    labels = list(out.coords["time"])
+    assert out.values[[str(t)[:10] for t in labels].index("2000-07-01")] == 121
+
+
+def test_frost_free_season_start(backend):                  # :1738-1764
+    from xclim_b200 import indices
+    tn = np.zeros(365) - 1
+    w = 5
+    tn[10:10 + w - 1] += 2
+    tn[20:20 + w] += 1
+    tn[30:30 + w + 1] += 1
+    out = indices.frost_free_season_start(series(tn + K2C, start="2000-01-01"), window=w)
+    assert out.values[0] == 21 and out.attrs["is_dayofyear"] == 1
+    out = indices.frost_free_season_start(series(np.zeros(365) - 1, start="2000-01-01"))
+    assert np.isnan(out.values[0])
+
+
+@pytest.mark.parametrize("d1,d2,mid_date,expected", [
+    ("1950-01-01", "1951-01-01", "07-01", np.nan), ("2000-01-06", "2000-12-31", "07-01", 365),
+    ("2000-07-10", "2001-01-01", "07-01", np.nan), ("2000-06-15", "2000-07-15", "07-01", 198),
+    ("2000-06-15", "2000-07-25", "07-15", 208), ("2000-06-15", "2000-07-15", "10-01", 275),
+    ("2000-06-15", "2000-07-15", "01-10", np.nan), ("2000-06-15", "2000-07-15", "06-15", np.nan)])
+def test_frost_free_season_end(backend, d1, d2, mid_date, expected):   # :1768-1794
+    from xclim_b200 import indices
+    out = indices.frost_free_season_end(_dated(0, 0.1 + K2C, d1, d2), mid_date=mid_date)
+    np.testing.assert_array_equal(out.values, [expected])
+    assert out.attrs["is_dayofyear"] == 1
+
+
+@pytest.mark.parametrize("d1,d2,expected", [("1950-01-01", "1951-01-01", 0), ("2000-01-01", "2000-12-31", 365),
+                                            ("2000-06-15", "2001-01-01", 199), ("2000-06-15", "2000-07-15", 31)])
+def test_frost_free_season_length(backend, d1, d2, expected):          # :1797-1814
+    from xclim_b200 import indices
+    out = indices.frost_free_season_length(_dated(270, 300, d1, d2), freq="YS", mid_date="07-01")
+    np.testing.assert_array_equal(out.values, [expected])
+
+
+def test_frost_free_season_length_south_hemisphere(backend):           # :1816-1822
+    from xclim_b200 import indices
+    tn = _dated(270, 300, "2000-11-01", "2001-03-01", n=730)
+    out = indices.frost_free_season_length(tn, freq="YS-JUL", mid_date="01-01")
+    labels = [str(t)[:10] for t in out.coords["time"]]
+    assert out.values[labels.index("2000-07-01")] == 121
+
+
+def test_frost_free_spell_max_length_and_hdd(backend):                 # :1825-1846
+    from xclim_b200 import indices
+    tn = np.zeros(365) - 1
+    tn[10:12] = 1
+    tn[20:30] = 1
+    assert indices.frost_free_spell_max_length(series(tn + K2C, start="2000-01-01")).values[0] == 10
+    a = np.zeros(365) + 17
+    a[:7] += [-3, -2, -1, 0, 1, 2, 3]
+    out = indices.heating_degree_days(series(a + K2C))
+    np.testing.assert_allclose(out.values[:1], 6, rtol=1e-4)
+    np.testing.assert_allclose(out.values[1:], 0, atol=1e-3)
