@@ -219,3 +219,93 @@ def test_frost_free_spell_max_length_and_hdd(backend):                 # :1825-1
     out = indices.heating_degree_days(series(a + K2C))
     np.testing.assert_allclose(out.values[:1], 6, rtol=1e-4)
     np.testing.assert_allclose(out.values[1:], 0, atol=1e-3)
+
+
+TN_HW = np.asarray([20, 23, 23, 23, 23, 22, 23, 23, 23, 23]) + K2C
+TX_HW = np.asarray([29, 31, 31, 31, 29, 31, 31, 31, 31, 31]) + K2C
+
+
+@pytest.mark.parametrize("ttn,ttx,window,expected", [("22 C", "30 C", 3, 2), ("22 C", "30 C", 4, 1),
+                                                     ("10 C", "10 C", 3, 1), ("40 C", "40 C", 3, 0)])
+def test_heat_wave_frequency(backend, ttn, ttx, window, expected):      # :1859-1888
+    from xclim_b200 import indices
+    out = indices.heat_wave_frequency(series(TN_HW), series(TX_HW), thresh_tasmin=ttn, thresh_tasmax=ttx, window=window)
+    np.testing.assert_allclose(out.values, expected)
+
+
+@pytest.mark.parametrize("ttn,ttx,window,expected", [("22 C", "30 C", 3, 4), ("10 C", "10 C", 3, 10),
+                                                     ("40 C", "40 C", 3, 0), ("22 C", "30 C", 5, 0)])
+def test_heat_wave_max_length(backend, ttn, ttx, window, expected):     # :1891-1920
+    from xclim_b200 import indices
+    out = indices.heat_wave_max_length(series(TN_HW), series(TX_HW), thresh_tasmin=ttn, thresh_tasmax=ttx, window=window)
+    np.testing.assert_allclose(out.values, expected)
+
+
+@pytest.mark.parametrize("ttn,ttx,window,expected", [("22 C", "30 C", 3, 7), ("10 C", "10 C", 3, 10),
+                                                     ("40 C", "40 C", 3, 0), ("22 C", "30 C", 5, 0)])
+def test_heat_wave_total_length(backend, ttn, ttx, window, expected):   # :1923-1953
+    from xclim_b200 import indices
+    out = indices.heat_wave_total_length(series(TN_HW), series(TX_HW), thresh_tasmin=ttn, thresh_tasmax=ttx,
+                                         window=window)
+    np.testing.assert_allclose(out.values, expected)
+
+
+def test_hot_days(backend):                                             # :2029-2037
+    from xclim_b200 import indices
+    a = np.zeros(365)
+    a[:6] += [27, 28, 29, 30, 31, 32]
+    out = indices.hot_days(series(a + K2C), thresh="30 C")
+    np.testing.assert_array_equal(out.values[:1], [2])
+    np.testing.assert_array_equal(out.values[1:], [0])
+
+
+@pytest.mark.parametrize("thresh,window,op,expected", [("30 C", 3, ">", 2), ("30 C", 4, ">", 1), ("29 C", 3, ">", 2),
+                                                       ("29 C", 3, ">=", 1), ("10 C", 3, ">", 1), ("40 C", 5, ">", 0)])
+def test_hot_spell_frequency(backend, thresh, window, op, expected):    # :2040-2056
+    from xclim_b200 import indices
+    out = indices.hot_spell_frequency(series(TX_HW), thresh=thresh, window=window, op=op)
+    np.testing.assert_allclose(out.values, expected)
+
+
+@pytest.mark.parametrize("before,expected", [(True, 1), (False, 0)])
+def test_hot_spell_frequency_resampling_order(backend, before, expected):   # :2058-2071
+    from xclim_b200 import indices
+    a = np.zeros(365)
+    a[5:35] = 31
+    out = indices.hot_spell_frequency(series(a + K2C), resample_before_rl=before, freq="MS")
+    assert out.values[1] == expected
+
+
+TX_HS = np.asarray([28, 31, 31, 31, 29, 31, 31, 31, 31, 31]) + K2C
+
+
+@pytest.mark.parametrize("thresh,window,op,expected", [("30 C", 3, ">", 5), ("10 C", 3, ">", 10), ("29 C", 3, ">", 5),
+                                                       ("29 C", 3, ">=", 9), ("40 C", 3, ">", 0), ("30 C", 5, ">", 5)])
+def test_hot_spell_max_length(backend, thresh, window, op, expected):   # :2085-2101
+    from xclim_b200 import indices
+    out = indices.hot_spell_max_length(series(TX_HS), thresh=thresh, window=window, op=op)
+    np.testing.assert_allclose(out.values, expected)
+
+
+@pytest.mark.parametrize("thresh,window,op,expected", [("30 C", 3, ">", 8), ("10 C", 3, ">", 10), ("29 C", 3, ">", 8),
+                                                       ("29 C", 3, ">=", 9), ("40 C", 3, ">", 0), ("30 C", 5, ">", 5)])
+def test_hot_spell_total_length(backend, thresh, window, op, expected):  # :2104-2120
+    from xclim_b200 import indices
+    out = indices.hot_spell_total_length(series(TX_HS), thresh=thresh, window=window, op=op)
+    np.testing.assert_allclose(out.values, expected)
+
+
+def test_hot_spell_total_length_and_magnitude_monthly(backend):          # :2122-2142
+    from xclim_b200 import indices
+    a = np.zeros(365)
+    a[10:20] += 30
+    a[40:43] += 50
+    a[80:100] += 30
+    out = indices.hot_spell_total_length(series(a + K2C), window=5, thresh="25 C", freq="MS")
+    np.testing.assert_array_equal(out.values, [10, 0, 12, 8, 0, 0, 0, 0, 0, 0, 0, 0])
+    a = np.zeros(365)
+    a[15:20] += 30
+    a[40:42] += 50
+    a[86:96] += 30
+    out = indices.hot_spell_max_magnitude(series(a + K2C), thresh="25 C", freq="MS")
+    np.testing.assert_allclose(out.values, [25, 0, 30, 20, 0, 0, 0, 0, 0, 0, 0, 0], atol=1e-3)
