@@ -309,3 +309,134 @@ def test_hot_spell_total_length_and_magnitude_monthly(backend):          # :2122
     a[86:96] += 30
     out = indices.hot_spell_max_magnitude(series(a + K2C), thresh="25 C", freq="MS")
     np.testing.assert_allclose(out.values, [25, 0, 30, 20, 0, 0, 0, 0, 0, 0, 0, 0], atol=1e-3)
+
+
+def _ramp(sign=1):
+    a = np.zeros(365)
+    a[:6] += sign * np.array([27, 28, 29, 30, 31, 32])
+    return series(a + K2C)
+
+
+def test_tn_tg_tx_days(backend):                                        # :2145-2281
+    from xclim_b200 import indices
+    for above, below in ((indices.tn_days_above, indices.tn_days_below), (indices.tg_days_above, indices.tg_days_below),
+                         (indices.tx_days_above, indices.tx_days_below)):
+        out = above(_ramp(), thresh="30 C")
+        np.testing.assert_array_equal(out.values, [2, 0])
+        np.testing.assert_array_equal(below(_ramp(-1), thresh="-10 C").values, [6, 0])
+        np.testing.assert_array_equal(below(_ramp(-1), thresh="-30 C").values, [2, 0])
+    with pytest.warns(UserWarning, match="renamed"):
+        np.testing.assert_array_equal(indices.tn_days_above(_ramp(), thresh="30 C", op="gteq").values, [3, 0])
+    np.testing.assert_array_equal(indices.tn_days_above(_ramp(), thresh="29 C", op=">=").values, [4, 0])
+    np.testing.assert_array_equal(indices.tn_days_above(_ramp(), thresh="28 C", op=">=").values, [5, 0])
+    np.testing.assert_array_equal(indices.tn_days_below(_ramp(-1), thresh="-31 C", op="<=").values, [2, 0])
+    np.testing.assert_array_equal(indices.tn_days_below(_ramp(-1), thresh="-28 C", op="<=").values, [5, 0])
+    with pytest.warns(UserWarning, match="renamed"):
+        np.testing.assert_array_equal(indices.tn_days_below(_ramp(-1), thresh="-30 C", op="lteq").values, [3, 0])
+    for bad in ("<=", "lt"):
+        with pytest.raises(ValueError):
+            indices.tn_days_above(_ramp(), thresh="30 C", op=bad)
+    for bad in (">=", "gt"):
+        with pytest.raises(ValueError):
+            indices.tn_days_below(_ramp(-1), thresh="30 C", op=bad)
+
+
+def test_maximum_consecutive_tx_days(backend):                          # :2384-2391
+    from xclim_b200 import indices
+    a = np.zeros(365) + 273.15
+    a[5:15] += 30
+    out = indices.maximum_consecutive_tx_days(series(a, start="2010-01-01"), thresh="25 C", freq="MS")
+    assert out.values[0] == 10
+    np.testing.assert_array_equal(out.values[1:], 0)
+
+
+def test_precip_accumulation(backend):                                  # :2394-2420
+    import calendar
+    from xclim_b200 import indices
+    pr = np.zeros(100)
+    pr[5:10] = 1
+    assert indices.precip_accumulation(series(pr, "mm/d"), freq="MS").values[0] == 5
+    import pandas as pd
+    t = pd.date_range("2000-01-01", "2010-12-31", freq="D")
+    out = indices.precip_accumulation(series(t.year.values, "mm d-1", start="2000-01-01"))
+    np.testing.assert_allclose(out.values, [(365 + calendar.isleap(y)) * y for y in range(2000, 2011)])
+
+
+def test_tx_statistics(backend):                                        # :2640-2666
+    from xclim_b200 import indices
+    assert indices.tx_min(series([20, 25, -15, 19]), freq="YS").values[0] == -15
+    assert indices.tx_max(series([20, 25, -15, 19]), freq="YS").values[0] == 25
+    out = indices.tx_mean(series([320, 321, 322, 323, 324]), freq="YS")
+    assert out.values[0] == 322 and out.attrs["units"] == "K"
+    out = indices.tx_mean(series([20, 21, 22, 23, 24], units="°C"), freq="YS")
+    assert out.values[0] == 22 and out.attrs["units"] == "°C"
+
+
+def test_warm_day_and_night_frequency(backend):                         # :3088-3115
+    from xclim_b200 import indices
+    for fn, hot in ((indices.warm_day_frequency, 31), (indices.warm_night_frequency, 23)):
+        a = np.zeros(35)
+        a[25:] = hot
+        da = series(a + K2C)
+        np.testing.assert_allclose(fn(da, freq="MS").values, [6, 4])
+        np.testing.assert_allclose(fn(da, freq="YS").values, [10])
+        np.testing.assert_allclose(fn(da, thresh="-1 C").values, [35])
+        np.testing.assert_allclose(fn(da, thresh="50 C").values, [0])
+
+
+def test_wind_indices(backend):                                         # :3118-3136
+    from xclim_b200 import indices
+    a = np.full(365, 20.0)
+    a[10:20] = 2
+    a[40:50] = 3.1
+    out = indices.calm_days(series(a, "km h-1"), thresh="3 km h-1", freq="MS")
+    np.testing.assert_array_equal(out.values, [10, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0])
+    assert out.attrs["units"] == "d"
+    a = np.zeros(365)
+    a[10:20] = 10.8
+    a[40:50] = 12
+    a[80:90] = 15
+    out = indices.windy_days(series(a, "km h-1"), thresh="12 km h-1", freq="MS")
+    np.testing.assert_array_equal(out.values, [0, 10, 10, 0, 0, 0, 0, 0, 0, 0, 0, 0])
+
+
+def test_tx_tn_days_above(backend):                                     # :3139-3161
+    from xclim_b200 import indices
+    tn = series(np.asarray([20, 23, 23, 23, 23, 22, 23, 23, 23, 23]) + K2C)
+    tx = series(np.asarray([29, 31, 31, 31, 29, 31, 30, 31, 31, 31]) + K2C)
+    np.testing.assert_allclose(indices.tx_tn_days_above(tn, tx).values, [6])
+    np.testing.assert_allclose(indices.tx_tn_days_above(tn, tx, thresh_tasmax="50 C").values, [0])
+    np.testing.assert_allclose(indices.tx_tn_days_above(tn, tx, thresh_tasmax="0 C", thresh_tasmin="0 C").values, [10])
+    np.testing.assert_allclose(indices.tx_tn_days_above(tn, tx, op=">=").values, [8])
+    with pytest.raises(ValueError):
+        indices.tx_tn_days_above(tn, tx, op="<")
+
+
+def _wet():
+    a = np.zeros(365)
+    a[:7] += [4, 5.5, 6, 6, 2, 7, 5]
+    a[100:106] += [1, 6, 7, 5, 2, 1]
+    return series(a, "mm/day")
+
+
+def test_wetdays_and_proportion(backend):                               # :4211-4240
+    from xclim_b200 import indices
+    np.testing.assert_allclose(indices.wetdays(_wet(), thresh="5 mm/day", freq="MS").values,
+                               [5, 0, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0])
+    np.testing.assert_allclose(indices.wetdays(_wet(), thresh="5 mm/day", freq="MS", op=">").values,
+                               [4, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0])
+    np.testing.assert_allclose(indices.wetdays_prop(_wet(), thresh="5 mm/day", freq="MS").values,
+                               [5 / 31, 0, 0, 3 / 31, 0, 0, 0, 0, 0, 0, 0, 0])
+    np.testing.assert_allclose(indices.wetdays_prop(_wet(), thresh="5 mm/day", freq="MS", op=">").values,
+                               [4 / 31, 0, 0, 2 / 31, 0, 0, 0, 0, 0, 0, 0, 0])
+
+
+def test_surface_wind_statistics(backend):                              # :4443-4482
+    from xclim_b200 import indices
+    w = series([14.11, 15.27, 10.70], "m s-1")
+    np.testing.assert_allclose(indices.sfcWind_max(w).values, [15.27], rtol=1e-6)
+    np.testing.assert_allclose(indices.sfcWind_mean(w).values, [13.36], rtol=1e-6)
+    np.testing.assert_allclose(indices.sfcWind_min(w).values, [10.70], rtol=1e-6)
+    np.testing.assert_allclose(indices.sfcWindmax_max(w).values, [15.27], rtol=1e-6)
+    np.testing.assert_allclose(indices.sfcWindmax_mean(w).values, [13.36], rtol=1e-6)
+    np.testing.assert_allclose(indices.sfcWindmax_min(w).values, [10.70], rtol=1e-6)

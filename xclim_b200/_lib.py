@@ -105,6 +105,11 @@ def check(status: int) -> None:
 
 def op_code(op: str, constrain=None) -> int:
     """Operator name -> code with the validation of indices/generic.py:255-298 (`get_op`)."""
+    if op in ("gteq", "lteq"):     # deprecated spellings, renamed with a warning (indices/generic.py:273-278)
+        import warnings
+        renamed = {"gteq": "ge", "lteq": "le"}[op]
+        warnings.warn(f"`{op}` is being renamed `{renamed}` for compatibility.")
+        op = renamed
     if op not in OPS:
         raise ValueError(f"Operation `{op}` not recognized.")
     if constrain:

@@ -20,6 +20,8 @@ _ALIASES = {
     "mm/d": "mm/d", "mm/day": "mm/d", "mm d-1": "mm/d", "mm day-1": "mm/d", "mm d^-1": "mm/d",
     "kg m-2 s-1": "kg m-2 s-1", "kg/m2/s": "kg m-2 s-1", "kg m^-2 s^-1": "kg m-2 s-1", "mm/s": "kg m-2 s-1",
     "mm": "mm", "d": "d", "days": "d", "day": "d", "": "", "1": "", "m/s": "m s-1", "m s-1": "m s-1",
+    "km h-1": "km h-1", "km/h": "km h-1", "kph": "km h-1", "km hr-1": "km h-1",
+    "kg/m**2/s": "kg m-2 s-1", "kg m**-2 s**-1": "kg m-2 s-1",
 }
 
 
@@ -50,6 +52,10 @@ def _to_base(v: float, u: str):
         return v / 86400.0, "prflux"
     if u == "kg m-2 s-1":
         return v, "prflux"
+    if u == "m s-1":
+        return v, "speed"
+    if u == "km h-1":
+        return v / 3.6, "speed"
     return v, u
 
 
@@ -62,6 +68,8 @@ def _from_base(v: float, u: str):
         return (v - 273.15) * 9.0 / 5.0 + 32.0
     if u == "mm/d":
         return v * 86400.0
+    if u == "km h-1":
+        return v * 3.6
     return v
 
 
