@@ -153,11 +153,3 @@ def test_device_outputs_option_matches_host_outputs(cuda):
                                          mask.time), 2, freq="YS", coord="dayofyear")
     np.testing.assert_array_equal(got.numpy(), ref.values)
     assert not xclim_b200.options.OPTIONS["device_outputs"]
-
-
-def test_more_index_entry_points_on_device(cuda):
-    """The same assertions as tests/test_host_layer_cpu.py::test_more_index_entry_points, through the
-    real kernels instead of the oracle stand-ins."""
-    import test_host_layer_cpu as cpu_side
-    cpu_side.test_more_index_entry_points(None)
-    cpu_side.test_days_over_precip_thresh(None)

@@ -210,20 +210,3 @@ def test_percentile_doy_mid_percentiles_selection_kernel(cuda, calendar, years, 
     assert g.shape == exp.shape
     np.testing.assert_allclose(g, exp, rtol=RTOL, equal_nan=True)
     np.testing.assert_array_equal(g, exp)
-
-
-@pytest.mark.parametrize("n_src,doy_min,doy_max", [(360, 1, 366), (366, 1, 360), (365, 1, 366), (92, 153, 244)])
-def test_doy_interp_reference_known_answers(cuda, n_src, doy_min, doy_max):
-    """tests/test_calendar.py:142-200: the re-mapped table keeps its end points; everything in between
-    follows numpy's interp on linspace(doy_min, doy_max, n_src) (core/calendar.py:720-722)."""
-    import torch
-    from xclim_b200 import device
-    rng = np.random.default_rng(17)
-    tab = np.arange(n_src, dtype=np.float64)[:, None] + rng.standard_normal((n_src, 7)).cumsum(0)
-    tab[:, 0] = np.arange(n_src)
-    got = device.doy_interp(torch.from_numpy(tab).cuda(), doy_min, doy_max).cpu().numpy()
-    exp = O.interpolate_doy_calendar(tab, doy_max, doy_min)
-    assert got.shape == exp.shape == (doy_max - doy_min + 1, 7)
-    np.testing.assert_array_equal(got[0], tab[0])
-    np.testing.assert_array_equal(got[-1], tab[-1])
-    np.testing.assert_allclose(got, exp, rtol=1e-12, atol=1e-12)

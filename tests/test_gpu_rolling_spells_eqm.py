@@ -170,17 +170,3 @@ def test_spell_length_statistics_min_gap(cuda, min_gap, op, thr):
             np.testing.assert_array_equal(got.values, exp, err_msg=f"{min_gap} {op} {red} {freq}")
     with pytest.raises(NotImplementedError):
         generic.spell_length_statistics(da, thr, 3, "sum", op, "max", "YS", min_gap=2)
-
-
-def test_spell_min_gap_reference_known_answer(cuda):
-    """tests/test_run_length.py:150-162 through the product path: gaps of 1 and 2 steps are bridged by
-    min_gap=3, the 4-step gap is kept -> spells of 10 and 5 steps."""
-    from xclim_b200 import generic
-    v = np.zeros(365, np.float32)
-    a = [0, 1, 0, 1, 1, 0, 0, 1, 1, 1, 1, 0, 0, 0, 0, 1, 1, 1, 1, 1, 0, 0, 0, 0]
-    v[:len(a)] = a
-    da = make_field(v, "2000-01-01", calendar="noleap", units="")
-    mx, total, n = generic.spell_length_statistics(da, 0.5, 1, None, ">", ["max", "sum", "count"], "YS", min_gap=3)
-    assert mx.values[0] == 10 and total.values[0] == 15 and n.values[0] == 2
-    mx1, n1 = generic.spell_length_statistics(da, 0.5, 1, None, ">", ["max", "count"], "YS")
-    assert mx1.values[0] == 5 and n1.values[0] == 4

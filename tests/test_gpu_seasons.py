@@ -85,22 +85,3 @@ def test_growing_season_reference_known_answers(cuda, d1, d2, mid_date, expected
     if mid_date == "07-01":
         exp_len = {"1950-01-01": 0, "2000-01-01": 365, "2000-07-10": 0, "2000-06-15": 31}[d1]
         assert indices.growing_season_length(da).values[0] == exp_len
-
-
-@pytest.mark.parametrize("op,expected", [(">", 6), (">=", 5), ("==", 5), ("!=", 1), ("lt", 5), ("le", 4), ("eq", 4),
-                                         ("ne", 1)])
-def test_first_day_threshold_reached_reference_known_answers(cuda, op, expected):
-    """tests/test_generic.py:343-383: pr = 0, .001, ..., .007 (flipped for the '<' family), threshold
-    0.004 kg m-2 s-1, after 01-01, window 1."""
-    from xclim_b200 import generic
-    a = np.zeros(365, np.float32)
-    a[:8] = (np.arange(8) / 1000).astype(np.float32)
-    if op in ("lt", "le", "eq", "ne"):
-        a[:8] = a[:8][::-1].copy()
-    pr = make_field(a, "2000-01-01", calendar="noleap", units="kg m-2 s-1")
-    out = generic.first_day_threshold_reached(pr, threshold="0.004 kg m-2 s-1", op=op, after_date="01-01", window=1,
-                                              freq="YS")
-    assert out.values[0] == expected
-    with pytest.raises(ValueError):
-        generic.first_day_threshold_reached(pr, threshold="0.004 kg m-2 s-1", op=">", after_date="01-01", window=1,
-                                            freq="YS", constrain=("<", "<="))
