@@ -184,13 +184,60 @@ def period_boundary_run_range(x2d, poff, range_lo, range_hi, op_code, thr, windo
     return torch.from_numpy(out)
 
 
+def bootstrap_doy_count(x2d, base_start, n_base_years, year_len, step_period, P, window, percentile, alpha, beta,
+                        op_code):
+    """(P, C) float64: mean over the other base years of the in-base period counts; 0 for periods without
+    base steps (the C-ABI contract of xc_bootstrap_doy_count_f32)."""
+    x = _np(x2d)
+    nb = n_base_years * year_len
+    xb = x[base_start:base_start + nb]
+    year = np.repeat(np.arange(n_base_years), year_len)
+    doy = np.tile(np.arange(1, year_len + 1), n_base_years)
+    sp = np.asarray(step_period)
+    out = np.zeros((P, x.shape[1]))
+    for y in range(n_base_years):
+        rows = np.nonzero(year == y)[0]
+        acc = {}
+        for s_ in range(n_base_years):
+            if s_ == y:
+                continue
+            z = xb.copy()
+            z[rows] = xb[year == s_]
+            tab = O.percentile_doy(z, year, doy, int(window), float(percentile), alpha, beta)[:, 0]
+            hit = O.compare(xb[rows].astype(np.float64), OP_NAME[op_code], tab[doy[rows] - 1])
+            for p in np.unique(sp[rows]):
+                acc.setdefault(int(p), []).append(hit[sp[rows] == p].sum(0))
+        for p, lst in acc.items():
+            out[p] = np.mean(np.stack(lst), axis=0)
+    return torch.from_numpy(out)
+
+
+def eqm_train(ref2d, hist2d, nq, kind_code):
+    af, hq = O.eqm_train(_np(ref2d), _np(hist2d), int(nq), "+" if kind_code == 0 else "*")
+    return torch.from_numpy(np.ascontiguousarray(af, dtype=np.float32)), \
+        torch.from_numpy(np.ascontiguousarray(hq, dtype=np.float32))
+
+
+def eqm_adjust(sim2d, af, hq, kind_code, interp_code):
+    out = O.eqm_adjust(_np(sim2d), _np(af), _np(hq), "+" if kind_code == 0 else "*",
+                       "linear" if interp_code == 1 else "nearest")
+    return torch.from_numpy(np.ascontiguousarray(out, dtype=np.float32))
+
+
+def period_run_quantile(x2d, poff, op_code, thr, q, window, resample_before_rl=True, cmp_f64=False):
+    out = O.resample_and_rl(_cond(_np(x2d), op_code, thr, cmp_f64), bool(resample_before_rl), O.rle_statistics,
+                            poff=poff, reducer=f"q{int(round(q * 100)):02d}", window=int(window))
+    return torch.from_numpy(np.asarray(out, dtype=np.float32))
+
+
 def dev_ints(arr, dtype, device):
     return torch.from_numpy(np.ascontiguousarray(np.asarray(arr, dtype=dtype)))
 
 
 FUNCTIONS = [to_time_cell, period_count, period_runstat, period_runstat_gap, period_reduce, rolling_period_reduce,
              spell_runstat, period_run_maxsum, period_runstat2, percentile_doy, doy_interp, doy_threshold_count,
-             mask_steps, dev_ints, period_boundary_run, period_boundary_run_range]
+             mask_steps, dev_ints, period_boundary_run, period_boundary_run_range, bootstrap_doy_count, eqm_train,
+             eqm_adjust, period_run_quantile]
 
 
 def install(monkeypatch):

@@ -141,3 +141,54 @@ def test_days_over_precip_thresh(host):
         assert got.values.dtype == np.int64 and got.attrs["units"] == "d"
     # the clamp matters: many doy percentiles of this dry series are below 1 mm/d
     assert (tab < 1.0).any() and (tab > 1.0).any()
+
+
+@pytest.mark.parametrize("freq", ["YS", "MS"])
+def test_bootstrap_equal_blocks_host_logic(host, freq):
+    """bootstrapping.py on a noleap calendar: base slice, step -> period map, merge of in-base (bootstrapped)
+    and out-of-base (plain) periods, error behaviour -- against the oracle's literal bootstrap."""
+    from xclim_b200 import calendar as xcal, indices
+    rng = np.random.default_rng(8)
+    T = 365 * 6
+    t = np.arange(T)
+    x = (288 + 10 * np.sin(2 * np.pi * t / 365)[:, None] + 3 * rng.standard_normal((T, 2))).astype(np.float32)
+    da = make_field(x, "1981-01-01", calendar="noleap", units="K")
+    base = da.isel_time(da.time.sel_years(1982, 1985))
+    pdoy = xcal.select_percentile(xcal.percentile_doy(base, window=5, per=90.0), 90.0)
+    got = indices.tx90p(da, pdoy, freq=freq, bootstrap=True)
+    exp = O.bootstrap_doy_count(x, da.time.year, da.time.doy, da.time.period_offsets(freq), (1982, 1985), window=5,
+                                per=90.0, op=">")
+    np.testing.assert_array_equal(got.values, exp)
+    plain = indices.tx90p(da, pdoy, freq=freq).values
+    yrs = np.array([int(s[:4]) for s in da.time.period_labels(freq)])
+    outside = (yrs < 1982) | (yrs > 1985)
+    np.testing.assert_array_equal(got.values[outside], plain[outside])
+    p_all = xcal.select_percentile(xcal.percentile_doy(da, per=90.0), 90.0)
+    with pytest.raises(KeyError, match="all years are overlapping"):
+        indices.tx90p(da, p_all, bootstrap=True)
+
+
+def test_eqm_host_wrapper(host):
+    """sdba.EmpiricalQuantileMapping: train / ds / adjust wrapping (dims, coords, dtype, errors)."""
+    from xclim_b200 import sdba
+    rng = np.random.default_rng(9)
+    T, shape = 730, (2, 3)
+    ref = (285 + 6 * rng.standard_normal((T,) + shape)).astype(np.float32)
+    hist = (286.5 + 7 * rng.standard_normal((T,) + shape)).astype(np.float32)
+    sim = (288.5 + 7 * rng.standard_normal((T,) + shape)).astype(np.float32)
+    f = lambda a: make_field(a, "1981-01-01", calendar="noleap", units="K")  # noqa: E731
+    qm = sdba.EmpiricalQuantileMapping.train(f(ref), f(hist), nquantiles=15, kind="+", group="time")
+    ds = qm.ds
+    assert ds["af"].values.shape == (15,) + shape and ds["hist_q"].dims[0] == "quantiles"
+    np.testing.assert_allclose(ds["af"].coords["quantiles"], sdba.equally_spaced_nodes(15), rtol=1e-6)
+    af, hq = O.eqm_train(ref, hist, 15, "+")
+    np.testing.assert_allclose(ds["af"].values, af, rtol=1e-5, atol=1e-5)
+    scen = qm.adjust(f(sim), interp="linear")
+    np.testing.assert_allclose(scen.values, O.eqm_adjust(sim, af, hq, "+", "linear"), rtol=1e-5)
+    assert scen.values.dtype == np.float32 and scen.values.shape == sim.shape and scen.attrs["units"] == "K"
+    with pytest.raises(NotImplementedError):
+        sdba.EmpiricalQuantileMapping.train(f(ref), f(hist), group="time.month")
+    with pytest.raises(ValueError):
+        sdba.EmpiricalQuantileMapping.train(f(ref), f(hist), kind="-")
+    with pytest.raises(NotImplementedError):
+        qm.adjust(f(sim), interp="cubic")
