@@ -192,3 +192,61 @@ def test_eqm_host_wrapper(host):
         sdba.EmpiricalQuantileMapping.train(f(ref), f(hist), kind="-")
     with pytest.raises(NotImplementedError):
         qm.adjust(f(sim), interp="cubic")
+
+
+# ---- the bodies of the GPU parity tests, run on the CPU over the oracle-backed device functions -------------
+# Every GPU test that talks to the package only through its public host API (no explicit .cuda() tensors,
+# no error raised by the C library itself) is executed here as well: the comparison against the oracle is
+# then trivial for the kernels, but every line of host code on the way (unit conversion, operator codes,
+# period offsets, date ranges of the season functions, missing-value masks, bootstrap bookkeeping, wrapping)
+# runs in the GPU-less suite too.
+GPU_BODIES = {
+    "test_gpu_missing": ["test_indicator_level_entry_points_apply_missing_any", "test_missing_masks"],
+    "test_gpu_seasons": ["test_date_bounded_runs_parity", "test_growing_season_reference_known_answers",
+                         "test_season_parity"],
+    "test_gpu_boundary": ["test_first_last_run"],
+    "test_gpu_period_stats": ["test_bivariate_heat_waves", "test_cdd_reference_known_answers",
+                              "test_hot_spell_max_magnitude", "test_resample_reductions",
+                              "test_run_length_module_masks", "test_run_length_quantile_reducers",
+                              "test_run_length_reference_known_answers", "test_select_time_indexers_on_resample_ops",
+                              "test_spell_length_statistics_window1", "test_threshold_count_all_ops"],
+    "test_gpu_rolling_spells_eqm": ["test_dry_spell_reference_known_answers", "test_eqm_train_adjust",
+                                    "test_rolling_reference_known_answers", "test_rolling_resample",
+                                    "test_spell_length_statistics_min_gap", "test_spell_length_statistics_windows",
+                                    "test_spell_mask_reference_truth_tables"],
+    "test_gpu_bootstrap": ["test_bootstrap_error_behaviour", "test_bootstrap_matches_literal_restatement",
+                           "test_bootstrap_standard_calendar_365_366_blocks"],
+    "test_gpu_percentile": ["test_percentile_doy_mid_percentiles_selection_kernel",
+                            "test_percentile_doy_reference_known_answers",
+                            "test_percentile_doy_standard_calendar_and_366", "test_tx90p_counts",
+                            "test_tx90p_reference_known_answer_leap_year"],
+}
+MAX_COMBOS = 4   # per test function: the oracle is slow, the host code paths repeat
+
+
+def _gpu_body_cases():
+    import importlib
+    cases = []
+    for mod, names in GPU_BODIES.items():
+        m = importlib.import_module(mod)
+        for name in names:
+            fn = getattr(m, name)
+            combos = [{}]
+            for mk in [k for k in getattr(fn, "pytestmark", []) if k.name == "parametrize"]:
+                keys = [n.strip() for n in mk.args[0].split(",")]
+                grown = []
+                for c in combos:
+                    for val in mk.args[1]:
+                        vals = tuple(val) if (isinstance(val, (tuple, list)) and len(keys) > 1) else (val,)
+                        grown.append({**c, **dict(zip(keys, vals))})
+                combos = grown
+            step = max(1, len(combos) // MAX_COMBOS)
+            for i, c in enumerate(combos[::step][:MAX_COMBOS]):
+                cases.append(pytest.param(mod, name, c, id=f"{mod[9:]}.{name[5:]}-{i}"))
+    return cases
+
+
+@pytest.mark.parametrize("mod,name,kwargs", _gpu_body_cases())
+def test_gpu_test_bodies_over_oracle_backed_device(host, mod, name, kwargs):
+    import importlib
+    getattr(importlib.import_module(mod), name)(None, **kwargs)
