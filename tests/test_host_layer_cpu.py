@@ -250,3 +250,28 @@ def _gpu_body_cases():
 def test_gpu_test_bodies_over_oracle_backed_device(host, mod, name, kwargs):
     import importlib
     getattr(importlib.import_module(mod), name)(None, **kwargs)
+
+
+def test_atmos_generic_missing_any_wrapper(host):
+    """atmos.<index> built by with_missing_any: the index value, NaN where the period has a missing step in
+    ANY time-dependent input (core/indicator.py:1522-1549 + core/missing.py:310-322)."""
+    from xclim_b200 import atmos, indices
+    data = batch._inputs()                                     # 0.3 % NaN scattered in every variable
+    units = {"tas": "K", "tasmax": "K", "tasmin": "K", "pr": "mm/d"}
+    f = {k: make_field(v, "1981-01-01", calendar="noleap", units=units[k]) for k, v in data.items()}
+    for name, var in [("frost_days", "tasmin"), ("dry_spell_frequency", "pr"), ("growing_degree_days", "tas"),
+                      ("tx_max", "tasmax")]:
+        freq = "MS"
+        got = getattr(atmos, name)(f[var], freq=freq).values
+        ref = getattr(indices, name)(f[var], freq=freq).values.astype(np.float64)
+        miss = O.missing_any(data[var], f[var].time.period_offsets(freq))
+        assert miss.any() and not miss.all()
+        np.testing.assert_array_equal(np.isnan(got), miss | np.isnan(ref), err_msg=name)
+        np.testing.assert_array_equal(got[~miss], ref[~miss], err_msg=name)
+    # two time-dependent inputs: either one missing masks the period
+    got = atmos.heat_wave_frequency(f["tasmin"], f["tasmax"], freq="MS") if hasattr(atmos, "heat_wave_frequency") else None
+    hw = atmos.with_missing_any(indices.heat_wave_frequency)(f["tasmin"], f["tasmax"], freq="MS").values
+    poff = f["tasmin"].time.period_offsets("MS")
+    both = O.missing_any(data["tasmin"], poff) | O.missing_any(data["tasmax"], poff)
+    np.testing.assert_array_equal(np.isnan(hw), both)
+    assert got is None or np.array_equal(np.isnan(got.values), both)

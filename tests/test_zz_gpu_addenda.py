@@ -66,3 +66,9 @@ def test_first_day_threshold_reached_reference_known_answers(cuda, op, expected)
     with pytest.raises(ValueError):
         generic.first_day_threshold_reached(pr, threshold="0.004 kg m-2 s-1", op=">", after_date="01-01", window=1,
                                             freq="YS", constrain=("<", "<="))
+
+
+def test_atmos_generic_missing_any_wrapper_on_device(cuda):
+    """tests/test_host_layer_cpu.py::test_atmos_generic_missing_any_wrapper through the real kernels."""
+    import test_host_layer_cpu as cpu_side
+    cpu_side.test_atmos_generic_missing_any_wrapper(None)

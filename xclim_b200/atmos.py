@@ -77,3 +77,68 @@ def tx90p(tasmax, tasmax_per, freq="YS", bootstrap=False, op=">"):
     attrs.update(units="days", cell_methods="time: sum over days")
     return _wrap_periods(tasmax, _mask_missing(cnt, valid, poff), cell_shape, other, ta, freq, attrs, dtype=np.float64,
                          name="tx90p")
+
+
+# ---- generic indicator wrapper ---------------------------------------------------------------------------
+def with_missing_any(index_fn, name=None):
+    """Indicator-level version of an index function: the same call, then periods in which ANY input
+    variable has a missing (NaN) step become NaN -- ``CheckMissingIndicator._postprocess``
+    (core/indicator.py:1522-1549) with the default ``MissingAny`` (core/missing.py:310-322).  The
+    non-NaN counts come from one extra streaming pass per input (``xc_period_count_f32`` with the
+    NOTNAN operator); the three hand-written entry points above fuse that count into the index kernel."""
+    import functools
+    import inspect
+
+    from .field import Field, dims_of, is_xarray
+
+    sig = inspect.signature(index_fn)
+
+    @functools.wraps(index_fn)
+    def indicator(*args, **kwargs):
+        out = index_fn(*args, **kwargs)
+        bound = sig.bind(*args, **kwargs)
+        bound.apply_defaults()
+        freq = bound.arguments.get("freq")
+        if freq is None:
+            return out
+        bad = None
+        for val in bound.arguments.values():
+            if not (isinstance(val, Field) or is_xarray(val)) or "time" not in dims_of(val):
+                continue                     # thresholds, percentile tables (dayofyear), options
+            x2d, cell_shape, other, ta = _unwrap(val)
+            poff = ta.period_offsets(freq)
+            _, valid = device.period_count(x2d, poff, _lib.OP_NOTNAN, 0.0, want_valid=True)
+            n = torch.from_numpy(np.diff(poff).astype(np.int32)).to(valid.device)[:, None]
+            miss = (valid != n).reshape((len(poff) - 1,) + cell_shape)
+            bad = miss if bad is None else (bad | miss)
+        if bad is None:
+            return out
+        outs = out if isinstance(out, tuple) else (out,)
+        masked = []
+        for o in outs:
+            v = o.values
+            if hasattr(v, "is_cuda"):
+                v = torch.where(bad.to(v.device), torch.full_like(v, float("nan"), dtype=torch.float64), v.to(torch.float64))
+            else:
+                v = np.where(bad.cpu().numpy(), np.nan, np.asarray(v, dtype=np.float64))
+            if is_xarray(o):
+                masked.append(o.copy(data=v))
+            else:
+                masked.append(Field(v, o.dims, o.time, dict(o.coords), dict(o.attrs), o.name))
+        return tuple(masked) if isinstance(out, tuple) else masked[0]
+
+    indicator.__name__ = name or index_fn.__name__
+    return indicator
+
+
+def _register_batch():
+    """``atmos.<name>`` for every index of the batch-of-50 list that has no hand-fused version above."""
+    from . import indices
+    g = globals()
+    for nm, _var in indices.BATCH_INDICATORS:
+        if nm not in g:
+            g[nm] = with_missing_any(getattr(indices, nm), nm)
+
+
+_register_batch()
+
