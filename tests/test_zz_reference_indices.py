@@ -440,3 +440,27 @@ def test_surface_wind_statistics(backend):                              # :4443-
     np.testing.assert_allclose(indices.sfcWindmax_max(w).values, [15.27], rtol=1e-6)
     np.testing.assert_allclose(indices.sfcWindmax_mean(w).values, [13.36], rtol=1e-6)
     np.testing.assert_allclose(indices.sfcWindmax_min(w).values, [10.70], rtol=1e-6)
+
+
+def test_atmos_consecutive_frost_days(backend):          # tests/test_temperature.py:291-340
+    """Indicator level (index + MissingAny): the answers of atmos.consecutive_frost_days."""
+    from xclim_b200 import atmos
+    f = atmos.maximum_consecutive_frost_days
+
+    def ts(mod, units="K", base=K2C + 5.0):
+        a = np.zeros(365) + base
+        mod(a)
+        return series(a, units)
+
+    def one(a): a[2] -= 20
+    def three(a): a[2:5] -= 20
+    def two_equal(a): a[2:5] -= 20; a[6:9] -= 20
+    def two_events(a): a[2:5] -= 20; a[6:10] -= 20
+    np.testing.assert_array_equal(f(ts(one)).values, [1])
+    np.testing.assert_array_equal(f(ts(three)).values, [3])
+    np.testing.assert_array_equal(f(ts(two_equal)).values, [3])
+    np.testing.assert_array_equal(f(ts(two_events)).values, [4])
+    np.testing.assert_array_equal(f(ts(two_events, units="C", base=5.0)).values, [4])
+
+    def one_nan(a): a[2] -= 20; a[-1] = np.nan
+    np.testing.assert_array_equal(f(ts(one_nan)).values, [np.nan])
