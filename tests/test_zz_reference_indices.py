@@ -464,3 +464,33 @@ def test_atmos_consecutive_frost_days(backend):          # tests/test_temperatur
 
     def one_nan(a): a[2] -= 20; a[-1] = np.nan
     np.testing.assert_array_equal(f(ts(one_nan)).values, [np.nan])
+
+
+def test_atmos_cold_spell_days_and_frequency(backend):   # tests/test_temperature.py:368-403
+    from xclim_b200 import atmos
+    a = np.zeros(365)
+    a[10:20] -= 15
+    a[40:43] -= 50
+    a[80:100] -= 30
+    for ts in (series(a + K2C), series(a, "C")):
+        np.testing.assert_array_equal(atmos.cold_spell_days(ts, thresh="-10 C", freq="MS").values,
+                                      [10, 0, 12, 8, 0, 0, 0, 0, 0, 0, 0, 0])
+        np.testing.assert_array_equal(atmos.cold_spell_frequency(ts, thresh="-10 C", freq="MS").values,
+                                      [1, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, 0])
+    b = a + K2C
+    b[-1] = np.nan
+    np.testing.assert_array_equal(atmos.cold_spell_days(series(b), thresh="-10 C", freq="MS").values,
+                                  [10, 0, 12, 8, 0, 0, 0, 0, 0, 0, 0, np.nan])
+    np.testing.assert_array_equal(atmos.cold_spell_frequency(series(b), thresh="-10 C", freq="MS").values,
+                                  [1, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0, np.nan])
+
+
+def test_atmos_heat_wave_index(backend):                  # tests/test_temperature.py:821-845
+    from xclim_b200 import atmos
+    tx = np.zeros(366)
+    tx[:10] = np.array([29, 31, 31, 31, 29, 31, 31, 31, 31, 31])
+    np.testing.assert_array_equal(atmos.heat_wave_index(series(tx + K2C, start="2000-01-01"), freq="YS").values, [10])
+    np.testing.assert_array_equal(atmos.heat_wave_index(series(tx, "C", start="2000-01-01"), freq="YS").values, [10])
+    tx[-1] = np.nan
+    np.testing.assert_array_equal(atmos.heat_wave_index(series(tx + K2C, start="2000-01-01"), freq="YS").values,
+                                  [np.nan])
