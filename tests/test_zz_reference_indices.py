@@ -494,3 +494,18 @@ def test_atmos_heat_wave_index(backend):                  # tests/test_temperatu
     tx[-1] = np.nan
     np.testing.assert_array_equal(atmos.heat_wave_index(series(tx + K2C, start="2000-01-01"), freq="YS").values,
                                   [np.nan])
+
+
+def test_atmos_dry_spell_total_and_max_length_with_missing_day(backend):   # tests/test_precip.py:645-674
+    """Without the select_time indexer: the NaN on 1 January masks January, no 7-day window totalling
+    less than 3.1 mm exists after it."""
+    from xclim_b200 import atmos, indices
+    pr = series([np.nan] + [1] * 4 + [0] * 10 + [1] * 350, "mm/d", start="1900-01-01")
+    out = atmos.dry_spell_total_length(pr, window=7, op="sum", thresh="3.1 mm", freq="MS")
+    np.testing.assert_allclose(out.values, [np.nan] + [0] * 11)
+    out = atmos.dry_spell_max_length(pr, window=7, op="sum", thresh="3.1 mm", freq="MS")
+    np.testing.assert_allclose(out.values, [np.nan] + [0] * 11)
+    # the index itself (no missing-value mask) sees the dry spell of January: the ten zeros plus the
+    # days whose 7-day windows still total less than 3.1 mm
+    raw = indices.dry_spell_total_length(pr, window=7, op="sum", thresh="3.1 mm", freq="MS").values
+    assert raw[0] > 0 and (raw[1:] == 0).all()
