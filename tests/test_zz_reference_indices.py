@@ -509,3 +509,31 @@ def test_atmos_dry_spell_total_and_max_length_with_missing_day(backend):   # tes
     # days whose 7-day windows still total less than 3.1 mm
     raw = indices.dry_spell_total_length(pr, window=7, op="sum", thresh="3.1 mm", freq="MS").values
     assert raw[0] > 0 and (raw[1:] == 0).all()
+
+
+@pytest.mark.parametrize("name", ["tg90p", "tn90p", "tx90p"])
+def test_atmos_t90p(backend, name):                       # tests/test_temperature.py:1090-1181
+    from xclim_b200 import atmos, calendar as xcal
+    arr = np.arange(366, dtype=np.float32)
+    t90 = xcal.select_percentile(xcal.percentile_doy(series(arr, start="2000-01-01"), window=1, per=90), 90.0)
+    x = arr.copy()
+    x[175:180] = 1
+    out = getattr(atmos, name)(series(x, start="2000-01-01"), t90, freq="MS").values
+    assert out[0] == 30 and out[1] == 29 and out[5] == 25
+    x[33] = np.nan
+    out = getattr(atmos, name)(series(x, start="2000-01-01"), t90, freq="MS").values
+    assert out[0] == 30 and np.isnan(out[1]) and out[5] == 25
+
+
+@pytest.mark.parametrize("name", ["tg10p", "tn10p", "tx10p"])
+def test_atmos_t10p(backend, name):                       # tests/test_temperature.py:1197-1288
+    from xclim_b200 import atmos, calendar as xcal
+    arr = np.arange(366, dtype=np.float32)
+    t10 = xcal.select_percentile(xcal.percentile_doy(series(arr, start="2000-01-01"), per=10), 10.0)
+    x = arr.copy()
+    x[175:180] = 1
+    out = getattr(atmos, name)(series(x, start="2000-01-01"), t10, freq="MS").values
+    assert out[0] == 0 and out[5] == 5
+    x[33] = np.nan
+    out = getattr(atmos, name)(series(x, start="2000-01-01"), t10, freq="MS").values
+    assert out[0] == 0 and np.isnan(out[1]) and out[5] == 5

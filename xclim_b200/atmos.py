@@ -142,3 +142,14 @@ def _register_batch():
 
 _register_batch()
 
+
+def __getattr__(name):
+    """Any other index of :mod:`xclim_b200.indices` at indicator level, built on first use."""
+    from . import indices
+    fn = getattr(indices, name, None)
+    if callable(fn) and not name.startswith("_"):
+        wrapped = with_missing_any(fn, name)
+        globals()[name] = wrapped
+        return wrapped
+    raise AttributeError(f"module 'xclim_b200.atmos' has no attribute {name!r}")
+
