@@ -111,12 +111,14 @@ def threshold_count(x, op, threshold, poff, constrain=None):
 # --------------------------------------------------------------------------------------------------
 # a19 MissingAny (core/missing.py:296-298, 318-322; applied core/indicator.py:1536-1547)
 # --------------------------------------------------------------------------------------------------
-def missing_any(x, poff):
-    """True where a period has fewer valid (non-NaN) steps than source steps."""
+def missing_any(x, poff, expected=None):
+    """core/missing.py:310-322: True where a period has fewer valid (non-NaN) steps than ``expected``
+    (``expected_count``, :64-160: the length of the complete period in the calendar; the observed
+    number of steps when not given, which is the same for periods the series covers completely)."""
     valid = ~np.isnan(x)
     out = []
-    for s, e in _groups(poff):
-        out.append(valid[s:e].sum(axis=0) != (e - s))
+    for p, (s, e) in enumerate(_groups(poff)):
+        out.append(valid[s:e].sum(axis=0) != ((e - s) if expected is None else int(expected[p])))
     return np.stack(out, axis=0)
 
 
@@ -803,12 +805,13 @@ def season(cond, window, mids, poff, stat, doy=None, has_date=True):
 # --------------------------------------------------------------------------------------------------
 # missing-value masks beyond "any" (core/missing.py:338-522)
 # --------------------------------------------------------------------------------------------------
-def missing_pct(x, poff, tolerance):
-    """core/missing.py:476-482."""
+def missing_pct(x, poff, tolerance, expected=None):
+    """core/missing.py:476-482 (``count`` = ``expected_count``, see :func:`missing_any`)."""
     valid = ~np.isnan(x)
     out = []
-    for s, e in _groups(poff):
-        out.append(((e - s) - valid[s:e].sum(axis=0)) / (e - s) >= tolerance)
+    for p, (s, e) in enumerate(_groups(poff)):
+        n = (e - s) if expected is None else int(expected[p])
+        out.append((n - valid[s:e].sum(axis=0)) / n >= tolerance)
     return np.stack(out)
 
 

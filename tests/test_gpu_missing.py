@@ -20,8 +20,11 @@ def test_missing_masks(cuda):
     ta = da.time
     for freq in ("YS", "MS", "QS-DEC"):
         poff = ta.period_offsets(freq)
-        np.testing.assert_array_equal(missing.missing_any(da, freq).values, O.missing_any(x, poff))
-        np.testing.assert_array_equal(missing.missing_pct(da, freq, 0.05).values, O.missing_pct(x, poff, 0.05))
+        n_exp = ta.expected_period_lengths(freq)      # QS-DEC: the first and last quarters are incomplete
+        np.testing.assert_array_equal(missing.missing_any(da, freq).values, O.missing_any(x, poff, n_exp))
+        np.testing.assert_array_equal(missing.missing_pct(da, freq, 0.05).values, O.missing_pct(x, poff, 0.05, n_exp))
+        if freq == "QS-DEC":
+            assert missing.missing_any(da, freq).values[[0, -1]].all()
         np.testing.assert_array_equal(missing.at_least_n_valid(da, freq, 25).values, O.at_least_n_valid(x, poff, 25))
         pm = ta.period_offsets("MS")
         parent = np.searchsorted(poff, pm[:-1], side="right") - 1

@@ -34,3 +34,22 @@ def test_bootstrap_groups():
     np.testing.assert_array_equal(ta.bootstrap_group_ids("MS"), ta.group_ids("YS"))
     np.testing.assert_array_equal(ta.bootstrap_group_ids("YS-JUL"), ta.group_ids("YS-JUL"))
     assert parse_offset("QS-DEC") == (1, "Q", True, "DEC")
+
+
+@pytest.mark.parametrize("start,n", [("2000-01-01", 731), ("1999-11-17", 900), ("2003-02-28", 400)])
+@pytest.mark.parametrize("freq", ["YS", "YS-JUL", "QS-DEC", "MS", "YE", "ME"])
+def test_expected_period_lengths_match_pandas(start, n, freq):
+    """core/missing.py:64-160 (`expected_count`, daily source): the days between consecutive period labels."""
+    import pandas as pd
+    from xclim_b200 import TimeAxis
+    ta = TimeAxis.daily(start, n)
+    idx = pd.date_range(start, periods=n, freq="D")
+    res = pd.Series(1, index=idx).resample(freq).count().index
+    if freq.endswith("S") or "S-" in freq:
+        nxt = res.shift(1, freq=freq)
+        exp = (nxt - res).days
+    else:
+        prev = res.shift(-1, freq=freq)
+        exp = (res - prev).days
+    np.testing.assert_array_equal(ta.expected_period_lengths(freq), np.asarray(exp))
+    assert (ta.expected_period_lengths(freq) >= np.diff(ta.period_offsets(freq))).all()

@@ -537,3 +537,16 @@ def test_atmos_t10p(backend, name):                       # tests/test_temperatu
     x[33] = np.nan
     out = getattr(atmos, name)(series(x, start="2000-01-01"), t10, freq="MS").values
     assert out[0] == 0 and np.isnan(out[1]) and out[5] == 5
+
+
+def test_atmos_frost_season_length_incomplete_periods(backend):   # tests/test_temperature.py:351-365
+    """The first and last YS-JUL periods of a 2000-01-01 .. 2001-12-31 series are incomplete: MissingAny
+    compares the valid count with the length of the COMPLETE period (core/missing.py:64-160)."""
+    from xclim_b200 import atmos
+    a = np.zeros(731) + K2C + 15
+    a[300:400] = K2C - 5
+    a[404:407] = K2C - 5
+    tasmin = series(a, start="2000-01-01")
+    np.testing.assert_array_equal(atmos.frost_season_length(tasmin).values, [np.nan, 107, np.nan])
+    np.testing.assert_array_equal(atmos.frost_season_length(tasmin, window=3).values, [np.nan, 100, np.nan])
+    np.testing.assert_array_equal(atmos.frost_season_length(tasmin, mid_date="07-01", freq="YS").values, [0, 181])

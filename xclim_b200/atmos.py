@@ -20,8 +20,11 @@ from .generic import _unwrap, _wrap_periods
 from .units import threshold_in_units_of
 
 
-def _mask_missing(out, valid, poff):
-    n = torch.from_numpy(np.diff(poff).astype(np.int32)).to(out.device)[:, None]
+def _mask_missing(out, valid, poff, expected=None):
+    """NaN where the period does not hold every step a complete period has (``expected``: TimeAxis.
+    expected_period_lengths; the observed period lengths when not given)."""
+    n = np.diff(poff) if expected is None else np.asarray(expected)
+    n = torch.from_numpy(n.astype(np.int32)).to(out.device)[:, None]
     res = out.to(torch.float64) if out.dtype in (torch.int32, torch.int64) else out.clone()
     res[valid != n] = float("nan")
     return res
@@ -38,7 +41,7 @@ def maximum_consecutive_dry_days(pr, thresh="1 mm/day", freq="YS", resample_befo
     attrs = attrs_of(pr)
     attrs.update(units="days", standard_name="number_of_days_with_lwe_thickness_of_precipitation_amount_below_threshold",
                  cell_methods="time: maximum over days")
-    return _wrap_periods(pr, _mask_missing(out, valid, poff), cell_shape, other, ta, freq, attrs, dtype=np.float32,
+    return _wrap_periods(pr, _mask_missing(out, valid, poff, ta.expected_period_lengths(freq)), cell_shape, other, ta, freq, attrs, dtype=np.float32,
                          name="cdd")
 
 
@@ -49,7 +52,7 @@ def tg_mean(tas, freq="YS"):
     out, valid = device.period_reduce(x2d, poff, _lib.STATS["mean"], want_valid=True)
     attrs = attrs_of(tas)
     attrs.update(cell_methods="time: mean over days")
-    return _wrap_periods(tas, _mask_missing(out, valid, poff), cell_shape, other, ta, freq, attrs, name="tg_mean")
+    return _wrap_periods(tas, _mask_missing(out, valid, poff, ta.expected_period_lengths(freq)), cell_shape, other, ta, freq, attrs, name="tg_mean")
 
 
 def tx90p(tasmax, tasmax_per, freq="YS", bootstrap=False, op=">"):
@@ -63,7 +66,7 @@ def tx90p(tasmax, tasmax_per, freq="YS", bootstrap=False, op=">"):
         _, valid = device.period_count(x2d, poff, _lib.OP_NOTNAN, 0.0, want_valid=True)
         vals = out.values if hasattr(out.values, "is_cuda") else torch.from_numpy(np.asarray(out.values, np.float64))
         vals = vals.reshape(len(poff) - 1, -1).to(x2d.device)
-        masked = _mask_missing(vals, valid, poff)
+        masked = _mask_missing(vals, valid, poff, ta.expected_period_lengths(freq))
         attrs = attrs_of(out)
         attrs["units"] = "days"
         return _wrap_periods(tasmax, masked, cell_shape, other, ta, freq, attrs, dtype=np.float64, name="tx90p")
@@ -75,7 +78,7 @@ def tx90p(tasmax, tasmax_per, freq="YS", bootstrap=False, op=">"):
     cnt, valid = device.doy_threshold_count(x2d, poff, doy_idx, table, code, want_valid=True)
     attrs = attrs_of(tasmax)
     attrs.update(units="days", cell_methods="time: sum over days")
-    return _wrap_periods(tasmax, _mask_missing(cnt, valid, poff), cell_shape, other, ta, freq, attrs, dtype=np.float64,
+    return _wrap_periods(tasmax, _mask_missing(cnt, valid, poff, ta.expected_period_lengths(freq)), cell_shape, other, ta, freq, attrs, dtype=np.float64,
                          name="tx90p")
 
 
@@ -108,7 +111,7 @@ def with_missing_any(index_fn, name=None):
             x2d, cell_shape, other, ta = _unwrap(val)
             poff = ta.period_offsets(freq)
             _, valid = device.period_count(x2d, poff, _lib.OP_NOTNAN, 0.0, want_valid=True)
-            n = torch.from_numpy(np.diff(poff).astype(np.int32)).to(valid.device)[:, None]
+            n = torch.from_numpy(ta.expected_period_lengths(freq).astype(np.int32)).to(valid.device)[:, None]
             miss = (valid != n).reshape((len(poff) - 1,) + cell_shape)
             bad = miss if bad is None else (bad | miss)
         if bad is None:

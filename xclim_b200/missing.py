@@ -36,7 +36,9 @@ def missing_any(da, freq, src_timestep="D", **indexer):
         raise NotImplementedError("select_time indexers are outside the B200 hot path")
     x2d, cell_shape, other, ta = _unwrap(da)
     poff = ta.period_offsets(freq)
-    n = torch.from_numpy(np.diff(poff).astype(np.int32)).to(x2d.device)[:, None]
+    # expected_count (core/missing.py:64-160): a complete period of this calendar, so that a first / last
+    # period the series only partly covers is missing as well
+    n = torch.from_numpy(ta.expected_period_lengths(freq).astype(np.int32)).to(x2d.device)[:, None]
     return _finish(da, _valid_counts(x2d, poff) != n, cell_shape, other, ta, freq)
 
 
@@ -48,7 +50,7 @@ def missing_pct(da, freq, tolerance, src_timestep="D", **indexer):
         raise ValueError("Options (tolerance) are invalid for missing method MissingPct.")
     x2d, cell_shape, other, ta = _unwrap(da)
     poff = ta.period_offsets(freq)
-    n = torch.from_numpy(np.diff(poff).astype(np.float64)).to(x2d.device)[:, None]
+    n = torch.from_numpy(ta.expected_period_lengths(freq).astype(np.float64)).to(x2d.device)[:, None]
     miss = (n - _valid_counts(x2d, poff).double()) / n >= tolerance
     return _finish(da, miss, cell_shape, other, ta, freq)
 

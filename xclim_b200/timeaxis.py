@@ -227,6 +227,45 @@ class TimeAxis:
                 labels.append(f"{ye:04d}-{me:02d}-{dl:02d}")
         return labels
 
+    def expected_period_lengths(self, freq: str) -> np.ndarray:
+        """Number of daily steps every ``resample(time=freq)`` period holds in this calendar when it is
+        complete -- ``expected_count`` of core/missing.py:64-160 for a daily source without indexer
+        (``end_time - start_time`` between consecutive period labels).  A first / last period that the
+        series only partly covers therefore expects more steps than it has."""
+        mult, base, start, anchor = parse_offset(freq)
+        off = self.period_offsets(freq)
+        P = off.size - 1
+        if base == "D":
+            return np.full(P, mult, np.int64)
+        span = {"Y": 12, "Q": 3, "M": 1}[base] * mult
+        out = np.zeros(P, np.int64)
+        for p in range(P):
+            i = int(off[p])
+            y, m = int(self.year[i]), int(self.month[i])
+            if base == "M":
+                ys, ms = y, m
+            elif base == "Q":
+                am = _MONTHS.index(anchor)
+                first_month = (am if start else (am + 1)) % 3
+                tot = ((y * 12 + m - 1 - first_month) // 3) * 3 + first_month
+                ys, ms = divmod(tot, 12)
+                ms += 1
+            else:
+                am = _MONTHS.index(anchor)
+                first_month = am if start else (am + 1) % 12
+                ys = y if (m - 1) >= first_month else y - 1
+                ms = first_month + 1
+            n = 0
+            for k in range(span):
+                yy, mm = divmod(ys * 12 + ms - 1 + k, 12)
+                if self.calendar == "360_day":
+                    n += 30
+                else:
+                    dpm = _DPM_LEAP if bool(_is_leap(np.array(yy), self.calendar)) else _DPM_NOLEAP
+                    n += int(dpm[mm])
+            out[p] = n
+        return out
+
     def bootstrap_group_ids(self, freq: str) -> np.ndarray:
         """Year grouping used by the percentile bootstrap (core/bootstrapping.py:214-223):
         ``Y`` + ``S``/``E`` + the anchor of ``freq`` when its base is yearly or quarterly."""
