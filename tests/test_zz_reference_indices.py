@@ -550,3 +550,29 @@ def test_atmos_frost_season_length_incomplete_periods(backend):   # tests/test_t
     np.testing.assert_array_equal(atmos.frost_season_length(tasmin).values, [np.nan, 107, np.nan])
     np.testing.assert_array_equal(atmos.frost_season_length(tasmin, window=3).values, [np.nan, 100, np.nan])
     np.testing.assert_array_equal(atmos.frost_season_length(tasmin, mid_date="07-01", freq="YS").values, [0, 181])
+
+
+def test_atmos_growing_season_length(backend):            # tests/test_temperature.py:904-958
+    """Warm May..August (>= 5.5 degC above freezing), 0 degC otherwise: the season is those 123 days."""
+    from xclim_b200 import atmos
+    rng = np.random.default_rng(21)
+
+    def year_series(n_years=1, units="K", nan_at=None):
+        vals, starts = [], 0
+        ta = series(np.zeros(366 * n_years), start="2000-01-01").time
+        v = np.zeros(len(ta)) + (K2C if units == "K" else 0)
+        tt = (ta.month >= 5) & (ta.month <= 8)
+        v[tt] += rng.uniform(5.5, 23, size=int(tt.sum()))
+        if nan_at is not None:
+            v[nan_at] = np.nan
+        return series(v, units, start="2000-01-01"), tt
+
+    ts, tt = year_series()
+    np.testing.assert_array_equal(atmos.growing_season_length(ts).values, [tt.sum()])
+    ts, tt = year_series(units="C")
+    np.testing.assert_array_equal(atmos.growing_season_length(ts).values, [tt.sum()])
+    ts, _ = year_series(units="C", nan_at=50)
+    np.testing.assert_array_equal(atmos.growing_season_length(ts).values, [np.nan])
+    ts, tt = year_series(n_years=10, units="C")
+    out = atmos.growing_season_length(ts).values
+    assert out[3] == tt[:366].sum() and np.isnan(out[-1])   # 3660 days end on 2010-01-07: the last year is incomplete
