@@ -576,3 +576,17 @@ def test_atmos_growing_season_length(backend):            # tests/test_temperatu
     ts, tt = year_series(n_years=10, units="C")
     out = atmos.growing_season_length(ts).values
     assert out[3] == tt[:366].sum() and np.isnan(out[-1])   # 3660 days end on 2010-01-07: the last year is incomplete
+
+
+@pytest.mark.parametrize("name", ["tg10p", "tx10p", "tn10p"])
+def test_index_t10p_and_dayofyear_requirement(backend, name):   # :2529-2570
+    from xclim_b200 import calendar as xcal, indices
+    arr = np.arange(366, dtype=np.float32)
+    tas = series(arr, start="2000-01-01")
+    t10 = xcal.select_percentile(xcal.percentile_doy(tas, per=10), 10.0)
+    x = arr.copy()
+    x[175:180] = 1
+    out = getattr(indices, name)(series(x, start="2000-01-01"), t10, freq="MS").values
+    assert out[0] == 0 and out[5] == 5
+    with pytest.raises(AttributeError, match="dayofyear"):
+        getattr(indices, name)(tas, tas, freq="MS")
