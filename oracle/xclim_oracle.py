@@ -821,19 +821,25 @@ def at_least_n_valid(x, poff, n):
     return np.stack([valid[s:e].sum(axis=0) < n for s, e in _groups(poff)])
 
 
-def missing_wmo(x, poff_month, parent, n_parent, nm=11, nc=5):
-    """core/missing.py:434-450 at the monthly step, then MissingAny over the months of every coarser
-    period (:384-391).  ``parent[m]`` = index of the coarser period holding month m."""
+def missing_wmo(x, poff_month, parent, n_parent, nm=11, nc=5, expected_month=None, months_per_period=None):
+    """core/missing.py:434-450 at the monthly step (``count`` = days of the complete month when
+    ``expected_month`` is given), then MissingAny over the months of every coarser period (:384-391:
+    missing months are NaN, and a period holding fewer than ``months_per_period`` months is missing).
+    ``parent[m]`` = index of the coarser period holding month m."""
     valid = ~np.isnan(x)
     miss_m = []
-    for s, e in _groups(poff_month):
-        missing_days = (e - s) - valid[s:e].sum(axis=0)
+    for m, (s, e) in enumerate(_groups(poff_month)):
+        n = (e - s) if expected_month is None else int(expected_month[m])
+        missing_days = n - valid[s:e].sum(axis=0)
         longest = rle_statistics(~valid[s:e], "max", 1)
         miss_m.append((missing_days >= nm) | (longest >= nc))
     miss_m = np.stack(miss_m)
     out = np.zeros((n_parent,) + x.shape[1:], bool)
     for m, p in enumerate(parent):
         out[p] |= miss_m[m]
+    if months_per_period is not None:
+        short = np.bincount(np.asarray(parent), minlength=n_parent) != months_per_period
+        out |= short.reshape((-1,) + (1,) * (x.ndim - 1))
     return out
 
 

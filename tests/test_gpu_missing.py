@@ -28,7 +28,8 @@ def test_missing_masks(cuda):
         np.testing.assert_array_equal(missing.at_least_n_valid(da, freq, 25).values, O.at_least_n_valid(x, poff, 25))
         pm = ta.period_offsets("MS")
         parent = np.searchsorted(poff, pm[:-1], side="right") - 1
-        exp = O.missing_wmo(x, pm, parent, len(poff) - 1)
+        exp = O.missing_wmo(x, pm, parent, len(poff) - 1, expected_month=ta.expected_period_lengths("MS"),
+                            months_per_period={"YS": 12, "MS": 1, "QS-DEC": 3}[freq])
         np.testing.assert_array_equal(missing.missing_wmo(da, freq).values, exp, err_msg=freq)
     with pytest.raises(ValueError):
         missing.missing_pct(da, "YS", 1.5)

@@ -275,3 +275,22 @@ def test_atmos_generic_missing_any_wrapper(host):
     both = O.missing_any(data["tasmin"], poff) | O.missing_any(data["tasmax"], poff)
     np.testing.assert_array_equal(np.isnan(hw), both)
     assert got is None or np.array_equal(np.isnan(got.values), both)
+
+
+def test_missing_masks_on_partly_covered_periods(host):
+    """expected_count (core/missing.py:64-160): 400 days from 2000-01-01 -> 2001 holds 34 of 365 days."""
+    from xclim_b200 import missing
+    x = np.ones((400, 2), np.float32)
+    x[10, 1] = np.nan
+    da = make_field(x, "2000-01-01", units="K")
+    np.testing.assert_array_equal(missing.missing_any(da, "YS").values, [[False, True], [True, True]])
+    np.testing.assert_array_equal(missing.missing_pct(da, "YS", 0.5).values, [[False, False], [True, True]])
+    np.testing.assert_array_equal(missing.missing_pct(da, "YS", 0.002).values, [[False, True], [True, True]])
+    np.testing.assert_array_equal(missing.at_least_n_valid(da, "YS", 30).values, [[False, False], [False, False]])
+    np.testing.assert_array_equal(missing.at_least_n_valid(da, "YS", 35).values, [[False, False], [True, True]])
+    np.testing.assert_array_equal(missing.missing_wmo(da, "YS").values, [[False, False], [True, True]])
+    # monthly: February 2001 holds 3 of its 28 days -> 25 missing days >= nm
+    m = missing.missing_wmo(da, "MS").values
+    assert not m[:13].any() and m[13].all()
+    a = missing.missing_any(da, "MS").values
+    assert a[0, 1] and not a[0, 0] and a[13].all() and not a[1:13].any()

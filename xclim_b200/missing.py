@@ -76,7 +76,9 @@ def missing_wmo(da, freq, nm=11, nc=5, src_timestep="D", **indexer):
         raise ValueError(f"Input source timestep {src_timestep} is invalid for missing method MissingWMO.")
     x2d, cell_shape, other, ta = _unwrap(da)
     pm = ta.period_offsets("MS")
-    nmon = torch.from_numpy(np.diff(pm).astype(np.int32)).to(x2d.device)[:, None]
+    # expected_count at the monthly step: the days of the complete month, so a month the series only
+    # partly covers counts its absent days as missing
+    nmon = torch.from_numpy(ta.expected_period_lengths("MS").astype(np.int32)).to(x2d.device)[:, None]
     missing_days = nmon - _valid_counts(x2d, pm)
     longest, _ = device.period_runstat(x2d, pm, _lib.OP_ISNAN, 0.0, _lib.RL_REDUCERS["max"], 1, True)
     miss_m = (missing_days >= nm) | (longest >= nc)
@@ -86,4 +88,10 @@ def missing_wmo(da, freq, nm=11, nc=5, src_timestep="D", **indexer):
     par = torch.from_numpy(parent.astype(np.int64)).to(x2d.device)
     miss = torch.zeros((P, x2d.shape[1]), dtype=torch.int32, device=x2d.device)
     miss.index_add_(0, par, miss_m.to(torch.int32))
-    return _finish(da, miss > 0, cell_shape, other, ta, freq)
+    # second step = MissingAny over the months (:384-391): a period that does not hold all its months is
+    # missing as well
+    from .timeaxis import parse_offset
+    mult, base, _, _ = parse_offset(freq)
+    want = {"Y": 12, "Q": 3, "M": 1}[base] * mult
+    short = torch.from_numpy(np.bincount(parent, minlength=P) != want).to(x2d.device)[:, None]
+    return _finish(da, (miss > 0) | short, cell_shape, other, ta, freq)
