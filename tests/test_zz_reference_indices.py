@@ -590,3 +590,49 @@ def test_index_t10p_and_dayofyear_requirement(backend, name):   # :2529-2570
     assert out[0] == 0 and out[5] == 5
     with pytest.raises(AttributeError, match="dayofyear"):
         getattr(indices, name)(tas, tas, freq="MS")
+
+
+# ---- tests/test_missing.py (values only) --------------------------------------------------------------------
+def test_missing_any_reference_known_answers(backend):     # :55-98
+    from xclim_b200 import missing
+    a = np.arange(360.0)
+    a[5:10] = np.nan
+    out = missing.missing_any(series(a), freq="MS").values
+    assert out[0] and not out[1]
+    np.testing.assert_array_equal(missing.missing_any(series(np.arange(66), "", "2001-12-30"), "MS").values,
+                                  [True, False, False, True])
+    np.testing.assert_array_equal(missing.missing_any(series(np.arange(378), "", "2001-12-31"), "YS").values,
+                                  [True, False, True])
+    np.testing.assert_array_equal(missing.missing_any(series(np.arange(378), "", "2001-12-31"), "QE-NOV").values,
+                                  [True, False, False, False, True])
+    b = np.zeros(365) + K2C + 5.0
+    b[2] -= 20
+    np.testing.assert_array_equal(missing.missing_any(series(b), freq="YS-JUL").values, [False])
+    np.testing.assert_array_equal(missing.missing_any(series(b), freq="YE-JUN").values, [False])
+
+
+def test_missing_wmo_reference_known_answers(backend):     # :165-197
+    from xclim_b200 import missing
+    a = np.arange(360.0)
+    a[5:7] = np.nan
+    a[40:45] = np.nan
+    a[70:92:2] = np.nan
+    out = missing.missing_wmo(series(a), freq="MS").values
+    assert not out[0] and out[1] and out[2]
+    a = np.arange(350.0)
+    a[5:16] = np.nan
+    np.testing.assert_array_equal(missing.missing_wmo(series(a), freq="QS-JAN").values, [True, False, False, True])
+    np.testing.assert_array_equal(missing.missing_wmo(series(np.arange(31.0)), freq="YS").values, [True])
+
+
+def test_missing_pct_and_at_least_n_reference_known_answers(backend):   # :199-230
+    from xclim_b200 import missing
+    a = np.arange(360.0)
+    a[5:7] = np.nan
+    a[40:45] = np.nan
+    out = missing.missing_pct(series(a), freq="MS", tolerance=0.1).values
+    assert not out[0] and out[1]
+    a = np.arange(360.0)
+    a[5:10] = np.nan
+    a[40:55] = np.nan
+    np.testing.assert_array_equal(missing.at_least_n_valid(series(a), freq="MS", n=20).values[:2], [False, True])
