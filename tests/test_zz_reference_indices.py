@@ -636,3 +636,38 @@ def test_missing_pct_and_at_least_n_reference_known_answers(backend):   # :199-2
     a[5:10] = np.nan
     a[40:55] = np.nan
     np.testing.assert_array_equal(missing.at_least_n_valid(series(a), freq="MS", n=20).values[:2], [False, True])
+
+
+def _ar1(alpha, n, rng, positive=False):
+    """tests/test_bootstrapping.py `ar1`: a red-noise series (values only matter statistically)."""
+    x = np.empty(n)
+    x[0] = rng.standard_normal()
+    for i in range(1, n):
+        x[i] = alpha * x[i - 1] + rng.standard_normal()
+    return np.abs(x) if positive else x + 280
+
+
+@pytest.mark.parametrize("name,p,freq", [("tg90p", 98, "MS"), ("tn90p", 98, "YS-JUL"), ("tx90p", 98, "QS-APR"),
+                                         ("tn10p", 2, "MS"), ("tx10p", 2, "YS"), ("tg10p", 2, "MS")])
+def test_bootstrap_property_standard_calendar(backend, name, p, freq):   # tests/test_bootstrapping.py:22-74
+    """Four years on the standard calendar, base 2000-2001 (a leap and a common year: unequal blocks; with
+    anchored frequencies the year groups are partial at both ends): bootstrapping raises the in-base index
+    more often than it lowers it and leaves the out-of-base periods untouched."""
+    from xclim_b200 import calendar as xcal, indices
+    rng = np.random.default_rng(int(p) + len(freq))
+    n = int(4 * 365.25)
+    da = series(_ar1(0.8, n, rng), start="2000-01-01")
+    base = da.isel_time(da.time.sel_years(2000, 2001))
+    per = xcal.select_percentile(xcal.percentile_doy(base, per=p), float(p))
+    fn = getattr(indices, name)
+    plain = fn(da, per, freq=freq, bootstrap=False).values.astype(np.float64)
+    boot = fn(da, per, freq=freq, bootstrap=True).values
+    labels = np.array([int(str(s)[:4]) * 100 + int(str(s)[5:7]) for s in da.time.period_labels(freq)])
+    lengths = np.diff(da.time.period_offsets(freq))
+    starts = da.time.period_offsets(freq)[:-1]
+    in_base = da.time.year[starts] <= 2001                       # the period starts inside the base
+    ends_in_base = da.time.year[starts + lengths - 1] <= 2001
+    inside, outside = in_base & ends_in_base, ~in_base
+    assert np.count_nonzero(boot[inside] > plain[inside]) > np.count_nonzero(boot[inside] < plain[inside])
+    np.testing.assert_array_almost_equal(boot[outside], plain[outside], 15)
+    assert labels.size == boot.shape[0]
