@@ -215,3 +215,23 @@ def test_snowfall_frequency_intensity_and_dates(backend):
     assert indices.last_snowfall(prsnd).values[0] == 187
     none = make_field(np.zeros(5, np.float32), "2000-07-01", units="mm/day")
     assert indices.snowfall_intensity(none).values[0] == 0 and np.isnan(indices.first_snowfall(none).values[0])
+
+
+def test_threshold_and_domain_count(backend):
+    """tests/test_generic.py:69-81 (year-end labels)."""
+    from xclim_b200 import generic
+    ts = make_field(np.arange(365, dtype=np.float32), "2000-07-01", units="K")
+    np.testing.assert_array_equal(generic.threshold_count(ts, "<", 50, "YE").values, [50, 0])
+    np.testing.assert_array_equal(generic.domain_count(ts, low=10, high=20, freq="YE").values, [10, 0])
+
+
+def test_rolling_resample_known_answers(backend):
+    """tests/test_generic.py:35-67: q = 1 .. 1096 over 2000-2002."""
+    from xclim_b200 import generic
+    q = make_field(np.arange(1, 366 + 365 + 365 + 1, dtype=np.float32), "2000-01-01", units="m3 s-1")
+    o = generic.select_rolling_resample_op(q, "max", window=14, window_center=False, window_op="mean")
+    np.testing.assert_array_equal(o.values, [np.mean(np.arange(353, 367)), np.mean(np.arange(353 + 365, 367 + 365)),
+                                             np.mean(np.arange(353 + 730, 367 + 730))])
+    assert o.attrs["units"] == "m3 s-1"
+    o = generic.select_rolling_resample_op(q, "max", window=3, window_center=True, window_op="sum", freq="MS")
+    np.testing.assert_array_equal(o.values[:2], [30 + 31 + 32, 59 + 60 + 61])
