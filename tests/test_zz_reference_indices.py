@@ -671,3 +671,15 @@ def test_bootstrap_property_standard_calendar(backend, name, p, freq):   # tests
     assert np.count_nonzero(boot[inside] > plain[inside]) > np.count_nonzero(boot[inside] < plain[inside])
     np.testing.assert_array_almost_equal(boot[outside], plain[outside], 15)
     assert labels.size == boot.shape[0]
+
+
+def test_precip_average(backend):                         # :2441-2465
+    import pandas as pd
+    from xclim_b200 import indices
+    pr = np.zeros(100)
+    pr[5:10] = 1
+    np.testing.assert_allclose(indices.precip_average(series(pr, "mm/d"), freq="MS").values[0], 5 / 31, rtol=1e-6)
+    t = pd.date_range("2000-01-01", "2010-12-31", freq="D")
+    out = indices.precip_average(series(t.year.values, "mm d-1", start="2000-01-01"))
+    np.testing.assert_allclose(out.values, np.arange(2000, 2011))
+    assert out.attrs["units"] == "mm"

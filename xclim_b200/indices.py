@@ -269,6 +269,12 @@ def precip_accumulation(pr, freq="YS"):
     return _resample(pr, "sum", freq).assign_attrs(units="mm")
 
 
+def precip_average(pr, freq="YS"):
+    """Mean daily precipitation amount -- indices/_multivariate.py:994-1054 without phase separation (input in
+    mm/d -> mm)."""
+    return _resample(pr, "mean", freq).assign_attrs(units="mm")
+
+
 def sfcWind_max(sfcWind, freq="YS"):
     return _resample(sfcWind, "max", freq)
 
