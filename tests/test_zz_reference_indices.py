@@ -683,3 +683,37 @@ def test_precip_average(backend):                         # :2441-2465
     out = indices.precip_average(series(t.year.values, "mm d-1", start="2000-01-01"))
     np.testing.assert_allclose(out.values, np.arange(2000, 2011))
     assert out.attrs["units"] == "mm"
+
+
+# ---- select_time indexers at the indicator level ------------------------------------------------------------
+def test_missing_any_with_indexers(backend):              # tests/test_missing.py:100-124
+    from xclim_b200 import missing
+    ts = series(np.zeros(36))                              # 2000-07-01 .. 2000-08-05
+    np.testing.assert_array_equal(missing.missing_any(ts, freq="YS", month=7).values, [False])
+    np.testing.assert_array_equal(missing.missing_any(ts, freq="YS", month=8).values, [True])
+    np.testing.assert_array_equal(missing.missing_any(ts, freq="YS", month=[7, 8]).values, [True])
+    ts = series(np.zeros(76))
+    np.testing.assert_array_equal(missing.missing_any(ts, freq="YS", month=[7, 8]).values, [False])
+    for cal, n in (("standard", 360), ("noleap", 359), ("360_day", 354)):
+        ts = series(np.zeros(n), start="2000-01-01", calendar=cal)   # ends on 25 (24) December
+        np.testing.assert_array_equal(missing.missing_any(ts, freq="YS", season="MAM").values, [False])
+        np.testing.assert_array_equal(missing.missing_any(ts, freq="YS", season="DJF").values, [True])
+
+
+def test_atmos_tx90p_seasonal_indexer(backend):           # tests/test_temperature.py:1183-1194
+    from xclim_b200 import atmos, calendar as xcal
+    arr = np.arange(366, dtype=np.float32)
+    t90 = xcal.select_percentile(xcal.percentile_doy(series(arr, start="2000-01-01"), window=1, per=90), 90.0)
+    x = arr.copy()
+    x[175:180] = 1
+    out = atmos.tg90p(series(x, start="2000-01-01"), t90, freq="YS", season="JJA")
+    assert out.values[0] == 87      # 92 JJA days minus the five cold ones
+
+
+def test_atmos_dry_spell_with_date_bounds(backend):       # tests/test_precip.py:645-674
+    """The indexer masks the INPUT (NaN before 10 January), then the index runs: three 7-day windows
+    (starting 10, 11, 12 January) total less than 3.1 mm and cover nine days."""
+    from xclim_b200 import atmos
+    pr = series([np.nan] + [1] * 4 + [0] * 10 + [1] * 350, "mm/d", start="1900-01-01")
+    out = atmos.dry_spell_total_length(pr, window=7, op="sum", thresh="3.1 mm", freq="MS", date_bounds=("01-10", "12-31"))
+    np.testing.assert_allclose(out.values, [9] + [0] * 11)

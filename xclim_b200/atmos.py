@@ -95,25 +95,35 @@ def with_missing_any(index_fn, name=None):
     from .field import Field, dims_of, is_xarray
 
     sig = inspect.signature(index_fn)
+    INDEXERS = ("season", "month", "doy_bounds", "date_bounds", "include_bounds")
 
     @functools.wraps(index_fn)
     def indicator(*args, **kwargs):
-        out = index_fn(*args, **kwargs)
+        # select_time indexers are an INDICATOR-level feature (ResamplingIndicatorWithIndexing,
+        # core/indicator.py:1611-1673): the inputs are masked (NaN outside the selection) before the index runs
+        indexer = {k: kwargs.pop(k) for k in INDEXERS if k in kwargs and k not in sig.parameters}
         bound = sig.bind(*args, **kwargs)
         bound.apply_defaults()
         freq = bound.arguments.get("freq")
-        if freq is None:
-            return out
         bad = None
-        for val in bound.arguments.values():
+        for key, val in list(bound.arguments.items()):
             if not (isinstance(val, Field) or is_xarray(val)) or "time" not in dims_of(val):
                 continue                     # thresholds, percentile tables (dayofyear), options
-            x2d, cell_shape, other, ta = _unwrap(val)
+            x2d, cell_shape, other, ta = _unwrap(val, indexer)
+            if indexer and not is_xarray(val):
+                bound.arguments[key] = Field(x2d.reshape((x2d.shape[0],) + cell_shape), ("time",) + other, ta,
+                                             {k: v for k, v in val.coords.items() if k != "time"}, dict(val.attrs),
+                                             val.name)
+            elif indexer:
+                raise NotImplementedError("select_time indexers on xarray inputs: pass xclim_b200.Field inputs")
+            if freq is None:
+                continue
             poff = ta.period_offsets(freq)
             _, valid = device.period_count(x2d, poff, _lib.OP_NOTNAN, 0.0, want_valid=True)
-            n = torch.from_numpy(ta.expected_period_lengths(freq).astype(np.int32)).to(valid.device)[:, None]
+            n = torch.from_numpy(ta.expected_period_lengths(freq, **indexer).astype(np.int32)).to(valid.device)[:, None]
             miss = (valid != n).reshape((len(poff) - 1,) + cell_shape)
             bad = miss if bad is None else (bad | miss)
+        out = index_fn(*bound.args, **bound.kwargs)
         if bad is None:
             return out
         outs = out if isinstance(out, tuple) else (out,)

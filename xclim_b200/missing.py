@@ -31,35 +31,30 @@ def _valid_counts(x2d, poff):
 
 
 def missing_any(da, freq, src_timestep="D", **indexer):
-    """core/missing.py:310-322: a period is missing if any expected step is missing."""
-    if indexer:
-        raise NotImplementedError("select_time indexers are outside the B200 hot path")
-    x2d, cell_shape, other, ta = _unwrap(da)
+    """core/missing.py:310-322: a period is missing if any expected step is missing.  With a
+    ``select_time`` indexer only the selected steps count, on both sides of the comparison."""
+    x2d, cell_shape, other, ta = _unwrap(da, indexer)
     poff = ta.period_offsets(freq)
     # expected_count (core/missing.py:64-160): a complete period of this calendar, so that a first / last
     # period the series only partly covers is missing as well
-    n = torch.from_numpy(ta.expected_period_lengths(freq).astype(np.int32)).to(x2d.device)[:, None]
+    n = torch.from_numpy(ta.expected_period_lengths(freq, **indexer).astype(np.int32)).to(x2d.device)[:, None]
     return _finish(da, _valid_counts(x2d, poff) != n, cell_shape, other, ta, freq)
 
 
 def missing_pct(da, freq, tolerance, src_timestep="D", **indexer):
     """core/missing.py:453-482: missing when the fraction of missing steps reaches ``tolerance``."""
-    if indexer:
-        raise NotImplementedError("select_time indexers are outside the B200 hot path")
     if not 0 <= tolerance <= 1:
         raise ValueError("Options (tolerance) are invalid for missing method MissingPct.")
-    x2d, cell_shape, other, ta = _unwrap(da)
+    x2d, cell_shape, other, ta = _unwrap(da, indexer)
     poff = ta.period_offsets(freq)
-    n = torch.from_numpy(ta.expected_period_lengths(freq).astype(np.float64)).to(x2d.device)[:, None]
+    n = torch.from_numpy(ta.expected_period_lengths(freq, **indexer).astype(np.float64)).to(x2d.device)[:, None]
     miss = (n - _valid_counts(x2d, poff).double()) / n >= tolerance
     return _finish(da, miss, cell_shape, other, ta, freq)
 
 
 def at_least_n_valid(da, freq, n=20, src_timestep="D", **indexer):
     """core/missing.py:485-522: missing when fewer than ``n`` valid steps."""
-    if indexer:
-        raise NotImplementedError("select_time indexers are outside the B200 hot path")
-    x2d, cell_shape, other, ta = _unwrap(da)
+    x2d, cell_shape, other, ta = _unwrap(da, indexer)
     poff = ta.period_offsets(freq)
     return _finish(da, _valid_counts(x2d, poff) < n, cell_shape, other, ta, freq)
 

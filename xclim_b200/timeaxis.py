@@ -227,44 +227,58 @@ class TimeAxis:
                 labels.append(f"{ye:04d}-{me:02d}-{dl:02d}")
         return labels
 
-    def expected_period_lengths(self, freq: str) -> np.ndarray:
-        """Number of daily steps every ``resample(time=freq)`` period holds in this calendar when it is
-        complete -- ``expected_count`` of core/missing.py:64-160 for a daily source without indexer
-        (``end_time - start_time`` between consecutive period labels).  A first / last period that the
-        series only partly covers therefore expects more steps than it has."""
+    def _period_first_month(self, freq: str, p: int):
+        """(year, month) of the first month of period ``p`` of ``resample(time=freq)`` and its span in months."""
         mult, base, start, anchor = parse_offset(freq)
-        off = self.period_offsets(freq)
-        P = off.size - 1
+        i = int(self.period_offsets(freq)[p])
+        y, m = int(self.year[i]), int(self.month[i])
+        if base == "M":
+            return y, m, mult
+        if base == "Q":
+            am = _MONTHS.index(anchor)
+            first_month = (am if start else (am + 1)) % 3
+            tot = ((y * 12 + m - 1 - first_month) // 3) * 3 + first_month
+            ys, ms = divmod(tot, 12)
+            return ys, ms + 1, 3 * mult
+        am = _MONTHS.index(anchor)
+        first_month = am if start else (am + 1) % 12
+        return (y if (m - 1) >= first_month else y - 1), first_month + 1, 12 * mult
+
+    def _month_days(self, year: int, month0: int) -> int:
+        if self.calendar == "360_day":
+            return 30
+        dpm = _DPM_LEAP if bool(_is_leap(np.array(year), self.calendar)) else _DPM_NOLEAP
+        return int(dpm[month0])
+
+    def expected_period_lengths(self, freq: str, **indexer) -> np.ndarray:
+        """Number of daily steps every ``resample(time=freq)`` period holds in this calendar when it is
+        complete -- ``expected_count`` of core/missing.py:64-160 for a daily source (``end_time -
+        start_time`` between consecutive period labels).  A first / last period that the series only
+        partly covers therefore expects more steps than it has.  With a ``select_time`` indexer (season,
+        month, doy_bounds, date_bounds): the number of SELECTED days of the complete period (:122-141)."""
+        mult, base, start, anchor = parse_offset(freq)
+        P = self.period_offsets(freq).size - 1
         if base == "D":
-            return np.full(P, mult, np.int64)
-        span = {"Y": 12, "Q": 3, "M": 1}[base] * mult
+            full = np.full(P, mult, np.int64)
+            if not indexer:
+                return full
+            return np.add.reduceat(self.select_mask(**indexer).astype(np.int64), self.period_offsets(freq)[:-1])
         out = np.zeros(P, np.int64)
         for p in range(P):
-            i = int(off[p])
-            y, m = int(self.year[i]), int(self.month[i])
-            if base == "M":
-                ys, ms = y, m
-            elif base == "Q":
-                am = _MONTHS.index(anchor)
-                first_month = (am if start else (am + 1)) % 3
-                tot = ((y * 12 + m - 1 - first_month) // 3) * 3 + first_month
-                ys, ms = divmod(tot, 12)
-                ms += 1
-            else:
-                am = _MONTHS.index(anchor)
-                first_month = am if start else (am + 1) % 12
-                ys = y if (m - 1) >= first_month else y - 1
-                ms = first_month + 1
+            ys, ms, span = self._period_first_month(freq, p)
             n = 0
             for k in range(span):
                 yy, mm = divmod(ys * 12 + ms - 1 + k, 12)
-                if self.calendar == "360_day":
-                    n += 30
-                else:
-                    dpm = _DPM_LEAP if bool(_is_leap(np.array(yy), self.calendar)) else _DPM_NOLEAP
-                    n += int(dpm[mm])
+                n += self._month_days(yy, mm)
             out[p] = n
-        return out
+        if not indexer or P == 0:
+            return out
+        # a synthetic gap-free axis over the complete periods, select_time on it, count per period
+        ys, ms, _ = self._period_first_month(freq, 0)
+        full_axis = TimeAxis.daily(f"{ys:04d}-{ms:02d}-01", int(out.sum()), self.calendar)
+        keep = full_axis.select_mask(**indexer).astype(np.int64)
+        starts = np.concatenate([[0], np.cumsum(out)[:-1]])
+        return np.add.reduceat(keep, starts)
 
     def bootstrap_group_ids(self, freq: str) -> np.ndarray:
         """Year grouping used by the percentile bootstrap (core/bootstrapping.py:214-223):
