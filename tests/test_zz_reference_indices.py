@@ -706,8 +706,9 @@ def test_atmos_tx90p_seasonal_indexer(backend):           # tests/test_temperatu
     t90 = xcal.select_percentile(xcal.percentile_doy(series(arr, start="2000-01-01"), window=1, per=90), 90.0)
     x = arr.copy()
     x[175:180] = 1
-    out = atmos.tg90p(series(x, start="2000-01-01"), t90, freq="YS", season="JJA")
-    assert out.values[0] == 87      # 92 JJA days minus the five cold ones
+    for fn in (atmos.tg90p, atmos.tx90p):                  # generic wrapper and the hand-fused entry point
+        out = fn(series(x, start="2000-01-01"), t90, freq="YS", season="JJA")
+        assert out.values[0] == 87  # 92 JJA days minus the five cold ones
 
 
 def test_atmos_dry_spell_with_date_bounds(backend):       # tests/test_precip.py:645-674

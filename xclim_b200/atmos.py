@@ -30,9 +30,13 @@ def _mask_missing(out, valid, poff, expected=None):
     return res
 
 
-def maximum_consecutive_dry_days(pr, thresh="1 mm/day", freq="YS", resample_before_rl=True):
+def maximum_consecutive_dry_days(pr, thresh="1 mm/day", freq="YS", resample_before_rl=True, **indexer):
     """``xclim.atmos.maximum_consecutive_dry_days`` (identifier ``cdd``, indicators/atmos/_precip.py:237-247):
     the index of indices/_threshold.py:2895-2937 with periods holding a missing day set to NaN."""
+    if indexer:     # select_time on the input: the generic wrapper (one extra counting pass)
+        from . import indices
+        return with_missing_any(indices.maximum_consecutive_dry_days)(pr, thresh=thresh, freq=freq,
+                                                                      resample_before_rl=resample_before_rl, **indexer)
     thr = threshold_in_units_of(thresh, pr)
     x2d, cell_shape, other, ta = _unwrap(pr)
     poff = ta.period_offsets(freq)
@@ -45,8 +49,11 @@ def maximum_consecutive_dry_days(pr, thresh="1 mm/day", freq="YS", resample_befo
                          name="cdd")
 
 
-def tg_mean(tas, freq="YS"):
+def tg_mean(tas, freq="YS", **indexer):
     """``xclim.atmos.tg_mean`` (indicators/atmos/_temperature.py:475-485)."""
+    if indexer:
+        from . import indices
+        return with_missing_any(indices.tg_mean)(tas, freq=freq, **indexer)
     x2d, cell_shape, other, ta = _unwrap(tas)
     poff = ta.period_offsets(freq)
     out, valid = device.period_reduce(x2d, poff, _lib.STATS["mean"], want_valid=True)
@@ -55,10 +62,12 @@ def tg_mean(tas, freq="YS"):
     return _wrap_periods(tas, _mask_missing(out, valid, poff, ta.expected_period_lengths(freq)), cell_shape, other, ta, freq, attrs, name="tg_mean")
 
 
-def tx90p(tasmax, tasmax_per, freq="YS", bootstrap=False, op=">"):
+def tx90p(tasmax, tasmax_per, freq="YS", bootstrap=False, op=">", **indexer):
     """``xclim.atmos.tx90p`` (indicators/atmos/_temperature.py:1269-1281): counts become float with NaN
     where the period has a missing day."""
     from .indices import tx90p as index_tx90p
+    if indexer:
+        return with_missing_any(index_tx90p)(tasmax, tasmax_per, freq=freq, bootstrap=bootstrap, op=op, **indexer)
     if bootstrap:
         out = index_tx90p(tasmax, tasmax_per, freq=freq, bootstrap=True, op=op)
         x2d, cell_shape, other, ta = _unwrap(tasmax)
