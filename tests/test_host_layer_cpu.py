@@ -294,3 +294,27 @@ def test_missing_masks_on_partly_covered_periods(host):
     assert not m[:13].any() and m[13].all()
     a = missing.missing_any(da, "MS").values
     assert a[0, 1] and not a[0, 0] and a[13].all() and not a[1:13].any()
+
+
+def test_atmos_check_missing_options(host):
+    """set_options(check_missing=..., missing_options=...) selects the criterion of atmos.* (core/options.py)."""
+    import xclim_b200
+    from xclim_b200 import atmos, indices
+    a = np.arange(360.0)
+    a[5:7] = np.nan           # 2 of 31 days missing in July
+    a[40:45] = np.nan         # 5 consecutive days missing in August
+    ts = make_field((a + 280).astype(np.float32), "2000-07-01", units="K")
+    raw = indices.tg_max(ts, freq="MS").values
+    assert np.isnan(atmos.tg_max(ts, freq="MS").values[:2]).all()                       # any
+    with xclim_b200.set_options(check_missing="pct", missing_options={"tolerance": 0.1}):
+        out = atmos.tg_max(ts, freq="MS").values
+        assert out[0] == raw[0] and np.isnan(out[1])
+    with xclim_b200.set_options(check_missing="wmo"):
+        out = atmos.tg_max(ts, freq="MS").values
+        assert out[0] == raw[0] and np.isnan(out[1])
+    with xclim_b200.set_options(check_missing="at_least_n", missing_options={"n": 28}):
+        out = atmos.tg_max(ts, freq="MS").values
+        assert out[0] == raw[0] and np.isnan(out[1])
+    with xclim_b200.set_options(check_missing="skip"):
+        np.testing.assert_array_equal(atmos.tg_max(ts, freq="MS").values, raw)
+    assert xclim_b200.options.OPTIONS["check_missing"] == "any"

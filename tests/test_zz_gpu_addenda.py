@@ -72,3 +72,9 @@ def test_atmos_generic_missing_any_wrapper_on_device(cuda):
     """tests/test_host_layer_cpu.py::test_atmos_generic_missing_any_wrapper through the real kernels."""
     import test_host_layer_cpu as cpu_side
     cpu_side.test_atmos_generic_missing_any_wrapper(None)
+
+
+def test_atmos_check_missing_options_on_device(cuda):
+    """tests/test_host_layer_cpu.py::test_atmos_check_missing_options through the real kernels."""
+    import test_host_layer_cpu as cpu_side
+    cpu_side.test_atmos_check_missing_options(None)

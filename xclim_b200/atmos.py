@@ -17,6 +17,7 @@ from . import _lib, device
 from .calendar import adjust_table, table_on_device
 from .field import attrs_of
 from .generic import _unwrap, _wrap_periods
+from .options import OPTIONS, set_options
 from .units import threshold_in_units_of
 
 
@@ -125,12 +126,25 @@ def with_missing_any(index_fn, name=None):
                                              val.name)
             elif indexer:
                 raise NotImplementedError("select_time indexers on xarray inputs: pass xclim_b200.Field inputs")
-            if freq is None:
+            method = OPTIONS["check_missing"]
+            if freq is None or method == "skip":
                 continue
             poff = ta.period_offsets(freq)
-            _, valid = device.period_count(x2d, poff, _lib.OP_NOTNAN, 0.0, want_valid=True)
-            n = torch.from_numpy(ta.expected_period_lengths(freq, **indexer).astype(np.int32)).to(valid.device)[:, None]
-            miss = (valid != n).reshape((len(poff) - 1,) + cell_shape)
+            if method == "any":
+                _, valid = device.period_count(x2d, poff, _lib.OP_NOTNAN, 0.0, want_valid=True)
+                n = torch.from_numpy(ta.expected_period_lengths(freq, **indexer).astype(np.int32))
+                miss = (valid != n.to(valid.device)[:, None]).reshape((len(poff) - 1,) + cell_shape)
+            else:
+                from . import missing as _missing
+                fn = {"pct": _missing.missing_pct, "at_least_n": _missing.at_least_n_valid,
+                      "wmo": _missing.missing_wmo}.get(method)
+                if fn is None:
+                    raise ValueError(f"unknown check_missing method {method!r}")
+                masked_in = Field(x2d.reshape((x2d.shape[0],) + cell_shape), ("time",) + other, ta, {}, dict(val.attrs))
+                with set_options(device_outputs=True):
+                    m = fn(masked_in, freq, **OPTIONS["missing_options"], **(indexer if method != "wmo" else {}))
+                miss = m.values if hasattr(m.values, "is_cuda") else torch.from_numpy(np.asarray(m.values))
+                miss = miss.to(x2d.device).reshape((len(poff) - 1,) + cell_shape).bool()
             bad = miss if bad is None else (bad | miss)
         out = index_fn(*bound.args, **bound.kwargs)
         if bad is None:

@@ -4,10 +4,14 @@
 result as a Field whose ``values`` is a CUDA tensor instead of copying it to the host, so that
 a batch of indices over device-resident inputs runs without a device->host round trip per call
 (``Field.numpy()`` materialises it).  xarray inputs always get numpy-backed DataArrays back.
+
+``check_missing`` / ``missing_options`` (like xclim's options of the same names, core/options.py): the
+missing-value criterion of the indicator-level entry points ``xclim_b200.atmos.*`` -- "any" (default),
+"pct" (``{"tolerance": ...}``), "at_least_n" (``{"n": ...}``), "wmo" (``{"nm": ..., "nc": ...}``) or "skip".
 """
 from __future__ import annotations
 
-OPTIONS = {"device_outputs": False}
+OPTIONS = {"device_outputs": False, "check_missing": "any", "missing_options": {}}
 
 
 class set_options:
