@@ -57,12 +57,26 @@ def _percentile_day_count(da, per, freq, bootstrap, op, constrain):
         from .bootstrapping import bootstrap_doy_count
         return bootstrap_doy_count(da, per, freq, op, constrain)
     x2d, cell_shape, other, ta = _unwrap(da)
-    table = table_on_device(per, cell_shape, other, x2d.device)
+    table = _table_in_units_of(table_on_device(per, cell_shape, other, x2d.device), per, da)
     table, doy_idx = adjust_table(table, ta)
     out, _ = device.doy_threshold_count(x2d, ta.period_offsets(freq), doy_idx, table, code)
     attrs = attrs_of(da)
     attrs["units"] = "d"
     return _wrap_periods(da, out, cell_shape, other, ta, freq, attrs, dtype=np.int64)
+
+
+def _table_in_units_of(table, per, da):
+    """``convert_units_to(per, da)`` (indices/_multivariate.py:1583) on the device table: the conversions
+    of the small unit table are affine, so two probe values give scale and offset."""
+    from .field import attrs_of
+    from .units import convert_units_to
+    pu, du = attrs_of(per).get("units"), attrs_of(da).get("units")
+    if pu is None or du is None or pu == du:
+        return table
+    f0, f1 = convert_units_to(f"0 {pu}", du), convert_units_to(f"1 {pu}", du)
+    if f0 == 0.0 and f1 == 1.0:
+        return table
+    return table * (f1 - f0) + f0
 
 
 def days_over_precip_thresh(pr, pr_per, thresh="1 mm/day", freq="YS", bootstrap=False, op=">"):
