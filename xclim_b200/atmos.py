@@ -83,7 +83,8 @@ def tx90p(tasmax, tasmax_per, freq="YS", bootstrap=False, op=">", **indexer):
     code = _lib.op_code(op, (">", ">="))
     x2d, cell_shape, other, ta = _unwrap(tasmax)
     poff = ta.period_offsets(freq)
-    table = table_on_device(tasmax_per, cell_shape, other, x2d.device)
+    from .indices import _table_in_units_of
+    table = _table_in_units_of(table_on_device(tasmax_per, cell_shape, other, x2d.device), tasmax_per, tasmax)
     table, doy_idx = adjust_table(table, ta)
     cnt, valid = device.doy_threshold_count(x2d, poff, doy_idx, table, code, want_valid=True)
     attrs = attrs_of(tasmax)

@@ -96,7 +96,7 @@ def days_over_precip_thresh(pr, pr_per, thresh="1 mm/day", freq="YS", bootstrap=
     code = _lib.op_code(op, (">", ">="))
     thr = threshold_in_units_of(thresh, pr) if isinstance(thresh, str) else float(thresh)
     x2d, cell_shape, other, ta = _unwrap(pr)
-    table = table_on_device(pr_per, cell_shape, other, x2d.device)
+    table = _table_in_units_of(table_on_device(pr_per, cell_shape, other, x2d.device), pr_per, pr)
     table = torch.where(table > thr, table, torch.full_like(table, thr))     # NaN percentiles -> thresh
     table, doy_idx = adjust_table(table, ta)
     out, _ = device.doy_threshold_count(x2d, ta.period_offsets(freq), doy_idx, table, code)
