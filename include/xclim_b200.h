@@ -371,6 +371,21 @@ int32_t xc_period_runstat_f32_host(const float* x_host, int64_t T, int64_t C,
                                    float* out_host, int32_t* valid_count_host,
                                    void* workspace, int64_t workspace_bytes);
 
+/* Percentile table layout change: (n_per, n_doy, C) doy-major (the kernels' coalesced layout) ->
+ * (C, n_doy, n_per), the reference's `(*space, dayofyear, percentiles)` order of
+ * core/calendar.py:479-483 (`.transpose(..., "dayofyear", "percentiles")`), on the device. */
+int32_t xc_table_cell_major_f64(const double* table, int32_t n_per, int32_t n_doy, int64_t C,
+                                double* out, void* stream);
+
+/* Slab copy between a strided host box and device memory (either direction), asynchronous on
+ * `stream`: `height` rows of `width_bytes`, row r at src + r*src_pitch -> dst + r*dst_pitch.
+ * This is the unwrap step of the end-to-end path (core/indicator.py:884-886 hands host arrays to
+ * the index function): a lat tile `x[:, r0:r1, :]` of a (time, lat, lon) host array is one such box
+ * (width = rows*lon*4 bytes, height = time).  Pinned host memory is copied by the DMA engines
+ * without staging; pageable memory is accepted.  to_device != 0: host -> device, else device -> host. */
+int32_t xc_copy_box_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
+                          int64_t width_bytes, int64_t height, int32_t to_device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

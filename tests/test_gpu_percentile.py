@@ -210,3 +210,34 @@ def test_percentile_doy_mid_percentiles_selection_kernel(cuda, calendar, years, 
     assert g.shape == exp.shape
     np.testing.assert_allclose(g, exp, rtol=RTOL, equal_nan=True)
     np.testing.assert_array_equal(g, exp)
+
+
+@pytest.mark.parametrize("years", [30, 31, 32])
+@pytest.mark.parametrize("per", [90.0, 10.0])
+def test_percentile_doy_tma_path(cuda, years, per, monkeypatch):
+    """The TMA-fed window-5 kernel (30..32 uniform years, ldx % 4 == 0): bit-exact vs the oracle and vs
+    the lane-by-lane kernel, with NaNs, infinities of both signs (the FADD NaN probe's false positive),
+    cells beyond the last full 128-cell tile, and windows that reach into the neighbouring year."""
+    import torch
+    from xclim_b200 import device
+    rng = np.random.default_rng(100 + years)
+    L, T = 365, years * 365
+    shape = (4, 35)                       # 140 cells: one full TMA tile + a partial one
+    x = _tas(rng, T, shape, nan_frac=0.002)
+    x[:, 0, 0] = np.nan
+    x[100:900, 0, 1] = np.nan
+    x[7, 1, 2], x[365 + 7, 1, 2] = np.inf, -np.inf        # same day of year: inf + (-inf) = NaN in the probe
+    x[0:3, 2, 3] = np.nan                                 # first days of the series
+    x[T - 2:, 2, 4] = np.nan                              # last days
+    doy = (np.arange(T) % L + 1).astype(np.int16)
+    yidx = (np.arange(T) // L).astype(np.int16)
+    xd = torch.from_numpy(x.reshape(T, -1)).cuda()
+    assert xd.shape[1] % 4 == 0
+    monkeypatch.delenv("XCLIM_B200_NO_TMA", raising=False)
+    a = device.percentile_doy(xd, doy, yidx, L, years, 5, [per], 1 / 3, 1 / 3)
+    monkeypatch.setenv("XCLIM_B200_NO_TMA", "1")
+    b = device.percentile_doy(xd, doy, yidx, L, years, 5, [per], 1 / 3, 1 / 3)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
+    exp = O.percentile_doy(x, yidx.astype(np.int64), doy.astype(np.int64), 5, per)[:, 0]
+    np.testing.assert_array_equal(a[0].cpu().numpy().reshape((L,) + shape), exp)

@@ -14,20 +14,39 @@ from .generic import _unwrap
 _TABLE_CACHE: dict = {}
 
 
-def _remember_table(host_array, table_dev):
+def _fingerprint(arr):
+    """A few sampled values of a host array: detects in-place edits of a percentile array after
+    ``percentile_doy`` handed it out (e.g. ``per.values -= 273.15``) at negligible cost."""
+    if not isinstance(arr, np.ndarray) or arr.size == 0:
+        return None
+    flat = arr.reshape(-1) if arr.flags.c_contiguous else arr.ravel()[:0]
+    if flat.size == 0:
+        return None
+    idx = np.linspace(0, flat.size - 1, 16).astype(np.int64)
+    return flat[idx].tobytes()
+
+
+def _remember_table(host_array, table_dev, meta=None):
+    """Cache the doy-major device table of a percentile array handed to the caller, keyed by the
+    identity of its values; ``meta`` = (other_dims, cell_shape) of the data the table was built from."""
     key = id(host_array)
     try:
         ref = weakref.ref(host_array, lambda _r, k=key: _TABLE_CACHE.pop(k, None))
     except TypeError:
         return
-    _TABLE_CACHE[key] = (ref, table_dev)
+    _TABLE_CACHE[key] = (ref, table_dev, meta, _fingerprint(host_array))
 
 
-def _recall_table(host_array):
+def _recall_table(host_array, meta=None):
     hit = _TABLE_CACHE.get(id(host_array))
-    if hit is not None and hit[0]() is host_array:
-        return hit[1]
-    return None
+    if hit is None or hit[0]() is not host_array:
+        return None
+    if meta is not None and hit[2] is not None and tuple(hit[2]) != tuple(meta):
+        return None                       # same values, other grid / dim order: rebuild from the values
+    if hit[3] is not None and hit[3] != _fingerprint(host_array):
+        _TABLE_CACHE.pop(id(host_array), None)   # edited in place since percentile_doy returned it
+        return None
+    return hit[1]
 
 
 def year_ordinals(ta):
@@ -59,13 +78,14 @@ def percentile_doy(arr, window=5, per=10.0, alpha=1.0 / 3.0, beta=1.0 / 3.0, cop
     attrs["history"] = (hist + "\n" if hist else "") + (
         f"percentile_doy(arr, window={window}, per={pers}, alpha={alpha}, beta={beta}) - xclim_b200")
     nd = table.shape[1]
-    host = table.cpu().numpy().reshape((len(pers), nd) + cell_shape)
-    # reference dim order: (*space, dayofyear, percentiles)
-    host_t = np.moveaxis(host, (0, 1), (-1, -2))
+    # reference dim order: (*space, dayofyear, percentiles); transposed in HBM, not on the host
+    vals = device.table_cell_major(table.contiguous()).reshape(cell_shape + (nd, len(pers)))
+    from .options import OPTIONS
+    host_t = vals if (OPTIONS["device_outputs"] and not is_xarray(arr)) else vals.cpu().numpy()
     out = wrap_like(arr, host_t, other + ("dayofyear", "percentiles"),
                     coords_extra={"dayofyear": np.arange(1, nd + 1), "percentiles": np.asarray(pers)},
                     attrs=attrs, name="per")
-    _remember_table(out.values if isinstance(out, Field) else out.data, table)
+    _remember_table(out.values if isinstance(out, Field) else out.data, table, (tuple(other), tuple(cell_shape)))
     return out
 
 
@@ -82,13 +102,14 @@ def select_percentile(per_da, percentile=None):
     ax = dims.index("percentiles")
     pcs = np.asarray(per_da.coords["percentiles"])
     i = 0 if percentile is None else int(np.nonzero(pcs == percentile)[0][0])
-    vals = np.take(per_da.values, i, axis=ax)
+    vals = per_da.values[(slice(None),) * ax + (i,)]     # a view (numpy or device tensor): no copy of the table
     out = Field(vals, tuple(d for d in dims if d != "percentiles"), None,
                 {k: v for k, v in per_da.coords.items() if k != "percentiles"}, dict(per_da.attrs), per_da.name)
     out.coords["percentiles"] = pcs[i]
+    hit = _TABLE_CACHE.get(id(per_da.values))
     parent = _recall_table(per_da.values)
     if parent is not None:
-        _TABLE_CACHE[id(vals)] = (weakref.ref(vals, lambda _r, k=id(vals): _TABLE_CACHE.pop(k, None)), parent[i:i + 1])
+        _remember_table(vals, parent[i:i + 1], hit[2])
     return out
 
 
@@ -96,18 +117,26 @@ def table_on_device(per_da, cell_shape, other_dims, dev):
     """(n_doy, C) float64 device table from a percentile array (dims ``(*space, dayofyear)``)."""
     import torch
     vals = raw_values(per_da)
-    cached = _recall_table(vals)
-    if cached is not None and cached.shape[0] == 1:
+    cached = _recall_table(vals, (tuple(other_dims), tuple(cell_shape)))
+    if cached is not None and cached.shape[0] == 1 and cached.device == torch.device(dev):
         return cached[0]
     dims = dims_of(per_da)
     if "percentiles" in dims:
         ax = dims.index("percentiles")
-        if np.asarray(vals).shape[ax] != 1:
+        if vals.shape[ax] != 1:
             raise ValueError("select one percentile first: per.sel(percentiles=p)")
-        vals = np.take(np.asarray(vals), 0, axis=ax)
+        vals = vals[(slice(None),) * ax + (0,)]
         dims = tuple(d for d in dims if d != "percentiles")
     if "dayofyear" not in dims:
         raise AttributeError("Source should have `dayofyear` coordinates.")  # core/calendar.py:781-782
+    if hasattr(vals, "is_cuda"):       # a device-resident table in the reference's dim order
+        space = tuple(d for d in dims if d != "dayofyear")
+        t = vals.to(dev, torch.float64).movedim(dims.index("dayofyear"), 0)
+        if space != tuple(other_dims):
+            t = t.permute((0,) + tuple(1 + space.index(d) for d in other_dims))
+        if tuple(t.shape[1:]) != tuple(cell_shape):
+            raise ValueError(f"percentile array shape {tuple(t.shape[1:])} does not match the data grid {cell_shape}")
+        return t.reshape(t.shape[0], -1).contiguous()
     a = np.moveaxis(np.asarray(vals, dtype=np.float64), dims.index("dayofyear"), 0)
     space = tuple(d for d in dims if d != "dayofyear")
     if space != tuple(other_dims):

@@ -115,3 +115,19 @@ extern "C" int32_t xc_period_runstat_f32_host(const float* x_host, int64_t T, in
   cleanup();
   return XC_OK;
 }
+
+extern "C" int32_t xc_copy_box_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
+                                     int64_t width_bytes, int64_t height, int32_t to_device, void* stream) {
+  XC_REQUIRE(dst && src, "null pointer argument");
+  XC_REQUIRE(width_bytes > 0 && height > 0 && dst_pitch >= width_bytes && src_pitch >= width_bytes,
+             "bad box: width %lld, height %lld, pitches %lld / %lld", (long long)width_bytes, (long long)height,
+             (long long)dst_pitch, (long long)src_pitch);
+  const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+  if (dst_pitch == width_bytes && src_pitch == width_bytes) {
+    XC_CHECK_CUDA(cudaMemcpyAsync(dst, src, (size_t)(width_bytes * height), kind, (cudaStream_t)stream));
+  } else {
+    XC_CHECK_CUDA(cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)width_bytes,
+                                    (size_t)height, kind, (cudaStream_t)stream));
+  }
+  return XC_OK;
+}

@@ -19,6 +19,10 @@
 //     every input row is read once per chunk (+2h halo days).
 // No shared memory, no tensor cores (there is no contraction); the kernel is bound by the
 // min/max (ALU) pipe, see DESIGN.md.
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
+#include <stdlib.h>
+
 #include <type_traits>
 #include <vector>
 
@@ -732,6 +736,235 @@ percentile_doy_w5p_kernel(const float* __restrict__ x, int32_t T, int64_t C, int
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Window 5, paired days, rows delivered by TMA (sm_100a: cp.async.bulk.tensor + mbarrier).
+//
+// Same arithmetic as percentile_doy_w5p_kernel (identical networks, identical results), but the N
+// rows of a day-of-year are no longer fetched lane by lane (N loads, 2 N 64-bit address adds on the
+// min/max pipe, N cp.async issue slots per lane and day -- ncu capture r2: 59 IADD3 + 30 LDGSTS +
+// 28 FSETP of 545 ALU-pipe instructions per warp-day): the input is described ONCE as a 3-D tensor
+// (cell, day-of-year, year) and a dedicated producer warp issues ONE bulk tensor copy per day --
+// box 128 cells x 1 day x N years -> the [N][128] staging tile -- against an mbarrier; the four
+// consumer warps only wait, read their column (conflict-free LDS) and run the networks.  A window
+// day that reaches into the neighbouring year is the same box shifted by one year: the year that
+// does not exist is OUT OF BOUNDS and the TMA unit fills it with NaN, which the lists drop -- the
+// edge days need no special path.  Cells beyond C are NaN-filled the same way (never stored).
+// Two staging tiles: the copy of day i+2 is issued as soon as the four warps have read day i.
+// The NaN probe is an FADD tree on the FMA pipe (a NaN, or +inf with -inf, sends the lane to the
+// exact slow path), keeping the min/max pipe for the networks.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "XC_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra XC_MBAR_DONE;\n"
+      "bra XC_MBAR_WAIT;\n"
+      "XC_MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+#ifndef XC_PCTL_TMA_MINBLOCKS
+#define XC_PCTL_TMA_MINBLOCKS 3
+#endif
+#ifndef XC_PCTL_TMA_PROBE      // 0: compare chain (min/max pipe), 2: FADD tree (FMA pipe)
+#define XC_PCTL_TMA_PROBE 2
+#endif
+constexpr int kTmaCells = kThreads;                 // cells per CTA = consumer threads
+constexpr int kTmaThreads = kThreads + 32;          // + one producer warp
+
+// values of one chunk -> descending sorted list (NaN -> -inf, counted out), cf. finish_chunk
+template <int K, int NV>
+__device__ __forceinline__ void finish_chunk_t(bool top, float (&v)[K], int& nv) {
+#pragma unroll
+  for (int k = NV; k < K; ++k) v[k] = XC_NEG_INF;
+  if (!top) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = -v[k];
+  }
+#if XC_PCTL_TMA_PROBE == 2
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < NV; ++k) acc[k & 3] = __fadd_rn(acc[k & 3], v[k]);
+  const float q = __fadd_rn(__fadd_rn(acc[0], acc[1]), __fadd_rn(acc[2], acc[3]));
+  const bool suspicious = (q != q);
+#else
+  bool suspicious = false;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) suspicious = suspicious || (v[k] != v[k]);
+#endif
+  nv = NV;
+  if (suspicious) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const bool bad = (v[k] != v[k]);
+      nv -= bad ? 1 : 0;
+      v[k] = bad ? XC_NEG_INF : v[k];
+    }
+  }
+  if constexpr (NV == K) sort_desc<K>(v);
+  else sort_desc_first<K, NV>(v);
+}
+
+template <int N2>   // years = 16 + N2, N2 in {14, 15, 16}
+__global__ void __launch_bounds__(kTmaThreads, XC_PCTL_TMA_MINBLOCKS)
+percentile_doy_w5t_kernel(const __grid_constant__ CUtensorMap tmap, int64_t C, int32_t L, QuantSpec spec,
+                          int32_t doys_per_chunk, double* __restrict__ out, int32_t d_begin, int32_t d_end) {
+  constexpr int K = 16;
+  constexpr int N = K + N2;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);                     // [2][N][kTmaCells]
+  float* sA = tile + (size_t)2 * N * kTmaCells;                         // [K][kThreads]
+  float* sY = sA + (size_t)K * kThreads;                                // [2][K][kThreads]
+  float* sE = sY + (size_t)2 * K * kThreads;                            // [K][kThreads]
+  int* sn = reinterpret_cast<int*>(sE + (size_t)K * kThreads);          // [4][kThreads]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sn + 4 * kThreads);      // [2]
+  uint64_t* empty = full + 2;                                           // [2]
+  const int tid = threadIdx.x;
+  const int p0 = d_begin + blockIdx.y * doys_per_chunk;
+  const int p1 = min(d_end, p0 + doys_per_chunk);
+  if (p0 >= p1) return;   // uniform over the CTA
+  const int n_lists = (p1 - p0) + 4;                 // day lists e = p0-2 .. p1+1
+  const int c0 = blockIdx.x * kTmaCells;
+  constexpr uint32_t kTileBytes = (uint32_t)N * kTmaCells * 4u;
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_init(&empty[0], kThreads / 32);
+    mbar_init(&empty[1], kThreads / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (tid >= kThreads) {
+    // ---------------- producer warp: one elected lane issues the copies ----------------
+    if (tid == kThreads) {
+      for (int i = 0; i < n_lists; ++i) {
+        const int st = i & 1;
+        if (i >= 2) mbar_wait(&empty[st], (uint32_t)(((i >> 1) - 1) & 1));   // day i-2 has been read
+        const int e = p0 - 2 + i;
+        // e < 0: the day belongs to the previous year (box starts at year -1); e >= L: to the next
+        const int doy = (e < 0) ? e + L : (e >= L ? e - L : e);
+        const int y0 = (e < 0) ? -1 : (e >= L ? 1 : 0);
+        mbar_expect_tx(&full[st], kTileBytes);
+        tma_load_3d(tile + (size_t)st * N * kTmaCells, &tmap, &full[st], c0, doy, y0);
+      }
+    }
+    return;
+  }
+
+  // ---------------- consumer warps: lane = cell ----------------
+  const int lane = tid;
+  const int64_t c = (int64_t)c0 + lane;
+  const bool top = spec.top != 0;
+  auto store_list = [&](float* dst, const float (&a)[K]) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) dst[(size_t)k * kThreads + lane] = a[k];
+  };
+  float t[K], ynew[K], o[K];
+  int nnew, nB = 0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) t[k] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sn[k * kThreads + lane] = 0;
+  int s = 0;  // slot of Y(d-3)
+#pragma unroll 1
+  for (int i = 0; i < n_lists; ++i) {
+    const int day = p0 - 4 + i;
+    const int st = i & 1;
+    {
+      // Y(day + 2): the staged column -> two sorted chunks -> top-K of the day
+      const float* col = tile + (size_t)st * N * kTmaCells + lane;
+      float v2[K];
+      mbar_wait(&full[st], (uint32_t)((i >> 1) & 1));
+#pragma unroll
+      for (int k = 0; k < K; ++k) ynew[k] = col[(size_t)k * kTmaCells];
+#pragma unroll
+      for (int k = 0; k < N2; ++k) v2[k] = col[(size_t)(K + k) * kTmaCells];
+      __syncwarp();
+      if ((lane & 31) == 0) mbar_arrive(&empty[st]);    // this warp has read the tile
+      int n1, n2;
+      finish_chunk_t<K, K>(top, ynew, n1);
+      finish_chunk_t<K, N2>(top, v2, n2);
+      nnew = n1 + n2;
+      merge_top_desc<K>(ynew, v2);
+    }
+    int n;
+    if ((i & 1) == 0) {
+      // first day of the pair (day = d-1): ynew = Y(d+1)
+#pragma unroll
+      for (int k = 0; k < K; ++k) o[k] = fmaxf(sE[(size_t)k * kThreads + lane], ynew[K - 1 - k]);
+      bitonic_finish_desc<K>(o);       // o <- A(d+1)
+      const int nA1 = sn[3 * kThreads + lane] + nnew;
+#pragma unroll
+      for (int k = 0; k < K; ++k) t[k] = fmaxf(sA[(size_t)k * kThreads + lane], o[K - 1 - k]);
+      bitonic_finish_desc<K>(t);       // t <- B(d)
+      nB = sn[lane] + nA1;
+      store_list(sA, o);
+      sn[lane] = nA1;
+      float* slot = sY + (size_t)s * K * kThreads;
+#pragma unroll
+      for (int k = 0; k < K; ++k) o[k] = slot[(size_t)k * kThreads + lane];   // Y(d-3)
+      n = nB + sn[(1 + s) * kThreads + lane];
+      store_list(slot, ynew);          // Y(d+1) replaces Y(d-3)
+      sn[(1 + s) * kThreads + lane] = nnew;
+      s ^= 1;
+    } else {
+      // second day of the pair (day = d): ynew = Y(d+2), the even-position list of the next pair
+      store_list(sE, ynew);
+      sn[3 * kThreads + lane] = nnew;
+#pragma unroll
+      for (int k = 0; k < K; ++k) o[k] = ynew[k];
+      n = nB + nnew;
+    }
+    if (day < p0) continue;
+    // quantile of (t U o), both sorted descending, n valid values in the window
+    float u[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) u[k] = fmaxf(t[k], o[K - 1 - k]);
+    const QuantIdx qi = quant_index(n, spec);
+    const bool in_range = (n >= 2) && (qi.vi < (double)n - 1.0) && (qi.vi >= 0.0);
+    const bool fast = in_range && (top ? (n - 1 - qi.ilo == K - 1) : (qi.ilo + 1 == K - 1));
+    double res;
+    if (__all_sync(0xffffffffu, fast)) {
+      float m[K / 2];
+#pragma unroll
+      for (int j = 0; j < K / 2; ++j) m[j] = fminf(u[j], u[j + K / 2]);
+#pragma unroll
+      for (int h = K / 4; h >= 2; h >>= 1) {
+#pragma unroll
+        for (int j = 0; j < h; ++j) m[j] = fminf(m[j], m[j + h]);
+      }
+      const float smallest = fminf(m[0], m[1]), second = fmaxf(m[0], m[1]);
+      res = top ? quant_lerp(smallest, second, qi) : quant_lerp(-second, -smallest, qi);
+    } else {
+      bitonic_finish_desc<K>(u);
+      res = finalize_quantile<K>(u, n, spec);
+    }
+    if (c < C) out[(int64_t)day * C + c] = res;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // doy table interpolation (core/calendar.py:690-726)
 // ------------------------------------------------------------------------------------------------
@@ -1037,6 +1270,63 @@ int32_t launch_w5(const float* x, int64_t T, int64_t C, int64_t ldx, int32_t L, 
   return launch_status("percentile_doy_w5p_kernel");
 }
 
+
+// TMA path of launch_w5<16>: needs a 16-byte aligned base, ldx % 4 == 0 (global strides are multiples of
+// 16 bytes) and 30..32 years.  Returns 1 when the shape does not qualify (caller falls back).
+typedef CUresult (*XcEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static XcEncodeTiled tensor_map_encoder() {
+  static XcEncodeTiled fn = []() -> XcEncodeTiled {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+    return (XcEncodeTiled)p;
+  }();
+  return fn;
+}
+
+int32_t launch_w5_tma(const float* x, int64_t T, int64_t C, int64_t ldx, int32_t L, int32_t N, const QuantSpec& spec,
+                      double* out, cudaStream_t st) {
+  if (N < 30 || N > 32 || (ldx % 4) != 0 || !aligned16(x) || T != (int64_t)L * N || L < 8) return 1;
+  if (C > 2147483647LL - kTmaCells) return 1;
+  XcEncodeTiled enc = tensor_map_encoder();
+  if (!enc) return 1;
+  CUtensorMap map;
+  const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)N};
+  const cuuint64_t strides[2] = {(cuuint64_t)ldx * 4ull, (cuuint64_t)L * (cuuint64_t)ldx * 4ull};
+  const cuuint32_t box[3] = {(cuuint32_t)kTmaCells, 1u, (cuuint32_t)N};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA);
+  if (r != CUDA_SUCCESS) return 1;
+  const int nd = L;
+  const int64_t cblocks = (C + kTmaCells - 1) / kTmaCells;
+  int chunks = (int)((148 * 12 + cblocks - 1) / cblocks);
+  chunks = chunks < 1 ? 1 : chunks;
+  int per = (nd + chunks - 1) / chunks;
+  if (per < 40) per = 40;  // 4 extra day lists per chunk
+  per = (per + 1) & ~1;    // whole pairs of days
+  if (per > nd) per = nd;
+  chunks = (nd + per - 1) / per;
+  const size_t smem = (size_t)2 * N * kTmaCells * 4 + (size_t)4 * (16 + 1) * kThreads * 4 + 64;
+  dim3 grid((unsigned)cblocks, (unsigned)chunks, 1);
+  auto go = [&](auto kern) -> int32_t {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(percentile_doy_w5t_kernel)");
+    kern<<<grid, kTmaThreads, smem, st>>>(map, C, L, spec, per, out, 0, L);
+    return launch_status("percentile_doy_w5t_kernel");
+  };
+  if (N == 30) return go(percentile_doy_w5t_kernel<14>);
+  if (N == 31) return go(percentile_doy_w5t_kernel<15>);
+  return go(percentile_doy_w5t_kernel<16>);
+}
+
 }  // namespace
 }  // namespace xc
 
@@ -1152,10 +1442,13 @@ static int32_t percentile_doy_impl(const float* x, int64_t T, int64_t C, int64_t
     const bool fast_ok = window >= 3 && need <= 32 && smem_need <= 200 * 1024 && (L_int - 2 * h) >= 8;
     int32_t e = XC_OK;
     if (uniform && fast_ok) {
-      if (window == 5 && need <= 16)
-        e = need <= 8 ? launch_w5<8>(x, T, C, ldx, n_doy, n_years, spec, o, st)
-                      : launch_w5<16>(x, T, C, ldx, n_doy, n_years, spec, o, st);
-      else
+      if (window == 5 && need <= 16) {
+        e = 1;
+        if (need > 8 && !getenv("XCLIM_B200_NO_TMA")) e = launch_w5_tma(x, T, C, ldx, n_doy, n_years, spec, o, st);
+        if (e == 1)
+          e = need <= 8 ? launch_w5<8>(x, T, C, ldx, n_doy, n_years, spec, o, st)
+                        : launch_w5<16>(x, T, C, ldx, n_doy, n_years, spec, o, st);
+      } else
         e = need <= 8    ? launch_uniform<8>(x, T, C, ldx, n_doy, n_years, window, spec, o, st)
             : need <= 16 ? launch_uniform<16>(x, T, C, ldx, n_doy, n_years, window, spec, o, st)
                          : launch_uniform<32>(x, T, C, ldx, n_doy, n_years, window, spec, o, st);

@@ -164,6 +164,16 @@ def percentile_doy(x2d, doy_index, year_index, n_doy, n_years, window, percentil
     return out
 
 
+def table_cell_major(table):
+    """(n_per, n_doy, C) float64 doy-major table -> (C, n_doy, n_per), the reference's
+    ``(*space, dayofyear, percentiles)`` order (core/calendar.py:479-483), transposed in HBM."""
+    n_per, n_doy, C = table.shape
+    assert table.dtype == torch.float64 and table.is_contiguous()
+    out = torch.empty((C, n_doy, n_per), dtype=torch.float64, device=table.device)
+    check(load().xc_table_cell_major_f64(table.data_ptr(), n_per, n_doy, C, out.data_ptr(), current_stream_ptr()))
+    return out
+
+
 def doy_interp(table2d, doy_min, doy_max):
     """core/calendar.py:690-726 on a (n_src, C) float64 device table."""
     n_src, C = table2d.shape

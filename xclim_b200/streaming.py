@@ -1,0 +1,250 @@
+"""End-to-end slab streaming: host arrays -> lat slabs in HBM -> index kernels -> host result.
+
+The reference hands host (numpy / dask) arrays to its index functions (core/indicator.py:884-886
+``self.compute(**args)``); dask walks them chunk by chunk (indices/run_length.py:209-216,
+indices/helpers.py:949-974).  Every value on this path depends on ONE grid cell's series, so the
+device analogue is: cut the leading spatial dimension (lat) into slabs, copy slab k+1 host -> device
+on a copy stream (``xc_copy_box_async``: one strided box per input) while the kernels of slab k run,
+and copy each slab's small result back.  :func:`streamed` wraps an index function with exactly that;
+inputs that are already device-resident, or small, take the direct path unchanged.
+
+PyTorch is plumbing here (device buffers, streams, events); the copies and the kernels go through
+the C ABI.
+"""
+from __future__ import annotations
+
+import functools
+
+import numpy as np
+
+from .field import Field, attrs_of, dims_of, is_xarray, raw_values, time_axis_of
+from .options import OPTIONS, set_options
+
+#: inputs below this many bytes are unwrapped in one piece (device.to_time_cell)
+STREAM_MIN_BYTES = 256 << 20
+#: target size of one slab of one input in HBM (two slabs per input are resident)
+SLAB_BYTES = 1 << 30
+
+_staging: dict = {}
+
+
+def plan_slabs(n_rows: int, bytes_per_row: int, slab_bytes: int = None) -> list[tuple[int, int]]:
+    """Contiguous [r0, r1) ranges of the leading spatial dimension, each about ``slab_bytes``."""
+    slab_bytes = SLAB_BYTES if slab_bytes is None else slab_bytes
+    rows = int(max(1, min(n_rows, slab_bytes // max(1, bytes_per_row))))
+    n = -(-n_rows // rows)
+    rows = -(-n_rows // n)            # even out: no tiny last slab
+    return [(r, min(n_rows, r + rows)) for r in range(0, n_rows, rows)]
+
+
+def _host_array(obj):
+    """The numpy view of a host-backed input, or None (device tensor, unsupported container)."""
+    v = raw_values(obj)
+    if hasattr(v, "is_cuda"):
+        if v.is_cuda:
+            return None
+        return v.numpy()
+    return v if isinstance(v, np.ndarray) else None
+
+
+def _is_labelled(a):
+    return isinstance(a, Field) or is_xarray(a)
+
+
+def _classify(args, kwargs):
+    """Split the labelled inputs of a call into series (time first) and per-cell tables."""
+    series, tables = {}, {}
+    items = [(("a", i), a) for i, a in enumerate(args)] + [(("k", k), v) for k, v in kwargs.items()]
+    for key, a in items:
+        if not _is_labelled(a):
+            continue
+        dims = dims_of(a)
+        if "time" in dims:
+            series[key] = a
+        else:
+            tables[key] = a
+    return series, tables
+
+
+def _streamable(series, tables):
+    if not series:
+        return None
+    lead, shape = None, None
+    total = 0
+    for a in series.values():
+        dims = dims_of(a)
+        h = _host_array(a)
+        if h is None or dims[0] != "time" or len(dims) < 2 or h.dtype != np.float32 or not h.flags.c_contiguous:
+            return None
+        if lead is None:
+            lead, shape = dims[1], h.shape
+        elif dims[1] != lead or h.shape != shape:
+            return None
+        total = max(total, h.nbytes)
+    if total < OPTIONS.get("stream_min_bytes", STREAM_MIN_BYTES):
+        return None
+    for a in tables.values():
+        dims = dims_of(a)
+        h = _host_array(a)
+        if h is None or lead not in dims or dims[0] != lead or h.shape[0] != shape[1]:
+            return None
+    return lead, shape
+
+
+def _pinned(name, nbytes):
+    import torch
+    buf = _staging.get(name)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, pin_memory=True)
+        _staging[name] = buf
+    return buf
+
+
+def _slice_lead(a, r0, r1, values):
+    """The slab [r0, r1) of a labelled input as a Field around ``values``."""
+    dims = dims_of(a)
+    coords = {}
+    if isinstance(a, Field):
+        coords = {k: v for k, v in a.coords.items() if k not in dims}
+    else:   # xarray: scalar / non-dimension coordinates the wrappers look at
+        for k in ("percentiles",):
+            if k in a.coords and k not in dims:
+                coords[k] = a.coords[k].values
+    ta = time_axis_of(a) if "time" in dims else None
+    return Field(values, dims, ta, coords, attrs_of(a), getattr(a, "name", None))
+
+
+def run_streamed(fn, args, kwargs, lead, shape, series, tables):
+    import torch
+
+    from . import device
+    from ._lib import check, load
+
+    device._require_cuda()
+    lib = load()
+    T, n_lead = shape[0], shape[1]
+    rest = int(np.prod(shape[2:], dtype=np.int64)) if len(shape) > 2 else 1
+    slabs = plan_slabs(n_lead, T * rest * 4, OPTIONS.get("stream_slab_bytes", SLAB_BYTES))
+    rows_max = max(b - a for a, b in slabs)
+    comp = torch.cuda.current_stream()
+    s_copy, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    s_copy.wait_stream(comp)
+    keys = list(series)
+    hosts = {k: _host_array(series[k]) for k in keys}
+    bufs = {k: [torch.empty(T * rows_max * rest, dtype=torch.float32, device="cuda") for _ in range(2)] for k in keys}
+    copied = [torch.cuda.Event() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+
+    def issue_copy(k):
+        r0, r1 = slabs[k]
+        b = k & 1
+        if k >= 2:
+            s_copy.wait_event(done[b])            # the kernels of slab k-2 have released the buffer
+        w = (r1 - r0) * rest * 4
+        for key in keys:
+            h = hosts[key]
+            check(lib.xc_copy_box_async(bufs[key][b].data_ptr(), w, h.ctypes.data + r0 * rest * 4, n_lead * rest * 4,
+                                        w, T, 1, s_copy.cuda_stream))
+        copied[b].record(s_copy)
+
+    out_host = None
+    out_axis = None
+    template = next(iter(series.values()))
+    result_meta = None
+    keep = []                                     # device results stay alive until their D2H has run
+    issue_copy(0)
+    with set_options(device_outputs=True):
+        for k, (r0, r1) in enumerate(slabs):
+            b = k & 1
+            if k + 1 < len(slabs):
+                issue_copy(k + 1)                 # prefetch before the (possibly synchronising) index call
+            comp.wait_event(copied[b])
+            a2, k2 = list(args), dict(kwargs)
+            for key in keys:
+                v = bufs[key][b][: T * (r1 - r0) * rest].view((T, r1 - r0) + tuple(shape[2:]))
+                f = _slice_lead(series[key], r0, r1, v)
+                if key[0] == "a":
+                    a2[key[1]] = f
+                else:
+                    k2[key[1]] = f
+            for key, tab in tables.items():
+                f = _slice_lead(tab, r0, r1, np.ascontiguousarray(_host_array(tab)[r0:r1]))
+                if key[0] == "a":
+                    a2[key[1]] = f
+                else:
+                    k2[key[1]] = f
+            res = fn(*a2, **k2)
+            done[b].record(comp)
+            if not isinstance(res, Field):
+                raise TypeError(f"{getattr(fn, '__name__', fn)} returned {type(res).__name__}: cannot stream it")
+            vals = res.values
+            rdims = tuple(res.dims)
+            if out_host is None:
+                if lead not in rdims:
+                    raise ValueError(f"the result of {fn.__name__} has no `{lead}` dimension: cannot stream it")
+                out_axis = rdims.index(lead)
+                vshape = tuple(vals.shape)
+                full = vshape[:out_axis] + (n_lead,) + vshape[out_axis + 1:]
+                np_dtype = np.dtype(str(vals.dtype).replace("torch.", "")) if hasattr(vals, "is_cuda") else vals.dtype
+                out_host = np.empty(full, dtype=np_dtype)
+                result_meta = res
+                stage = _pinned("out", out_host.nbytes)
+                stage_np = stage[: out_host.nbytes].numpy().view(np_dtype).reshape(full)
+            A = int(np.prod(out_host.shape[:out_axis], dtype=np.int64))
+            B = int(np.prod(out_host.shape[out_axis + 1:], dtype=np.int64)) * out_host.itemsize
+            if hasattr(vals, "is_cuda") and vals.is_cuda:
+                vals = vals.contiguous()
+                keep.append(vals)
+                s_out.wait_stream(comp)
+                dst = stage_np.ctypes.data + r0 * B
+                check(lib.xc_copy_box_async(dst, n_lead * B, vals.data_ptr(), (r1 - r0) * B, (r1 - r0) * B, A, 0,
+                                            s_out.cuda_stream))
+            else:   # the index returned host values (e.g. percentile tables)
+                idx = [slice(None)] * out_host.ndim
+                idx[out_axis] = slice(r0, r1)
+                stage_np[tuple(idx)] = np.asarray(vals)
+    s_out.synchronize()
+    comp.synchronize()
+    s_copy.synchronize()
+    np.copyto(out_host, stage_np)
+    del keep
+    return _assemble(template, result_meta, out_host, lead)
+
+
+def _assemble(template, res, values, lead):
+    """The full-grid container of the same family as the inputs (labels of the sliced dimension and
+    the other spatial coordinates come from the template; the rest from the slab results)."""
+    dims = tuple(res.dims)
+    if is_xarray(template):
+        import xarray as xr
+        coords = {d: template.coords[d] for d in dims if d != "time" and d in template.coords}
+        for k, v in res.coords.items():
+            if k not in coords:
+                coords[k] = v
+        return xr.DataArray(values, dims=dims, coords=coords, attrs=dict(res.attrs), name=res.name)
+    coords = dict(res.coords)
+    for d in dims:
+        if d != "time" and d in getattr(template, "coords", {}):
+            coords[d] = template.coords[d]
+    return Field(values, dims, res.time, coords, dict(res.attrs), res.name)
+
+
+def streamed(fn):
+    """Route host-backed inputs of an index function through the slab streamer (see module doc)."""
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        if OPTIONS.get("device_outputs") or OPTIONS.get("_in_stream"):
+            return fn(*args, **kwargs)
+        series, tables = _classify(args, kwargs)
+        plan = _streamable(series, tables)
+        if plan is None:
+            return fn(*args, **kwargs)
+        OPTIONS["_in_stream"] = True
+        try:
+            return run_streamed(fn, args, kwargs, plan[0], plan[1], series, tables)
+        finally:
+            OPTIONS["_in_stream"] = False
+
+    wrapper.__wrapped_index__ = fn
+    return wrapper
