@@ -1,15 +1,21 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the xclim_b200 hot path (contract: see DESIGN.md section 6).
+"""bench.py -- headline benchmark of the xclim_b200 hot path (contract: DESIGN.md section 6).
 
     python bench.py --gpus N --steps K --warmup W            # our arm (CUDA kernels)
     python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle port on host cores
 
 Workload (BASELINE.json configs[1]): ``maximum_consecutive_dry_days`` (+ fused MissingAny valid
-count) on synthetic daily float32 ``pr`` of shape (10950, 721, 1440) in mm/d, yearly periods.
-One step = one pass of the hot path over the whole grid.  ``value`` = grid-cells/s with the input
-resident in HBM; ``e2e`` = the same through the host-buffer C-ABI call (pinned host input, H2D and
-D2H inside the timed region).  At N > 1 every rank owns one (10950, 721, 1440) lat tile of an
-N x 721-row global grid (weak scaling, no collective on the data path).
+count) on ONE synthetic daily float32 ``pr`` grid of shape (10950, 721, 1440) in mm/d, yearly
+periods.  One step = one pass of the hot path over the whole grid.  With N GPUs the grid is cut into
+contiguous lat tiles (721 rows -> 91, 90, ..., 90 on 8 ranks; xclim_b200.multigpu.lat_tiles): every
+rank owns one tile, there is no collective on the data path and ``value`` = 1,038,240 cells /
+max-over-ranks time (STRONG scaling).  The optional NCCL gather of the (30, 721, 1440) result and
+the replicated (weak) figure are reported as secondary keys.
+
+Further sections of the same JSON line (BASELINE.json configs[2..4], each on this rank's lat tile):
+``tx90p`` (percentile_doy + count, sub-case 3a), ``bootstrap`` (3b: 15-year base, bootstrap=True),
+``eqm`` (EmpiricalQuantileMapping train + adjust), ``batch50`` (50 indicators), ``e2e`` (host
+buffers through the Python index functions, H2D/D2H inside the timed region), ``cpu_baseline``.
 """
 from __future__ import annotations
 
@@ -29,6 +35,7 @@ if ROOT not in sys.path:
 T_FULL, Y_FULL, X_FULL, YEAR = 10950, 721, 1440, 365
 METRIC = "grid_cells_per_s:maximum_consecutive_dry_days(10950x721x1440,f32)"
 UNIT = "grid-cells/s"
+ALL_SECTIONS = ("parity", "weak", "gather", "tx90p", "bootstrap", "eqm", "batch50", "e2e", "cpu")
 
 
 def parse_args():
@@ -37,12 +44,23 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--lat", type=int, default=Y_FULL, help="lat rows per rank (default: full 721)")
+    ap.add_argument("--lat", type=int, default=Y_FULL, help="lat rows of the GLOBAL grid (default: full 721)")
+    ap.add_argument("--sections", default=",".join(ALL_SECTIONS),
+                    help="comma list of secondary sections to run (default: all): " + ",".join(ALL_SECTIONS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-tx90p", action="store_true")
-    ap.add_argument("--cpu-lat", type=int, default=6, help="lat rows of the bounded CPU sample")
-    return ap.parse_args()
+    ap.add_argument("--cpu-lat", type=int, default=6, help="lat rows per worker of the bounded CPU sample")
+    a = ap.parse_args()
+    sec = [s for s in a.sections.split(",") if s]
+    if a.no_e2e and "e2e" in sec:
+        sec.remove("e2e")
+    if a.no_cpu and "cpu" in sec:
+        sec.remove("cpu")
+    if a.no_tx90p and "tx90p" in sec:
+        sec.remove("tx90p")
+    a.sections = sec
+    return a
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -111,7 +129,8 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------ CPU arm
 def _cpu_cdd_band(args):
-    """One worker: `lat` rows of (10950, 1, 1440), processed row by row to bound memory."""
+    """One worker: `lat` rows of (10950, 1, 1440), processed row by row to bound memory.  The input
+    distribution is the GPU arm's (10-day wet/dry regimes, exponential amounts), generated with numpy."""
     from oracle import xclim_oracle as O
     seed, lat, X = args
     rng = np.random.default_rng(seed)
@@ -119,8 +138,10 @@ def _cpu_cdd_band(args):
     busy = 0.0
     acc = 0.0
     for _ in range(lat):
-        x = rng.random((T_FULL, 1, X), dtype=np.float32) * 12.0
-        x[x < 6.0] = 0.0
+        regime = np.repeat(rng.random((T_FULL // 10 + 1, 1, X)) < 0.5, 10, axis=0)[:T_FULL]
+        dry = rng.random((T_FULL, 1, X), dtype=np.float32) < np.where(regime, np.float32(0.8), np.float32(0.3))
+        x = rng.standard_exponential((T_FULL, 1, X), dtype=np.float32) * np.float32(6.0)
+        x[dry] = 0.0
         t = time.perf_counter()
         out = O.maximum_consecutive_dry_days(x, 1.0, poff)
         miss = O.missing_any(x, poff)
@@ -160,19 +181,29 @@ def cpu_arm(lat_rows: int, cores: int, steps: int = 1, warmup: int = 0):
 
 
 def run_reference(args):
+    """The reference arm: xclim itself is not importable offline (xarray / dask / pint / cftime are
+    absent from the image and from /opt/wheelhouse), so the oracle port -- the numpy restatement of the
+    reference's whole-array algorithm, pinned to the reference's own cores (tests/golden) -- is timed on
+    every host core.  One step = ONE lat row per core (a bounded sample of the same workload, scaled by
+    cells), so that --steps 20 --warmup 5 ends within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     use = _cpu_procs()
-    value, dt, cells = cpu_arm(args.cpu_lat, use, steps=args.steps, warmup=min(args.warmup, 1))
+    rows = 1
+    value, dt, cells = cpu_arm(rows, use, steps=args.steps, warmup=min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "maximum_consecutive_dry_days (10950,721,1440) f32 pr mm/d, freq=YS, + MissingAny",
-                   "note": "reference package not importable offline (xarray/dask/pint absent): oracle port timed"},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "maximum_consecutive_dry_days (10950,721,1440) f32 pr mm/d, thresh 1 mm/day, op <, "
+                               "freq=YS, fused MissingAny valid count",
+                   "global_grid": [T_FULL, Y_FULL, X_FULL],
+                   "note": "reference package not importable offline (xarray/dask/pint absent): the oracle port "
+                           "(restatement, not reference) is timed on the host cores"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": use, "kind": "port",
-                         "sample": f"{use} lat bands of (10950,{args.cpu_lat},1440) per step, one process per core, {dt:.1f} s busy"},
+                         "sample": f"{use} lat bands of (10950,{rows},1440) per step, one process per core, "
+                                   f"{dt:.1f} s busy per step"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -183,7 +214,8 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from xclim_b200 import _lib, device
+    import bench_sections as S
+    from xclim_b200 import _lib, device, multigpu
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -198,13 +230,23 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    T, Y, X = T_FULL, args.lat, X_FULL
-    C = Y * X
+    def max_over_ranks(vals):
+        tt = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return [float(v) for v in tt.tolist()]
+
+    ctx = S.Ctx(args=args, dev=dev, rank=rank, world=world, local=local, barrier=barrier,
+                max_over_ranks=max_over_ranks, peak=S.measured_peak(ROOT), root=ROOT)
+    T, Yg, X = T_FULL, args.lat, X_FULL
+    tiles = multigpu.lat_tiles(Yg, world)
+    r0, r1 = tiles[rank]
+    ctx.rows, ctx.row0, ctx.n_lat_global = r1 - r0, r0, Yg
+    C = ctx.rows * X
     P = T // YEAR
     poff = np.arange(P + 1, dtype=np.int32) * YEAR
-    n_lat_global = Y * world
-    # ---- inputs generated in HBM (each rank: its lat tile of the global grid)
-    pr = device.synth(T, C, kind=0, seed=2, cell_offset=rank * C, cells_per_lat=X, n_lat_global=n_lat_global)
+    # ---- this rank's lat tile of the ONE global grid, generated in HBM by the stateless generator
+    pr = device.synth(T, C, kind=0, seed=2, cell_offset=r0 * X, cells_per_lat=X, n_lat_global=Yg)
     op, red = _lib.OPS["<"], _lib.RL_REDUCERS["max"]
     launches = [0]
 
@@ -213,7 +255,8 @@ def run_ours(args):
         launches[0] += 1
         return out, valid
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         out, valid = step()
     barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
@@ -226,76 +269,68 @@ def run_ours(args):
             ev[i + 1].record()
         barrier()
     per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    total_ms = ev[0].elapsed_time(ev[args.steps])
-    tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    total_ms = float(tt.item())
+    (total_ms,) = max_over_ranks([ev[0].elapsed_time(ev[args.steps])])
     ms_per_step = total_ms / args.steps
-    cells_total = C * world
+    cells_total = Yg * X
     value = cells_total / (ms_per_step * 1e-3)
-    # ---- roofline of the dominant kernel (period_runstat_kernel): algorithmic bytes / launch time
+    # ---- roofline of the dominant kernel (period_runstat_kernel) on THIS rank's tile
     alg_bytes = T * C * 4 + P * C * 4 + P * C * 4  # read x once; write out f32 + valid i32
     kern_ms = float(np.mean(per_step))
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, from the ncu
-                # --set full capture summarised in profiles/ncu_full_r1.md (45.475 GB + 0.216 GB per launch)
-                "traffic": 45.691e9 if (Y == Y_FULL) else None,
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": ctx.peak["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / ctx.peak["hbm_gbs"],
+                "traffic": S.ncu_traffic(ROOT, "period_runstat_kernel", [T, ctx.rows, X]),
                 "kernel": "period_runstat_kernel<LT,MAX,VEC4,VALID,FASTMAX>",
-                "algorithmic_bytes": alg_bytes,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"}
-
-    # ---- checksum of checksums (size-independent sanity: every output in [0, 365], NaN rows counted)
+                "algorithmic_bytes": alg_bytes, "launch_ms": kern_ms, "tile": [T, ctx.rows, X],
+                "peak_source": ctx.peak["source"]}
     out_max = float(out.max().item())
     n_missing = int((valid != YEAR).sum().item())
     assert 0 <= out_max <= YEAR
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"maximum_consecutive_dry_days ({T},{Y},{X}) f32 pr mm/d per GPU, thresh 1 mm/day, "
-                               f"op <, freq=YS, fused MissingAny valid count",
-                   "global_grid": [T, n_lat_global, X], "partition": f"lat tiles x{world}, no collective",
-                   "l2_policy": "input 45.5 GB >> 126 MB L2, read once per step (no flush needed)"},
+        "config": {"workload": f"maximum_consecutive_dry_days ({T},{Yg},{X}) f32 pr mm/d, thresh 1 mm/day, op <, "
+                               f"freq=YS, fused MissingAny valid count",
+                   "global_grid": [T, Yg, X],
+                   "partition": f"one global grid, contiguous lat tiles over {world} rank(s): "
+                                + ",".join(str(b - a) for a, b in tiles) + " rows; no collective on the data path",
+                   "l2_policy": f"per-rank input {T * C * 4 / 1e9:.1f} GB >> 126 MB L2, read once per step "
+                                "(no flush needed)"},
         "roofline": roofline, "gpu_launches": launches[0], "clocks": clk.summary(),
         "check": {"out_max_days": out_max, "periods_masked_missing": n_missing},
     }
-
-    # ---- tx90p (second headline kernel) when available
-    if not args.no_tx90p:
+    sec = args.sections
+    # ---- full-size parity: sampled cells of this tile (incl. the last CTA's) against the oracle
+    if "parity" in sec:
+        line["parity"] = S.parity_cdd(ctx, pr, poff, out, valid)
+    if "gather" in sec and world > 1:
+        line["gather"] = S.gather_section(ctx, out, P)
+    # ---- end to end through the Python index functions with host buffers
+    if "e2e" in sec:
+        affinity = os.sched_getaffinity(0)   # the e2e leg pins this process to the GPU's NUMA node
         try:
-            from bench_tx90p import tx90p_section  # optional module, added with the percentile kernels
-            line["tx90p"] = tx90p_section(args, dev, rank, world, peak, barrier)
-        except ImportError:
-            pass
-
-    # ---- end to end through the host-buffer C-ABI call
-    if not args.no_e2e:
-        try:
-            from bench_e2e import e2e_section
-            affinity = os.sched_getaffinity(0)   # the e2e leg pins this process to the GPU's NUMA node
-            try:
-                line["e2e"] = e2e_section(args, dev, rank, world, pr, poff, barrier, out, valid)
-            finally:
-                os.sched_setaffinity(0, affinity)  # ... the CPU arm below must see every core again
-        except ImportError:
-            line["e2e"] = None
-
+            line["e2e"] = S.e2e_section(ctx, pr, poff, out, valid)
+        finally:
+            os.sched_setaffinity(0, affinity)  # ... the CPU arm below must see every core again
+    del pr, out, valid
+    torch.cuda.empty_cache()
+    if "weak" in sec and world > 1:
+        line["weak_replicas"] = S.weak_section(ctx)
+    if "tx90p" in sec or "bootstrap" in sec:
+        S.tx90p_sections(ctx, line, want_3a="tx90p" in sec, want_3b="bootstrap" in sec)
+    if "eqm" in sec:
+        line["eqm"] = S.eqm_section(ctx)
+    if "batch50" in sec:
+        line["batch50"] = S.batch50_section(ctx)
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N == 1 only
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and "cpu" in sec:
         use = _cpu_procs()
         v, dt, cells = cpu_arm(args.cpu_lat, use)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": use, "kind": "port",
                                 "sample": f"{use} lat bands of (10950,{args.cpu_lat},1440), one process per core, "
-                                          f"{dt:.1f} s"}
+                                          f"{dt:.1f} s (restatement, not reference: xclim is not importable here)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -318,3 +318,51 @@ def test_atmos_check_missing_options(host):
     with xclim_b200.set_options(check_missing="skip"):
         np.testing.assert_array_equal(atmos.tg_max(ts, freq="MS").values, raw)
     assert xclim_b200.options.OPTIONS["check_missing"] == "any"
+
+
+def test_atmos_fused_entry_points_honour_check_missing(host):
+    """The three hand-fused indicators (cdd, tg_mean, tx90p) follow set_options(check_missing=...) like the
+    generic ``with_missing_any`` wrappers (they always applied MissingAny)."""
+    import xclim_b200
+    from xclim_b200 import atmos, calendar as xcal, indices
+    rng = np.random.default_rng(21)
+    T = 365 * 3
+    x = (285 + 5 * rng.standard_normal((T, 2))).astype(np.float32)
+    x[400:403, 0] = np.nan                      # 3 missing days in year 2 of cell 0
+    tas = make_field(x, "2001-01-01", calendar="noleap", units="K")
+    pr = make_field(np.abs(x - 285).astype(np.float32), "2001-01-01", calendar="noleap", units="mm/d")
+    per = xcal.select_percentile(xcal.percentile_doy(tas, window=5, per=90.0), 90.0)
+    cases = [(atmos.tg_mean, indices.tg_mean, (tas,), {}),
+             (atmos.maximum_consecutive_dry_days, indices.maximum_consecutive_dry_days, (pr,), {}),
+             (atmos.tx90p, indices.tx90p, (tas, per), {})]
+    for ind, idx, args, kw in cases:
+        raw = np.asarray(idx(*args, **kw).values, dtype=np.float64)
+        assert np.isnan(ind(*args, **kw).values[1, 0])                                   # default: any
+        with xclim_b200.set_options(check_missing="skip"):
+            np.testing.assert_allclose(ind(*args, **kw).values, raw, rtol=1e-6)
+        with xclim_b200.set_options(check_missing="pct", missing_options={"tolerance": 0.05}):
+            out = ind(*args, **kw).values
+            assert not np.isnan(out).any() and np.allclose(out, raw, rtol=1e-6)
+        with xclim_b200.set_options(check_missing="at_least_n", missing_options={"n": 364}):
+            assert np.isnan(ind(*args, **kw).values[1, 0])
+
+
+def test_bootstrap_converts_table_units(host):
+    """degC data against a K percentile table with bootstrap=True: the out-of-base periods are counted
+    against the table converted to the data units (indices/_multivariate.py:1583)."""
+    from xclim_b200 import calendar as xcal, indices
+    rng = np.random.default_rng(22)
+    T = 365 * 5
+    t = np.arange(T)
+    xk = (288 + 10 * np.sin(2 * np.pi * t / 365)[:, None] + 3 * rng.standard_normal((T, 3))).astype(np.float32)
+    da_k = make_field(xk, "1981-01-01", calendar="noleap", units="K")
+    # exactly representable shift so that both unit systems see the same ordering
+    da_c = make_field((xk - np.float32(273.15)).astype(np.float32), "1981-01-01", calendar="noleap", units="degC")
+    base_k = da_k.isel_time(da_k.time.sel_years(1982, 1984))
+    per_k = xcal.select_percentile(xcal.percentile_doy(base_k, window=5, per=90.0), 90.0)
+    got_c = indices.tx90p(da_c, per_k, freq="YS", bootstrap=True).values
+    plain_c = indices.tx90p(da_c, per_k, freq="YS").values
+    # out-of-base years (1981, 1985): bootstrap == plain count (tests/test_bootstrapping.py:69-71), and the
+    # plain count itself is sane (about 10 % of days, not 0 or 365 as with an unconverted K table)
+    np.testing.assert_array_equal(got_c[[0, 4]], plain_c[[0, 4]])
+    assert (plain_c[[0, 4]] > 5).all() and (plain_c[[0, 4]] < 120).all()

@@ -78,3 +78,13 @@ def test_atmos_check_missing_options_on_device(cuda):
     """tests/test_host_layer_cpu.py::test_atmos_check_missing_options through the real kernels."""
     import test_host_layer_cpu as cpu_side
     cpu_side.test_atmos_check_missing_options(None)
+
+
+def test_atmos_fused_entry_points_honour_check_missing_on_device(cuda):
+    import test_host_layer_cpu as cpu_side
+    cpu_side.test_atmos_fused_entry_points_honour_check_missing(None)
+
+
+def test_bootstrap_converts_table_units_on_device(cuda):
+    import test_host_layer_cpu as cpu_side
+    cpu_side.test_bootstrap_converts_table_units(None)

@@ -34,7 +34,8 @@ def _mask_missing(out, valid, poff, expected=None):
 def maximum_consecutive_dry_days(pr, thresh="1 mm/day", freq="YS", resample_before_rl=True, **indexer):
     """``xclim.atmos.maximum_consecutive_dry_days`` (identifier ``cdd``, indicators/atmos/_precip.py:237-247):
     the index of indices/_threshold.py:2895-2937 with periods holding a missing day set to NaN."""
-    if indexer:     # select_time on the input: the generic wrapper (one extra counting pass)
+    if indexer or OPTIONS["check_missing"] != "any":
+        # select_time on the input / another missing-value criterion: the generic wrapper (one extra pass)
         from . import indices
         return with_missing_any(indices.maximum_consecutive_dry_days)(pr, thresh=thresh, freq=freq,
                                                                       resample_before_rl=resample_before_rl, **indexer)
@@ -52,7 +53,7 @@ def maximum_consecutive_dry_days(pr, thresh="1 mm/day", freq="YS", resample_befo
 
 def tg_mean(tas, freq="YS", **indexer):
     """``xclim.atmos.tg_mean`` (indicators/atmos/_temperature.py:475-485)."""
-    if indexer:
+    if indexer or OPTIONS["check_missing"] != "any":
         from . import indices
         return with_missing_any(indices.tg_mean)(tas, freq=freq, **indexer)
     x2d, cell_shape, other, ta = _unwrap(tas)
@@ -67,7 +68,7 @@ def tx90p(tasmax, tasmax_per, freq="YS", bootstrap=False, op=">", **indexer):
     """``xclim.atmos.tx90p`` (indicators/atmos/_temperature.py:1269-1281): counts become float with NaN
     where the period has a missing day."""
     from .indices import tx90p as index_tx90p
-    if indexer:
+    if indexer or OPTIONS["check_missing"] != "any":
         return with_missing_any(index_tx90p)(tasmax, tasmax_per, freq=freq, bootstrap=bootstrap, op=op, **indexer)
     if bootstrap:
         out = index_tx90p(tasmax, tasmax_per, freq=freq, bootstrap=True, op=op)
@@ -165,7 +166,18 @@ def with_missing_any(index_fn, name=None):
         return tuple(masked) if isinstance(out, tuple) else masked[0]
 
     indicator.__name__ = name or index_fn.__name__
-    return indicator
+    from .streaming import streamed
+    return streamed(indicator)       # host-backed inputs: missing counts + index per lat slab
+
+
+def _stream_fused():
+    from .streaming import streamed
+    g = globals()
+    for nm in ("maximum_consecutive_dry_days", "tg_mean", "tx90p"):
+        g[nm] = streamed(g[nm])
+
+
+_stream_fused()
 
 
 def _register_batch():

@@ -51,7 +51,8 @@ def bootstrap_doy_count(da, per, freq, op, constrain):
         boot = _bootstrap_unequal_blocks(x2d, ta, sl, starts, lens, poff, step_period, window, percentile, alpha,
                                          beta, code)
     # periods outside the base: plain count against the original table (:205-207)
-    table = table_on_device(per, cell_shape, other, x2d.device)
+    from .indices import _table_in_units_of          # convert_units_to(per, da): indices/_multivariate.py:1583
+    table = _table_in_units_of(table_on_device(per, cell_shape, other, x2d.device), per, da)
     table, doy_idx = adjust_table(table, ta)
     plain, _ = device.doy_threshold_count(x2d, poff, doy_idx, table, code)
     in_base = np.zeros(P, bool)

@@ -89,6 +89,15 @@ def percentile_doy(arr, window=5, per=10.0, alpha=1.0 / 3.0, beta=1.0 / 3.0, cop
     return out
 
 
+def _stream_percentile_doy():
+    global percentile_doy
+    from .streaming import streamed
+    percentile_doy = streamed(percentile_doy)
+
+
+_stream_percentile_doy()
+
+
 def _interp_each(table, n_per):
     import torch
     return torch.stack([device.doy_interp(table[i, :365].contiguous(), 1, 366) for i in range(n_per)])

@@ -713,3 +713,18 @@ def snowfall_intensity(prsn, thresh="1 mm/day", freq="YS-JUL"):
     attrs["units"] = "mm/day"
     return _wrap_periods(prsn, out, cell_shape, other, ta, freq, attrs)
 
+
+
+# ---- end-to-end path: host-backed inputs stream through HBM in lat slabs (xclim_b200/streaming.py)
+def _stream_entry_points():
+    import inspect
+
+    from .streaming import streamed
+    g = globals()
+    for nm, fn in list(g.items()):
+        if nm.startswith("_") or not inspect.isfunction(fn) or fn.__module__ != __name__:
+            continue
+        g[nm] = streamed(fn)
+
+
+_stream_entry_points()
