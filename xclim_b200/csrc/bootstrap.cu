@@ -16,6 +16,8 @@
 // insertions into a short list and one lerp remain.  Counts are accumulated per output period with
 // integer atomics and divided by N-1 at the end (mean over the N-1 altered series,
 // core/bootstrapping.py:203; numpy's int64 mean is exactly sum/(N-1) in float64).
+#include <stdlib.h>
+
 #include <type_traits>
 #include <vector>
 
@@ -251,6 +253,355 @@ bootstrap_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int64_t ba
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Window-5 kernel (KA = 16 kept extremes, quantile within the top 8): the same decomposition as
+// bootstrap_kernel, with the exact per-(y, s) step turned into a RANK UPDATE instead of a rebuild.
+//
+// For an in-band year y the altered sample is M = A_y + I_s with A_y = S - R_y (sorted top list, built
+// once per y) and I_s the five window values of year s.  The two order statistics the quantile
+// interpolates are ranks k1+1 and k1+2 of a union of two sorted lists, i.e.
+//     u_hi = max( a[k1],   min(a[k1-1], i1), min(a[k1-2], i2), ..., min(a[k1-5], i5) )
+//     u_lo = max( a[k1+1], min(a[k1],   i1), min(a[k1-1], i2), ..., min(a[k1-4], i5) )
+// (the max-min formula for the r-th largest of a union; a[<0] = +inf): 20 min/max on a sorted I_s, no
+// insertion, no per-s list copy -- against ~150 instructions per (y, s) of the insert-and-finalize path.
+// And only the OWNER years need it: when the largest window value of year s is <= a[k1+1] the union's two
+// ranks are a[k1], a[k1+1] themselves, one threshold P0 shared by all such s (at most k1+1 years own a
+// value above a[k1+1]).
+// Classification of the years is two-staged: two compares against day-constant list entries settle
+// "never" / "always" for most years (x below rank k1max+7 of S never beats a threshold; x above rank
+// floor(k1min/2)+1 always does, because every value of year s that is >= x is itself a member of A_y,
+// so #{I_s >= x} <= #{A_y >= x}); the rest go through the exact rank test of bootstrap_kernel.
+// Irregular items (a NaN among the inserted values, windows reaching into the neighbouring year, plotting
+// positions outside the sample) take the insert-and-finalize path of bootstrap_kernel verbatim, so the
+// results stay bit-identical to it.
+// Shared memory per lane: ring [4][KA+1], raw [5][N], top1 [N], scratch [KA]  (696 bytes for N = 15).
+// ------------------------------------------------------------------------------------------------
+#ifndef XC_BOOT_THREADS
+#define XC_BOOT_THREADS 64
+#endif
+constexpr int kBT = XC_BOOT_THREADS;
+constexpr float kPosInf = __builtin_huge_valf();
+
+__device__ __forceinline__ void sort5_desc(float& a, float& b, float& c, float& d, float& e) {
+  // 9-comparator network
+  ce_desc(a, b); ce_desc(d, e); ce_desc(c, e); ce_desc(c, d); ce_desc(a, d);
+  ce_desc(a, c); ce_desc(b, e); ce_desc(b, d); ce_desc(b, c);
+}
+
+// remove ONE instance of r from the sorted (descending) list: everything not above r moves up one slot.
+// r is a member of the sample the list is the top of, so either it is in the list (one instance goes) or it
+// lies below it (a[k] > r for every k: nothing moves).  Entries beyond rank K - #removals become inexact,
+// like remove_one's; 2 K independent instructions instead of a K-long dependent chain.
+template <int K>
+__device__ __forceinline__ void remove_shift(float (&a)[K], float r) {
+#pragma unroll
+  for (int k = 0; k < K - 1; ++k) a[k] = (a[k] > r) ? a[k] : a[k + 1];
+  a[K - 1] = (a[K - 1] > r) ? a[K - 1] : XC_NEG_INF;
+}
+
+template <int OP>
+__global__ void __launch_bounds__(kBT)
+bootstrap5_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int64_t base_start, int32_t N, int32_t L,
+                  QuantSpec spec, const int32_t* __restrict__ step_period, int32_t doys_per_chunk,
+                  int32_t* __restrict__ counts) {
+  constexpr int KA = 16, KB = 8, W = 5, H = 2, R = 4;
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x;
+  float* sring = smem;                                                     // [R][KA][kBT]
+  int* scnt = reinterpret_cast<int*>(smem + (size_t)R * KA * kBT);         // [R][kBT]
+  float* raw = smem + (size_t)R * (KA + 1) * kBT;                          // [W][N][kBT]
+  float* stop = raw + (size_t)W * N * kBT;                                 // [N][kBT] largest window value of year s
+  float* sa = stop + (size_t)N * kBT;                                      // [KA][kBT] scratch (A_y)
+  const int64_t c = (int64_t)blockIdx.x * kBT + lane;
+  if (c >= C) return;
+  const int d0 = blockIdx.y * doys_per_chunk;
+  const int d1 = min(L, d0 + doys_per_chunk);
+  if (d0 >= d1) return;
+  const unsigned wmask = __activemask();
+  const bool top = spec.top != 0;
+  const float sgn = top ? 1.f : -1.f;
+  const float* xb = x + base_start * ldx + c;
+
+  // the first KA years of a day are fetched one iteration ahead (issue_day) so that their latency hides
+  // behind the previous day's work; years beyond KA (N > 16) are loaded in place
+  float pre[KA];
+  auto issue_day = [&](int e) {
+    const int dd = e < 0 ? e + L : (e >= L ? e - L : e);
+#pragma unroll
+    for (int k = 0; k < KA; ++k)
+      pre[k] = (k < N) ? ld_stream(xb + ((int64_t)k * L + dd) * ldx) : 0.f;
+  };
+  auto load_day = [&](int e, int rs, float (&lst)[KA], int& n, bool have_pre) {
+    const int dd = e < 0 ? e + L : (e >= L ? e - L : e);
+    const int blo = (e >= L) ? 1 : 0;
+    const int bhi = (e < 0) ? N - 1 : N;
+    n = 0;
+    bool first = true;
+    for (int b0 = 0; b0 < N; b0 += KA) {
+      float v[KA];
+#pragma unroll
+      for (int k = 0; k < KA; ++k) {
+        const int b = b0 + k;
+        float r = XC_NEG_INF;
+        if (b < N) {
+          const float xv = (have_pre && b0 == 0) ? pre[k] : ld_stream(xb + ((int64_t)b * L + dd) * ldx);
+          const float sv = sgn * xv;            // selection-side value (exact: sgn = +-1); NaN stays NaN
+          raw[((size_t)rs * N + b) * kBT + lane] = sv;
+          const bool ok = (b >= blo) && (b < bhi) && (xv == xv);
+          n += ok ? 1 : 0;
+          r = ok ? sv : XC_NEG_INF;
+        }
+        v[k] = r;
+      }
+      sort_desc<KA>(v);
+      if (first) {
+#pragma unroll
+        for (int k = 0; k < KA; ++k) lst[k] = v[k];
+        first = false;
+      } else {
+        merge_top_desc<KA>(lst, v);
+      }
+    }
+  };
+  auto k1_of = [&](int n, bool& ok) {
+    const QuantIdx q = quant_index(n, spec);
+    ok = (n >= 2) && (q.vi < (double)n - 1.0) && (q.vi >= 0.0);
+    return top ? (n - 2 - q.ilo) : q.ilo;
+  };
+
+  float ynew[KA];
+  int nnew;
+  for (int s = 0; s < R; ++s) {
+    load_day(d0 - H + s, s % W, ynew, nnew, false);
+#pragma unroll
+    for (int k = 0; k < KA; ++k) sring[((size_t)s * KA + k) * kBT + lane] = ynew[k];
+    scnt[s * kBT + lane] = nnew;
+  }
+  int oldest = 0, raw_first = 0;
+  issue_day(d0 + H);
+  for (int d = d0; d < d1; ++d) {
+    const int raw_new = (raw_first + W - 1) % W;
+    load_day(d + H, raw_new, ynew, nnew, true);
+    if (d + 1 < d1) issue_day(d + 1 + H);
+    float tl[KA];
+#pragma unroll
+    for (int k = 0; k < KA; ++k) tl[k] = ynew[k];
+    int nbase = nnew;
+#pragma unroll 1
+    for (int s = 0; s < R; ++s) {
+      const float* slot = sring + (size_t)s * KA * kBT + lane;
+#pragma unroll
+      for (int k = 0; k < KA; ++k) tl[k] = fmaxf(tl[k], slot[(size_t)(KA - 1 - k) * kBT]);
+      bitonic_finish_desc<KA>(tl);
+      nbase += scnt[s * kBT + lane];
+    }
+    const bool interior = (d >= H) && (d + H < L);   // the window stays inside the year: every position valid
+    // ---- day constants: list ranks of the interpolated order statistics over every possible count
+    // na in [nbase - W, nbase] of A_y (k1 is non-decreasing in n), cf. the per-year test below
+    bool okA, okB, okC;
+    const int k1lo = k1_of(nbase - W, okA);            // smallest k1min over the years
+    const int k1hi = k1_of(nbase + W, okB);            // largest k1max
+    const int k1reg = k1_of(nbase, okC);               // regular item: na + W = nbase
+    const bool day_ok = okA && okB && (nbase - W >= 2);
+    // never: gtA >= k1max + 2  <=  gtT - W >= k1hi + 2  <=  xs < tl[k1hi + W + 1]
+    // always: geT < KA and geA + slack <= k1min  <=  geT <= idx with 2 idx <= k1lo (interior) / idx + W <= k1lo
+    const int i_never = k1hi + W + 1;
+    const int i_always = interior ? (k1lo >> 1) : (k1lo - W);
+    const float thr_never = (day_ok && i_never < KA) ? pick<KA>(tl, i_never) : XC_NEG_INF;   // xs < -inf: never true
+    const float thr_always = (day_ok && i_always >= 0 && i_always < KA) ? pick<KA>(tl, i_always) : kPosInf;
+    // ---- per year: largest window value (selection side) and NaN flag; cheap classification
+    const int raw_mid = (raw_first + H) % W;
+    unsigned nanmask = 0u, maybe = 0u;
+#pragma unroll 3
+    for (int y = 0; y < N; ++y) {
+      float m = XC_NEG_INF;
+      bool bad = false;
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        const float r = raw[((size_t)k * N + y) * kBT + lane];
+        bad = bad || !(r == r);
+        m = fmaxf(m, r);                  // fmaxf ignores a NaN operand
+      }
+      stop[(size_t)y * kBT + lane] = m;
+      nanmask |= bad ? (1u << y) : 0u;
+      const float xs = raw[((size_t)raw_mid * N + y) * kBT + lane];
+      if (xs == xs) {
+        if (xs > thr_always) {
+          atomicAdd(counts + (int64_t)step_period[y * L + d] * C + c, N - 1);
+        } else if (!(xs < thr_never)) {
+          maybe |= 1u << y;
+        }
+      }
+    }
+    // ---- exact rank test of the undecided years
+    unsigned band = 0u;
+    while (true) {
+      int y = -1;
+      if (maybe) { y = __ffs(maybe) - 1; maybe &= maybe - 1u; }
+      if (!__any_sync(wmask, y != -1)) break;
+      if (y < 0) continue;
+      const float xs = raw[((size_t)raw_mid * N + y) * kBT + lane];
+      int geT = 0, gtT = 0;
+#pragma unroll
+      for (int k = 0; k < KA; ++k) {
+        geT += (tl[k] >= xs) ? 1 : 0;
+        gtT += (tl[k] > xs) ? 1 : 0;
+      }
+      int geR = 0, gtR = 0, nr = 0;
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        const int e = d - H + k;
+        const bool valid = (e < 0) ? (y + 1 < N) : ((e >= L) ? (y >= 1) : true);
+        const float r = raw[((size_t)((raw_first + k) % W) * N + y) * kBT + lane];
+        if (valid && r == r) {
+          ++nr;
+          geR += (r >= xs) ? 1 : 0;
+          gtR += (r > xs) ? 1 : 0;
+        }
+      }
+      const int geA = geT - geR, gtA = (gtT == KA) ? KA : gtT - gtR;
+      const int na = nbase - nr;
+      bool ok0 = okA, ok1 = okC;               // nr == W (no missing value of year y): the day constants
+      int k1min = k1lo, k1max = k1reg;
+      if (nr != W) {
+        k1min = k1_of(na, ok0);
+        k1max = k1_of(na + W, ok1);
+      }
+      ok0 = ok0 && (na >= 2);
+      const int slack = interior ? min(W, geA) : W;
+      bool decided = false;
+      if (ok0 && ok1) {
+        if (gtA >= k1max + 2) {
+          decided = true;
+        } else if (geT < KA && geA + slack <= k1min) {
+          decided = true;
+          atomicAdd(counts + (int64_t)step_period[y * L + d] * C + c, N - 1);
+        }
+      }
+      if (!decided) band |= (1u << y);
+    }
+    // ---- exact evaluation of the in-band years
+    while (true) {
+      int y = -1;
+      if (band) { y = __ffs(band) - 1; band &= band - 1u; }
+      if (!__any_sync(wmask, y != -1)) break;
+      if (y < 0) continue;
+      float a[KA];
+#pragma unroll
+      for (int k = 0; k < KA; ++k) a[k] = tl[k];
+      int na = nbase;
+      unsigned vmask = 0;
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        const int e = d - H + k;
+        const bool valid = (e < 0) ? (y + 1 < N) : ((e >= L) ? (y >= 1) : true);
+        const float r = raw[((size_t)((raw_first + k) % W) * N + y) * kBT + lane];
+        if (valid) {
+          vmask |= 1u << k;
+          if (r == r) {
+            remove_shift<KA>(a, r);
+            na -= 1;
+          }
+        }
+      }
+      const float xq = sgn * raw[((size_t)raw_mid * N + y) * kBT + lane];   // the data value itself
+      // regular item: all five positions valid, the quantile of na + 5 values interpolates list ranks
+      // k1+1, k1+2 with k1 + 1 <= KA - 1 - W (those ranks of A_y are exact after the removals)
+      const int nm0 = na + W;
+      bool okm;
+      const int k1 = (nm0 == nbase) ? k1reg : k1_of(nm0, okm);
+      if (nm0 == nbase) okm = okC;
+      const bool regular = interior && okm && k1 >= 0 && (k1 + 1 <= KA - 1 - W);
+      const QuantIdx qm = quant_index(nm0, spec);
+      float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f, b4 = 0.f, b5 = 0.f, b6 = 0.f;
+      unsigned slow = ~0u;          // years evaluated by insert-and-finalize
+      int cnt = 0;
+      if (regular) {
+#pragma unroll
+        for (int k = 0; k < KA; ++k) sa[(size_t)k * kBT + lane] = a[k];
+        auto at = [&](int idx) { return idx >= 0 ? sa[(size_t)idx * kBT + lane] : kPosInf; };
+        b0 = at(k1 + 1); b1 = at(k1); b2 = at(k1 - 1); b3 = at(k1 - 2);
+        b4 = at(k1 - 3); b5 = at(k1 - 4); b6 = at(k1 - 5);
+        // years whose largest window value is <= a[k1+1] leave the two ranks at a[k1], a[k1+1]
+        const double p0 = top ? quant_lerp(b0, b1, qm) : quant_lerp(-b1, -b0, qm);
+        const int t0 = cmpd<OP>((double)xq, p0) ? 1 : 0;
+        unsigned owners = 0u;
+#pragma unroll 5
+        for (int s = 0; s < N; ++s) owners |= (stop[(size_t)s * kBT + lane] > b0) ? (1u << s) : 0u;
+        const unsigned all = (N >= 32) ? ~0u : ((1u << N) - 1u);
+        const unsigned others = all & ~(1u << y) & ~nanmask;
+        cnt = t0 * __popc(others & ~owners);
+        unsigned todo = others & owners;
+        slow = all & ~(1u << y) & nanmask;
+        while (todo) {
+          const int s = __ffs(todo) - 1;
+          todo &= todo - 1u;
+          float i1 = raw[((size_t)0 * N + s) * kBT + lane], i2 = raw[((size_t)1 * N + s) * kBT + lane],
+                i3 = raw[((size_t)2 * N + s) * kBT + lane], i4 = raw[((size_t)3 * N + s) * kBT + lane],
+                i5 = raw[((size_t)4 * N + s) * kBT + lane];
+          sort5_desc(i1, i2, i3, i4, i5);
+          const float uhi = fmaxf(fmaxf(fmaxf(b1, fminf(b2, i1)), fmaxf(fminf(b3, i2), fminf(b4, i3))),
+                                  fmaxf(fminf(b5, i4), fminf(b6, i5)));
+          const float ulo = fmaxf(fmaxf(fmaxf(b0, fminf(b1, i1)), fmaxf(fminf(b2, i2), fminf(b3, i3))),
+                                  fmaxf(fminf(b4, i4), fminf(b5, i5)));
+          const double p = top ? quant_lerp(ulo, uhi, qm) : quant_lerp(-uhi, -ulo, qm);
+          cnt += cmpd<OP>((double)xq, p) ? 1 : 0;
+        }
+      } else {
+        slow = ((N >= 32) ? ~0u : ((1u << N) - 1u)) & ~(1u << y);
+      }
+      while (slow) {   // insert-and-finalize (bootstrap_kernel's exact step)
+        const int s = __ffs(slow) - 1;
+        slow &= slow - 1u;
+        float bl[KB];
+#pragma unroll
+        for (int k = 0; k < KB; ++k) bl[k] = a[k];
+        int nm = na;
+#pragma unroll 1
+        for (int k = 0; k < W; ++k) {
+          if (!((vmask >> k) & 1u)) continue;
+          const float v = raw[((size_t)((raw_first + k) % W) * N + s) * kBT + lane];
+          const bool ok = (v == v);
+          nm += ok ? 1 : 0;
+          insert_desc<KB>(bl, ok ? v : XC_NEG_INF);
+        }
+        const double p = finalize_quantile<KB>(bl, nm, spec);
+        cnt += cmpd<OP>((double)xq, p) ? 1 : 0;
+      }
+      if (cnt) atomicAdd(counts + (int64_t)step_period[y * L + d] * C + c, cnt);
+    }
+#pragma unroll
+    for (int k = 0; k < KA; ++k) sring[((size_t)oldest * KA + k) * kBT + lane] = ynew[k];
+    scnt[oldest * kBT + lane] = nnew;
+    oldest = (oldest + 1 == R) ? 0 : oldest + 1;
+    raw_first = (raw_first + 1 == W) ? 0 : raw_first + 1;
+  }
+}
+
+int32_t launch_bootstrap5(int32_t op, const float* x, int64_t C, int64_t ldx, int64_t base_start, int32_t N, int32_t L,
+                          const QuantSpec& spec, const int32_t* step_period, int32_t* counts, cudaStream_t st) {
+  const int64_t cblocks = (C + kBT - 1) / kBT;
+  int chunks = (int)((148 * 12 + cblocks - 1) / cblocks);
+  chunks = chunks < 1 ? 1 : chunks;
+  int per = (L + chunks - 1) / chunks;
+  if (per < 20) per = 20;
+  if (per > L) per = L;
+  chunks = (L + per - 1) / per;
+  const size_t smem = ((size_t)4 * 17 + (size_t)6 * N + 16) * kBT * 4;
+  if (smem > 227 * 1024) return 1;
+  dim3 grid((unsigned)cblocks, (unsigned)chunks, 1);
+  return dispatch_op(op, [&](auto OPC) -> int32_t {
+    constexpr int OP = decltype(OPC)::value;
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(bootstrap5_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(bootstrap5_kernel)");
+    }
+    bootstrap5_kernel<OP><<<grid, kBT, smem, st>>>(x, C, ldx, base_start, N, L, spec, step_period, per, counts);
+    return launch_status("bootstrap5_kernel");
+  });
+}
+
 __global__ void __launch_bounds__(256)
 bootstrap_finish_kernel(const int32_t* __restrict__ counts, int64_t n, double denom, double* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -308,8 +659,11 @@ extern "C" int32_t xc_bootstrap_doy_count_f32(const float* x, int64_t T, int64_t
   QuantSpec spec;
   const int need = plan_quantile(percentile, alpha, beta, n_base_years * window, &spec);
   XC_CHECK_CUDA(cudaMemsetAsync(count_scratch, 0, (size_t)P * C * 4, st));
-  int32_t e;
-  if (need > 0 && need <= 8 && need + window <= 16)
+  int32_t e = 1;
+  if (need > 0 && need <= 8 && window == 5 && n_base_years <= 32 && year_len > 8 && !getenv("XCLIM_B200_BOOT_V1"))
+    e = launch_bootstrap5(op, x, C, ldx, base_start, n_base_years, year_len, spec, step_period, count_scratch, st);
+  if (e != 1) {
+  } else if (need > 0 && need <= 8 && need + window <= 16)
     e = launch_bootstrap<16, 8>(op, x, C, ldx, base_start, n_base_years, year_len, window, spec, step_period,
                                 count_scratch, st);
   else if (need > 0 && need <= 16 && need + window <= 32)
