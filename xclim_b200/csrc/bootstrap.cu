@@ -275,10 +275,12 @@ bootstrap_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int64_t ba
 // Irregular items (a NaN among the inserted values, windows reaching into the neighbouring year, plotting
 // positions outside the sample) take the insert-and-finalize path of bootstrap_kernel verbatim, so the
 // results stay bit-identical to it.
-// Shared memory per lane: ring [4][KA+1], raw [5][N], top1 [N], scratch [KA]  (696 bytes for N = 15).
+// Shared memory per lane: raw [5][N], the three largest window values of every year [3][N], scratch [KA]
+// (544 bytes for N = 15: the sorted day lists are rebuilt from the raw ring instead of being kept, which
+// trades 7 % more instructions for 50 % more resident warps in a latency-bound kernel).  N <= 16.
 // ------------------------------------------------------------------------------------------------
 #ifndef XC_BOOT_THREADS
-#define XC_BOOT_THREADS 64
+#define XC_BOOT_THREADS 32
 #endif
 constexpr int kBT = XC_BOOT_THREADS;
 constexpr float kPosInf = __builtin_huge_valf();
@@ -300,19 +302,28 @@ __device__ __forceinline__ void remove_shift(float (&a)[K], float r) {
   a[K - 1] = (a[K - 1] > r) ? a[K - 1] : XC_NEG_INF;
 }
 
+// entry idx of a register list through a 4-level select tree (depth 4 instead of a 15-long chain)
+__device__ __forceinline__ float pick16(const float (&l)[16], int idx) {
+  float t8[8], t4[4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t8[i] = (idx & 1) ? l[2 * i + 1] : l[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) t4[i] = (idx & 2) ? t8[2 * i + 1] : t8[2 * i];
+  const float u0 = (idx & 4) ? t4[1] : t4[0], u1 = (idx & 4) ? t4[3] : t4[2];
+  return (idx & 8) ? u1 : u0;
+}
+
 template <int OP>
 __global__ void __launch_bounds__(kBT)
 bootstrap5_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int64_t base_start, int32_t N, int32_t L,
                   QuantSpec spec, const int32_t* __restrict__ step_period, int32_t doys_per_chunk,
                   int32_t* __restrict__ counts) {
-  constexpr int KA = 16, KB = 8, W = 5, H = 2, R = 4;
+  constexpr int KA = 16, KB = 8, W = 5, H = 2;
   extern __shared__ float smem[];
   const int lane = threadIdx.x;
-  float* sring = smem;                                                     // [R][KA][kBT]
-  int* scnt = reinterpret_cast<int*>(smem + (size_t)R * KA * kBT);         // [R][kBT]
-  float* raw = smem + (size_t)R * (KA + 1) * kBT;                          // [W][N][kBT]
-  float* stop = raw + (size_t)W * N * kBT;                                 // [N][kBT] largest window value of year s
-  float* sa = stop + (size_t)N * kBT;                                      // [KA][kBT] scratch (A_y)
+  float* raw = smem;                                                       // [W][N][kBT] selection-side values
+  float* stop = raw + (size_t)W * N * kBT;                                 // [3][N][kBT] three largest window values
+  float* sa = stop + (size_t)3 * N * kBT;                                  // [KA][kBT] scratch (A_y)
   const int64_t c = (int64_t)blockIdx.x * kBT + lane;
   if (c >= C) return;
   const int d0 = blockIdx.y * doys_per_chunk;
@@ -322,47 +333,24 @@ bootstrap5_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int64_t b
   const bool top = spec.top != 0;
   const float sgn = top ? 1.f : -1.f;
   const float* xb = x + base_start * ldx + c;
+  const int64_t ystride = (int64_t)L * ldx;
 
-  // the first KA years of a day are fetched one iteration ahead (issue_day) so that their latency hides
-  // behind the previous day's work; years beyond KA (N > 16) are loaded in place
+  // day e (may reach into the neighbouring year) -> registers; stored to the raw ring one iteration later,
+  // so that the load latency hides behind a whole day of work
   float pre[KA];
   auto issue_day = [&](int e) {
     const int dd = e < 0 ? e + L : (e >= L ? e - L : e);
+    const float* p = xb + (int64_t)dd * ldx;
+#pragma unroll
+    for (int k = 0; k < KA; ++k) {
+      pre[k] = (k < N) ? ld_stream(p) : 0.f;
+      p += ystride;
+    }
+  };
+  auto store_day = [&](int rs) {
 #pragma unroll
     for (int k = 0; k < KA; ++k)
-      pre[k] = (k < N) ? ld_stream(xb + ((int64_t)k * L + dd) * ldx) : 0.f;
-  };
-  auto load_day = [&](int e, int rs, float (&lst)[KA], int& n, bool have_pre) {
-    const int dd = e < 0 ? e + L : (e >= L ? e - L : e);
-    const int blo = (e >= L) ? 1 : 0;
-    const int bhi = (e < 0) ? N - 1 : N;
-    n = 0;
-    bool first = true;
-    for (int b0 = 0; b0 < N; b0 += KA) {
-      float v[KA];
-#pragma unroll
-      for (int k = 0; k < KA; ++k) {
-        const int b = b0 + k;
-        float r = XC_NEG_INF;
-        if (b < N) {
-          const float xv = (have_pre && b0 == 0) ? pre[k] : ld_stream(xb + ((int64_t)b * L + dd) * ldx);
-          const float sv = sgn * xv;            // selection-side value (exact: sgn = +-1); NaN stays NaN
-          raw[((size_t)rs * N + b) * kBT + lane] = sv;
-          const bool ok = (b >= blo) && (b < bhi) && (xv == xv);
-          n += ok ? 1 : 0;
-          r = ok ? sv : XC_NEG_INF;
-        }
-        v[k] = r;
-      }
-      sort_desc<KA>(v);
-      if (first) {
-#pragma unroll
-        for (int k = 0; k < KA; ++k) lst[k] = v[k];
-        first = false;
-      } else {
-        merge_top_desc<KA>(lst, v);
-      }
-    }
+      if (k < N) raw[((size_t)rs * N + k) * kBT + lane] = sgn * pre[k];   // exact (sgn = +-1); NaN stays NaN
   };
   auto k1_of = [&](int n, bool& ok) {
     const QuantIdx q = quant_index(n, spec);
@@ -370,31 +358,40 @@ bootstrap5_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int64_t b
     return top ? (n - 2 - q.ilo) : q.ilo;
   };
 
-  float ynew[KA];
-  int nnew;
-  for (int s = 0; s < R; ++s) {
-    load_day(d0 - H + s, s % W, ynew, nnew, false);
-#pragma unroll
-    for (int k = 0; k < KA; ++k) sring[((size_t)s * KA + k) * kBT + lane] = ynew[k];
-    scnt[s * kBT + lane] = nnew;
+  // prologue: days d0-2 .. d0+1 into raw slots 0..3; day d0+2 in flight
+  for (int k = 0; k < W - 1; ++k) {
+    issue_day(d0 - H + k);
+    store_day(k);
   }
-  int oldest = 0, raw_first = 0;
   issue_day(d0 + H);
+  int raw_first = 0;
   for (int d = d0; d < d1; ++d) {
-    const int raw_new = (raw_first + W - 1) % W;
-    load_day(d + H, raw_new, ynew, nnew, true);
+    store_day((raw_first + W - 1) % W);
     if (d + 1 < d1) issue_day(d + 1 + H);
+    // ---- sorted extremes of the base sample S(d): the five day lists are sorted from the raw ring (N <= 16)
     float tl[KA];
-#pragma unroll
-    for (int k = 0; k < KA; ++k) tl[k] = ynew[k];
-    int nbase = nnew;
+    int nbase = 0;
 #pragma unroll 1
-    for (int s = 0; s < R; ++s) {
-      const float* slot = sring + (size_t)s * KA * kBT + lane;
+    for (int k = 0; k < W; ++k) {
+      const int e = d - H + k;
+      const int blo = (e >= L) ? 1 : 0;
+      const int bhi = (e < 0) ? N - 1 : N;
+      const float* col = raw + ((size_t)((raw_first + k) % W) * N) * kBT + lane;
+      float v[KA];
 #pragma unroll
-      for (int k = 0; k < KA; ++k) tl[k] = fmaxf(tl[k], slot[(size_t)(KA - 1 - k) * kBT]);
-      bitonic_finish_desc<KA>(tl);
-      nbase += scnt[s * kBT + lane];
+      for (int b = 0; b < KA; ++b) {
+        const float r = (b < N) ? col[(size_t)b * kBT] : XC_NEG_INF;
+        const bool ok = (b >= blo) && (b < bhi) && (r == r);
+        nbase += ok ? 1 : 0;
+        v[b] = ok ? r : XC_NEG_INF;
+      }
+      sort_desc<KA>(v);
+      if (k == 0) {
+#pragma unroll
+        for (int b = 0; b < KA; ++b) tl[b] = v[b];
+      } else {
+        merge_top_desc<KA>(tl, v);
+      }
     }
     const bool interior = (d >= H) && (d + H < L);   // the window stays inside the year: every position valid
     // ---- day constants: list ranks of the interpolated order statistics over every possible count
@@ -408,22 +405,26 @@ bootstrap5_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int64_t b
     // always: geT < KA and geA + slack <= k1min  <=  geT <= idx with 2 idx <= k1lo (interior) / idx + W <= k1lo
     const int i_never = k1hi + W + 1;
     const int i_always = interior ? (k1lo >> 1) : (k1lo - W);
-    const float thr_never = (day_ok && i_never < KA) ? pick<KA>(tl, i_never) : XC_NEG_INF;   // xs < -inf: never true
-    const float thr_always = (day_ok && i_always >= 0 && i_always < KA) ? pick<KA>(tl, i_always) : kPosInf;
-    // ---- per year: largest window value (selection side) and NaN flag; cheap classification
+    const float thr_never = (day_ok && i_never < KA) ? pick16(tl, i_never) : XC_NEG_INF;   // xs < -inf: never true
+    const float thr_always = (day_ok && i_always >= 0 && i_always < KA) ? pick16(tl, i_always) : kPosInf;
+    // ---- per year: three largest window values (selection side) and NaN flag; cheap classification
     const int raw_mid = (raw_first + H) % W;
     unsigned nanmask = 0u, maybe = 0u;
 #pragma unroll 3
     for (int y = 0; y < N; ++y) {
-      float m = XC_NEG_INF;
+      float m = XC_NEG_INF, m2 = XC_NEG_INF, m3 = XC_NEG_INF;
       bool bad = false;
 #pragma unroll
       for (int k = 0; k < W; ++k) {
         const float r = raw[((size_t)k * N + y) * kBT + lane];
         bad = bad || !(r == r);
-        m = fmaxf(m, r);                  // fmaxf ignores a NaN operand
+        m3 = fmaxf(m3, fminf(m2, r));     // fmaxf / fminf ignore a NaN operand (years with a NaN go the slow way)
+        m2 = fmaxf(m2, fminf(m, r));
+        m = fmaxf(m, r);
       }
-      stop[(size_t)y * kBT + lane] = m;
+      stop[((size_t)0 * N + y) * kBT + lane] = m;
+      stop[((size_t)1 * N + y) * kBT + lane] = m2;
+      stop[((size_t)2 * N + y) * kBT + lane] = m3;
       nanmask |= bad ? (1u << y) : 0u;
       const float xs = raw[((size_t)raw_mid * N + y) * kBT + lane];
       if (xs == xs) {
@@ -442,12 +443,6 @@ bootstrap5_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int64_t b
       if (!__any_sync(wmask, y != -1)) break;
       if (y < 0) continue;
       const float xs = raw[((size_t)raw_mid * N + y) * kBT + lane];
-      int geT = 0, gtT = 0;
-#pragma unroll
-      for (int k = 0; k < KA; ++k) {
-        geT += (tl[k] >= xs) ? 1 : 0;
-        gtT += (tl[k] > xs) ? 1 : 0;
-      }
       int geR = 0, gtR = 0, nr = 0;
 #pragma unroll
       for (int k = 0; k < W; ++k) {
@@ -460,7 +455,6 @@ bootstrap5_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int64_t b
           gtR += (r > xs) ? 1 : 0;
         }
       }
-      const int geA = geT - geR, gtA = (gtT == KA) ? KA : gtT - gtR;
       const int na = nbase - nr;
       bool ok0 = okA, ok1 = okC;               // nr == W (no missing value of year y): the day constants
       int k1min = k1lo, k1max = k1reg;
@@ -469,12 +463,21 @@ bootstrap5_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int64_t b
         k1max = k1_of(na + W, ok1);
       }
       ok0 = ok0 && (na >= 2);
-      const int slack = interior ? min(W, geA) : W;
+      // bootstrap_kernel's test on geT = #{tl >= xs}, gtT = #{tl > xs} (tl sorted, counts saturate at KA):
+      //   never : gtA >= k1max + 2, gtA = (gtT == KA) ? KA : gtT - gtR   <=>  gtT >= min(KA, k1max + 2 + gtR)
+      //                                                               <=>  xs < tl[min(KA, k1max + 2 + gtR) - 1]
+      //   always: geT < KA and geA + slack <= k1min, geA = geT - geR, slack = interior ? min(W, geA) : W
+      //           <=>  geA <= gmax := interior ? max(k1min - W, k1min >> 1) : k1min - W   (geA >= 0)
+      //           <=>  geT <= min(KA - 1, gmax + geR)  <=>  xs > tl[min(KA - 1, gmax + geR)]
       bool decided = false;
       if (ok0 && ok1) {
-        if (gtA >= k1max + 2) {
+        const int jn = min(KA, k1max + 2 + gtR) - 1;
+        const int gmax = interior ? max(k1min - W, k1min >> 1) : (k1min - W);
+        const int ja = min(KA - 1, gmax + geR);
+        const float tn = pick16(tl, jn < 0 ? 0 : jn), ta = pick16(tl, ja < 0 ? 0 : ja);
+        if (jn >= 0 && xs < tn) {
           decided = true;
-        } else if (geT < KA && geA + slack <= k1min) {
+        } else if (gmax >= 0 && xs > ta) {
           decided = true;
           atomicAdd(counts + (int64_t)step_period[y * L + d] * C + c, N - 1);
         }
@@ -515,7 +518,8 @@ bootstrap5_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int64_t b
       const bool regular = interior && okm && k1 >= 0 && (k1 + 1 <= KA - 1 - W);
       const QuantIdx qm = quant_index(nm0, spec);
       float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f, b4 = 0.f, b5 = 0.f, b6 = 0.f;
-      unsigned slow = ~0u;          // years evaluated by insert-and-finalize
+      const unsigned all = (N >= 32) ? ~0u : ((1u << N) - 1u);
+      unsigned slow = all & ~(1u << y);          // years evaluated by insert-and-finalize
       int cnt = 0;
       if (regular) {
 #pragma unroll
@@ -526,30 +530,40 @@ bootstrap5_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int64_t b
         // years whose largest window value is <= a[k1+1] leave the two ranks at a[k1], a[k1+1]
         const double p0 = top ? quant_lerp(b0, b1, qm) : quant_lerp(-b1, -b0, qm);
         const int t0 = cmpd<OP>((double)xq, p0) ? 1 : 0;
-        unsigned owners = 0u;
+        unsigned owners = 0u, deep = 0u;
 #pragma unroll 5
-        for (int s = 0; s < N; ++s) owners |= (stop[(size_t)s * kBT + lane] > b0) ? (1u << s) : 0u;
-        const unsigned all = (N >= 32) ? ~0u : ((1u << N) - 1u);
+        for (int s = 0; s < N; ++s) {
+          owners |= (stop[((size_t)0 * N + s) * kBT + lane] > b0) ? (1u << s) : 0u;
+          deep |= (stop[((size_t)2 * N + s) * kBT + lane] > b0) ? (1u << s) : 0u;   // three or more values above a[k1+1]
+        }
         const unsigned others = all & ~(1u << y) & ~nanmask;
         cnt = t0 * __popc(others & ~owners);
-        unsigned todo = others & owners;
+        unsigned todo = others & owners & ~deep;
+        unsigned full = others & deep;
         slow = all & ~(1u << y) & nanmask;
-        while (todo) {
+        while (todo) {     // at most two values of year s above a[k1+1]: every other term min(a[.], i_j) <= a[k1+1]
           const int s = __ffs(todo) - 1;
           todo &= todo - 1u;
-          float i1 = raw[((size_t)0 * N + s) * kBT + lane], i2 = raw[((size_t)1 * N + s) * kBT + lane],
-                i3 = raw[((size_t)2 * N + s) * kBT + lane], i4 = raw[((size_t)3 * N + s) * kBT + lane],
-                i5 = raw[((size_t)4 * N + s) * kBT + lane];
-          sort5_desc(i1, i2, i3, i4, i5);
-          const float uhi = fmaxf(fmaxf(fmaxf(b1, fminf(b2, i1)), fmaxf(fminf(b3, i2), fminf(b4, i3))),
-                                  fmaxf(fminf(b5, i4), fminf(b6, i5)));
-          const float ulo = fmaxf(fmaxf(fmaxf(b0, fminf(b1, i1)), fmaxf(fminf(b2, i2), fminf(b3, i3))),
-                                  fmaxf(fminf(b4, i4), fminf(b5, i5)));
+          const float i1 = stop[((size_t)0 * N + s) * kBT + lane], i2 = stop[((size_t)1 * N + s) * kBT + lane];
+          const float uhi = fmaxf(b1, fmaxf(fminf(b2, i1), fminf(b3, i2)));
+          const float ulo = fmaxf(b0, fmaxf(fminf(b1, i1), fminf(b2, i2)));
           const double p = top ? quant_lerp(ulo, uhi, qm) : quant_lerp(-uhi, -ulo, qm);
           cnt += cmpd<OP>((double)xq, p) ? 1 : 0;
         }
-      } else {
-        slow = ((N >= 32) ? ~0u : ((1u << N) - 1u)) & ~(1u << y);
+        while (full) {     // rare: the whole sorted window
+          const int s = __ffs(full) - 1;
+          full &= full - 1u;
+          float j1 = raw[((size_t)0 * N + s) * kBT + lane], j2 = raw[((size_t)1 * N + s) * kBT + lane],
+                j3 = raw[((size_t)2 * N + s) * kBT + lane], j4 = raw[((size_t)3 * N + s) * kBT + lane],
+                j5 = raw[((size_t)4 * N + s) * kBT + lane];
+          sort5_desc(j1, j2, j3, j4, j5);
+          const float uhi = fmaxf(fmaxf(fmaxf(b1, fminf(b2, j1)), fmaxf(fminf(b3, j2), fminf(b4, j3))),
+                                  fmaxf(fminf(b5, j4), fminf(b6, j5)));
+          const float ulo = fmaxf(fmaxf(fmaxf(b0, fminf(b1, j1)), fmaxf(fminf(b2, j2), fminf(b3, j3))),
+                                  fmaxf(fminf(b4, j4), fminf(b5, j5)));
+          const double p = top ? quant_lerp(ulo, uhi, qm) : quant_lerp(-uhi, -ulo, qm);
+          cnt += cmpd<OP>((double)xq, p) ? 1 : 0;
+        }
       }
       while (slow) {   // insert-and-finalize (bootstrap_kernel's exact step)
         const int s = __ffs(slow) - 1;
@@ -571,10 +585,6 @@ bootstrap5_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int64_t b
       }
       if (cnt) atomicAdd(counts + (int64_t)step_period[y * L + d] * C + c, cnt);
     }
-#pragma unroll
-    for (int k = 0; k < KA; ++k) sring[((size_t)oldest * KA + k) * kBT + lane] = ynew[k];
-    scnt[oldest * kBT + lane] = nnew;
-    oldest = (oldest + 1 == R) ? 0 : oldest + 1;
     raw_first = (raw_first + 1 == W) ? 0 : raw_first + 1;
   }
 }
@@ -588,7 +598,7 @@ int32_t launch_bootstrap5(int32_t op, const float* x, int64_t C, int64_t ldx, in
   if (per < 20) per = 20;
   if (per > L) per = L;
   chunks = (L + per - 1) / per;
-  const size_t smem = ((size_t)4 * 17 + (size_t)6 * N + 16) * kBT * 4;
+  const size_t smem = ((size_t)8 * N + 16) * kBT * 4;
   if (smem > 227 * 1024) return 1;
   dim3 grid((unsigned)cblocks, (unsigned)chunks, 1);
   return dispatch_op(op, [&](auto OPC) -> int32_t {
@@ -660,7 +670,7 @@ extern "C" int32_t xc_bootstrap_doy_count_f32(const float* x, int64_t T, int64_t
   const int need = plan_quantile(percentile, alpha, beta, n_base_years * window, &spec);
   XC_CHECK_CUDA(cudaMemsetAsync(count_scratch, 0, (size_t)P * C * 4, st));
   int32_t e = 1;
-  if (need > 0 && need <= 8 && window == 5 && n_base_years <= 32 && year_len > 8 && !getenv("XCLIM_B200_BOOT_V1"))
+  if (need > 0 && need <= 8 && window == 5 && n_base_years <= 16 && year_len > 8 && !getenv("XCLIM_B200_BOOT_V1"))
     e = launch_bootstrap5(op, x, C, ldx, base_start, n_base_years, year_len, spec, step_period, count_scratch, st);
   if (e != 1) {
   } else if (need > 0 && need <= 8 && need + window <= 16)
