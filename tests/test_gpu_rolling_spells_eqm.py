@@ -170,3 +170,33 @@ def test_spell_length_statistics_min_gap(cuda, min_gap, op, thr):
             np.testing.assert_array_equal(got.values, exp, err_msg=f"{min_gap} {op} {red} {freq}")
     with pytest.raises(NotImplementedError):
         generic.spell_length_statistics(da, thr, 3, "sum", op, "max", "YS", min_gap=2)
+
+
+def test_eqm_train_eight_cell_kernel_matches_one_cell_kernel(cuda, monkeypatch):
+    """The 8-cells-per-CTA multi-select (C % 8 == 0) against the oracle and, bit for bit, against the
+    one-cell-per-CTA kernel; a group holds an all-NaN cell, a constant cell and a cell that needs the redo list."""
+    import torch
+    from xclim_b200 import device
+    rng = np.random.default_rng(45)
+    T, C = 10950, 32
+    ref = (285 + 6 * rng.standard_normal((T, C))).astype(np.float32)
+    hist = (286.5 + 7 * rng.standard_normal((T, C))).astype(np.float32)
+    hist[rng.random(hist.shape) < 0.01] = np.nan
+    ref[:, 3] = np.nan
+    hist[:, 9] = 280.0
+    hist[:, 17] = np.where(rng.random(T) < 0.5, 1.0, 1.0 + 1e-6).astype(np.float32)
+    hist[:2, 17] = [0.0, 1000.0]                     # heavy, non-constant bin -> redo list
+    pr = rng.gamma(0.5, 5.0, size=(T,)).astype(np.float32)
+    pr[rng.random(T) < 0.5] = 0.0
+    ref[:, 20] = pr                                  # heavy constant bin (dry days)
+    rd, hd = torch.from_numpy(ref).cuda(), torch.from_numpy(hist).cuda()
+    monkeypatch.delenv("XCLIM_B200_EQM_V1", raising=False)
+    af, hq = device.eqm_train(rd, hd, 20, 0)
+    monkeypatch.setenv("XCLIM_B200_EQM_V1", "1")
+    af1, hq1 = device.eqm_train(rd, hd, 20, 0)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.nan_to_num(af, nan=-7.0), torch.nan_to_num(af1, nan=-7.0))
+    assert torch.equal(torch.nan_to_num(hq, nan=-7.0), torch.nan_to_num(hq1, nan=-7.0))
+    af_o, hq_o = O.eqm_train(ref, hist, 20, "+")
+    np.testing.assert_allclose(hq.cpu().numpy(), hq_o, rtol=1e-5, atol=1e-7, equal_nan=True)
+    np.testing.assert_allclose(af.cpu().numpy(), af_o, rtol=1e-4, atol=1e-5, equal_nan=True)

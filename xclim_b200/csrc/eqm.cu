@@ -15,6 +15,8 @@
 // gather are shared through L2.  adjust is a streaming pass: a lane owns one cell, keeps the 2*nq
 // table entries of its cell in a conflict-free shared-memory column and does a binary search per
 // element.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace xc {
@@ -58,7 +60,8 @@ __device__ void block_bitonic_sort(float* keys, int tid) {
 template <int NPAD>
 __global__ void __launch_bounds__(kSortThreads)
 eqm_train_kernel(const float* __restrict__ ref, const float* __restrict__ hist, int32_t T, int64_t C, int64_t ldx,
-                 int32_t nq, int32_t kind, float* __restrict__ af, float* __restrict__ hist_q) {
+                 int32_t nq, int32_t kind, float* __restrict__ af, float* __restrict__ hist_q,
+                 const int32_t* __restrict__ redo = nullptr) {
   extern __shared__ float keys[];             // NPAD keys | nq ref quantiles | candidate lists
   float* refq = keys + NPAD;
   float* cand = refq + ((nq + 3) & ~3);       // [2 * nq][kCap]
@@ -70,10 +73,14 @@ eqm_train_kernel(const float* __restrict__ ref, const float* __restrict__ hist, 
   __shared__ float red_min[kSortThreads / 32], red_max[kSortThreads / 32];
   __shared__ int red_cnt[kSortThreads / 32];
   __shared__ int s_flag, s_nslots;
-  const int64_t c = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int ntg = 2 * nq;
+  // redo == nullptr: CTA = cell blockIdx.x.  Otherwise the CTAs walk the work list redo[1 .. redo[0]] (cells
+  // eqm_train8_kernel could not finish); the trip count is uniform over the CTA.
+  const int n_items = redo ? redo[0] : (int)gridDim.x;
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x)
   for (int pass = 0; pass < 2; ++pass) {
+    const int64_t c = redo ? (int64_t)redo[1 + item] : (int64_t)item;
     const float* src = (pass == 0 ? ref : hist) + c;
     // ---- load, count valid, min / max
     float mn = INFINITY, mx = -INFINITY;
@@ -248,6 +255,335 @@ eqm_train_kernel(const float* __restrict__ ref, const float* __restrict__ hist, 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// train, 8 cells per CTA: the same multi-select (min/max -> 1024-bin histogram -> gather the wanted
+// bins -> rank by counting), but a CTA owns EIGHT ADJACENT CELLS, i.e. one 32-byte sector of every time
+// row: thread = (time row mod 32, cell), so every sector fetched from HBM is used whole and DRAM traffic
+// is the algorithmic 2 T C 4 bytes (the one-cell kernel fetched each sector for eight CTAs and leaned on
+// L2; ncu r1 capture E: 4 useful bytes per 32-byte sector).  The three passes re-read the CTA's
+// 8 x T x 4 = 350 KB slice, which stays L2-resident between passes.  Histograms are packed two
+// 16-bit counters per word (T <= 32768), candidate storage is allocated exactly from the histogram
+// counts (prefix over the wanted bins) in a 1024-float pool per cell.
+// A cell this layout cannot finish -- a wanted bin with more than kHeavy elements that are not all equal,
+// or a candidate total beyond the pool -- is appended to a redo list that eqm_train_redo_kernel resolves
+// with the one-cell kernel's full machinery (sort fallback included): the results are those of
+// eqm_train_kernel bit for bit.
+// ------------------------------------------------------------------------------------------------
+#ifndef XC_EQM_GROUP
+#define XC_EQM_GROUP 16
+#endif
+constexpr int kG = XC_EQM_GROUP;   // cells per CTA: 16 = one 64-byte DRAM fetch pair per time row (8 = one sector)
+constexpr int kGT = 32 * kG;       // threads: one warp per cell for the scans, 128 time rows x kG / 4 loads in flight
+constexpr int kSub = kG / 4;       // threads (128-bit loads) per time row
+constexpr int kPool = 1024;        // candidate floats per cell
+constexpr int kHeavy = 192;        // bins above this must be constant
+
+__device__ __forceinline__ int float_key(float v) {   // order-preserving int key (for atomicMin / atomicMax)
+  const int b = __float_as_int(v);
+  return b >= 0 ? b : (b ^ 0x7fffffff);
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : (k ^ 0x7fffffff)); }
+
+// dynamic shared memory of eqm_train8_kernel for ntg = 2 * nq targets per cell
+__host__ __device__ inline size_t train8_smem_bytes(int ntg) {
+  return (size_t)kG * (kBins / 2) * 4      // packed 16-bit histogram, then exclusive prefix sums
+         + (size_t)kG * kPool * 4          // candidate pool
+         + (size_t)kG * kBins * 2          // bin -> slot
+         + (size_t)kG * ntg * (4 * 8);     // tgt_rank, tgt_bin, tgt_val, slot_bin, slot_off, slot_n, slot_min / max (2)
+}
+
+__global__ void __launch_bounds__(kGT, (kG == 8 ? 3 : 1))
+eqm_train8_kernel(const float* __restrict__ ref, const float* __restrict__ hist, int32_t T, int64_t C, int64_t ldx,
+                  int32_t nq, int32_t kind, float* __restrict__ af, float* __restrict__ hist_q,
+                  int32_t* __restrict__ redo /* [0] = count, then cell indexes */) {
+  extern __shared__ __align__(16) unsigned char sm8[];
+  const int ntg = 2 * nq;
+  uint32_t* h32 = reinterpret_cast<uint32_t*>(sm8);                          // [kG][kBins / 2]
+  float* pool = reinterpret_cast<float*>(h32 + kG * (kBins / 2));            // [kG][kPool]
+  unsigned short* slot_of_bin = reinterpret_cast<unsigned short*>(pool + kG * kPool);   // [kG][kBins]
+  int* tgt_rank = reinterpret_cast<int*>(slot_of_bin + kG * kBins);          // [kG][ntg]
+  int* tgt_bin = tgt_rank + kG * ntg;
+  float* tgt_val = reinterpret_cast<float*>(tgt_bin + kG * ntg);
+  int* slot_bin = reinterpret_cast<int*>(tgt_val + kG * ntg);
+  int* slot_off = slot_bin + kG * ntg;
+  int* slot_n = slot_off + kG * ntg;
+  int* slot_mm = slot_n + kG * ntg;                                          // [kG][ntg][2] min, max keys
+  __shared__ int nslots[kG], bad_cell[kG], cell_n[kG];
+  __shared__ float cell_mn[kG], cell_scale[kG];
+  __shared__ float red_mn[kGT / 32][kG], red_mx[kGT / 32][kG];
+  __shared__ int red_n[kGT / 32][kG];
+  __shared__ float refq[kG][64];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  // thread = (time row mod 128, half sector): one 128-bit load covers 4 adjacent cells of a row, a warp covers
+  // 16 rows x 32 bytes; kU loads in flight per thread keep ~100 KB per SM on the wire (Little's law at 7 TB/s)
+  const int half = tid % kSub, trow = tid / kSub;
+  constexpr int kRows = kGT / kSub, kU = 8;
+  const int cell = tid & (kG - 1);                           // the cell this thread reduces / owns after the passes
+  const int64_t c0 = (int64_t)blockIdx.x * kG;
+  constexpr unsigned short kFree = 0xffffu, kBusy = 0xfffeu;
+  auto pref_at = [&](int cc, int i) -> int {   // exclusive prefix sum of cell cc at bin i (i <= kBins)
+    if (i >= kBins) return cell_n[cc];
+    return (int)((h32[cc * (kBins / 2) + (i >> 1)] >> ((i & 1) * 16)) & 0xffffu);
+  };
+  for (int pass = 0; pass < 2; ++pass) {
+    // ---- pass 1: valid count, min, max of every cell
+    const float* src = (pass == 0 ? ref : hist) + c0 + 4 * half;
+    float mn4[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    int nv4[4] = {0, 0, 0, 0};
+    {
+      int t = trow;
+      for (; t + (kU - 1) * kRows < T; t += kU * kRows) {
+        float4 v[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) v[u] = ld_stream4(src + (int64_t)(t + u * kRows) * ldx);
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (e[i] == e[i]) { mn4[i] = fminf(mn4[i], e[i]); mx4[i] = fmaxf(mx4[i], e[i]); ++nv4[i]; }
+        }
+      }
+      for (; t < T; t += kRows) {
+        const float4 v = ld_stream4(src + (int64_t)t * ldx);
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (e[i] == e[i]) { mn4[i] = fminf(mn4[i], e[i]); mx4[i] = fmaxf(mx4[i], e[i]); ++nv4[i]; }
+      }
+    }
+    // lanes equal modulo kSub hold the same four cells
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      for (int o = kSub; o < 32; o <<= 1) {
+        mn4[i] = fminf(mn4[i], __shfl_xor_sync(0xffffffffu, mn4[i], o));
+        mx4[i] = fmaxf(mx4[i], __shfl_xor_sync(0xffffffffu, mx4[i], o));
+        nv4[i] += __shfl_xor_sync(0xffffffffu, nv4[i], o);
+      }
+      if (lane < kSub) { red_mn[wid][4 * lane + i] = mn4[i]; red_mx[wid][4 * lane + i] = mx4[i]; red_n[wid][4 * lane + i] = nv4[i]; }
+    }
+    for (int i = tid; i < kG * (kBins / 2); i += kGT) h32[i] = 0u;
+    for (int i = tid; i < kG * kBins; i += kGT) slot_of_bin[i] = kFree;
+    __syncthreads();
+    float mn = INFINITY, mx = -INFINITY;
+    int n = 0;
+#pragma unroll
+    for (int w = 0; w < kGT / 32; ++w) { mn = fminf(mn, red_mn[w][cell]); mx = fmaxf(mx, red_mx[w][cell]); n += red_n[w][cell]; }
+    {
+      const bool degenerate = !(mx > mn) || !(mx - mn < INFINITY);
+      const float scale = degenerate ? 0.f : (float)kBins / (mx - mn);
+      if (tid < kG) { nslots[tid] = 0; bad_cell[tid] = 0; cell_n[tid] = n; cell_mn[tid] = mn; cell_scale[tid] = scale; }
+    }
+    __syncthreads();
+    // the four cells this thread streams
+    float cmn[4], csc[4];
+    bool cwork[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      cmn[i] = cell_mn[4 * half + i];
+      csc[i] = cell_scale[4 * half + i];
+      cwork[i] = (cell_n[4 * half + i] > 0) && (csc[i] != 0.f);
+    }
+    // ---- pass 2: histogram (two 16-bit counters per word; T <= 32768)
+    {
+      auto tally = [&](const float4& v) {
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (cwork[i] && e[i] == e[i]) {
+            const int b = min(kBins - 1, (int)((e[i] - cmn[i]) * csc[i]));
+            atomicAdd(&h32[(4 * half + i) * (kBins / 2) + (b >> 1)], (b & 1) ? 65536u : 1u);
+          }
+        }
+      };
+      int t = trow;
+      for (; t + (kU - 1) * kRows < T; t += kU * kRows) {
+        float4 v[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) v[u] = ld_stream4(src + (int64_t)(t + u * kRows) * ldx);
+#pragma unroll
+        for (int u = 0; u < kU; ++u) tally(v[u]);
+      }
+      for (; t < T; t += kRows) tally(ld_stream4(src + (int64_t)t * ldx));
+    }
+    __syncthreads();
+    {  // in-place exclusive scan of the kBins counters of cell `wid` by warp `wid` (kGT / 32 == kG)
+      constexpr int per = kBins / 32;
+      uint32_t* hc = h32 + wid * (kBins / 2) + lane * (per / 2);
+      int loc[per], sum = 0;
+#pragma unroll
+      for (int i = 0; i < per; i += 2) {
+        const uint32_t w2 = hc[i >> 1];
+        loc[i] = (int)(w2 & 0xffffu);
+        loc[i + 1] = (int)(w2 >> 16);
+        sum += loc[i] + loc[i + 1];
+      }
+      int incl = sum;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      int run = incl - sum;
+#pragma unroll
+      for (int i = 0; i < per; i += 2) {
+        const uint32_t lo16 = (uint32_t)run;
+        run += loc[i];
+        const uint32_t hi16 = (uint32_t)run;
+        run += loc[i + 1];
+        hc[i >> 1] = lo16 | (hi16 << 16);
+      }
+    }
+    __syncthreads();
+    // ---- wanted order statistics of every cell: bin + rank inside the bin; claim the bins
+    for (int g = tid; g < kG * ntg; g += kGT) {
+      const int cc = g / ntg, k = g - cc * ntg;
+      const int nn = cell_n[cc];
+      if (nn <= 0 || cell_scale[cc] == 0.f || c0 + cc >= C) continue;
+      const int j = k >> 1;
+      const double q = (double)(float)(((double)j + 0.5) / (double)nq);
+      const int ilo = (int)floor(q * (double)(nn - 1));
+      const int r = (k & 1) ? min(ilo + 1, nn - 1) : ilo;
+      int lo = 0, hi = kBins;  // bin b with prefix[b] <= r < prefix[b+1]
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (pref_at(cc, mid) <= r) lo = mid; else hi = mid;
+      }
+      tgt_bin[cc * ntg + k] = lo;
+      tgt_rank[cc * ntg + k] = r - pref_at(cc, lo);
+      if (atomicCAS(&slot_of_bin[cc * kBins + lo], kFree, kBusy) == kFree) {  // first to claim the bin allocates its slot
+        const int sl = atomicAdd(&nslots[cc], 1);
+        slot_bin[cc * ntg + sl] = lo;
+        slot_n[cc * ntg + sl] = 0;
+        slot_mm[(cc * ntg + sl) * 2] = 0x7fffffff;
+        slot_mm[(cc * ntg + sl) * 2 + 1] = (int)0x80000000;
+        slot_of_bin[cc * kBins + lo] = (unsigned short)sl;
+      }
+    }
+    __syncthreads();
+    // ---- candidate storage: exact offsets from the histogram counts (heavy bins are not gathered)
+    if (tid < kG) {
+      int off = 0;
+      for (int sl = 0; sl < nslots[tid]; ++sl) {
+        const int bb = slot_bin[tid * ntg + sl];
+        const int cnt = pref_at(tid, bb + 1) - pref_at(tid, bb);
+        slot_off[tid * ntg + sl] = (cnt > kHeavy) ? -1 : off;
+        if (cnt <= kHeavy) off += cnt;
+      }
+      if (off > kPool) bad_cell[tid] = 1;
+    }
+    __syncthreads();
+    // ---- pass 3: gather the elements of the wanted bins (min / max of the heavy ones)
+    {
+      bool cgo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) cgo[i] = cwork[i] && !bad_cell[4 * half + i];
+      auto gather = [&](const float4& v) {
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (cgo[i] && e[i] == e[i]) {
+            const int cc = 4 * half + i;
+            const unsigned short sl = slot_of_bin[cc * kBins + min(kBins - 1, (int)((e[i] - cmn[i]) * csc[i]))];
+            if (sl != kFree) {
+              const int off = slot_off[cc * ntg + sl];
+              if (off >= 0) {
+                const int p = atomicAdd(&slot_n[cc * ntg + sl], 1);
+                pool[cc * kPool + off + p] = e[i];
+              } else {
+                const int kx = float_key(e[i]);
+                atomicMin(&slot_mm[(cc * ntg + sl) * 2], kx);
+                atomicMax(&slot_mm[(cc * ntg + sl) * 2 + 1], kx);
+              }
+            }
+          }
+        }
+      };
+      int t = trow;
+      for (; t + (kU - 1) * kRows < T; t += kU * kRows) {
+        float4 v[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) v[u] = ld_stream4(src + (int64_t)(t + u * kRows) * ldx);
+#pragma unroll
+        for (int u = 0; u < kU; ++u) gather(v[u]);
+      }
+      for (; t < T; t += kRows) gather(ld_stream4(src + (int64_t)t * ldx));
+    }
+    __syncthreads();
+    // ---- heavy bins must be constant
+    for (int g = tid; g < kG * ntg; g += kGT) {
+      const int cc = g / ntg, sl = g - cc * ntg;
+      if (sl < nslots[cc] && slot_off[cc * ntg + sl] < 0 &&
+          slot_mm[(cc * ntg + sl) * 2] != slot_mm[(cc * ntg + sl) * 2 + 1])
+        bad_cell[cc] = 1;
+    }
+    __syncthreads();
+    // ---- rank inside the bin by counting: one warp per (cell, target)
+    for (int g = wid; g < kG * ntg; g += kGT / 32) {
+      const int cc = g / ntg, k = g - cc * ntg;
+      if (cell_n[cc] <= 0 || cell_scale[cc] == 0.f || bad_cell[cc] || c0 + cc >= C) continue;
+      const int sl = slot_of_bin[cc * kBins + tgt_bin[cc * ntg + k]];
+      const int off = slot_off[cc * ntg + sl];
+      if (off < 0) {                                   // constant heavy bin
+        if (lane == 0) tgt_val[cc * ntg + k] = key_float(slot_mm[(cc * ntg + sl) * 2]);
+        continue;
+      }
+      const int m = slot_n[cc * ntg + sl];
+      const float* cl = pool + cc * kPool + off;
+      const int want = tgt_rank[cc * ntg + k];
+      float found = NAN;
+      for (int i = lane; i < m; i += 32) {
+        const float vi = cl[i];
+        int less = 0;
+        for (int kk = 0; kk < m; ++kk) {
+          const float vk = cl[kk];
+          less += (vk < vi || (vk == vi && kk < i)) ? 1 : 0;
+        }
+        if (less == want) found = vi;
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const float other = __shfl_xor_sync(0xffffffffu, found, o);
+        found = (found == found) ? found : other;
+      }
+      if (lane == 0) tgt_val[cc * ntg + k] = found;
+    }
+    __syncthreads();
+    // ---- quantiles (numpy's _lerp on the two neighbours)
+    for (int g = tid; g < kG * nq; g += kGT) {
+      const int cc = g / nq, j = g - cc * nq;
+      if (c0 + cc >= C) continue;
+      const int nn = cell_n[cc];
+      float qv = NAN;
+      if (nn > 0) {
+        if (cell_scale[cc] == 0.f) {
+          qv = cell_mn[cc];  // every valid value equals mn (or the range is not finite: not supported, gives mn)
+        } else if (!bad_cell[cc]) {
+          const double q = (double)(float)(((double)j + 0.5) / (double)nq);
+          const double pos = q * (double)(nn - 1);
+          const double lo = floor(pos);
+          const double gq = pos - lo;
+          const double a0 = (double)tgt_val[cc * ntg + 2 * j], a1 = (double)tgt_val[cc * ntg + 2 * j + 1];
+          const double d = a1 - a0;
+          qv = (float)((gq >= 0.5) ? (a1 - d * (1.0 - gq)) : (a0 + d * gq));
+        }
+      }
+      if (pass == 0) {
+        refq[cc][j] = qv;
+      } else {
+        hist_q[(int64_t)j * C + c0 + cc] = qv;
+        af[(int64_t)j * C + c0 + cc] = (kind == 0) ? (refq[cc][j] - qv) : (refq[cc][j] / qv);
+      }
+    }
+    __syncthreads();
+    // a cell that could not be finished goes to the redo list (both passes are redone there)
+    if (tid < kG && bad_cell[tid] && c0 + tid < C) {
+      const int slot = atomicAdd(&redo[0], 1);
+      redo[1 + slot] = (int)(c0 + tid);
+    }
+    __syncthreads();
+  }
+}
+
 constexpr int kAdjThreads = 128;
 
 template <int INTERP, int KIND>
@@ -327,24 +663,15 @@ eqm_adjust_kernel(const float* __restrict__ sim, int64_t T, int64_t C, int64_t l
 using namespace xc;
 
 extern "C" int64_t xc_eqm_train_workspace_bytes(int64_t T, int64_t C, int32_t nq) {
-  (void)T; (void)C; (void)nq;
-  return 0;  // the sort runs in shared memory
+  (void)T; (void)nq;
+  // redo list of the 8-cells-per-CTA kernel: a counter + at most two entries per cell
+  return 256 + (2 * C + 1) * 4;
 }
 
-extern "C" int32_t xc_eqm_train_f32(const float* ref, const float* hist, int64_t T, int64_t C, int64_t ldx,
-                                    int32_t nq, int32_t kind, float* af, float* hist_q, void* workspace,
-                                    int64_t workspace_bytes, void* stream) {
-  (void)workspace; (void)workspace_bytes;
-  XC_REQUIRE(ref && hist && af && hist_q, "null pointer argument");
-  XC_REQUIRE(T > 0 && C > 0 && ldx >= C, "bad shape");
-  XC_REQUIRE(nq >= 1 && nq <= 64, "nquantiles must be in [1, 64]");
-  XC_REQUIRE(kind == 0 || kind == 1, "kind must be 0 ('+') or 1 ('*')");
-  XC_REQUIRE(C <= 2147483647LL, "too many cells for one launch");
-  if (T > 32768) {
-    set_error("eqm_train: series longer than 32768 steps do not fit the shared-memory sort");
-    return XC_ERR_UNSUPPORTED;
-  }
-  cudaStream_t st = (cudaStream_t)stream;
+// the one-cell-per-CTA kernel on `grid` CTAs: every cell (redo == nullptr, grid == C) or a work list
+static int32_t launch_train_cells(const float* ref, const float* hist, int64_t T, int64_t C, int64_t ldx, int32_t nq,
+                                  int32_t kind, float* af, float* hist_q, const int32_t* redo, unsigned grid,
+                                  cudaStream_t st) {
   int npad = 1024;
   while (npad < T) npad <<= 1;
   const size_t smem = ((size_t)npad + ((nq + 3) & ~3) + (size_t)2 * nq * kCap) * 4;
@@ -355,8 +682,8 @@ extern "C" int32_t xc_eqm_train_f32(const float* ref, const float* hist, int64_t
                                             (int)smem);                                                            \
       if (e_ != cudaSuccess) return cuda_fail(e_, "cudaFuncSetAttribute(eqm_train_kernel)");                       \
     }                                                                                                              \
-    eqm_train_kernel<NP><<<(unsigned)C, kSortThreads, smem, st>>>(ref, hist, (int32_t)T, C, ldx, nq, kind, af,     \
-                                                                  hist_q);                                         \
+    eqm_train_kernel<NP><<<grid, kSortThreads, smem, st>>>(ref, hist, (int32_t)T, C, ldx, nq, kind, af, hist_q,    \
+                                                           redo);                                                  \
   } while (0)
   switch (npad) {
     case 1024: XC_TRAIN(1024); break;
@@ -368,6 +695,38 @@ extern "C" int32_t xc_eqm_train_f32(const float* ref, const float* hist, int64_t
   }
 #undef XC_TRAIN
   return launch_status("eqm_train_kernel");
+}
+
+extern "C" int32_t xc_eqm_train_f32(const float* ref, const float* hist, int64_t T, int64_t C, int64_t ldx,
+                                    int32_t nq, int32_t kind, float* af, float* hist_q, void* workspace,
+                                    int64_t workspace_bytes, void* stream) {
+  XC_REQUIRE(ref && hist && af && hist_q, "null pointer argument");
+  XC_REQUIRE(T > 0 && C > 0 && ldx >= C, "bad shape");
+  XC_REQUIRE(nq >= 1 && nq <= 64, "nquantiles must be in [1, 64]");
+  XC_REQUIRE(kind == 0 || kind == 1, "kind must be 0 ('+') or 1 ('*')");
+  XC_REQUIRE(C <= 2147483647LL, "too many cells for one launch");
+  if (T > 32768) {
+    set_error("eqm_train: series longer than 32768 steps do not fit the shared-memory sort");
+    return XC_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t need = xc_eqm_train_workspace_bytes(T, C, nq);
+  const bool vec_ok = (C % kG == 0) && (ldx % 4 == 0) && aligned16(ref) && aligned16(hist);
+  if (workspace == nullptr || workspace_bytes < need || !vec_ok || getenv("XCLIM_B200_EQM_V1")) {
+    // no scratch for a redo list, or a layout without whole 32-byte sectors per CTA: the one-cell-per-CTA
+    // kernel (complete in itself)
+    return launch_train_cells(ref, hist, T, C, ldx, nq, kind, af, hist_q, nullptr, (unsigned)C, st);
+  }
+  int32_t* redo = (int32_t*)workspace;
+  XC_CHECK_CUDA(cudaMemsetAsync(redo, 0, 4, st));
+  const size_t smem8 = train8_smem_bytes(2 * nq);
+  XC_CHECK_CUDA(cudaFuncSetAttribute(eqm_train8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+  const int64_t groups = (C + kG - 1) / kG;
+  eqm_train8_kernel<<<(unsigned)groups, kGT, smem8, st>>>(ref, hist, (int32_t)T, C, ldx, nq, kind, af, hist_q, redo);
+  int32_t e = launch_status("eqm_train8_kernel");
+  if (e) return e;
+  // cells the eight-cell layout could not finish (heavy non-constant bins): a small fixed grid walks the list
+  return launch_train_cells(ref, hist, T, C, ldx, nq, kind, af, hist_q, redo, 296u, st);
 }
 
 extern "C" int32_t xc_eqm_adjust_f32(const float* sim, int64_t T, int64_t C, int64_t ldx, const float* af,

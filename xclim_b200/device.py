@@ -280,8 +280,10 @@ def eqm_train(ref2d, hist2d, nq, kind_code):
     assert hist2d.shape == ref2d.shape and ref2d.stride(0) == hist2d.stride(0)
     af = torch.empty((nq, C), dtype=torch.float32, device=ref2d.device)
     hq = torch.empty((nq, C), dtype=torch.float32, device=ref2d.device)
-    check(load().xc_eqm_train_f32(ref2d.data_ptr(), hist2d.data_ptr(), T, C, ref2d.stride(0), int(nq), kind_code,
-                                  af.data_ptr(), hq.data_ptr(), None, 0, current_stream_ptr()))
+    lib = load()
+    ws = torch.empty(int(lib.xc_eqm_train_workspace_bytes(T, C, int(nq))), dtype=torch.uint8, device=ref2d.device)
+    check(lib.xc_eqm_train_f32(ref2d.data_ptr(), hist2d.data_ptr(), T, C, ref2d.stride(0), int(nq), kind_code,
+                               af.data_ptr(), hq.data_ptr(), ws.data_ptr(), ws.numel(), current_stream_ptr()))
     return af, hq
 
 
