@@ -371,6 +371,48 @@ int32_t xc_period_runstat_f32_host(const float* x_host, int64_t T, int64_t C,
                                    float* out_host, int32_t* valid_count_host,
                                    void* workspace, int64_t workspace_bytes);
 
+/* threshold_count with an ARRAY threshold -- indices/generic.py:301-361 (`compare(da, op, threshold)` with a
+ * DataArray threshold): out[p, c] = #{ t in period p : (double)x[t, c] op thr[t * thr_tstride + c] }, thr float64
+ * (numpy promotes float32 data against a float64 array to float64); thr_tstride = 0: one threshold per cell. */
+int32_t xc_period_count_arr_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                const int32_t* period_offsets, int32_t P, int32_t op,
+                                const double* thr, int64_t thr_tstride, int32_t* out_count, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused multi-output pass (batch of indicators over ONE variable and ONE resampling frequency):
+ * core/indicator.py:884-886 runs the indicators one after the other, each re-reading its input; here
+ * every count / run-length / reduction output that shares (x, period_offsets) comes out of a single
+ * streaming pass ("unique inputs once each").
+ *   Conditions are normalised on the host to  sgn * x > thr  (x >= t  <=>  x > pred(t), x < t  <=>
+ *   -x > -t, ...; indices/generic.py:301-326), runs are cut at the period edges
+ *   (resample_before_rl=True, indices/run_length.py:122-129).
+ *   lite[i]:  n_true (threshold_count, generic.py:329-361) and the longest run (rle_statistics "max")
+ *   full[i]:  + total length / number of the runs >= wa and >= wb (windowed_run_count / _events,
+ *             run_length.py:381-488) and the largest run sum of (x - ms_thr0) over runs >= wms
+ *             (windowed_max_run_sum, run_length.py:491-540)
+ *   sums[i]:  mode 0: sum of (off_sgn * (x - off)).clip(0) (cumulative_difference, generic.py:1514-1552);
+ *             mode 1: sum of x where the condition holds (thresholded_statistics "sum", generic.py:1278-1320)
+ *   plain:    sum / mean / min / max of x (select_resample_op, generic.py:83-125)
+ *   Every `slot_*` is an index into `out` (slot s occupies out[s*P*C .. (s+1)*P*C), 4-byte elements:
+ *   int32 for n_true and the run counts, float32 otherwise) or -1 when that output is not wanted.
+ *   A longest run shorter than `wmax` is reported as 0 (`max_l.where(max_l >= window, 0)`,
+ *   indices/_threshold.py:311).  Needs C % 4 == 0, ldx % 4 == 0 and 16-byte aligned buffers.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct { float sgn, thr; int32_t wmax, slot_n, slot_max; } XcMultiLite;
+typedef struct { float sgn, thr; int32_t wmax, wa, wb, wms; float ms_sgn, ms_thr0;
+                 int32_t slot_n, slot_max, slot_sum_a, slot_cnt_a, slot_sum_b, slot_cnt_b, slot_ms; } XcMultiFull;
+typedef struct { float sgn, thr, off_sgn, off; int32_t mode, slot; } XcMultiSum;
+typedef struct {
+  int32_t n_lite, n_full, n_sums;
+  XcMultiLite lite[4];
+  XcMultiFull full[2];
+  XcMultiSum sums[3];
+  int32_t slot_sum, slot_mean, slot_min, slot_max;
+} XcMultiPlan;
+int32_t xc_period_multi_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                            const int32_t* period_offsets, int32_t P, const XcMultiPlan* plan_host,
+                            void* out, int32_t n_slots, void* stream);
+
 /* Percentile table layout change: (n_per, n_doy, C) doy-major (the kernels' coalesced layout) ->
  * (C, n_doy, n_per), the reference's `(*space, dayofyear, percentiles)` order of
  * core/calendar.py:479-483 (`.transpose(..., "dayofyear", "percentiles")`), on the device. */

@@ -234,6 +234,65 @@ def table_cell_major(table):
     return table.permute(2, 1, 0).contiguous()
 
 
+def period_count_arr(x2d, poff, op_code, thr2d, per_time):
+    x = _np(x2d).astype(np.float64)
+    t = _np(thr2d)
+    with np.errstate(invalid="ignore"):
+        cond = O.compare(x, OP_NAME[op_code], t if per_time else t[0][None, :])
+    return torch.from_numpy(np.stack([cond[a:b].sum(0) for a, b in O._groups(poff)]).astype(np.int32))
+
+
+def period_multi(x2d, poff, plan, n_slots):
+    """Oracle composition of the fused multi-output pass (include/xclim_b200.h: XcMultiPlan)."""
+    x = _np(x2d)
+    P, C = len(poff) - 1, x.shape[1]
+    out = np.zeros((max(1, n_slots), P, C), dtype=np.float32)
+    groups = O._groups(poff)
+
+    def put(slot, v, as_int=False):
+        if slot >= 0:
+            v = np.asarray(v)
+            out[slot] = v.astype(np.int32).view(np.float32) if as_int else v.astype(np.float32)
+
+    def run_stat(cond, red, w):
+        return O.resample_and_rl(cond, True, O.rle_statistics, poff=poff, reducer=red, window=int(w))
+
+    x64 = x.astype(np.float64)
+    put(plan.slot_sum, O.resample_reduce(x64, poff, "sum"))
+    put(plan.slot_mean, O.resample_reduce(x64, poff, "mean"))
+    put(plan.slot_min, O.resample_reduce(x64, poff, "min"))
+    put(plan.slot_max, O.resample_reduce(x64, poff, "max"))
+    with np.errstate(invalid="ignore"):
+        for j in range(plan.n_lite):
+            e = plan.lite[j]
+            cond = np.float32(e.sgn) * x > np.float32(e.thr)
+            put(e.slot_n, np.stack([cond[a:b].sum(0) for a, b in groups]), True)
+            m = run_stat(cond, "max", 1)
+            put(e.slot_max, np.where(m >= e.wmax, m, 0))
+        for j in range(plan.n_full):
+            e = plan.full[j]
+            cond = np.float32(e.sgn) * x > np.float32(e.thr)
+            put(e.slot_n, np.stack([cond[a:b].sum(0) for a, b in groups]), True)
+            m = run_stat(cond, "max", 1)
+            put(e.slot_max, np.where(m >= e.wmax, m, 0))
+            put(e.slot_sum_a, run_stat(cond, "sum", e.wa))
+            put(e.slot_cnt_a, run_stat(cond, "count", e.wa))
+            put(e.slot_sum_b, run_stat(cond, "sum", e.wb))
+            put(e.slot_cnt_b, run_stat(cond, "count", e.wb))
+            if e.slot_ms >= 0:
+                exc = np.where(cond, np.float32(e.ms_sgn) * (x - np.float32(e.ms_thr0)), np.float32(0)).astype(np.float64)
+                put(e.slot_ms, O.resample_and_rl(exc, True, O.windowed_max_run_sum, int(e.wms), poff=poff))
+        for j in range(plan.n_sums):
+            e = plan.sums[j]
+            if e.mode == 0:
+                d = np.float32(e.off_sgn) * (x - np.float32(e.off))
+                v = np.where(np.isnan(d), 0.0, np.maximum(d, np.float32(0)).astype(np.float64))
+            else:
+                v = np.where(np.float32(e.sgn) * x > np.float32(e.thr), x64, 0.0)
+            put(e.slot, np.stack([v[a:b].sum(0) for a, b in groups]))
+    return torch.from_numpy(out)
+
+
 def dev_ints(arr, dtype, device):
     return torch.from_numpy(np.ascontiguousarray(np.asarray(arr, dtype=dtype)))
 
@@ -241,7 +300,7 @@ def dev_ints(arr, dtype, device):
 FUNCTIONS = [to_time_cell, period_count, period_runstat, period_runstat_gap, period_reduce, rolling_period_reduce,
              spell_runstat, period_run_maxsum, period_runstat2, percentile_doy, doy_interp, doy_threshold_count,
              mask_steps, dev_ints, period_boundary_run, period_boundary_run_range, bootstrap_doy_count, eqm_train,
-             eqm_adjust, period_run_quantile, table_cell_major]
+             eqm_adjust, period_run_quantile, table_cell_major, period_multi, period_count_arr]
 
 
 def install(monkeypatch):

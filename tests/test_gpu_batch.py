@@ -95,3 +95,28 @@ def test_device_outputs_option_matches_host_outputs(cuda):
                                          mask.time), 2, freq="YS", coord="dayofyear")
     np.testing.assert_array_equal(got.numpy(), ref.values)
     assert not xclim_b200.options.OPTIONS["device_outputs"]
+
+
+def test_run_batch_fused_passes_match_single_calls(cuda):
+    """The fused multi-output kernel behind indices.run_batch against the 50 single-output calls."""
+    import test_host_layer_cpu as cpu_side
+    cpu_side._check_run_batch_against_single_calls()
+
+
+def test_run_batch_device_resident(cuda):
+    import torch
+    import xclim_b200
+    from xclim_b200 import Field, calendar as xcal, indices
+    data = _inputs()
+    units = {"tas": "K", "tasmax": "K", "tasmin": "K", "pr": "mm/d"}
+    host = {k: make_field(v, "1981-01-01", calendar="noleap", units=units[k]) for k, v in data.items()}
+    dev = {k: Field(torch.from_numpy(v).cuda(), f.dims, f.time, dict(f.coords), dict(f.attrs)) for (k, v), f in
+           zip(data.items(), host.values())}
+    with xclim_b200.set_options(device_outputs=True):
+        pers = {(var, p_): xcal.select_percentile(xcal.percentile_doy(dev[var], window=5, per=p_), p_)
+                for var, p_ in (("tasmax", 90.0), ("tasmax", 10.0), ("tasmin", 90.0))}
+        out = indices.run_batch(dev, pers)
+    assert all(o.values.is_cuda for o in out.values())
+    ref = indices.run_batch(host, {k: Field(v.numpy(), v.dims, v.time, dict(v.coords), dict(v.attrs)) for k, v in pers.items()})
+    for name in out:
+        np.testing.assert_array_equal(out[name].numpy(), ref[name].values, err_msg=name)

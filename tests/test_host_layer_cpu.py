@@ -366,3 +366,109 @@ def test_bootstrap_converts_table_units(host):
     # plain count itself is sane (about 10 % of days, not 0 or 365 as with an unconverted K table)
     np.testing.assert_array_equal(got_c[[0, 4]], plain_c[[0, 4]])
     assert (plain_c[[0, 4]] > 5).all() and (plain_c[[0, 4]] < 120).all()
+
+
+def _check_run_batch_against_single_calls(exact=True):
+    """indices.run_batch (fused passes) == the one-call-per-indicator functions: values, dtypes, dims, attrs.
+    (exact=False: the oracle stand-ins of the CPU suite sum in different precisions.)"""
+    from xclim_b200 import calendar as xcal, indices
+    data = batch._inputs()
+    units = {"tas": "K", "tasmax": "K", "tasmin": "K", "pr": "mm/d"}
+    fields = {k: make_field(v, "1981-01-01", calendar="noleap", units=units[k]) for k, v in data.items()}
+    pers = {(var, p_): xcal.select_percentile(xcal.percentile_doy(fields[var], window=5, per=p_), p_)
+            for var, p_ in (("tasmax", 90.0), ("tasmax", 10.0), ("tasmin", 90.0))}
+    per_of = {"tx90p": ("tasmax", 90.0), "tx10p": ("tasmax", 10.0), "tn90p": ("tasmin", 90.0)}
+    fused = indices.run_batch(fields, pers)
+    assert list(fused) == [n for n, _ in indices.BATCH_INDICATORS]
+    n_fused = 0
+    for name, var in indices.BATCH_INDICATORS:
+        fn = getattr(indices, name)
+        ref = fn(fields[var], pers[per_of[name]]) if name in per_of else fn(fields[var])
+        got = fused[name]
+        assert got.dims == ref.dims and got.values.dtype == ref.values.dtype, name
+        if exact or np.issubdtype(ref.values.dtype, np.integer):
+            np.testing.assert_array_equal(got.values, ref.values, err_msg=name)
+        else:
+            np.testing.assert_allclose(got.values, ref.values, rtol=2e-6, equal_nan=True, err_msg=name)
+        assert got.attrs == ref.attrs, (name, got.attrs, ref.attrs)
+        n_fused += indices.BATCH_FUSED[name] is not None
+    assert n_fused >= 42
+
+
+def test_run_batch_fused_passes_host_logic(host):
+    _check_run_batch_against_single_calls(exact=False)
+
+
+def _check_reference_default_call_shapes():
+    """Call shapes that used to raise: freq=None (the reference default of the run-length functions,
+    indices/run_length.py:275-335), index="last" (run_length.py:223-272), array thresholds in threshold_count
+    (indices/generic.py:329-335), tuple spell_reducer (generic.py:555-585)."""
+    from xclim_b200 import Field, generic, run_length as rl
+    rng = np.random.default_rng(33)
+    T, shape = 365 * 2 + 30, (2, 3)
+    x = rng.gamma(0.5, 4.0, (T,) + shape).astype(np.float32)
+    x[rng.random(x.shape) < 0.01] = np.nan
+    da = make_field(x, "2001-01-01", calendar="noleap", units="mm/d")
+    mask = make_field((x > 1.0).astype(np.float32), "2001-01-01", calendar="noleap", units="")
+    m = x > 1.0
+    whole = np.array([0, T])
+    # ---- freq=None: the statistic of the whole series, no time dimension
+    for red, win in (("max", 1), ("sum", 3), ("count", 2), ("mean", 1), ("std", 1)):
+        got = rl.rle_statistics(mask, red, win)            # freq=None is the default
+        assert got.dims == da.dims[1:] and got.values.shape == shape
+        exp = O.resample_and_rl(m, True, O.rle_statistics, poff=whole, reducer=red, window=win)[0]
+        np.testing.assert_allclose(got.values, exp, rtol=1e-6)
+    np.testing.assert_array_equal(rl.longest_run(mask).values,
+                                  O.resample_and_rl(m, True, O.rle_statistics, poff=whole, reducer="max", window=1)[0])
+    np.testing.assert_array_equal(rl.windowed_run_count(mask, 3).values,
+                                  O.resample_and_rl(m, True, O.rle_statistics, poff=whole, reducer="sum", window=3)[0])
+    fr = rl.first_run(mask, 3)
+    np.testing.assert_array_equal(fr.values, O.first_run(m, 3, poff=whole)[0])
+    assert fr.dims == da.dims[1:]
+    cd = generic.cumulative_difference(da, 1.0, ">", freq=None)
+    np.testing.assert_allclose(cd.values, O.cumulative_difference(x, 1.0, ">", whole)[0], rtol=1e-5)
+    # ---- index="last": a run counts for the period of its last element
+    poff = da.time.period_offsets("MS")
+    got = rl.rle_statistics(mask, "max", 1, freq="MS", index="last").values
+    exp = np.zeros((len(poff) - 1,) + shape, np.float32)
+    for idx in np.ndindex(shape):
+        col = m[(slice(None),) + idx]
+        t = 0
+        while t < T:
+            if col[t]:
+                e = t
+                while e + 1 < T and col[e + 1]:
+                    e += 1
+                p = np.searchsorted(poff, e, side="right") - 1
+                exp[(p,) + idx] = max(exp[(p,) + idx], e - t + 1)
+                t = e + 1
+            else:
+                t += 1
+    np.testing.assert_array_equal(got, exp)
+    first = rl.rle_statistics(mask, "max", 1, freq="MS", index="first").values
+    assert (first != got).any()
+    with pytest.raises(ValueError):
+        rl.rle_statistics(mask, "max", 1, freq="MS", index="middle")
+    # ---- array thresholds: per cell and per time step, compared in float64
+    thr_cell = (0.5 + rng.random(shape)).astype(np.float64)
+    thr_full = (0.5 + rng.random((T,) + shape)).astype(np.float64)
+    poff_y = da.time.period_offsets("YS")
+    with np.errstate(invalid="ignore"):
+        exp_cell = np.stack([(x[a:b].astype(np.float64) > thr_cell).sum(0) for a, b in O._groups(poff_y)])
+        exp_full = np.stack([(x[a:b].astype(np.float64) >= thr_full[a:b]).sum(0) for a, b in O._groups(poff_y)])
+    got = generic.threshold_count(da, ">", Field(thr_cell, da.dims[1:], None, {}, {}), "YS")
+    np.testing.assert_array_equal(got.values, exp_cell)
+    assert got.values.dtype == np.int64
+    np.testing.assert_array_equal(generic.threshold_count(da, ">=", thr_full, "YS").values, exp_full)
+    swapped = Field(np.moveaxis(thr_full, 0, -1).copy(), da.dims[1:] + ("time",), da.time, {}, {})
+    np.testing.assert_array_equal(generic.threshold_count(da, ">=", swapped, "YS").values, exp_full)
+    with pytest.raises(ValueError):
+        generic.threshold_count(da, ">", np.zeros((3, 3)), "YS")
+    # ---- tuple spell_reducer
+    a, b = generic.spell_length_statistics(da, 1.0, 1, None, "<", ("max", "count"), "YS")
+    np.testing.assert_array_equal(a.values, O.spell_length_statistics(x, 1.0, 1, None, "<", "max", poff_y))
+    np.testing.assert_array_equal(b.values, O.spell_length_statistics(x, 1.0, 1, None, "<", "count", poff_y))
+
+
+def test_reference_default_call_shapes(host):
+    _check_reference_default_call_shapes()

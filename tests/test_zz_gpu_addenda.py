@@ -88,3 +88,9 @@ def test_atmos_fused_entry_points_honour_check_missing_on_device(cuda):
 def test_bootstrap_converts_table_units_on_device(cuda):
     import test_host_layer_cpu as cpu_side
     cpu_side.test_bootstrap_converts_table_units(None)
+
+
+def test_reference_default_call_shapes_on_device(cuda):
+    """freq=None, index="last", array thresholds, tuple reducers through the real kernels."""
+    import test_host_layer_cpu as cpu_side
+    cpu_side._check_reference_default_call_shapes()

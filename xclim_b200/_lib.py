@@ -61,11 +61,37 @@ SIGNATURES = {
     "xc_synth_f32": (_i32, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _u64, _vp]),
     "xc_mask_steps_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "xc_host_stream_workspace_bytes": (_i64, [_i64, _i64, _vp, _i32]),
+    "xc_period_count_arr_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _i32, _vp, _i64, _vp, _vp]),
+    "xc_period_multi_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _i32, _vp]),
     "xc_table_cell_major_f64": (_i32, [_vp, _i32, _i32, _i64, _vp, _vp]),
     "xc_copy_box_async": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp]),
     "xc_period_runstat_f32_host": (_i32, [_vp, _i64, _i64, _vp, _i32, _i32, _f64, _i32, _i32, _i32, _vp, _vp,
                                           _vp, _i64]),
 }
+
+
+
+# ---- plan of the fused multi-output pass (include/xclim_b200.h: XcMultiPlan)
+class MultiLite(C.Structure):
+    _fields_ = [("sgn", C.c_float), ("thr", C.c_float), ("wmax", _i32), ("slot_n", _i32), ("slot_max", _i32)]
+
+
+class MultiFull(C.Structure):
+    _fields_ = [("sgn", C.c_float), ("thr", C.c_float), ("wmax", _i32), ("wa", _i32), ("wb", _i32), ("wms", _i32),
+                ("ms_sgn", C.c_float), ("ms_thr0", C.c_float), ("slot_n", _i32), ("slot_max", _i32),
+                ("slot_sum_a", _i32), ("slot_cnt_a", _i32), ("slot_sum_b", _i32), ("slot_cnt_b", _i32),
+                ("slot_ms", _i32)]
+
+
+class MultiSum(C.Structure):
+    _fields_ = [("sgn", C.c_float), ("thr", C.c_float), ("off_sgn", C.c_float), ("off", C.c_float), ("mode", _i32),
+                ("slot", _i32)]
+
+
+class MultiPlan(C.Structure):
+    _fields_ = [("n_lite", _i32), ("n_full", _i32), ("n_sums", _i32), ("lite", MultiLite * 4), ("full", MultiFull * 2),
+                ("sums", MultiSum * 3), ("slot_sum", _i32), ("slot_mean", _i32), ("slot_min", _i32), ("slot_max", _i32)]
+
 
 _lib = None
 

@@ -400,6 +400,181 @@ int32_t check_common(const void* x, int64_t T, int64_t C, int64_t ldx, const voi
   return XC_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// threshold count against an ARRAY threshold (indices/generic.py:301-361 with a DataArray threshold:
+// numpy compares float32 data with a float64 array in float64); thr_tstride = 0 for a
+// per-cell threshold (lat, lon), C for one that also varies in time.
+// ------------------------------------------------------------------------------------------------
+template <int OP>
+__global__ void __launch_bounds__(kThreads)
+period_count_arr_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, const int32_t* __restrict__ poff,
+                        const double* __restrict__ thr, int64_t thr_tstride, int32_t* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (c >= C) return;
+  const int p = blockIdx.y;
+  const int t0 = poff[p], t1 = poff[p + 1];
+  int32_t n = 0;
+  const float* px = x + (int64_t)t0 * ldx + c;
+  const double* pt = thr + (int64_t)t0 * thr_tstride + c;
+#pragma unroll 4
+  for (int t = t0; t < t1; ++t) {
+    n += cmpd<OP>((double)ld_stream(px), *pt) ? 1 : 0;
+    px += ldx;
+    pt += thr_tstride;
+  }
+  out[(int64_t)p * C + c] = n;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// fused multi-output pass: every count / run statistic / reduction that shares (x, periods)
+// ------------------------------------------------------------------------------------------------
+// One thread = 4 adjacent cells x one period, like the single-output kernels; the state of NL "lite"
+// conditions (count + longest run), NF "full" conditions (+ two windowed run sums / counts + largest run
+// sum of an excess) and NS conditional sums lives in registers next to the plain statistics.  The
+// template arguments are the (rounded-up) numbers of each kind: unused entries are computed and dropped.
+template <int NL, int NF, int NS>
+__global__ void __launch_bounds__(kThreads)
+period_multi_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, const int32_t* __restrict__ poff,
+                    const XcMultiPlan plan, float* __restrict__ out, int64_t slot_stride) {
+  constexpr int VEC = 4;
+  const int64_t c0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * VEC;
+  if (c0 >= C) return;
+  const int p = blockIdx.y;
+  const int t0 = poff[p], t1 = poff[p + 1];
+  double s[VEC];
+  float mn[VEC], mx[VEC];
+  int32_t nok[VEC];
+  int32_t l_len[NL > 0 ? NL : 1][VEC], l_n[NL > 0 ? NL : 1][VEC], l_mx[NL > 0 ? NL : 1][VEC];
+  int32_t f_len[NF > 0 ? NF : 1][VEC], f_n[NF > 0 ? NF : 1][VEC], f_mx[NF > 0 ? NF : 1][VEC];
+  int32_t f_sa[NF > 0 ? NF : 1][VEC], f_ca[NF > 0 ? NF : 1][VEC], f_sb[NF > 0 ? NF : 1][VEC], f_cb[NF > 0 ? NF : 1][VEC];
+  double f_rs[NF > 0 ? NF : 1][VEC], f_best[NF > 0 ? NF : 1][VEC];
+  double q[NS > 0 ? NS : 1][VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    s[i] = 0.0; mn[i] = INFINITY; mx[i] = -INFINITY; nok[i] = 0;
+#pragma unroll
+    for (int j = 0; j < NL; ++j) { l_len[j][i] = 0; l_n[j][i] = 0; l_mx[j][i] = 0; }
+#pragma unroll
+    for (int j = 0; j < NF; ++j) {
+      f_len[j][i] = 0; f_n[j][i] = 0; f_mx[j][i] = 0; f_sa[j][i] = 0; f_ca[j][i] = 0; f_sb[j][i] = 0; f_cb[j][i] = 0;
+      f_rs[j][i] = 0.0; f_best[j][i] = 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < NS; ++j) q[j][i] = 0.0;
+  }
+  auto close_run = [&](int j, int i, int32_t L, double rs) {   // a run of L steps of full condition j has ended
+    f_sa[j][i] += (L >= plan.full[j].wa) ? L : 0;
+    f_ca[j][i] += (L >= plan.full[j].wa) ? 1 : 0;
+    f_sb[j][i] += (L >= plan.full[j].wb) ? L : 0;
+    f_cb[j][i] += (L >= plan.full[j].wb) ? 1 : 0;
+    f_best[j][i] = (L >= plan.full[j].wms) ? fmax(f_best[j][i], rs) : f_best[j][i];
+  };
+  stream_rows<VEC>(x + c0, ldx, t0, t1, [&](const Vec<VEC>& r) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float v = r.v[i];
+      const bool ok = (v == v);
+      nok[i] += ok ? 1 : 0;
+      s[i] += ok ? (double)v : 0.0;
+      mn[i] = fminf(mn[i], v);
+      mx[i] = fmaxf(mx[i], v);
+#pragma unroll
+      for (int j = 0; j < NL; ++j) {
+        const bool c = plan.lite[j].sgn * v > plan.lite[j].thr;
+        l_len[j][i] = c ? l_len[j][i] + 1 : 0;
+        l_n[j][i] += c ? 1 : 0;
+        l_mx[j][i] = max(l_mx[j][i], l_len[j][i]);
+      }
+#pragma unroll
+      for (int j = 0; j < NF; ++j) {
+        const bool c = plan.full[j].sgn * v > plan.full[j].thr;
+        const int32_t L = f_len[j][i];
+        // windows are >= 1, so a closing "run" of length 0 never qualifies
+        close_run(j, i, c ? 0 : L, f_rs[j][i]);
+        const float e = plan.full[j].ms_sgn * (v - plan.full[j].ms_thr0);   // float32 excess, like `tasmax - thresh`
+        f_rs[j][i] = c ? f_rs[j][i] + (double)e : 0.0;
+        f_len[j][i] = c ? L + 1 : 0;
+        f_n[j][i] += c ? 1 : 0;
+        f_mx[j][i] = max(f_mx[j][i], f_len[j][i]);
+      }
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        if (plan.sums[j].mode == 0) {
+          const float d = plan.sums[j].off_sgn * (v - plan.sums[j].off);     // (x - t) / (t - x) in float32
+          q[j][i] += ok ? (double)fmaxf(d, 0.f) : 0.0;
+        } else {
+          q[j][i] += (plan.sums[j].sgn * v > plan.sums[j].thr) ? (double)v : 0.0;
+        }
+      }
+    }
+  });
+  auto put_f = [&](int slot, const float (&v)[VEC]) {
+    if (slot >= 0) store_vec<VEC>(out + (int64_t)slot * slot_stride + (int64_t)p * C + c0, v);
+  };
+  auto put_i = [&](int slot, const int32_t (&v)[VEC]) {
+    if (slot >= 0) store_vec<VEC>(reinterpret_cast<int32_t*>(out) + (int64_t)slot * slot_stride + (int64_t)p * C + c0, v);
+  };
+  float rf[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) rf[i] = (float)s[i];
+  put_f(plan.slot_sum, rf);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) rf[i] = nok[i] ? (float)(s[i] / (double)nok[i]) : NAN;
+  put_f(plan.slot_mean, rf);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) rf[i] = nok[i] ? mn[i] : NAN;
+  put_f(plan.slot_min, rf);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) rf[i] = nok[i] ? mx[i] : NAN;
+  put_f(plan.slot_max, rf);
+#pragma unroll
+  for (int j = 0; j < NL; ++j) {
+    put_i(plan.lite[j].slot_n, l_n[j]);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) rf[i] = (l_mx[j][i] >= plan.lite[j].wmax) ? (float)l_mx[j][i] : 0.f;
+    put_f(plan.lite[j].slot_max, rf);
+  }
+#pragma unroll
+  for (int j = 0; j < NF; ++j) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) close_run(j, i, f_len[j][i], f_rs[j][i]);     // runs closed by the period end
+    put_i(plan.full[j].slot_n, f_n[j]);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) rf[i] = (f_mx[j][i] >= plan.full[j].wmax) ? (float)f_mx[j][i] : 0.f;
+    put_f(plan.full[j].slot_max, rf);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) rf[i] = (float)f_sa[j][i];
+    put_f(plan.full[j].slot_sum_a, rf);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) rf[i] = (float)f_ca[j][i];
+    put_f(plan.full[j].slot_cnt_a, rf);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) rf[i] = (float)f_sb[j][i];
+    put_f(plan.full[j].slot_sum_b, rf);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) rf[i] = (float)f_cb[j][i];
+    put_f(plan.full[j].slot_cnt_b, rf);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) rf[i] = (float)f_best[j][i];
+    put_f(plan.full[j].slot_ms, rf);
+  }
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) rf[i] = (float)q[j][i];
+    put_f(plan.sums[j].slot, rf);
+  }
+}
+
+template <int NL, int NF, int NS>
+int32_t launch_multi(const float* x, int64_t C, int64_t ldx, const int32_t* poff, int32_t P, const XcMultiPlan& plan,
+                     float* out, cudaStream_t st) {
+  period_multi_kernel<NL, NF, NS><<<grid_for(C, 4, P), kThreads, 0, st>>>(x, C, ldx, poff, plan, out, (int64_t)P * C);
+  return launch_status("period_multi_kernel");
+}
+
 }  // namespace
 }  // namespace xc
 
@@ -566,4 +741,55 @@ extern "C" int32_t xc_period_run_maxsum_f32(const float* x, int64_t T, int64_t C
   };
   return (op == XC_OP_GT || op == XC_OP_GE) ? go2(std::integral_constant<int, XC_OP_GT>{})
                                             : go2(std::integral_constant<int, XC_OP_LT>{});
+}
+
+extern "C" int32_t xc_period_multi_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                       const int32_t* period_offsets, int32_t P, const XcMultiPlan* plan_host,
+                                       void* out, int32_t n_slots, void* stream) {
+  int32_t e = check_common(x, T, C, ldx, period_offsets, P, out);
+  if (e) return e;
+  XC_REQUIRE(plan_host != nullptr, "null pointer argument");
+  const XcMultiPlan& pl = *plan_host;
+  XC_REQUIRE(pl.n_lite >= 0 && pl.n_lite <= 4 && pl.n_full >= 0 && pl.n_full <= 2 && pl.n_sums >= 0 && pl.n_sums <= 3,
+             "plan holds at most 4 lite, 2 full and 3 sum conditions");
+  XC_REQUIRE(can_vec4(x, C, ldx, out, nullptr), "xc_period_multi_f32 needs C, ldx multiples of 4 and 16-byte aligned buffers");
+  auto slot_ok = [&](int32_t sl) { return sl >= -1 && sl < n_slots; };
+  bool ok = slot_ok(pl.slot_sum) && slot_ok(pl.slot_mean) && slot_ok(pl.slot_min) && slot_ok(pl.slot_max);
+  for (int j = 0; j < 4; ++j) ok = ok && slot_ok(pl.lite[j].slot_n) && slot_ok(pl.lite[j].slot_max);
+  for (int j = 0; j < 2; ++j)
+    ok = ok && slot_ok(pl.full[j].slot_n) && slot_ok(pl.full[j].slot_max) && slot_ok(pl.full[j].slot_sum_a) &&
+         slot_ok(pl.full[j].slot_cnt_a) && slot_ok(pl.full[j].slot_sum_b) && slot_ok(pl.full[j].slot_cnt_b) &&
+         slot_ok(pl.full[j].slot_ms) && pl.full[j].wa >= 1 && pl.full[j].wb >= 1 && pl.full[j].wms >= 1;
+  for (int j = 0; j < 3; ++j) ok = ok && slot_ok(pl.sums[j].slot) && (pl.sums[j].mode == 0 || pl.sums[j].mode == 1);
+  XC_REQUIRE(ok, "plan: output slot outside [-1, n_slots) or window < 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* o = (float*)out;
+  // rounded-up instantiations: unused entries of the plan must carry slot -1 (their work is dropped)
+  const int nl = pl.n_lite == 0 ? 0 : (pl.n_lite <= 2 ? 2 : 4);
+  const int nf = pl.n_full;
+  const int ns = pl.n_sums == 0 ? 0 : 3;
+#define XC_MULTI(L, F, S) \
+  if (nl == L && nf == F && ns == S) return launch_multi<L, F, S>(x, C, ldx, period_offsets, P, pl, o, st)
+  XC_MULTI(0, 0, 0); XC_MULTI(0, 0, 3); XC_MULTI(0, 1, 0); XC_MULTI(0, 1, 3); XC_MULTI(0, 2, 0); XC_MULTI(0, 2, 3);
+  XC_MULTI(2, 0, 0); XC_MULTI(2, 0, 3); XC_MULTI(2, 1, 0); XC_MULTI(2, 1, 3); XC_MULTI(2, 2, 0); XC_MULTI(2, 2, 3);
+  XC_MULTI(4, 0, 0); XC_MULTI(4, 0, 3); XC_MULTI(4, 1, 0); XC_MULTI(4, 1, 3); XC_MULTI(4, 2, 0); XC_MULTI(4, 2, 3);
+#undef XC_MULTI
+  set_error("plan shape not instantiated");
+  return XC_ERR_UNSUPPORTED;
+}
+
+extern "C" int32_t xc_period_count_arr_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                           const int32_t* period_offsets, int32_t P, int32_t op,
+                                           const double* thr, int64_t thr_tstride, int32_t* out_count, void* stream) {
+  int32_t e = check_common(x, T, C, ldx, period_offsets, P, out_count);
+  if (e) return e;
+  XC_REQUIRE(thr != nullptr, "null pointer argument");
+  XC_REQUIRE(thr_tstride == 0 || thr_tstride >= C, "threshold time stride must be 0 (per cell) or >= C");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)((C + kThreads - 1) / kThreads), (unsigned)P, 1);
+  return dispatch_op(op, [&](auto OPC) -> int32_t {
+    constexpr int OP = decltype(OPC)::value;
+    period_count_arr_kernel<OP><<<grid, kThreads, 0, st>>>(x, C, ldx, period_offsets, thr, thr_tstride, out_count);
+    return launch_status("period_count_arr_kernel");
+  });
 }

@@ -93,6 +93,18 @@ def period_count(x2d, poff, op_code, thr, cmp_f64=False, want_valid=False):
     return out, valid
 
 
+def period_count_arr(x2d, poff, op_code, thr2d, per_time):
+    """Counts against an array threshold: ``thr2d`` float64 ``(T, C)`` (per_time) or ``(1, C)`` (per cell)."""
+    T, C = x2d.shape
+    P = len(poff) - 1
+    assert thr2d.dtype == torch.float64 and thr2d.is_contiguous() and thr2d.shape[-1] == C
+    poff_d = dev_ints(poff, np.int32, x2d.device)
+    out = torch.empty((P, C), dtype=torch.int32, device=x2d.device)
+    check(load().xc_period_count_arr_f32(x2d.data_ptr(), T, C, x2d.stride(0), poff_d.data_ptr(), P, op_code,
+                                         thr2d.data_ptr(), C if per_time else 0, out.data_ptr(), current_stream_ptr()))
+    return out
+
+
 def period_runstat(x2d, poff, op_code, thr, reducer_code, window, resample_before_rl=True, cmp_f64=False,
                    want_valid=False):
     T, C = x2d.shape
@@ -393,4 +405,34 @@ def period_run_quantile(x2d, poff, op_code, thr, q, window, resample_before_rl=T
                                             poff_h.ctypes.data, P, op_code, float(thr), int(bool(cmp_f64)), float(q),
                                             int(window), int(bool(resample_before_rl)), out.data_ptr(),
                                             current_stream_ptr()))
+    return out
+
+
+# ------------------------------------------------------------------------------------ fused multi-output pass
+def normalise_condition(op_code, thr):
+    """(sgn, thr') with  x op thr  <=>  sgn * x > thr'  for every float32 x (NaN: False on both sides).
+    ``thr`` is compared in float32 (numpy >= 2 weak-scalar rule, indices/generic.py:301-326)."""
+    t = np.float32(thr)
+    gt, lt, ge, le = _lib.OPS[">"], _lib.OPS["<"], _lib.OPS[">="], _lib.OPS["<="]
+    if op_code == gt:
+        return 1.0, float(t)
+    if op_code == lt:
+        return -1.0, float(-t)
+    if op_code == ge:                      # x >= t  <=>  x > pred(t)
+        return 1.0, float(np.nextafter(t, np.float32(-np.inf)))
+    if op_code == le:                      # x <= t  <=>  -x >= -t  <=>  -x > pred(-t)
+        return -1.0, float(np.nextafter(np.float32(-t), np.float32(-np.inf)))
+    raise NotImplementedError("the fused pass takes the operators >, >=, <, <=")
+
+
+def period_multi(x2d, poff, plan, n_slots):
+    """One streaming pass producing every output of ``plan`` (a ``_lib.MultiPlan``); returns the
+    ``(n_slots, P, C)`` float32 slot buffer (count slots hold int32 bits: view them with ``.view(torch.int32)``)."""
+    import ctypes
+    T, C = x2d.shape
+    P = len(poff) - 1
+    poff_d = dev_ints(poff, np.int32, x2d.device)
+    out = torch.empty((max(1, n_slots), P, C), dtype=torch.float32, device=x2d.device)
+    check(load().xc_period_multi_f32(x2d.data_ptr(), T, C, x2d.stride(0), poff_d.data_ptr(), P, ctypes.byref(plan),
+                                     out.data_ptr(), int(n_slots), current_stream_ptr()))
     return out

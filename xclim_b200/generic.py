@@ -41,7 +41,12 @@ def _period_time(da, ta, freq):
 
 
 def _wrap_periods(da, out2d, cell_shape, other_dims, ta, freq, attrs, dtype=None, name=None):
+    """(P, C) device result -> container of the input's family with dims (time=periods, *space); with
+    ``freq=None`` (reduction over the whole series) the time dimension is dropped, as the reference's
+    ``.reduce(dim="time")`` does."""
     vals = out2d.reshape((out2d.shape[0],) + cell_shape)
+    if freq is None:
+        vals = vals[0]
     if OPTIONS["device_outputs"] and not is_xarray(da) and getattr(vals, "is_cuda", False):
         if dtype is not None:      # same dtype as the host path, converted where the data are
             import torch
@@ -50,6 +55,8 @@ def _wrap_periods(da, out2d, cell_shape, other_dims, ta, freq, attrs, dtype=None
         vals = vals.cpu().numpy()
         if dtype is not None:
             vals = vals.astype(dtype, copy=False)
+    if freq is None:
+        return wrap_like(da, vals, tuple(other_dims), attrs=attrs, name=name)
     return wrap_like(da, vals, ("time",) + other_dims, time=_period_time(da, ta, freq), attrs=attrs, name=name)
 
 
@@ -64,6 +71,37 @@ def _scalar_threshold(threshold):
     if arr.ndim == 0:
         return float(arr), arr.dtype == np.float64
     raise NotImplementedError("array thresholds are supported through the doy-percentile entry points only")
+
+
+def _array_threshold(threshold, da, cell_shape, other_dims, x2d):
+    """A threshold given as an array (labelled like the data, or a bare array of the data's shape / of its
+    spatial shape) -> (float64 device tensor (T|1, C), varies_in_time); None for scalars."""
+    import torch
+    from .field import Field
+    if isinstance(threshold, (int, float, str, np.floating, np.integer)):
+        return None
+    labelled = isinstance(threshold, Field) or is_xarray(threshold)
+    vals = raw_values(threshold) if labelled else threshold
+    if getattr(vals, "ndim", 0) == 0:
+        return None
+    if hasattr(vals, "is_cuda"):
+        t = vals.to(x2d.device, torch.float64)
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(vals, dtype=np.float64))).to(x2d.device)
+    T = x2d.shape[0]
+    if labelled:
+        tdims = dims_of(threshold)
+        per_time = "time" in tdims
+        want = (("time",) if per_time else ()) + tuple(other_dims)
+        if set(tdims) != set(want):
+            raise ValueError(f"threshold dims {tdims} do not match the data dims {('time',) + tuple(other_dims)}")
+        t = t.permute([tdims.index(d) for d in want])
+    else:
+        per_time = tuple(t.shape) == (T,) + tuple(cell_shape)
+        if not per_time and tuple(t.shape) != tuple(cell_shape):
+            raise ValueError(f"threshold shape {tuple(t.shape)} matches neither the data nor its spatial shape")
+    t = t.contiguous().reshape((T if per_time else 1), -1)
+    return t, per_time
 
 
 # --------------------------------------------------------------------------------- a1  get_op/compare
@@ -81,9 +119,13 @@ def threshold_count(da, op, threshold, freq, constrain=None):
     if constrain is None:
         constrain = (">", "<", ">=", "<=")
     code = get_op(op, constrain)
-    thr, f64 = _scalar_threshold(threshold)
     x2d, cell_shape, other, ta = _unwrap(da)
-    out, _ = device.period_count(x2d, ta.period_offsets(freq), code, thr, cmp_f64=f64)
+    arr = _array_threshold(threshold, da, cell_shape, other, x2d)
+    if arr is not None:      # DataArray / array threshold: compared in float64
+        out = device.period_count_arr(x2d, ta.period_offsets(freq), code, arr[0], arr[1])
+    else:
+        thr, f64 = _scalar_threshold(threshold)
+        out, _ = device.period_count(x2d, ta.period_offsets(freq), code, thr, cmp_f64=f64)
     return _wrap_periods(da, out, cell_shape, other, ta, freq, attrs_of(da), dtype=np.int64)
 
 
@@ -119,9 +161,7 @@ def cumulative_difference(data, threshold, op, freq=None):
     """Sum of the excess over (deficit under) a threshold -- indices/generic.py:1514-1552."""
     code = get_op(op, constrain=(">", ">=", "<", "<="))
     thr = threshold_in_units_of(threshold, data) if isinstance(threshold, str) else float(threshold)
-    if freq is None:
-        raise NotImplementedError("freq=None (no resampling) is not part of the B200 hot path")
-    x2d, cell_shape, other, ta = _unwrap(data)
+    x2d, cell_shape, other, ta = _unwrap(data)      # freq=None: the whole series (one period, no time dim)
     out, _ = device.period_reduce(x2d, ta.period_offsets(freq), _lib.STATS["sum"], _lib.TF_EXCESS, code, thr)
     attrs = attrs_of(data)
     u = attrs.get("units", "")

@@ -715,6 +715,264 @@ def snowfall_intensity(prsn, thresh="1 mm/day", freq="YS-JUL"):
 
 
 
+
+# =====================================================================================================
+# The batch as FUSED passes ("unique inputs once each"): every output that shares an
+# input variable and a resampling frequency comes out of one streaming pass (``xc_period_multi_f32``).  The
+# table below says, per indicator, which slot of which pass it is; thresholds, windows, operators and
+# frequencies are read from the indicator functions' own defaults (so the two cannot drift apart), and
+# tests/test_gpu_batch.py checks run_batch against the one-call-per-indicator results, values and attrs.
+# Kinds: ("stat", name, units) | ("count", op_or_param) | ("prop",) | ("excess", op) | ("intensity",) |
+#        ("spell", op, reducer) | ("maxlen", op) | ("maxsum",) | None = not fusable here (own kernel).
+# =====================================================================================================
+BATCH_FUSED = {
+    "tg_mean": ("stat", "mean", None), "tg_max": ("stat", "max", None), "tg_min": ("stat", "min", None),
+    "tn_mean": ("stat", "mean", None), "tn_max": ("stat", "max", None), "tn_min": ("stat", "min", None),
+    "tx_mean": ("stat", "mean", None), "tx_max": ("stat", "max", None), "tx_min": ("stat", "min", None),
+    "max_1day_precipitation_amount": ("stat", "max", "mm"), "precip_accumulation": ("stat", "sum", "mm"),
+    "max_n_day_precipitation_amount": None,
+    "frost_days": ("count", "<"), "ice_days": ("count", "<"), "hot_days": ("count", ">"),
+    "tx_days_above": ("count", "op"), "tx_days_below": ("count", "op"), "tn_days_above": ("count", "op"),
+    "tn_days_below": ("count", "op"), "tg_days_above": ("count", "op"), "tg_days_below": ("count", "op"),
+    "wetdays": ("count", "op"), "dry_days": ("count", "op"), "wetdays_prop": ("prop",),
+    "growing_degree_days": ("excess", ">"), "cooling_degree_days": ("excess", ">"),
+    "heating_degree_days": ("excess", "<"), "daily_pr_intensity": ("intensity",),
+    "cold_spell_days": ("spell", "sum"), "cold_spell_frequency": ("spell", "count"),
+    "cold_spell_max_length": ("maxlen",), "cold_spell_total_length": ("spell", "sum"),
+    "hot_spell_frequency": ("spell", "count"), "hot_spell_max_length": ("maxlen",),
+    "hot_spell_total_length": ("spell", "sum"), "hot_spell_max_magnitude": ("maxsum",),
+    "heat_wave_index": ("spell", "sum"), "frost_free_spell_max_length": ("maxlen",),
+    "maximum_consecutive_frost_days": ("maxlen", "<"), "maximum_consecutive_frost_free_days": ("maxlen", ">="),
+    "maximum_consecutive_tx_days": ("maxlen", ">"),
+    "maximum_consecutive_dry_days": ("maxlen", "op"), "maximum_consecutive_wet_days": ("maxlen", ">="),
+    "dry_spell_frequency": None, "dry_spell_total_length": None, "dry_spell_max_length": ("maxlen", "<"),
+    "wet_spell_frequency": None, "tx90p": None, "tx10p": None, "tn90p": None,
+}
+
+
+class _PassBuilder:
+    """Collects the outputs wanted from one (variable, freq) pass and packs them into ``_lib.MultiPlan``s
+    (a pass that needs more conditions than one plan holds is split into several launches)."""
+
+    def __init__(self):
+        self.stats = {}          # name -> request key
+        self.conds = {}          # (sgn, thr) -> {"n": bool, "max": wmax or None, "runs": {(kind, w)}, "ms": (w, sgn, thr0)}
+        self.sums = {}           # (mode, sgn, thr, off_sgn, off) -> True
+
+    def cond(self, op_code, thr):
+        from . import device
+        key = device.normalise_condition(op_code, thr)
+        return self.conds.setdefault(key, {"n": False, "max": False, "runs": set(), "ms": None}), key
+
+    def plans(self):
+        """-> list of (plan, n_slots, {request key: (slot, is_int)})"""
+        from . import _lib
+        lite = [(k, c) for k, c in self.conds.items() if not c["runs"] and c["ms"] is None]
+        full = [(k, c) for k, c in self.conds.items() if c["runs"] or c["ms"] is not None]
+        sums = list(self.sums)
+        out = []
+        first = True
+        while first or lite or full or sums:
+            plan = _lib.MultiPlan()
+            for j in range(4):
+                plan.lite[j].slot_n = plan.lite[j].slot_max = -1
+                plan.lite[j].wmax = 1
+            for j in range(2):
+                f = plan.full[j]
+                f.slot_n = f.slot_max = f.slot_sum_a = f.slot_cnt_a = f.slot_sum_b = f.slot_cnt_b = f.slot_ms = -1
+                f.wmax = f.wa = f.wb = f.wms = 1
+            for j in range(3):
+                plan.sums[j].slot = -1
+            plan.slot_sum = plan.slot_mean = plan.slot_min = plan.slot_max = -1
+            where, n = {}, 0
+
+            def slot(key, is_int=False):
+                nonlocal n
+                where[key] = (n, is_int)
+                n += 1
+                return n - 1
+            if first:
+                for st in self.stats:
+                    setattr(plan, "slot_" + st, slot(("stat", st)))
+            take_l, lite = lite[:4], lite[4:]
+            plan.n_lite = len(take_l)
+            for j, ((sgn, thr), c) in enumerate(take_l):
+                e = plan.lite[j]
+                e.sgn, e.thr = sgn, thr
+                if c["n"]:
+                    e.slot_n = slot(("n", sgn, thr), True)
+                if c["max"]:
+                    e.slot_max = slot(("max", sgn, thr))
+            take_f, full = full[:2], full[2:]
+            plan.n_full = len(take_f)
+            for j, ((sgn, thr), c) in enumerate(take_f):
+                e = plan.full[j]
+                e.sgn, e.thr = sgn, thr
+                if c["n"]:
+                    e.slot_n = slot(("n", sgn, thr), True)
+                if c["max"]:
+                    e.slot_max = slot(("max", sgn, thr))
+                windows = sorted({w for _, w in c["runs"]})
+                if len(windows) > 2:
+                    raise NotImplementedError("at most two run windows per condition in one fused pass")
+                for wi, w in enumerate(windows):
+                    setattr(e, "wa" if wi == 0 else "wb", int(w))
+                    for kind in ("sum", "count"):
+                        if (kind, w) in c["runs"]:
+                            fld = ("slot_sum_" if kind == "sum" else "slot_cnt_") + ("a" if wi == 0 else "b")
+                            setattr(e, fld, slot((kind, sgn, thr, w)))
+                if c["ms"] is not None:
+                    w, ms_sgn, thr0 = c["ms"]
+                    e.wms, e.ms_sgn, e.ms_thr0 = int(w), ms_sgn, thr0
+                    e.slot_ms = slot(("ms", sgn, thr, w))
+            take_s, sums = sums[:3], sums[3:]
+            plan.n_sums = len(take_s)
+            for j, key in enumerate(take_s):
+                mode, sgn, thr, off_sgn, off = key
+                e = plan.sums[j]
+                e.mode, e.sgn, e.thr, e.off_sgn, e.off = mode, sgn, thr, off_sgn, off
+                e.slot = slot(("qsum",) + key)
+            out.append((plan, n, where))
+            first = False
+        return out
+
+
+def run_batch(fields, pers=None, names=None):
+    """The indicators of ``BATCH_INDICATORS`` (or ``names``) over ``fields = {"tas": ..., "tasmax": ..., "tasmin":
+    ..., "pr": ...}`` with one fused pass per (variable, frequency); ``pers[(variable, percentile)]`` are the
+    ``percentile_doy`` tables of tx90p / tx10p / tn90p.  Returns ``{name: result}``: the same containers, dtypes,
+    values and attrs as the one-call-per-indicator functions."""
+    import inspect
+
+    import numpy as np
+
+    from . import _lib, device
+    from .field import attrs_of, time_axis_of
+    from .generic import _unwrap, _wrap_periods
+
+    want = [(nm, var) for nm, var in BATCH_INDICATORS if names is None or nm in names]
+    per_of = {"tx90p": ("tasmax", 90.0), "tx10p": ("tasmax", 10.0), "tn90p": ("tasmin", 90.0)}
+    g = globals()
+    unwrapped = {}
+    passes = {}          # (var, freq) -> _PassBuilder
+    todo = []            # (name, var, freq, spec, params, request keys)
+    results = {}
+    for nm, var in want:
+        fn = g[nm]
+        spec = BATCH_FUSED.get(nm)
+        sig = inspect.signature(fn)
+        par = {k: v.default for k, v in sig.parameters.items() if v.default is not inspect.Parameter.empty}
+        if spec is None or par.get("resample_before_rl", True) is not True:
+            results[nm] = fn(fields[var], pers[per_of[nm]]) if nm in per_of else fn(fields[var])
+            continue
+        da = fields[var]
+        if var not in unwrapped:
+            unwrapped[var] = _unwrap(da)
+        freq = par["freq"]
+        pb = passes.setdefault((var, freq), _PassBuilder())
+        kind = spec[0]
+        th = par.get("thresh")
+        if isinstance(th, str) and th.endswith(" mm"):          # daily amounts on mm/d data (cf. dry_spell_max_length)
+            th = th.replace(" mm", " mm/d")
+        thr = threshold_in_units_of(th, da) if th is not None else None
+        op = None
+        if len(spec) > 1 and kind in ("count", "excess", "maxlen"):
+            op = par["op"] if spec[1] == "op" else spec[1]
+        elif "op" in par:
+            op = par["op"]
+        keys = None
+        if kind == "stat":
+            pb.stats[spec[1]] = True
+            keys = ("stat", spec[1])
+        elif kind in ("count", "prop"):
+            c, k = pb.cond(_lib.OPS[op], thr)
+            c["n"] = True
+            keys = ("n",) + k
+        elif kind == "excess":
+            sgn = 1.0 if op in (">", ">=") else -1.0
+            key = (0, 0.0, 0.0, sgn, float(np.float32(thr)))
+            pb.sums[key] = True
+            keys = ("qsum",) + key
+        elif kind == "intensity":
+            c, k = pb.cond(_lib.OPS[op], thr)
+            c["n"] = True
+            key = (1, k[0], k[1], 0.0, 0.0)
+            pb.sums[key] = True
+            keys = (("qsum",) + key, ("n",) + k)
+        elif kind == "spell":
+            c, k = pb.cond(_lib.OPS[op], thr)
+            c["runs"].add((spec[1], int(par["window"])))
+            keys = (spec[1],) + k + (int(par["window"]),)
+        elif kind == "maxlen":
+            c, k = pb.cond(_lib.OPS[op], thr)
+            c["max"] = True
+            keys = ("max",) + k
+        elif kind == "maxsum":
+            c, k = pb.cond(_lib.OPS[">"], thr)
+            c["ms"] = (int(par["window"]), 1.0, float(np.float32(thr)))
+            keys = ("ms",) + k + (int(par["window"]),)
+        todo.append((nm, var, freq, spec, par, keys))
+    # ---- one launch (or a few) per (variable, frequency)
+    slots = {}           # (var, freq, request key) -> device tensor (P, C)
+    for (var, freq), pb in passes.items():
+        x2d, cell_shape, other, ta = unwrapped[var]
+        poff = ta.period_offsets(freq)
+        for plan, n, where in pb.plans():
+            buf = device.period_multi(x2d, poff, plan, n)
+            for key, (sl, is_int) in where.items():
+                slots[(var, freq, key)] = buf[sl].view(_torch_int32()) if is_int else buf[sl]
+    # ---- wrap like the one-call-per-indicator functions
+    for nm, var, freq, spec, par, keys in todo:
+        da = fields[var]
+        x2d, cell_shape, other, ta = unwrapped[var]
+        attrs = attrs_of(da)
+        kind = spec[0]
+        get = lambda k: slots[(var, freq, k)]   # noqa: E731
+        if kind == "stat":
+            from .units import to_agg_units_attrs
+            attrs.update(to_agg_units_attrs(da, spec[1]))
+            out = _wrap_periods(da, get(keys), cell_shape, other, ta, freq, attrs)
+            results[nm] = out.assign_attrs(units=spec[2]) if spec[2] else out
+        elif kind == "count":
+            results[nm] = _wrap_periods(da, get(keys), cell_shape, other, ta, freq, attrs,
+                                        dtype=np.int64).assign_attrs(units="d")
+        elif kind == "prop":
+            cnt = _wrap_periods(da, get(keys), cell_shape, other, ta, freq, attrs, dtype=np.int64).assign_attrs(units="d")
+            n = np.diff(time_axis_of(da).period_offsets(freq)).reshape((-1,) + (1,) * (cnt.values.ndim - 1))
+            results[nm] = _like(cnt, _ratio(cnt.values, n), units="1")
+        elif kind == "excess":
+            u = attrs.get("units", "")
+            attrs["units"] = f"{u} d".strip()
+            results[nm] = _wrap_periods(da, get(keys), cell_shape, other, ta, freq, attrs)
+        elif kind == "intensity":
+            s_ = _wrap_periods(da, get(keys[0]), cell_shape, other, ta, freq, attrs)
+            wd = _wrap_periods(da, get(keys[1]), cell_shape, other, ta, freq, attrs, dtype=np.int64)
+            results[nm] = _like(s_, _ratio(s_.values, wd.values), units="mm d-1")
+        elif kind in ("spell", "maxlen"):
+            attrs["units"] = "" if (kind == "spell" and spec[1] == "count") else "d"
+            val = get(keys)
+            if kind == "maxlen" and int(par.get("window", 1)) > 1:     # `max_l.where(max_l >= window, 0)`
+                val = val * (val >= int(par["window"]))
+            results[nm] = _wrap_periods(da, val, cell_shape, other, ta, freq, attrs, dtype=np.float32)
+        elif kind == "maxsum":
+            attrs["units"] = "K d"
+            results[nm] = _wrap_periods(da, get(keys), cell_shape, other, ta, freq, attrs)
+    return {nm: results[nm] for nm, _ in want}
+
+
+def _torch_int32():
+    import torch
+    return torch.int32
+
+
+def _like(template, values, units):
+    from .field import Field, is_xarray
+    if is_xarray(template):
+        return template.copy(data=values).assign_attrs(units=units)
+    return Field(values, template.dims, template.time, dict(template.coords), {**template.attrs, "units": units},
+                 template.name)
+
+
 # ---- end-to-end path: host-backed inputs stream through HBM in lat slabs (xclim_b200/streaming.py)
 def _stream_entry_points():
     import inspect

@@ -20,11 +20,8 @@ _GT = _lib.OPS[">"]
 def _check(freq, index, ufunc_1dim):
     if ufunc_1dim is True and freq is not None:  # indices/run_length.py:67-68
         raise ValueError("Resampling after run length operations is not implemented for 1d method")
-    if index != "first":
-        raise NotImplementedError("index='last' is not supported by the B200 hot path")
-    if freq is None:
-        raise NotImplementedError("freq=None (whole-series statistics) : pass a freq covering the series, e.g. via "
-                                  "resample_and_rl(..., freq=...)")
+    if index not in ("first", "last"):
+        raise ValueError(f"index must be 'first' or 'last', got {index!r}")
 
 
 def _run_reduce(x2d, poff, reducer, window, resample_before_rl):
@@ -61,7 +58,14 @@ def rle_statistics(da, reducer, window, dim="time", freq=None, ufunc_1dim="from_
         raise NotImplementedError("only dim='time' is supported")
     _check(freq, index, ufunc_1dim)
     x2d, cell_shape, other, ta = _mask_unwrap(da)
-    out = _run_reduce(x2d, ta.period_offsets(freq), reducer, window, False)
+    poff = ta.period_offsets(freq)
+    if index == "last" and freq is not None:
+        # a run is attributed to the period of its LAST element (run_length.py:223-272): the same statistic on the
+        # time-reversed series, whose runs start where the original ones end
+        T = x2d.shape[0]
+        out = _run_reduce(x2d.flip(0), (T - np.asarray(poff)[::-1]).astype(np.int32), reducer, window, False).flip(0)
+    else:
+        out = _run_reduce(x2d, poff, reducer, window, False)
     return _wrap_periods(da, out, cell_shape, other, ta, freq, attrs_of(da), dtype=np.float32)
 
 
@@ -101,8 +105,6 @@ def resample_and_rl(da, resample_before_rl, compute, *args, freq, dim="time", **
 def _boundary(da, window, dim, freq, coord, position):
     if dim != "time":
         raise NotImplementedError("only dim='time' is supported")
-    if freq is None:
-        raise NotImplementedError("freq=None: pass a freq covering the series")
     if coord not in (False, None, "dayofyear"):
         raise NotImplementedError("coord must be False or 'dayofyear'")
     x2d, cell_shape, other, ta = _mask_unwrap(da)
@@ -143,8 +145,6 @@ def windowed_max_run_sum(da, window, dim="time", freq=None, index="first"):
     largest run sum of the positive values over runs at least ``window`` long."""
     if dim != "time" or index != "first":
         raise NotImplementedError("only dim='time', index='first' are supported")
-    if freq is None:
-        raise NotImplementedError("freq=None: pass a freq covering the series")
     x2d, cell_shape, other, ta = _mask_unwrap(da)
     out = device.period_run_maxsum(x2d, ta.period_offsets(freq), _GT, 0.0, window, resample_before_rl=False)
     return _wrap_periods(da, out, cell_shape, other, ta, freq, attrs_of(da), dtype=np.float32)

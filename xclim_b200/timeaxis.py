@@ -171,7 +171,10 @@ class TimeAxis:
         return gid
 
     def period_offsets(self, freq: str) -> np.ndarray:
-        """int32 array of P+1 boundaries: period p covers ``[off[p], off[p+1])``."""
+        """int32 array of P+1 boundaries: period p covers ``[off[p], off[p+1])``.  ``freq=None`` is the
+        reference's "no resampling" (indices/run_length.py:275-335 default): one period, the whole series."""
+        if freq is None:
+            return np.array([0, len(self)], dtype=np.int32)
         key = ("poff", freq)
         if key not in self._cache:
             gid = self.group_ids(freq)
