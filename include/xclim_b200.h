@@ -384,29 +384,38 @@ int32_t xc_period_count_arr_f32(const float* x, int64_t T, int64_t C, int64_t ld
  * every count / run-length / reduction output that shares (x, period_offsets) comes out of a single
  * streaming pass ("unique inputs once each").
  *   Conditions are normalised on the host to  sgn * x > thr  (x >= t  <=>  x > pred(t), x < t  <=>
- *   -x > -t, ...; indices/generic.py:301-326), runs are cut at the period edges
+ *   -x > -t, ...; indices/generic.py:301-326); runs are cut at the period edges
  *   (resample_before_rl=True, indices/run_length.py:122-129).
- *   lite[i]:  n_true (threshold_count, generic.py:329-361) and the longest run (rle_statistics "max")
- *   full[i]:  + total length / number of the runs >= wa and >= wb (windowed_run_count / _events,
- *             run_length.py:381-488) and the largest run sum of (x - ms_thr0) over runs >= wms
- *             (windowed_max_run_sum, run_length.py:491-540)
- *   sums[i]:  mode 0: sum of (off_sgn * (x - off)).clip(0) (cumulative_difference, generic.py:1514-1552);
- *             mode 1: sum of x where the condition holds (thresholded_statistics "sum", generic.py:1278-1320)
- *   plain:    sum / mean / min / max of x (select_resample_op, generic.py:83-125)
- *   Every `slot_*` is an index into `out` (slot s occupies out[s*P*C .. (s+1)*P*C), 4-byte elements:
- *   int32 for n_true and the run counts, float32 otherwise) or -1 when that output is not wanted.
- *   A longest run shorter than `wmax` is reported as 0 (`max_l.where(max_l >= window, 0)`,
- *   indices/_threshold.py:311).  Needs C % 4 == 0, ldx % 4 == 0 and 16-byte aligned buffers.
+ *   cond[i]: n_true (threshold_count, generic.py:329-361) and the longest run (rle_statistics "max";
+ *            a longest run shorter than `wmax` is reported as 0: `max_l.where(max_l >= window, 0)`,
+ *            indices/_threshold.py:311)
+ *   runs[k]: total length (kind 0, windowed_run_count) or number (kind 1, windowed_run_events) of the runs
+ *            of condition k / 2 that are at least `window` long (run_length.py:381-488): the first
+ *            n_runs / 2 conditions own two run outputs each (slot -1: unused), so that the kernel
+ *            needs no indirection; `cond` must equal k / 2
+ *   msum[0]: largest run sum of sgn * (x - thr0) over the runs of condition 0 at least `window` long
+ *            (windowed_max_run_sum, run_length.py:491-540; hot_spell_max_magnitude); `cond` must be 0
+ *   sums[k]: mode 0: sum of (off_sgn * (x - off)).clip(0) (cumulative_difference, generic.py:1514-1552);
+ *            mode 1: sum of x where sgn * x > thr (thresholded_statistics "sum", generic.py:1278-1320)
+ *   plain:   sum / mean / min / max of x (select_resample_op, generic.py:83-125)
+ *   Every `slot` is an index into `out` (slot s occupies out[s*P*C .. (s+1)*P*C), 4-byte elements: int32
+ *   for n_true, float32 otherwise) or -1 when that output is not wanted.  n_runs is even.  Needs C % 4 == 0,
+ *   ldx % 4 == 0 and 16-byte aligned buffers.
  * ------------------------------------------------------------------------------------------- */
-typedef struct { float sgn, thr; int32_t wmax, slot_n, slot_max; } XcMultiLite;
-typedef struct { float sgn, thr; int32_t wmax, wa, wb, wms; float ms_sgn, ms_thr0;
-                 int32_t slot_n, slot_max, slot_sum_a, slot_cnt_a, slot_sum_b, slot_cnt_b, slot_ms; } XcMultiFull;
+#define XC_MULTI_MAX_COND 6
+#define XC_MULTI_MAX_RUNS 4
+#define XC_MULTI_MAX_MSUM 1
+#define XC_MULTI_MAX_SUMS 3
+typedef struct { float sgn, thr; int32_t wmax, slot_n, slot_max; } XcMultiCond;
+typedef struct { int32_t cond, window, kind, slot; } XcMultiRun;
+typedef struct { int32_t cond, window; float sgn, thr0; int32_t slot; } XcMultiMaxSum;
 typedef struct { float sgn, thr, off_sgn, off; int32_t mode, slot; } XcMultiSum;
 typedef struct {
-  int32_t n_lite, n_full, n_sums;
-  XcMultiLite lite[4];
-  XcMultiFull full[2];
-  XcMultiSum sums[3];
+  int32_t n_cond, n_runs, n_msum, n_sums;
+  XcMultiCond cond[XC_MULTI_MAX_COND];
+  XcMultiRun runs[XC_MULTI_MAX_RUNS];
+  XcMultiMaxSum msum[XC_MULTI_MAX_MSUM];
+  XcMultiSum sums[XC_MULTI_MAX_SUMS];
   int32_t slot_sum, slot_mean, slot_min, slot_max;
 } XcMultiPlan;
 int32_t xc_period_multi_f32(const float* x, int64_t T, int64_t C, int64_t ldx,

@@ -263,25 +263,24 @@ def period_multi(x2d, poff, plan, n_slots):
     put(plan.slot_min, O.resample_reduce(x64, poff, "min"))
     put(plan.slot_max, O.resample_reduce(x64, poff, "max"))
     with np.errstate(invalid="ignore"):
-        for j in range(plan.n_lite):
-            e = plan.lite[j]
+        conds = []
+        for j in range(plan.n_cond):
+            e = plan.cond[j]
             cond = np.float32(e.sgn) * x > np.float32(e.thr)
+            conds.append(cond)
             put(e.slot_n, np.stack([cond[a:b].sum(0) for a, b in groups]), True)
             m = run_stat(cond, "max", 1)
             put(e.slot_max, np.where(m >= e.wmax, m, 0))
-        for j in range(plan.n_full):
-            e = plan.full[j]
-            cond = np.float32(e.sgn) * x > np.float32(e.thr)
-            put(e.slot_n, np.stack([cond[a:b].sum(0) for a, b in groups]), True)
-            m = run_stat(cond, "max", 1)
-            put(e.slot_max, np.where(m >= e.wmax, m, 0))
-            put(e.slot_sum_a, run_stat(cond, "sum", e.wa))
-            put(e.slot_cnt_a, run_stat(cond, "count", e.wa))
-            put(e.slot_sum_b, run_stat(cond, "sum", e.wb))
-            put(e.slot_cnt_b, run_stat(cond, "count", e.wb))
-            if e.slot_ms >= 0:
-                exc = np.where(cond, np.float32(e.ms_sgn) * (x - np.float32(e.ms_thr0)), np.float32(0)).astype(np.float64)
-                put(e.slot_ms, O.resample_and_rl(exc, True, O.windowed_max_run_sum, int(e.wms), poff=poff))
+        for k in range(plan.n_runs):
+            r = plan.runs[k]
+            assert r.cond == k // 2
+            if r.slot >= 0:
+                put(r.slot, run_stat(conds[r.cond], "sum" if r.kind == 0 else "count", r.window))
+        for k in range(plan.n_msum):
+            m = plan.msum[k]
+            assert m.cond == 0
+            exc = np.where(conds[m.cond], np.float32(m.sgn) * (x - np.float32(m.thr0)), np.float32(0)).astype(np.float64)
+            put(m.slot, O.resample_and_rl(exc, True, O.windowed_max_run_sum, int(m.window), poff=poff))
         for j in range(plan.n_sums):
             e = plan.sums[j]
             if e.mode == 0:

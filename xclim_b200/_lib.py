@@ -72,15 +72,19 @@ SIGNATURES = {
 
 
 # ---- plan of the fused multi-output pass (include/xclim_b200.h: XcMultiPlan)
-class MultiLite(C.Structure):
+MULTI_MAX_COND, MULTI_MAX_RUNS, MULTI_MAX_MSUM, MULTI_MAX_SUMS = 6, 4, 1, 3
+
+
+class MultiCond(C.Structure):
     _fields_ = [("sgn", C.c_float), ("thr", C.c_float), ("wmax", _i32), ("slot_n", _i32), ("slot_max", _i32)]
 
 
-class MultiFull(C.Structure):
-    _fields_ = [("sgn", C.c_float), ("thr", C.c_float), ("wmax", _i32), ("wa", _i32), ("wb", _i32), ("wms", _i32),
-                ("ms_sgn", C.c_float), ("ms_thr0", C.c_float), ("slot_n", _i32), ("slot_max", _i32),
-                ("slot_sum_a", _i32), ("slot_cnt_a", _i32), ("slot_sum_b", _i32), ("slot_cnt_b", _i32),
-                ("slot_ms", _i32)]
+class MultiRun(C.Structure):
+    _fields_ = [("cond", _i32), ("window", _i32), ("kind", _i32), ("slot", _i32)]
+
+
+class MultiMaxSum(C.Structure):
+    _fields_ = [("cond", _i32), ("window", _i32), ("sgn", C.c_float), ("thr0", C.c_float), ("slot", _i32)]
 
 
 class MultiSum(C.Structure):
@@ -89,8 +93,10 @@ class MultiSum(C.Structure):
 
 
 class MultiPlan(C.Structure):
-    _fields_ = [("n_lite", _i32), ("n_full", _i32), ("n_sums", _i32), ("lite", MultiLite * 4), ("full", MultiFull * 2),
-                ("sums", MultiSum * 3), ("slot_sum", _i32), ("slot_mean", _i32), ("slot_min", _i32), ("slot_max", _i32)]
+    _fields_ = [("n_cond", _i32), ("n_runs", _i32), ("n_msum", _i32), ("n_sums", _i32),
+                ("cond", MultiCond * MULTI_MAX_COND), ("runs", MultiRun * MULTI_MAX_RUNS),
+                ("msum", MultiMaxSum * MULTI_MAX_MSUM), ("sums", MultiSum * MULTI_MAX_SUMS),
+                ("slot_sum", _i32), ("slot_mean", _i32), ("slot_min", _i32), ("slot_max", _i32)]
 
 
 _lib = None

@@ -59,19 +59,19 @@ __device__ __forceinline__ void store_vec(T* dst, const T (&v)[VEC]) {
   }
 }
 
-// Iterate f(t, Vec) over t in [t0, t1) with kUnroll loads in flight.
-template <int VEC, typename F>
+// Iterate f(t, Vec) over t in [t0, t1) with UNROLL loads in flight.
+template <int VEC, int UNROLL = kUnroll, typename F>
 __device__ __forceinline__ void stream_rows(const float* __restrict__ col, int64_t ldx, int t0, int t1,
                                             F&& f) {
   int t = t0;
   const float* p = col + (int64_t)t0 * ldx;
-  for (; t + kUnroll <= t1; t += kUnroll) {
-    Vec<VEC> r[kUnroll];
+  for (; t + UNROLL <= t1; t += UNROLL) {
+    Vec<VEC> r[UNROLL];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) r[u].load(p + (int64_t)u * ldx);
+    for (int u = 0; u < UNROLL; ++u) r[u].load(p + (int64_t)u * ldx);
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) f(r[u]);
-    p += (int64_t)kUnroll * ldx;
+    for (int u = 0; u < UNROLL; ++u) f(r[u]);
+    p += (int64_t)UNROLL * ldx;
   }
   for (; t < t1; ++t) {
     Vec<VEC> r;
@@ -430,82 +430,116 @@ period_count_arr_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, con
 // ------------------------------------------------------------------------------------------------
 // fused multi-output pass: every count / run statistic / reduction that shares (x, periods)
 // ------------------------------------------------------------------------------------------------
-// One thread = 4 adjacent cells x one period, like the single-output kernels; the state of NL "lite"
-// conditions (count + longest run), NF "full" conditions (+ two windowed run sums / counts + largest run
-// sum of an excess) and NS conditional sums lives in registers next to the plain statistics.  The
-// template arguments are the (rounded-up) numbers of each kind: unused entries are computed and dropped.
-template <int NL, int NF, int NS>
+// One thread = 2 adjacent cells x one period (64-bit loads, kUnroll rows in flight); the state of NC
+// conditions (run length, count, longest run), NR windowed run outputs, NM largest-run-sum outputs and NS
+// conditional sums lives in registers next to the plain statistics -- about 25 registers per cell for the
+// richest pass of the batch (tasmax), so that 4-5 CTAs stay resident per SM.  Per element and cell: 7
+// instructions per condition, 3 per run output, ~10 per run sum, 6 per conditional sum, 8 for the plain
+// statistics.  The template arguments are the (rounded-up) numbers of each kind: unused entries are
+// computed and dropped (their slots are -1).
+template <>
+struct Vec<2> {
+  float v[2];
+  __device__ __forceinline__ void load(const float* p) {
+    float2 q;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(q.x), "=f"(q.y) : "l"(p));
+    v[0] = q.x; v[1] = q.y;
+  }
+};
+
+// a[j] for a warp-uniform runtime j without dynamic register indexing (which would go through local memory)
+template <int N, typename T>
+__device__ __forceinline__ T pick_uniform(const T (&a)[N], int j) {
+  T r = a[0];
+#pragma unroll
+  for (int k = 1; k < N; ++k) r = (j == k) ? a[k] : r;
+  return r;
+}
+
+// Pipe balance (sm_100a issues one warp instruction per clock but the ALU pipe -- compares, selects, integer
+// adds, min/max -- and the FMA pipe each take one every OTHER clock): run lengths and counters are kept as
+// float32 (exact below 2^24 steps) so that their updates are FFMA / FADD on the FMA pipe,
+//     cf = (sgn * v > thr) ? 1 : 0;   len' = cf * len + cf;   fin = len - cf * len;   n += cf
+// leaving one FSET and one FMNMX per condition on the ALU pipe, and the run outputs sit at fixed places (two
+// per leading condition) so that no select chain is needed to find their condition.  History (tasmax pass of
+// the batch, quarter grid, HBM time 1.75 ms): integer state, 4 cells per thread 19.1 ms (255 registers);
+// unit list + 2 cells 15.4 ms; float state 13.3 ms (ncu: ALU pipe 74 %, 18 FSEL + 18 ISETP per element in
+// the select chains, long_scoreboard 50 % at 16 warps per SM).
+// VEC / UNROLL: light passes (no run outputs) take 4 cells per thread, the others 2 cells and more rows in flight.
+template <int NC, int NCR, int NM, int NS, int VEC, int UNROLL>
 __global__ void __launch_bounds__(kThreads)
 period_multi_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, const int32_t* __restrict__ poff,
                     const XcMultiPlan plan, float* __restrict__ out, int64_t slot_stride) {
-  constexpr int VEC = 4;
+  constexpr int NR = 2 * NCR;
+  constexpr int NC1 = NC > 0 ? NC : 1, NR1 = NR > 0 ? NR : 1, NM1 = NM > 0 ? NM : 1, NS1 = NS > 0 ? NS : 1;
+  static_assert(NCR <= NC && (NM == 0 || NC > 0), "run outputs need their condition");
   const int64_t c0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * VEC;
   if (c0 >= C) return;
   const int p = blockIdx.y;
   const int t0 = poff[p], t1 = poff[p + 1];
   double s[VEC];
-  float mn[VEC], mx[VEC];
-  int32_t nok[VEC];
-  int32_t l_len[NL > 0 ? NL : 1][VEC], l_n[NL > 0 ? NL : 1][VEC], l_mx[NL > 0 ? NL : 1][VEC];
-  int32_t f_len[NF > 0 ? NF : 1][VEC], f_n[NF > 0 ? NF : 1][VEC], f_mx[NF > 0 ? NF : 1][VEC];
-  int32_t f_sa[NF > 0 ? NF : 1][VEC], f_ca[NF > 0 ? NF : 1][VEC], f_sb[NF > 0 ? NF : 1][VEC], f_cb[NF > 0 ? NF : 1][VEC];
-  double f_rs[NF > 0 ? NF : 1][VEC], f_best[NF > 0 ? NF : 1][VEC];
-  double q[NS > 0 ? NS : 1][VEC];
+  float mn[VEC], mx[VEC], nok[VEC];
+  float c_len[NC1][VEC], c_n[NC1][VEC], c_mx[NC1][VEC];
+  float r_acc[NR1][VEC];
+  double m_rs[NM1][VEC], m_best[NM1][VEC];
+  double q[NS1][VEC];
+  // run outputs: value added when a run of length L >= window closes = ra * L + rb  (sum: L, count: 1)
+  float r_w[NR1], r_a[NR1], r_b[NR1];
+#pragma unroll
+  for (int k = 0; k < NR; ++k) {
+    r_w[k] = (float)plan.runs[k].window;
+    r_a[k] = plan.runs[k].kind == 0 ? 1.f : 0.f;
+    r_b[k] = 1.f - r_a[k];
+  }
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    s[i] = 0.0; mn[i] = INFINITY; mx[i] = -INFINITY; nok[i] = 0;
+    s[i] = 0.0; mn[i] = INFINITY; mx[i] = -INFINITY; nok[i] = 0.f;
 #pragma unroll
-    for (int j = 0; j < NL; ++j) { l_len[j][i] = 0; l_n[j][i] = 0; l_mx[j][i] = 0; }
+    for (int j = 0; j < NC; ++j) { c_len[j][i] = 0.f; c_n[j][i] = 0.f; c_mx[j][i] = 0.f; }
 #pragma unroll
-    for (int j = 0; j < NF; ++j) {
-      f_len[j][i] = 0; f_n[j][i] = 0; f_mx[j][i] = 0; f_sa[j][i] = 0; f_ca[j][i] = 0; f_sb[j][i] = 0; f_cb[j][i] = 0;
-      f_rs[j][i] = 0.0; f_best[j][i] = 0.0;
-    }
+    for (int k = 0; k < NR; ++k) r_acc[k][i] = 0.f;
 #pragma unroll
-    for (int j = 0; j < NS; ++j) q[j][i] = 0.0;
+    for (int k = 0; k < NM; ++k) { m_rs[k][i] = 0.0; m_best[k][i] = 0.0; }
+#pragma unroll
+    for (int k = 0; k < NS; ++k) q[k][i] = 0.0;
   }
-  auto close_run = [&](int j, int i, int32_t L, double rs) {   // a run of L steps of full condition j has ended
-    f_sa[j][i] += (L >= plan.full[j].wa) ? L : 0;
-    f_ca[j][i] += (L >= plan.full[j].wa) ? 1 : 0;
-    f_sb[j][i] += (L >= plan.full[j].wb) ? L : 0;
-    f_cb[j][i] += (L >= plan.full[j].wb) ? 1 : 0;
-    f_best[j][i] = (L >= plan.full[j].wms) ? fmax(f_best[j][i], rs) : f_best[j][i];
-  };
-  stream_rows<VEC>(x + c0, ldx, t0, t1, [&](const Vec<VEC>& r) {
+  stream_rows<VEC, UNROLL>(x + c0, ldx, t0, t1, [&](const Vec<VEC>& r) {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       const float v = r.v[i];
       const bool ok = (v == v);
-      nok[i] += ok ? 1 : 0;
+      nok[i] += ok ? 1.f : 0.f;
       s[i] += ok ? (double)v : 0.0;
       mn[i] = fminf(mn[i], v);
       mx[i] = fmaxf(mx[i], v);
+      float cf[NC1], fin[NC1];   // cf: condition as 1 / 0; fin: length of the run that ends at this step (0: none)
 #pragma unroll
-      for (int j = 0; j < NL; ++j) {
-        const bool c = plan.lite[j].sgn * v > plan.lite[j].thr;
-        l_len[j][i] = c ? l_len[j][i] + 1 : 0;
-        l_n[j][i] += c ? 1 : 0;
-        l_mx[j][i] = max(l_mx[j][i], l_len[j][i]);
+      for (int j = 0; j < NC; ++j) {
+        cf[j] = (plan.cond[j].sgn * v > plan.cond[j].thr) ? 1.f : 0.f;
+        const float L = c_len[j][i];
+        fin[j] = __fmaf_rn(-cf[j], L, L);
+        c_len[j][i] = __fmaf_rn(cf[j], L, cf[j]);
+        c_n[j][i] += cf[j];
+        c_mx[j][i] = fmaxf(c_mx[j][i], c_len[j][i]);
       }
 #pragma unroll
-      for (int j = 0; j < NF; ++j) {
-        const bool c = plan.full[j].sgn * v > plan.full[j].thr;
-        const int32_t L = f_len[j][i];
-        // windows are >= 1, so a closing "run" of length 0 never qualifies
-        close_run(j, i, c ? 0 : L, f_rs[j][i]);
-        const float e = plan.full[j].ms_sgn * (v - plan.full[j].ms_thr0);   // float32 excess, like `tasmax - thresh`
-        f_rs[j][i] = c ? f_rs[j][i] + (double)e : 0.0;
-        f_len[j][i] = c ? L + 1 : 0;
-        f_n[j][i] += c ? 1 : 0;
-        f_mx[j][i] = max(f_mx[j][i], f_len[j][i]);
+      for (int k = 0; k < NR; ++k) {   // windows are >= 1: fin == 0 never qualifies
+        const float L = fin[k >> 1];
+        const float take = (L >= r_w[k]) ? 1.f : 0.f;
+        r_acc[k][i] = __fmaf_rn(take, __fmaf_rn(r_a[k], L, r_b[k]), r_acc[k][i]);
+      }
+      if constexpr (NM > 0) {
+        const float e = plan.msum[0].sgn * (v - plan.msum[0].thr0);   // float32 excess, like `tasmax - thresh`
+        m_best[0][i] = (fin[0] >= (float)plan.msum[0].window) ? fmax(m_best[0][i], m_rs[0][i]) : m_best[0][i];
+        m_rs[0][i] = (cf[0] != 0.f) ? m_rs[0][i] + (double)e : 0.0;
       }
 #pragma unroll
-      for (int j = 0; j < NS; ++j) {
-        if (plan.sums[j].mode == 0) {
-          const float d = plan.sums[j].off_sgn * (v - plan.sums[j].off);     // (x - t) / (t - x) in float32
-          q[j][i] += ok ? (double)fmaxf(d, 0.f) : 0.0;
+      for (int k = 0; k < NS; ++k) {
+        if (plan.sums[k].mode == 0) {
+          const float d = plan.sums[k].off_sgn * (v - plan.sums[k].off);     // (x - t) / (t - x) in float32
+          q[k][i] += ok ? (double)fmaxf(d, 0.f) : 0.0;
         } else {
-          q[j][i] += (plan.sums[j].sgn * v > plan.sums[j].thr) ? (double)v : 0.0;
+          q[k][i] += (plan.sums[k].sgn * v > plan.sums[k].thr) ? (double)v : 0.0;
         }
       }
     }
@@ -521,57 +555,61 @@ period_multi_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, const i
   for (int i = 0; i < VEC; ++i) rf[i] = (float)s[i];
   put_f(plan.slot_sum, rf);
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) rf[i] = nok[i] ? (float)(s[i] / (double)nok[i]) : NAN;
+  for (int i = 0; i < VEC; ++i) rf[i] = (nok[i] != 0.f) ? (float)(s[i] / (double)nok[i]) : NAN;
   put_f(plan.slot_mean, rf);
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) rf[i] = nok[i] ? mn[i] : NAN;
+  for (int i = 0; i < VEC; ++i) rf[i] = (nok[i] != 0.f) ? mn[i] : NAN;
   put_f(plan.slot_min, rf);
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) rf[i] = nok[i] ? mx[i] : NAN;
+  for (int i = 0; i < VEC; ++i) rf[i] = (nok[i] != 0.f) ? mx[i] : NAN;
   put_f(plan.slot_max, rf);
 #pragma unroll
-  for (int j = 0; j < NL; ++j) {
-    put_i(plan.lite[j].slot_n, l_n[j]);
+  for (int j = 0; j < NC; ++j) {
+    int32_t ri[VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) rf[i] = (l_mx[j][i] >= plan.lite[j].wmax) ? (float)l_mx[j][i] : 0.f;
-    put_f(plan.lite[j].slot_max, rf);
+    for (int i = 0; i < VEC; ++i) ri[i] = (int32_t)c_n[j][i];
+    put_i(plan.cond[j].slot_n, ri);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) rf[i] = (c_mx[j][i] >= (float)plan.cond[j].wmax) ? c_mx[j][i] : 0.f;
+    put_f(plan.cond[j].slot_max, rf);
   }
 #pragma unroll
-  for (int j = 0; j < NF; ++j) {
+  for (int k = 0; k < NR; ++k) {      // runs closed by the period end
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) close_run(j, i, f_len[j][i], f_rs[j][i]);     // runs closed by the period end
-    put_i(plan.full[j].slot_n, f_n[j]);
+    for (int i = 0; i < VEC; ++i) {
+      const float L = c_len[k >> 1][i];
+      rf[i] = r_acc[k][i] + ((L >= r_w[k]) ? __fmaf_rn(r_a[k], L, r_b[k]) : 0.f);
+    }
+    put_f(plan.runs[k].slot, rf);
+  }
+  if constexpr (NM > 0) {
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) rf[i] = (f_mx[j][i] >= plan.full[j].wmax) ? (float)f_mx[j][i] : 0.f;
-    put_f(plan.full[j].slot_max, rf);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) rf[i] = (float)f_sa[j][i];
-    put_f(plan.full[j].slot_sum_a, rf);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) rf[i] = (float)f_ca[j][i];
-    put_f(plan.full[j].slot_cnt_a, rf);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) rf[i] = (float)f_sb[j][i];
-    put_f(plan.full[j].slot_sum_b, rf);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) rf[i] = (float)f_cb[j][i];
-    put_f(plan.full[j].slot_cnt_b, rf);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) rf[i] = (float)f_best[j][i];
-    put_f(plan.full[j].slot_ms, rf);
+    for (int i = 0; i < VEC; ++i) {
+      const float L = c_len[0][i];
+      rf[i] = (float)((L >= (float)plan.msum[0].window) ? fmax(m_best[0][i], m_rs[0][i]) : m_best[0][i]);
+    }
+    put_f(plan.msum[0].slot, rf);
   }
 #pragma unroll
-  for (int j = 0; j < NS; ++j) {
+  for (int k = 0; k < NS; ++k) {
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) rf[i] = (float)q[j][i];
-    put_f(plan.sums[j].slot, rf);
+    for (int i = 0; i < VEC; ++i) rf[i] = (float)q[k][i];
+    put_f(plan.sums[k].slot, rf);
   }
 }
 
-template <int NL, int NF, int NS>
+template <int NC, int NCR, int NM, int NS>
 int32_t launch_multi(const float* x, int64_t C, int64_t ldx, const int32_t* poff, int32_t P, const XcMultiPlan& plan,
                      float* out, cudaStream_t st) {
-  period_multi_kernel<NL, NF, NS><<<grid_for(C, 4, P), kThreads, 0, st>>>(x, C, ldx, poff, plan, out, (int64_t)P * C);
+  // 4 cells per thread only pays for the lightest passes (measured: conditional sums are bound by the
+  // float32 -> float64 conversions on the XU pipe, more conditions by registers)
+  if constexpr (NCR == 0 && NM == 0 && NS == 0 && NC <= 2) {
+    period_multi_kernel<NC, NCR, NM, NS, 4, 8><<<grid_for(C, 4, P), kThreads, 0, st>>>(x, C, ldx, poff, plan, out,
+                                                                                        (int64_t)P * C);
+  } else {
+    period_multi_kernel<NC, NCR, NM, NS, 2, 12><<<grid_for(C, 2, P), kThreads, 0, st>>>(x, C, ldx, poff, plan, out,
+                                                                                         (int64_t)P * C);
+  }
   return launch_status("period_multi_kernel");
 }
 
@@ -749,30 +787,50 @@ extern "C" int32_t xc_period_multi_f32(const float* x, int64_t T, int64_t C, int
   int32_t e = check_common(x, T, C, ldx, period_offsets, P, out);
   if (e) return e;
   XC_REQUIRE(plan_host != nullptr, "null pointer argument");
-  const XcMultiPlan& pl = *plan_host;
-  XC_REQUIRE(pl.n_lite >= 0 && pl.n_lite <= 4 && pl.n_full >= 0 && pl.n_full <= 2 && pl.n_sums >= 0 && pl.n_sums <= 3,
-             "plan holds at most 4 lite, 2 full and 3 sum conditions");
+  XcMultiPlan pl = *plan_host;
+  XC_REQUIRE(pl.n_cond >= 0 && pl.n_cond <= XC_MULTI_MAX_COND && pl.n_runs >= 0 && pl.n_runs <= XC_MULTI_MAX_RUNS &&
+                 pl.n_runs % 2 == 0 && pl.n_msum >= 0 && pl.n_msum <= XC_MULTI_MAX_MSUM && pl.n_sums >= 0 &&
+                 pl.n_sums <= XC_MULTI_MAX_SUMS,
+             "plan holds at most %d conditions, %d run outputs (an even number), %d run sums and %d conditional sums",
+             XC_MULTI_MAX_COND, XC_MULTI_MAX_RUNS, XC_MULTI_MAX_MSUM, XC_MULTI_MAX_SUMS);
+  XC_REQUIRE(pl.n_runs / 2 <= pl.n_cond && (pl.n_msum == 0 || pl.n_cond > 0), "run outputs need their condition");
   XC_REQUIRE(can_vec4(x, C, ldx, out, nullptr), "xc_period_multi_f32 needs C, ldx multiples of 4 and 16-byte aligned buffers");
   auto slot_ok = [&](int32_t sl) { return sl >= -1 && sl < n_slots; };
   bool ok = slot_ok(pl.slot_sum) && slot_ok(pl.slot_mean) && slot_ok(pl.slot_min) && slot_ok(pl.slot_max);
-  for (int j = 0; j < 4; ++j) ok = ok && slot_ok(pl.lite[j].slot_n) && slot_ok(pl.lite[j].slot_max);
-  for (int j = 0; j < 2; ++j)
-    ok = ok && slot_ok(pl.full[j].slot_n) && slot_ok(pl.full[j].slot_max) && slot_ok(pl.full[j].slot_sum_a) &&
-         slot_ok(pl.full[j].slot_cnt_a) && slot_ok(pl.full[j].slot_sum_b) && slot_ok(pl.full[j].slot_cnt_b) &&
-         slot_ok(pl.full[j].slot_ms) && pl.full[j].wa >= 1 && pl.full[j].wb >= 1 && pl.full[j].wms >= 1;
-  for (int j = 0; j < 3; ++j) ok = ok && slot_ok(pl.sums[j].slot) && (pl.sums[j].mode == 0 || pl.sums[j].mode == 1);
-  XC_REQUIRE(ok, "plan: output slot outside [-1, n_slots) or window < 1");
+  // entries beyond the declared counts are neutralised (the rounded-up instantiation computes and drops them)
+  for (int j = 0; j < XC_MULTI_MAX_COND; ++j) {
+    if (j >= pl.n_cond) { pl.cond[j].slot_n = pl.cond[j].slot_max = -1; pl.cond[j].wmax = 1; pl.cond[j].sgn = 0.f; pl.cond[j].thr = 0.f; }
+    ok = ok && slot_ok(pl.cond[j].slot_n) && slot_ok(pl.cond[j].slot_max);
+  }
+  for (int k = 0; k < XC_MULTI_MAX_RUNS; ++k) {
+    if (k >= pl.n_runs) { pl.runs[k].slot = -1; pl.runs[k].cond = k / 2; pl.runs[k].window = 1; pl.runs[k].kind = 0; }
+    ok = ok && slot_ok(pl.runs[k].slot) && pl.runs[k].window >= 1 && (pl.runs[k].kind == 0 || pl.runs[k].kind == 1) &&
+         pl.runs[k].cond == k / 2;
+  }
+  for (int k = 0; k < XC_MULTI_MAX_MSUM; ++k) {
+    if (k >= pl.n_msum) { pl.msum[k].slot = -1; pl.msum[k].cond = 0; pl.msum[k].window = 1; }
+    ok = ok && slot_ok(pl.msum[k].slot) && pl.msum[k].window >= 1 && pl.msum[k].cond == 0;
+  }
+  for (int k = 0; k < XC_MULTI_MAX_SUMS; ++k) {
+    if (k >= pl.n_sums) { pl.sums[k].slot = -1; pl.sums[k].mode = 0; }
+    ok = ok && slot_ok(pl.sums[k].slot) && (pl.sums[k].mode == 0 || pl.sums[k].mode == 1);
+  }
+  XC_REQUIRE(ok, "plan: output slot outside [-1, n_slots), window < 1 or run output not at its condition's place");
   cudaStream_t st = (cudaStream_t)stream;
   float* o = (float*)out;
-  // rounded-up instantiations: unused entries of the plan must carry slot -1 (their work is dropped)
-  const int nl = pl.n_lite == 0 ? 0 : (pl.n_lite <= 2 ? 2 : 4);
-  const int nf = pl.n_full;
+  const int ncr = pl.n_runs / 2;
+  int nc = pl.n_cond == 0 ? 0 : (pl.n_cond <= 2 ? 2 : (pl.n_cond <= 4 ? 4 : 6));
+  const int nm = pl.n_msum;
   const int ns = pl.n_sums == 0 ? 0 : 3;
-#define XC_MULTI(L, F, S) \
-  if (nl == L && nf == F && ns == S) return launch_multi<L, F, S>(x, C, ldx, period_offsets, P, pl, o, st)
-  XC_MULTI(0, 0, 0); XC_MULTI(0, 0, 3); XC_MULTI(0, 1, 0); XC_MULTI(0, 1, 3); XC_MULTI(0, 2, 0); XC_MULTI(0, 2, 3);
-  XC_MULTI(2, 0, 0); XC_MULTI(2, 0, 3); XC_MULTI(2, 1, 0); XC_MULTI(2, 1, 3); XC_MULTI(2, 2, 0); XC_MULTI(2, 2, 3);
-  XC_MULTI(4, 0, 0); XC_MULTI(4, 0, 3); XC_MULTI(4, 1, 0); XC_MULTI(4, 1, 3); XC_MULTI(4, 2, 0); XC_MULTI(4, 2, 3);
+#define XC_MULTI(CN, R, M, S) \
+  if (nc == CN && ncr == R && nm == M && ns == S) return launch_multi<CN, R, M, S>(x, C, ldx, period_offsets, P, pl, o, st)
+#define XC_MULTI_C(CN)                                                                                   \
+  XC_MULTI(CN, 0, 0, 0); XC_MULTI(CN, 0, 0, 3); XC_MULTI(CN, 1, 0, 0); XC_MULTI(CN, 1, 0, 3);            \
+  XC_MULTI(CN, 2, 0, 0); XC_MULTI(CN, 2, 0, 3); XC_MULTI(CN, 0, 1, 0); XC_MULTI(CN, 0, 1, 3);            \
+  XC_MULTI(CN, 1, 1, 0); XC_MULTI(CN, 1, 1, 3); XC_MULTI(CN, 2, 1, 0); XC_MULTI(CN, 2, 1, 3)
+  XC_MULTI(0, 0, 0, 0); XC_MULTI(0, 0, 0, 3);
+  XC_MULTI_C(2); XC_MULTI_C(4); XC_MULTI_C(6);
+#undef XC_MULTI_C
 #undef XC_MULTI
   set_error("plan shape not instantiated");
   return XC_ERR_UNSUPPORTED;

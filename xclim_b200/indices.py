@@ -730,7 +730,7 @@ BATCH_FUSED = {
     "tn_mean": ("stat", "mean", None), "tn_max": ("stat", "max", None), "tn_min": ("stat", "min", None),
     "tx_mean": ("stat", "mean", None), "tx_max": ("stat", "max", None), "tx_min": ("stat", "min", None),
     "max_1day_precipitation_amount": ("stat", "max", "mm"), "precip_accumulation": ("stat", "sum", "mm"),
-    "max_n_day_precipitation_amount": None,
+    "max_n_day_precipitation_amount": ("stat1", "max", "mm"),
     "frost_days": ("count", "<"), "ice_days": ("count", "<"), "hot_days": ("count", ">"),
     "tx_days_above": ("count", "op"), "tx_days_below": ("count", "op"), "tn_days_above": ("count", "op"),
     "tn_days_below": ("count", "op"), "tg_days_above": ("count", "op"), "tg_days_below": ("count", "op"),
@@ -765,24 +765,22 @@ class _PassBuilder:
         return self.conds.setdefault(key, {"n": False, "max": False, "runs": set(), "ms": None}), key
 
     def plans(self):
-        """-> list of (plan, n_slots, {request key: (slot, is_int)})"""
+        """-> list of (plan, n_slots, {request key: (slot, is_int)}).  Layout of a plan (include/xclim_b200.h):
+        the conditions that own run outputs come first, two output places each (a condition with more than two
+        is listed again), the one with a largest-run-sum output is condition 0."""
         from . import _lib
-        lite = [(k, c) for k, c in self.conds.items() if not c["runs"] and c["ms"] is None]
-        full = [(k, c) for k, c in self.conds.items() if c["runs"] or c["ms"] is not None]
+        # units: one entry per condition place = (key, cond dict, [run outputs (<= 2)], wants n/max here?)
+        places = []
+        for key, c in sorted(self.conds.items(), key=lambda kv: (kv[1]["ms"] is None, -len(kv[1]["runs"]))):
+            runs = sorted(c["runs"], key=lambda kw: (kw[1], kw[0]))
+            chunks = [runs[i:i + 2] for i in range(0, len(runs), 2)] or [[]]
+            for ci, ch in enumerate(chunks):
+                places.append({"key": key, "c": c, "runs": ch, "first": ci == 0})
         sums = list(self.sums)
         out = []
         first = True
-        while first or lite or full or sums:
+        while first or places or sums:
             plan = _lib.MultiPlan()
-            for j in range(4):
-                plan.lite[j].slot_n = plan.lite[j].slot_max = -1
-                plan.lite[j].wmax = 1
-            for j in range(2):
-                f = plan.full[j]
-                f.slot_n = f.slot_max = f.slot_sum_a = f.slot_cnt_a = f.slot_sum_b = f.slot_cnt_b = f.slot_ms = -1
-                f.wmax = f.wa = f.wb = f.wms = 1
-            for j in range(3):
-                plan.sums[j].slot = -1
             plan.slot_sum = plan.slot_mean = plan.slot_min = plan.slot_max = -1
             where, n = {}, 0
 
@@ -794,38 +792,53 @@ class _PassBuilder:
             if first:
                 for st in self.stats:
                     setattr(plan, "slot_" + st, slot(("stat", st)))
-            take_l, lite = lite[:4], lite[4:]
-            plan.n_lite = len(take_l)
-            for j, ((sgn, thr), c) in enumerate(take_l):
-                e = plan.lite[j]
-                e.sgn, e.thr = sgn, thr
-                if c["n"]:
-                    e.slot_n = slot(("n", sgn, thr), True)
-                if c["max"]:
-                    e.slot_max = slot(("max", sgn, thr))
-            take_f, full = full[:2], full[2:]
-            plan.n_full = len(take_f)
-            for j, ((sgn, thr), c) in enumerate(take_f):
-                e = plan.full[j]
-                e.sgn, e.thr = sgn, thr
-                if c["n"]:
-                    e.slot_n = slot(("n", sgn, thr), True)
-                if c["max"]:
-                    e.slot_max = slot(("max", sgn, thr))
-                windows = sorted({w for _, w in c["runs"]})
-                if len(windows) > 2:
-                    raise NotImplementedError("at most two run windows per condition in one fused pass")
-                for wi, w in enumerate(windows):
-                    setattr(e, "wa" if wi == 0 else "wb", int(w))
-                    for kind in ("sum", "count"):
-                        if (kind, w) in c["runs"]:
-                            fld = ("slot_sum_" if kind == "sum" else "slot_cnt_") + ("a" if wi == 0 else "b")
-                            setattr(e, fld, slot((kind, sgn, thr, w)))
-                if c["ms"] is not None:
+            # pick the places of this launch: run-owning places first (at most MAX_RUNS / 2), a max-sum owner at 0
+            take, rest = [], []
+            n_run_places = 0
+            have_ms = False
+            for pl in places:
+                owns_runs = bool(pl["runs"])
+                owns_ms = pl["first"] and pl["c"]["ms"] is not None
+                if len(take) >= _lib.MULTI_MAX_COND or (owns_runs and n_run_places >= _lib.MULTI_MAX_RUNS // 2) or \
+                        (owns_ms and (have_ms or take)):
+                    rest.append(pl)
+                    continue
+                if owns_ms and not owns_runs and n_run_places:      # must sit at 0: only as the first place
+                    rest.append(pl)
+                    continue
+                take.append(pl)
+                n_run_places += owns_runs
+                have_ms = have_ms or owns_ms
+            # order: max-sum owner, then run owners, then the plain ones
+            take.sort(key=lambda pl: (not (pl["first"] and pl["c"]["ms"] is not None), not pl["runs"]))
+            ncr = sum(1 for pl in take if pl["runs"])
+            if take and take[0]["first"] and take[0]["c"]["ms"] is not None and not take[0]["runs"] and ncr:
+                ncr += 1      # the max-sum owner occupies run place 0 without using it
+            places = rest
+            plan.n_cond = len(take)
+            for j, pl in enumerate(take):
+                sgn, thr = pl["key"]
+                c = pl["c"]
+                e = plan.cond[j]
+                e.sgn, e.thr, e.wmax = sgn, thr, 1
+                e.slot_n = slot(("n", sgn, thr), True) if (pl["first"] and c["n"]) else -1
+                e.slot_max = slot(("max", sgn, thr)) if (pl["first"] and c["max"]) else -1
+                for u in range(2):
+                    if j < ncr:
+                        r = plan.runs[2 * j + u]
+                        r.cond, r.window, r.kind, r.slot = j, 1, 0, -1
+                        if u < len(pl["runs"]):
+                            kind, w = pl["runs"][u]
+                            r.window, r.kind = int(w), 0 if kind == "sum" else 1
+                            r.slot = slot((kind, sgn, thr, w))
+                if j == 0 and pl["first"] and c["ms"] is not None:
                     w, ms_sgn, thr0 = c["ms"]
-                    e.wms, e.ms_sgn, e.ms_thr0 = int(w), ms_sgn, thr0
-                    e.slot_ms = slot(("ms", sgn, thr, w))
-            take_s, sums = sums[:3], sums[3:]
+                    m = plan.msum[0]
+                    m.cond, m.window, m.sgn, m.thr0 = 0, int(w), ms_sgn, thr0
+                    m.slot = slot(("ms", sgn, thr, w))
+                    plan.n_msum = 1
+            plan.n_runs = 2 * ncr
+            take_s, sums = sums[:_lib.MULTI_MAX_SUMS], sums[_lib.MULTI_MAX_SUMS:]
             plan.n_sums = len(take_s)
             for j, key in enumerate(take_s):
                 mode, sgn, thr, off_sgn, off = key
@@ -881,6 +894,11 @@ def run_batch(fields, pers=None, names=None):
         elif "op" in par:
             op = par["op"]
         keys = None
+        if kind == "stat1":       # rolling(window).sum() -> max: with the default window of 1 the rolled series IS the series
+            if int(par.get("window", 1)) != 1:
+                results[nm] = fn(fields[var])
+                continue
+            kind, spec = "stat", ("stat",) + tuple(spec[1:])
         if kind == "stat":
             pb.stats[spec[1]] = True
             keys = ("stat", spec[1])
@@ -928,7 +946,10 @@ def run_batch(fields, pers=None, names=None):
         attrs = attrs_of(da)
         kind = spec[0]
         get = lambda k: slots[(var, freq, k)]   # noqa: E731
-        if kind == "stat":
+        if kind == "stat" and BATCH_FUSED[nm][0] == "stat1":     # max_n_day_precipitation_amount: units only
+            attrs["units"] = spec[2]
+            results[nm] = _wrap_periods(da, get(keys), cell_shape, other, ta, freq, attrs)
+        elif kind == "stat":
             from .units import to_agg_units_attrs
             attrs.update(to_agg_units_attrs(da, spec[1]))
             out = _wrap_periods(da, get(keys), cell_shape, other, ta, freq, attrs)
