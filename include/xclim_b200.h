@@ -215,6 +215,18 @@ int32_t xc_spell_runstat_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
                              int32_t window, int32_t window_stat, int32_t op, double thr,
                              int32_t reducer, int32_t resample_before_rl, float* out, void* stream);
 
+/* The spell mask itself, with `select_time` applied to it -- indices/generic.py:503-535 + 557-558
+ * (`is_in_spell = select_time(spell_mask(...), **indexer)`): out_mask (T, C) float32 = NaN where
+ * keep[t] == 0, else 1 / 0 (day t is / is not covered by a qualifying length-`window` block of the
+ * UNMASKED series).  keep (device uint8[T], NULL = keep all): 0 out of season, 1 in season, 2 first
+ * in-season day after a masked one inside a resampling group; drop_nan_adjacent != 0 zeroes the runs that
+ * start on a `2` day (the whole-array `rle` of run_length.py:264), 0 counts them with their in-season
+ * length (the per-series path, pinned by tests/test_indices.py:4116-4126).  Feed the mask to
+ * xc_period_runstat_f32 with op `>` 0. */
+int32_t xc_spell_mask_f32(const float* x, int64_t T, int64_t C, int64_t ldx, int32_t window,
+                          int32_t window_stat, int32_t op, double thr, const uint8_t* keep,
+                          int32_t drop_nan_adjacent, float* out_mask, void* stream);
+
 /* Host-side helper of the entry point above (no device work; exported so that it can be tested
  * without a GPU): for sum / mean windows the kernels compare the float64 window SUM s instead of
  * the float32 statistic r(s) = (float)(s) or (float)(s / window).  r is monotone in s, hence

@@ -234,6 +234,26 @@ def table_cell_major(table):
     return table.permute(2, 1, 0).contiguous()
 
 
+def spell_mask(x2d, window, window_stat_code, op_code, thr, keep=None, drop_nan_adjacent=False):
+    """Oracle spell mask (oracle.spell_mask, indices/generic.py:503-535) + select_time + the two NaN rules."""
+    x = _np(x2d)
+    m = O.spell_mask(x, int(window), STAT_NAME[window_stat_code], OP_NAME[op_code], float(thr)).astype(np.float32)
+    if keep is not None:
+        keep = np.asarray(keep)
+        if drop_nan_adjacent:
+            for c in range(m.shape[1]):
+                t = 0
+                while t < m.shape[0]:
+                    if keep[t] == 2 and m[t, c] > 0:
+                        while t < m.shape[0] and keep[t] != 0 and m[t, c] > 0:
+                            m[t, c] = 0
+                            t += 1
+                    else:
+                        t += 1
+        m[keep == 0] = np.nan
+    return torch.from_numpy(m)
+
+
 def period_count_arr(x2d, poff, op_code, thr2d, per_time):
     x = _np(x2d).astype(np.float64)
     t = _np(thr2d)
@@ -299,7 +319,7 @@ def dev_ints(arr, dtype, device):
 FUNCTIONS = [to_time_cell, period_count, period_runstat, period_runstat_gap, period_reduce, rolling_period_reduce,
              spell_runstat, period_run_maxsum, period_runstat2, percentile_doy, doy_interp, doy_threshold_count,
              mask_steps, dev_ints, period_boundary_run, period_boundary_run_range, bootstrap_doy_count, eqm_train,
-             eqm_adjust, period_run_quantile, table_cell_major, period_multi, period_count_arr]
+             eqm_adjust, period_run_quantile, table_cell_major, period_multi, period_count_arr, spell_mask]
 
 
 def install(monkeypatch):

@@ -472,3 +472,49 @@ def _check_reference_default_call_shapes():
 
 def test_reference_default_call_shapes(host):
     _check_reference_default_call_shapes()
+
+
+def _check_spell_statistics_with_indexers():
+    """select_time on the spell mask (indices/generic.py:557-558): the reference's known answer
+    (tests/test_indices.py:4116-4126: 9), the whole-array `rle` variant, and a random case against the oracle."""
+    import xclim_b200
+    from xclim_b200 import generic, indices
+    a = np.array([1] * 5 + [0] * 10 + [1] * 350, dtype=np.float32)
+    pr = make_field(a, "1900-01-01", calendar="standard", units="mm/d")
+    for fn in (indices.dry_spell_total_length, indices.dry_spell_max_length):
+        out = fn(pr, window=7, op="sum", thresh="3.1 mm", freq="MS", date_bounds=("01-10", "12-31"))
+        np.testing.assert_allclose(out.values, [9] + [0] * 11)
+        assert out.values.dtype == np.float32 and out.attrs["units"] == "d"
+        with xclim_b200.set_options(rle_nan_adjacent="drop"):       # the whole-array rle drops the run next to the NaN
+            out = fn(pr, window=7, op="sum", thresh="3.1 mm", freq="MS", date_bounds=("01-10", "12-31"))
+        np.testing.assert_allclose(out.values, [0] * 12)
+    # without the indexer the spell is whole: 16 days (3 wet days fit in a 7-day window under 3.1 mm)
+    np.testing.assert_allclose(indices.dry_spell_total_length(pr, window=7, op="sum", thresh="3.1 mm", freq="MS").values,
+                               [16] + [0] * 11)
+    # random: season JJA, window 3, both orders, against the oracle mask with NaN -> run break
+    rng = np.random.default_rng(55)
+    T, shape = 365 * 2, (2, 3)
+    x = rng.gamma(0.4, 5.0, (T,) + shape).astype(np.float32)
+    x[rng.random(x.shape) < 0.5] = 0
+    da = make_field(x, "2001-01-01", calendar="noleap", units="mm/d")
+    keep = da.time.select_mask(season="JJA")
+    m = O.spell_mask(x, 3, "sum", "<", 1.0).astype(np.float32)
+    m[~keep] = 0.0
+    for freq in ("YS", "QS-DEC"):
+        poff = da.time.period_offsets(freq)
+        for red in ("max", "sum", "count"):
+            for before in (True, False):
+                got = generic.spell_length_statistics(da, 1.0, 3, "sum", "<", red, freq, resample_before_rl=before,
+                                                      season="JJA")
+                exp = O.resample_and_rl(m > 0, before, O.rle_statistics, poff=poff, reducer=red, window=1)
+                np.testing.assert_array_equal(got.values, exp, err_msg=f"{freq} {red} {before}")
+    # window == 1 with an indexer goes the same way
+    got = generic.spell_length_statistics(da, 1.0, 1, None, "<", "max", "YS", month=[6, 7])
+    k2 = da.time.select_mask(month=[6, 7])
+    exp = O.resample_and_rl((x < 1.0) & k2[:, None, None], True, O.rle_statistics, poff=da.time.period_offsets("YS"),
+                            reducer="max", window=1)
+    np.testing.assert_array_equal(got.values, exp)
+
+
+def test_spell_statistics_with_indexers(host):
+    _check_spell_statistics_with_indexers()

@@ -94,3 +94,9 @@ def test_reference_default_call_shapes_on_device(cuda):
     """freq=None, index="last", array thresholds, tuple reducers through the real kernels."""
     import test_host_layer_cpu as cpu_side
     cpu_side._check_reference_default_call_shapes()
+
+
+def test_spell_statistics_with_indexers_on_device(cuda):
+    """select_time on the spell mask (xc_spell_mask_f32) through the real kernels."""
+    import test_host_layer_cpu as cpu_side
+    cpu_side._check_spell_statistics_with_indexers()

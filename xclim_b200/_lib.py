@@ -40,6 +40,7 @@ SIGNATURES = {
     "xc_period_reduce_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _f64, _vp, _vp, _vp]),
     "xc_rolling_period_reduce_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "xc_spell_runstat_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _f64, _i32, _i32, _vp, _vp]),
+    "xc_spell_mask_f32": (_i32, [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _f64, _vp, _i32, _vp, _vp]),
     "xc_spell_sum_interval": (_i32, [_i32, _f64, _i32, _i32, _vp, _vp, _vp]),
     "xc_percentile_doy_workspace_bytes": (_i64, [_i64, _i64, _i32, _i32, _i32, _i32]),
     "xc_percentile_doy_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _f64, _f64,

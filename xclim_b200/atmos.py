@@ -143,8 +143,11 @@ def with_missing_any(index_fn, name=None):
                 if fn is None:
                     raise ValueError(f"unknown check_missing method {method!r}")
                 masked_in = Field(x2d.reshape((x2d.shape[0],) + cell_shape), ("time",) + other, ta, {}, dict(val.attrs))
+                mopts = OPTIONS["missing_options"]
+                if isinstance(mopts.get(method), dict):      # xclim's nested form {"pct": {"tolerance": ...}}
+                    mopts = mopts[method]
                 with set_options(device_outputs=True):
-                    m = fn(masked_in, freq, **OPTIONS["missing_options"], **(indexer if method != "wmo" else {}))
+                    m = fn(masked_in, freq, **mopts, **(indexer if method != "wmo" else {}))
                 miss = m.values if hasattr(m.values, "is_cuda") else torch.from_numpy(np.asarray(m.values))
                 miss = miss.to(x2d.device).reshape((len(poff) - 1,) + cell_shape).bool()
             bad = miss if bad is None else (bad | miss)

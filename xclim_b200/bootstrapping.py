@@ -26,8 +26,7 @@ def bootstrap_doy_count(da, per, freq, op, constrain):
         raise ValueError("select one percentile first: per.sel(percentiles=p)")
     percentile = float(pcs[0])
     x2d, cell_shape, other, ta = _unwrap(da)
-    y0, y1 = int(str(clim[0])[:4]), int(str(clim[1])[:4])
-    sl = ta.sel_years(y0, y1)                                 # da.sel(time=slice(*clim))  (:158)
+    sl = ta.sel_dates(str(clim[0])[:10], str(clim[1])[:10])    # da.sel(time=slice(*clim))  (:158): full dates
     n_over = sl.stop - sl.start
     if n_over == len(ta):
         raise KeyError("`bootstrap` is unnecessary when all years are overlapping between reference "

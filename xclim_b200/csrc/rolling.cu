@@ -915,6 +915,54 @@ inline bool can_stream4(const float* x, int64_t C, int64_t ldx, const float* out
   return (C % 4 == 0) && (ldx % 4 == 0) && aligned16(x) && aligned16(out) && (size_t)w * kThreads * 16 <= 160 * 1024;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// spell mask, materialised (`select_time` on the spell mask, indices/generic.py:557-558)
+// ------------------------------------------------------------------------------------------------
+// mask[t, c] = NaN where keep[t] == 0 (out of the selected season), else 1 / 0 = day t belongs / does not
+// belong to a length-w block whose window statistic satisfies the condition (indices/generic.py:503-535,
+// computed on the UNMASKED series: the reference selects after the spell mask is built).  Run statistics of
+// this mask with `x > 0` are the reference's per-series path (statistics_run_1d, run_length.py:1408-1437):
+// a NaN ends a run, the in-season part of a spell under way on the first in-season day counts with its
+// in-season length (tests/test_indices.py:4116-4126 expects 9).  keep[t] == 2 marks a first in-season day
+// that is not the first step of its resampling group: with drop_nan_adjacent != 0 a run STARTING there is
+// zeroed, which is what the whole-array `rle` does (its `where(shift == 0)` test fails next to a NaN,
+// run_length.py:264) -- the two reference paths disagree, the caller chooses.
+// A lane owns a cell and walks the series (this is the rarely used seasonal path, not a headline kernel).
+__global__ void __launch_bounds__(kThreads)
+spell_mask_kernel(const float* __restrict__ x, int64_t T, int64_t C, int64_t ldx, int32_t w, int32_t wstat,
+                  int32_t op, float thr, const uint8_t* __restrict__ keep, int32_t drop_nan_adjacent,
+                  float* __restrict__ mask) {
+  const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (c >= C) return;
+  BlockStream bs;
+  bs.col = x + c;
+  bs.ldx = ldx;
+  bs.T = (int)T;
+  bs.w = w;
+  bs.wstat = wstat;
+  bs.op = op;
+  bs.thr = thr;
+  bs.init(0);
+  int last = -(1 << 30);      // start of the latest qualifying block
+  bool dropping = false;
+  for (int t = 0; t < (int)T; ++t) {
+    if (t + w <= (int)T && bs.next()) last = t;           // block [t, t + w - 1]
+    const bool in = last >= t - w + 1;
+    const int k = keep ? (int)keep[t] : 1;
+    float v;
+    if (k == 0) {
+      v = NAN;
+      dropping = false;
+    } else {
+      if (drop_nan_adjacent && k == 2 && in) dropping = true;   // a run starts right after a masked step
+      if (!in) dropping = false;
+      v = (in && !dropping) ? 1.f : 0.f;
+    }
+    mask[(int64_t)t * C + c] = v;
+  }
+}
+
 }  // namespace
 }  // namespace xc
 
@@ -1014,4 +1062,20 @@ extern "C" int32_t xc_spell_runstat_f32(const float* x, int64_t T, int64_t C, in
                                                                     window_stat, op, (float)thr, reducer,
                                                                     resample_before_rl ? 0 : 1, out);
   return launch_status("spell_runstat_kernel");
+}
+
+extern "C" int32_t xc_spell_mask_f32(const float* x, int64_t T, int64_t C, int64_t ldx, int32_t window,
+                                     int32_t window_stat, int32_t op, double thr, const uint8_t* keep,
+                                     int32_t drop_nan_adjacent, float* out_mask, void* stream) {
+  XC_REQUIRE(x && out_mask, "null pointer argument");
+  XC_REQUIRE(T > 0 && C > 0 && ldx >= C && T < 2147483647LL, "bad shape");
+  XC_REQUIRE(window >= 1 && window <= T, "window must be in [1, T]");
+  XC_REQUIRE(window_stat == XC_STAT_SUM || window_stat == XC_STAT_MEAN || window_stat == XC_STAT_MIN ||
+                 window_stat == XC_STAT_MAX,
+             "window reducer must be sum, mean, min or max");
+  XC_REQUIRE(op >= XC_OP_GT && op <= XC_OP_NE, "Operation `%d` not recognized.", op);
+  dim3 grid((unsigned)((C + kThreads - 1) / kThreads), 1, 1);
+  spell_mask_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, T, C, ldx, window, window_stat, op, (float)thr,
+                                                                 keep, drop_nan_adjacent, out_mask);
+  return launch_status("spell_mask_kernel");
 }

@@ -241,6 +241,9 @@ def period_runstat_host(x_host, poff, op_code, thr, reducer_code, window, cmp_f6
         out_host = torch.empty((P, C), dtype=torch.float32).pin_memory()
     if want_valid and valid_host is None:
         valid_host = torch.empty((P, C), dtype=torch.int32).pin_memory()
+    # the entry point works on its own non-blocking streams: nothing queued on torch's stream may still be
+    # using a block the caching allocator has just recycled into `workspace`
+    torch.cuda.current_stream().synchronize()
     check(lib.xc_period_runstat_f32_host(x_host.data_ptr(), T, C, poff_h.ctypes.data, P, op_code, float(thr),
                                          int(bool(cmp_f64)), reducer_code, int(window), out_host.data_ptr(),
                                          valid_host.data_ptr() if want_valid else None, workspace.data_ptr(),
@@ -283,6 +286,17 @@ def spell_runstat(x2d, poff, window, window_stat_code, op_code, thr, reducer_cod
     check(load().xc_spell_runstat_f32(x2d.data_ptr(), T, C, x2d.stride(0), poff_d.data_ptr(), P, int(window),
                                       window_stat_code, op_code, float(thr), reducer_code,
                                       int(bool(resample_before_rl)), out.data_ptr(), current_stream_ptr()))
+    return out
+
+
+def spell_mask(x2d, window, window_stat_code, op_code, thr, keep=None, drop_nan_adjacent=False):
+    """(T, C) float32 spell mask with ``select_time`` applied (NaN out of season), see xc_spell_mask_f32."""
+    T, C = x2d.shape
+    k = None if keep is None else dev_ints(np.asarray(keep, dtype=np.uint8), np.uint8, x2d.device)
+    out = torch.empty((T, C), dtype=torch.float32, device=x2d.device)
+    check(load().xc_spell_mask_f32(x2d.data_ptr(), T, C, x2d.stride(0), int(window), window_stat_code, op_code,
+                                   float(thr), _ptr(k), int(bool(drop_nan_adjacent)), out.data_ptr(),
+                                   current_stream_ptr()))
     return out
 
 

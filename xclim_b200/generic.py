@@ -177,8 +177,8 @@ def spell_length_statistics(data, threshold, window, win_reducer, op, spell_redu
     ``window == 1`` (the maximum_consecutive_dry/wet_days family) is one fused kernel:
     compare -> run-length state machine -> reducer, per (period, cell).
     """
-    if indexer:
-        raise NotImplementedError("select_time indexers are outside the B200 hot path (SURVEY.md section 8f)")
+    if indexer and (min_gap > 1):
+        raise NotImplementedError("select_time indexers together with min_gap > 1 are not supported")
     if min_gap < 1:
         raise ValueError("min_gap must be >= 1")
     if min_gap > 1 and (window != 1 or not resample_before_rl):
@@ -188,11 +188,27 @@ def spell_length_statistics(data, threshold, window, win_reducer, op, spell_redu
     reducers = [spell_reducer] if isinstance(spell_reducer, str) else list(spell_reducer)
     x2d, cell_shape, other, ta = _unwrap(data)
     poff = ta.period_offsets(freq)
+    sel_mask = None
+    if indexer:
+        # is_in_spell = select_time(spell_mask(...), **indexer)  (indices/generic.py:557-558): the mask is built
+        # on the whole series, masked (NaN) out of season, and the run statistics run on it with `mask > 0`
+        keep = ta.select_mask(**indexer).astype(np.uint8)
+        starts = np.zeros(len(ta), bool)
+        starts[np.asarray(poff[:-1])] = True
+        first_in = keep.astype(bool) & ~np.concatenate([[True], keep[:-1].astype(bool)])
+        keep[first_in & ~(starts if resample_before_rl else np.zeros(len(ta), bool))] = 2
+        if not resample_before_rl:
+            keep[0] = min(keep[0], 1)
+        wstat = _lib.STATS[(win_reducer or "sum").replace("integral", "sum")]
+        sel_mask = device.spell_mask(x2d, window, wstat, code, thr, keep,
+                                     drop_nan_adjacent=(OPTIONS["rle_nan_adjacent"] == "drop"))
     outs = []
     for sr in reducers:
         if sr not in _lib.RL_REDUCERS:
             raise NotImplementedError(f"spell reducer {sr!r} is not supported by the B200 hot path")
-        if window == 1 and min_gap > 1:     # runs_with_holes (indices/generic.py:537-538)
+        if sel_mask is not None:
+            out, _ = device.period_runstat(sel_mask, poff, _lib.OPS[">"], 0.0, _lib.RL_REDUCERS[sr], 1, resample_before_rl)
+        elif window == 1 and min_gap > 1:     # runs_with_holes (indices/generic.py:537-538)
             out = device.period_runstat_gap(x2d, poff, code, thr, _lib.RL_REDUCERS[sr], min_gap)
         elif window == 1:
             out, _ = device.period_runstat(x2d, poff, code, thr, _lib.RL_REDUCERS[sr], 1, resample_before_rl)

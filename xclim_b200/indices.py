@@ -15,10 +15,12 @@ def maximum_consecutive_dry_days(pr, thresh="1 mm/day", op="<", freq="YS", resam
     return generic.spell_length_statistics(pr, thr, 1, None, op, "max", freq, resample_before_rl=resample_before_rl)
 
 
-def maximum_consecutive_wet_days(pr, thresh="1 mm/day", freq="YS", resample_before_rl=True):
-    """indices/_threshold.py:799-841 (``op`` is fixed to ">=")."""
+def maximum_consecutive_wet_days(pr, thresh="1 mm/day", op=">=", freq="YS", resample_before_rl=True):
+    """indices/_threshold.py:799-841 (``op`` in {">", ">="}, third positional argument like the reference)."""
+    from . import _lib
+    _lib.op_code(op, (">", ">="))
     thr = threshold_in_units_of(thresh, pr)
-    return generic.spell_length_statistics(pr, thr, 1, None, ">=", "max", freq, resample_before_rl=resample_before_rl)
+    return generic.spell_length_statistics(pr, thr, 1, None, op, "max", freq, resample_before_rl=resample_before_rl)
 
 
 def tg_mean(tas, freq="YS"):
@@ -151,46 +153,46 @@ def max_n_day_precipitation_amount(pr, window=1, freq="YS"):
     return _wrap_periods(pr, out, cell_shape, other, ta, freq, attrs)
 
 
-def _dry_wet_spell(pr, thresh, window, op, win_reducer, spell_reducer, freq, resample_before_rl):
+def _dry_wet_spell(pr, thresh, window, op, win_reducer, spell_reducer, freq, resample_before_rl, **indexer):
     thr = threshold_in_units_of(thresh, pr)
     return generic.spell_length_statistics(pr, thr, window, win_reducer, op, spell_reducer, freq,
-                                           resample_before_rl=resample_before_rl)
+                                           resample_before_rl=resample_before_rl, **indexer)
 
 
-def dry_spell_frequency(pr, thresh="1.0 mm", window=3, freq="YS", resample_before_rl=True, op="sum"):
+def dry_spell_frequency(pr, thresh="1.0 mm", window=3, freq="YS", resample_before_rl=True, op="sum", **indexer):
     """indices/_threshold.py:3314-3382 (input in mm/d so that the daily amount equals the rate)."""
     return _dry_wet_spell(pr, thresh.replace(" mm", " mm/d") if isinstance(thresh, str) else thresh, window, "<", op,
-                          "count", freq, resample_before_rl)
+                          "count", freq, resample_before_rl, **indexer)
 
 
-def dry_spell_total_length(pr, thresh="1.0 mm", window=3, op="sum", freq="YS", resample_before_rl=True):
+def dry_spell_total_length(pr, thresh="1.0 mm", window=3, op="sum", freq="YS", resample_before_rl=True, **indexer):
     """indices/_threshold.py:3385-3454."""
     return _dry_wet_spell(pr, thresh.replace(" mm", " mm/d") if isinstance(thresh, str) else thresh, window, "<", op,
-                          "sum", freq, resample_before_rl)
+                          "sum", freq, resample_before_rl, **indexer)
 
 
-def dry_spell_max_length(pr, thresh="1.0 mm", window=1, op="sum", freq="YS", resample_before_rl=True):
+def dry_spell_max_length(pr, thresh="1.0 mm", window=1, op="sum", freq="YS", resample_before_rl=True, **indexer):
     """indices/_threshold.py:3457-3522."""
     return _dry_wet_spell(pr, thresh.replace(" mm", " mm/d") if isinstance(thresh, str) else thresh, window, "<", op,
-                          "max", freq, resample_before_rl)
+                          "max", freq, resample_before_rl, **indexer)
 
 
-def wet_spell_frequency(pr, thresh="1.0 mm", window=3, freq="YS", resample_before_rl=True, op="sum"):
+def wet_spell_frequency(pr, thresh="1.0 mm", window=3, freq="YS", resample_before_rl=True, op="sum", **indexer):
     """indices/_threshold.py:3525-3592."""
     return _dry_wet_spell(pr, thresh.replace(" mm", " mm/d") if isinstance(thresh, str) else thresh, window, ">=", op,
-                          "count", freq, resample_before_rl)
+                          "count", freq, resample_before_rl, **indexer)
 
 
-def wet_spell_total_length(pr, thresh="1.0 mm", window=3, op="sum", freq="YS", resample_before_rl=True):
+def wet_spell_total_length(pr, thresh="1.0 mm", window=3, op="sum", freq="YS", resample_before_rl=True, **indexer):
     """indices/_threshold.py:3596-3663."""
     return _dry_wet_spell(pr, thresh.replace(" mm", " mm/d") if isinstance(thresh, str) else thresh, window, ">=", op,
-                          "sum", freq, resample_before_rl)
+                          "sum", freq, resample_before_rl, **indexer)
 
 
-def wet_spell_max_length(pr, thresh="1.0 mm", window=1, op="sum", freq="YS", resample_before_rl=True):
+def wet_spell_max_length(pr, thresh="1.0 mm", window=1, op="sum", freq="YS", resample_before_rl=True, **indexer):
     """indices/_threshold.py:3667-3733."""
     return _dry_wet_spell(pr, thresh.replace(" mm", " mm/d") if isinstance(thresh, str) else thresh, window, ">=", op,
-                          "max", freq, resample_before_rl)
+                          "max", freq, resample_before_rl, **indexer)
 
 
 def hot_spell_max_magnitude(tasmax, thresh="25.0 degC", window=3, freq="YS", resample_before_rl=True):
@@ -744,7 +746,7 @@ BATCH_FUSED = {
     "heat_wave_index": ("spell", "sum"), "frost_free_spell_max_length": ("maxlen",),
     "maximum_consecutive_frost_days": ("maxlen", "<"), "maximum_consecutive_frost_free_days": ("maxlen", ">="),
     "maximum_consecutive_tx_days": ("maxlen", ">"),
-    "maximum_consecutive_dry_days": ("maxlen", "op"), "maximum_consecutive_wet_days": ("maxlen", ">="),
+    "maximum_consecutive_dry_days": ("maxlen", "op"), "maximum_consecutive_wet_days": ("maxlen", "op"),
     "dry_spell_frequency": None, "dry_spell_total_length": None, "dry_spell_max_length": ("maxlen", "<"),
     "wet_spell_frequency": None, "tx90p": None, "tx10p": None, "tn90p": None,
 }

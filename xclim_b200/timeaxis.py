@@ -141,6 +141,13 @@ class TimeAxis:
             return slice(0, 0)
         return slice(int(idx[0]), int(idx[-1]) + 1)
 
+    def sel_dates(self, first: str, last: str) -> slice:
+        """``time.sel(time=slice(first, last))`` for "YYYY-MM-DD" bounds (both inclusive), as an index slice."""
+        key = self.year.astype(np.int64) * 10000 + self.month * 100 + self.day
+        f = int(first[:4]) * 10000 + int(first[5:7]) * 100 + int(first[8:10])
+        la = int(last[:4]) * 10000 + int(last[5:7]) * 100 + int(last[8:10])
+        return slice(int(np.searchsorted(key, f, side="left")), int(np.searchsorted(key, la, side="right")))
+
     def date_strings(self, idx) -> list[str]:
         idx = np.atleast_1d(idx)
         return [f"{int(self.year[i]):04d}-{int(self.month[i]):02d}-{int(self.day[i]):02d}" for i in idx]
