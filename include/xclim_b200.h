@@ -448,6 +448,9 @@ int32_t xc_table_cell_major_f64(const double* table, int32_t n_per, int32_t n_do
  * without staging; pageable memory is accepted.  to_device != 0: host -> device, else device -> host. */
 int32_t xc_copy_box_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
                           int64_t width_bytes, int64_t height, int32_t to_device, void* stream);
+/* 1 when host_ptr lies in page-locked (pinned / registered) host memory, 0 otherwise (pageable memory,
+ * memory-mapped files: the slab streamer stages those through its own pinned buffers). */
+int32_t xc_host_pinned(const void* host_ptr);
 
 #ifdef __cplusplus
 }

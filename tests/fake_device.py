@@ -230,6 +230,10 @@ def period_run_quantile(x2d, poff, op_code, thr, q, window, resample_before_rl=T
     return torch.from_numpy(np.asarray(out, dtype=np.float32))
 
 
+def transpose_f64(m):
+    return m.t().contiguous()
+
+
 def table_cell_major(table):
     return table.permute(2, 1, 0).contiguous()
 
@@ -319,7 +323,7 @@ def dev_ints(arr, dtype, device):
 FUNCTIONS = [to_time_cell, period_count, period_runstat, period_runstat_gap, period_reduce, rolling_period_reduce,
              spell_runstat, period_run_maxsum, period_runstat2, percentile_doy, doy_interp, doy_threshold_count,
              mask_steps, dev_ints, period_boundary_run, period_boundary_run_range, bootstrap_doy_count, eqm_train,
-             eqm_adjust, period_run_quantile, table_cell_major, period_multi, period_count_arr, spell_mask]
+             eqm_adjust, period_run_quantile, table_cell_major, period_multi, period_count_arr, spell_mask, transpose_f64]
 
 
 def install(monkeypatch):

@@ -78,3 +78,30 @@ def test_plan_slabs_covers_every_row():
             pl = streaming.plan_slabs(n, 10 ** 5, slab)
             assert pl[0][0] == 0 and pl[-1][1] == n and all(a[1] == b[0] for a, b in zip(pl, pl[1:]))
             assert all(b > a for a, b in pl)
+
+
+def test_memory_mapped_file_in_file_out(cuda, tmp_path):
+    """SURVEY.md 8f.3: .npy on disk -> memory map -> reader thread -> pinned slabs -> kernels -> .npy on disk;
+    the result equals the in-memory call."""
+    import xclim_b200
+    from xclim_b200 import atmos, indices, io
+    rng = np.random.default_rng(73)
+    tas, pr = _inputs(rng, T=365 * 3, shape=(11, 16))
+    f_pr = make_field(pr, "1981-01-01", calendar="noleap", units="mm/d", dims=("time", "lat", "lon"))
+    path = str(tmp_path / "pr.npy")
+    io.save_npy(path, f_pr)
+    lazy = io.open_npy(path)
+    assert isinstance(lazy.values, np.memmap) and lazy.dims == ("time", "lat", "lon") and lazy.attrs["units"] == "mm/d"
+    assert lazy.time.calendar == "noleap" and len(lazy.time) == pr.shape[0]
+    ref = atmos.maximum_consecutive_dry_days(f_pr).values
+    row = pr.shape[0] * pr.shape[2] * 4
+    with xclim_b200.set_options(stream_min_bytes=0, stream_slab_bytes=2 * row):     # 11 rows -> 6 slabs
+        out = atmos.maximum_consecutive_dry_days(lazy)
+        wet = indices.wetdays(lazy)
+    np.testing.assert_array_equal(out.values, ref)
+    np.testing.assert_array_equal(wet.values, indices.wetdays(f_pr).values)
+    out_path = str(tmp_path / "cdd.npy")
+    io.save_npy(out_path, out)
+    back = io.open_npy(out_path, mmap=False)
+    np.testing.assert_array_equal(back.values, ref)
+    assert back.attrs["units"] == "days" and back.dims == ("time", "lat", "lon")

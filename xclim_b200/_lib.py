@@ -65,6 +65,7 @@ SIGNATURES = {
     "xc_period_count_arr_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _i32, _vp, _i64, _vp, _vp]),
     "xc_period_multi_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _vp, _vp, _i32, _vp]),
     "xc_table_cell_major_f64": (_i32, [_vp, _i32, _i32, _i64, _vp, _vp]),
+    "xc_host_pinned": (_i32, [_vp]),
     "xc_copy_box_async": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp]),
     "xc_period_runstat_f32_host": (_i32, [_vp, _i64, _i64, _vp, _i32, _i32, _f64, _i32, _i32, _i32, _vp, _vp,
                                           _vp, _i64]),

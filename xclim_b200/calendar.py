@@ -146,8 +146,17 @@ def table_on_device(per_da, cell_shape, other_dims, dev):
         if tuple(t.shape[1:]) != tuple(cell_shape):
             raise ValueError(f"percentile array shape {tuple(t.shape[1:])} does not match the data grid {cell_shape}")
         return t.reshape(t.shape[0], -1).contiguous()
-    a = np.moveaxis(np.asarray(vals, dtype=np.float64), dims.index("dayofyear"), 0)
     space = tuple(d for d in dims if d != "dayofyear")
+    h = np.asarray(vals, dtype=np.float64)
+    if dims[-1] == "dayofyear" and space == tuple(other_dims) and h.flags.c_contiguous:
+        # the reference layout (*space, dayofyear): upload as it lies and transpose in HBM (a host-side
+        # transpose of the 3 GB full-grid table costs seconds)
+        if tuple(h.shape[:-1]) != tuple(cell_shape):
+            raise ValueError(f"percentile array shape {h.shape[:-1]} does not match the data grid {cell_shape}")
+        n_doy = h.shape[-1]
+        t = torch.from_numpy(h.reshape(-1, n_doy)).to(dev)           # (C, n_doy)
+        return device.transpose_f64(t)                                # (n_doy, C)
+    a = np.moveaxis(h, dims.index("dayofyear"), 0)
     if space != tuple(other_dims):
         a = np.transpose(a, (0,) + tuple(1 + space.index(d) for d in other_dims))
     if tuple(a.shape[1:]) != tuple(cell_shape):

@@ -131,3 +131,13 @@ extern "C" int32_t xc_copy_box_async(void* dst, int64_t dst_pitch, const void* s
   }
   return XC_OK;
 }
+
+extern "C" int32_t xc_host_pinned(const void* host_ptr) {
+  if (host_ptr == nullptr) return 0;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host_ptr) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return a.type == cudaMemoryTypeHost ? 1 : 0;
+}

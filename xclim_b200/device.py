@@ -186,6 +186,15 @@ def table_cell_major(table):
     return out
 
 
+def transpose_f64(m):
+    """(A, B) float64 -> (B, A), tiled in shared memory (the layout kernel of table_cell_major with n_per = 1)."""
+    A, B = m.shape
+    assert m.dtype == torch.float64 and m.is_contiguous()
+    out = torch.empty((B, A), dtype=torch.float64, device=m.device)
+    check(load().xc_table_cell_major_f64(m.data_ptr(), 1, A, B, out.data_ptr(), current_stream_ptr()))
+    return out
+
+
 def doy_interp(table2d, doy_min, doy_max):
     """core/calendar.py:690-726 on a (n_src, C) float64 device table."""
     n_src, C = table2d.shape

@@ -134,17 +134,48 @@ def run_streamed(fn, args, kwargs, lead, shape, series, tables):
     bufs = {k: [torch.empty(T * rows_max * rest, dtype=torch.float32, device="cuda") for _ in range(2)] for k in keys}
     copied = [torch.cuda.Event() for _ in range(2)]
     done = [torch.cuda.Event() for _ in range(2)]
+    # Inputs that are not page-locked (plain numpy arrays, memory-mapped files: the I/O step of SURVEY.md 8f.3)
+    # are staged by a reader thread: slab k+2 is gathered from the file / pageable memory into a pinned buffer
+    # while slab k+1 crosses PCIe and slab k is computed, so disk, PCIe and kernels overlap.
+    staged = {k: not lib.xc_host_pinned(hosts[k].ctypes.data) for k in keys}
+    stage_bufs, pool, futures = {}, None, {}
+    if any(staged.values()):
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max_workers=1)
+        for key in keys:
+            if staged[key]:
+                stage_bufs[key] = [_pinned(f"in{len(stage_bufs)}_{i}", T * rows_max * rest * 4) for i in range(2)]
+
+    def stage(k):
+        r0, r1 = slabs[k]
+        b = k & 1
+        if k >= 2:
+            copied[b].synchronize()               # the H2D copy of slab k-2 has drained this staging buffer
+        for key in keys:
+            if staged[key]:
+                dst = stage_bufs[key][b][: T * (r1 - r0) * rest * 4].numpy().view(np.float32)
+                np.copyto(dst.reshape((T, r1 - r0) + tuple(shape[2:])), hosts[key][:, r0:r1])
+
+    def submit_stage(k):
+        if pool is not None and k < len(slabs):
+            futures[k] = pool.submit(stage, k)
 
     def issue_copy(k):
         r0, r1 = slabs[k]
         b = k & 1
+        if k in futures:
+            futures.pop(k).result()
         if k >= 2:
             s_copy.wait_event(done[b])            # the kernels of slab k-2 have released the buffer
         w = (r1 - r0) * rest * 4
         for key in keys:
-            h = hosts[key]
-            check(lib.xc_copy_box_async(bufs[key][b].data_ptr(), w, h.ctypes.data + r0 * rest * 4, n_lead * rest * 4,
-                                        w, T, 1, s_copy.cuda_stream))
+            if staged[key]:
+                check(lib.xc_copy_box_async(bufs[key][b].data_ptr(), w, stage_bufs[key][b].data_ptr(), w, w, T, 1,
+                                            s_copy.cuda_stream))
+            else:
+                h = hosts[key]
+                check(lib.xc_copy_box_async(bufs[key][b].data_ptr(), w, h.ctypes.data + r0 * rest * 4,
+                                            n_lead * rest * 4, w, T, 1, s_copy.cuda_stream))
         copied[b].record(s_copy)
 
     out_host = None
@@ -152,12 +183,15 @@ def run_streamed(fn, args, kwargs, lead, shape, series, tables):
     template = next(iter(series.values()))
     result_meta = None
     keep = []                                     # device results stay alive until their D2H has run
+    submit_stage(0)
+    submit_stage(1)
     issue_copy(0)
     with set_options(device_outputs=True):
         for k, (r0, r1) in enumerate(slabs):
             b = k & 1
             if k + 1 < len(slabs):
                 issue_copy(k + 1)                 # prefetch before the (possibly synchronising) index call
+            submit_stage(k + 2)
             comp.wait_event(copied[b])
             a2, k2 = list(args), dict(kwargs)
             for key in keys:
@@ -186,10 +220,17 @@ def run_streamed(fn, args, kwargs, lead, shape, series, tables):
                 vshape = tuple(vals.shape)
                 full = vshape[:out_axis] + (n_lead,) + vshape[out_axis + 1:]
                 np_dtype = np.dtype(str(vals.dtype).replace("torch.", "")) if hasattr(vals, "is_cuda") else vals.dtype
-                out_host = np.empty(full, dtype=np_dtype)
+                nbytes = int(np.prod(full, dtype=np.int64)) * np_dtype.itemsize
                 result_meta = res
-                stage = _pinned("out", out_host.nbytes)
-                stage_np = stage[: out_host.nbytes].numpy().view(np_dtype).reshape(full)
+                if nbytes >= (256 << 20):
+                    # large results (percentile tables): the result array itself is page-locked, the slabs
+                    # land in it directly (numpy keeps the torch storage alive through the buffer protocol)
+                    own = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+                    out_host = stage_np = own.numpy().view(np_dtype).reshape(full)
+                else:
+                    out_host = np.empty(full, dtype=np_dtype)
+                    stage = _pinned("out", nbytes)
+                    stage_np = stage[:nbytes].numpy().view(np_dtype).reshape(full)
             A = int(np.prod(out_host.shape[:out_axis], dtype=np.int64))
             B = int(np.prod(out_host.shape[out_axis + 1:], dtype=np.int64)) * out_host.itemsize
             if hasattr(vals, "is_cuda") and vals.is_cuda:
@@ -206,7 +247,10 @@ def run_streamed(fn, args, kwargs, lead, shape, series, tables):
     s_out.synchronize()
     comp.synchronize()
     s_copy.synchronize()
-    np.copyto(out_host, stage_np)
+    if pool is not None:
+        pool.shutdown(wait=True)
+    if out_host is not stage_np:
+        np.copyto(out_host, stage_np)
     del keep
     return _assemble(template, result_meta, out_host, lead)
 
