@@ -146,7 +146,7 @@ def run_streamed(fn, args, kwargs, lead, shape, series, tables):
             if staged[key]:
                 stage_bufs[key] = [_pinned(f"in{len(stage_bufs)}_{i}", T * rows_max * rest * 4) for i in range(2)]
 
-    def stage(k):
+    def fill_stage(k):
         r0, r1 = slabs[k]
         b = k & 1
         if k >= 2:
@@ -158,7 +158,7 @@ def run_streamed(fn, args, kwargs, lead, shape, series, tables):
 
     def submit_stage(k):
         if pool is not None and k < len(slabs):
-            futures[k] = pool.submit(stage, k)
+            futures[k] = pool.submit(fill_stage, k)
 
     def issue_copy(k):
         r0, r1 = slabs[k]
@@ -229,8 +229,8 @@ def run_streamed(fn, args, kwargs, lead, shape, series, tables):
                     out_host = stage_np = own.numpy().view(np_dtype).reshape(full)
                 else:
                     out_host = np.empty(full, dtype=np_dtype)
-                    stage = _pinned("out", nbytes)
-                    stage_np = stage[:nbytes].numpy().view(np_dtype).reshape(full)
+                    out_stage = _pinned("out", nbytes)
+                    stage_np = out_stage[:nbytes].numpy().view(np_dtype).reshape(full)
             A = int(np.prod(out_host.shape[:out_axis], dtype=np.int64))
             B = int(np.prod(out_host.shape[out_axis + 1:], dtype=np.int64)) * out_host.itemsize
             if hasattr(vals, "is_cuda") and vals.is_cuda:
