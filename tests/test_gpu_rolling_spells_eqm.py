@@ -191,12 +191,17 @@ def test_eqm_train_eight_cell_kernel_matches_one_cell_kernel(cuda, monkeypatch):
     ref[:, 20] = pr                                  # heavy constant bin (dry days)
     rd, hd = torch.from_numpy(ref).cuda(), torch.from_numpy(hist).cuda()
     monkeypatch.delenv("XCLIM_B200_EQM_V1", raising=False)
-    af, hq = device.eqm_train(rd, hd, 20, 0)
+    monkeypatch.delenv("XCLIM_B200_EQM_STAGE", raising=False)
+    af, hq = device.eqm_train(rd, hd, 20, 0)                 # 16 cells per CTA, three sweeps over global memory
+    monkeypatch.setenv("XCLIM_B200_EQM_STAGE", "1")
+    af2, hq2 = device.eqm_train(rd, hd, 20, 0)               # 4 cells per CTA, slice staged in shared memory
+    monkeypatch.delenv("XCLIM_B200_EQM_STAGE", raising=False)
     monkeypatch.setenv("XCLIM_B200_EQM_V1", "1")
-    af1, hq1 = device.eqm_train(rd, hd, 20, 0)
+    af1, hq1 = device.eqm_train(rd, hd, 20, 0)               # one cell per CTA
     torch.cuda.synchronize()
-    assert torch.equal(torch.nan_to_num(af, nan=-7.0), torch.nan_to_num(af1, nan=-7.0))
-    assert torch.equal(torch.nan_to_num(hq, nan=-7.0), torch.nan_to_num(hq1, nan=-7.0))
+    for a_, h_ in ((af2, hq2), (af1, hq1)):
+        assert torch.equal(torch.nan_to_num(af, nan=-7.0), torch.nan_to_num(a_, nan=-7.0))
+        assert torch.equal(torch.nan_to_num(hq, nan=-7.0), torch.nan_to_num(h_, nan=-7.0))
     af_o, hq_o = O.eqm_train(ref, hist, 20, "+")
     np.testing.assert_allclose(hq.cpu().numpy(), hq_o, rtol=1e-5, atol=1e-7, equal_nan=True)
     np.testing.assert_allclose(af.cpu().numpy(), af_o, rtol=1e-4, atol=1e-5, equal_nan=True)

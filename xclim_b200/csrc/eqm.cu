@@ -270,12 +270,15 @@ eqm_train_kernel(const float* __restrict__ ref, const float* __restrict__ hist, 
 // with the one-cell kernel's full machinery (sort fallback included): the results are those of
 // eqm_train_kernel bit for bit.
 // ------------------------------------------------------------------------------------------------
-#ifndef XC_EQM_GROUP
-#define XC_EQM_GROUP 16
-#endif
-constexpr int kG = XC_EQM_GROUP;   // cells per CTA: 16 = one 64-byte DRAM fetch pair per time row (8 = one sector)
-constexpr int kGT = 32 * kG;       // threads: one warp per cell for the scans, 128 time rows x kG / 4 loads in flight
-constexpr int kSub = kG / 4;       // threads (128-bit loads) per time row
+// Two instantiations (template <cells per CTA, threads, slice staged in shared memory>):
+//   <16, 512, false>  DEFAULT: 16 cells per CTA (whole 64-byte fetch pairs), three sweeps over global memory
+//                     (full grid: 150 ms, 252 GB of DRAM reads for 91 GB of input -- the 700 KB slice does not
+//                     survive in L2 between the sweeps).
+//   <4, 1024, true>   the CTA's slice (4 cells x T x 4 bytes = 175 KB for 30 years of days) is written to shared
+//                     memory by the first sweep and the two other sweeps read it there: DRAM traffic = the
+//                     algorithmic 2 T C 4 bytes, yet SLOWER (203 ms): 16 bytes per row and CTA mean four times
+//                     the (CTA, row) touches, each in another DRAM / TLB page.  XCLIM_B200_EQM_STAGE=1 selects it.
+constexpr int kStageMaxT = 11264;  // 4 cells x 11264 steps x 4 bytes = 176 KB of the 227 KB
 constexpr int kPool = 1024;        // candidate floats per cell
 constexpr int kHeavy = 192;        // bins above this must be constant
 
@@ -286,20 +289,25 @@ __device__ __forceinline__ int float_key(float v) {   // order-preserving int ke
 __device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : (k ^ 0x7fffffff)); }
 
 // dynamic shared memory of eqm_train8_kernel for ntg = 2 * nq targets per cell
-__host__ __device__ inline size_t train8_smem_bytes(int ntg) {
-  return (size_t)kG * (kBins / 2) * 4      // packed 16-bit histogram, then exclusive prefix sums
+__host__ __device__ inline size_t train8_smem_bytes(int kG, int ntg, int64_t stage_rows) {
+  return (size_t)stage_rows * kG * 4       // the staged slice [T][kG] (0 rows when not staged)
+         + (size_t)kG * (kBins / 2) * 4    // packed 16-bit histogram, then exclusive prefix sums
          + (size_t)kG * kPool * 4          // candidate pool
          + (size_t)kG * kBins * 2          // bin -> slot
          + (size_t)kG * ntg * (4 * 8);     // tgt_rank, tgt_bin, tgt_val, slot_bin, slot_off, slot_n, slot_min / max (2)
 }
 
-__global__ void __launch_bounds__(kGT, (kG == 8 ? 3 : 1))
+template <int kG, int kGT, bool STAGE>
+__global__ void __launch_bounds__(kGT, 1)
 eqm_train8_kernel(const float* __restrict__ ref, const float* __restrict__ hist, int32_t T, int64_t C, int64_t ldx,
                   int32_t nq, int32_t kind, float* __restrict__ af, float* __restrict__ hist_q,
                   int32_t* __restrict__ redo /* [0] = count, then cell indexes */) {
   extern __shared__ __align__(16) unsigned char sm8[];
   const int ntg = 2 * nq;
-  uint32_t* h32 = reinterpret_cast<uint32_t*>(sm8);                          // [kG][kBins / 2]
+  constexpr int kSub = kG / 4;       // threads (128-bit loads) per time row
+  static_assert(kG % 4 == 0 && kGT % 32 == 0 && kGT / 32 >= kG, "one warp per cell for the scans");
+  float4* keys4 = reinterpret_cast<float4*>(sm8);                             // [T][kSub] staged slice (STAGE only)
+  uint32_t* h32 = reinterpret_cast<uint32_t*>(sm8 + (STAGE ? (size_t)T * kG * 4 : 0));   // [kG][kBins / 2]
   float* pool = reinterpret_cast<float*>(h32 + kG * (kBins / 2));            // [kG][kPool]
   unsigned short* slot_of_bin = reinterpret_cast<unsigned short*>(pool + kG * kPool);   // [kG][kBins]
   int* tgt_rank = reinterpret_cast<int*>(slot_of_bin + kG * kBins);          // [kG][ntg]
@@ -339,6 +347,7 @@ eqm_train8_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
         for (int u = 0; u < kU; ++u) v[u] = ld_stream4(src + (int64_t)(t + u * kRows) * ldx);
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
+          if constexpr (STAGE) keys4[(size_t)(t + u * kRows) * kSub + half] = v[u];
           const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
           for (int i = 0; i < 4; ++i)
@@ -347,6 +356,7 @@ eqm_train8_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
       }
       for (; t < T; t += kRows) {
         const float4 v = ld_stream4(src + (int64_t)t * ldx);
+        if constexpr (STAGE) keys4[(size_t)t * kSub + half] = v;
         const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -397,18 +407,22 @@ eqm_train8_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
           }
         }
       };
-      int t = trow;
-      for (; t + (kU - 1) * kRows < T; t += kU * kRows) {
-        float4 v[kU];
+      if constexpr (STAGE) {
+        for (int t = trow; t < T; t += kRows) tally(keys4[(size_t)t * kSub + half]);
+      } else {
+        int t = trow;
+        for (; t + (kU - 1) * kRows < T; t += kU * kRows) {
+          float4 v[kU];
 #pragma unroll
-        for (int u = 0; u < kU; ++u) v[u] = ld_stream4(src + (int64_t)(t + u * kRows) * ldx);
+          for (int u = 0; u < kU; ++u) v[u] = ld_stream4(src + (int64_t)(t + u * kRows) * ldx);
 #pragma unroll
-        for (int u = 0; u < kU; ++u) tally(v[u]);
+          for (int u = 0; u < kU; ++u) tally(v[u]);
+        }
+        for (; t < T; t += kRows) tally(ld_stream4(src + (int64_t)t * ldx));
       }
-      for (; t < T; t += kRows) tally(ld_stream4(src + (int64_t)t * ldx));
     }
     __syncthreads();
-    {  // in-place exclusive scan of the kBins counters of cell `wid` by warp `wid` (kGT / 32 == kG)
+    if (wid < kG) {  // in-place exclusive scan of the kBins counters of cell `wid` by warp `wid`
       constexpr int per = kBins / 32;
       uint32_t* hc = h32 + wid * (kBins / 2) + lane * (per / 2);
       int loc[per], sum = 0;
@@ -499,15 +513,19 @@ eqm_train8_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
           }
         }
       };
-      int t = trow;
-      for (; t + (kU - 1) * kRows < T; t += kU * kRows) {
-        float4 v[kU];
+      if constexpr (STAGE) {
+        for (int t = trow; t < T; t += kRows) gather(keys4[(size_t)t * kSub + half]);
+      } else {
+        int t = trow;
+        for (; t + (kU - 1) * kRows < T; t += kU * kRows) {
+          float4 v[kU];
 #pragma unroll
-        for (int u = 0; u < kU; ++u) v[u] = ld_stream4(src + (int64_t)(t + u * kRows) * ldx);
+          for (int u = 0; u < kU; ++u) v[u] = ld_stream4(src + (int64_t)(t + u * kRows) * ldx);
 #pragma unroll
-        for (int u = 0; u < kU; ++u) gather(v[u]);
+          for (int u = 0; u < kU; ++u) gather(v[u]);
+        }
+        for (; t < T; t += kRows) gather(ld_stream4(src + (int64_t)t * ldx));
       }
-      for (; t < T; t += kRows) gather(ld_stream4(src + (int64_t)t * ldx));
     }
     __syncthreads();
     // ---- heavy bins must be constant
@@ -738,18 +756,32 @@ extern "C" int32_t xc_eqm_train_f32(const float* ref, const float* hist, int64_t
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t need = xc_eqm_train_workspace_bytes(T, C, nq);
-  const bool vec_ok = (C % kG == 0) && (ldx % 4 == 0) && aligned16(ref) && aligned16(hist);
+  // the staged variant is a measured NEGATIVE result (full grid 203 ms vs 150 ms): what costs is the number of
+  // (CTA, time row) touches -- every row of a CTA's slice lies in another DRAM / TLB page at a 4 MB row stride --
+  // and 4 cells per CTA touch 4x as many rows per byte; it stays selectable for the record
+  const bool staged = T <= kStageMaxT && getenv("XCLIM_B200_EQM_STAGE") != nullptr;
+  const int g = staged ? 4 : 16;
+  const bool vec_ok = (C % g == 0) && (ldx % 4 == 0) && aligned16(ref) && aligned16(hist);
   if (workspace == nullptr || workspace_bytes < need || !vec_ok || getenv("XCLIM_B200_EQM_V1")) {
-    // no scratch for a redo list, or a layout without whole 32-byte sectors per CTA: the one-cell-per-CTA
+    // no scratch for a redo list, or a layout without whole 16-byte pieces per CTA: the one-cell-per-CTA
     // kernel (complete in itself)
     return launch_train_cells(ref, hist, T, C, ldx, nq, kind, af, hist_q, nullptr, (unsigned)C, st);
   }
   int32_t* redo = (int32_t*)workspace;
   XC_CHECK_CUDA(cudaMemsetAsync(redo, 0, 4, st));
-  const size_t smem8 = train8_smem_bytes(2 * nq);
-  XC_CHECK_CUDA(cudaFuncSetAttribute(eqm_train8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-  const int64_t groups = (C + kG - 1) / kG;
-  eqm_train8_kernel<<<(unsigned)groups, kGT, smem8, st>>>(ref, hist, (int32_t)T, C, ldx, nq, kind, af, hist_q, redo);
+  const size_t smem8 = train8_smem_bytes(g, 2 * nq, staged ? T : 0);
+  const int64_t groups = C / g;
+  if (staged) {
+    XC_CHECK_CUDA(cudaFuncSetAttribute(eqm_train8_kernel<4, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem8));
+    eqm_train8_kernel<4, 1024, true><<<(unsigned)groups, 1024, smem8, st>>>(ref, hist, (int32_t)T, C, ldx, nq, kind, af,
+                                                                             hist_q, redo);
+  } else {
+    XC_CHECK_CUDA(cudaFuncSetAttribute(eqm_train8_kernel<16, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem8));
+    eqm_train8_kernel<16, 512, false><<<(unsigned)groups, 512, smem8, st>>>(ref, hist, (int32_t)T, C, ldx, nq, kind, af,
+                                                                             hist_q, redo);
+  }
   int32_t e = launch_status("eqm_train8_kernel");
   if (e) return e;
   // cells the eight-cell layout could not finish (heavy non-constant bins): a small fixed grid walks the list
