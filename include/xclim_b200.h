@@ -307,16 +307,6 @@ int32_t xc_doy_threshold_count_years_f32(const float* x, int64_t T, int64_t C, i
                                          const double* table, int32_t op,
                                          int32_t* out_count, int32_t* valid_count, void* stream);
 
-/* Fused percentile_doy + percentile-threshold count for the case "the percentile base IS the studied
- * series" (tx90p sub-case 3a: core/calendar.py:395-494 followed by indices/_multivariate.py:1583-1590
- * on the same array): uniform calendar (T == n_years * year_len, series starts on doy 1), window 5,
- * yearly periods.  One pass over x produces table (year_len, C) float64 and out_count /
- * valid_count (n_years, C) int32. */
-int32_t xc_percentile_doy_count_f32(const float* x, int64_t T, int64_t C, int64_t ldx, int32_t year_len,
-                                    int32_t n_years, int32_t window, double percentile, double alpha,
-                                    double beta, int32_t op, double* table, int32_t* out_count,
-                                    int32_t* valid_count, void* stream);
-
 /* ---------------------------------------------------------------------------------------------
  * a17  percentile bootstrap (Zhang 2005) -- core/bootstrapping.py:81-211, 235-282
  *   x: (T, C) studied series; the base (climatology) period is the n_base_years equal-length

@@ -167,26 +167,6 @@ def test_doy_count_year_blocked_kernel_exact_ties(cuda, op):
                                   np.stack([(~np.isnan(x[s:e])).sum(0) for s, e in zip(month[:-1], month[1:])]))
 
 
-@pytest.mark.parametrize("per,op", [(90.0, ">"), (90.0, ">="), (10.0, "<")])
-def test_fused_percentile_and_count(cuda, per, op):
-    """tx90p sub-case 3a in one pass: identical table and counts to the two separate kernels / the oracle."""
-    import torch
-    from xclim_b200 import device, _lib
-    rng = np.random.default_rng(16)
-    L, N, C = 365, 9, 96
-    x = _tas(rng, L * N, (C,), nan_frac=0.01)
-    x[:, 0] = np.round(x[:, 0])
-    xd = torch.from_numpy(x).cuda()
-    doy = np.tile(np.arange(1, L + 1), N).astype(np.int16)
-    yidx = np.repeat(np.arange(N), L).astype(np.int16)
-    poff = np.arange(N + 1, dtype=np.int32) * L
-    table, cnt, valid = device.percentile_doy_count(xd, L, N, 5, per, 1 / 3, 1 / 3, _lib.OPS[op], want_valid=True)
-    tab_o = O.percentile_doy(x, yidx.astype(int), doy.astype(int), 5, per)[:, 0]
-    np.testing.assert_array_equal(table.cpu().numpy(), tab_o)
-    np.testing.assert_array_equal(cnt.cpu().numpy(), O.doy_threshold_count(x, tab_o, doy.astype(int), poff, op))
-    np.testing.assert_array_equal(valid.cpu().numpy(), np.stack([(~np.isnan(x[s:e])).sum(0) for s, e in zip(poff[:-1], poff[1:])]))
-
-
 @pytest.mark.parametrize("calendar,years,window", [("noleap", 30, 5), ("standard", 20, 9), ("360_day", 40, 5)])
 def test_percentile_doy_mid_percentiles_selection_kernel(cuda, calendar, years, window):
     """Percentiles whose order statistics are more than 64 ranks from both ends of the sample (the

@@ -496,137 +496,11 @@ __device__ __forceinline__ float fold_thr(double t) {
 }
 
 
-// Window 5 specialisation: adjacent day lists are merged in PAIRS, A(e) = Y(e-1) U Y(e), which are
-// reused by two different days:  S(d) = A(d-1) U A(d+1) U Y(d+2).  Per day: one pair merge, one
-// merge of two stored pairs and one final merge -- and when no NaN is present in the lane's sample
-// (warp-uniform test) the final merge only extracts the two order statistics the quantile needs
-// (the two smallest of the top-K) instead of sorting: 16 min/max instead of 80 + two select chains.
-// Ring in shared memory: 3 pair lists per lane, [slot][k][lane].
-#ifndef XC_PCTL_MINBLOCKS
-#define XC_PCTL_MINBLOCKS 7
-#endif
 #ifndef XC_PCTL_PAIR_MINBLOCKS   // with the staging buffer 4 CTAs fit an SM (51 KB each): 13.33 ms;
 #define XC_PCTL_PAIR_MINBLOCKS 4  // 6 (80 registers) gives 13.59 ms, no staging 13.65 ms
 #endif
-// COUNT_OP >= 0 fuses the percentile-threshold day count of the SAME series (tx90p with the base period
-// equal to the studied period, sub-case 3a of SURVEY.md section 8d): once P(d) is known the N values
-// of day d (read two iterations earlier, so they come from L2) are compared with it and tallied per
-// year in shared memory; the input is read from HBM once for both results.
-template <int K, bool TABLE, int COUNT_OP = -1>
-__global__ void __launch_bounds__(kThreads, XC_PCTL_MINBLOCKS)
-percentile_doy_w5_kernel(const float* __restrict__ x, int32_t T, int64_t C, int64_t ldx, int32_t L, int32_t N,
-                         QuantSpec spec, int32_t doys_per_chunk, double* __restrict__ out,
-                         const int32_t* __restrict__ pos, int32_t n_doy, int32_t d_begin, int32_t d_end,
-                         int32_t* __restrict__ year_counts = nullptr, int32_t* __restrict__ year_valid = nullptr) {
-  extern __shared__ float smem[];
-  float* ring = smem;                                                   // [3][K][kThreads]
-  int* rcnt = reinterpret_cast<int*>(smem + (size_t)3 * K * kThreads);  // [3][kThreads]
-  unsigned* ycnt = reinterpret_cast<unsigned*>(rcnt + 3 * kThreads);    // [N][kThreads], COUNT_OP >= 0 only
-  const int lane = threadIdx.x;
-  const int64_t c = (int64_t)blockIdx.x * kThreads + lane;
-  if (c >= C) return;
-  const int d0 = d_begin + blockIdx.y * doys_per_chunk;
-  const int d1 = min(d_end, d0 + doys_per_chunk);
-  if (d0 >= d1) return;
-  const bool top = spec.top != 0;
-  const int n_full = 5 * N;
-  if constexpr (COUNT_OP >= 0) {
-    for (int y = 0; y < N; ++y) ycnt[y * kThreads + lane] = 0u;
-  }
-
-  auto store_pair = [&](int slot, const float (&a)[K], int n) {
-#pragma unroll
-    for (int k = 0; k < K; ++k) ring[((size_t)slot * K + k) * kThreads + lane] = a[k];
-    rcnt[slot * kThreads + lane] = n;
-  };
-
-  float yprev[K], ynew[K];
-  int nprev, nnew;
-  // prologue: A(d0-1) -> slot 0, A(d0) -> slot 1, A(d0+1) -> slot 2 ; yprev = Y(d0+1)
-  load_day_list<K, TABLE>(x, c, ldx, T, L, N, d0 - 2, top, yprev, nprev, pos, n_doy);
-  for (int j = 0; j < 3; ++j) {
-    load_day_list<K, TABLE>(x, c, ldx, T, L, N, d0 - 1 + j, top, ynew, nnew, pos, n_doy);
-    merge_top_desc<K>(yprev, ynew);  // yprev <- A(d0-1+j)
-    store_pair(j, yprev, nprev + nnew);
-#pragma unroll
-    for (int k = 0; k < K; ++k) yprev[k] = ynew[k];
-    nprev = nnew;
-  }
-  int s_lo = 0;  // slot of A(d-1); A(d+1) lives in slot (s_lo + 2) % 3
-  for (int d = d0; d < d1; ++d) {
-    load_day_list<K, TABLE>(x, c, ldx, T, L, N, d + 2, top, ynew, nnew, pos, n_doy);
-    const int s_hi = (s_lo + 2 >= 3) ? s_lo - 1 : s_lo + 2;
-    float t[K];
-    {
-      const float* a = ring + (size_t)s_lo * K * kThreads + lane;
-      const float* b = ring + (size_t)s_hi * K * kThreads + lane;
-#pragma unroll
-      for (int k = 0; k < K; ++k) t[k] = fmaxf(a[(size_t)k * kThreads], b[(size_t)(K - 1 - k) * kThreads]);
-      bitonic_finish_desc<K>(t);
-    }
-    const int n = rcnt[s_lo * kThreads + lane] + rcnt[s_hi * kThreads + lane] + nnew;
-    // final merge with Y(d+2): the K largest of the union as a bitonic sequence
-#pragma unroll
-    for (int k = 0; k < K; ++k) t[k] = fmaxf(t[k], ynew[K - 1 - k]);
-    const QuantIdx qi = quant_index(n, spec);
-    const bool in_range = (n >= 2) && (qi.vi < (double)n - 1.0) && (qi.vi >= 0.0);
-    const bool fast = in_range && (top ? (n - 1 - qi.ilo == K - 1) : (qi.ilo + 1 == K - 1));
-    double res;
-    if (__all_sync(__activemask(), fast)) {
-      // the two smallest of t: halve the bitonic sequence keeping the minima
-      float m[K / 2];
-#pragma unroll
-      for (int i = 0; i < K / 2; ++i) m[i] = fminf(t[i], t[i + K / 2]);
-#pragma unroll
-      for (int h = K / 4; h >= 2; h >>= 1) {
-#pragma unroll
-        for (int i = 0; i < h; ++i) m[i] = fminf(m[i], m[i + h]);
-      }
-      const float smallest = fminf(m[0], m[1]), second = fmaxf(m[0], m[1]);
-      res = top ? quant_lerp(smallest, second, qi) : quant_lerp(-second, -smallest, qi);
-    } else {
-      bitonic_finish_desc<K>(t);
-      res = finalize_quantile<K>(t, n, spec);
-    }
-    out[(int64_t)d * C + c] = res;
-    if constexpr (COUNT_OP >= 0) {
-      // low 16 bits: exceedances of year y, high 16 bits: valid days of year y.  P(d) is folded once to
-      // the float32 threshold with the same truth table (directed rounding); 16 rows in flight.
-      const float thr = fold_thr<COUNT_OP>(res);
-      const float* p = x + (int64_t)d * ldx + c;
-      const int64_t ystride = (int64_t)L * ldx;
-      for (int y0 = 0; y0 < N; y0 += 16) {
-        float v[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = (y0 + k < N) ? __ldg(p + (int64_t)(y0 + k) * ystride) : NAN;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          if (y0 + k < N) {
-            unsigned add = cmp<COUNT_OP>(v[k], thr) ? 1u : 0u;
-            add += (v[k] == v[k]) ? 65536u : 0u;
-            ycnt[(y0 + k) * kThreads + lane] += add;
-          }
-        }
-      }
-    }
-    // A(d+2) = Y(d+1) U Y(d+2) replaces A(d-1)
-    merge_top_desc<K>(yprev, ynew);
-    store_pair(s_lo, yprev, nprev + nnew);
-#pragma unroll
-    for (int k = 0; k < K; ++k) yprev[k] = ynew[k];
-    nprev = nnew;
-    s_lo = (s_lo + 1 == 3) ? 0 : s_lo + 1;
-  }
-  (void)n_full;
-  if constexpr (COUNT_OP >= 0) {
-    for (int y = 0; y < N; ++y) {
-      const unsigned v = ycnt[y * kThreads + lane];
-      atomicAdd(year_counts + (int64_t)y * C + c, (int)(v & 0xffffu));
-      if (year_valid) atomicAdd(year_valid + (int64_t)y * C + c, (int)(v >> 16));
-    }
-  }
-}
-
+// (The day-by-day window-5 kernel with the fused per-year count of the same series -- tx90p sub-case 3a in one
+// pass -- was removed in round 2: 38 ms against 10.5 + 7.1 ms for the two-kernel path.)
 // Window 5, days handled in PAIRS.  With B(d) = Y(d-2..d+1) = A(d-1) U A(d+1) the windows of two
 // neighbouring days are one rank-only merge away:  S(d-1) = Y(d-3) U B(d)  and  S(d) = B(d) U Y(d+2).
 // Per pair of days: one pair merge A(d+1), one merge B(d), two rank-only finals (2*80 + 2*32
@@ -1642,55 +1516,5 @@ extern "C" int32_t xc_doy_threshold_count_years_f32(const float* x, int64_t T, i
                                                                          table, out_count, valid_count);
     }
     return launch_status("doy_count_years_kernel");
-  });
-}
-
-// Fused tx90p for the case "the percentile base IS the studied series" (uniform calendar, freq YS):
-// one pass produces the (n_doy, C) float64 table and the (n_years, C) int32 day counts.
-extern "C" int32_t xc_percentile_doy_count_f32(const float* x, int64_t T, int64_t C, int64_t ldx, int32_t year_len,
-                                               int32_t n_years, int32_t window, double percentile, double alpha,
-                                               double beta, int32_t op, double* table, int32_t* out_count,
-                                               int32_t* valid_count, void* stream) {
-  XC_REQUIRE(x && table && out_count, "null pointer argument");
-  XC_REQUIRE(T > 0 && C > 0 && ldx >= C && T == (int64_t)year_len * n_years, "series must be n_years whole years");
-  XC_REQUIRE(op >= XC_OP_GT && op <= XC_OP_LE, "Operation `%d` not permitted for indice.", op);
-  if (window != 5) {
-    set_error("the fused percentile + count kernel exists for window == 5 only");
-    return XC_ERR_UNSUPPORTED;
-  }
-  QuantSpec spec;
-  const int need = plan_quantile(percentile, alpha, beta, n_years * window, &spec);
-  if (need < 0 || need > 16 || year_len < 8) {
-    set_error("the fused percentile + count kernel keeps at most 16 order statistics (needs %d)", need);
-    return XC_ERR_UNSUPPORTED;
-  }
-  cudaStream_t st = (cudaStream_t)stream;
-  XC_CHECK_CUDA(cudaMemsetAsync(out_count, 0, (size_t)n_years * C * 4, st));
-  if (valid_count) XC_CHECK_CUDA(cudaMemsetAsync(valid_count, 0, (size_t)n_years * C * 4, st));
-  const int64_t cblocks = (C + kThreads - 1) / kThreads;
-  int chunks = (int)((148 * 16 + cblocks - 1) / cblocks);
-  chunks = chunks < 1 ? 1 : chunks;
-  int per = (year_len + chunks - 1) / chunks;
-  if (per < 40) per = 40;
-  if (per > year_len) per = year_len;
-  chunks = (year_len + per - 1) / per;
-  const size_t smem = ((size_t)3 * (16 + 1) + (size_t)n_years) * kThreads * 4;
-  if (smem > 200 * 1024) {
-    set_error("too many years (%d) for the fused kernel", n_years);
-    return XC_ERR_UNSUPPORTED;
-  }
-  dim3 grid((unsigned)cblocks, (unsigned)chunks, 1);
-  return dispatch_op(op, [&](auto OPC) -> int32_t {
-    constexpr int OP = decltype(OPC)::value;
-    if constexpr (OP <= XC_OP_LE) {
-      if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(percentile_doy_w5_kernel<16, false, OP>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(percentile_doy_w5_kernel)");
-      }
-      percentile_doy_w5_kernel<16, false, OP><<<grid, kThreads, smem, st>>>(
-          x, (int32_t)T, C, ldx, year_len, n_years, spec, per, table, nullptr, 0, 0, year_len, out_count, valid_count);
-    }
-    return launch_status("percentile_doy_w5_kernel<count>");
   });
 }

@@ -383,18 +383,6 @@ def period_runstat2(x1, x2, poff, op1, thr1, op2, thr2, reducer_code, window, re
     return out
 
 
-def percentile_doy_count(x2d, year_len, n_years, window, percentile, alpha, beta, op_code, want_valid=False):
-    """Fused percentile table + yearly exceedance counts of the same series (tx90p sub-case 3a)."""
-    T, C = x2d.shape
-    table = torch.empty((year_len, C), dtype=torch.float64, device=x2d.device)
-    cnt = torch.empty((n_years, C), dtype=torch.int32, device=x2d.device)
-    valid = torch.empty((n_years, C), dtype=torch.int32, device=x2d.device) if want_valid else None
-    check(load().xc_percentile_doy_count_f32(x2d.data_ptr(), T, C, x2d.stride(0), int(year_len), int(n_years),
-                                             int(window), float(percentile), float(alpha), float(beta), op_code,
-                                             table.data_ptr(), cnt.data_ptr(), _ptr(valid), current_stream_ptr()))
-    return table, cnt, valid
-
-
 def mask_steps(x2d, keep):
     """``select_time`` with drop=False: NaN on the steps where ``keep`` is False (a new buffer)."""
     T, C = x2d.shape

@@ -213,8 +213,11 @@ def spell_length_statistics(data, threshold, window, win_reducer, op, spell_redu
         elif window == 1:
             out, _ = device.period_runstat(x2d, poff, code, thr, _lib.RL_REDUCERS[sr], 1, resample_before_rl)
         else:
-            from .spells import spell_runstat  # rolling-window spell masks
-            out = spell_runstat(x2d, poff, window, win_reducer, code, thr, _lib.RL_REDUCERS[sr], resample_before_rl)
+            # rolling-window spell masks (indices/generic.py:434-585 for window > 1)
+            if win_reducer not in ("min", "max", "sum", "mean"):
+                raise ValueError(f"win_reducer must be one of min, max, sum, mean; got {win_reducer!r}")
+            out = device.spell_runstat(x2d, poff, window, _lib.STATS[win_reducer], code, thr, _lib.RL_REDUCERS[sr],
+                                       resample_before_rl)
         attrs = attrs_of(data)
         attrs["units"] = "" if sr == "count" else "d"
         outs.append(_wrap_periods(data, out, cell_shape, other, ta, freq, attrs, dtype=np.float32))
