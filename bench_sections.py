@@ -249,7 +249,7 @@ def tx90p_sections(ctx, line, want_3a=True, want_3b=True):
             "api": "xclim_b200.calendar.percentile_doy + xclim_b200.indices.tx90p(bootstrap=True), device-resident Fields",
             "value": cells_total / (ms * 1e-3), "unit": "grid-cells/s", "ms_per_step": ms, "ms_bootstrap_kernel": ms_k,
             "steps": bsteps,
-            "roofline": roofline(ctx, alg, ms_k, "bootstrap_kernel<16,16>", [T, ctx.rows, X], bound="compute (min/max pipe); "
+            "roofline": roofline(ctx, alg, ms_k, "bootstrap5_kernel<GT>", [T, ctx.rows, X], bound="compute (min/max pipe); "
                                  "fraction of the HBM roofline reported for reference"),
             "cpu_baseline": {"value": sel_b.size / dt, "unit": "grid-cells/s", "cores": 1, "kind": "port",
                              "sample": f"(10950, {sel_b.size}) cells, literal bootstrap restatement, {dt:.1f} s"},

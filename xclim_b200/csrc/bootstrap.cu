@@ -358,41 +358,53 @@ bootstrap5_kernel(const float* __restrict__ x, int64_t C, int64_t ldx, int64_t b
     return top ? (n - 2 - q.ilo) : q.ilo;
   };
 
-  // prologue: days d0-2 .. d0+1 into raw slots 0..3; day d0+2 in flight
+  // sorted (descending, masked) list of the day in raw slot `rs` -- day e of the calendar year
+  auto sort_day = [&](int e, int rs, float (&v)[KA], int& n) {
+    const int blo = (e >= L) ? 1 : 0;
+    const int bhi = (e < 0) ? N - 1 : N;
+    const float* col = raw + ((size_t)rs * N) * kBT + lane;
+    n = 0;
+#pragma unroll
+    for (int b = 0; b < KA; ++b) {
+      const float r = (b < N) ? col[(size_t)b * kBT] : XC_NEG_INF;
+      const bool ok = (b >= blo) && (b < bhi) && (r == r);
+      n += ok ? 1 : 0;
+      v[b] = ok ? r : XC_NEG_INF;
+    }
+    sort_desc<KA>(v);
+  };
+  // prologue: days d0-2 .. d0+1 into raw slots 0..3 and, sorted, into the four register lists; day d0+2 in flight.
+  // The older day lists live in REGISTERS (64 of them) between days: only the entering day is sorted per
+  // iteration (re-sorting all five from the raw ring cost 18 % of the instructions).
+  float y0[KA], y1[KA], y2[KA], y3[KA];
+  int n0, n1, n2, n3;
   for (int k = 0; k < W - 1; ++k) {
     issue_day(d0 - H + k);
     store_day(k);
   }
+  sort_day(d0 - 2, 0, y0, n0);
+  sort_day(d0 - 1, 1, y1, n1);
+  sort_day(d0, 2, y2, n2);
+  sort_day(d0 + 1, 3, y3, n3);
   issue_day(d0 + H);
   int raw_first = 0;
   for (int d = d0; d < d1; ++d) {
     store_day((raw_first + W - 1) % W);
     if (d + 1 < d1) issue_day(d + 1 + H);
-    // ---- sorted extremes of the base sample S(d): the five day lists are sorted from the raw ring (N <= 16)
-    float tl[KA];
-    int nbase = 0;
-#pragma unroll 1
-    for (int k = 0; k < W; ++k) {
-      const int e = d - H + k;
-      const int blo = (e >= L) ? 1 : 0;
-      const int bhi = (e < 0) ? N - 1 : N;
-      const float* col = raw + ((size_t)((raw_first + k) % W) * N) * kBT + lane;
-      float v[KA];
+    // ---- sorted extremes of the base sample S(d): four kept day lists + the entering one
+    float tl[KA], ynew[KA];
+    int nnew;
+    sort_day(d + H, (raw_first + W - 1) % W, ynew, nnew);
 #pragma unroll
-      for (int b = 0; b < KA; ++b) {
-        const float r = (b < N) ? col[(size_t)b * kBT] : XC_NEG_INF;
-        const bool ok = (b >= blo) && (b < bhi) && (r == r);
-        nbase += ok ? 1 : 0;
-        v[b] = ok ? r : XC_NEG_INF;
-      }
-      sort_desc<KA>(v);
-      if (k == 0) {
+    for (int b = 0; b < KA; ++b) tl[b] = y0[b];
+    merge_top_desc<KA>(tl, y1);
+    merge_top_desc<KA>(tl, y2);
+    merge_top_desc<KA>(tl, y3);
+    merge_top_desc<KA>(tl, ynew);
+    const int nbase = n0 + n1 + n2 + n3 + nnew;
 #pragma unroll
-        for (int b = 0; b < KA; ++b) tl[b] = v[b];
-      } else {
-        merge_top_desc<KA>(tl, v);
-      }
-    }
+    for (int b = 0; b < KA; ++b) { y0[b] = y1[b]; y1[b] = y2[b]; y2[b] = y3[b]; y3[b] = ynew[b]; }
+    n0 = n1; n1 = n2; n2 = n3; n3 = nnew;
     const bool interior = (d >= H) && (d + H < L);   // the window stays inside the year: every position valid
     // ---- day constants: list ranks of the interpolated order statistics over every possible count
     // na in [nbase - W, nbase] of A_y (k1 is non-decreasing in n), cf. the per-year test below
