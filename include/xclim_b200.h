@@ -215,6 +215,14 @@ int32_t xc_spell_runstat_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
                              int32_t window, int32_t window_stat, int32_t op, double thr,
                              int32_t reducer, int32_t resample_before_rl, float* out, void* stream);
 
+/* The same with `select_time` applied to the ROLLED series -- indices/generic.py:169-174
+ * (`select_resample_op(rolled, op=op, freq=freq, **indexer)`): only the windows whose label t has
+ * keep[t] != 0 (device uint8[T]) enter the per-period reduction. */
+int32_t xc_rolling_period_reduce_sel_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                         const int32_t* period_offsets, int32_t P, int32_t window,
+                                         int32_t window_stat, int32_t center, int32_t stat,
+                                         const uint8_t* keep, float* out, void* stream);
+
 /* The spell mask itself, with `select_time` applied to it -- indices/generic.py:503-535 + 557-558
  * (`is_in_spell = select_time(spell_mask(...), **indexer)`): out_mask (T, C) float32 = NaN where
  * keep[t] == 0, else 1 / 0 (day t is / is not covered by a qualifying length-`window` block of the

@@ -81,6 +81,12 @@ def rolling_period_reduce(x2d, poff, window, window_stat_code, center, stat_code
     return torch.from_numpy(np.asarray(out, dtype=np.float32))
 
 
+def rolling_period_reduce_sel(x2d, poff, window, window_stat_code, center, stat_code, keep):
+    rolled = O.rolling(_np(x2d).astype(np.float64), int(window), STAT_NAME[window_stat_code], center=bool(center))
+    rolled = np.where(np.asarray(keep, bool)[:, None], rolled, np.nan)
+    return torch.from_numpy(np.asarray(O.resample_reduce(rolled, poff, STAT_NAME[stat_code]), dtype=np.float32))
+
+
 def spell_runstat(x2d, poff, window, window_stat_code, op_code, thr, reducer_code, resample_before_rl=True):
     out = O.spell_length_statistics(_np(x2d), float(thr), int(window), STAT_NAME[window_stat_code], OP_NAME[op_code],
                                     RED_NAME[reducer_code], poff, resample_before_rl=bool(resample_before_rl))
@@ -323,7 +329,8 @@ def dev_ints(arr, dtype, device):
 FUNCTIONS = [to_time_cell, period_count, period_runstat, period_runstat_gap, period_reduce, rolling_period_reduce,
              spell_runstat, period_run_maxsum, period_runstat2, percentile_doy, doy_interp, doy_threshold_count,
              mask_steps, dev_ints, period_boundary_run, period_boundary_run_range, bootstrap_doy_count, eqm_train,
-             eqm_adjust, period_run_quantile, table_cell_major, period_multi, period_count_arr, spell_mask, transpose_f64]
+             eqm_adjust, period_run_quantile, table_cell_major, period_multi, period_count_arr, spell_mask, transpose_f64,
+             rolling_period_reduce_sel]
 
 
 def install(monkeypatch):

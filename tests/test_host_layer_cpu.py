@@ -518,3 +518,26 @@ def _check_spell_statistics_with_indexers():
 
 def test_spell_statistics_with_indexers(host):
     _check_spell_statistics_with_indexers()
+
+
+def _check_rolling_with_indexers():
+    """select_rolling_resample_op(**indexer): the selection applies to the ROLLED series (indices/generic.py:169-174)."""
+    from xclim_b200 import generic
+    rng = np.random.default_rng(66)
+    T, shape = 365 * 2, (2, 4)
+    x = rng.gamma(0.5, 4.0, (T,) + shape).astype(np.float32)
+    x[rng.random(x.shape) < 0.01] = np.nan
+    da = make_field(x, "2001-01-01", calendar="noleap", units="mm/d")
+    for freq, idx in (("YS", {"season": "DJF"}), ("MS", {"month": [1, 7]}), ("YS", {"date_bounds": ("03-01", "06-15")})):
+        keep = da.time.select_mask(**idx)
+        poff = da.time.period_offsets(freq)
+        for wop, op, center, w in (("sum", "max", False, 5), ("mean", "mean", True, 3), ("max", "min", False, 4)):
+            got = generic.select_rolling_resample_op(da, op, w, window_center=center, window_op=wop, freq=freq, **idx)
+            rolled = O.rolling(x.astype(np.float64), w, wop, center=center)
+            rolled = np.where(keep[:, None, None], rolled, np.nan)
+            exp = O.resample_reduce(rolled, poff, op)
+            np.testing.assert_allclose(got.values, exp, rtol=1e-5, equal_nan=True, err_msg=f"{freq} {idx} {wop} {op}")
+
+
+def test_rolling_with_indexers(host):
+    _check_rolling_with_indexers()

@@ -100,3 +100,9 @@ def test_spell_statistics_with_indexers_on_device(cuda):
     """select_time on the spell mask (xc_spell_mask_f32) through the real kernels."""
     import test_host_layer_cpu as cpu_side
     cpu_side._check_spell_statistics_with_indexers()
+
+
+def test_rolling_with_indexers_on_device(cuda):
+    """select_rolling_resample_op(**indexer) (xc_rolling_period_reduce_sel_f32) through the real kernel."""
+    import test_host_layer_cpu as cpu_side
+    cpu_side._check_rolling_with_indexers()

@@ -39,6 +39,7 @@ SIGNATURES = {
     "xc_period_runstat_gap_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _i32, _f64, _i32, _i32, _i32, _i32, _vp, _vp]),
     "xc_period_reduce_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _f64, _vp, _vp, _vp]),
     "xc_rolling_period_reduce_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "xc_rolling_period_reduce_sel_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "xc_spell_runstat_f32": (_i32, [_vp, _i64, _i64, _i64, _vp, _i32, _i32, _i32, _i32, _f64, _i32, _i32, _vp, _vp]),
     "xc_spell_mask_f32": (_i32, [_vp, _i64, _i64, _i64, _i32, _i32, _i32, _f64, _vp, _i32, _vp, _vp]),
     "xc_spell_sum_interval": (_i32, [_i32, _f64, _i32, _i32, _vp, _vp, _vp]),

@@ -963,6 +963,54 @@ spell_mask_kernel(const float* __restrict__ x, int64_t T, int64_t C, int64_t ldx
   }
 }
 
+
+// select_rolling_resample_op(**indexer) -- indices/generic.py:128-174: the rolling statistic is computed on the
+// WHOLE series and `select_time` then keeps the rolled values whose label lies in the selection
+// (generic.py:169-174), so the selection is a mask on the LABELS of the windows, not on the input.
+// Lane = (cell, period); every kept label re-reads its window (L1 hits).  The seasonal path, not a headline.
+__global__ void __launch_bounds__(kThreads)
+rolling_period_reduce_sel_kernel(const float* __restrict__ x, int64_t T, int64_t C, int64_t ldx,
+                                 const int32_t* __restrict__ poff, int32_t w, int32_t wstat, int32_t shift,
+                                 int32_t stat, const uint8_t* __restrict__ keep, float* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (c >= C) return;
+  const int p = blockIdx.y;
+  const int t0 = poff[p], t1 = poff[p + 1];
+  const float* col = x + c;
+  double s = 0.0, q = 0.0;
+  float m = (stat == XC_STAT_MIN) ? INFINITY : -INFINITY;
+  int n = 0;
+  for (int t = t0; t < t1; ++t) {
+    if (!keep[t]) continue;
+    const int i = t + shift - w + 1;
+    if (i < 0 || i + w > (int)T) continue;            // incomplete window: NaN, skipped by the reduction
+    const float r = window_stat(col, ldx, i, w, wstat);
+    if (r == r) {
+      ++n;
+      s += (double)r;
+      q += (double)r * (double)r;
+      m = (stat == XC_STAT_MIN) ? fminf(m, r) : fmaxf(m, r);
+    }
+  }
+  float res;
+  const double nn = (double)n;
+  switch (stat) {
+    case XC_STAT_SUM: res = (float)s; break;
+    case XC_STAT_COUNT: res = (float)n; break;
+    case XC_STAT_MEAN: res = n ? (float)(s / nn) : NAN; break;
+    case XC_STAT_MIN:
+    case XC_STAT_MAX: res = n ? m : NAN; break;
+    default: {
+      if (!n) { res = NAN; break; }
+      const double mean = s / nn;
+      double var = q / nn - mean * mean;
+      var = var > 0.0 ? var : 0.0;
+      res = (stat == XC_STAT_STD) ? (float)sqrt(var) : (float)var;
+    }
+  }
+  out[(int64_t)p * C + c] = res;
+}
+
 }  // namespace
 }  // namespace xc
 
@@ -1078,4 +1126,25 @@ extern "C" int32_t xc_spell_mask_f32(const float* x, int64_t T, int64_t C, int64
   spell_mask_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, T, C, ldx, window, window_stat, op, (float)thr,
                                                                  keep, drop_nan_adjacent, out_mask);
   return launch_status("spell_mask_kernel");
+}
+
+extern "C" int32_t xc_rolling_period_reduce_sel_f32(const float* x, int64_t T, int64_t C, int64_t ldx,
+                                                    const int32_t* period_offsets, int32_t P, int32_t window,
+                                                    int32_t window_stat, int32_t center, int32_t stat,
+                                                    const uint8_t* keep, float* out, void* stream) {
+  XC_REQUIRE(x && period_offsets && out && keep, "null pointer argument");
+  XC_REQUIRE(T > 0 && C > 0 && ldx >= C && P > 0 && P <= 65535 && T < 2147483647LL, "bad shape");
+  XC_REQUIRE(window >= 1 && window <= T, "window must be in [1, T]");
+  XC_REQUIRE(window_stat == XC_STAT_SUM || window_stat == XC_STAT_MEAN || window_stat == XC_STAT_MIN ||
+                 window_stat == XC_STAT_MAX,
+             "window statistic must be sum, mean, min or max");
+  XC_REQUIRE(stat >= XC_STAT_SUM && stat <= XC_STAT_COUNT, "unknown reduction %d", stat);
+  if (center && window % 2 == 0) {
+    set_error("centred rolling windows of even length are not supported");
+    return XC_ERR_UNSUPPORTED;
+  }
+  dim3 grid((unsigned)((C + kThreads - 1) / kThreads), (unsigned)P, 1);
+  rolling_period_reduce_sel_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(
+      x, T, C, ldx, period_offsets, window, window_stat, center ? window / 2 : 0, stat, keep, out);
+  return launch_status("rolling_period_reduce_sel_kernel");
 }

@@ -287,6 +287,19 @@ def rolling_period_reduce(x2d, poff, window, window_stat_code, center, stat_code
     return out
 
 
+def rolling_period_reduce_sel(x2d, poff, window, window_stat_code, center, stat_code, keep):
+    """rolling_period_reduce with ``select_time`` on the rolled series (labels with keep[t] == 0 dropped)."""
+    T, C = x2d.shape
+    P = len(poff) - 1
+    poff_d = dev_ints(poff, np.int32, x2d.device)
+    k = dev_ints(np.asarray(keep, dtype=np.uint8), np.uint8, x2d.device)
+    out = torch.empty((P, C), dtype=torch.float32, device=x2d.device)
+    check(load().xc_rolling_period_reduce_sel_f32(x2d.data_ptr(), T, C, x2d.stride(0), poff_d.data_ptr(), P,
+                                                  int(window), window_stat_code, int(bool(center)), stat_code,
+                                                  k.data_ptr(), out.data_ptr(), current_stream_ptr()))
+    return out
+
+
 def spell_runstat(x2d, poff, window, window_stat_code, op_code, thr, reducer_code, resample_before_rl=True):
     T, C = x2d.shape
     P = len(poff) - 1

@@ -229,17 +229,19 @@ def select_rolling_resample_op(da, op, window, window_center=True, window_op="me
                                **indexer):
     """Rolling window statistic, then per-period reduction -- indices/generic.py:128-174."""
     wop = window_op.replace("integral", "sum")
-    if indexer:
-        # the reference selects AFTER rolling (indices/generic.py:169-174): rolling on the full series, then
-        # select_time on the rolled values -- not expressible as a mask on the input
-        raise NotImplementedError("select_time indexers on rolling ops are not supported by the B200 hot path")
     if wop not in ("sum", "mean", "min", "max"):
         raise NotImplementedError(f"rolling window_op {window_op!r} is not supported by the B200 hot path")
     if not isinstance(op, str) or op not in _lib.STATS:
         raise NotImplementedError(f"resample op {op!r} is not supported by the B200 hot path")
     x2d, cell_shape, other, ta = _unwrap(da)
-    out = device.rolling_period_reduce(x2d, ta.period_offsets(freq), window, _lib.STATS[wop], window_center,
-                                       _lib.STATS[op])
+    if indexer:
+        # the reference selects AFTER rolling (indices/generic.py:169-174): rolling on the full series, then
+        # select_time on the rolled values -- a mask on the window LABELS
+        out = device.rolling_period_reduce_sel(x2d, ta.period_offsets(freq), window, _lib.STATS[wop], window_center,
+                                               _lib.STATS[op], ta.select_mask(**indexer))
+    else:
+        out = device.rolling_period_reduce(x2d, ta.period_offsets(freq), window, _lib.STATS[wop], window_center,
+                                           _lib.STATS[op])
     attrs = attrs_of(da)
     if out_units is not None:
         attrs["units"] = out_units
