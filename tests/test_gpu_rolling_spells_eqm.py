@@ -172,13 +172,15 @@ def test_spell_length_statistics_min_gap(cuda, min_gap, op, thr):
         generic.spell_length_statistics(da, thr, 3, "sum", op, "max", "YS", min_gap=2)
 
 
-def test_eqm_train_eight_cell_kernel_matches_one_cell_kernel(cuda, monkeypatch):
-    """The 8-cells-per-CTA multi-select (C % 8 == 0) against the oracle and, bit for bit, against the
-    one-cell-per-CTA kernel; a group holds an all-NaN cell, a constant cell and a cell that needs the redo list."""
+def test_eqm_train_group_kernels_match_one_cell_kernel(cuda, monkeypatch):
+    """The cell-group multi-select (32 cells per CTA with 1024 or 512 threads, 16 cells per CTA) against the oracle
+    and, bit for bit, against the one-cell-per-CTA kernel; the groups hold an all-NaN cell, a constant cell, a cell
+    that needs the redo list (heavy non-constant bin), one whose range is subnormal (scale overflow -> redo), a
+    precipitation-like cell with a heavy constant bin, cells full of ties."""
     import torch
     from xclim_b200 import device
     rng = np.random.default_rng(45)
-    T, C = 10950, 32
+    T, C = 10950, 64
     ref = (285 + 6 * rng.standard_normal((T, C))).astype(np.float32)
     hist = (286.5 + 7 * rng.standard_normal((T, C))).astype(np.float32)
     hist[rng.random(hist.shape) < 0.01] = np.nan
@@ -189,19 +191,37 @@ def test_eqm_train_eight_cell_kernel_matches_one_cell_kernel(cuda, monkeypatch):
     pr = rng.gamma(0.5, 5.0, size=(T,)).astype(np.float32)
     pr[rng.random(T) < 0.5] = 0.0
     ref[:, 20] = pr                                  # heavy constant bin (dry days)
+    ref[:, 40] = (rng.integers(0, 7, T) * np.float32(1e-42)).astype(np.float32)   # subnormal range
+    hist[:, 41] = np.round(hist[:, 41])              # many ties
+    ref[:, 50] = rng.integers(0, 3, T).astype(np.float32)                          # three values only
     rd, hd = torch.from_numpy(ref).cuda(), torch.from_numpy(hist).cuda()
-    monkeypatch.delenv("XCLIM_B200_EQM_V1", raising=False)
-    monkeypatch.delenv("XCLIM_B200_EQM_STAGE", raising=False)
-    af, hq = device.eqm_train(rd, hd, 20, 0)                 # 16 cells per CTA, three sweeps over global memory
-    monkeypatch.setenv("XCLIM_B200_EQM_STAGE", "1")
-    af2, hq2 = device.eqm_train(rd, hd, 20, 0)               # 4 cells per CTA, slice staged in shared memory
-    monkeypatch.delenv("XCLIM_B200_EQM_STAGE", raising=False)
+    for k in ("XCLIM_B200_EQM_V1", "XCLIM_B200_EQM_KG", "XCLIM_B200_EQM_GT"):
+        monkeypatch.delenv(k, raising=False)
+    af, hq = device.eqm_train(rd, hd, 20, 0)                 # 32 cells per CTA, 1024 threads
+    others = []
+    monkeypatch.setenv("XCLIM_B200_EQM_GT", "512")
+    others.append(device.eqm_train(rd, hd, 20, 0))           # 32 cells per CTA, 512 threads
+    monkeypatch.delenv("XCLIM_B200_EQM_GT", raising=False)
+    monkeypatch.setenv("XCLIM_B200_EQM_KG", "16")
+    others.append(device.eqm_train(rd, hd, 20, 0))           # 16 cells per CTA
+    monkeypatch.delenv("XCLIM_B200_EQM_KG", raising=False)
+    others.append(device.eqm_train(rd[:, :48].contiguous(), hd[:, :48].contiguous(), 20, 0))   # C % 32 != 0 -> 16
     monkeypatch.setenv("XCLIM_B200_EQM_V1", "1")
     af1, hq1 = device.eqm_train(rd, hd, 20, 0)               # one cell per CTA
+    others.append((af1, hq1))
     torch.cuda.synchronize()
-    for a_, h_ in ((af2, hq2), (af1, hq1)):
-        assert torch.equal(torch.nan_to_num(af, nan=-7.0), torch.nan_to_num(a_, nan=-7.0))
-        assert torch.equal(torch.nan_to_num(hq, nan=-7.0), torch.nan_to_num(h_, nan=-7.0))
+    for a_, h_ in others:
+        n = a_.shape[1]
+        assert torch.equal(torch.nan_to_num(af[:, :n], nan=-7.0), torch.nan_to_num(a_, nan=-7.0))
+        assert torch.equal(torch.nan_to_num(hq[:, :n], nan=-7.0), torch.nan_to_num(h_, nan=-7.0))
+    monkeypatch.delenv("XCLIM_B200_EQM_V1", raising=False)
+    for nq in (1, 7, 50):                                    # 50 quantiles: the targets of 32 cells do not fit -> 16
+        a_g, h_g = device.eqm_train(rd, hd, nq, 1)
+        monkeypatch.setenv("XCLIM_B200_EQM_V1", "1")
+        a_1, h_1 = device.eqm_train(rd, hd, nq, 1)
+        monkeypatch.delenv("XCLIM_B200_EQM_V1", raising=False)
+        assert torch.equal(torch.nan_to_num(a_g, nan=-7.0), torch.nan_to_num(a_1, nan=-7.0)), nq
+        assert torch.equal(torch.nan_to_num(h_g, nan=-7.0), torch.nan_to_num(h_1, nan=-7.0)), nq
     af_o, hq_o = O.eqm_train(ref, hist, 20, "+")
     np.testing.assert_allclose(hq.cpu().numpy(), hq_o, rtol=1e-5, atol=1e-7, equal_nan=True)
     np.testing.assert_allclose(af.cpu().numpy(), af_o, rtol=1e-4, atol=1e-5, equal_nan=True)

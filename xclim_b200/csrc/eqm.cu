@@ -257,30 +257,40 @@ eqm_train_kernel(const float* __restrict__ ref, const float* __restrict__ hist, 
 
 
 // ------------------------------------------------------------------------------------------------
-// train, 8 cells per CTA: the same multi-select (min/max -> 1024-bin histogram -> gather the wanted
-// bins -> rank by counting), but a CTA owns EIGHT ADJACENT CELLS, i.e. one 32-byte sector of every time
-// row: thread = (time row mod 32, cell), so every sector fetched from HBM is used whole and DRAM traffic
-// is the algorithmic 2 T C 4 bytes (the one-cell kernel fetched each sector for eight CTAs and leaned on
-// L2; ncu r1 capture E: 4 useful bytes per 32-byte sector).  The three passes re-read the CTA's
-// 8 x T x 4 = 350 KB slice, which stays L2-resident between passes.  Histograms are packed two
-// 16-bit counters per word (T <= 32768), candidate storage is allocated exactly from the histogram
-// counts (prefix over the wanted bins) in a 1024-float pool per cell.
+// train, a GROUP of adjacent cells per CTA: the same multi-select (min/max -> 1024-bin histogram -> gather the
+// wanted bins -> rank by counting), but a CTA owns kG adjacent cells, i.e. kG * 4 contiguous bytes of every
+// time row, and every fetched sector is used whole (the one-cell kernel fetched each sector for eight CTAs:
+// ncu r1 capture E, 4 useful bytes per 32-byte sector).
+//
+// What bounds it (measured, r2): the number of (CTA, time row) TOUCHES.  At a 4 MB row stride every row of a
+// CTA's slice lies in another DRAM page, and both earlier variants ran at the same ~28 G touches/s whatever the
+// bytes per touch (16 cells x 3 sweeps: 4.3 G touches in 150 ms; 4 cells staged in shared memory x 1 sweep:
+// 5.7 G touches in 203 ms).  So the group is as WIDE as shared memory allows -- 32 cells = 128 bytes per touch --
+// which needs the per-cell state small:
+//   * the packed histogram (two 16-bit counters per word, T <= 32768) and the candidate pool share one
+//     1024-word block per cell (the prefix sums are dead once the candidate offsets are known);
+//   * bin -> slot is one byte per bin;
+// and the sweeps short (they were ~30 instructions per element and sweep):
+//   * bin = mantissa of fma(x - min, scale, 1.5 * 2^23): FADD + FFMA + IADD + VIMNMX, no F2I, no clamp pair;
+//     a NaN lands in the extra bin kBins by the same unsigned min, so the histogram and the gather need no
+//     branch on validity (bins are internal: any monotone binning yields the same order statistics);
+//   * min / max by FMNMX alone (fminf / fmaxf drop NaN), the valid count is the histogram total.
+// Candidate storage is allocated exactly from the histogram counts (prefix over the wanted bins).
 // A cell this layout cannot finish -- a wanted bin with more than kHeavy elements that are not all equal,
-// or a candidate total beyond the pool -- is appended to a redo list that eqm_train_redo_kernel resolves
-// with the one-cell kernel's full machinery (sort fallback included): the results are those of
-// eqm_train_kernel bit for bit.
+// a candidate total beyond the pool, or a range so small that the scale overflows -- is appended to a redo
+// list that the one-cell kernel resolves with its full machinery (sort fallback included): the results are
+// those of eqm_train_kernel bit for bit.
+// Instantiations: <32, 1024> default; <32, 512>; <16, 512> when C is a multiple of 16 only or the targets of
+// 32 cells do not fit (nq > 40).
 // ------------------------------------------------------------------------------------------------
-// Two instantiations (template <cells per CTA, threads, slice staged in shared memory>):
-//   <16, 512, false>  DEFAULT: 16 cells per CTA (whole 64-byte fetch pairs), three sweeps over global memory
-//                     (full grid: 150 ms, 252 GB of DRAM reads for 91 GB of input -- the 700 KB slice does not
-//                     survive in L2 between the sweeps).
-//   <4, 1024, true>   the CTA's slice (4 cells x T x 4 bytes = 175 KB for 30 years of days) is written to shared
-//                     memory by the first sweep and the two other sweeps read it there: DRAM traffic = the
-//                     algorithmic 2 T C 4 bytes, yet SLOWER (203 ms): 16 bytes per row and CTA mean four times
-//                     the (CTA, row) touches, each in another DRAM / TLB page.  XCLIM_B200_EQM_STAGE=1 selects it.
-constexpr int kStageMaxT = 11264;  // 4 cells x 11264 steps x 4 bytes = 176 KB of the 227 KB
-constexpr int kPool = 1024;        // candidate floats per cell
-constexpr int kHeavy = 192;        // bins above this must be constant
+constexpr int kPool = 1024;                 // candidate floats per cell (the same words hold the histogram first)
+constexpr int kHeavy = 192;                 // bins above this must be constant
+constexpr int kHistWords = kBins / 2 + 1;   // 512 words of two counters + the word of bin kBins (NaN sink)
+constexpr int kClaimWord = kHistWords + 15; // 32 words of the block: one claim bit per bin (dead before the gather)
+constexpr int kSobStride = kBins + 4;       // bin -> slot bytes per cell; entry kBins is never claimed
+constexpr float kBinBias = 12582912.0f;     // 1.5 * 2^23: ulp 1 over [bias, bias + kBins]
+constexpr int kBinBiasBits = 0x4B400000;
+static_assert(kClaimWord + 32 <= kPool, "histogram + claim bits inside the cell's block");
 
 __device__ __forceinline__ int float_key(float v) {   // order-preserving int key (for atomicMin / atomicMax)
   const int b = __float_as_int(v);
@@ -288,143 +298,140 @@ __device__ __forceinline__ int float_key(float v) {   // order-preserving int ke
 }
 __device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : (k ^ 0x7fffffff)); }
 
-// dynamic shared memory of eqm_train8_kernel for ntg = 2 * nq targets per cell
-__host__ __device__ inline size_t train8_smem_bytes(int kG, int ntg, int64_t stage_rows) {
-  return (size_t)stage_rows * kG * 4       // the staged slice [T][kG] (0 rows when not staged)
-         + (size_t)kG * (kBins / 2) * 4    // packed 16-bit histogram, then exclusive prefix sums
-         + (size_t)kG * kPool * 4          // candidate pool
-         + (size_t)kG * kBins * 2          // bin -> slot
+// bin of x: round((x - mn) * sc) for valid x (0 .. kBins - 1 since (mx - mn) * sc <= 1023 (1 + 2^-24)), kBins for NaN
+__device__ __forceinline__ unsigned bin_index(float x, float mn, float sc) {
+  const float t = fmaf(x - mn, sc, kBinBias);
+  return min((unsigned)(__float_as_int(t) - kBinBiasBits), (unsigned)kBins);
+}
+
+// dynamic shared memory of eqm_train_group_kernel for ntg = 2 * nq targets per cell
+__host__ __device__ inline size_t train_group_smem_bytes(int kG, int ntg) {
+  return (size_t)kG * kPool * 4            // histogram / claim bits, then the candidate pool
+         + (size_t)kG * kSobStride         // bin -> slot
          + (size_t)kG * ntg * (4 * 8);     // tgt_rank, tgt_bin, tgt_val, slot_bin, slot_off, slot_n, slot_min / max (2)
 }
 
-template <int kG, int kGT, bool STAGE>
+template <int kG, int kGT>
 __global__ void __launch_bounds__(kGT, 1)
-eqm_train8_kernel(const float* __restrict__ ref, const float* __restrict__ hist, int32_t T, int64_t C, int64_t ldx,
-                  int32_t nq, int32_t kind, float* __restrict__ af, float* __restrict__ hist_q,
-                  int32_t* __restrict__ redo /* [0] = count, then cell indexes */) {
-  extern __shared__ __align__(16) unsigned char sm8[];
+eqm_train_group_kernel(const float* __restrict__ ref, const float* __restrict__ hist, int32_t T, int64_t C,
+                       int64_t ldx, int32_t nq, int32_t kind, float* __restrict__ af, float* __restrict__ hist_q,
+                       int32_t* __restrict__ redo /* [0] = count, then cell indexes */) {
+  extern __shared__ __align__(16) unsigned char smg[];
   const int ntg = 2 * nq;
   constexpr int kSub = kG / 4;       // threads (128-bit loads) per time row
-  static_assert(kG % 4 == 0 && kGT % 32 == 0 && kGT / 32 >= kG, "one warp per cell for the scans");
-  float4* keys4 = reinterpret_cast<float4*>(sm8);                             // [T][kSub] staged slice (STAGE only)
-  uint32_t* h32 = reinterpret_cast<uint32_t*>(sm8 + (STAGE ? (size_t)T * kG * 4 : 0));   // [kG][kBins / 2]
-  float* pool = reinterpret_cast<float*>(h32 + kG * (kBins / 2));            // [kG][kPool]
-  unsigned short* slot_of_bin = reinterpret_cast<unsigned short*>(pool + kG * kPool);   // [kG][kBins]
-  int* tgt_rank = reinterpret_cast<int*>(slot_of_bin + kG * kBins);          // [kG][ntg]
+  constexpr int kW = kGT / 32;
+  static_assert(kG % 4 == 0 && kSub <= 16 && kGT % 32 == 0 && kW * 2 <= kPool, "layout");
+  uint32_t* un = reinterpret_cast<uint32_t*>(smg);                            // [kG][kPool]
+  unsigned char* sob = smg + (size_t)kG * kPool * 4;                          // [kG][kSobStride]
+  int* tgt_rank = reinterpret_cast<int*>(sob + (size_t)kG * kSobStride);      // [kG][ntg]
   int* tgt_bin = tgt_rank + kG * ntg;
   float* tgt_val = reinterpret_cast<float*>(tgt_bin + kG * ntg);
   int* slot_bin = reinterpret_cast<int*>(tgt_val + kG * ntg);
   int* slot_off = slot_bin + kG * ntg;
   int* slot_n = slot_off + kG * ntg;
-  int* slot_mm = slot_n + kG * ntg;                                          // [kG][ntg][2] min, max keys
+  int* slot_mm = slot_n + kG * ntg;                                           // [kG][ntg][2] min, max keys
+  float* red_mn = reinterpret_cast<float*>(un);                               // [kW][kG], dead before the histogram
+  float* red_mx = red_mn + kW * kG;
   __shared__ int nslots[kG], bad_cell[kG], cell_n[kG];
   __shared__ float cell_mn[kG], cell_scale[kG];
-  __shared__ float red_mn[kGT / 32][kG], red_mx[kGT / 32][kG];
-  __shared__ int red_n[kGT / 32][kG];
   __shared__ float refq[kG][64];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  // thread = (time row mod 128, half sector): one 128-bit load covers 4 adjacent cells of a row, a warp covers
-  // 16 rows x 32 bytes; kU loads in flight per thread keep ~100 KB per SM on the wire (Little's law at 7 TB/s)
+  // thread = (time row mod kRows, 16-byte piece of the row): one 128-bit load covers 4 adjacent cells, kU loads in
+  // flight per thread keep ~64 KB per SM on the wire
   const int half = tid % kSub, trow = tid / kSub;
-  constexpr int kRows = kGT / kSub, kU = 8;
-  const int cell = tid & (kG - 1);                           // the cell this thread reduces / owns after the passes
+  constexpr int kRows = kGT / kSub, kU = (kGT >= 1024) ? 4 : 8;
   const int64_t c0 = (int64_t)blockIdx.x * kG;
-  constexpr unsigned short kFree = 0xffffu, kBusy = 0xfffeu;
+  constexpr unsigned kFree = 0xffu;
   auto pref_at = [&](int cc, int i) -> int {   // exclusive prefix sum of cell cc at bin i (i <= kBins)
     if (i >= kBins) return cell_n[cc];
-    return (int)((h32[cc * (kBins / 2) + (i >> 1)] >> ((i & 1) * 16)) & 0xffffu);
+    return (int)((un[cc * kPool + (i >> 1)] >> ((i & 1) * 16)) & 0xffffu);
+  };
+  // every sweep: f(v, u) on the float4 of row t for this thread's 4 cells
+  auto sweep = [&](const float* src, auto&& f) {
+    const int64_t step = (int64_t)kRows * ldx;
+    const float* p = src + (int64_t)trow * ldx;
+    int t = trow;
+    for (; t + (kU - 1) * kRows < T; t += kU * kRows) {
+      float4 v[kU];
+#pragma unroll
+      for (int u = 0; u < kU; ++u) v[u] = ld_stream4(p + u * step);
+#pragma unroll
+      for (int u = 0; u < kU; ++u) f(v[u]);
+      p += kU * step;
+    }
+    for (; t < T; t += kRows) {
+      f(ld_stream4(p));
+      p += step;
+    }
   };
   for (int pass = 0; pass < 2; ++pass) {
-    // ---- pass 1: valid count, min, max of every cell
     const float* src = (pass == 0 ? ref : hist) + c0 + 4 * half;
-    float mn4[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-    int nv4[4] = {0, 0, 0, 0};
+    // ---- sweep 1: min, max of every cell (fminf / fmaxf drop NaN)
     {
-      int t = trow;
-      for (; t + (kU - 1) * kRows < T; t += kU * kRows) {
-        float4 v[kU];
+      float mn4[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      sweep(src, [&](const float4& v) {
+        mn4[0] = fminf(mn4[0], v.x); mx4[0] = fmaxf(mx4[0], v.x);
+        mn4[1] = fminf(mn4[1], v.y); mx4[1] = fmaxf(mx4[1], v.y);
+        mn4[2] = fminf(mn4[2], v.z); mx4[2] = fmaxf(mx4[2], v.z);
+        mn4[3] = fminf(mn4[3], v.w); mx4[3] = fmaxf(mx4[3], v.w);
+      });
+      // lanes equal modulo kSub hold the same four cells
 #pragma unroll
-        for (int u = 0; u < kU; ++u) v[u] = ld_stream4(src + (int64_t)(t + u * kRows) * ldx);
+      for (int i = 0; i < 4; ++i) {
 #pragma unroll
-        for (int u = 0; u < kU; ++u) {
-          if constexpr (STAGE) keys4[(size_t)(t + u * kRows) * kSub + half] = v[u];
-          const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (e[i] == e[i]) { mn4[i] = fminf(mn4[i], e[i]); mx4[i] = fmaxf(mx4[i], e[i]); ++nv4[i]; }
+        for (int o = kSub; o < 32; o <<= 1) {
+          mn4[i] = fminf(mn4[i], __shfl_xor_sync(0xffffffffu, mn4[i], o));
+          mx4[i] = fmaxf(mx4[i], __shfl_xor_sync(0xffffffffu, mx4[i], o));
         }
-      }
-      for (; t < T; t += kRows) {
-        const float4 v = ld_stream4(src + (int64_t)t * ldx);
-        if constexpr (STAGE) keys4[(size_t)t * kSub + half] = v;
-        const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (e[i] == e[i]) { mn4[i] = fminf(mn4[i], e[i]); mx4[i] = fmaxf(mx4[i], e[i]); ++nv4[i]; }
+        if (lane < kSub) { red_mn[wid * kG + 4 * lane + i] = mn4[i]; red_mx[wid * kG + 4 * lane + i] = mx4[i]; }
       }
     }
-    // lanes equal modulo kSub hold the same four cells
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      for (int o = kSub; o < 32; o <<= 1) {
-        mn4[i] = fminf(mn4[i], __shfl_xor_sync(0xffffffffu, mn4[i], o));
-        mx4[i] = fmaxf(mx4[i], __shfl_xor_sync(0xffffffffu, mx4[i], o));
-        nv4[i] += __shfl_xor_sync(0xffffffffu, nv4[i], o);
-      }
-      if (lane < kSub) { red_mn[wid][4 * lane + i] = mn4[i]; red_mx[wid][4 * lane + i] = mx4[i]; red_n[wid][4 * lane + i] = nv4[i]; }
-    }
-    for (int i = tid; i < kG * (kBins / 2); i += kGT) h32[i] = 0u;
-    for (int i = tid; i < kG * kBins; i += kGT) slot_of_bin[i] = kFree;
     __syncthreads();
-    float mn = INFINITY, mx = -INFINITY;
-    int n = 0;
-#pragma unroll
-    for (int w = 0; w < kGT / 32; ++w) { mn = fminf(mn, red_mn[w][cell]); mx = fmaxf(mx, red_mx[w][cell]); n += red_n[w][cell]; }
-    {
+    if (tid < kG) {
+      float mn = INFINITY, mx = -INFINITY;
+      for (int w = 0; w < kW; ++w) { mn = fminf(mn, red_mn[w * kG + tid]); mx = fmaxf(mx, red_mx[w * kG + tid]); }
       const bool degenerate = !(mx > mn) || !(mx - mn < INFINITY);
-      const float scale = degenerate ? 0.f : (float)kBins / (mx - mn);
-      if (tid < kG) { nslots[tid] = 0; bad_cell[tid] = 0; cell_n[tid] = n; cell_mn[tid] = mn; cell_scale[tid] = scale; }
+      float scale = degenerate ? 0.f : (float)(kBins - 1) / (mx - mn);
+      const bool overflow = !(scale < INFINITY);       // a (sub)normal range: left to the one-cell kernel
+      if (overflow) scale = 0.f;
+      nslots[tid] = 0;
+      bad_cell[tid] = overflow ? 1 : 0;
+      cell_n[tid] = (mx >= mn) ? 1 : 0;                // any valid value; the histogram total replaces it below
+      cell_mn[tid] = mn;
+      cell_scale[tid] = scale;
     }
     __syncthreads();
+    for (int cc = wid; cc < kG; cc += kW) {
+      for (int w = lane; w < kClaimWord + 32; w += 32) un[cc * kPool + w] = 0u;
+    }
+    {
+      uint32_t* sw = reinterpret_cast<uint32_t*>(sob);
+      for (int i = tid; i < kG * kSobStride / 4; i += kGT) sw[i] = 0xffffffffu;
+    }
     // the four cells this thread streams
     float cmn[4], csc[4];
-    bool cwork[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       cmn[i] = cell_mn[4 * half + i];
       csc[i] = cell_scale[4 * half + i];
-      cwork[i] = (cell_n[4 * half + i] > 0) && (csc[i] != 0.f);
     }
-    // ---- pass 2: histogram (two 16-bit counters per word; T <= 32768)
+    __syncthreads();
+    // ---- sweep 2: histogram (two 16-bit counters per word; a degenerate cell counts into bin 0, unused)
     {
-      auto tally = [&](const float4& v) {
+      uint32_t* hb = un + (4 * half) * kPool;
+      sweep(src, [&](const float4& v) {
         const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (cwork[i] && e[i] == e[i]) {
-            const int b = min(kBins - 1, (int)((e[i] - cmn[i]) * csc[i]));
-            atomicAdd(&h32[(4 * half + i) * (kBins / 2) + (b >> 1)], (b & 1) ? 65536u : 1u);
-          }
+          const unsigned b = bin_index(e[i], cmn[i], csc[i]);
+          atomicAdd(hb + i * kPool + (b >> 1), 1u + (b & 1u) * 65535u);
         }
-      };
-      if constexpr (STAGE) {
-        for (int t = trow; t < T; t += kRows) tally(keys4[(size_t)t * kSub + half]);
-      } else {
-        int t = trow;
-        for (; t + (kU - 1) * kRows < T; t += kU * kRows) {
-          float4 v[kU];
-#pragma unroll
-          for (int u = 0; u < kU; ++u) v[u] = ld_stream4(src + (int64_t)(t + u * kRows) * ldx);
-#pragma unroll
-          for (int u = 0; u < kU; ++u) tally(v[u]);
-        }
-        for (; t < T; t += kRows) tally(ld_stream4(src + (int64_t)t * ldx));
-      }
+      });
     }
     __syncthreads();
-    if (wid < kG) {  // in-place exclusive scan of the kBins counters of cell `wid` by warp `wid`
+    for (int cc = wid; cc < kG; cc += kW) {  // in-place exclusive scan of the kBins counters of cell cc by one warp
       constexpr int per = kBins / 32;
-      uint32_t* hc = h32 + wid * (kBins / 2) + lane * (per / 2);
+      uint32_t* hc = un + cc * kPool + lane * (per / 2);
       int loc[per], sum = 0;
 #pragma unroll
       for (int i = 0; i < per; i += 2) {
@@ -447,9 +454,10 @@ eqm_train8_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
         run += loc[i + 1];
         hc[i >> 1] = lo16 | (hi16 << 16);
       }
+      if (lane == 31 && cell_scale[cc] != 0.f) cell_n[cc] = run;   // the valid count
     }
     __syncthreads();
-    // ---- wanted order statistics of every cell: bin + rank inside the bin; claim the bins
+    // ---- wanted order statistics of every cell: bin + rank inside the bin; the first to want a bin gives it a slot
     for (int g = tid; g < kG * ntg; g += kGT) {
       const int cc = g / ntg, k = g - cc * ntg;
       const int nn = cell_n[cc];
@@ -463,69 +471,58 @@ eqm_train8_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
         const int mid = (lo + hi) >> 1;
         if (pref_at(cc, mid) <= r) lo = mid; else hi = mid;
       }
+      const int below = pref_at(cc, lo);
       tgt_bin[cc * ntg + k] = lo;
-      tgt_rank[cc * ntg + k] = r - pref_at(cc, lo);
-      if (atomicCAS(&slot_of_bin[cc * kBins + lo], kFree, kBusy) == kFree) {  // first to claim the bin allocates its slot
+      tgt_rank[cc * ntg + k] = r - below;
+      const uint32_t bit = 1u << (lo & 31);
+      if (!(atomicOr(&un[cc * kPool + kClaimWord + (lo >> 5)], bit) & bit)) {
         const int sl = atomicAdd(&nslots[cc], 1);
         slot_bin[cc * ntg + sl] = lo;
+        slot_off[cc * ntg + sl] = pref_at(cc, lo + 1) - below;     // the count; the offset after the next barrier
         slot_n[cc * ntg + sl] = 0;
         slot_mm[(cc * ntg + sl) * 2] = 0x7fffffff;
         slot_mm[(cc * ntg + sl) * 2 + 1] = (int)0x80000000;
-        slot_of_bin[cc * kBins + lo] = (unsigned short)sl;
+        sob[cc * kSobStride + lo] = (unsigned char)sl;
       }
     }
     __syncthreads();
     // ---- candidate storage: exact offsets from the histogram counts (heavy bins are not gathered)
     if (tid < kG) {
       int off = 0;
-      for (int sl = 0; sl < nslots[tid]; ++sl) {
-        const int bb = slot_bin[tid * ntg + sl];
-        const int cnt = pref_at(tid, bb + 1) - pref_at(tid, bb);
+      const int ns = nslots[tid];
+      for (int sl = 0; sl < ns; ++sl) {
+        const int cnt = slot_off[tid * ntg + sl];
         slot_off[tid * ntg + sl] = (cnt > kHeavy) ? -1 : off;
         if (cnt <= kHeavy) off += cnt;
       }
-      if (off > kPool) bad_cell[tid] = 1;
+      if (off > kPool) {       // does not fit: nothing is gathered (min / max only) and the cell is redone
+        bad_cell[tid] = 1;
+        for (int sl = 0; sl < ns; ++sl) slot_off[tid * ntg + sl] = -1;
+      }
     }
     __syncthreads();
-    // ---- pass 3: gather the elements of the wanted bins (min / max of the heavy ones)
+    // ---- sweep 3: gather the elements of the wanted bins (min / max of the heavy ones)
     {
-      bool cgo[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) cgo[i] = cwork[i] && !bad_cell[4 * half + i];
-      auto gather = [&](const float4& v) {
+      const unsigned char* sb = sob + (4 * half) * kSobStride;
+      sweep(src, [&](const float4& v) {
         const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (cgo[i] && e[i] == e[i]) {
+          const unsigned sl = sb[i * kSobStride + bin_index(e[i], cmn[i], csc[i])];
+          if (sl != kFree) {
             const int cc = 4 * half + i;
-            const unsigned short sl = slot_of_bin[cc * kBins + min(kBins - 1, (int)((e[i] - cmn[i]) * csc[i]))];
-            if (sl != kFree) {
-              const int off = slot_off[cc * ntg + sl];
-              if (off >= 0) {
-                const int p = atomicAdd(&slot_n[cc * ntg + sl], 1);
-                pool[cc * kPool + off + p] = e[i];
-              } else {
-                const int kx = float_key(e[i]);
-                atomicMin(&slot_mm[(cc * ntg + sl) * 2], kx);
-                atomicMax(&slot_mm[(cc * ntg + sl) * 2 + 1], kx);
-              }
+            const int off = slot_off[cc * ntg + sl];
+            if (off >= 0) {
+              const int p = atomicAdd(&slot_n[cc * ntg + sl], 1);
+              reinterpret_cast<float*>(un)[cc * kPool + off + p] = e[i];
+            } else {
+              const int kx = float_key(e[i]);
+              atomicMin(&slot_mm[(cc * ntg + sl) * 2], kx);
+              atomicMax(&slot_mm[(cc * ntg + sl) * 2 + 1], kx);
             }
           }
         }
-      };
-      if constexpr (STAGE) {
-        for (int t = trow; t < T; t += kRows) gather(keys4[(size_t)t * kSub + half]);
-      } else {
-        int t = trow;
-        for (; t + (kU - 1) * kRows < T; t += kU * kRows) {
-          float4 v[kU];
-#pragma unroll
-          for (int u = 0; u < kU; ++u) v[u] = ld_stream4(src + (int64_t)(t + u * kRows) * ldx);
-#pragma unroll
-          for (int u = 0; u < kU; ++u) gather(v[u]);
-        }
-        for (; t < T; t += kRows) gather(ld_stream4(src + (int64_t)t * ldx));
-      }
+      });
     }
     __syncthreads();
     // ---- heavy bins must be constant
@@ -536,34 +533,52 @@ eqm_train8_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
         bad_cell[cc] = 1;
     }
     __syncthreads();
-    // ---- rank inside the bin by counting: one warp per (cell, target)
-    for (int g = wid; g < kG * ntg; g += kGT / 32) {
-      const int cc = g / ntg, k = g - cc * ntg;
+    // ---- rank inside the bin by counting: one warp per (cell, quantile); its two neighbours share the count
+    // when they fall in the same bin
+    for (int g = wid; g < kG * nq; g += kW) {
+      const int cc = g / nq, j = g - cc * nq;
       if (cell_n[cc] <= 0 || cell_scale[cc] == 0.f || bad_cell[cc] || c0 + cc >= C) continue;
-      const int sl = slot_of_bin[cc * kBins + tgt_bin[cc * ntg + k]];
-      const int off = slot_off[cc * ntg + sl];
-      if (off < 0) {                                   // constant heavy bin
-        if (lane == 0) tgt_val[cc * ntg + k] = key_float(slot_mm[(cc * ntg + sl) * 2]);
-        continue;
-      }
-      const int m = slot_n[cc * ntg + sl];
-      const float* cl = pool + cc * kPool + off;
-      const int want = tgt_rank[cc * ntg + k];
-      float found = NAN;
-      for (int i = lane; i < m; i += 32) {
-        const float vi = cl[i];
-        int less = 0;
-        for (int kk = 0; kk < m; ++kk) {
-          const float vk = cl[kk];
-          less += (vk < vi || (vk == vi && kk < i)) ? 1 : 0;
+      const int k0 = cc * ntg + 2 * j;
+      const int b0 = tgt_bin[k0], b1 = tgt_bin[k0 + 1];
+      for (int h = 0; h < 2; ++h) {
+        if (h == 1 && b1 == b0) break;
+        const bool both = (h == 0 && b1 == b0);
+        const int sl = sob[cc * kSobStride + (h ? b1 : b0)];
+        const int off = slot_off[cc * ntg + sl];
+        if (off < 0) {                                   // constant heavy bin
+          if (lane == 0) {
+            const float cv = key_float(slot_mm[(cc * ntg + sl) * 2]);
+            tgt_val[k0 + h] = cv;
+            if (both) tgt_val[k0 + 1] = cv;
+          }
+          continue;
         }
-        if (less == want) found = vi;
+        const int m = slot_n[cc * ntg + sl];
+        const float* cl = reinterpret_cast<const float*>(un) + cc * kPool + off;
+        const int want0 = tgt_rank[k0 + h];
+        const int want1 = both ? tgt_rank[k0 + 1] : -1;
+        float f0 = NAN, f1 = NAN;
+        for (int i = lane; i < m; i += 32) {
+          const float vi = cl[i];
+          int less = 0;
+          for (int kk = 0; kk < m; ++kk) {
+            const float vk = cl[kk];
+            less += (vk < vi || (vk == vi && kk < i)) ? 1 : 0;
+          }
+          if (less == want0) f0 = vi;
+          if (less == want1) f1 = vi;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          const float o0 = __shfl_xor_sync(0xffffffffu, f0, o);
+          const float o1 = __shfl_xor_sync(0xffffffffu, f1, o);
+          f0 = (f0 == f0) ? f0 : o0;
+          f1 = (f1 == f1) ? f1 : o1;
+        }
+        if (lane == 0) {
+          tgt_val[k0 + h] = f0;
+          if (both) tgt_val[k0 + 1] = f1;
+        }
       }
-      for (int o = 16; o > 0; o >>= 1) {
-        const float other = __shfl_xor_sync(0xffffffffu, found, o);
-        found = (found == found) ? found : other;
-      }
-      if (lane == 0) tgt_val[cc * ntg + k] = found;
     }
     __syncthreads();
     // ---- quantiles (numpy's _lerp on the two neighbours)
@@ -601,6 +616,7 @@ eqm_train8_kernel(const float* __restrict__ ref, const float* __restrict__ hist,
     __syncthreads();
   }
 }
+
 
 constexpr int kAdjThreads = 128;
 constexpr int kLut = 32;   // coarse position table per cell
@@ -709,7 +725,7 @@ using namespace xc;
 
 extern "C" int64_t xc_eqm_train_workspace_bytes(int64_t T, int64_t C, int32_t nq) {
   (void)T; (void)nq;
-  // redo list of the 8-cells-per-CTA kernel: a counter + at most two entries per cell
+  // redo list of the cell-group kernel: a counter + at most two entries per cell
   return 256 + (2 * C + 1) * 4;
 }
 
@@ -756,33 +772,37 @@ extern "C" int32_t xc_eqm_train_f32(const float* ref, const float* hist, int64_t
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t need = xc_eqm_train_workspace_bytes(T, C, nq);
-  // the staged variant is a measured NEGATIVE result (full grid 203 ms vs 150 ms): what costs is the number of
-  // (CTA, time row) touches -- every row of a CTA's slice lies in another DRAM / TLB page at a 4 MB row stride --
-  // and 4 cells per CTA touch 4x as many rows per byte; it stays selectable for the record
-  const bool staged = T <= kStageMaxT && getenv("XCLIM_B200_EQM_STAGE") != nullptr;
-  const int g = staged ? 4 : 16;
+  // widest group first: 32 cells = 128 bytes per (CTA, time row) touch; 16 when C is not a multiple of 32 or the
+  // targets of 32 cells do not fit in shared memory.  (A variant that staged a 4-cell slice in shared memory and
+  // read DRAM once was a measured NEGATIVE result -- 203 ms vs 150 ms: four times the row touches -- and is gone.)
+  const char* kg_env = getenv("XCLIM_B200_EQM_KG");
+  const char* gt_env = getenv("XCLIM_B200_EQM_GT");
+  int g = 32;
+  if (kg_env && atoi(kg_env) == 16) g = 16;
+  if (g == 32 && (C % 32 != 0 || train_group_smem_bytes(32, 2 * nq) + 12 * 1024 > 227 * 1024)) g = 16;
+  const bool fits = train_group_smem_bytes(g, 2 * nq) + 8 * 1024 <= 227 * 1024;
   const bool vec_ok = (C % g == 0) && (ldx % 4 == 0) && aligned16(ref) && aligned16(hist);
-  if (workspace == nullptr || workspace_bytes < need || !vec_ok || getenv("XCLIM_B200_EQM_V1")) {
+  if (workspace == nullptr || workspace_bytes < need || !vec_ok || !fits || getenv("XCLIM_B200_EQM_V1")) {
     // no scratch for a redo list, or a layout without whole 16-byte pieces per CTA: the one-cell-per-CTA
     // kernel (complete in itself)
     return launch_train_cells(ref, hist, T, C, ldx, nq, kind, af, hist_q, nullptr, (unsigned)C, st);
   }
   int32_t* redo = (int32_t*)workspace;
   XC_CHECK_CUDA(cudaMemsetAsync(redo, 0, 4, st));
-  const size_t smem8 = train8_smem_bytes(g, 2 * nq, staged ? T : 0);
+  const size_t smemg = train_group_smem_bytes(g, 2 * nq);
   const int64_t groups = C / g;
-  if (staged) {
-    XC_CHECK_CUDA(cudaFuncSetAttribute(eqm_train8_kernel<4, 1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem8));
-    eqm_train8_kernel<4, 1024, true><<<(unsigned)groups, 1024, smem8, st>>>(ref, hist, (int32_t)T, C, ldx, nq, kind, af,
-                                                                             hist_q, redo);
-  } else {
-    XC_CHECK_CUDA(cudaFuncSetAttribute(eqm_train8_kernel<16, 512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem8));
-    eqm_train8_kernel<16, 512, false><<<(unsigned)groups, 512, smem8, st>>>(ref, hist, (int32_t)T, C, ldx, nq, kind, af,
-                                                                             hist_q, redo);
-  }
-  int32_t e = launch_status("eqm_train8_kernel");
+#define XC_TRAIN_GROUP(G, GT)                                                                                      \
+  do {                                                                                                             \
+    XC_CHECK_CUDA(cudaFuncSetAttribute(eqm_train_group_kernel<G, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)smemg));                                                               \
+    eqm_train_group_kernel<G, GT><<<(unsigned)groups, GT, smemg, st>>>(ref, hist, (int32_t)T, C, ldx, nq, kind,   \
+                                                                        af, hist_q, redo);                         \
+  } while (0)
+  if (g == 32 && gt_env && atoi(gt_env) == 512) XC_TRAIN_GROUP(32, 512);
+  else if (g == 32) XC_TRAIN_GROUP(32, 1024);
+  else XC_TRAIN_GROUP(16, 512);
+#undef XC_TRAIN_GROUP
+  int32_t e = launch_status("eqm_train_group_kernel");
   if (e) return e;
   // cells the eight-cell layout could not finish (heavy non-constant bins): a small fixed grid walks the list
   return launch_train_cells(ref, hist, T, C, ldx, nq, kind, af, hist_q, redo, 296u, st);
