@@ -28,23 +28,34 @@ SLAB_BYTES = 1 << 30
 _staging: dict = {}
 
 
-def plan_slabs(n_rows: int, bytes_per_row: int, slab_bytes: int = None) -> list[tuple[int, int]]:
-    """Contiguous [r0, r1) ranges of the leading spatial dimension, each about ``slab_bytes``."""
+def plan_slabs(n_rows: int, bytes_per_row: int, slab_bytes: int = None, align: int = 1) -> list[tuple[int, int]]:
+    """Contiguous [r0, r1) ranges of the leading spatial dimension, each about ``slab_bytes``.
+    With ``align`` > 1 (the chunk length of a file-backed input along that dimension) every slab edge
+    but the last is a multiple of it, so that no chunk of the file is read or inflated twice."""
     slab_bytes = SLAB_BYTES if slab_bytes is None else slab_bytes
     rows = int(max(1, min(n_rows, slab_bytes // max(1, bytes_per_row))))
     n = -(-n_rows // rows)
     rows = -(-n_rows // n)            # even out: no tiny last slab
+    if align > 1:
+        rows = max(align, rows // align * align)
     return [(r, min(n_rows, r + rows)) for r in range(0, n_rows, rows)]
 
 
 def _host_array(obj):
-    """The numpy view of a host-backed input, or None (device tensor, unsupported container)."""
+    """The numpy view (or lazy file-backed source, io.LazyGrid) of a host-backed input, or None
+    (device tensor, unsupported container)."""
+    from .io import LazyGrid
     v = raw_values(obj)
     if hasattr(v, "is_cuda"):
         if v.is_cuda:
             return None
         return v.numpy()
-    return v if isinstance(v, np.ndarray) else None
+    return v if isinstance(v, (np.ndarray, LazyGrid)) else None
+
+
+def _is_lazy(h):
+    from .io import LazyGrid
+    return isinstance(h, LazyGrid)
 
 
 def _is_labelled(a):
@@ -74,7 +85,8 @@ def _streamable(series, tables):
     for a in series.values():
         dims = dims_of(a)
         h = _host_array(a)
-        if h is None or dims[0] != "time" or len(dims) < 2 or h.dtype != np.float32 or not h.flags.c_contiguous:
+        if h is None or dims[0] != "time" or len(dims) < 2 or h.dtype != np.float32 or \
+                not (_is_lazy(h) or h.flags.c_contiguous):
             return None
         if lead is None:
             lead, shape = dims[1], h.shape
@@ -86,7 +98,7 @@ def _streamable(series, tables):
     for a in tables.values():
         dims = dims_of(a)
         h = _host_array(a)
-        if h is None or lead not in dims or dims[0] != lead or h.shape[0] != shape[1]:
+        if h is None or _is_lazy(h) or lead not in dims or dims[0] != lead or h.shape[0] != shape[1]:
             return None
     return lead, shape
 
@@ -124,20 +136,22 @@ def run_streamed(fn, args, kwargs, lead, shape, series, tables):
     lib = load()
     T, n_lead = shape[0], shape[1]
     rest = int(np.prod(shape[2:], dtype=np.int64)) if len(shape) > 2 else 1
-    slabs = plan_slabs(n_lead, T * rest * 4, OPTIONS.get("stream_slab_bytes", SLAB_BYTES))
+    keys = list(series)
+    hosts = {k: _host_array(series[k]) for k in keys}
+    align = int(np.lcm.reduce([int(getattr(h, "lead_chunk", 1)) for h in hosts.values()]))
+    slabs = plan_slabs(n_lead, T * rest * 4, OPTIONS.get("stream_slab_bytes", SLAB_BYTES), align)
     rows_max = max(b - a for a, b in slabs)
     comp = torch.cuda.current_stream()
     s_copy, s_out = torch.cuda.Stream(), torch.cuda.Stream()
     s_copy.wait_stream(comp)
-    keys = list(series)
-    hosts = {k: _host_array(series[k]) for k in keys}
     bufs = {k: [torch.empty(T * rows_max * rest, dtype=torch.float32, device="cuda") for _ in range(2)] for k in keys}
     copied = [torch.cuda.Event() for _ in range(2)]
     done = [torch.cuda.Event() for _ in range(2)]
     # Inputs that are not page-locked (plain numpy arrays, memory-mapped files: the I/O step of SURVEY.md 8f.3)
     # are staged by a reader thread: slab k+2 is gathered from the file / pageable memory into a pinned buffer
     # while slab k+1 crosses PCIe and slab k is computed, so disk, PCIe and kernels overlap.
-    staged = {k: not lib.xc_host_pinned(hosts[k].ctypes.data) for k in keys}
+    # File-backed lazy sources (io.LazyGrid: NetCDF-3, zarr) are read and decoded by the same thread.
+    staged = {k: _is_lazy(hosts[k]) or not lib.xc_host_pinned(hosts[k].ctypes.data) for k in keys}
     stage_bufs, pool, futures = {}, None, {}
     if any(staged.values()):
         from concurrent.futures import ThreadPoolExecutor
@@ -154,7 +168,11 @@ def run_streamed(fn, args, kwargs, lead, shape, series, tables):
         for key in keys:
             if staged[key]:
                 dst = stage_bufs[key][b][: T * (r1 - r0) * rest * 4].numpy().view(np.float32)
-                np.copyto(dst.reshape((T, r1 - r0) + tuple(shape[2:])), hosts[key][:, r0:r1])
+                dst = dst.reshape((T, r1 - r0) + tuple(shape[2:]))
+                if _is_lazy(hosts[key]):
+                    hosts[key].read_rows(r0, r1, out=dst)
+                else:
+                    np.copyto(dst, hosts[key][:, r0:r1])
 
     def submit_stage(k):
         if pool is not None and k < len(slabs):
