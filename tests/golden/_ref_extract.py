@@ -38,8 +38,17 @@ def _extract(relpath: str, names: list[str], extra_ns: dict) -> dict:
     with open(path) as f:
         src = f.read()
     tree = ast.parse(src)
-    wanted = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
-    missing = set(names) - {n.name for n in wanted}
+    def _name(n):
+        if isinstance(n, ast.FunctionDef):
+            return n.name
+        if isinstance(n, ast.Assign) and len(n.targets) == 1 and isinstance(n.targets[0], ast.Name):
+            return n.targets[0].id          # module-level constant tables (e.g. DAY_LENGTHS)
+        if isinstance(n, ast.AnnAssign) and isinstance(n.target, ast.Name):
+            return n.target.id
+        return None
+
+    wanted = [n for n in tree.body if _name(n) in names]
+    missing = set(names) - {_name(n) for n in wanted}
     if missing:
         raise RuntimeError(f"reference functions not found in {relpath}: {sorted(missing)}")
     mod = ast.Module(body=wanted, type_ignores=[])
@@ -66,3 +75,26 @@ def load_run_length() -> dict:
 def load_utils() -> dict:
     ns = {"np": np, "Sequence": Sequence}
     return _extract("src/xclim/core/utils.py", UTILS_FUNCS, ns)
+
+
+CFFWIS_NAMES = [
+    "default_params", "DAY_LENGTHS", "DAY_LENGTH_FACTORS", "_day_length", "_day_length_factor",
+    "_fine_fuel_moisture_code", "_duff_moisture_code", "_drought_code", "initial_spread_index", "build_up_index",
+    "fire_weather_index", "daily_severity_rating", "_overwintering_drought_code", "_fire_season",
+    "_fire_weather_calc",
+]
+
+
+def load_cffwis() -> dict:
+    """The numba / numpy cores of the Canadian Forest Fire Weather Index System
+    (indices/fire/_cffwis.py:161-900), executed where they lie."""
+    from collections import OrderedDict
+
+    from numba import njit, vectorize
+
+    class _XR:
+        DataArray = object
+
+    ns = {"np": np, "njit": njit, "vectorize": vectorize, "OrderedDict": OrderedDict, "xr": _XR,
+          "Sequence": Sequence, "namedtuple": namedtuple}
+    return _extract("src/xclim/indices/fire/_cffwis.py", CFFWIS_NAMES, ns)
