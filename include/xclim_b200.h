@@ -450,6 +450,51 @@ int32_t xc_copy_box_async(void* dst, int64_t dst_pitch, const void* src, int64_t
  * memory-mapped files: the slab streamer stages those through its own pinned buffers). */
 int32_t xc_host_pinned(const void* host_ptr);
 
+/* ---------------------------------------------------------------------------------------------
+ * f4  Canadian Forest Fire Weather Index System -- indices/fire/_cffwis.py
+ *   Replaces the day loop `_fire_weather_calc` (:680-873; the gufunc core of `fire_weather_ufunc`
+ *   :879-1151, behind `cffwis_indices` :1273-1402, `drought_code` :1415-1500, `duff_moisture_code`
+ *   :1513-1594) with its numba step functions (`_fine_fuel_moisture_code` :246-319,
+ *   `_duff_moisture_code` :322-393, `_drought_code` :396-446, `_overwintering_drought_code` :549-583),
+ *   the numpy indices (`initial_spread_index` :449-469, `build_up_index` :472-501,
+ *   `fire_weather_index` :504-528, `daily_severity_rating` :531-546) and the season masks
+ *   (`_fire_season` :590-677).  One lane walks one cell through time; every requested output is
+ *   written in the same pass.
+ *   Inputs (T, C) float32 with leading dimension ldx, units as `fire_weather_ufunc` takes them:
+ *   tas degC, pr mm/day, hurs %, ws km/h, snd m (NULL where the requested codes / modes do not
+ *   need them).  season_mask_in: (T, C) uint8, season_mode == XC_FWI_SEASON_MASK only.
+ *   month: device int8[T] (1..12).  lat: device float64[C] (degrees north).
+ *   dc0 / dmc0 / ffmc0 / winter_pr0: device float32[C] or NULL (= NaN, NaN, NaN, 0).
+ *   Outputs: any of DC..DSR (T, C) float32, season_mask_out (T, C) uint8, winter_pr_out float32[C]
+ *   may be NULL; codes an index depends on are computed whether or not they are stored, as the
+ *   reference adds them to `indexes` (:1046-1057).  Arithmetic as the reference's for float32
+ *   inputs: the three codes in float64 (sqrt of the wind speed and log of the previous DMC in
+ *   float32, as numba types them), stored and carried as float32; ISI / BUI / FWI / DSR in float32.
+ *   Limits: temp_condition_days, snow_condition_days <= 32, snow_cover_days <= 128.
+ * ------------------------------------------------------------------------------------------- */
+#define XC_FWI_SEASON_ALWAYS 0   /* season_method=None: no start-ups or shut-downs */
+#define XC_FWI_SEASON_MASK   1   /* season_mask given */
+#define XC_FWI_SEASON_WF93   2
+#define XC_FWI_SEASON_LA08   3
+#define XC_FWI_SEASON_GFWED  4
+#define XC_FWI_DRY_NONE       0
+#define XC_FWI_DRY_CFS        1
+#define XC_FWI_DRY_GFWED      2
+#define XC_FWI_DRY_GFWED_SNOW 3  /* "GFWED" with snow depth given (:1085-1088) */
+typedef struct {
+  int32_t season_mode, overwintering, dry_start, initial_start_up;
+  int32_t temp_condition_days, snow_condition_days, snow_cover_days;
+  float temp_start_thresh, temp_end_thresh, snow_thresh, prec_thresh, snow_min_mean_depth;
+  float dc_start, dmc_start, ffmc_start, dc_dry_factor, dmc_dry_factor;
+  double snow_min_cover_frac, carry_over_fraction, wetting_efficiency_fraction, min_dc;
+} XcFwiParams;
+int32_t xc_fwi_f32(const float* tas, const float* pr, const float* hurs, const float* ws, const float* snd,
+                   const uint8_t* season_mask_in, const int8_t* month, const double* lat,
+                   const float* dc0, const float* dmc0, const float* ffmc0, const float* winter_pr0,
+                   int64_t T, int64_t C, int64_t ldx, const XcFwiParams* params_host,
+                   float* DC, float* DMC, float* FFMC, float* ISI, float* BUI, float* FWI, float* DSR,
+                   uint8_t* season_mask_out, float* winter_pr_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -211,6 +211,19 @@ def fire_season(tas, snd=None, method="WF93", temp_start_thresh=12.0, temp_end_t
     return mask
 
 
+_ORDER = ["DC", "DMC", "FFMC", "ISI", "BUI", "FWI", "DSR"]
+
+
+def complete_indexes(indexes=None):
+    """The index list ``fire_weather_ufunc`` works with (:1046-1057): every index an asked one depends on is
+    added, in the fixed order DC, DMC, FFMC, ISI, BUI, FWI, DSR."""
+    want = set(indexes or _ORDER)
+    for idx, needs in (("DSR", {"FWI"}), ("FWI", {"ISI", "BUI"}), ("BUI", {"DC", "DMC"}), ("ISI", {"FFMC"})):
+        if idx in want:
+            want |= needs
+    return sorted(want, key=_ORDER.index)
+
+
 def fire_weather_calc(tas, pr, hurs, ws, snd, mth, lat, season_mask, dc0, dmc0, ffmc0, winter_pr, *, outputs,
                       season_method=None, overwintering=False, dry_start=None, initial_start_up=True, **params):
     """The day loop (680-873) on ``(T, C)`` float32 series; per-cell ``lat`` and previous codes ``(C,)``.

@@ -1,0 +1,59 @@
+"""The DEVICE code of the fire-weather kernel (xclim_b200/csrc/fwi_core.cuh), compiled for the host, against
+the reference fixtures and the oracle.  The CUDA kernel adds only the thread-to-cell mapping to this code
+(xclim_b200/csrc/fwi.cu); its run on a GPU is tests/test_zz_gpu_fire.py."""
+import numpy as np
+import pytest
+
+import fwi_host_build as hb
+from oracle import fire_oracle as FO
+from test_fire_oracle import case_inputs, check_outputs, golden, mg  # noqa: F401
+
+
+@pytest.mark.parametrize("name", list(mg.CFFWIS_CASES))
+def test_host_build_of_the_kernel_matches_reference_fixture(golden, name):  # noqa: F811
+    args, kw, exp = case_inputs(golden, name)
+    if kw.get("season_method") is None:
+        args = args[:4] + (None,) + args[5:]      # snd is not needed: the library accepts NULL
+    got = hb.run(*args, **kw)
+    check_outputs(got, exp, name, exact_frac=0.99)
+
+
+def test_host_build_matches_oracle_on_other_parameters():
+    rng = np.random.default_rng(11)
+    inp = mg.cffwis_inputs(seed=5, C=16, T=500)
+    tc = lambda a: np.ascontiguousarray(a.T)   # noqa: E731
+    dc0, dmc0, ffmc0, wpr = mg.cffwis_state(inp, "some")
+    base = (tc(inp["tas"]), tc(inp["pr"]), tc(inp["hurs"]), tc(inp["ws"]), tc(inp["snd"]), inp["mth"], inp["lat"])
+    cases = [
+        dict(season_method="GFWED", temp_condition_days=9, snow_condition_days=12, outputs=["FFMC", "ISI", "season_mask"]),
+        dict(season_method="LA08", snow_condition_days=5, temp_condition_days=2, dry_start="CFS", outputs=["DC", "DMC", "BUI", "season_mask"]),
+        dict(season_method="GFWED", dry_start="GFWED+SNOW", snow_cover_days=61, snow_min_cover_frac=0.3,
+             snow_min_mean_depth=0.02, outputs=["DC", "DMC", "season_mask"]),
+        dict(season_method="WF93", overwintering=True, carry_over_fraction=1.0, wetting_efficiency_fraction=0.5,
+             dc_start=20, outputs=["DC", "FWI", "DSR", "winter_pr", "season_mask"]),
+        dict(season_method=None, ffmc_start=70, dmc_start=10, dc_start=200, outputs=["FWI"]),
+    ]
+    for kw in cases:
+        asked = kw.pop("outputs")
+        extra = [o for o in asked if o in ("season_mask", "winter_pr")]
+        exp = FO.fire_weather_calc(*base, None, dc0, dmc0, ffmc0, wpr, outputs=FO.complete_indexes(
+            [o for o in asked if o not in extra]) + extra, **kw)
+        got = hb.run(*base, None, dc0, dmc0, ffmc0, wpr, outputs=asked, **kw)   # the library adds what it needs
+        assert set(got) == set(asked)
+        check_outputs(got, {k: np.asarray(exp[k]) for k in asked}, str(kw), exact_frac=0.99)
+    assert rng is not None
+
+
+def test_argument_checks_of_the_library():
+    inp = {k: (v[:4, :400] if getattr(v, "ndim", 0) == 2 else v[:400] if k == "mth" else v[:4]) for k, v in mg.cffwis_inputs().items()}
+    tc = lambda a: np.ascontiguousarray(a.T)   # noqa: E731
+    a = (tc(inp["tas"]), tc(inp["pr"]), None, None, None, inp["mth"], inp["lat"], None, None, None, None, None)
+    assert set(hb.run(*a, outputs=["DC"])) == {"DC"}
+    with pytest.raises(ValueError, match="hurs"):
+        hb.run(*a, outputs=["DMC"])
+    with pytest.raises(ValueError, match="overwintering"):
+        hb.run(*a, outputs=["DC"], overwintering=True)
+    with pytest.raises(ValueError, match="snd"):
+        hb.run(*a, outputs=["DC"], season_method="LA08")
+    with pytest.raises(ValueError, match="1..32"):
+        hb.run(*a, outputs=["DC"], season_method="WF93", temp_condition_days=40)
