@@ -487,6 +487,10 @@ typedef struct {
   float temp_start_thresh, temp_end_thresh, snow_thresh, prec_thresh, snow_min_mean_depth;
   float dc_start, dmc_start, ffmc_start, dc_dry_factor, dmc_dry_factor;
   double snow_min_cover_frac, carry_over_fraction, wetting_efficiency_fraction, min_dc;
+  /* unit conversion of the five series on load, value = raw * in_scale[i] + in_offset[i] in float32 (one
+   * rounding each, no fused multiply-add), i = tas, pr, hurs, ws, snd: what `convert_units_to` does to the
+   * arrays in `cffwis_indices` (:1369-1374), e.g. K -> degC {1, -273.15}, kg m-2 s-1 -> mm/day {86400, 0}. */
+  float in_scale[5], in_offset[5];
 } XcFwiParams;
 int32_t xc_fwi_f32(const float* tas, const float* pr, const float* hurs, const float* ws, const float* snd,
                    const uint8_t* season_mask_in, const int8_t* month, const double* lat,

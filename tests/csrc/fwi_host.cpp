@@ -30,13 +30,11 @@ extern "C" int32_t fwi_host_f32(const float* tas, const float* pr, const float* 
   a.DC = DC; a.DMC = DMC; a.FFMC = FFMC; a.ISI = ISI; a.BUI = BUI; a.FWI = FWI; a.DSR = DSR;
   a.mask_out = season_mask_out;
   a.winter_pr_out = winter_pr_out;
-  a.day_lengths = h_day_lengths;
-  a.day_length_factors = h_day_length_factors;
   const char* msg = fwi::check_args(a);
   if (msg) { g_msg = msg; return XC_ERR_INVALID; }
   for (int64_t c = 0; c < C; ++c) {
-    if (fwi::needs_rings(a.P)) fwi::run_cell<true>(a, c);
-    else fwi::run_cell<false>(a, c);
+    if (fwi::needs_rings(a.P)) fwi::run_cell<true>(a, c, h_day_lengths, h_day_length_factors);
+    else fwi::run_cell<false>(a, c, h_day_lengths, h_day_length_factors);
   }
   return XC_OK;
 }

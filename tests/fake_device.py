@@ -326,11 +326,54 @@ def dev_ints(arr, dtype, device):
     return torch.from_numpy(np.ascontiguousarray(np.asarray(arr, dtype=dtype)))
 
 
+def fire_weather(tas, pr, hurs, ws, snd, month, lat, season_mask, dc0, dmc0, ffmc0, winter_pr, outputs, params):
+    """The oracle day loop behind the argument list of ``device.fire_weather`` (``params``: _lib.FwiParams)."""
+    from oracle import fire_oracle as FO
+    P = params
+    season = {v: k for k, v in _lib.FWI_SEASONS.items()}[P.season_mode]
+    dry = {v: k for k, v in _lib.FWI_DRY_STARTS.items()}[P.dry_start]
+    ref = tas if tas is not None else pr
+    T, C = ref.shape
+
+    def series(x, i):
+        if x is None:
+            return np.full((T, C), np.nan, np.float32)
+        return (_np(x).astype(np.float32) * np.float32(P.in_scale[i]) + np.float32(P.in_offset[i])).astype(np.float32)
+
+    def state(x, fill):
+        return np.full(C, fill, np.float32) if x is None else _np(x).astype(np.float32)
+
+    codes = [o for o in outputs if o in FO._ORDER]
+    full = FO.complete_indexes(codes) if codes else []
+    extra = [o for o in outputs if o in ("season_mask", "winter_pr")]
+    if P.season_mode >= 2 and "season_mask" not in extra:
+        extra = extra + ["season_mask"]
+    kw = dict(season_method=season, overwintering=bool(P.overwintering), dry_start=dry,
+              initial_start_up=bool(P.initial_start_up), temp_start_thresh=P.temp_start_thresh,
+              temp_end_thresh=P.temp_end_thresh, snow_thresh=P.snow_thresh, prec_thresh=P.prec_thresh,
+              snow_min_mean_depth=P.snow_min_mean_depth, dc_start=P.dc_start, dmc_start=P.dmc_start,
+              ffmc_start=P.ffmc_start, dc_dry_factor=P.dc_dry_factor, dmc_dry_factor=P.dmc_dry_factor,
+              snow_min_cover_frac=P.snow_min_cover_frac, carry_over_fraction=P.carry_over_fraction,
+              wetting_efficiency_fraction=P.wetting_efficiency_fraction,
+              temp_condition_days=P.temp_condition_days, snow_condition_days=P.snow_condition_days,
+              snow_cover_days=P.snow_cover_days)
+    lat_h = np.zeros(C) if lat is None else np.asarray(lat, dtype=np.float64)
+    mask = None if season_mask is None else _np(season_mask).astype(bool)
+    res = FO.fire_weather_calc(series(tas, 0), series(pr, 1), series(hurs, 2), series(ws, 3), series(snd, 4),
+                               np.asarray(month), lat_h, mask, state(dc0, np.nan), state(dmc0, np.nan),
+                               state(ffmc0, np.nan), state(winter_pr, 0.0), outputs=full + extra, **kw)
+    out = {}
+    for name in outputs:
+        a = np.asarray(res[name])
+        out[name] = torch.from_numpy(np.ascontiguousarray(a.astype(np.uint8) if name == "season_mask" else a))
+    return out
+
+
 FUNCTIONS = [to_time_cell, period_count, period_runstat, period_runstat_gap, period_reduce, rolling_period_reduce,
              spell_runstat, period_run_maxsum, period_runstat2, percentile_doy, doy_interp, doy_threshold_count,
              mask_steps, dev_ints, period_boundary_run, period_boundary_run_range, bootstrap_doy_count, eqm_train,
              eqm_adjust, period_run_quantile, table_cell_major, period_multi, period_count_arr, spell_mask, transpose_f64,
-             rolling_period_reduce_sel]
+             rolling_period_reduce_sel, fire_weather]
 
 
 def install(monkeypatch):

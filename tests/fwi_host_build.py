@@ -19,7 +19,8 @@ class XcFwiParams(ctypes.Structure):
                                                  "snow_min_mean_depth", "dc_start", "dmc_start", "ffmc_start",
                                                  "dc_dry_factor", "dmc_dry_factor")]
                 + [(n, ctypes.c_double) for n in ("snow_min_cover_frac", "carry_over_fraction",
-                                                  "wetting_efficiency_fraction", "min_dc")])
+                                                  "wetting_efficiency_fraction", "min_dc")]
+                + [("in_scale", ctypes.c_float * 5), ("in_offset", ctypes.c_float * 5)])
 
 
 def load():
@@ -60,6 +61,8 @@ def params(season_method=None, overwintering=False, dry_start=None, initial_star
               "wetting_efficiency_fraction"):
         setattr(P, k, float(p[k]))
     P.min_dc = float(p["dc_start"])
+    for i, (sc, of) in enumerate(p.get("in_affine", [(1.0, 0.0)] * 5)):
+        P.in_scale[i], P.in_offset[i] = sc, of
     return P
 
 

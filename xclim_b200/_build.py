@@ -26,6 +26,10 @@ NVCC_FLAGS = [
 ]
 
 
+#: per-file flags.  fwi.cu mirrors numba / numpy arithmetic, which never fuses a multiply with an add.
+EXTRA_FLAGS = {"fwi.cu": ["-fmad=false"]}
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -53,7 +57,8 @@ def build_variant(tag: str, defines: list[str]) -> str:
     objs = []
     for src in sources():
         obj = os.path.join(odir, os.path.basename(src)[:-3] + ".o")
-        r = subprocess.run([nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", src, "-o", obj],
+        r = subprocess.run([nvcc, *NVCC_FLAGS, *EXTRA_FLAGS.get(os.path.basename(src), []),
+                            *[f"-D{d}" for d in defines], "-c", src, "-o", obj],
                            capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(r.stderr)
@@ -85,7 +90,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *EXTRA_FLAGS.get(os.path.basename(src), []), "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".ptxas.log")
         with open(log, "w") as f:

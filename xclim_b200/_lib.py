@@ -66,6 +66,7 @@ SIGNATURES = {
     "xc_table_cell_major_f64": (_i32, [_vp, _i32, _i32, _i64, _vp, _vp]),
     "xc_host_pinned": (_i32, [_vp]),
     "xc_copy_box_async": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp]),
+    "xc_fwi_f32": (_i32, [_vp] * 12 + [_i64, _i64, _i64, _vp] + [_vp] * 9 + [_vp]),
     "xc_period_runstat_f32_host": (_i32, [_vp, _i64, _i64, _vp, _i32, _i32, _f64, _i32, _i32, _i32, _vp, _vp,
                                           _vp, _i64]),
 }
@@ -99,6 +100,21 @@ class MultiPlan(C.Structure):
                 ("msum", MultiMaxSum * MULTI_MAX_MSUM), ("sums", MultiSum * MULTI_MAX_SUMS),
                 ("slot_sum", _i32), ("slot_mean", _i32), ("slot_min", _i32), ("slot_max", _i32)]
 
+
+class FwiParams(C.Structure):
+    """include/xclim_b200.h XcFwiParams."""
+    _fields_ = ([(n, _i32) for n in ("season_mode", "overwintering", "dry_start", "initial_start_up",
+                                     "temp_condition_days", "snow_condition_days", "snow_cover_days")]
+                + [(n, C.c_float) for n in ("temp_start_thresh", "temp_end_thresh", "snow_thresh", "prec_thresh",
+                                            "snow_min_mean_depth", "dc_start", "dmc_start", "ffmc_start",
+                                            "dc_dry_factor", "dmc_dry_factor")]
+                + [(n, _f64) for n in ("snow_min_cover_frac", "carry_over_fraction", "wetting_efficiency_fraction",
+                                       "min_dc")]
+                + [("in_scale", C.c_float * 5), ("in_offset", C.c_float * 5)])
+
+
+FWI_SEASONS = {None: 0, "mask": 1, "WF93": 2, "LA08": 3, "GFWED": 4}
+FWI_DRY_STARTS = {None: 0, "CFS": 1, "GFWED": 2, "GFWED+SNOW": 3}
 
 _lib = None
 

@@ -23,12 +23,10 @@ __constant__ double c_day_lengths[60] = XC_FWI_DAY_LENGTHS;
 __constant__ double c_day_length_factors[36] = XC_FWI_DAY_LENGTH_FACTORS;
 
 template <bool RINGS>
-__global__ void __launch_bounds__(kThreads) fwi_kernel(fwi::Args a) {
+__global__ void __launch_bounds__(kThreads) fwi_kernel(const __grid_constant__ fwi::Args a) {
   const int64_t c = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (c >= a.C) return;
-  a.day_lengths = c_day_lengths;
-  a.day_length_factors = c_day_length_factors;
-  fwi::run_cell<RINGS>(a, c);
+  fwi::run_cell<RINGS>(a, c, c_day_lengths, c_day_length_factors);
 }
 
 }  // namespace

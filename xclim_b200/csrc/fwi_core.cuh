@@ -203,7 +203,6 @@ struct Args {
   float *DC, *DMC, *FFMC, *ISI, *BUI, *FWI, *DSR;
   uint8_t* mask_out;
   float* winter_pr_out;
-  const double *day_lengths, *day_length_factors;   // the two tables (device constant memory / host)
 };
 
 struct Rings {              // GFWED season means and the snow-cover history of the "SNOW" dry start
@@ -219,8 +218,9 @@ struct NoRings {};
 
 // One cell through all T days: the loop of _fire_weather_calc (:721-866) with the season masks of
 // _fire_season (:636-675) computed on the way.  RINGS = the modes that need window means.
+// day_lengths / day_length_factors: the two tables (device constant memory / host statics).
 template <bool RINGS>
-XC_FWI_HD void run_cell(const Args& a, int64_t c) {
+XC_FWI_HD void run_cell(const Args& a, int64_t c, const double* day_lengths, const double* day_length_factors) {
   const XcFwiParams& P = a.P;
   const int want = a.want;
   const bool always = P.season_mode == XC_FWI_SEASON_ALWAYS;
@@ -233,8 +233,8 @@ XC_FWI_HD void run_cell(const Args& a, int64_t c) {
 
   const double lat = a.lat ? a.lat[c] : 0.0;
   const int band = day_length_band(lat), fband = day_length_factor_band(lat);
-  const double* dl_row = a.day_lengths + 12 * (band < 0 ? 0 : band);
-  const double* fl_row = a.day_length_factors + 12 * (fband < 0 ? 0 : fband);
+  const double* dl_row = day_lengths + 12 * (band < 0 ? 0 : band);
+  const double* fl_row = day_length_factors + 12 * (fband < 0 ? 0 : fband);
   const bool bad_lat = band < 0;   // the reference raises ValueError("Invalid lat specified."): NaN codes here
 
   // previous codes (:683-693, 709-718)
@@ -261,11 +261,12 @@ XC_FWI_HD void run_cell(const Args& a, int64_t c) {
   const int64_t ldx = a.ldx;
   for (int64_t it = 0; it < a.T; ++it) {
     const int64_t off = it * ldx + c;
-    const float tas = a.tas ? XC_FWI_LD(a.tas + off) : nan_f;
-    const float pr = a.pr ? XC_FWI_LD(a.pr + off) : nan_f;
-    const float hurs = a.hurs ? XC_FWI_LD(a.hurs + off) : nan_f;
-    const float ws = a.ws ? XC_FWI_LD(a.ws + off) : nan_f;
-    const float snd = a.snd ? XC_FWI_LD(a.snd + off) : nan_f;
+    // load + unit conversion (cffwis_indices :1369-1374: one float32 operation per array)
+    const float tas = a.tas ? XC_FWI_LD(a.tas + off) * P.in_scale[0] + P.in_offset[0] : nan_f;
+    const float pr = a.pr ? XC_FWI_LD(a.pr + off) * P.in_scale[1] + P.in_offset[1] : nan_f;
+    const float hurs = a.hurs ? XC_FWI_LD(a.hurs + off) * P.in_scale[2] + P.in_offset[2] : nan_f;
+    const float ws = a.ws ? XC_FWI_LD(a.ws + off) * P.in_scale[3] + P.in_offset[3] : nan_f;
+    const float snd = a.snd ? XC_FWI_LD(a.snd + off) * P.in_scale[4] + P.in_offset[4] : nan_f;
     const int mth = a.month[it];
 
     // ---- season mask of the day (:636-675) ----

@@ -460,3 +460,64 @@ def period_multi(x2d, poff, plan, n_slots):
     check(load().xc_period_multi_f32(x2d.data_ptr(), T, C, x2d.stride(0), poff_d.data_ptr(), P, ctypes.byref(plan),
                                      out.data_ptr(), int(n_slots), current_stream_ptr()))
     return out
+
+
+# ------------------------------------------------------------------------------------ fire weather
+FWI_OUTPUTS = ("DC", "DMC", "FFMC", "ISI", "BUI", "FWI", "DSR")
+
+
+def fwi_params(season_method=None, overwintering=False, dry_start=None, initial_start_up=True, in_affine=None, **p):
+    """``_lib.FwiParams`` from the keyword parameters of ``fire_weather_ufunc`` (indices/fire/_cffwis.py:161-178:
+    thresholds compare in float32 with the float32 data, as numpy does for Python scalars)."""
+    P = _lib.FwiParams()
+    P.season_mode = _lib.FWI_SEASONS[season_method]
+    P.dry_start = _lib.FWI_DRY_STARTS[dry_start]
+    P.overwintering, P.initial_start_up = int(bool(overwintering)), int(bool(initial_start_up))
+    for k in ("temp_condition_days", "snow_condition_days", "snow_cover_days"):
+        setattr(P, k, int(p[k]))
+    for k in ("temp_start_thresh", "temp_end_thresh", "snow_thresh", "prec_thresh", "snow_min_mean_depth", "dc_start",
+              "dmc_start", "ffmc_start", "dc_dry_factor", "dmc_dry_factor", "snow_min_cover_frac", "carry_over_fraction",
+              "wetting_efficiency_fraction"):
+        setattr(P, k, float(p[k]))
+    P.min_dc = float(p["dc_start"])
+    for i, (scale, offset) in enumerate(in_affine or [(1.0, 0.0)] * 5):   # tas, pr, hurs, ws, snd
+        P.in_scale[i], P.in_offset[i] = scale, offset
+    return P
+
+
+def fire_weather(tas, pr, hurs, ws, snd, month, lat, season_mask, dc0, dmc0, ffmc0, winter_pr, outputs, params):
+    """The fire-weather day loop on ``(T, C)`` float32 device series (``xc_fwi_f32``).
+
+    ``month`` int8[T] and ``lat`` float64[C] host arrays; ``season_mask`` (T, C) uint8 / previous codes (C,)
+    float32 device tensors or None.  ``outputs``: names among DC..DSR, "season_mask", "winter_pr".
+    Returns a dict name -> device tensor.
+    """
+    import ctypes
+    ref = tas if tas is not None else pr
+    T, C = ref.shape
+    dev = ref.device
+    ld = ref.stride(0)
+    for x in (tas, pr, hurs, ws, snd):
+        if x is not None and (tuple(x.shape) != (T, C) or x.stride(0) != ld or x.dtype != torch.float32):
+            raise ValueError("fire_weather: the inputs must share their (T, C) float32 layout")
+    if season_mask is not None and (tuple(season_mask.shape) != (T, C) or season_mask.dtype != torch.uint8
+                                    or season_mask.stride(0) != ld):
+        raise ValueError("fire_weather: season_mask must be (T, C) uint8 with the layout of the inputs")
+    month_d = dev_ints(np.asarray(month, dtype=np.int8), np.int8, dev)
+    lat_d = None if lat is None else torch.from_numpy(np.ascontiguousarray(lat, dtype=np.float64)).to(dev)
+    out = {}
+    for name in outputs:
+        if name in FWI_OUTPUTS:      # outputs use the leading dimension of the inputs
+            out[name] = torch.empty((T, ld), dtype=torch.float32, device=dev)[:, :C]
+        elif name == "season_mask":
+            out[name] = torch.empty((T, ld), dtype=torch.uint8, device=dev)[:, :C]
+        elif name == "winter_pr":
+            out[name] = torch.empty(C, dtype=torch.float32, device=dev)
+        else:
+            raise ValueError(f"unknown fire weather output {name!r}")
+    optr = [_ptr(out.get(n)) for n in FWI_OUTPUTS]
+    check(load().xc_fwi_f32(_ptr(tas), _ptr(pr), _ptr(hurs), _ptr(ws), _ptr(snd), _ptr(season_mask), month_d.data_ptr(),
+                            _ptr(lat_d), _ptr(dc0), _ptr(dmc0), _ptr(ffmc0), _ptr(winter_pr), T, C, ld,
+                            ctypes.byref(params), *optr, _ptr(out.get("season_mask")), _ptr(out.get("winter_pr")),
+                            current_stream_ptr()))
+    return out
