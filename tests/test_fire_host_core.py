@@ -1,6 +1,6 @@
 """The DEVICE code of the fire-weather kernel (xclim_b200/csrc/fwi_core.cuh), compiled for the host, against
 the reference fixtures and the oracle.  The CUDA kernel adds only the thread-to-cell mapping to this code
-(xclim_b200/csrc/fwi.cu); its run on a GPU is tests/test_zz_gpu_fire.py."""
+(xclim_b200/csrc/fwi.cu); its run on a GPU is tests/test_zzz_gpu_fire.py."""
 import numpy as np
 import pytest
 

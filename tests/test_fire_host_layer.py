@@ -1,6 +1,6 @@
 """Host layer of the fire-weather path (xclim_b200/fire.py) on the oracle-backed device stand-in: argument
 handling, unit conversion folded into the kernel parameters, output wrapping, reference errors.  The same
-bodies run on the GPU in tests/test_zz_gpu_fire.py."""
+bodies run on the GPU in tests/test_zzz_gpu_fire.py."""
 import numpy as np
 import pytest
 

