@@ -304,7 +304,7 @@ def eqm_section(ctx):
                     f"lat-tiled over {ctx.world} rank(s)",
         "value": cells_total / ((ms_train + ms_adj) * 1e-3), "unit": "grid-cells/s", "ms_train": ms_train,
         "ms_adjust": ms_adj, "steps": steps,
-        "roofline_train": roofline(ctx, alg, ms_train, "eqm_train_kernel", tile),
+        "roofline_train": roofline(ctx, alg, ms_train, "eqm_train_group_kernel<32 cells per CTA> (xc_eqm_train_f32 default dispatch)", tile),
         "roofline_adjust": roofline(ctx, alg, ms_adj, "eqm_adjust_kernel", tile),
         "cpu_baseline": {"value": sel.size / dt, "unit": "grid-cells/s", "cores": 1, "kind": "port",
                          "sample": f"(10950, {sel.size}) cells, train + adjust restatement, {dt:.2f} s"},
