@@ -114,3 +114,40 @@ def test_fire_host_layer_on_the_oracle_backed_device(monkeypatch):
     from xclim_b200 import Field, fire
     fake_device.install(monkeypatch)
     check_bodies(fire, Field)
+
+
+def test_fire_weather_streams_in_lat_slabs(monkeypatch, tmp_path):
+    import fake_stream
+    check_streaming(tmp_path, fake_stream.install(monkeypatch))
+
+
+def check_streaming(tmp_path, lib=None):
+    """File-backed inputs -> slab streamer -> every output of the multi-output call assembled on the host.
+    Shared with the GPU test (``lib``: the recording stand-in of the C ABI on the CPU, None on the GPU)."""
+    import xclim_b200
+    from xclim_b200 import Field, fire, io
+    f, lat, _ = fields(T=400)
+    lazy = {}
+    for k in ("tas", "pr", "hurs", "ws", "snd"):
+        f[k].coords["lat"] = lat
+        lazy[k] = io.open_field(io.save_zarr(str(tmp_path / f"{k}.zarr"), f[k], name=k, chunks=(200, 2, 4), compressor=None))
+    latF = Field(lat, ("lat",), None, {}, {"units": "degrees_north"})
+    dc0 = np.linspace(50, 400, 16, dtype=np.float32).reshape(4, 4)
+    kw = dict(lat=latF, dc0=dc0, season_method="LA08", overwintering=True)
+    ref = fire.fire_weather_ufunc(tas=f["tas"], pr=f["pr"], hurs=f["hurs"], sfcWind=f["ws"], snd=f["snd"], **kw)
+    row = 400 * 4 * 4
+    with xclim_b200.set_options(stream_min_bytes=0, stream_slab_bytes=row):
+        got = fire.fire_weather_ufunc(tas=lazy["tas"], pr=lazy["pr"], hurs=lazy["hurs"], sfcWind=lazy["ws"],
+                                      snd=lazy["snd"], **kw)
+        ci = fire.cffwis_indices(lazy["tas"], lazy["pr"], lazy["ws"], lazy["hurs"], latF)
+    # slabs follow the 2-row chunks of the stores: 2 slabs x 5 inputs, then 2 slabs x 4 inputs (no snd)
+    assert lib is None or len([b for b in lib.boxes if b[2] == 1]) == 2 * 5 + 2 * 4
+    assert list(got) == list(ref) == ["DC", "DMC", "FFMC", "ISI", "BUI", "FWI", "DSR", "season_mask", "winter_pr"]
+    for k in ref:
+        assert got[k].dims == ref[k].dims and isinstance(got[k].values, np.ndarray), k
+        np.testing.assert_array_equal(got[k].values, np.asarray(ref[k].values), err_msg=k)
+    np.testing.assert_array_equal(got["DC"].coords["lat"], lat)
+    cj = fire.cffwis_indices(f["tas"], f["pr"], f["ws"], f["hurs"], latF)
+    assert type(ci).__name__ == "CFFWISIndices"
+    for a, b in zip(ci, cj):
+        np.testing.assert_array_equal(a.values, np.asarray(b.values))

@@ -215,3 +215,50 @@ def test_streamer_reads_lazy_sources_slab_by_slab(tmp_path, monkeypatch, kind):
     back = io.open_field(io.save_netcdf3(str(tmp_path / "cdd.nc"), out, name="cdd", calendar="noleap"))
     np.testing.assert_array_equal(np.asarray(back.values), ref_cdd.values)
     assert back.attrs["units"] == "days"
+
+
+def test_slab_output_device_leg_and_multi_output_containers(monkeypatch):
+    """The D2H leg of the streamer (one strided box per slab result into the page-locked result array) and the
+    rebuilding of dict / namedtuple results, on the CPU stand-ins."""
+    import collections
+
+    import torch
+
+    import fake_stream
+    from xclim_b200 import Field, streaming
+    lib = fake_stream.install(monkeypatch)
+    rng = np.random.default_rng(12)
+    full = rng.standard_normal((5, 11, 7)).astype(np.float32)          # (periods, lat, lon)
+    flat = rng.integers(0, 9, size=(11, 7)).astype(np.int32)           # (lat, lon): no time dimension
+    template = Field(np.zeros((3, 11, 7), np.float32), ("time", "lat", "lon"), None, {"lat": np.arange(11.0)}, {})
+
+    def part(r0, r1):
+        return {"a": Field(torch.from_numpy(full[:, r0:r1].copy()), ("time", "lat", "lon"), None, {"time": list("abcde")},
+                           {"units": "K"}),
+                "b": Field(torch.from_numpy(flat[r0:r1].copy()), ("lat", "lon"), None, {}, {"units": ""})}
+
+    outs = {}
+    keep = []
+    for r0, r1 in ((0, 4), (4, 8), (8, 11)):
+        parts, rebuild = streaming._result_parts(test_plan_slabs_follow_chunk_edges, part(r0, r1))
+        for name, p in parts:
+            if name not in outs:
+                outs[name] = streaming._SlabOutput(test_plan_slabs_follow_chunk_edges, p, "lat", 11, name)
+            outs[name].put(p, r0, r1, lib, fake_stream._Stream(), fake_stream._Stream(), keep)
+    res = rebuild({n: o.finish(template, "lat") for n, o in outs.items()})
+    assert list(res) == ["a", "b"] and res["a"].dims == ("time", "lat", "lon") and res["b"].dims == ("lat", "lon")
+    np.testing.assert_array_equal(res["a"].values, full)
+    np.testing.assert_array_equal(res["b"].values, flat)
+    assert res["b"].values.dtype == np.int32 and res["a"].attrs == {"units": "K"}
+    np.testing.assert_array_equal(res["a"].coords["lat"], np.arange(11.0))
+    # device -> host boxes: 5 rows of (r1 - r0) * 7 * 4 bytes for "a", one row for "b"
+    assert [b for b in lib.boxes if b[2] == 0][:2] == [(4 * 7 * 4, 5, 0), (4 * 7 * 4, 1, 0)]
+    # containers
+    Pair = collections.namedtuple("Pair", ["x", "y"])
+    fa, fb = part(0, 11)["a"], part(0, 11)["b"]
+    parts, rebuild = streaming._result_parts(len, Pair(fa, fb))
+    assert [n for n, _ in parts] == [0, 1] and isinstance(rebuild({0: 1, 1: 2}), Pair)
+    parts, rebuild = streaming._result_parts(len, fa)
+    assert parts == [(None, fa)] and rebuild({None: 7}) == 7
+    with pytest.raises(TypeError, match="cannot stream"):
+        streaming._result_parts(len, 3)

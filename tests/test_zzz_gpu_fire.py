@@ -68,3 +68,8 @@ def test_host_layer_on_device(cuda):
     from test_fire_host_layer import check_bodies
     from xclim_b200 import Field, fire
     check_bodies(fire, Field)
+
+
+def test_fire_weather_streams_from_files_on_device(cuda, tmp_path):
+    from test_fire_host_layer import check_streaming
+    check_streaming(tmp_path)

@@ -190,6 +190,21 @@ def _unwrap_mask(mask):
     return t.reshape(t.shape[0], -1).contiguous(), cell_shape, None, None
 
 
+def _label_per_cell(obj, template):
+    """Per-cell arguments given as bare arrays get the spatial dims of the series, so that the slab streamer
+    can cut them along the leading spatial dimension together with the series."""
+    if obj is None or isinstance(obj, Field) or is_xarray(obj):
+        return obj
+    space = tuple(d for d in dims_of(template) if d != "time")
+    shape = tuple(n for d, n in zip(dims_of(template), template.shape) if d != "time")
+    a = np.asarray(obj)
+    if a.shape == shape:
+        return Field(a, space, None, {}, {})
+    if a.ndim == 1 and space and a.shape[0] == shape[0]:
+        return Field(a, space[:1], None, {}, {})
+    return obj                                   # scalars and other broadcastable shapes: used whole
+
+
 def fire_weather_ufunc(*, tas, pr, hurs=None, sfcWind=None, snd=None, lat=None, dc0=None, dmc0=None, ffmc0=None,
                        winter_pr=None, season_mask=None, start_dates=None, indexes=None, season_method=None,
                        overwintering=False, dry_start=None, initial_start_up=True, _affine_of=None, **params):
@@ -197,8 +212,21 @@ def fire_weather_ufunc(*, tas, pr, hurs=None, sfcWind=None, snd=None, lat=None, 
 
     ``tas`` degC, ``pr`` mm/day, ``hurs`` %, ``sfcWind`` km/h, ``snd`` m.  Returns a dict of the indexes
     asked for plus the ones they depend on (:1046-1057), ``season_mask`` when it is computed here and
-    ``winter_pr`` under overwintering, like the reference.
+    ``winter_pr`` under overwintering, like the reference.  Host-backed series beyond the streaming
+    threshold go through the slab streamer (every output is assembled on the host slab by slab), as for
+    the other indices.
     """
+    from .streaming import streamed
+    lat, dc0, dmc0, ffmc0, winter_pr = (_label_per_cell(v, tas) for v in (lat, dc0, dmc0, ffmc0, winter_pr))
+    return streamed(_fire_weather)(tas=tas, pr=pr, hurs=hurs, sfcWind=sfcWind, snd=snd, lat=lat, dc0=dc0, dmc0=dmc0,
+                                   ffmc0=ffmc0, winter_pr=winter_pr, season_mask=season_mask, indexes=indexes,
+                                   season_method=season_method, overwintering=overwintering, dry_start=dry_start,
+                                   initial_start_up=initial_start_up, _affine_of=_affine_of, **params)
+
+
+def _fire_weather(*, tas, pr, hurs=None, sfcWind=None, snd=None, lat=None, dc0=None, dmc0=None, ffmc0=None,
+                  winter_pr=None, season_mask=None, indexes=None, season_method=None, overwintering=False,
+                  dry_start=None, initial_start_up=True, _affine_of=None, **params):
     want = set(indexes or _ORDER)
     unknown = want - set(_ORDER)
     if unknown:

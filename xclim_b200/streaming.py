@@ -196,10 +196,9 @@ def run_streamed(fn, args, kwargs, lead, shape, series, tables):
                                             n_lead * rest * 4, w, T, 1, s_copy.cuda_stream))
         copied[b].record(s_copy)
 
-    out_host = None
-    out_axis = None
     template = next(iter(series.values()))
-    result_meta = None
+    outs: dict = {}                               # one _SlabOutput per result of the call
+    shape_of = None                               # how to rebuild the result container (Field / tuple / dict)
     keep = []                                     # device results stay alive until their D2H has run
     submit_stage(0)
     submit_stage(1)
@@ -227,50 +226,89 @@ def run_streamed(fn, args, kwargs, lead, shape, series, tables):
                     k2[key[1]] = f
             res = fn(*a2, **k2)
             done[b].record(comp)
-            if not isinstance(res, Field):
-                raise TypeError(f"{getattr(fn, '__name__', fn)} returned {type(res).__name__}: cannot stream it")
-            vals = res.values
-            rdims = tuple(res.dims)
-            if out_host is None:
-                if lead not in rdims:
-                    raise ValueError(f"the result of {fn.__name__} has no `{lead}` dimension: cannot stream it")
-                out_axis = rdims.index(lead)
-                vshape = tuple(vals.shape)
-                full = vshape[:out_axis] + (n_lead,) + vshape[out_axis + 1:]
-                np_dtype = np.dtype(str(vals.dtype).replace("torch.", "")) if hasattr(vals, "is_cuda") else vals.dtype
-                nbytes = int(np.prod(full, dtype=np.int64)) * np_dtype.itemsize
-                result_meta = res
-                if nbytes >= (256 << 20):
-                    # large results (percentile tables): the result array itself is page-locked, the slabs
-                    # land in it directly (numpy keeps the torch storage alive through the buffer protocol)
-                    own = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
-                    out_host = stage_np = own.numpy().view(np_dtype).reshape(full)
-                else:
-                    out_host = np.empty(full, dtype=np_dtype)
-                    out_stage = _pinned("out", nbytes)
-                    stage_np = out_stage[:nbytes].numpy().view(np_dtype).reshape(full)
-            A = int(np.prod(out_host.shape[:out_axis], dtype=np.int64))
-            B = int(np.prod(out_host.shape[out_axis + 1:], dtype=np.int64)) * out_host.itemsize
-            if hasattr(vals, "is_cuda") and vals.is_cuda:
-                vals = vals.contiguous()
-                keep.append(vals)
-                s_out.wait_stream(comp)
-                dst = stage_np.ctypes.data + r0 * B
-                check(lib.xc_copy_box_async(dst, n_lead * B, vals.data_ptr(), (r1 - r0) * B, (r1 - r0) * B, A, 0,
-                                            s_out.cuda_stream))
-            else:   # the index returned host values (e.g. percentile tables)
-                idx = [slice(None)] * out_host.ndim
-                idx[out_axis] = slice(r0, r1)
-                stage_np[tuple(idx)] = np.asarray(vals)
+            parts, shape_of = _result_parts(fn, res)
+            for name, part in parts:
+                if name not in outs:
+                    outs[name] = _SlabOutput(fn, part, lead, n_lead, name)
+                outs[name].put(part, r0, r1, lib, comp, s_out, keep)
     s_out.synchronize()
     comp.synchronize()
     s_copy.synchronize()
     if pool is not None:
         pool.shutdown(wait=True)
-    if out_host is not stage_np:
-        np.copyto(out_host, stage_np)
     del keep
-    return _assemble(template, result_meta, out_host, lead)
+    done_parts = {name: o.finish(template, lead) for name, o in outs.items()}
+    return shape_of(done_parts)
+
+
+def _result_parts(fn, res):
+    """``[(name, Field), ...]`` of what an index returned and the function that rebuilds the same kind of
+    container from ``{name: assembled}``: a single Field, a (named) tuple of Fields (``cffwis_indices``) or a
+    dict of Fields (``fire_weather_ufunc``)."""
+    if isinstance(res, Field):
+        return [(None, res)], lambda d: d[None]
+    if isinstance(res, dict) and res and all(isinstance(v, Field) for v in res.values()):
+        names = list(res)
+        return list(res.items()), lambda d: {n: d[n] for n in names}
+    if isinstance(res, tuple) and res and all(isinstance(v, Field) for v in res):
+        n = len(res)
+        rebuild = (lambda d: type(res)(*(d[i] for i in range(n)))) if hasattr(res, "_fields") else \
+            (lambda d: tuple(d[i] for i in range(n)))
+        return list(enumerate(res)), rebuild
+    raise TypeError(f"{getattr(fn, '__name__', fn)} returned {type(res).__name__}: cannot stream it")
+
+
+def _on_device(vals) -> bool:
+    return bool(getattr(vals, "is_cuda", False))
+
+
+class _SlabOutput:
+    """The host array one result of a streamed call is assembled in, slab by slab."""
+
+    def __init__(self, fn, res, lead, n_lead, name):
+        import torch
+        vals = res.values
+        rdims = tuple(res.dims)
+        if lead not in rdims:
+            raise ValueError(f"the result of {fn.__name__} has no `{lead}` dimension: cannot stream it")
+        self.axis = rdims.index(lead)
+        self.n_lead = n_lead
+        vshape = tuple(vals.shape)
+        full = vshape[:self.axis] + (n_lead,) + vshape[self.axis + 1:]
+        np_dtype = np.dtype(str(vals.dtype).replace("torch.", "")) if hasattr(vals, "is_cuda") else vals.dtype
+        nbytes = int(np.prod(full, dtype=np.int64)) * np_dtype.itemsize
+        self.meta = res
+        if nbytes >= (256 << 20):
+            # large results (percentile tables, daily series): the result array itself is page-locked, the slabs
+            # land in it directly (numpy keeps the torch storage alive through the buffer protocol)
+            own = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            self.host = self.stage = own.numpy().view(np_dtype).reshape(full)
+        else:
+            self.host = np.empty(full, dtype=np_dtype)
+            out_stage = _pinned("out" if name is None else f"out_{name}", nbytes)
+            self.stage = out_stage[:nbytes].numpy().view(np_dtype).reshape(full)
+
+    def put(self, res, r0, r1, lib, comp, s_out, keep):
+        from ._lib import check
+        vals = res.values
+        A = int(np.prod(self.host.shape[:self.axis], dtype=np.int64))
+        B = int(np.prod(self.host.shape[self.axis + 1:], dtype=np.int64)) * self.host.itemsize
+        if _on_device(vals):
+            vals = vals.contiguous()
+            keep.append(vals)
+            s_out.wait_stream(comp)
+            dst = self.stage.ctypes.data + r0 * B
+            check(lib.xc_copy_box_async(dst, self.n_lead * B, vals.data_ptr(), (r1 - r0) * B, (r1 - r0) * B, A, 0,
+                                        s_out.cuda_stream))
+        else:   # the index returned host values (e.g. percentile tables)
+            idx = [slice(None)] * self.host.ndim
+            idx[self.axis] = slice(r0, r1)
+            self.stage[tuple(idx)] = np.asarray(vals)
+
+    def finish(self, template, lead):
+        if self.host is not self.stage:
+            np.copyto(self.host, self.stage)
+        return _assemble(template, self.meta, self.host, lead)
 
 
 def _assemble(template, res, values, lead):
