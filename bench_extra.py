@@ -201,6 +201,43 @@ def main():
             haf, hhq = O.eqm_train(host["tas"], host["hist"], 20, "+")
         report("eqm_adjust linear (sim -> scen)", ms, 2 * T * C * 4 + 2 * 20 * C * 4,
                cpu=lambda: O.eqm_adjust(host["hist"], haf, hhq, "+", "linear"))
+    if want("fwi") and a.only:      # the fire-weather kernel: opt-in (--only fwi), never part of a default run
+        import time
+
+        from xclim_b200 import fire
+        # degC / mm/d / % / km/h series from the generators above; humidity and wind from hashed noise
+        tas_c = tas - 273.15
+        hurs = device.synth(T, C, kind=1, seed=11, cells_per_lat=X, n_lat_global=a.lat)
+        hurs = ((hurs - hurs.mean()) * 4.0 + 55.0).clamp_(5.0, 100.0)
+        ws = (device.synth(T, C, kind=1, seed=12, cells_per_lat=X, n_lat_global=a.lat) - 270.0).abs_().mul_(0.5)
+        month = (np.minimum((np.arange(T) % YEAR) // 30.42, 11) + 1).astype(np.int8)
+        lat = np.repeat(np.linspace(-60, 75, a.lat), X)
+        p = {k: (v if not isinstance(v, tuple) else v[0]) for k, v in fire.default_params.items()}
+        for label, outs, kw in (
+                ("fwi always-on, 6 outputs", ["DC", "DMC", "FFMC", "ISI", "BUI", "FWI"], {}),
+                ("fwi WF93 season, 6 outputs + mask", ["DC", "DMC", "FFMC", "ISI", "BUI", "FWI", "season_mask"],
+                 {"season_method": "WF93"}),
+                ("fwi drought code only", ["DC"], {})):
+            P = device.fwi_params(kw.get("season_method"), False, None, True, **p)
+            need = [tas_c, pr] + ([hurs, ws] if len(outs) > 1 else [None, None])
+            run = lambda: device.fire_weather(need[0], need[1], need[2], need[3], None, month, lat, None, None, None,  # noqa: E731
+                                              None, None, outs, P)
+            ms = timeit(run, a.steps)
+            n_in = sum(x is not None for x in need)
+            n_out = sum(o != "season_mask" for o in outs)
+            extra = {"bound": "FP64 pipe (about twenty float64 transcendentals per element)"}
+            if a.cpu:
+                from oracle import fire_oracle as FO
+                Sf = min(S, 256)
+                hh = [None if x is None else x[:, :Sf].cpu().numpy() for x in need]
+                t0 = time.perf_counter()
+                FO.fire_weather_calc(hh[0], hh[1], hh[2], hh[3], None, month, lat[:Sf], None,
+                                     *(np.full(Sf, np.nan, np.float32),) * 3, np.zeros(Sf, np.float32),
+                                     outputs=FO.complete_indexes([o for o in outs if o != "season_mask"])
+                                     + (["season_mask"] if "season_mask" in outs else []), **kw)
+                dt = time.perf_counter() - t0
+                extra["cpu_port"] = {"cells_per_s": Sf / dt, "cores": 1, "kind": "port", "sample": f"({T}, {Sf}) cells, {dt:.1f} s"}
+            report(label, ms, (n_in + n_out) * T * C * 4 + (T * C if "season_mask" in outs else 0), extra)
 
 
 if __name__ == "__main__":
