@@ -169,7 +169,7 @@ def test_spell_length_statistics_min_gap(cuda, min_gap, op, thr):
             exp = O.spell_length_statistics(x, thr, 1, None, op, red, poff, min_gap=min_gap)
             np.testing.assert_array_equal(got.values, exp, err_msg=f"{min_gap} {op} {red} {freq}")
     with pytest.raises(NotImplementedError):
-        generic.spell_length_statistics(da, thr, 3, "sum", op, "max", "YS", min_gap=2)
+        generic.spell_length_statistics(da, thr, 3, "sum", op, "max", "YS", min_gap=2, resample_before_rl=False)
 
 
 def test_eqm_train_group_kernels_match_one_cell_kernel(cuda, monkeypatch):

@@ -58,7 +58,12 @@ def test_unit_strings_and_operator_validation(host):
     with pytest.raises(ValueError, match="not permitted"):
         generic.threshold_count(da, "==", 1.0, "YS", constrain=(">", ">="))
     with pytest.raises(NotImplementedError):
-        generic.spell_length_statistics(da, 1.0, 3, "sum", "<", "max", "YS", min_gap=2)
+        generic.spell_length_statistics(da, 1.0, 3, "sum", "<", "max", "YS", min_gap=2, resample_before_rl=False)
+    for wr, op_, thr_ in (("sum", "<", 1.0), ("min", ">=", 0.5), ("mean", ">", 2.0)):      # window > 1 with min_gap
+        out = generic.spell_length_statistics(da, thr_, 3, wr, op_, ["max", "count"], "YS", min_gap=3)
+        for o, red in zip(out, ("max", "count")):
+            exp = O.spell_length_statistics(pr, thr_, 3, wr, op_, red, da.time.period_offsets("YS"), min_gap=3)
+            np.testing.assert_array_equal(o.values, exp, err_msg=f"{wr} {op_} {red}")
     out = generic.spell_length_statistics(da, 1.0, 1, None, "<", "max", "MS", min_gap=2)
     exp = O.spell_length_statistics(pr, 1.0, 1, None, "<", "max", da.time.period_offsets("MS"), min_gap=2)
     np.testing.assert_array_equal(out.values, exp)

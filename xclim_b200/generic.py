@@ -181,8 +181,8 @@ def spell_length_statistics(data, threshold, window, win_reducer, op, spell_redu
         raise NotImplementedError("select_time indexers together with min_gap > 1 are not supported")
     if min_gap < 1:
         raise ValueError("min_gap must be >= 1")
-    if min_gap > 1 and (window != 1 or not resample_before_rl):
-        raise NotImplementedError("min_gap > 1 is supported for window == 1 spells with resample_before_rl=True")
+    if min_gap > 1 and not resample_before_rl:
+        raise NotImplementedError("min_gap > 1 is supported with resample_before_rl=True only")
     code = get_op(op)
     thr = threshold_in_units_of(threshold, data) if isinstance(threshold, str) else _scalar_threshold(threshold)[0]
     reducers = [spell_reducer] if isinstance(spell_reducer, str) else list(spell_reducer)
@@ -202,11 +202,20 @@ def spell_length_statistics(data, threshold, window, win_reducer, op, spell_redu
         wstat = _lib.STATS[(win_reducer or "sum").replace("integral", "sum")]
         sel_mask = device.spell_mask(x2d, window, wstat, code, thr, keep,
                                      drop_nan_adjacent=(OPTIONS["rle_nan_adjacent"] == "drop"))
+    gap_mask = None
+    if min_gap > 1 and window > 1:
+        # spell_mask(window > 1) materialised once (indices/generic.py:519-535), then runs_with_holes + the run
+        # statistics on it (:537-538, 557-585): the window-1 min_gap kernel on the 0/1 mask
+        if win_reducer not in ("min", "max", "sum", "mean"):
+            raise ValueError(f"win_reducer must be one of min, max, sum, mean; got {win_reducer!r}")
+        gap_mask = device.spell_mask(x2d, window, _lib.STATS[win_reducer], code, thr)
     outs = []
     for sr in reducers:
         if sr not in _lib.RL_REDUCERS:
             raise NotImplementedError(f"spell reducer {sr!r} is not supported by the B200 hot path")
-        if sel_mask is not None:
+        if gap_mask is not None:
+            out = device.period_runstat_gap(gap_mask, poff, _lib.OPS[">"], 0.5, _lib.RL_REDUCERS[sr], min_gap)
+        elif sel_mask is not None:
             out, _ = device.period_runstat(sel_mask, poff, _lib.OPS[">"], 0.0, _lib.RL_REDUCERS[sr], 1, resample_before_rl)
         elif window == 1 and min_gap > 1:     # runs_with_holes (indices/generic.py:537-538)
             out = device.period_runstat_gap(x2d, poff, code, thr, _lib.RL_REDUCERS[sr], min_gap)
