@@ -6,7 +6,7 @@ import pytest
 
 import fake_device
 from oracle import fire_oracle as FO
-from test_fire_oracle import mg
+from test_fire_oracle import assert_index_close, mg
 from xb_helpers import make_field
 
 
@@ -46,8 +46,7 @@ def check_bodies(fire, Field):
                                *(np.full(16, np.nan, np.float32),) * 3, np.zeros(16, np.float32), outputs=list(out))
     for k in out:
         assert out[k].dims == ("time", "lat", "lon") and out[k].values.dtype == np.float32
-        np.testing.assert_allclose(np.asarray(out[k].values).reshape(T, -1), exp[k], rtol=1e-5, atol=1e-6, equal_nan=True,
-                                   err_msg=k)
+        assert_index_close(np.asarray(out[k].values).reshape(T, -1), exp[k], k, rtol=1e-5, atol=1e-6)
 
     # 2. only what is asked for (+ dependencies), computed season, overwintering, previous codes as Fields
     dc0 = Field(np.linspace(50, 400, 16, dtype=np.float32).reshape(4, 4), ("lat", "lon"), None, {}, {})
