@@ -35,7 +35,7 @@ def case_inputs(g, name):
     return args, kw, exp
 
 
-def assert_index_close(got, exp, label, rtol=1e-5, atol=1e-7):
+def assert_index_close(got, exp, label, rtol=1e-5, atol=1e-6):
     """ISI / BUI / FWI / DSR within the 1e-5 of the north star -- except just above FWI = 1, where Eq. 30b
     (fwi -> exp(2.72 (0.434 ln fwi)^0.647), _cffwis.py:527) has an unbounded derivative: an input that differs
     by one float32 ulp moves the result by up to 5e-5 there, in the reference as anywhere else."""
