@@ -150,3 +150,40 @@ def check_streaming(tmp_path, lib=None):
     assert type(ci).__name__ == "CFFWISIndices"
     for a, b in zip(ci, cj):
         np.testing.assert_array_equal(a.values, np.asarray(b.values))
+
+
+def test_fire_dataarray_boundary(monkeypatch):
+    """DataArray in -> DataArray out for the fire-weather functions (through tests/mini_xarray.py: xarray is
+    absent from the image), latitude taken from a DataArray coordinate as `lat=ds.lat` is in the reference."""
+    import mini_xarray as mx
+    from xclim_b200 import fire
+    fake_device.install(monkeypatch)
+    mx.install(monkeypatch)
+    inp = mg.cffwis_inputs(seed=13, C=15, T=420)
+    T = 420
+
+    def da(a, units):
+        return mx.daily(np.ascontiguousarray(a.T).reshape(T, 3, 5), "1995-01-01", units=units)
+    tas, pr, hurs, ws = da(inp["tas"], "degC"), da(inp["pr"], "mm/d"), da(inp["hurs"], "%"), da(inp["ws"], "km/h")
+    lat = tas.coords["lat"]
+    out = fire.cffwis_indices(tas, pr, ws, hurs, lat, season_method="WF93")
+    assert all(isinstance(o, mx.DataArray) and o.dims == ("time", "lat", "lon") for o in out)
+    assert out.FWI.attrs["units"] == "" and out.DC.values.dtype == np.float32
+    np.testing.assert_array_equal(out.DC.coords["lon"].values, tas.coords["lon"].values)
+    lat_cells = np.repeat(np.asarray(lat.values, dtype=np.float64), 5)
+    x = lambda d: np.asarray(d.values).reshape(T, -1)   # noqa: E731
+    exp = FO.fire_weather_calc(x(tas), x(pr), x(hurs), x(ws), None, np.asarray(mx_month(tas)), lat_cells, None,
+                               *(np.full(15, np.nan, np.float32),) * 3, np.zeros(15, np.float32),
+                               outputs=["DC", "DMC", "FFMC", "ISI", "BUI", "FWI", "season_mask"], season_method="WF93")
+    for k in out._fields:
+        assert_index_close(x(getattr(out, k)), exp[k], k)
+    mask = fire.fire_season(tas, method="WF93")
+    assert isinstance(mask, mx.DataArray) and mask.values.dtype == bool
+    np.testing.assert_array_equal(x(mask), exp["season_mask"])
+    dc = fire.drought_code(tas, pr, lat, season_mask=mask)
+    np.testing.assert_allclose(x(dc), exp["DC"], rtol=2e-6, equal_nan=True)
+
+
+def mx_month(da):
+    from xclim_b200.timeaxis import TimeAxis
+    return TimeAxis.from_xarray(da["time"]).month
