@@ -302,28 +302,43 @@ def run_ours(args):
         "check": {"out_max_days": out_max, "periods_masked_missing": n_missing},
     }
     sec = args.sections
+
+    def guarded(name, fn):
+        """A secondary section must not cost the headline line: its failure is recorded, not raised.
+        (Under torchrun every rank runs the same sections, so a failure that hits one rank only could still
+        stall the others in a collective: the sections synchronise through ctx.barrier / max_over_ranks.)"""
+        try:
+            return fn()
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            print(f"[bench] section {name} failed:\n{traceback.format_exc()}", file=sys.stderr, flush=True)
+            torch.cuda.empty_cache()
+            return {"error": f"{type(e).__name__}: {e}"[:400]}
+
     # ---- full-size parity: sampled cells of this tile (incl. the last CTA's) against the oracle
     if "parity" in sec:
         line["parity"] = S.parity_cdd(ctx, pr, poff, out, valid)
     if "gather" in sec and world > 1:
-        line["gather"] = S.gather_section(ctx, out, P)
+        line["gather"] = guarded("gather", lambda: S.gather_section(ctx, out, P))
     # ---- end to end through the Python index functions with host buffers
     if "e2e" in sec:
         affinity = os.sched_getaffinity(0)   # the e2e leg pins this process to the GPU's NUMA node
         try:
-            line["e2e"] = S.e2e_section(ctx, pr, poff, out, valid)
+            line["e2e"] = guarded("e2e", lambda: S.e2e_section(ctx, pr, poff, out, valid))
         finally:
             os.sched_setaffinity(0, affinity)  # ... the CPU arm below must see every core again
     del pr, out, valid
     torch.cuda.empty_cache()
     if "weak" in sec and world > 1:
-        line["weak_replicas"] = S.weak_section(ctx)
+        line["weak_replicas"] = guarded("weak", lambda: S.weak_section(ctx))
     if "tx90p" in sec or "bootstrap" in sec:
-        S.tx90p_sections(ctx, line, want_3a="tx90p" in sec, want_3b="bootstrap" in sec)
+        err = guarded("tx90p", lambda: S.tx90p_sections(ctx, line, want_3a="tx90p" in sec, want_3b="bootstrap" in sec))
+        if isinstance(err, dict) and "error" in err:
+            line.setdefault("tx90p", err)
     if "eqm" in sec:
-        line["eqm"] = S.eqm_section(ctx)
+        line["eqm"] = guarded("eqm", lambda: S.eqm_section(ctx))
     if "batch50" in sec:
-        line["batch50"] = S.batch50_section(ctx)
+        line["batch50"] = guarded("batch50", lambda: S.batch50_section(ctx))
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N == 1 only
     if rank == 0 and world == 1 and "cpu" in sec:
         use = _cpu_procs()
