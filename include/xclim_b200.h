@@ -499,6 +499,23 @@ int32_t xc_fwi_f32(const float* tas, const float* pr, const float* hurs, const f
                    float* DC, float* DMC, float* FFMC, float* ISI, float* BUI, float* FWI, float* DSR,
                    uint8_t* season_mask_out, float* winter_pr_out, void* stream);
 
+/* The element-wise members of the same module on float32 arrays of n values (device pointers):
+ *   XC_FWI_EW_ISI  out = initial_spread_index(a = ws [km/h], b = ffmc)            :449-469
+ *   XC_FWI_EW_BUI  out = build_up_index(a = dmc, b = dc)                          :472-501
+ *   XC_FWI_EW_FWI  out = fire_weather_index(a = isi, b = bui)                     :504-528
+ *   XC_FWI_EW_DSR  out = daily_severity_rating(a = fwi)                           :531-546
+ *   XC_FWI_EW_OWDC out = overwintering_drought_code(a = last_dc, b = winter_pr [mm], p0 = carry-over
+ *                  fraction, p1 = wetting efficiency fraction, p2 = min_dc)       :549-583, 1165-1250
+ * float32 arithmetic for the first four (numpy on float32 arrays), float64 for the last (numba), as the
+ * reference. */
+#define XC_FWI_EW_ISI  0
+#define XC_FWI_EW_BUI  1
+#define XC_FWI_EW_FWI  2
+#define XC_FWI_EW_DSR  3
+#define XC_FWI_EW_OWDC 4
+int32_t xc_fwi_elementwise_f32(int32_t kind, const float* a, const float* b, int64_t n,
+                               double p0, double p1, double p2, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

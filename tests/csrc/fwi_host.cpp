@@ -38,3 +38,9 @@ extern "C" int32_t fwi_host_f32(const float* tas, const float* pr, const float* 
   }
   return XC_OK;
 }
+
+extern "C" int32_t fwi_host_elementwise_f32(int32_t kind, const float* a, const float* b, int64_t n, double p0, double p1,
+                                            double p2, float* out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = xc::fwi::elementwise(kind, a[i], b ? b[i] : 0.0f, p0, p1, p2);
+  return XC_OK;
+}

@@ -369,11 +369,27 @@ def fire_weather(tas, pr, hurs, ws, snd, month, lat, season_mask, dc0, dmc0, ffm
     return out
 
 
+def to_device_f32(values):
+    return torch.from_numpy(np.ascontiguousarray(_np(values), dtype=np.float32))
+
+
+def fire_elementwise(kind, a, b=None, p=(0.0, 0.0, 0.0)):
+    from oracle import fire_oracle as FO
+    x, y = _np(a).astype(np.float32), (None if b is None else _np(b).astype(np.float32))
+    if kind == "OWDC":
+        r = FO.overwintering_drought_code(x, y, *p)
+    else:
+        fn = {"ISI": FO.initial_spread_index, "BUI": FO.build_up_index, "FWI": FO.fire_weather_index,
+              "DSR": FO.daily_severity_rating}[kind]
+        r = fn(x) if y is None else fn(x, y)
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(r, dtype=np.float32)))
+
+
 FUNCTIONS = [to_time_cell, period_count, period_runstat, period_runstat_gap, period_reduce, rolling_period_reduce,
              spell_runstat, period_run_maxsum, period_runstat2, percentile_doy, doy_interp, doy_threshold_count,
              mask_steps, dev_ints, period_boundary_run, period_boundary_run_range, bootstrap_doy_count, eqm_train,
              eqm_adjust, period_run_quantile, table_cell_major, period_multi, period_count_arr, spell_mask, transpose_f64,
-             rolling_period_reduce_sel, fire_weather]
+             rolling_period_reduce_sel, fire_weather, fire_elementwise, to_device_f32]
 
 
 def install(monkeypatch):

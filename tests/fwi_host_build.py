@@ -106,3 +106,17 @@ def run(tas, pr, hurs, ws, snd, mth, lat, season_mask, dc0, dmc0, ffmc0, winter_
     if "season_mask" in out:
         out["season_mask"] = out["season_mask"].astype(bool)
     return out
+
+
+def elementwise(kind, a, b=None, p=(0.0, 0.0, 0.0)):
+    """The element-wise entry point on the host build (kind: ISI, BUI, FWI, DSR, OWDC)."""
+    lib = load()
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    bb = None if b is None else np.ascontiguousarray(np.broadcast_to(b, a.shape), dtype=np.float32)
+    out = np.empty_like(a)
+    code = {"ISI": 0, "BUI": 1, "FWI": 2, "DSR": 3, "OWDC": 4}[kind]
+    lib.fwi_host_elementwise_f32(ctypes.c_int32(code), a.ctypes.data_as(ctypes.c_void_p),
+                                 None if bb is None else bb.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(a.size),
+                                 ctypes.c_double(p[0]), ctypes.c_double(p[1]), ctypes.c_double(p[2]),
+                                 out.ctypes.data_as(ctypes.c_void_p))
+    return out

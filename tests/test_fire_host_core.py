@@ -69,3 +69,22 @@ def test_parameter_struct_layouts_agree():
     for (n1, _), (n2, _) in zip(_lib.FwiParams._fields_, hb.XcFwiParams._fields_):
         assert n1 == n2 and getattr(_lib.FwiParams, n1).offset == getattr(hb.XcFwiParams, n2).offset
     assert _lib.FwiParams.snow_min_cover_frac.offset == 72 and _lib.FwiParams.in_scale.offset == 104
+
+
+def test_elementwise_functions_of_the_host_build(golden):  # noqa: F811
+    """ISI / BUI / FWI / DSR of the stored codes reproduce the reference's own arrays; the overwintered DC its
+    tests' known answers (tests/test_cffwis.py:126-145)."""
+    from test_fire_oracle import assert_index_close
+    g = golden
+    ws = g["ws"].T
+    ffmc, dmc, dc = (g[f"always_on__{k}"].T for k in ("FFMC", "DMC", "DC"))
+    assert_index_close(hb.elementwise("ISI", ws, ffmc), g["always_on__ISI"].T, "ISI")
+    assert_index_close(hb.elementwise("BUI", dmc, dc), g["always_on__BUI"].T, "BUI")
+    assert_index_close(hb.elementwise("FWI", g["always_on__ISI"].T, g["always_on__BUI"].T), g["always_on__FWI"].T, "FWI")
+    assert_index_close(hb.elementwise("DSR", g["always_on__FWI"].T), g["always_on__DSR"].T, "DSR")
+    for (dcf, wpr, a, b, mn), exp in (((300, 110, 0.75, 0.75, 15), 109.4657), ((300, 110, 1.0, 0.9, 15), 16.35315),
+                                      ((100, 50, 0.75, 0.75, 15), 105.176), ((1, 550, 0.75, 0.75, 10), 10)):
+        got = hb.elementwise("OWDC", np.array([dcf], np.float32), np.array([wpr], np.float32), (a, b, mn))
+        np.testing.assert_allclose(got, exp, rtol=1e-6)
+    assert np.isnan(hb.elementwise("OWDC", np.array([np.nan], np.float32), np.array([5.0], np.float32), (0.75, 0.75, 15)))[0]
+    assert hb.elementwise("BUI", np.zeros(1, np.float32), np.zeros(1, np.float32))[0] == 0

@@ -42,6 +42,7 @@ def check_bodies(fire, Field):
     # 1. always-on, all indexes, through fire_weather_ufunc
     out = fire.fire_weather_ufunc(tas=f["tas"], pr=f["pr"], hurs=f["hurs"], sfcWind=f["ws"], lat=latF)
     assert list(out) == ["DC", "DMC", "FFMC", "ISI", "BUI", "FWI", "DSR"]
+    out_all = out
     exp = FO.fire_weather_calc(tc(f["tas"]), tc(f["pr"]), tc(f["hurs"]), tc(f["ws"]), None, month, lat2d.reshape(-1), None,
                                *(np.full(16, np.nan, np.float32),) * 3, np.zeros(16, np.float32), outputs=list(out))
     for k in out:
@@ -93,6 +94,20 @@ def check_bodies(fire, Field):
                                np.full(16, np.nan, np.float32), np.full(16, 20.0, np.float32),
                                np.full(16, np.nan, np.float32), np.zeros(16, np.float32), outputs=["DMC"])
     np.testing.assert_allclose(np.asarray(dmc.values).reshape(T, -1), exp["DMC"], rtol=2e-6, equal_nan=True)
+
+    # 4b. the element-wise members on labelled arrays and bare arrays
+    isi = fire.initial_spread_index(f["ws"], out_all["FFMC"])
+    assert isi.dims == ("time", "lat", "lon") and isi.attrs["units"] == ""
+    assert_index_close(np.asarray(isi.values), np.asarray(out_all["ISI"].values), "ISI")
+    bui = fire.build_up_index(out_all["DMC"], out_all["DC"])
+    assert_index_close(np.asarray(bui.values), np.asarray(out_all["BUI"].values), "BUI")
+    fwi = fire.fire_weather_index(np.asarray(isi.values), np.asarray(bui.values))
+    assert isinstance(fwi, np.ndarray)
+    assert_index_close(fwi, np.asarray(out_all["FWI"].values), "FWI")
+    assert_index_close(np.asarray(fire.daily_severity_rating(out_all["FWI"]).values), np.asarray(out_all["DSR"].values), "DSR")
+    wdc = fire.overwintering_drought_code(Field(np.array([[300.0, 100.0]], np.float32), ("lat", "lon"), None, {}, {}),
+                                          Field(np.array([[0.11, 0.05]], np.float32), ("lat", "lon"), None, {}, {"units": "m"}))
+    np.testing.assert_allclose(np.asarray(wdc.values), [[109.4657, 105.176]], rtol=1e-5)
 
     # 5. the reference's errors
     with pytest.raises(TypeError, match="Missing input argument hurs"):

@@ -67,6 +67,7 @@ SIGNATURES = {
     "xc_host_pinned": (_i32, [_vp]),
     "xc_copy_box_async": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp]),
     "xc_fwi_f32": (_i32, [_vp] * 12 + [_i64, _i64, _i64, _vp] + [_vp] * 9 + [_vp]),
+    "xc_fwi_elementwise_f32": (_i32, [_i32, _vp, _vp, _i64, _f64, _f64, _f64, _vp, _vp]),
     "xc_period_runstat_f32_host": (_i32, [_vp, _i64, _i64, _vp, _i32, _i32, _f64, _i32, _i32, _i32, _vp, _vp,
                                           _vp, _i64]),
 }
@@ -113,6 +114,7 @@ class FwiParams(C.Structure):
                 + [("in_scale", C.c_float * 5), ("in_offset", C.c_float * 5)])
 
 
+FWI_ELEMENTWISE = {"ISI": 0, "BUI": 1, "FWI": 2, "DSR": 3, "OWDC": 4}
 FWI_SEASONS = {None: 0, "mask": 1, "WF93": 2, "LA08": 3, "GFWED": 4}
 FWI_DRY_STARTS = {None: 0, "CFS": 1, "GFWED": 2, "GFWED+SNOW": 3}
 

@@ -29,6 +29,14 @@ __global__ void __launch_bounds__(kThreads) fwi_kernel(const __grid_constant__ f
   fwi::run_cell<RINGS>(a, c, c_day_lengths, c_day_length_factors);
 }
 
+__global__ void __launch_bounds__(256)
+fwi_elementwise_kernel(int kind, const float* __restrict__ a, const float* __restrict__ b, int64_t n, double p0,
+                       double p1, double p2, float* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = fwi::elementwise(kind, a[i], b ? b[i] : 0.0f, p0, p1, p2);
+}
+
 }  // namespace
 }  // namespace xc
 
@@ -58,4 +66,16 @@ extern "C" int32_t xc_fwi_f32(const float* tas, const float* pr, const float* hu
   if (fwi::needs_rings(a.P)) fwi_kernel<true><<<blocks, kThreads, 0, s>>>(a);
   else fwi_kernel<false><<<blocks, kThreads, 0, s>>>(a);
   return launch_status("fwi_kernel");
+}
+
+extern "C" int32_t xc_fwi_elementwise_f32(int32_t kind, const float* a, const float* b, int64_t n, double p0, double p1,
+                                          double p2, float* out, void* stream) {
+  using namespace xc;
+  XC_REQUIRE(kind >= XC_FWI_EW_ISI && kind <= XC_FWI_EW_OWDC, "unknown element-wise fire weather function %d", kind);
+  XC_REQUIRE(a && out && (b || kind == XC_FWI_EW_DSR), "null pointer argument");
+  XC_REQUIRE(n > 0, "bad shape");
+  const int64_t want = (n + 255) / 256;
+  const unsigned blocks = (unsigned)(want < 148 * 16 ? want : 148 * 16);   // grid-stride: 16 CTAs per SM at most
+  fwi_elementwise_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kind, a, b, n, p0, p1, p2, out);
+  return launch_status("fwi_elementwise_kernel");
 }

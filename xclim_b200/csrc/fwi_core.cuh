@@ -405,6 +405,17 @@ XC_FWI_HD void run_cell(const Args& a, int64_t c, const double* day_lengths, con
   (void)nan_d;
 }
 
+// One element of the element-wise entry point (xc_fwi_elementwise_f32).
+XC_FWI_HD float elementwise(int kind, float a, float b, double p0, double p1, double p2) {
+  switch (kind) {
+    case XC_FWI_EW_ISI: return isi_of(a, b);
+    case XC_FWI_EW_BUI: return bui_of(a, b);
+    case XC_FWI_EW_FWI: return fwi_of(a, b);
+    case XC_FWI_EW_DSR: return dsr_of(a);
+    default: return (float)overwintered_dc(a, b, p0, p1, p2);
+  }
+}
+
 // The W_* bits implied by the outputs asked for (:1046-1057).
 inline int want_bits(bool DC, bool DMC, bool FFMC, bool ISI, bool BUI, bool FWI, bool DSR) {
   int w = (DC ? W_DC : 0) | (DMC ? W_DMC : 0) | (FFMC ? W_FFMC : 0) | (ISI ? W_ISI : 0) | (BUI ? W_BUI : 0) |

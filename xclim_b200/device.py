@@ -521,3 +521,23 @@ def fire_weather(tas, pr, hurs, ws, snd, month, lat, season_mask, dc0, dmc0, ffm
                             ctypes.byref(params), *optr, _ptr(out.get("season_mask")), _ptr(out.get("winter_pr")),
                             current_stream_ptr()))
     return out
+
+
+def to_device_f32(values):
+    """Any array (numpy, torch) as a float32 CUDA tensor of the same shape."""
+    _require_cuda()
+    if isinstance(values, torch.Tensor):
+        return values.to(device="cuda", dtype=torch.float32)
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(values), dtype=np.float32)).to("cuda")
+
+
+def fire_elementwise(kind, a, b=None, p=(0.0, 0.0, 0.0)):
+    """One of the element-wise fire-weather functions on float32 device tensors (``xc_fwi_elementwise_f32``)."""
+    if b is not None and tuple(b.shape) != tuple(a.shape):
+        raise ValueError("fire_elementwise: the two inputs must share their shape")
+    a = a.contiguous()
+    b = None if b is None else b.contiguous()
+    out = torch.empty_like(a)
+    check(load().xc_fwi_elementwise_f32(_lib.FWI_ELEMENTWISE[kind], a.data_ptr(), _ptr(b), a.numel(), float(p[0]),
+                                        float(p[1]), float(p[2]), out.data_ptr(), current_stream_ptr()))
+    return out

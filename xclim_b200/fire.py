@@ -9,7 +9,9 @@ output in the same pass.  The functions keep the reference's names, argument mea
 * :func:`fire_weather_ufunc` (:879-1151) -- no unit handling, inputs in degC, mm/day, %, km/h, m;
 * :func:`cffwis_indices` (:1273-1402), :func:`drought_code` (:1415-1500), :func:`duff_moisture_code`
   (:1513-1594) -- unit-aware: the conversion of the input arrays is folded into the kernel's loads;
-* :func:`fire_season` (:1609-1691, ``freq=None``).
+* :func:`fire_season` (:1609-1691, ``freq=None``);
+* the element-wise members :func:`initial_spread_index`, :func:`build_up_index`, :func:`fire_weather_index`,
+  :func:`daily_severity_rating` (:449-546) and :func:`overwintering_drought_code` (:1165-1250).
 """
 from __future__ import annotations
 
@@ -349,3 +351,71 @@ def fire_season(tas, snd=None, method="WF93", freq=None, temp_start_thresh="12 d
     state = {"dc0": None, "dmc0": None, "ffmc0": None, "winter_pr": None}
     out = _run(series, affine, None, state, None, ["season_mask"], method, False, None, True, kw)
     return _unitless(out)["season_mask"]
+
+
+# ------------------------------------------------------------------------------------ element-wise members
+def _elementwise(kind, a, b=None, p=(0.0, 0.0, 0.0), attrs=None, scale_b=1.0):
+    """Unwrap one or two arrays of any (equal) shape to float32 device tensors, run one element-wise kernel,
+    wrap the result like the first labelled argument."""
+    import torch
+    template = next((x for x in (a, b) if isinstance(x, Field) or is_xarray(x)), None)
+
+    def dev(x):
+        if x is None:
+            return None
+        return device.to_device_f32(raw_values(x) if (isinstance(x, Field) or is_xarray(x)) else x)
+
+    ta, tb = dev(a), dev(b)
+    if tb is not None and tuple(tb.shape) != tuple(ta.shape):
+        ta, tb = torch.broadcast_tensors(ta, tb)
+    if tb is not None and scale_b != 1.0:
+        tb = tb * np.float32(scale_b)
+    out = device.fire_elementwise(kind, ta, tb, p)
+    if template is None:
+        return out.cpu().numpy()
+    keep_dev = OPTIONS["device_outputs"] and not is_xarray(template)
+    vals = out if keep_dev else out.cpu().numpy()
+    dims = dims_of(template)
+    time = None
+    if "time" in dims:
+        from .field import time_axis_of
+        ta_ = time_axis_of(template)
+        time = ta_ if ta_.coord is None else ta_.coord
+    return wrap_like(template, vals, tuple(dims), time=time, attrs=dict(attrs or {"units": ""}))
+
+
+def initial_spread_index(ws, ffmc):
+    """Initial spread index from the wind speed [km/h] and the FFMC -- indices/fire/_cffwis.py:449-469."""
+    return _elementwise("ISI", ws, ffmc)
+
+
+def build_up_index(dmc, dc):
+    """Build-up index -- indices/fire/_cffwis.py:472-501."""
+    return _elementwise("BUI", dmc, dc)
+
+
+def fire_weather_index(isi, bui):
+    """Fire weather index -- indices/fire/_cffwis.py:504-528."""
+    return _elementwise("FWI", isi, bui)
+
+
+def daily_severity_rating(fwi):
+    """Daily severity rating -- indices/fire/_cffwis.py:531-546."""
+    return _elementwise("DSR", fwi)
+
+
+def overwintering_drought_code(last_dc, winter_pr, carry_over_fraction=default_params["carry_over_fraction"],
+                               wetting_efficiency_fraction=default_params["wetting_efficiency_fraction"],
+                               min_dc=default_params["dc_start"]):
+    """Season-starting drought code from last season's last DC and the winter precipitation --
+    indices/fire/_cffwis.py:1165-1250 (scalar fractions)."""
+    if not all(np.isscalar(v) for v in (carry_over_fraction, wetting_efficiency_fraction, min_dc)):
+        raise NotImplementedError("overwintering_drought_code: array-valued fractions are not supported")
+    scale = 1.0
+    if (isinstance(winter_pr, Field) or is_xarray(winter_pr)) and "units" in winter_pr.attrs:
+        u = winter_pr.attrs["units"].strip()
+        if u not in _LENGTH:
+            raise ValueError(f"Cannot convert {u!r} to 'mm'")
+        scale = _LENGTH[u] / _LENGTH["mm"]
+    return _elementwise("OWDC", last_dc, winter_pr, (carry_over_fraction, wetting_efficiency_fraction, min_dc),
+                        scale_b=scale)
