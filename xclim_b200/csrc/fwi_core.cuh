@@ -267,7 +267,8 @@ XC_FWI_HD void run_cell(const Args& a, int64_t c, const double* day_lengths, con
     const float hurs = a.hurs ? XC_FWI_LD(a.hurs + off) * P.in_scale[2] + P.in_offset[2] : nan_f;
     const float ws = a.ws ? XC_FWI_LD(a.ws + off) * P.in_scale[3] + P.in_offset[3] : nan_f;
     const float snd = a.snd ? XC_FWI_LD(a.snd + off) * P.in_scale[4] + P.in_offset[4] : nan_f;
-    const int mth = a.month[it];
+    int mth = a.month[it];
+    mth = mth < 1 ? 1 : (mth > 12 ? 12 : mth);     // the tables have twelve columns
 
     // ---- season mask of the day (:636-675) ----
     int on = 1;
