@@ -96,3 +96,34 @@ def test_argument_validation_happens_before_any_device_work(lib):
     th = threading.Thread(target=lambda: seen.append(lib.xc_last_error()))
     th.start(); th.join()
     assert seen == [b""]
+
+
+def test_fire_weather_argument_validation(lib):
+    """xc_fwi_f32 / xc_fwi_elementwise_f32 refuse inconsistent arguments on the host, with the reference's
+    message where it has one (indices/fire/_cffwis.py:1115-1117)."""
+    import ctypes as C
+
+    from xclim_b200 import _lib, device
+    from xclim_b200.fire import default_params
+    INVALID = -1
+    buf = (C.c_float * 64)()
+    p = C.cast(buf, C.c_void_p)
+    month = C.cast((C.c_int8 * 4)(1, 1, 1, 1), C.c_void_p)
+    kw = {k: (v if not isinstance(v, tuple) else v[0]) for k, v in default_params.items()}
+
+    def call(P, tas=p, pr=p, hurs=None, ws=None, snd=None, mask=None, mth=month, lat=p, outs=(p,) + (None,) * 6):
+        return lib.xc_fwi_f32(tas, pr, hurs, ws, snd, mask, mth, lat, None, None, None, None, 4, 4, 4, C.byref(P), *outs,
+                              None, None, None)
+
+    P = device.fwi_params(None, False, None, True, **kw)
+    assert call(P, mth=None) == INVALID and b"month" in lib.xc_last_error()
+    assert call(P, outs=(None,) * 7) == INVALID and b"no output" in lib.xc_last_error()
+    assert call(P, outs=(None, p) + (None,) * 5) == INVALID and b"hurs" in lib.xc_last_error()      # DMC without hurs
+    assert call(P, lat=None) == INVALID and b"lat" in lib.xc_last_error()
+    assert call(device.fwi_params(None, True, None, True, **kw)) == INVALID
+    assert b"either `season_method` or `season_mask` must be given" in lib.xc_last_error()
+    assert call(device.fwi_params("mask", False, None, True, **kw)) == INVALID and b"season_mask" in lib.xc_last_error()
+    assert call(device.fwi_params("LA08", False, None, True, **kw)) == INVALID and b"snd" in lib.xc_last_error()
+    assert call(device.fwi_params("WF93", False, None, True, **{**kw, "temp_condition_days": 33})) == INVALID
+    assert lib.xc_fwi_elementwise_f32(9, p, p, 4, 0.0, 0.0, 0.0, p, None) == INVALID
+    assert lib.xc_fwi_elementwise_f32(_lib.FWI_ELEMENTWISE["BUI"], p, None, 4, 0.0, 0.0, 0.0, p, None) == INVALID
