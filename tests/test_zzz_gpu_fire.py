@@ -33,6 +33,24 @@ def run_on_device(args, kw):
     return {k: (v.cpu().numpy().astype(bool) if k == "season_mask" else v.cpu().numpy()) for k, v in res.items()}
 
 
+def test_elementwise_kernel_on_device(cuda, golden):  # noqa: F811
+    import torch
+
+    from test_fire_oracle import assert_index_close
+    from xclim_b200 import device
+    g = golden
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a.T)).cuda()   # noqa: E731
+    ffmc, dmc, dc = (d(g[f"always_on__{k}"]) for k in ("FFMC", "DMC", "DC"))
+    assert_index_close(device.fire_elementwise("ISI", d(g["ws"]), ffmc).cpu().numpy(), g["always_on__ISI"].T, "ISI")
+    assert_index_close(device.fire_elementwise("BUI", dmc, dc).cpu().numpy(), g["always_on__BUI"].T, "BUI")
+    assert_index_close(device.fire_elementwise("FWI", d(g["always_on__ISI"]), d(g["always_on__BUI"])).cpu().numpy(),
+                       g["always_on__FWI"].T, "FWI")
+    assert_index_close(device.fire_elementwise("DSR", d(g["always_on__FWI"])).cpu().numpy(), g["always_on__DSR"].T, "DSR")
+    got = device.fire_elementwise("OWDC", torch.tensor([300.0, 100.0, 1.0], device="cuda"),
+                                  torch.tensor([110.0, 50.0, 550.0], device="cuda"), (0.75, 0.75, 15))
+    np.testing.assert_allclose(got.cpu().numpy(), [109.4657, 105.176, 15.0], rtol=1e-6)
+
+
 @pytest.mark.parametrize("name", list(mg.CFFWIS_CASES))
 def test_kernel_matches_reference_fixture(cuda, golden, name):  # noqa: F811
     args, kw, exp = case_inputs(golden, name)
@@ -74,20 +92,3 @@ def test_fire_weather_streams_from_files_on_device(cuda, tmp_path):
     from test_fire_host_layer import check_streaming
     check_streaming(tmp_path)
 
-
-def test_elementwise_kernel_on_device(cuda, golden):  # noqa: F811
-    import torch
-
-    from test_fire_oracle import assert_index_close
-    from xclim_b200 import device
-    g = golden
-    d = lambda a: torch.from_numpy(np.ascontiguousarray(a.T)).cuda()   # noqa: E731
-    ffmc, dmc, dc = (d(g[f"always_on__{k}"]) for k in ("FFMC", "DMC", "DC"))
-    assert_index_close(device.fire_elementwise("ISI", d(g["ws"]), ffmc).cpu().numpy(), g["always_on__ISI"].T, "ISI")
-    assert_index_close(device.fire_elementwise("BUI", dmc, dc).cpu().numpy(), g["always_on__BUI"].T, "BUI")
-    assert_index_close(device.fire_elementwise("FWI", d(g["always_on__ISI"]), d(g["always_on__BUI"])).cpu().numpy(),
-                       g["always_on__FWI"].T, "FWI")
-    assert_index_close(device.fire_elementwise("DSR", d(g["always_on__FWI"])).cpu().numpy(), g["always_on__DSR"].T, "DSR")
-    got = device.fire_elementwise("OWDC", torch.tensor([300.0, 100.0, 1.0], device="cuda"),
-                                  torch.tensor([110.0, 50.0, 550.0], device="cuda"), (0.75, 0.75, 15))
-    np.testing.assert_allclose(got.cpu().numpy(), [109.4657, 105.176, 15.0], rtol=1e-6)
