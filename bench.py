@@ -35,7 +35,7 @@ if ROOT not in sys.path:
 T_FULL, Y_FULL, X_FULL, YEAR = 10950, 721, 1440, 365
 METRIC = "grid_cells_per_s:maximum_consecutive_dry_days(10950x721x1440,f32)"
 UNIT = "grid-cells/s"
-ALL_SECTIONS = ("parity", "weak", "gather", "tx90p", "bootstrap", "eqm", "batch50", "e2e", "cpu")
+ALL_SECTIONS = ("parity", "weak", "gather", "tx90p", "bootstrap", "eqm", "batch50", "e2e", "fwi", "cpu")
 
 
 def parse_args():
@@ -314,7 +314,10 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001
             import traceback
             print(f"[bench] section {name} failed:\n{traceback.format_exc()}", file=sys.stderr, flush=True)
-            torch.cuda.empty_cache()
+            try:
+                torch.cuda.empty_cache()
+            except Exception:  # noqa: BLE001  (a faulted context: nothing more to free)
+                pass
             return {"error": f"{type(e).__name__}: {e}"[:400]}
 
     # ---- full-size parity: sampled cells of this tile (incl. the last CTA's) against the oracle
@@ -341,6 +344,9 @@ def run_ours(args):
         line["eqm"] = guarded("eqm", lambda: S.eqm_section(ctx))
     if "batch50" in sec:
         line["batch50"] = guarded("batch50", lambda: S.batch50_section(ctx))
+    # ---- the fire-weather kernel: last GPU section, one GPU only, guarded (its first run on hardware)
+    if "fwi" in sec and world == 1:
+        line["fwi"] = guarded("fwi", lambda: S.fwi_section(ctx))
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0, N == 1 only
     if rank == 0 and world == 1 and "cpu" in sec:
         use = _cpu_procs()

@@ -260,6 +260,73 @@ def tx90p_sections(ctx, line, want_3a=True, want_3b=True):
     torch.cuda.empty_cache()
 
 
+# ------------------------------------------------------------------------------------------------ fire weather
+def fwi_section(ctx, rows=90):
+    """the six Canadian Fire Weather Index System indices (cffwis_indices, always-on season) on a
+    lat band of the grid, device-resident, with a sampled-cell check against the oracle.  This kernel was
+    written after the GPU budget of round 2 was spent: this section is its first measurement, which is why it
+    runs last and guarded."""
+    import torch
+    from oracle import fire_oracle as FO
+    from xclim_b200 import device, fire
+    T, X = T_FULL, X_FULL
+    rows = min(rows, ctx.rows)
+    C = rows * X
+    steps = max(1, min(ctx.args.steps, 3))
+    kw = dict(cells_per_lat=X, n_lat_global=ctx.n_lat_global, cell_offset=ctx.row0 * X)
+    tas = device.synth(T, C, kind=1, seed=3, **kw)
+    tas.sub_(273.15)                                        # degC
+    pr = device.synth(T, C, kind=0, seed=2, **kw)           # mm/d
+    hurs = device.synth(T, C, kind=1, seed=11, **kw)
+    hurs.sub_(hurs.mean()).mul_(4.0).add_(55.0).clamp_(5.0, 100.0)   # %
+    ws = device.synth(T, C, kind=1, seed=12, **kw)
+    ws.sub_(270.0).abs_().mul_(0.5)                         # km/h
+    month = (np.minimum((np.arange(T) % YEAR) // 30.42, 11) + 1).astype(np.int8)
+    lat_rows = np.linspace(-90.0, 90.0, ctx.n_lat_global)[ctx.row0:ctx.row0 + rows]
+    lat = np.repeat(lat_rows, X)
+    lat_d = torch.from_numpy(lat).to(ctx.dev)              # resident: no host copy inside the timed calls
+    p = {k: (v if not isinstance(v, tuple) else v[0]) for k, v in fire.default_params.items()}
+    P = device.fwi_params(None, False, None, True, **p)
+    outs = ["DC", "DMC", "FFMC", "ISI", "BUI", "FWI"]
+    run = lambda: device.fire_weather(tas, pr, hurs, ws, None, month, lat_d, None, None, None, None, None, outs, P)  # noqa: E731
+    res = run()
+    torch.cuda.synchronize()
+    ms = timeit(ctx, run, steps, warmup=1)
+    # sampled cells against the oracle (the same float32 series, copied back)
+    sel = sample_cells(C, 48, 23 + ctx.rank)
+    idx = torch.from_numpy(sel).to(ctx.dev)
+    host = [x[:, idx].cpu().numpy() for x in (tas, pr, hurs, ws)]
+    nanv = np.full(sel.size, np.nan, np.float32)
+    t0 = time.perf_counter()
+    exp = FO.fire_weather_calc(host[0], host[1], host[2], host[3], None, month, lat[sel], None, nanv, nanv, nanv,
+                               np.zeros(sel.size, np.float32), outputs=outs)
+    dt = time.perf_counter() - t0
+    worst = {}
+    for k in outs:
+        got = res[k][:, idx].cpu().numpy()
+        e = exp[k]
+        with np.errstate(all="ignore"):
+            rel = np.abs(got - e) / np.maximum(np.abs(e), 1e-3)
+        steep = (e > 1.0) & (e < 1.005) if k == "FWI" else np.zeros(e.shape, bool)   # Eq. 30b is singular at FWI = 1
+        rel = np.where(np.isnan(e) & np.isnan(got) | steep, 0.0, rel)
+        worst[k] = float(np.nanmax(rel)) if np.isfinite(rel).all() else float("inf")
+    ok = all(v <= 1e-5 for v in worst.values())
+    alg = (4 + len(outs)) * T * C * 4
+    r = roofline(ctx, alg, ms, "fwi_kernel<false>", None)
+    r["bound"] = "FP64 pipe expected (about twenty float64 transcendentals per element); fraction of the HBM roofline reported"
+    del res
+    return {
+        "workload": f"cffwis_indices (DC, DMC, FFMC, ISI, BUI, FWI; season always on) on a ({T},{rows},{X}) f32 band: "
+                    "tas degC, pr mm/d, hurs %, sfcWind km/h; device-resident",
+        "value": C / (ms * 1e-3), "unit": "grid-cells/s", "ms_per_step": ms, "steps": steps, "gpu_launches_per_step": 1,
+        "roofline": r,
+        "cpu_baseline": {"value": sel.size / dt, "unit": "grid-cells/s", "cores": 1, "kind": "port",
+                         "sample": f"({T}, {sel.size}) cells, oracle day loop, {dt:.1f} s"},
+        "check": {"oracle_cells": int(sel.size), "max_rel_err": worst, "tolerance": 1e-5, "within_tolerance": bool(ok)},
+        "note": "first execution of this kernel on hardware (written and CPU-verified after the round's GPU budget was spent)",
+    }
+
+
 # ------------------------------------------------------------------------------------------------ EQM
 def eqm_section(ctx):
     import torch

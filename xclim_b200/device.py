@@ -488,7 +488,7 @@ def fwi_params(season_method=None, overwintering=False, dry_start=None, initial_
 def fire_weather(tas, pr, hurs, ws, snd, month, lat, season_mask, dc0, dmc0, ffmc0, winter_pr, outputs, params):
     """The fire-weather day loop on ``(T, C)`` float32 device series (``xc_fwi_f32``).
 
-    ``month`` int8[T] and ``lat`` float64[C] host arrays; ``season_mask`` (T, C) uint8 / previous codes (C,)
+    ``month`` int8[T] host array, ``lat`` float64[C] host array or device tensor; ``season_mask`` (T, C) uint8 / previous codes (C,)
     float32 device tensors or None.  ``outputs``: names among DC..DSR, "season_mask", "winter_pr".
     Returns a dict name -> device tensor.
     """
@@ -504,7 +504,12 @@ def fire_weather(tas, pr, hurs, ws, snd, month, lat, season_mask, dc0, dmc0, ffm
                                     or season_mask.stride(0) != ld):
         raise ValueError("fire_weather: season_mask must be (T, C) uint8 with the layout of the inputs")
     month_d = dev_ints(np.asarray(month, dtype=np.int8), np.int8, dev)
-    lat_d = None if lat is None else torch.from_numpy(np.ascontiguousarray(lat, dtype=np.float64)).to(dev)
+    if lat is None or isinstance(lat, torch.Tensor):        # a float64 device tensor is used as it is
+        lat_d = lat
+    else:
+        lat_d = torch.from_numpy(np.ascontiguousarray(lat, dtype=np.float64)).to(dev)
+    if lat_d is not None and (lat_d.dtype != torch.float64 or lat_d.numel() != C):
+        raise ValueError("fire_weather: lat must hold one float64 value per cell")
     out = {}
     for name in outputs:
         if name in FWI_OUTPUTS:      # outputs use the leading dimension of the inputs
