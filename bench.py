@@ -358,6 +358,11 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    elif any(isinstance(v, dict) and "error" in v for v in line.values()):
+        # a section failed (possibly with a faulted CUDA context): the line is out, skip the teardown
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
