@@ -88,3 +88,59 @@ def test_elementwise_functions_of_the_host_build(golden):  # noqa: F811
         np.testing.assert_allclose(got, exp, rtol=1e-6)
     assert np.isnan(hb.elementwise("OWDC", np.array([np.nan], np.float32), np.array([5.0], np.float32), (0.75, 0.75, 15)))[0]
     assert hb.elementwise("BUI", np.zeros(1, np.float32), np.zeros(1, np.float32))[0] == 0
+
+
+@pytest.mark.skipif(not __import__("_ref_extract").available(), reason="reference sources not present (GPU box)")
+def test_every_mode_combination_against_the_live_reference():
+    """All combinations of season method x overwintering x dry start x initial_start_up, each with random
+    thresholds / window lengths / previous codes: the oracle AND the host build of the device code against the
+    reference's `_fire_weather_calc` executed where it lies."""
+    import itertools
+    import warnings
+
+    import _ref_extract as ref
+    fw = ref.load_cffwis()
+    rng = np.random.default_rng(123)
+    T = 320
+    combos = itertools.product([None, "mask", "WF93", "LA08", "GFWED"], [False, True], [None, "CFS", "GFWED", "GFWED+SNOW"],
+                               [True, False])
+    n = 0
+    for trial, (season, ow, dry, isu) in enumerate(combos):
+        if ow and season is None:
+            continue
+        inp = mg.cffwis_inputs(seed=1000 + trial, C=16, T=T)
+        dc0, dmc0, ffmc0, wpr = mg.cffwis_state(inp, [None, "some", "all"][trial % 3])
+        over = dict(season_method=season, overwintering=ow, dry_start=dry, initial_start_up=isu,
+                    temp_condition_days=int(rng.integers(1, 6)), snow_condition_days=int(rng.integers(1, 6)),
+                    snow_cover_days=int(rng.integers(5, 70)), temp_start_thresh=float(rng.uniform(8, 14)),
+                    temp_end_thresh=float(rng.uniform(2, 7)), snow_thresh=float(rng.choice([0.01, 0.03])),
+                    prec_thresh=float(rng.choice([1.0, 2.5])), dc_dry_factor=int(rng.integers(2, 7)),
+                    dmc_dry_factor=int(rng.integers(1, 4)), snow_min_cover_frac=float(rng.uniform(0.3, 0.8)),
+                    snow_min_mean_depth=float(rng.uniform(0.02, 0.1)), carry_over_fraction=float(rng.choice([0.5, 0.75, 1.0])),
+                    wetting_efficiency_fraction=float(rng.choice([0.5, 0.75, 0.9])))
+        outs = ["DC", "DMC", "FFMC", "ISI", "BUI", "FWI", "DSR"]
+        mask = None
+        if season == "mask":                      # a persistent random mask
+            mask = np.zeros((16, T), bool)
+            st = rng.random(16) < 0.5
+            for t in range(T):
+                st = np.where(rng.random(16) < 0.03, ~st, st)
+                mask[:, t] = st
+        elif season is not None:
+            outs.append("season_mask")
+        if ow:
+            outs.append("winter_pr")
+        kw = mg.cffwis_params(fw, outputs=outs, **over)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            res = fw["_fire_weather_calc"](inp["tas"], inp["pr"], inp["hurs"], inp["ws"], inp["snd"], inp["mth"], inp["lat"],
+                                           mask, dc0.copy(), dmc0.copy(), ffmc0.copy(), wpr.copy(), **kw)
+        exp = {o: (np.asarray(a).T if np.asarray(a).ndim == 2 else np.asarray(a)) for o, a in zip(outs, res)}
+        tc = lambda a: np.ascontiguousarray(a.T)   # noqa: E731
+        args = (tc(inp["tas"]), tc(inp["pr"]), tc(inp["hurs"]), tc(inp["ws"]), tc(inp["snd"]), inp["mth"], inp["lat"],
+                None if mask is None else np.ascontiguousarray(mask.T), dc0, dmc0, ffmc0, wpr)
+        label = f"{season},{ow},{dry},{isu}"
+        check_outputs(FO.fire_weather_calc(*args, outputs=outs, **over), exp, "oracle:" + label, exact_frac=0.98)
+        check_outputs(hb.run(*args, outputs=outs, **over), exp, "host build:" + label, exact_frac=0.98)
+        n += 1
+    assert n == 72

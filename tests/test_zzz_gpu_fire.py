@@ -92,3 +92,48 @@ def test_fire_weather_streams_from_files_on_device(cuda, tmp_path):
     from test_fire_host_layer import check_streaming
     check_streaming(tmp_path)
 
+
+
+def test_kernel_every_mode_combination_against_the_oracle(cuda):
+    """All season x overwintering x dry-start x initial_start_up combinations with random parameters: the kernel
+    against the oracle, which tests/test_fire_host_core.py pins to the live reference on the SAME combinations
+    (there, with the host build of this kernel's device code)."""
+    import itertools
+    rng = np.random.default_rng(123)
+    T = 320
+    n = 0
+    for trial, (season, ow, dry, isu) in enumerate(itertools.product(
+            [None, "mask", "WF93", "LA08", "GFWED"], [False, True], [None, "CFS", "GFWED", "GFWED+SNOW"], [True, False])):
+        if ow and season is None:
+            continue
+        inp = mg.cffwis_inputs(seed=1000 + trial, C=16, T=T)
+        dc0, dmc0, ffmc0, wpr = mg.cffwis_state(inp, [None, "some", "all"][trial % 3])
+        over = dict(season_method=season, overwintering=ow, dry_start=dry, initial_start_up=isu,
+                    temp_condition_days=int(rng.integers(1, 6)), snow_condition_days=int(rng.integers(1, 6)),
+                    snow_cover_days=int(rng.integers(5, 70)), temp_start_thresh=float(rng.uniform(8, 14)),
+                    temp_end_thresh=float(rng.uniform(2, 7)), snow_thresh=float(rng.choice([0.01, 0.03])),
+                    prec_thresh=float(rng.choice([1.0, 2.5])), dc_dry_factor=int(rng.integers(2, 7)),
+                    dmc_dry_factor=int(rng.integers(1, 4)), snow_min_cover_frac=float(rng.uniform(0.3, 0.8)),
+                    snow_min_mean_depth=float(rng.uniform(0.02, 0.1)), carry_over_fraction=float(rng.choice([0.5, 0.75, 1.0])),
+                    wetting_efficiency_fraction=float(rng.choice([0.5, 0.75, 0.9])))
+        outs = ["DC", "DMC", "FFMC", "ISI", "BUI", "FWI", "DSR"]
+        mask = None
+        if season == "mask":
+            m = np.zeros((16, T), bool)
+            st = rng.random(16) < 0.5
+            for t in range(T):
+                st = np.where(rng.random(16) < 0.03, ~st, st)
+                m[:, t] = st
+            mask = np.ascontiguousarray(m.T)
+        elif season is not None:
+            outs.append("season_mask")
+        if ow:
+            outs.append("winter_pr")
+        tc = lambda a: np.ascontiguousarray(a.T)   # noqa: E731
+        args = (tc(inp["tas"]), tc(inp["pr"]), tc(inp["hurs"]), tc(inp["ws"]), tc(inp["snd"]), inp["mth"], inp["lat"], mask,
+                dc0, dmc0, ffmc0, wpr)
+        exp = FO.fire_weather_calc(*args, outputs=outs, **over)
+        got = run_on_device(args, dict(outputs=outs, **over))
+        check_outputs(got, {k: np.asarray(v) for k, v in exp.items()}, f"{season},{ow},{dry},{isu}", exact_frac=0.90)
+        n += 1
+    assert n == 72
