@@ -44,3 +44,6 @@ extern "C" int32_t fwi_host_elementwise_f32(int32_t kind, const float* a, const 
   for (int64_t i = 0; i < n; ++i) out[i] = xc::fwi::elementwise(kind, a[i], b ? b[i] : 0.0f, p0, p1, p2);
   return XC_OK;
 }
+
+// test hook: numpy's float32 mean of a ring (newest value at `head`)
+extern "C" float fwi_host_np_mean(const float* ring, int32_t n, int32_t head) { return xc::fwi::np_mean_f32(ring, n, head); }

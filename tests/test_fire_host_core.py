@@ -144,3 +144,20 @@ def test_every_mode_combination_against_the_live_reference():
         check_outputs(hb.run(*args, outputs=outs, **over), exp, "host build:" + label, exact_frac=0.98)
         n += 1
     assert n == 72
+
+
+def test_ring_mean_rounds_as_numpy_mean():
+    """The GFWED season and the snow-aware dry start compare float32 window means with thresholds
+    (_cffwis.py:661-668, 746-756): np_mean_f32 must round exactly as np.mean does (pairwise summation)."""
+    import ctypes
+    lib = hb.load()
+    lib.fwi_host_np_mean.restype = ctypes.c_float
+    rng = np.random.default_rng(4)
+    for n in list(range(1, 41)) + [59, 60, 61, 64, 100, 127, 128]:
+        for _ in range(6):
+            vals = (rng.random(n) * rng.choice([1e-3, 1.0, 1e3], size=n)).astype(np.float32)
+            head = int(rng.integers(0, n))
+            ring = np.empty(n, np.float32)
+            ring[(head + 1 + np.arange(n)) % n] = vals            # oldest value right after the head
+            got = lib.fwi_host_np_mean(ring.ctypes.data_as(ctypes.c_void_p), ctypes.c_int32(n), ctypes.c_int32(head))
+            assert np.float32(got) == np.mean(vals), (n, head)
