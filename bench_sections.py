@@ -303,12 +303,15 @@ def fwi_section(ctx, rows=90):
     dt = time.perf_counter() - t0
     worst = {}
     for k in outs:
-        got = res[k][:, idx].cpu().numpy()
-        e = exp[k]
+        got = res[k][:, idx].cpu().numpy().astype(np.float64)
+        e = exp[k].astype(np.float64)
         with np.errstate(all="ignore"):
             rel = np.abs(got - e) / np.maximum(np.abs(e), 1e-3)
-        steep = (e > 1.0) & (e < 1.005) if k == "FWI" else np.zeros(e.shape, bool)   # Eq. 30b is singular at FWI = 1
-        rel = np.where(np.isnan(e) & np.isnan(got) | steep, 0.0, rel)
+            if k == "FWI":   # Eq. 30b (fwi -> exp(2.72 (0.434 ln fwi)^0.647), fwi > 1) amplifies a difference of its input:
+                ln_in = (np.log(e) / 2.72) ** (1.0 / 0.647) / 0.434          # errors are reported per unit of its
+                cond = 2.72 * 0.647 * 0.434 ** 0.647 * ln_in ** -0.353       # condition number (unbounded at fwi = 1)
+                rel = rel / np.where(e > 1.0, np.clip(np.nan_to_num(cond, nan=1.0, posinf=200.0), 1.0, 200.0), 1.0)
+        rel = np.where(np.isnan(e) & np.isnan(got), 0.0, rel)
         worst[k] = float(np.nanmax(rel)) if np.isfinite(rel).all() else float("inf")
     ok = all(v <= 1e-5 for v in worst.values())
     alg = (4 + len(outs)) * T * C * 4
@@ -322,7 +325,8 @@ def fwi_section(ctx, rows=90):
         "roofline": r,
         "cpu_baseline": {"value": sel.size / dt, "unit": "grid-cells/s", "cores": 1, "kind": "port",
                          "sample": f"({T}, {sel.size}) cells, oracle day loop, {dt:.1f} s"},
-        "check": {"oracle_cells": int(sel.size), "max_rel_err": worst, "tolerance": 1e-5, "within_tolerance": bool(ok)},
+        "check": {"oracle_cells": int(sel.size), "max_rel_err": worst, "tolerance": 1e-5, "within_tolerance": bool(ok),
+                  "note": "FWI errors are divided by the condition number of Eq. 30b where it exceeds 1"},
         "note": "first execution of this kernel on hardware (written and CPU-verified after the round's GPU budget was spent)",
     }
 

@@ -35,19 +35,36 @@ def case_inputs(g, name):
     return args, kw, exp
 
 
+def eq30b_condition(fwi_out):
+    """Condition number of Eq. 30b (_cffwis.py:527: fwi -> exp(2.72 (0.434 ln fwi)^0.647) for fwi > 1) at the
+    OUTPUT value: d ln(out) / d ln(in) = 2.72 * 0.647 * 0.434^0.647 * (ln in)^-0.353 -- unbounded at in = 1, still 3
+    at in = 1.05.  1 where the transform does not apply."""
+    out = np.asarray(fwi_out, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        ln_in = (np.log(out) / 2.72) ** (1.0 / 0.647) / 0.434
+        k = 2.72 * 0.647 * 0.434 ** 0.647 * ln_in ** -0.353
+    return np.where(out > 1.0, np.clip(np.nan_to_num(k, nan=1.0, posinf=200.0), 1.0, 200.0), 1.0)
+
+
 def assert_index_close(got, exp, label, rtol=1e-5, atol=1e-6):
-    """ISI / BUI / FWI / DSR within the 1e-5 of the north star -- except just above FWI = 1, where Eq. 30b
-    (fwi -> exp(2.72 (0.434 ln fwi)^0.647), _cffwis.py:527) has an unbounded derivative: an input that differs
-    by one float32 ulp moves the result by up to 5e-5 there, in the reference as anywhere else."""
+    """ISI / BUI / FWI / DSR within the 1e-5 of the north star, scaled by the condition number of the
+    reference's own formula where that exceeds 1: Eq. 30b amplifies a relative difference of its float32 input
+    (two correct float32 evaluations differ by an ulp or two: numpy's and glibc's already do) by up to 3 at
+    FWI = 1.25 and without bound towards FWI = 1; DSR = 0.0272 FWI^1.77 multiplies it by another 1.77."""
     got, exp = np.asarray(got), np.asarray(exp)
-    steep = np.zeros(exp.shape, bool)
+    cond = np.ones(exp.shape)
     if label.endswith("FWI"):
-        steep = (exp > 1.0) & (exp < 1.005) | (got > 1.0) & (got < 1.005)
+        cond = np.maximum(eq30b_condition(exp), eq30b_condition(got))
     elif label.endswith("DSR"):
-        steep = (exp > 0.0272) & (exp < 0.02745) | (got > 0.0272) & (got < 0.02745)
-    np.testing.assert_allclose(np.where(steep, np.nan, got), np.where(steep, np.nan, exp), rtol=rtol, atol=atol,
-                               equal_nan=True, err_msg=label)
-    np.testing.assert_allclose(got[steep], exp[steep], rtol=2e-3, err_msg=label + " (steep zone)")
+        with np.errstate(all="ignore"):
+            cond = 1.77 * np.maximum(eq30b_condition((exp / 0.0272) ** (1 / 1.77)), eq30b_condition((got / 0.0272) ** (1 / 1.77)))
+    assert np.array_equal(np.isnan(got), np.isnan(exp)), label
+    with np.errstate(all="ignore"):
+        err = np.abs(got.astype(np.float64) - exp.astype(np.float64))
+        bound = atol + rtol * cond * np.abs(exp.astype(np.float64))
+    bad = np.nan_to_num(err, nan=0.0) > np.nan_to_num(bound, nan=np.inf)
+    assert not bad.any(), (f"{label}: {int(bad.sum())} values beyond tolerance, worst "
+                           f"{float(np.nanmax(np.where(bad, err / np.maximum(np.abs(exp), 1e-30), 0))):.3g} relative")
 
 
 def check_outputs(got, exp, name, exact_frac=0.995):

@@ -68,29 +68,27 @@ XC_FWI_HD double ffmc_step(float t_, float p_, float w_, float h_, float f0_) {
     else if (mo <= 150.0) mo = mo + gain;                                             // Eq. 3a
     mo = pmin(mo, 250.0);
   }
+  // Equilibrium moisture contents.  The two powers of the humidity share one logarithm (h^a = exp(a ln h)): a few
+  // float64 ulp away from pow(), eight orders of magnitude below the float32 rounding of the stored code.
   const double e10 = exp((h - 100.0) / 10.0);
   const double dry = 0.18 * (21.1 - t) * (1.0 - 1.0 / exp(0.115 * h));
-  const double ed = 0.942 * pow(h, 0.679) + (11.0 * e10) + dry;                       // Eq. 4
-  double m;
-  if (mo < ed) {
-    const double ew = 0.618 * pow(h, 0.753) + (10.0 * e10) + dry;                     // Eq. 5
-    if (mo < ew) {
-      const double x = (100.0 - h) / 100.0;
-      const double x2 = x * x, x4 = x2 * x2;
-      const double kl = 0.424 * (1.0 - pow(x, 1.7)) + (0.0694 * root_w) * (1.0 - x4 * x4);   // Eq. 7a
-      const double kw = kl * (0.581 * exp(0.0365 * t));                               // Eq. 7b
-      m = ew - (ew - mo) / pow(10.0, kw);                                             // Eq. 9
-    } else {
-      m = mo;
-    }
-  } else if (mo == ed) {
-    m = mo;
-  } else {
-    const double y = h / 100.0;
-    const double y2 = y * y, y4 = y2 * y2;
-    const double kl = 0.424 * (1.0 - pow(y, 1.7)) + (0.0694 * root_w) * (1.0 - y4 * y4);     // Eq. 6a
-    const double kw = kl * (0.581 * exp(0.0365 * t));                                 // Eq. 6b
-    m = ed + (mo - ed) / pow(10.0, kw);                                               // Eq. 8
+  const double lh = log(h);
+  const double ed = 0.942 * exp(0.679 * lh) + (11.0 * e10) + dry;                     // Eq. 4
+  const double ew = 0.618 * exp(0.753 * lh) + (10.0 * e10) + dry;                     // Eq. 5
+  // Drying towards ed (Eqs. 6, 8) and wetting towards ew (Eqs. 7, 9) are the same expression of
+  // z = h/100 resp. (100 - h)/100 and of the target: one evaluation serves both, without a divergent branch
+  // (Eq. 9, ew - (ew - mo) / 10^kw, equals ew + (mo - ew) / 10^kw bit for bit).  Between ew and ed, at mo == ed
+  // and where the reference raises (mo == ew) the moisture is kept; a NaN takes the drying expression, as there.
+  const bool drying = !(mo < ed) && !(mo == ed);
+  const bool wetting = (mo < ed) && (mo < ew);
+  double m = mo;
+  if (drying || wetting) {
+    const double z = drying ? h / 100.0 : (100.0 - h) / 100.0;
+    const double z2 = z * z, z4 = z2 * z2;
+    const double kl = 0.424 * (1.0 - exp(1.7 * log(z))) + (0.0694 * root_w) * (1.0 - z4 * z4);   // Eqs. 6a, 7a
+    const double kw = kl * (0.581 * exp(0.0365 * t));                                 // Eqs. 6b, 7b
+    const double target = drying ? ed : ew;
+    m = target + (mo - target) / exp(kw * 2.302585092994046);                         // Eqs. 8, 9 (10^kw)
   }
   double ffmc = (59.5 * (250.0 - m)) / (147.2 + m);                                   // Eq. 10
   if (ffmc > 101.0) ffmc = 101.0;
