@@ -58,6 +58,7 @@ XC_FWI_HD int day_length_factor_band(double lat) {
 // ---- the three codes over one day ---------------------------------------------------------------
 // _fine_fuel_moisture_code (:246-319).  Where the reference raises (mo == ew exactly) the moisture is kept.
 XC_FWI_HD double ffmc_step(float t_, float p_, float w_, float h_, float f0_) {
+  if (f0_ != f0_) return (double)NAN;   // outside the season: every path below propagates the NaN (nothing to evaluate)
   const double t = t_, p = p_, h = h_, f0 = f0_;
   const double root_w = (double)sqrtf(w_);
   double mo = (147.2 * (101.0 - f0)) / (59.5 + f0);                                   // Eq. 1
@@ -120,6 +121,7 @@ XC_FWI_HD double dmc_step(float t_, float p_, float h_, double dl, float d0_) {
 
 // _drought_code (:396-446); fl = day-length factor of the cell's band for the month.
 XC_FWI_HD double dc_step(float t_, float p_, double fl, float c0_) {
+  if (c0_ != c0_) return (double)NAN;   // outside the season (:439-440 and c0 + pe both give NaN)
   const double p = p_, c0 = c0_;
   const double t = pmax((double)t_, -2.8);
   const double pe = pmax((0.36 * (t + 2.8) + fl) / 2, 0.0);                           // Eq. 22
