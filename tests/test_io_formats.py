@@ -262,3 +262,28 @@ def test_slab_output_device_leg_and_multi_output_containers(monkeypatch):
     assert parts == [(None, fa)] and rebuild({None: 7}) == 7
     with pytest.raises(TypeError, match="cannot stream"):
         streaming._result_parts(len, 3)
+
+
+def test_non_daily_time_axes_are_labels_only(tmp_path, monkeypatch):
+    """A monthly file opens, but carries no daily TimeAxis: the hot path (which resamples daily series) refuses
+    it with a clear error instead of mis-reading the steps as days."""
+    from scipy.io import netcdf_file
+
+    import fake_device
+    from xclim_b200 import indices, io
+    fake_device.install(monkeypatch)
+    path = str(tmp_path / "monthly.nc")
+    with netcdf_file(path, "w") as nc:
+        nc.createDimension("time", None); nc.createDimension("lat", 2); nc.createDimension("lon", 3)
+        t = nc.createVariable("time", "f8", ("time",)); t[:] = np.array([15.5, 45.0, 74.5, 105.0])
+        t.units = "days since 2001-01-01"; t.calendar = "noleap"
+        v = nc.createVariable("pr", "f4", ("time", "lat", "lon")); v[:] = np.ones((4, 2, 3), np.float32); v.units = "mm/d"
+        w = nc.createVariable("orog", "f4", ("lat", "lon")); w[:] = np.zeros((2, 3), np.float32)
+    f = io.open_netcdf3(path)                      # the only variable with a time dimension
+    assert f.name == "pr" and f.time is None and list(f.coords["time"]) == [15.5, 45.0, 74.5, 105.0]
+    with pytest.raises(ValueError, match="no time axis"):
+        indices.wetdays(f)
+    with pytest.raises(KeyError):
+        io.open_netcdf3(path, "tas")
+    o = io.open_netcdf3(path, "orog")
+    assert o.dims == ("lat", "lon") and o.time is None and np.asarray(o.values).shape == (2, 3)

@@ -254,8 +254,11 @@ class _Nc3Var(LazyGrid):
 
     def __init__(self, ncfile, var):
         super().__init__(var.shape)
-        self._file = ncfile                  # keeps the mapping alive
-        self._data = var.data
+        self._data = var.data                # a view into the file's memory map (which it keeps alive)
+        # scipy's close() warns when views of the mapping outlive the file object; the views own the mapping from
+        # here on, and the file object may go quietly
+        if getattr(ncfile, "_mm_buf", None) is not None:
+            ncfile._mm_buf = None
         self._decode = _cf_decoder(dict(var._attributes), self._data.dtype)
 
     def read_rows(self, r0, r1, out=None):
@@ -263,15 +266,6 @@ class _Nc3Var(LazyGrid):
         self._decode(self._data[:, r0:r1], out)
         return out
 
-    def __del__(self):      # release the mapping quietly (scipy warns when views of it are still alive)
-        import warnings
-        try:
-            self._data = None
-            with warnings.catch_warnings():
-                warnings.simplefilter("ignore")
-                self._file.close()
-        except Exception:
-            pass
 
 
 def _str_attr(v):
