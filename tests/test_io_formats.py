@@ -287,3 +287,45 @@ def test_non_daily_time_axes_are_labels_only(tmp_path, monkeypatch):
         io.open_netcdf3(path, "tas")
     o = io.open_netcdf3(path, "orog")
     assert o.dims == ("lat", "lon") and o.time is None and np.asarray(o.values).shape == (2, 3)
+
+
+def test_parallel_rows_covers_every_row_once(monkeypatch):
+    from xclim_b200 import io
+    monkeypatch.setattr(io, "PARALLEL_MIN_BYTES", 0)
+    monkeypatch.setattr(io, "copy_threads", lambda: 5)
+    monkeypatch.setattr(io, "_copy_pool", None)
+    for n in (1, 7, 10, 11, 97, 1000):
+        hits = np.zeros(n, np.int32)
+
+        def fn(a, b):
+            hits[a:b] += 1
+        io.parallel_rows(fn, n, 1)
+        assert (hits == 1).all(), n
+    with pytest.raises(ZeroDivisionError):          # a failing range is not swallowed
+        io.parallel_rows(lambda a, b: 1 // 0, 100, 1)
+
+
+@pytest.mark.parametrize("kind", ["netcdf3", "npy"])
+def test_streamer_with_parallel_staging_copies(tmp_path, monkeypatch, kind):
+    """The staging copy of a slab split over the copy threads (time ranges) gives the same bytes."""
+    import fake_stream
+    import xclim_b200
+    from xclim_b200 import indices, io
+    fake_stream.install(monkeypatch)
+    monkeypatch.setattr(io, "PARALLEL_MIN_BYTES", 0)
+    monkeypatch.setattr(io, "copy_threads", lambda: 4)
+    monkeypatch.setattr(io, "_copy_pool", None)
+    rng = np.random.default_rng(15)
+    pr = _pr(rng, T=365 * 2, shape=(9, 16))
+    f_pr = make_field(pr, "1981-01-01", calendar="noleap", units="mm/d", dims=("time", "lat", "lon"))
+    if kind == "netcdf3":
+        lazy = io.open_field(io.save_netcdf3(str(tmp_path / "pr.nc"), f_pr, name="pr"))
+        np.testing.assert_array_equal(lazy.values.read_rows(2, 7), pr[:, 2:7])
+    else:
+        lazy = io.open_field(io.save_npy(str(tmp_path / "pr.npy"), f_pr))
+    ref = indices.maximum_consecutive_dry_days(f_pr)
+    with xclim_b200.set_options(stream_min_bytes=0, stream_slab_bytes=3 * pr.shape[0] * pr.shape[2] * 4):
+        got = indices.maximum_consecutive_dry_days(lazy)
+        got2 = indices.maximum_consecutive_dry_days(f_pr)       # a plain (pageable) numpy array is staged the same way
+    np.testing.assert_array_equal(got.values, ref.values)
+    np.testing.assert_array_equal(got2.values, ref.values)

@@ -77,6 +77,37 @@ def _plain(v) -> bool:
     return isinstance(v, (str, int, float, bool, list)) or v is None
 
 
+# ------------------------------------------------------------------------------------------------ parallel host copies
+#: host copies / decodes of at least this many bytes are split over the copy threads
+PARALLEL_MIN_BYTES = 32 << 20
+_copy_pool = None
+
+
+def copy_threads() -> int:
+    return max(1, min(16, (os.cpu_count() or 1)))
+
+
+def parallel_rows(fn, n_rows: int, nbytes: int) -> None:
+    """Run ``fn(a, b)`` over contiguous ranges ``[a, b)`` that cover ``range(n_rows)``, on the copy threads when
+    the work is large.  One thread moves a strided (time, lat-slab, lon) box at 4-6 GB/s (big-endian data:
+    byte-swapped on the way; ``tools/time_staging_copy.py``), an order of magnitude under what PCIe takes; numpy
+    releases the GIL inside the copy, so time ranges of the box can go in parallel.  (The authoring container
+    gives its threads about one core in total, so the gain is not measurable there; on the GPU box the e2e
+    figures of bench.py use page-locked inputs and bypass this path.)"""
+    global _copy_pool
+    n = copy_threads()
+    if n == 1 or nbytes < PARALLEL_MIN_BYTES or n_rows < 2 * n:
+        fn(0, n_rows)
+        return
+    if _copy_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _copy_pool = ThreadPoolExecutor(n, thread_name_prefix="xclim_b200-copy")
+    edges = np.linspace(0, n_rows, n + 1).astype(np.int64)
+    futs = [_copy_pool.submit(fn, int(a), int(b)) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+    for f in futs:
+        f.result()
+
+
 # ------------------------------------------------------------------------------------------------ lazy sources
 
 
@@ -263,7 +294,7 @@ class _Nc3Var(LazyGrid):
 
     def read_rows(self, r0, r1, out=None):
         out = self._out(r0, r1, out)
-        self._decode(self._data[:, r0:r1], out)
+        parallel_rows(lambda a, b: self._decode(self._data[a:b, r0:r1], out[a:b]), self.shape[0], out.nbytes)
         return out
 
 

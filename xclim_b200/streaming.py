@@ -131,6 +131,7 @@ def run_streamed(fn, args, kwargs, lead, shape, series, tables):
 
     from . import device
     from ._lib import check, load
+    from .io import parallel_rows
 
     device._require_cuda()
     lib = load()
@@ -171,8 +172,9 @@ def run_streamed(fn, args, kwargs, lead, shape, series, tables):
                 dst = dst.reshape((T, r1 - r0) + tuple(shape[2:]))
                 if _is_lazy(hosts[key]):
                     hosts[key].read_rows(r0, r1, out=dst)
-                else:
-                    np.copyto(dst, hosts[key][:, r0:r1])
+                else:      # strided box of pageable / memory-mapped memory: time ranges on the copy threads
+                    src = hosts[key]
+                    parallel_rows(lambda a, b, s_=src, d_=dst: np.copyto(d_[a:b], s_[a:b, r0:r1]), T, dst.nbytes)
 
     def submit_stage(k):
         if pool is not None and k < len(slabs):
