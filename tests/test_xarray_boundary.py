@@ -83,3 +83,32 @@ def test_dataarray_inputs_stream_in_slabs(cuda, monkeypatch):
     assert isinstance(out, mx.DataArray) and out.dims == ("time", "lat", "lon")
     np.testing.assert_array_equal(out.values, O.maximum_consecutive_dry_days(pr, 1.0, ta.period_offsets("YS")))
     np.testing.assert_array_equal(out.coords["lat"].values, da_p.coords["lat"].values)
+
+
+def _indexer_scenario():
+    """Indicator-level `select_time` indexers on DataArray inputs (ResamplingIndicatorWithIndexing,
+    core/indicator.py:1611-1673): DataArray in -> DataArray out, same numbers as the Field path."""
+    from xclim_b200 import atmos
+    from xb_helpers import make_field
+    tas, pr = _data()
+    da_t = mx.daily(tas - 273.15 + 4, "2001-01-01", units="degC")
+    f_t = make_field(tas - 273.15 + 4, "2001-01-01", calendar="noleap", units="degC", dims=("time", "lat", "lon"))
+    for kw in (dict(date_bounds=("09-01", "12-31")), dict(month=[1, 2, 12]), dict(season="JJA")):
+        got = atmos.frost_days(da_t, freq="YS", **kw)
+        ref = atmos.frost_days(f_t, freq="YS", **kw)
+        assert isinstance(got, mx.DataArray) and got.dims == ("time", "lat", "lon"), kw
+        np.testing.assert_array_equal(np.asarray(got.values), np.asarray(ref.values), err_msg=str(kw))
+        assert got.attrs["units"] == ref.attrs["units"]
+        np.testing.assert_array_equal(got.coords["lon"].values, da_t.coords["lon"].values)
+    da_p = mx.daily(pr, "2001-01-01", units="mm/d")
+    f_p = make_field(pr, "2001-01-01", calendar="noleap", units="mm/d", dims=("time", "lat", "lon"))
+    got = atmos.maximum_consecutive_dry_days(da_p, freq="YS", season="DJF")
+    ref = atmos.maximum_consecutive_dry_days(f_p, freq="YS", season="DJF")
+    assert isinstance(got, mx.DataArray)
+    np.testing.assert_array_equal(np.asarray(got.values), np.asarray(ref.values))
+
+
+def test_indicator_indexers_on_dataarrays(monkeypatch):
+    fake_device.install(monkeypatch)
+    mx.install(monkeypatch)
+    _indexer_scenario()

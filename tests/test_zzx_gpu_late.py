@@ -27,3 +27,12 @@ def test_spell_length_statistics_min_gap_with_window(cuda, win_reducer, op, thr,
         for g, red in zip(got, ("max", "sum", "count")):
             exp = O.spell_length_statistics(x, thr, 3, win_reducer, op, red, poff, min_gap=min_gap)
             np.testing.assert_array_equal(g.values, exp, err_msg=f"{win_reducer} {op} {red} {freq} {min_gap}")
+
+
+def test_indicator_indexers_on_dataarrays_on_device(cuda, monkeypatch):
+    """atmos.<index>(DataArray, **indexer): the masked series runs as a device Field, the result is re-labelled
+    as a DataArray (tests/mini_xarray.py stands in for xarray, absent from the image)."""
+    import mini_xarray as mx
+    from test_xarray_boundary import _indexer_scenario
+    mx.install(monkeypatch)
+    _indexer_scenario()

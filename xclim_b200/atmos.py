@@ -118,16 +118,20 @@ def with_missing_any(index_fn, name=None):
         bound.apply_defaults()
         freq = bound.arguments.get("freq")
         bad = None
+        xr_template = None
         for key, val in list(bound.arguments.items()):
             if not (isinstance(val, Field) or is_xarray(val)) or "time" not in dims_of(val):
                 continue                     # thresholds, percentile tables (dayofyear), options
             x2d, cell_shape, other, ta = _unwrap(val, indexer)
-            if indexer and not is_xarray(val):
-                bound.arguments[key] = Field(x2d.reshape((x2d.shape[0],) + cell_shape), ("time",) + other, ta,
-                                             {k: v for k, v in val.coords.items() if k != "time"}, dict(val.attrs),
-                                             val.name)
-            elif indexer:
-                raise NotImplementedError("select_time indexers on xarray inputs: pass xclim_b200.Field inputs")
+            if indexer:
+                # the masked series stays in HBM as a Field; DataArray inputs get their result re-labelled below
+                if is_xarray(val):
+                    xr_template = val if xr_template is None else xr_template
+                    coords = {d: np.asarray(val.coords[d].values) for d in other if d in val.coords}
+                else:
+                    coords = {k: v for k, v in val.coords.items() if k != "time"}
+                bound.arguments[key] = Field(x2d.reshape((x2d.shape[0],) + cell_shape), ("time",) + other, ta, coords,
+                                             dict(val.attrs), val.name)
             method = OPTIONS["check_missing"]
             if freq is None or method == "skip":
                 continue
@@ -152,6 +156,15 @@ def with_missing_any(index_fn, name=None):
                 miss = miss.to(x2d.device).reshape((len(poff) - 1,) + cell_shape).bool()
             bad = miss if bad is None else (bad | miss)
         out = index_fn(*bound.args, **bound.kwargs)
+        if xr_template is not None:          # DataArray in -> DataArray out (the index ran on masked Fields)
+            from .streaming import _assemble
+
+            def relabel(o):
+                if not isinstance(o, Field):
+                    return o
+                v = o.values
+                return _assemble(xr_template, o, v.cpu().numpy() if hasattr(v, "is_cuda") else v, None)
+            out = tuple(relabel(o) for o in out) if isinstance(out, tuple) else relabel(out)
         if bad is None:
             return out
         outs = out if isinstance(out, tuple) else (out,)
