@@ -161,3 +161,45 @@ def test_ring_mean_rounds_as_numpy_mean():
             ring[(head + 1 + np.arange(n)) % n] = vals            # oldest value right after the head
             got = lib.fwi_host_np_mean(ring.ctypes.data_as(ctypes.c_void_p), ctypes.c_int32(n), ctypes.c_int32(head))
             assert np.float32(got) == np.mean(vals), (n, head)
+
+
+@pytest.mark.skipif(not __import__("_ref_extract").available(), reason="reference sources not present (GPU box)")
+def test_branch_point_inputs_against_the_live_reference():
+    """Inputs drawn from the branch points of the equations (rain thresholds 0.5 / 1.5 / 2.8 mm and just above,
+    humidity 0 and 100 %, calm and storm winds, temperatures at -2.8 / -1.1 / 21.1 degC, snow depth at its
+    threshold, latitudes on the band edges, previous codes at 0 / 33 / 65 / 101), with and without missing
+    values: oracle and host build of the device code against the reference executed where it lies."""
+    import warnings
+
+    import _ref_extract as ref
+    fw = ref.load_cffwis()
+    rng = np.random.default_rng(7)
+    C, T = 32, 240
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)   # noqa: E731
+    for trial in range(6):
+        tas = rng.choice([-45.0, -2.8, -1.1, 0.0, 21.1, 35.0, 50.0], size=(C, T)) + rng.normal(0, 0.5, (C, T))
+        pr = rng.choice([0.0, 0.5, 0.50001, 1.5, 1.50001, 2.8, 2.80001, 50.0, 300.0], size=(C, T))
+        hurs = rng.choice([0.0, 1e-3, 5.0, 50.0, 99.999, 100.0], size=(C, T))
+        ws = rng.choice([0.0, 1e-3, 10.0, 100.0, 250.0], size=(C, T))
+        snd = rng.choice([0.0, 0.01, 0.010001, 0.5], size=(C, T))
+        if trial % 3 == 0:
+            for a in (tas, pr, hurs, ws):
+                a[rng.random((C, T)) < 0.002] = np.nan
+        mth = rng.integers(1, 13, T).astype(np.int64)
+        lat = rng.choice([-90, -30, -15, 15, 30, 90, -29.999, 14.999, 0], size=C).astype(np.float64)
+        dc0, dmc0, ffmc0, wpr = mg.cffwis_state({"tas": f32(tas)}, [None, "some", "all"][trial % 3])
+        if trial % 3:
+            dc0[:4], dmc0[:4], ffmc0[:4] = [0.0, 1e-3, 800.0, 2000.0], [0.0, 33.0, 65.0, 500.0], [0.0, 101.0, 50.0, 99.9]
+        for season, ow, dry in ((None, False, None), ("WF93", True, "CFS"), ("GFWED", False, "GFWED+SNOW"), ("LA08", True, None)):
+            outs = ["DC", "DMC", "FFMC", "ISI", "BUI", "FWI", "DSR"] + (["season_mask"] if season else []) + \
+                (["winter_pr"] if ow else [])
+            over = dict(season_method=season, overwintering=ow, dry_start=dry, snow_cover_days=10)
+            kw = mg.cffwis_params(fw, outputs=outs, **over)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                res = fw["_fire_weather_calc"](f32(tas), f32(pr), f32(hurs), f32(ws), f32(snd), mth, lat, None, dc0.copy(),
+                                               dmc0.copy(), ffmc0.copy(), wpr.copy(), **kw)
+            exp = {o: (np.asarray(a).T if np.asarray(a).ndim == 2 else np.asarray(a)) for o, a in zip(outs, res)}
+            args = tuple(f32(a.T) for a in (tas, pr, hurs, ws, snd)) + (mth, lat, None, dc0, dmc0, ffmc0, wpr)
+            check_outputs(FO.fire_weather_calc(*args, outputs=outs, **over), exp, f"oracle {trial} {season}", exact_frac=0.97)
+            check_outputs(hb.run(*args, outputs=outs, **over), exp, f"host build {trial} {season}", exact_frac=0.97)
