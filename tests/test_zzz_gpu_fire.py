@@ -137,3 +137,33 @@ def test_kernel_every_mode_combination_against_the_oracle(cuda):
         check_outputs(got, {k: np.asarray(v) for k, v in exp.items()}, f"{season},{ow},{dry},{isu}", exact_frac=0.90)
         n += 1
     assert n == 72
+
+
+def test_kernel_branch_point_inputs_against_the_oracle(cuda):
+    """The branch-point inputs of tests/test_fire_host_core.py::test_branch_point_inputs_against_the_live_reference
+    (there: oracle and host build against the reference), here the kernel against the oracle."""
+    rng = np.random.default_rng(7)
+    C, T = 32, 240
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)   # noqa: E731
+    for trial in range(6):
+        tas = rng.choice([-45.0, -2.8, -1.1, 0.0, 21.1, 35.0, 50.0], size=(C, T)) + rng.normal(0, 0.5, (C, T))
+        pr = rng.choice([0.0, 0.5, 0.50001, 1.5, 1.50001, 2.8, 2.80001, 50.0, 300.0], size=(C, T))
+        hurs = rng.choice([0.0, 1e-3, 5.0, 50.0, 99.999, 100.0], size=(C, T))
+        ws = rng.choice([0.0, 1e-3, 10.0, 100.0, 250.0], size=(C, T))
+        snd = rng.choice([0.0, 0.01, 0.010001, 0.5], size=(C, T))
+        if trial % 3 == 0:
+            for a in (tas, pr, hurs, ws):
+                a[rng.random((C, T)) < 0.002] = np.nan
+        mth = rng.integers(1, 13, T).astype(np.int64)
+        lat = rng.choice([-90, -30, -15, 15, 30, 90, -29.999, 14.999, 0], size=C).astype(np.float64)
+        dc0, dmc0, ffmc0, wpr = mg.cffwis_state({"tas": f32(tas)}, [None, "some", "all"][trial % 3])
+        if trial % 3:
+            dc0[:4], dmc0[:4], ffmc0[:4] = [0.0, 1e-3, 800.0, 2000.0], [0.0, 33.0, 65.0, 500.0], [0.0, 101.0, 50.0, 99.9]
+        for season, ow, dry in ((None, False, None), ("WF93", True, "CFS"), ("GFWED", False, "GFWED+SNOW"), ("LA08", True, None)):
+            outs = ["DC", "DMC", "FFMC", "ISI", "BUI", "FWI", "DSR"] + (["season_mask"] if season else []) + \
+                (["winter_pr"] if ow else [])
+            over = dict(season_method=season, overwintering=ow, dry_start=dry, snow_cover_days=10)
+            args = tuple(f32(a.T) for a in (tas, pr, hurs, ws, snd)) + (mth, lat, None, dc0, dmc0, ffmc0, wpr)
+            exp = FO.fire_weather_calc(*args, outputs=outs, **over)
+            got = run_on_device(args, dict(outputs=outs, **over))
+            check_outputs(got, {k: np.asarray(v) for k, v in exp.items()}, f"{trial} {season}", exact_frac=0.90)
